@@ -1,0 +1,72 @@
+"""
+Case table shared by tests/golden/make_golden.py (runs the real reference) and the parity tests
+(run the oracle and the CUDA path on the same seeded inputs).  Inputs follow SURVEY.md §6/§8(d):
+``y = default_rng(seed).standard_normal``, ``x0 = 0``, ZERO padding.
+"""
+import numpy as np
+
+ADVDIFF = dict(velocity=(1.0, 0.5, 0.25), c=0.3, nu=0.2)
+
+
+def sample_index(n: int) -> np.ndarray:
+    return np.unique(np.linspace(0, n - 1, 257).astype(np.int64))
+
+
+def rhs_for(case: dict, n: int) -> np.ndarray:
+    rng = np.random.default_rng(case.get('seed', 0))
+    nb = case.get('batch', 1)
+    y = rng.standard_normal((nb, n))
+    scale = case.get('rhs_scale')
+    if scale is not None:          # batched-tolerance quirk probe: same vector at different magnitudes
+        y = y[:1] * np.asarray(scale)[:, None]
+    if case.get('zero_rhs_row') is not None:
+        y[case['zero_rhs_row']] = 0
+    return y.astype(case['dtype'])
+
+
+def _c(op, grid, dtype, method, rtol, atol=0.0, **kw):
+    return dict(op=op, grid=grid, dtype=dtype, method=method, rtol=rtol, atol=atol, **kw)
+
+
+SOLVE_CASES = {
+    # --- BASELINE config 1: 2-D 128² ---
+    'p128_cg_f64_default': _c('poisson', (128, 128), 'float64', 'CG', 1e-12, 1e-12),
+    'p128_cg_f64_1e10': _c('poisson', (128, 128), 'float64', 'CG', 1e-10),
+    'p128_cg_f32_default': _c('poisson', (128, 128), 'float32', 'CG', 1e-5, 1e-5),
+    'p128_cg_f64_torch': _c('poisson', (128, 128), 'float64', 'CG', 1e-12, 1e-12, backend='torch'),
+    'p128_cg_f32_torch': _c('poisson', (128, 128), 'float32', 'CG', 1e-5, 1e-5, backend='torch'),
+    'p128_auto_f64': _c('poisson', (128, 128), 'float64', 'auto', 1e-10),
+    'p128_auto_f32_torch': _c('poisson', (128, 128), 'float32', 'auto', 1e-5, backend='torch'),
+    'p128_cgadaptive_f32': _c('poisson', (128, 128), 'float32', 'CG-adaptive', 1e-5),
+    'p128_bicg2_f64': _c('poisson', (128, 128), 'float64', 'biCG-stab(2)', 1e-10),
+    'p128_jacobi_f64': _c('poisson', (128, 128), 'float64', 'CG', 1e-10, pre='jacobi'),
+    'p128_ilu_f64': _c('poisson', (128, 128), 'float64', 'CG', 1e-10, pre='ilu'),
+    'p128_ilu_f32': _c('poisson', (128, 128), 'float32', 'CG', 1e-5, pre='ilu'),
+    # --- small cases with full x stored ---
+    'p16_cg_f64': _c('poisson', (16, 16), 'float64', 'CG', 1e-10, batch=2, seed=1),
+    'p16_cg_f32': _c('poisson', (16, 16), 'float32', 'CG', 1e-5, batch=2, seed=1),
+    'p8x6x5_jacobi_f32': _c('poisson', (8, 6, 5), 'float32', 'CG', 1e-5, pre='jacobi', batch=3, seed=2),
+    'p8x6x5_ilu_f64': _c('poisson', (8, 6, 5), 'float64', 'CG', 1e-10, pre='ilu', batch=2, seed=2),
+    'a8x6x5_bicg1_f64': _c('advdiff', (8, 6, 5), 'float64', 'biCG-stab(1)', 1e-10, batch=2, seed=3),
+    'a8x6x5_bicg2_f64': _c('advdiff', (8, 6, 5), 'float64', 'biCG-stab(2)', 1e-10, batch=2, seed=3),
+    'a8x6x5_bicg2_f32': _c('advdiff', (8, 6, 5), 'float32', 'biCG-stab(2)', 1e-5, batch=2, seed=3),
+    'a8x6x5_bicg3_f64': _c('advdiff', (8, 6, 5), 'float64', 'biCG-stab(3)', 1e-10, batch=2, seed=3),
+    'a8x6x5_bicg1_jacobi_f64': _c('advdiff', (8, 6, 5), 'float64', 'biCG-stab(1)', 1e-10, pre='jacobi', batch=2, seed=3),
+    # --- 3-D (configs 2 and 4 at sizes the reference finishes in seconds) ---
+    'p32c_cg_f32': _c('poisson', (32, 32, 32), 'float32', 'CG', 1e-5),
+    'p32c_jacobi_f32': _c('poisson', (32, 32, 32), 'float32', 'CG', 1e-5, pre='jacobi'),
+    'p32c_ilu_f32': _c('poisson', (32, 32, 32), 'float32', 'CG', 1e-5, pre='ilu'),
+    'p32c_ilu_f64': _c('poisson', (32, 32, 32), 'float64', 'CG', 1e-8, pre='ilu'),
+    'p64c_cg_f32': _c('poisson', (64, 64, 64), 'float32', 'CG', 1e-5),
+    'p64c_cg_f32_torch': _c('poisson', (64, 64, 64), 'float32', 'CG', 1e-5, backend='torch'),
+    # --- config 3 in miniature: shared matrix, batch of RHS, min-tolerance quirk ---
+    'p32_batch8_f32': _c('poisson', (32, 32), 'float32', 'CG', 1e-5, batch=8, seed=4),
+    'p32_quirk_f32': _c('poisson', (32, 32), 'float32', 'CG', 1e-5, rhs_scale=(1.0, 1e-3), seed=5),
+    'p32_quirk_f64_torch': _c('poisson', (32, 32), 'float64', 'CG', 1e-10, rhs_scale=(1.0, 1e-3), seed=5, backend='torch'),
+    'p32_zero_rhs_f32': _c('poisson', (32, 32), 'float32', 'CG', 1e-5, 1e-5, batch=3, seed=6, zero_rhs_row=1),
+    'p32_maxiter_f32': _c('poisson', (32, 32), 'float32', 'CG', 1e-5, batch=2, seed=7, max_iter=10),
+    # --- config 5 in miniature: nonsymmetric, BiCGstab(2) ---
+    'a24_bicg2_f32': _c('advdiff', (24, 20, 28), 'float32', 'biCG-stab(2)', 1e-5),
+    'a24_bicg2_f64': _c('advdiff', (24, 20, 28), 'float64', 'biCG-stab(2)', 1e-10),
+    'a24_bicg1_f32': _c('advdiff', (24, 20, 28), 'float32', 'biCG-stab(1)', 1e-5),
+}

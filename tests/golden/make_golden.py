@@ -1,0 +1,201 @@
+"""
+Generates tests/golden/*.npz by RUNNING THE REAL REFERENCE (PhiML 1.15.1, imported from /root/reference).
+Run in the authoring container only:   python tests/golden/make_golden.py
+The GPU box has no /root/reference; tests read the committed .npz files.
+
+Inputs are never stored: they are re-created from ``np.random.default_rng(seed)`` in the tests
+(see tests/_cases.py, which this script shares with the tests).
+"""
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))          # tests/
+sys.path.insert(0, '/root/reference')
+
+from phiml import math                                                         # noqa: E402
+from phiml.math import spatial, batch, channel, Solve, SolveTape, extrapolation  # noqa: E402
+from phiml.math._sparse import native_matrix                                   # noqa: E402
+from phiml.math._lin_trace import matrix_from_function                         # noqa: E402
+from phiml.math._optimize import factor_ilu                                    # noqa: E402
+from phiml.backend._backend import get_backend, Preconditioner                 # noqa: E402
+from phiml.backend import NUMPY                                                # noqa: E402
+
+from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF                   # noqa: E402
+
+warnings.filterwarnings('ignore')
+DIMS = 'xyz'
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def neg_laplace(x):
+    return -math.laplace(x, padding=extrapolation.ZERO)
+
+
+def advdiff(x):
+    rank = x.shape.spatial_rank
+    u = math.wrap(list(ADVDIFF['velocity'][:rank]), channel(gradient=','.join(DIMS[:rank])))
+    g = math.spatial_gradient(x, padding=extrapolation.ZERO, difference='central', stack_dim=channel(gradient=','.join(DIMS[:rank])))
+    return x + ADVDIFF['c'] * math.sum(g * u, 'gradient') - ADVDIFF['nu'] * math.laplace(x, padding=extrapolation.ZERO)
+
+
+OPERATORS = {'poisson': neg_laplace, 'advdiff': advdiff}
+
+
+def build(op: str, grid, dtype):
+    """Reference assembly → (phiml matrix tensor, scipy csr, coo index array, coo values)."""
+    with math.precision(64 if dtype == np.float64 else 32):
+        x0 = math.zeros(spatial(**{DIMS[i]: g for i, g in enumerate(grid)}))
+        coo, _ = matrix_from_function(OPERATORS[op], x0, auto_compress=False)
+        m, _ = matrix_from_function(OPERATORS[op], x0, auto_compress=True)
+        csr = native_matrix(m, NUMPY)
+        idx = coo._indices.native([coo._indices.shape.non_channel, coo._indices.shape.channel])
+        val = coo._values.numpy()
+    return m, csr, np.asarray(idx), np.asarray(val)
+
+
+class RefJacobi(Preconditioner):
+    """5-line user preconditioner the reference's generic cg() is driven with."""
+    def __init__(self, csr): self.inv = (1 / csr.diagonal()).astype(csr.dtype)
+    def apply(self, vec): return vec * self.inv
+    def apply_inv_l(self, vec): return vec * self.inv
+    def apply_inv_u(self, vec): return vec
+    def __repr__(self): return "jacobi"
+
+
+def golden_assembly(out):
+    for op, grid, full in [('poisson', (3, 4), True), ('poisson', (6, 5, 4), True), ('advdiff', (6, 5, 4), True), ('advdiff', (5, 7), True),
+                           ('poisson', (128, 128), False), ('poisson', (32, 32, 32), False), ('poisson', (64, 64, 64), False), ('advdiff', (24, 20, 28), False)]:
+        for dtype in (np.float32, np.float64):
+            m, csr, idx, val = build(op, grid, dtype)
+            key = f"asm/{op}/{'x'.join(map(str, grid))}/{np.dtype(dtype).name}"
+            assert csr.indices.dtype == np.int32 and csr.indptr.dtype == np.int32 and csr.has_sorted_indices
+            out[key + '/nnz'] = np.int64(csr.nnz)
+            out[key + '/sha_indptr'] = sha(csr.indptr)
+            out[key + '/sha_indices'] = sha(csr.indices)
+            out[key + '/sha_data'] = sha(csr.data)
+            out[key + '/sha_coo_idx'] = sha(idx.astype(np.int64))
+            out[key + '/sha_coo_val'] = sha(val)
+            if full:
+                out[key + '/indptr'] = csr.indptr
+                out[key + '/indices'] = csr.indices
+                out[key + '/data'] = csr.data
+                out[key + '/coo_idx'] = idx.astype(np.int64)
+                out[key + '/coo_val'] = val
+            print(key, csr.nnz)
+
+
+def golden_spmv(out):
+    for op, grid in [('poisson', (128, 128)), ('advdiff', (24, 20, 28))]:
+        for dtype in (np.float32, np.float64):
+            _, csr, _, _ = build(op, grid, dtype)
+            x = np.random.default_rng(7).standard_normal((3, csr.shape[0])).astype(dtype)
+            yv = NUMPY.mul_matrix_batched_vector(csr, x)
+            out[f"spmv/{op}/{'x'.join(map(str, grid))}/{np.dtype(dtype).name}"] = yv
+
+
+def golden_solves(out):
+    for name, case in SOLVE_CASES.items():
+        dtype = np.dtype(case['dtype']).type
+        m, csr, _, _ = build(case['op'], case['grid'], dtype)
+        y = rhs_for(case, csr.shape[0])
+        x0 = np.zeros_like(y)
+        nb = y.shape[0]
+        rtol = np.full(nb, case['rtol'], dtype)
+        atol = np.full(nb, case['atol'], dtype)
+        max_iter = np.full((1, nb), case.get('max_iter', 5000))
+        pre_name = case.get('pre')
+        backend = get_backend(case.get('backend', 'numpy'))
+        with math.precision(64 if dtype == np.float64 else 32):
+            if pre_name == 'ilu':
+                from phiml.math._optimize import compute_preconditioner
+                pre = compute_preconditioner('ilu', m, 0, NUMPY, case['method'])
+                out[f"solve/{name}/pre_source"] = str(pre)
+            elif pre_name == 'jacobi':
+                pre = RefJacobi(csr)
+            else:
+                pre = None
+            if backend.name == 'torch':
+                import torch
+                lin = torch.sparse_csr_tensor(torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data), csr.shape)
+                args = [torch.as_tensor(a) for a in (y, x0, rtol, atol)]
+            else:
+                lin, args = csr, [y, x0, rtol, atol]
+            with backend:
+                ret = backend.linear_solve(case['method'], lin, *args, max_iter, pre, None)
+        x = backend.numpy(ret.x)
+        res = backend.numpy(ret.residual)
+        key = f"solve/{name}"
+        out[key + '/method'] = ret.method
+        out[key + '/iterations'] = backend.numpy(ret.iterations)
+        out[key + '/function_evaluations'] = backend.numpy(ret.function_evaluations)
+        out[key + '/converged'] = backend.numpy(ret.converged)
+        out[key + '/diverged'] = backend.numpy(ret.diverged)
+        out[key + '/x_norm'] = np.linalg.norm(x.astype(np.float64), axis=1)
+        out[key + '/res_norm'] = np.linalg.norm(res.astype(np.float64), axis=1)
+        si = sample_index(x.shape[1])
+        out[key + '/x_sample'] = x[:, si]
+        if x.size <= 4096:
+            out[key + '/x'] = x
+        print(key, ret.method, out[key + '/iterations'][:8], out[key + '/function_evaluations'][:4], out[key + '/converged'][:4], out[key + '/diverged'][:4])
+
+
+def golden_ilu(out):
+    for grid, sweeps in [((5,), 10), ((8, 8), 6), ((6, 5, 4), 8), ((6, 5, 4), 40)]:
+        with math.precision(64):
+            m, csr, _, _ = build('poisson', grid, np.float64)
+            lo, up = factor_ilu(m, sweeps)
+            L = native_matrix(lo, NUMPY).tocsr()
+            U = native_matrix(up, NUMPY).tocsr()
+        L.sort_indices(); U.sort_indices()
+        key = f"ilu/{'x'.join(map(str, grid))}/s{sweeps}"
+        for nm, t in (('L', L), ('U', U)):
+            out[f"{key}/{nm}_indptr"] = t.indptr
+            out[f"{key}/{nm}_indices"] = t.indices
+            out[f"{key}/{nm}_data"] = t.data
+        rhs = np.random.default_rng(3).standard_normal((2, csr.shape[0]))
+        out[f"{key}/solve_L"] = NUMPY.solve_triangular_sparse(L, rhs, True, True)
+        out[f"{key}/solve_U"] = NUMPY.solve_triangular_sparse(U, rhs, False, False)
+        print(key, L.nnz, U.nnz)
+
+
+def golden_frontend(out):
+    """A few results through the full math.solve_linear front end (named dims, SolveTape, exceptions)."""
+    f = math.jit_compile_linear(neg_laplace)
+    for backend_name in ('numpy', 'torch'):
+        backend = get_backend(backend_name)
+        with backend, math.precision(32):
+            rng = np.random.default_rng(0)
+            y = math.tensor(rng.standard_normal((3, 16, 16)).astype(np.float32), batch('b'), spatial('x,y'))
+            x0 = math.zeros(spatial(x=16, y=16))
+            solve = Solve('CG', 1e-5, 0, x0=x0, max_iterations=1000)
+            with SolveTape() as tape:
+                x = math.solve_linear(f, y, solve)
+            info = tape[solve]
+            key = f"front/{backend_name}/cg16"
+            out[key + '/x'] = x.numpy('b,x,y')
+            out[key + '/iterations'] = info.iterations.numpy('b')
+            out[key + '/function_evaluations'] = info.function_evaluations.numpy('b')
+            out[key + '/method'] = info.method
+            print(key, info.method, out[key + '/iterations'], out[key + '/function_evaluations'])
+
+
+def main():
+    groups = {'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend}
+    only = sys.argv[1:] or list(groups)
+    for g in only:
+        out = {}
+        groups[g](out)
+        np.savez_compressed(os.path.join(HERE, f"{g}.npz"), **out)
+        print(g, "->", os.path.getsize(os.path.join(HERE, f"{g}.npz")), "bytes")
+
+
+if __name__ == '__main__':
+    main()
