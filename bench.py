@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""
+bench.py — BASELINE.json metric: CG iterations/s (and HBM GB/s as a fraction of the measured peak) of the
+Jacobi-preconditioned CG solve of the 3-D Poisson system 256^3 (7-point Laplacian, ZERO padding) in fp32.
+
+A *step* is one CG iteration (one pass of the hot loop: SpMV + fused dots, x/r update + preconditioner + dot,
+direction update, on-device convergence test) over one system.  With N ranks every rank owns an independent system
+(weak scaling, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--format stencil|csr] [--n 256]
+
+Under torchrun every rank runs this file; rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = "cg_iterations_per_second"
+UNIT = "iterations/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=400)
+    p.add_argument('--warmup', type=int, default=20)
+    p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    p.add_argument('--format', default='stencil', choices=['stencil', 'csr'])
+    p.add_argument('--n', type=int, default=256)
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--no-e2e', action='store_true')
+    return p.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def workload_config(n, fmt, n_gpus):
+    return {"workload": f"3D Poisson {n}^3 7-point Laplacian (ZERO padding), Jacobi-preconditioned CG fp32, rel_tol 1e-5",
+            "matrix": "stencil-specialised kernels (auto-detected from the CSR native)" if fmt == 'stencil' else "general CSR int32",
+            "rows": n ** 3, "nnz": 7 * n ** 3 - 6 * n ** 2, "systems_per_gpu": 1, "parallelism": f"independent systems x{n_gpus}",
+            "l2": "working set (5 vectors x %.0f MB) exceeds the 126 MB L2; no flush needed" % (n ** 3 * 4 / 1e6)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (NumPy/SciPy restatement of the reference's generic cg + SciPy CSR matvec), 1 core
+# ----------------------------------------------------------------------------------------------------------------------
+
+def cpu_poisson_csr(n, dtype=np.float32):
+    """Canonical CSR of -laplace on n^3 through Kronecker sums (identical arrays to oracle.assemble.poisson_csr, far less memory)."""
+    import scipy.sparse as sp
+    one = sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1], format='csr', dtype=np.float64)
+    eye = sp.identity(n, format='csr', dtype=np.float64)
+    a = sp.kron(sp.kron(one, eye), eye) + sp.kron(sp.kron(eye, one), eye) + sp.kron(sp.kron(eye, eye), one)
+    a = a.tocsr()
+    a.sort_indices()
+    a = a.astype(dtype)
+    a.indices = a.indices.astype(np.int32)
+    a.indptr = a.indptr.astype(np.int32)
+    return a
+
+
+class TimedTrace(list):
+    def append(self, item):
+        item['t'] = time.perf_counter()
+        super().append(item)
+
+
+def cpu_iterations_per_second(n, warmup, steps):
+    """Runs the oracle's Jacobi-CG for warmup+steps iterations on the same system; returns (it/s, description)."""
+    from oracle import krylov, precond
+    a = cpu_poisson_csr(n)
+    y = np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32)
+    trace = TimedTrace()
+    total = warmup + steps
+    krylov.cg(a, y, np.zeros_like(y), np.float32([1e-5]), np.float32([0]), np.array([[total]]), precond.Jacobi(a), trace=trace)
+    ts = [t['t'] for t in trace]
+    done = len(ts)
+    w = min(warmup, max(0, done - 2))
+    its = done - 1 - w
+    dt = ts[-1] - ts[w]
+    return its / dt, its, dt
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import phiml_b200 as pb
+    from phiml_b200 import _engine as E
+    from oracle.assemble import laplace_shifts
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    n, N = args.n, args.n ** 3
+    w = 4
+    shifts = laplace_shifts(3)
+    stencil = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [c for _, c in shifts], torch.float32, dev)
+    csr = stencil.to_csr()                  # the native the torch backend would hold (device-side assembly, bit-exact)
+    native = torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape)
+    if args.format == 'stencil':
+        matrix = pb.as_matrix(native)       # recognised as a stencil on the device
+        assert matrix.stencil is not None, "stencil recognition failed"
+        solver_matrix = matrix.stencil
+    else:
+        matrix = pb.as_matrix(native, detect_stencil=False)
+        solver_matrix = matrix
+    pre = pb.JacobiPreconditioner(matrix)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    y = torch.randn((1, N), dtype=torch.float32, device=dev, generator=gen)
+    x0 = torch.zeros_like(y)
+    zero = torch.zeros(1, dtype=torch.float32, device=dev)
+    mi = torch.full((1,), 2 ** 30, dtype=torch.int32, device=dev)
+
+    # ---- device-resident throughput: K iterations with the convergence test executed but never satisfied (rtol=atol=0)
+    solver = pb.DeviceSolver(solver_matrix, pre, E.CG, 0, 1)
+    solver.start(y, x0, zero, zero, mi)
+    solver.advance(args.warmup)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = pb.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        solver.advance(args.steps)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches = pb.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    its_done = int(solver.result()[0][0])
+    assert its_done == args.warmup + args.steps, f"device executed {its_done} iterations, expected {args.warmup + args.steps}"
+    assert solver.any_continue()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launch stream) for the roofline line
+    solver.profile(True)
+    solver.advance(60)
+    prof = solver.profile_read()
+    solver.profile(False)
+    names = ["spmv+dot (q=A d, d.q, alpha)", "update (x,r, M^-1 r, r.s, beta, convergence test)", "direction (d = M^-1 r + beta d)"]
+    model_bytes = [2 * N * w, 7 * N * w, 4 * N * w] if args.format == 'stencil' else [8 * csr.values.numel() + 4 * (N + 1) + 2 * N * w, 7 * N * w, 4 * N * w]
+    peak, peak_src = measured_peak()
+    kernels = []
+    for k, (tot_ms, cnt) in enumerate(prof[:3]):
+        avg = tot_ms / max(cnt, 1)
+        kernels.append({"kernel": names[k], "avg_ms": avg, "bytes": model_bytes[k], "gbs": model_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else None})
+    dom = max(range(len(kernels)), key=lambda k: kernels[k]['avg_ms']) if kernels else None
+    roofline = None
+    if dom is not None:
+        kd = kernels[dom]
+        roofline = {"bound": "hbm", "kernel": kd['kernel'], "achieved": kd['gbs'], "peak": peak, "unit": "GB/s", "frac": kd['gbs'] / peak,
+                    "traffic": None, "peak_source": peak_src, "share_of_step": kd['avg_ms'] / sum(k_['avg_ms'] for k_ in kernels),
+                    "kernels": kernels}
+    iter_bytes = sum(model_bytes)
+    iteration = {"model_bytes": iter_bytes, "achieved_gbs": iter_bytes * (args.steps / (ms * 1e-3)) / 1e9,
+                 "frac_of_peak": iter_bytes * (args.steps / (ms * 1e-3)) / 1e9 / peak}
+
+    # ---- end to end through the Backend-level call: pinned host y/x0 -> device, solve to rel_tol 1e-5, x -> host
+    e2e = None
+    if not args.no_e2e:
+        y_host = torch.empty((1, N), dtype=torch.float32).pin_memory()
+        y_host.copy_(torch.as_tensor(np.random.default_rng(0).standard_normal((1, N)).astype(np.float32)))
+        x0_host = torch.zeros((1, N), dtype=torch.float32).pin_memory()
+        x_host = torch.empty((1, N), dtype=torch.float32).pin_memory()
+        backend = pb.B200Backend(dev)
+        e2e_its, e2e_s = 0, 0.0
+        for rep in range(3):
+            pb.clear_cache()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            yd = y_host.to(dev, non_blocking=True)
+            x0d = x0_host.to(dev, non_blocking=True)
+            m = pb.as_matrix(native, detect_stencil=(args.format == 'stencil'))
+            p = backend.compute_preconditioner('jacobi', m)
+            res = backend.linear_solve('CG', m, yd, x0d, [1e-5], [0.0], np.array([[5000]]), p, None)
+            x_host.copy_(res.x, non_blocking=True)
+            its = int(res.iterations.cpu()[0])
+            conv = bool(res.converged.cpu()[0])
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            assert conv, "e2e solve did not converge"
+            if rep > 0:
+                e2e_its += its
+                e2e_s += dt
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+        e2e = {"value": world * e2e_its / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * N * w, "d2h_bytes_per_step": N * w + 6,
+               "iterations_per_solve": e2e_its // 2, "seconds_per_solve": e2e_s / 2,
+               "call": "B200Backend.linear_solve('CG', csr_native, y, x0, rtol, atol, max_iter, jacobi) incl. stencil recognition + Jacobi set-up; matrix native resident on the device"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, its, dt = cpu_iterations_per_second(n, 3, 30)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{its} Jacobi-CG iterations of the same {n}^3 fp32 system with the oracle (NumPy ufuncs + SciPy csr_matvec, single-threaded like the reference's NumPy backend), {dt:.1f} s"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": workload_config(n, args.format, world), "clocks": clocks.summary(), "e2e": e2e,
+               "gpu_launches": launches, "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "impl": "phb200"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port: NumPy/SciPy, like its NumPy backend) on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = min(args.steps, 40)
+    warm = min(args.warmup, 5)
+    t0 = time.perf_counter()
+    v, its, dt = cpu_iterations_per_second(args.n, warm, steps)
+    out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": its, "warmup": warm, "ms_per_step": dt / its * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args.n, 'csr', args.gpus), "impl": "reference",
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"{its} timed Jacobi-CG iterations ({warm} warm-up) of the {args.n}^3 fp32 system, oracle port of phiml/backend/_linalg.py:52-90 on SciPy CSR; "
+                                      f"NumPy ufuncs and SciPy csr_matvec are single-threaded, so 1 core is all the path can use; whole run {time.perf_counter() - t0:.0f} s"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

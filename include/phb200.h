@@ -1,0 +1,180 @@
+/*
+ * phb200 — B200-native (sm_100a) sparse linear-solve path for PhiML's torch backend.  C ABI.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain device pointers, sizes and a
+ * cudaStream_t (as void*); no torch types.  All functions return 0 on success or a negative PHB200_ERR_* code
+ * (message via phb200_last_error()); they never throw and never allocate user-visible memory: vectors and
+ * factor storage are supplied by the caller after a *_bytes query.  Opaque handles own only small internal
+ * bookkeeping (reduction scratch, per-system scalars, level tables).
+ *
+ * Reference interfaces replaced (paths relative to the PhiML 1.15.1 tree):
+ *   phb200_spmv / phb200_spmv_coo      Backend.mul_matrix_batched_vector  phiml/backend/torch/_torch_backend.py:541-547
+ *                                      Backend.mul_csr_dense              phiml/backend/torch/_torch_backend.py:912-922
+ *                                      Backend.mul_coo_dense              phiml/backend/_backend.py:1303-1328
+ *   phb200_matrix_csr                  TorchBackend.csr_matrix/csc_matrix phiml/backend/torch/_torch_backend.py:869-896
+ *   phb200_stencil_* / _assemble_*     tracer_to_coo + compress           phiml/math/_lin_trace.py:750-807, phiml/math/_sparse.py:347-390
+ *   phb200_solver_* (PHB200_CG)        cg + stop_on_l2                    phiml/backend/_linalg.py:23-90
+ *                 (PHB200_CG_ADAPTIVE) cg_adaptive                        phiml/backend/_linalg.py:93-128
+ *                 (PHB200_CG_TORCH, PHB200_CG_ADAPTIVE_TORCH)
+ *                                      torch_sparse_cg(_adaptive)         phiml/backend/torch/_torch_backend.py:932-963,1353-1413
+ *                 (PHB200_BICGSTAB)    bicg / bicg_stab_first_order       phiml/backend/_linalg.py:131-274
+ *                                      Backend.while_loop (device-side)   phiml/backend/_backend.py:697-735
+ *   phb200_jacobi_setup                NEW ('jacobi' is absent from compute_preconditioner, phiml/math/_optimize.py:836-880)
+ *   phb200_ilu0_*                      incomplete_lu_coo (its fixed point)phiml/backend/_linalg.py:524-594
+ *   phb200_sptrsv                      Backend.solve_triangular_sparse    phiml/backend/_backend.py:1580-1586, _numpy_backend.py:579-580
+ */
+#ifndef PHB200_H
+#define PHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHB200_VERSION 100
+
+/* arithmetic type of values and vectors */
+#define PHB200_F32 0
+#define PHB200_F64 1
+
+/* status codes */
+#define PHB200_OK 0
+#define PHB200_ERR_ARG (-1)
+#define PHB200_ERR_CUDA (-2)
+#define PHB200_ERR_UNSUPPORTED (-3)
+#define PHB200_ERR_WORKSPACE (-4)
+#define PHB200_ERR_NOT_STENCIL (-5)
+
+/* solver methods (Backend.linear_solve method strings -> codes, phiml/backend/_backend.py:1499-1516) */
+#define PHB200_CG 0                /* 'CG' generic loop (_linalg.cg), any preconditioner                     */
+#define PHB200_CG_ADAPTIVE 1       /* 'CG-adaptive' / 'auto' generic loop (_linalg.cg_adaptive)              */
+#define PHB200_CG_TORCH 2          /* 'CG' torch fast path: |y|^2 tolerance, refresh every 20, div>100      */
+#define PHB200_CG_ADAPTIVE_TORCH 3 /* 'auto' torch fast path                                                  */
+#define PHB200_BICGSTAB 4          /* 'biCG-stab(L)', poly_order = L >= 1                                     */
+
+/* preconditioner kinds */
+#define PHB200_PRE_NONE 0
+#define PHB200_PRE_JACOBI 1
+#define PHB200_PRE_ILU 2
+
+/* matrix kinds */
+#define PHB200_MAT_CSR 0
+#define PHB200_MAT_STENCIL 1
+
+typedef struct phb200_matrix phb200_matrix;
+typedef struct phb200_precond phb200_precond;
+typedef struct phb200_solver phb200_solver;
+
+int phb200_version(void);
+const char* phb200_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches evidence) */
+int64_t phb200_launch_count(void);
+
+/* ---------------------------------------------------------------- matrices ------------------------------- */
+
+/* Non-owning CSR view (int32 row pointers / column indices as produced by SparseCoordinateTensor.compress).
+ * `transposed != 0` declares that the arrays describe A^T, i.e. a CSC native of A (backward pass,
+ * phiml/math/_optimize.py:824-833); products then scatter instead of gather. */
+int phb200_matrix_csr(phb200_matrix** out, const int32_t* rowptr, const int32_t* col, const void* val,
+                      int64_t n_rows, int64_t n_cols, int64_t nnz, int dtype, int transposed);
+
+/* Constant-coefficient stencil on a C-ordered grid (rank 1..3, slowest dim first) with ZERO boundaries
+ * (out-of-domain neighbours dropped) — what matrix_from_function emits for laplace / central differences.
+ * offsets: npts*rank ints (source = output + offset), coeffs: npts doubles (rounded to dtype). npts <= 16. */
+int phb200_matrix_stencil(phb200_matrix** out, int rank, const int64_t* grid, int npts,
+                          const int32_t* offsets, const double* coeffs, int dtype);
+
+/* Device-side check whether a CSR matrix is exactly such a stencil on `grid` (columns AND values bit-equal for
+ * every row).  On success *out is a new stencil handle; PHB200_ERR_NOT_STENCIL otherwise. Synchronises stream. */
+int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int rank, const int64_t* grid, void* stream);
+
+/* Stencil -> canonical CSR on the device (sorted columns, int32), byte-identical to the reference's compress().
+ * phb200_stencil_nnz gives the array sizes. */
+int phb200_stencil_nnz(const phb200_matrix* stencil, int64_t* nnz);
+int phb200_stencil_to_csr(const phb200_matrix* stencil, int32_t* rowptr, int32_t* col, void* val, void* stream);
+
+int phb200_matrix_info(const phb200_matrix* m, int* kind, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, int* dtype);
+int phb200_matrix_destroy(phb200_matrix* m);
+
+/* ---------------------------------------------------------------- products ------------------------------- */
+
+/* Y[b,:] = A X[b,:] for b < batch; X (batch, ldx>=n_cols), Y (batch, ldy>=n_rows), row-major. */
+int phb200_spmv(const phb200_matrix* A, const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, void* stream);
+
+/* COO product with int64 indices as torch stores them (sparse_coo_tensor, _torch_backend.py:857-867);
+ * Y must be zero-filled by the caller; accumulation by atomics (order not deterministic). */
+int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int64_t nnz, int64_t n_rows, int64_t n_cols,
+                    const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, int dtype, void* stream);
+
+/* ------------------------------------------------------------- preconditioners --------------------------- */
+
+/* inv_diag[i] = 1 / A[i,i]  (caller-owned, n_rows elements of A's dtype). */
+int phb200_jacobi_setup(const phb200_matrix* A, void* inv_diag, void* stream);
+int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n, int dtype);
+
+/* Exact ILU(0) on the pattern of a CSR matrix with sorted columns and a full diagonal.
+ * lu_val (nnz elements, caller-owned) receives L (strict lower, unit diagonal implied) and U (upper incl. diagonal)
+ * in A's own pattern.  The handle keeps the dependency-level schedule used by factorisation and both solves. */
+int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, void* stream);
+/* number of dependency levels of the lower / upper solve (diagnostics) */
+int phb200_precond_levels(const phb200_precond* p, int64_t* lower_levels, int64_t* upper_levels);
+
+/* Generic sparse triangular solve X = T^-1 B, T given as CSR with sorted columns (diagonal stored; ignored when
+ * unit_diagonal).  B, X (batch, ld) row-major; X may alias B.  Builds the level schedule on every call unless a
+ * `plan` from phb200_sptrsv_plan is passed. */
+typedef struct phb200_trsv_plan phb200_trsv_plan;
+int phb200_sptrsv_plan(phb200_trsv_plan** out, const phb200_matrix* T, int lower, void* stream);
+int phb200_sptrsv(const phb200_matrix* T, const phb200_trsv_plan* plan, int lower, int unit_diagonal,
+                  const void* B, void* X, int64_t batch, int64_t ld, void* stream);
+int phb200_sptrsv_plan_destroy(phb200_trsv_plan* p);
+
+/* apply M^-1 to (batch, ld) vectors: out = M^-1 in */
+int phb200_precond_apply(const phb200_precond* p, const void* in, void* out, int64_t batch, int64_t ld, void* stream);
+int phb200_precond_destroy(phb200_precond* p);
+
+/* ---------------------------------------------------------------- solver --------------------------------- */
+
+/* A solver object is one batched solve in flight: `batch` independent right-hand sides sharing one matrix.
+ * Life cycle:  create -> workspace_bytes -> start -> (advance | run)* -> result -> destroy.
+ * X and R given to start() ARE the live iterate and residual (SolveResult.x / .residual); they are valid after
+ * any advance()/run() has completed on the stream. */
+int phb200_solver_create(phb200_solver** out, const phb200_matrix* A, const phb200_precond* M /* may be NULL */,
+                         int method, int poly_order, int64_t batch);
+size_t phb200_solver_workspace_bytes(const phb200_solver* s);
+
+/* Y, X0: (batch, n) row-major (not modified).  X, R: (batch, n) outputs.  rtol, atol: device arrays (batch,) of the
+ * matrix dtype.  max_iter: device int32 (batch,).  Enqueues the initial residual, tolerance (minimum over the batch —
+ * the (batch,batch) broadcast of stop_on_l2, phiml/backend/_linalg.py:26-29) and first progress check. */
+int phb200_solver_start(phb200_solver* s, const void* Y, const void* X0, void* X, void* R,
+                        const void* rtol, const void* atol, const int32_t* max_iter,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Enqueue up to n_iter further iterations (asynchronous; iterations after all systems finished are skipped on
+ * the device). */
+int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream);
+
+/* Run until no system continues or iteration_cap loop passes were made; polls a pinned flag every few
+ * iterations, never once per iteration.  Synchronises the stream before returning. */
+int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream);
+
+/* *any_continue = 1 while at least one system is still iterating.  Synchronises the stream. */
+int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream);
+
+/* Device outputs, (batch,) each: iterations, function_evaluations int32; converged, diverged uint8. */
+int phb200_solver_result(phb200_solver* s, int32_t* iterations, int32_t* function_evaluations,
+                         uint8_t* converged, uint8_t* diverged, void* stream);
+/* loop passes executed so far (host counter), kernels launched by this solver */
+int phb200_solver_stats(const phb200_solver* s, int64_t* passes_enqueued, int64_t* launches);
+/* Optional per-kernel timing: while enabled, the k-th kernel of every pass is bracketed by CUDA events on the launch
+ * stream; profile_read() sums the elapsed milliseconds per position k (and clears the record).  Measurement aid for
+ * bench.py's roofline line; leave disabled otherwise. */
+int phb200_solver_profile(phb200_solver* s, int enable);
+int phb200_solver_profile_read(phb200_solver* s, double* ms_per_slot, int64_t* count_per_slot, int max_slots, int* n_slots);
+int phb200_solver_destroy(phb200_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHB200_H */

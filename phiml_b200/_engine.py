@@ -1,0 +1,134 @@
+"""
+ctypes binding of libphb200.so (C ABI declared in include/phb200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, an exception is raised.
+Build the library with ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C phiml_b200/csrc``.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libphb200.so')
+
+F32, F64 = 0, 1
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_NOT_STENCIL = 0, -1, -2, -3, -4, -5
+CG, CG_ADAPTIVE, CG_TORCH, CG_ADAPTIVE_TORCH, BICGSTAB = 0, 1, 2, 3, 4
+PRE_NONE, PRE_JACOBI, PRE_ILU = 0, 1, 2
+MAT_CSR, MAT_STENCIL = 0, 1
+
+_P = c_void_p
+_PP = POINTER(c_void_p)
+
+# name -> (restype, argtypes); must list every function of include/phb200.h (tests/test_abi.py checks it)
+SIGNATURES = {
+    'phb200_version': (c_int, []),
+    'phb200_last_error': (c_char_p, []),
+    'phb200_launch_count': (c_int64, []),
+    'phb200_matrix_csr': (c_int, [_PP, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int]),
+    'phb200_matrix_stencil': (c_int, [_PP, c_int, POINTER(c_int64), c_int, POINTER(c_int32), POINTER(c_double), c_int]),
+    'phb200_stencil_from_csr': (c_int, [_PP, _P, c_int, POINTER(c_int64), _P]),
+    'phb200_stencil_nnz': (c_int, [_P, POINTER(c_int64)]),
+    'phb200_stencil_to_csr': (c_int, [_P, _P, _P, _P, _P]),
+    'phb200_matrix_info': (c_int, [_P, POINTER(c_int), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
+    'phb200_matrix_destroy': (c_int, [_P]),
+    'phb200_spmv': (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P]),
+    'phb200_spmv_coo': (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int, _P]),
+    'phb200_jacobi_setup': (c_int, [_P, _P, _P]),
+    'phb200_precond_jacobi': (c_int, [_PP, _P, c_int64, c_int]),
+    'phb200_precond_ilu0': (c_int, [_PP, _P, _P, _P]),
+    'phb200_precond_levels': (c_int, [_P, POINTER(c_int64), POINTER(c_int64)]),
+    'phb200_sptrsv_plan': (c_int, [_PP, _P, c_int, _P]),
+    'phb200_sptrsv': (c_int, [_P, _P, c_int, c_int, _P, _P, c_int64, c_int64, _P]),
+    'phb200_sptrsv_plan_destroy': (c_int, [_P]),
+    'phb200_precond_apply': (c_int, [_P, _P, _P, c_int64, c_int64, _P]),
+    'phb200_precond_destroy': (c_int, [_P]),
+    'phb200_solver_create': (c_int, [_PP, _P, _P, c_int, c_int, c_int64]),
+    'phb200_solver_workspace_bytes': (c_size_t, [_P]),
+    'phb200_solver_start': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'phb200_solver_advance': (c_int, [_P, c_int, _P]),
+    'phb200_solver_run': (c_int, [_P, c_int64, _P]),
+    'phb200_solver_poll': (c_int, [_P, POINTER(c_int), _P]),
+    'phb200_solver_result': (c_int, [_P, _P, _P, _P, _P, _P]),
+    'phb200_solver_stats': (c_int, [_P, POINTER(c_int64), POINTER(c_int64)]),
+    'phb200_solver_profile': (c_int, [_P, c_int]),
+    'phb200_solver_profile_read': (c_int, [_P, POINTER(c_double), POINTER(c_int64), c_int, POINTER(c_int)]),
+    'phb200_solver_destroy': (c_int, [_P]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class NotAStencil(Exception):
+    pass
+
+
+def load(path: str = None) -> ctypes.CDLL:
+    """Loads libphb200.so and declares all prototypes.  Raises (never falls back) if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError(f"{path} not found. The CUDA extension is required (no CPU fallback); build it with "
+                          f"`make -C phiml_b200/csrc` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.phb200_version() < 100:
+        raise EngineError("libphb200.so is older than this package; rebuild")
+    _lib = lib
+    return lib
+
+
+def lib() -> ctypes.CDLL:
+    return _lib if _lib is not None else load()
+
+
+def check(rc: int):
+    if rc == OK:
+        return
+    msg = lib().phb200_last_error().decode('utf-8', 'replace')
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == ERR_NOT_STENCIL:
+        raise NotAStencil(msg)
+    if rc == ERR_WORKSPACE:
+        raise MemoryError(msg)
+    raise EngineError(f"phb200 error {rc}: {msg}")
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    if torch_dtype == torch.float32:
+        return F32
+    if torch_dtype == torch.float64:
+        return F64
+    raise TypeError(f"phb200 computes in float32 or float64, got {torch_dtype}")
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def stream_ptr(device=None) -> c_void_p:
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise EngineError("phb200 operates on CUDA tensors only (there is no CPU fallback); got a tensor on " + str(t.device))
+
+
+def launch_count() -> int:
+    return int(lib().phb200_launch_count())

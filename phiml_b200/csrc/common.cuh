@@ -1,0 +1,220 @@
+// phb200 internal helpers: error handling, per-system scalar records, deterministic fused reductions.
+// sm_100a only.  See include/phb200.h for the public C ABI and DESIGN.md for the kernel inventory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include "../../include/phb200.h"
+
+namespace phb {
+
+// ------------------------------------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define PHB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            phb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PHB200_ERR_CUDA;                                                             \
+        }                                                                                       \
+    } while (0)
+
+#define PHB_ARG(cond, ...)                                                                      \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            phb::set_error(__VA_ARGS__);                                                        \
+            return PHB200_ERR_ARG;                                                              \
+        }                                                                                       \
+    } while (0)
+
+#define PHB_TRY(expr)                                                                           \
+    do {                                                                                        \
+        int _r = (expr);                                                                        \
+        if (_r != PHB200_OK) return _r;                                                         \
+    } while (0)
+
+// launch + count + check
+#define PHB_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
+    do {                                                                                        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                             \
+        phb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t _e = cudaPeekAtLastError();                                                 \
+        if (_e != cudaSuccess) {                                                                \
+            phb::set_error("launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PHB200_ERR_CUDA;                                                             \
+        }                                                                                       \
+    } while (0)
+
+constexpr int kSMs = 148;          // B200
+constexpr int kBlock = 256;        // threads per CTA for all streaming kernels
+constexpr int kMaxDots = 4;        // fused dot products per kernel
+constexpr int kMaxStencil = 16;
+constexpr int kTargetCtas = kSMs * 8;   // upper bound on CTAs of one grid-stride launch (sizes the reduction scratch)
+
+// ------------------------------------------------------------------------------------------------ records
+
+// One record per system (batch entry).  Scalars are kept as doubles that hold values already rounded to the
+// arithmetic type T where the reference computes them in T.
+struct Sys {
+    double s[40];      // algorithm-specific scalar slots (alpha, beta, delta, rho, omega, tau[], sigma[], gamma[] ...)
+    double tol;        // this system's squared tolerance before the batch minimum
+    double rsq0;       // first monitored value seen by the progress check
+    double rsq;        // monitored value of the current pass (|r|^2 or r.M^-1 r)
+    int its, fev, go, conv, div, max_iter, pad0, pad1;
+};
+
+struct Glob {
+    double tol_min;    // minimum squared tolerance over the batch (the (batch,batch) broadcast of stop_on_l2)
+    int any_go;        // 1 while at least one system iterates
+    int checks;        // progress checks performed so far (0 -> first check semantics)
+    int pass;          // loop passes executed (torch fast path: true-residual refresh every 20th pass)
+    int refresh;       // 1 if this pass refreshes the residual
+    unsigned ticket;   // global "last block" counter
+    int pad[3];
+};
+
+struct Reduce {
+    double* partials;      // [batch][max_blocks][kMaxDots]
+    unsigned* tickets;     // [batch]
+    int max_blocks;
+};
+
+// ------------------------------------------------------------------------------------------------ device helpers
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename T> __device__ __forceinline__ T safe_div(T a, T b) { return b == T(0) ? T(0) : a / b; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum `ND` per-thread accumulators over the CTA; result valid in thread 0.  `sh` needs ND*8 doubles (256 threads).
+template <int ND>
+__device__ __forceinline__ void block_sum(double (&acc)[ND], double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        double v = warp_sum(acc[d]);
+        if (lane == 0) sh[d * 8 + warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double v = lane < (int)(blockDim.x >> 5) ? sh[d * 8 + lane] : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) acc[d] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// Deterministic cross-CTA reduction for system `b`.  Thread 0 of every CTA holds that CTA's sums in `tot`; every CTA
+// deposits them, the CTA that draws the last ticket adds all partials in a fixed order.  Returns true (in every
+// thread of that CTA) for the last CTA; `tot` then holds the totals in thread 0.  Tickets reset themselves, so
+// back-to-back kernels on one stream can share `red`.  nbx == 1 needs neither scratch nor tickets.
+template <int ND>
+__device__ __forceinline__ bool system_reduce(double (&tot)[ND], const Reduce& red, int b, int bx, int nbx) {
+    if (nbx == 1) return true;
+    __shared__ double sh[kMaxDots * 8];
+    __shared__ int s_last;
+    double* mine = red.partials + ((size_t)b * red.max_blocks) * kMaxDots;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) mine[(size_t)bx * kMaxDots + d] = tot[d];
+        __threadfence();
+        unsigned t = atomicAdd(&red.tickets[b], 1u);
+        s_last = (t == (unsigned)nbx - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    double part[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) part[d] = 0.0;
+    for (int i = threadIdx.x; i < nbx; i += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) part[d] += __ldcg(&mine[(size_t)i * kMaxDots + d]);
+    }
+    block_sum<ND>(part, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) tot[d] = part[d];
+        red.tickets[b] = 0u;
+    }
+    return true;
+}
+
+// Per-thread accumulators -> CTA sum -> system_reduce.
+template <int ND>
+__device__ __forceinline__ bool reduce_system(double (&acc)[ND], const Reduce& red, int b, int bx, int nbx) {
+    __shared__ double sh[kMaxDots * 8];
+    block_sum<ND>(acc, sh);
+    return system_reduce<ND>(acc, red, b, bx, nbx);
+}
+
+// After the per-system finaliser ran in thread 0 of a system's last CTA: draw the global ticket.  Returns true in
+// every thread of the one CTA that finished last over the whole batch.
+__device__ __forceinline__ bool last_of_batch(Glob* g, int batch) {
+    __shared__ int s_glast;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned t = atomicAdd(&g->ticket, 1u);
+        s_glast = (t == (unsigned)batch - 1u);
+        if (s_glast) g->ticket = 0u;
+    }
+    __syncthreads();
+    if (s_glast) __threadfence();
+    return s_glast != 0;
+}
+
+// Progress check of stop_on_l2 (phiml/backend/_linalg.py:23-40) for every system; run by ALL threads of one CTA.
+// torch_rules: torch_sparse_cg's variant (threshold 100, no non-finite test inside the loop).
+template <typename T>
+__device__ __forceinline__ void progress_check(Sys* sys, Glob* g, int batch, bool torch_rules, bool freeze_finished) {
+    const bool first = g->checks == 0;
+    const T tol = (T)g->tol_min;
+    int any = 0;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        volatile Sys* s = sys + b;
+        if (freeze_finished && !first && !s->go) continue;   // finished systems are frozen: same inputs, same flags
+        T rsq = (T)fabs(s->rsq);
+        bool conv = rsq <= tol;
+        bool nonfin = !isfinite(rsq);
+        bool div;
+        if (first) {
+            s->rsq0 = (double)rsq;
+            div = nonfin;
+        } else {
+            T ratio = rsq / (T)s->rsq0;
+            if (torch_rules) div = (ratio > T(100)) && s->its >= 8;
+            else div = ((ratio > T(1e5)) && s->its >= 8) || nonfin;
+        }
+        int go = (!conv && !div && s->its < s->max_iter) ? 1 : 0;
+        s->conv = conv;
+        s->div = div;
+        s->go = go;
+        any |= go;
+    }
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) {
+        g->any_go = any;
+        g->checks = g->checks + 1;
+        __threadfence();
+    }
+}
+
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+}  // namespace phb

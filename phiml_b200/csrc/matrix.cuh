@@ -1,0 +1,67 @@
+// Matrix views and the SpMV device code shared by phb200_spmv and the fused Krylov kernels.
+#pragma once
+#include "common.cuh"
+
+namespace phb {
+
+struct CsrView {
+    const int32_t* rowptr;
+    const int32_t* col;
+    const void* val;
+    int64_t n_rows, n_cols, nnz;
+};
+
+// Constant-coefficient stencil with ZERO boundaries on a C-ordered grid (dims[0] slowest).  Points are sorted by
+// flattened offset so that a row accumulates in the same order as the canonical (sorted-column) CSR row does.
+struct StencilDesc {
+    int rank, npts;
+    int64_t dims[3];        // padded with leading 1s: always (nx, ny, nz)
+    int off[kMaxStencil][3];
+    double coef[kMaxStencil];
+    int diag;               // index of the (0,0,0) point or -1
+};
+
+}  // namespace phb
+
+struct phb200_matrix {
+    int kind;               // PHB200_MAT_*
+    int dtype;
+    int transposed;         // CSR arrays describe A^T
+    phb::CsrView csr;
+    phb::StencilDesc st;
+    // lazily computed CSR analysis
+    mutable int analysed;
+    mutable int64_t max_block_nnz;   // max entries of any 256-row block
+    int64_t n_rows, n_cols, nnz;
+};
+
+namespace phb {
+
+constexpr int kCsrRows = 256;      // rows per CTA in the streaming CSR kernel
+constexpr int kCsrCap = 2048;      // matrix entries staged per CTA (avg <= 8 per row)
+
+int csr_analyse(const phb200_matrix* m, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------- stencil row
+// y_i = sum_p coef[p] * x[i + off[p]] over in-domain neighbours, accumulated in ascending column order with
+// separately rounded products (matches scipy's csr_matvec: sum += a*x without contraction).
+template <typename T, bool PRESCALE>
+__device__ __forceinline__ T stencil_row(const StencilDesc& st, const T* __restrict__ x, const T* __restrict__ scale,
+                                         int64_t ix, int64_t iy, int64_t iz, int64_t i) {
+    T sum = T(0);
+    const int64_t ny = st.dims[1], nz = st.dims[2];
+#pragma unroll 1
+    for (int p = 0; p < st.npts; ++p) {
+        int64_t jx = ix + st.off[p][0], jy = iy + st.off[p][1], jz = iz + st.off[p][2];
+        if (jx < 0 || jx >= st.dims[0] || jy < 0 || jy >= ny || jz < 0 || jz >= nz) continue;
+        int64_t j = (jx * ny + jy) * nz + jz;
+        T xv = x[j];
+        if (PRESCALE) xv = xv * scale[j];
+        T prod = (T)st.coef[p] * xv;
+        sum = sum + prod;
+    }
+    (void)i;
+    return sum;
+}
+
+}  // namespace phb

@@ -1,0 +1,366 @@
+// Preconditioners: Jacobi set-up, exact ILU(0) with a level schedule, level-scheduled sparse triangular solves.
+#include "phase.cuh"
+#include "precond.cuh"
+#include <vector>
+#include <stdlib.h>
+
+namespace phb {
+
+// ---------------------------------------------------------------------------------------------- Jacobi
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_jacobi_csr(CsrView A, T* __restrict__ inv_diag, int* missing) {
+    const T* __restrict__ val = (const T*)A.val;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock) {
+        T d = T(0);
+        bool found = false;
+        for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+            if (A.col[k] == (int32_t)i) { d = d + val[k]; found = true; }
+        if (!found) *missing = 1;
+        inv_diag[i] = T(1) / d;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_jacobi_const(T* __restrict__ inv_diag, int64_t n, T value) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) inv_diag[i] = value;
+}
+
+// ---------------------------------------------------------------------------------------------- level schedule
+// level(i) = 1 + max level of the rows i depends on (columns < i for a lower, > i for an upper solve).  Rows of one
+// level are independent.  The analysis runs once per matrix on the host (O(nnz)), the schedule lives on the device.
+static int build_plan(phb200_trsv_plan** out, const CsrView& A, int lower, cudaStream_t stream) {
+    const int64_t n = A.n_rows;
+    std::vector<int32_t> rowptr(n + 1), col((size_t)A.nnz);
+    PHB_CUDA(cudaMemcpyAsync(rowptr.data(), A.rowptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, stream));
+    if (A.nnz) PHB_CUDA(cudaMemcpyAsync(col.data(), A.col, sizeof(int32_t) * A.nnz, cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int32_t> level(n, 0);
+    int32_t n_levels = 0;
+    if (lower) {
+        for (int64_t i = 0; i < n; ++i) {
+            int32_t l = 0;
+            for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+                if (col[k] < i && level[col[k]] + 1 > l) l = level[col[k]] + 1;
+            level[i] = l;
+            if (l + 1 > n_levels) n_levels = l + 1;
+        }
+    } else {
+        for (int64_t i = n - 1; i >= 0; --i) {
+            int32_t l = 0;
+            for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k)
+                if (col[k] > i && level[col[k]] + 1 > l) l = level[col[k]] + 1;
+            level[i] = l;
+            if (l + 1 > n_levels) n_levels = l + 1;
+        }
+    }
+    std::vector<int32_t> level_ptr(n_levels + 1, 0), order(n);
+    for (int64_t i = 0; i < n; ++i) level_ptr[level[i] + 1]++;
+    int32_t max_rows = 0;
+    for (int32_t l = 0; l < n_levels; ++l) {
+        if (level_ptr[l + 1] > max_rows) max_rows = level_ptr[l + 1];
+        level_ptr[l + 1] += level_ptr[l];
+    }
+    std::vector<int32_t> cursor(level_ptr.begin(), level_ptr.end() - 1);
+    for (int64_t i = 0; i < n; ++i) order[cursor[level[i]]++] = (int32_t)i;
+    phb200_trsv_plan* p = new phb200_trsv_plan();
+    memset(p, 0, sizeof(*p));
+    p->lower = lower;
+    p->n = n;
+    p->n_levels = n_levels;
+    p->max_level_rows = max_rows;
+    p->h_level_ptr = (int32_t*)malloc(sizeof(int32_t) * (n_levels + 1));
+    memcpy(p->h_level_ptr, level_ptr.data(), sizeof(int32_t) * (n_levels + 1));
+    cudaError_t e = cudaMalloc(&p->order, sizeof(int32_t) * (n > 0 ? n : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->level_ptr, sizeof(int32_t) * (n_levels + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(p->order, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->level_ptr, level_ptr.data(), sizeof(int32_t) * (n_levels + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("level schedule upload failed: %s", cudaGetErrorString(e));
+        phb200_sptrsv_plan_destroy(p);
+        return PHB200_ERR_CUDA;
+    }
+    *out = p;
+    return PHB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- triangular solve
+// One launch per level: x_i = (b_i - sum_{j in deps} T_ij x_j) / T_ii for the rows of the level and every right-hand side.
+template <typename T, bool LOWER>
+__global__ void __launch_bounds__(kBlock) k_trsv_level(CsrView A, const int32_t* __restrict__ order, int r0, int r1, int unit_diagonal,
+                                                       const T* __restrict__ B, T* __restrict__ X, int64_t ld) {
+    const int b = blockIdx.y;
+    const T* __restrict__ val = (const T*)A.val;
+    const int k = r0 + blockIdx.x * kBlock + threadIdx.x;
+    if (k >= r1) return;
+    const int i = order[k];
+    T acc = B[(int64_t)b * ld + i];
+    T diag = T(1);
+    const T* xb = X + (int64_t)b * ld;
+    for (int e = A.rowptr[i]; e < A.rowptr[i + 1]; ++e) {
+        const int j = A.col[e];
+        if (LOWER ? (j < i) : (j > i)) acc -= val[e] * xb[j];
+        else if (j == i) diag = val[e];
+    }
+    X[(int64_t)b * ld + i] = unit_diagonal ? acc : acc / diag;
+}
+
+template <typename T>
+static int trsv(const CsrView& A, const phb200_trsv_plan* plan, int lower, int unit_diagonal, const T* B, T* X, int64_t batch, int64_t ld, cudaStream_t stream) {
+    for (int64_t l = 0; l < plan->n_levels; ++l) {
+        const int r0 = plan->h_level_ptr[l], r1 = plan->h_level_ptr[l + 1];
+        if (r1 == r0) continue;
+        dim3 grid((unsigned)((r1 - r0 + kBlock - 1) / kBlock), (unsigned)batch);
+        if (lower) PHB_LAUNCH((k_trsv_level<T, true>), grid, kBlock, 0, stream, A, plan->order, r0, r1, unit_diagonal, B, X, ld);
+        else PHB_LAUNCH((k_trsv_level<T, false>), grid, kBlock, 0, stream, A, plan->order, r0, r1, unit_diagonal, B, X, ld);
+    }
+    return PHB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- ILU(0)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_diag_pos(CsrView A, int32_t* __restrict__ diag_pos, int* missing) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock) {
+        int32_t pos = -1;
+        for (int k = A.rowptr[i]; k < A.rowptr[i + 1]; ++k)
+            if (A.col[k] == (int32_t)i) { pos = k; break; }
+        if (pos < 0) *missing = 1;
+        diag_pos[i] = pos;
+    }
+}
+
+// IKJ elimination of the rows of one level (they only depend on rows of earlier levels).  Columns are sorted, so
+// the update a_ij -= a_ik a_kj walks row i and row k with two cursors.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_ilu0_level(CsrView A, T* __restrict__ lu, const int32_t* __restrict__ diag_pos,
+                                                       const int32_t* __restrict__ order, int r0, int r1) {
+    const int t = r0 + blockIdx.x * kBlock + threadIdx.x;
+    if (t >= r1) return;
+    const int i = order[t];
+    const int beg = A.rowptr[i], end = A.rowptr[i + 1];
+    for (int p = beg; p < end; ++p) {
+        const int k = A.col[p];
+        if (k >= i) break;
+        const T lik = lu[p] / lu[diag_pos[k]];
+        lu[p] = lik;
+        int q = diag_pos[k] + 1;
+        const int qend = A.rowptr[k + 1];
+        int c = p + 1;
+        while (q < qend && c < end) {
+            const int jq = A.col[q], jc = A.col[c];
+            if (jq == jc) {
+                lu[c] = lu[c] - lik * lu[q];
+                ++q;
+                ++c;
+            } else if (jq < jc) {
+                ++q;
+            } else {
+                ++c;
+            }
+        }
+    }
+}
+
+template <typename T>
+static int ilu0_factor(const phb200_precond* p, cudaStream_t stream) {
+    const phb200_trsv_plan* plan = p->plan_l;
+    T* lu = (T*)p->lu.val;
+    for (int64_t l = 0; l < plan->n_levels; ++l) {
+        const int r0 = plan->h_level_ptr[l], r1 = plan->h_level_ptr[l + 1];
+        if (r1 == r0) continue;
+        PHB_LAUNCH(k_ilu0_level<T>, (unsigned)((r1 - r0 + kBlock - 1) / kBlock), kBlock, 0, stream, p->lu, lu, p->diag_pos, plan->order, r0, r1);
+    }
+    return PHB200_OK;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_scale_rows(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ w, int64_t n, int64_t ld) {
+    const int b = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock)
+        out[(int64_t)b * ld + i] = mul_rn(in[(int64_t)b * ld + i], w[i]);
+}
+
+int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int64_t batch, int64_t ld, cudaStream_t stream) {
+    if (p->kind == PHB200_PRE_JACOBI) {
+        dim3 grid((unsigned)grid_x((p->n + kBlock - 1) / kBlock, batch), (unsigned)batch);
+        if (p->dtype == PHB200_F32) PHB_LAUNCH(k_scale_rows<float>, grid, kBlock, 0, stream, (const float*)in, (float*)out, (const float*)p->inv_diag, p->n, ld);
+        else PHB_LAUNCH(k_scale_rows<double>, grid, kBlock, 0, stream, (const double*)in, (double*)out, (const double*)p->inv_diag, p->n, ld);
+        return PHB200_OK;
+    }
+    if (p->kind == PHB200_PRE_ILU) {
+        if (p->dtype == PHB200_F32) return trsv<float>(p->lu, p->plan_l, 1, 1, (const float*)in, (float*)out, batch, ld, stream);
+        return trsv<double>(p->lu, p->plan_l, 1, 1, (const double*)in, (double*)out, batch, ld, stream);
+    }
+    set_error("preconditioner kind %d has no apply_inv_l", p->kind);
+    return PHB200_ERR_UNSUPPORTED;
+}
+
+int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp, int64_t batch, int64_t ld, cudaStream_t stream) {
+    if (p->kind == PHB200_PRE_JACOBI) return precond_apply_inv_l(p, in, out, batch, ld, stream);
+    if (p->kind == PHB200_PRE_ILU) {
+        // out = U^-1 (L^-1 in); the upper solve may run in place, so `tmp` is not needed
+        (void)tmp;
+        PHB_TRY(precond_apply_inv_l(p, in, out, batch, ld, stream));
+        if (p->dtype == PHB200_F32) return trsv<float>(p->lu, p->plan_u, 0, 0, (const float*)out, (float*)out, batch, ld, stream);
+        return trsv<double>(p->lu, p->plan_u, 0, 0, (const double*)out, (double*)out, batch, ld, stream);
+    }
+    set_error("preconditioner kind %d cannot be applied", p->kind);
+    return PHB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace phb
+
+using namespace phb;
+
+extern "C" {
+
+int phb200_jacobi_setup(const phb200_matrix* A, void* inv_diag, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(A && inv_diag, "null argument");
+    PHB_ARG(A->n_rows == A->n_cols, "matrix must be square");
+    const int64_t n = A->n_rows;
+    const unsigned gridx = (unsigned)grid_x((n + kBlock - 1) / kBlock, 1);
+    if (A->kind == PHB200_MAT_STENCIL) {
+        PHB_ARG(A->st.diag >= 0, "stencil has no diagonal entry");
+        const double c = A->st.coef[A->st.diag];
+        if (A->dtype == PHB200_F32) PHB_LAUNCH(k_jacobi_const<float>, gridx, kBlock, 0, stream, (float*)inv_diag, n, 1.0f / (float)c);
+        else PHB_LAUNCH(k_jacobi_const<double>, gridx, kBlock, 0, stream, (double*)inv_diag, n, 1.0 / c);
+        return PHB200_OK;
+    }
+    // the diagonal of A^T is the diagonal of A, so transposed views need no special case
+    int* d_missing = nullptr;
+    PHB_CUDA(cudaMallocAsync(&d_missing, sizeof(int), stream));
+    PHB_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int), stream));
+    if (A->dtype == PHB200_F32) PHB_LAUNCH(k_jacobi_csr<float>, gridx, kBlock, 0, stream, A->csr, (float*)inv_diag, d_missing);
+    else PHB_LAUNCH(k_jacobi_csr<double>, gridx, kBlock, 0, stream, A->csr, (double*)inv_diag, d_missing);
+    int h = 0;
+    PHB_CUDA(cudaMemcpyAsync(&h, d_missing, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    PHB_CUDA(cudaFreeAsync(d_missing, stream));
+    PHB_ARG(!h, "All diagonal elements must be present in sparse matrix.");
+    return PHB200_OK;
+}
+
+int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n, int dtype) {
+    PHB_ARG(out && inv_diag && n >= 0, "null argument");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    phb200_precond* p = new phb200_precond();
+    memset(p, 0, sizeof(*p));
+    p->kind = PHB200_PRE_JACOBI;
+    p->dtype = dtype;
+    p->n = n;
+    p->inv_diag = inv_diag;
+    *out = p;
+    return PHB200_OK;
+}
+
+int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(out && A && lu_val, "null argument");
+    PHB_ARG(A->kind == PHB200_MAT_CSR && !A->transposed, "ILU(0) needs a plain CSR matrix");
+    PHB_ARG(A->n_rows == A->n_cols, "incomplete_lu_coo only implemented for square matrices");
+    const size_t w = A->dtype == PHB200_F32 ? 4 : 8;
+    phb200_precond* p = new phb200_precond();
+    memset(p, 0, sizeof(*p));
+    p->kind = PHB200_PRE_ILU;
+    p->dtype = A->dtype;
+    p->n = A->n_rows;
+    p->lu = A->csr;
+    p->lu.val = lu_val;
+    int r = PHB200_OK;
+    int* d_missing = nullptr;
+    do {
+        if (cudaMalloc(&p->diag_pos, sizeof(int32_t) * (p->n > 0 ? p->n : 1)) != cudaSuccess) { set_error("cudaMalloc failed"); r = PHB200_ERR_CUDA; break; }
+        if (cudaMallocAsync(&d_missing, sizeof(int), stream) != cudaSuccess) { set_error("cudaMallocAsync failed"); r = PHB200_ERR_CUDA; break; }
+        cudaMemsetAsync(d_missing, 0, sizeof(int), stream);
+        if (lu_val != A->csr.val) cudaMemcpyAsync(lu_val, A->csr.val, w * A->nnz, cudaMemcpyDeviceToDevice, stream);
+        const unsigned gridx = (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1);
+        if (A->dtype == PHB200_F32) k_diag_pos<float><<<gridx, kBlock, 0, stream>>>(A->csr, p->diag_pos, d_missing);
+        else k_diag_pos<double><<<gridx, kBlock, 0, stream>>>(A->csr, p->diag_pos, d_missing);
+        g_launches.fetch_add(1);
+        int h = 0;
+        cudaMemcpyAsync(&h, d_missing, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("diagonal search failed: %s", cudaGetErrorString(cudaGetLastError())); r = PHB200_ERR_CUDA; break; }
+        if (h) { set_error("All diagonal elements must be present in sparse matrix."); r = PHB200_ERR_ARG; break; }
+        r = build_plan(&p->plan_l, A->csr, 1, stream);
+        if (r != PHB200_OK) break;
+        r = build_plan(&p->plan_u, A->csr, 0, stream);
+        if (r != PHB200_OK) break;
+        r = A->dtype == PHB200_F32 ? ilu0_factor<float>(p, stream) : ilu0_factor<double>(p, stream);
+    } while (0);
+    if (d_missing) cudaFreeAsync(d_missing, stream);
+    if (r != PHB200_OK) {
+        phb200_precond_destroy(p);
+        return r;
+    }
+    *out = p;
+    return PHB200_OK;
+}
+
+int phb200_precond_levels(const phb200_precond* p, int64_t* lower_levels, int64_t* upper_levels) {
+    PHB_ARG(p && p->kind == PHB200_PRE_ILU, "need an ILU preconditioner");
+    if (lower_levels) *lower_levels = p->plan_l->n_levels;
+    if (upper_levels) *upper_levels = p->plan_u->n_levels;
+    return PHB200_OK;
+}
+
+int phb200_sptrsv_plan(phb200_trsv_plan** out, const phb200_matrix* T, int lower, void* stream_) {
+    PHB_ARG(out && T, "null argument");
+    PHB_ARG(T->kind == PHB200_MAT_CSR && !T->transposed, "triangular solves need a plain CSR matrix");
+    PHB_ARG(T->n_rows == T->n_cols, "triangular matrix must be square");
+    return build_plan(out, T->csr, lower ? 1 : 0, (cudaStream_t)stream_);
+}
+
+int phb200_sptrsv(const phb200_matrix* T, const phb200_trsv_plan* plan, int lower, int unit_diagonal,
+                  const void* B, void* X, int64_t batch, int64_t ld, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(T && B && X, "null argument");
+    PHB_ARG(T->kind == PHB200_MAT_CSR && !T->transposed, "triangular solves need a plain CSR matrix");
+    PHB_ARG(batch >= 0 && batch <= 65535 && ld >= T->n_rows, "bad batch / leading dimension");
+    if (batch == 0 || T->n_rows == 0) return PHB200_OK;
+    phb200_trsv_plan* own = nullptr;
+    if (!plan) {
+        PHB_TRY(build_plan(&own, T->csr, lower ? 1 : 0, stream));
+        plan = own;
+    }
+    int r;
+    if (plan->lower != (lower ? 1 : 0) || plan->n != T->n_rows) {
+        set_error("plan does not match this solve");
+        r = PHB200_ERR_ARG;
+    } else if (T->dtype == PHB200_F32) {
+        r = trsv<float>(T->csr, plan, lower ? 1 : 0, unit_diagonal, (const float*)B, (float*)X, batch, ld, stream);
+    } else {
+        r = trsv<double>(T->csr, plan, lower ? 1 : 0, unit_diagonal, (const double*)B, (double*)X, batch, ld, stream);
+    }
+    if (own) {
+        cudaStreamSynchronize(stream);
+        phb200_sptrsv_plan_destroy(own);
+    }
+    return r;
+}
+
+int phb200_sptrsv_plan_destroy(phb200_trsv_plan* p) {
+    if (!p) return PHB200_OK;
+    if (p->order) cudaFree(p->order);
+    if (p->level_ptr) cudaFree(p->level_ptr);
+    if (p->h_level_ptr) free(p->h_level_ptr);
+    delete p;
+    return PHB200_OK;
+}
+
+int phb200_precond_apply(const phb200_precond* p, const void* in, void* out, int64_t batch, int64_t ld, void* stream_) {
+    PHB_ARG(p && in && out, "null argument");
+    PHB_ARG(batch >= 0 && batch <= 65535 && ld >= p->n, "bad batch / leading dimension");
+    if (batch == 0 || p->n == 0) return PHB200_OK;
+    return precond_apply(p, in, out, nullptr, batch, ld, (cudaStream_t)stream_);
+}
+
+int phb200_precond_destroy(phb200_precond* p) {
+    if (!p) return PHB200_OK;
+    if (p->diag_pos) cudaFree(p->diag_pos);
+    phb200_sptrsv_plan_destroy(p->plan_l);
+    phb200_sptrsv_plan_destroy(p->plan_u);
+    delete p;
+    return PHB200_OK;
+}
+
+}  // extern "C"

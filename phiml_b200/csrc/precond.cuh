@@ -1,0 +1,34 @@
+// Preconditioner handles (Jacobi, ILU(0)) and the level-scheduled triangular solve plans.
+#pragma once
+#include "matrix.cuh"
+
+struct phb200_trsv_plan {
+    int lower;
+    int64_t n;
+    int64_t n_levels;
+    int32_t* order;        // device: rows sorted by level
+    int32_t* level_ptr;    // device: n_levels+1 offsets into order
+    int32_t* h_level_ptr;  // host copy
+    int32_t max_level_rows;
+};
+
+struct phb200_precond {
+    int kind;              // PHB200_PRE_*
+    int dtype;
+    int64_t n;
+    const void* inv_diag;  // Jacobi (caller-owned)
+    // ILU(0): factors share A's pattern; values in lu_val (caller-owned); diag_pos[i] = index of (i,i) in row i
+    phb::CsrView lu;
+    int32_t* diag_pos;     // device, owned
+    phb200_trsv_plan* plan_l;
+    phb200_trsv_plan* plan_u;
+};
+
+namespace phb {
+
+// out = M^-1 in for (batch, ld) vectors; tmp is a scratch vector set of the same shape (ILU only).
+int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp, int64_t batch, int64_t ld, cudaStream_t stream);
+// out = L^-1 in (ILU) / D^-1 in (Jacobi) — Preconditioner.apply_inv_l
+int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int64_t batch, int64_t ld, cudaStream_t stream);
+
+}  // namespace phb

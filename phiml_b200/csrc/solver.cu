@@ -1,0 +1,1161 @@
+// Krylov loops on the device: CG (generic / adaptive / torch fast-path rules) and BiCGstab(L).
+// Algorithms follow phiml/backend/_linalg.py:23-274 and phiml/backend/torch/_torch_backend.py:1353-1413 (see
+// include/phb200.h); the loop of Backend.while_loop (phiml/backend/_backend.py:697-735) runs on the device: every
+// kernel starts with a test of Glob::any_go, per-system `go` flags freeze finished systems, the host only polls a
+// pinned flag every few passes.
+#include "phase.cuh"
+#include "precond.cuh"
+#include <vector>
+
+namespace phb {
+
+enum Slot {
+    S_ALPHA = 0, S_BETA, S_DELTA, S_DQ, S_DR, S_RQ, S_RHO0, S_RHO1, S_OMEGA, S_RHOP, S_GAMMA, S_YY,
+    S_TAU = 12, S_SIGMA = 17, S_GAM = 22, S_GAMP = 27, S_GAMPP = 32   // 5 entries each: poly_order <= 4
+};
+
+enum Rules { RULES_GENERIC = 0, RULES_TORCH = 1 };
+
+// ------------------------------------------------------------------------------------------------ functor base
+struct FBase : Ctx {
+    int always;   // 1: initialisation kernel — never idle, never skip
+    int freeze;   // 1: finished systems are skipped (their x, r stay untouched)
+    __device__ bool idle() const { return !always && glob->any_go == 0; }
+    __device__ bool skip(int b) const { return !always && freeze && sys[b].go == 0; }
+};
+
+template <typename T>
+__device__ __forceinline__ void check_all(const FBase& f, int rules) {
+    progress_check<T>(f.sys, f.glob, f.batch, rules == RULES_TORCH, f.freeze != 0);
+}
+
+// ------------------------------------------------------------------------------------------------ initial residual
+// r = y - q (q = A x0), s = M r, d = s.  Dots: r.s, y.y, r.r.  Sets up tolerances (minimum over the batch) and runs
+// the first progress check.  PRE: 0 none, 1 Jacobi (inv_diag), 2 external (r and s already computed).
+template <typename T, int PRE>
+struct InitResidual : FBase {
+    static constexpr int NA = 5;   // r, y, q|s, d, w
+    static constexpr unsigned RMASK = PRE == 2 ? 0b00111u : (PRE == 1 ? 0b10110u : 0b00110u);
+    static constexpr unsigned WMASK = PRE == 2 ? 0b01000u : 0b01001u;
+    static constexpr unsigned SHARED = 0b10000u;
+    static constexpr int ND = 3;
+    static constexpr bool GLOBAL = true;
+    const void* v[NA];
+    const T* rtol;
+    const T* atol;
+    const int32_t* max_iter;
+    int tol_from_y;    // 0: tolerance relative to |r0.M^-1 r0| and monitor r.M^-1 r (generic cg); 1: |y|^2 and r.r
+    int rules;
+    int bicg;
+    struct Scal {};
+    __device__ Scal load(int) const { return Scal{}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[ND], const Scal&) const {
+        T s;
+        if (PRE == 2) {
+            s = e[2];
+        } else {
+            e[0] = add_rn(e[1], -e[2]);
+            s = PRE == 1 ? mul_rn(e[0], e[4]) : e[0];
+        }
+        e[3] = s;
+        acc[0] += (double)mul_rn(e[0], s);
+        acc[1] += (double)mul_rn(e[1], e[1]);
+        acc[2] += (double)mul_rn(e[0], e[0]);
+    }
+    __device__ void finalize(int b, const double (&tot)[ND]) const {
+        Sys& s = sys[b];
+        const T delta0 = (T)tot[0], yy = (T)tot[1], rr = (T)tot[2];
+        const T norm = tol_from_y ? yy : (T)fabs((double)delta0);
+        const T rt = rtol[b], at = atol[b];
+        const T t1 = rt * rt * norm, t2 = at * at;
+        s.tol = (double)(t1 > t2 ? t1 : (t2 >= t1 ? t2 : (T)NAN));   // np.maximum propagates NaN
+        s.rsq = (double)(tol_from_y ? rr : delta0);
+        s.rsq0 = 0.0;
+        s.its = 0;
+        s.fev = 1;
+        s.go = 1;
+        s.conv = s.div = 0;
+        s.max_iter = max_iter[b];
+        for (int k = 0; k < 40; ++k) s.s[k] = 0.0;
+        s.s[S_DELTA] = (double)(tol_from_y ? rr : delta0);
+        s.s[S_YY] = (double)yy;
+        if (bicg) {
+            s.s[S_RHO0] = s.s[S_RHO1] = s.s[S_OMEGA] = s.s[S_RHOP] = 1.0;
+        }
+    }
+    __device__ void finalize_all() const {
+        __shared__ double s_min[kBlock];
+        double m = INFINITY;
+        bool nan = false;
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            double t = ((volatile Sys*)sys)[b].tol;
+            if (t != t) nan = true;
+            else m = fmin(m, t);
+        }
+        s_min[threadIdx.x] = nan ? NAN : m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double mm = INFINITY;
+            bool anynan = false;
+            for (int k = 0; k < (int)blockDim.x; ++k) {
+                if (s_min[k] != s_min[k]) anynan = true;
+                else mm = fmin(mm, s_min[k]);
+            }
+            glob->tol_min = anynan ? NAN : mm;
+            glob->checks = 0;
+            glob->pass = 0;
+            glob->refresh = 0;
+            __threadfence();
+        }
+        __syncthreads();
+        check_all<T>(*this, rules);
+    }
+};
+
+// r = y - q only (ILU path: s = M r is then computed by the triangular solves before InitResidual<T,2>)
+template <typename T>
+struct Residual : FBase {
+    static constexpr int NA = 3;   // r, y, q
+    static constexpr unsigned RMASK = 0b110u, WMASK = 0b001u, SHARED = 0u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal {};
+    __device__ Scal load(int) const { return Scal{}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal&) const { e[0] = add_rn(e[1], -e[2]); }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// ------------------------------------------------------------------------------------------------ CG: q = A d, d.q
+template <typename T>
+struct CgDq : FBase {   // SpMV epilogue
+    static constexpr int ND = 1;
+    static constexpr bool GLOBAL = false;
+    const T* d;
+    int64_t ld;
+    __device__ void row(int b, int64_t i, T y, double (&acc)[1]) const { acc[0] += (double)mul_rn(d[(int64_t)b * ld + i], y); }
+    __device__ void finalize(int b, const double (&tot)[1]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        s.its += s.go;
+        s.fev += s.go;
+        const T dq = (T)tot[0];
+        s.s[S_DQ] = (double)dq;
+        s.s[S_ALPHA] = s.go ? (double)safe_div((T)s.s[S_DELTA], dq) : 0.0;
+    }
+    __device__ void finalize_all() const {}
+};
+
+// x += alpha d ; r -= alpha q ; s = M r ; delta' = r.s     (PRE 0/1 fused; PRE 2: no dot, s comes from the ILU solves)
+template <typename T, int PRE>
+struct CgUpdate : FBase {
+    static constexpr int NA = 5;   // x, r, d, q, w
+    static constexpr unsigned RMASK = PRE == 1 ? 0b11111u : 0b01111u, WMASK = 0b00011u, SHARED = 0b10000u;
+    static constexpr int ND = PRE == 2 ? 0 : 1;
+    static constexpr bool GLOBAL = PRE != 2;
+    const void* v[NA];
+    int rules;
+    struct Scal { T alpha; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA]}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[ND == 0 ? 1 : ND], const Scal& sc) const {
+        e[0] = add_rn(e[0], mul_rn(sc.alpha, e[2]));
+        e[1] = add_rn(e[1], -mul_rn(sc.alpha, e[3]));
+        if (PRE != 2) {
+            const T s = PRE == 1 ? mul_rn(e[1], e[4]) : e[1];
+            acc[0] += (double)mul_rn(e[1], s);
+        }
+    }
+    __device__ void finalize(int b, const double (&tot)[ND == 0 ? 1 : ND]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        const T dold = (T)s.s[S_DELTA], dnew = (T)tot[0];
+        s.s[S_DELTA] = (double)dnew;
+        s.s[S_BETA] = (double)safe_div(dnew, dold);
+        s.rsq = (double)dnew;
+    }
+    __device__ void finalize_all() const {
+        check_all<T>(*this, rules);
+        if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+    }
+};
+
+// delta' = r.s with s given (ILU), same scalar update as CgUpdate
+template <typename T>
+struct CgDeltaDot : FBase {
+    static constexpr int NA = 2;   // r, s
+    static constexpr unsigned RMASK = 0b11u, WMASK = 0u, SHARED = 0u;
+    static constexpr int ND = 1;
+    static constexpr bool GLOBAL = true;
+    const void* v[NA];
+    int rules;
+    struct Scal {};
+    __device__ Scal load(int) const { return Scal{}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[1], const Scal&) const { acc[0] += (double)mul_rn(e[0], e[1]); }
+    __device__ void finalize(int b, const double (&tot)[1]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        const T dold = (T)s.s[S_DELTA], dnew = (T)tot[0];
+        s.s[S_DELTA] = (double)dnew;
+        s.s[S_BETA] = (double)safe_div(dnew, dold);
+        s.rsq = (double)dnew;
+    }
+    __device__ void finalize_all() const {
+        check_all<T>(*this, rules);
+        if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+    }
+};
+
+// d = s + beta d
+template <typename T, int PRE>
+struct CgDirection : FBase {
+    static constexpr int NA = 3;   // d, r|s, w
+    static constexpr unsigned RMASK = PRE == 1 ? 0b111u : 0b011u, WMASK = 0b001u, SHARED = 0b100u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal { T beta; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_BETA]}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal& sc) const {
+        const T s = PRE == 1 ? mul_rn(e[1], e[2]) : e[1];
+        e[0] = add_rn(s, mul_rn(sc.beta, e[0]));
+    }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// ------------------------------------------------------------------------------------------------ torch refresh pass
+// x += alpha d only
+template <typename T>
+struct AxpyX : FBase {
+    static constexpr int NA = 2;   // x, d
+    static constexpr unsigned RMASK = 0b11u, WMASK = 0b01u, SHARED = 0u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal { T alpha; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA]}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal& sc) const { e[0] = add_rn(e[0], mul_rn(sc.alpha, e[1])); }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// SpMV epilogue that only carries the idle test (t = A x in the refresh pass)
+template <typename T>
+struct PlainEpi : FBase {
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    __device__ void row(int, int64_t, T, double (&)[1]) const {}
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// r = y - t ; dots r.r, r.q ; function_evaluations += 1 for ALL systems (torch_sparse_cg, :1372-1373)
+template <typename T, bool ADAPTIVE>
+struct RefreshResidual : FBase {
+    static constexpr int NA = 4;   // r, y, t, q
+    static constexpr unsigned RMASK = ADAPTIVE ? 0b1110u : 0b0110u, WMASK = 0b0001u, SHARED = 0u;
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = !ADAPTIVE;
+    const void* v[NA];
+    int rules;
+    struct Scal {};
+    __device__ Scal load(int) const { return Scal{}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[2], const Scal&) const {
+        e[0] = add_rn(e[1], -e[2]);
+        acc[0] += (double)mul_rn(e[0], e[0]);
+        if (ADAPTIVE) acc[1] += (double)mul_rn(e[0], e[3]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const {
+        Sys& s = sys[b];
+        s.fev += 1;
+        const T dold = (T)s.s[S_DELTA], dnew = (T)tot[0];
+        s.s[S_DELTA] = (double)dnew;
+        s.s[S_BETA] = (double)safe_div(dnew, dold);
+        s.s[S_RQ] = (double)(T)tot[1];
+        s.rsq = (double)dnew;
+        if (ADAPTIVE) s.its += s.go;
+    }
+    __device__ void finalize_all() const {
+        check_all<T>(*this, rules);
+        if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ CG-adaptive
+// x += alpha d ; r -= alpha q ; dots r.r, r.q
+template <typename T>
+struct AdUpdate : FBase {
+    static constexpr int NA = 4;   // x, r, d, q
+    static constexpr unsigned RMASK = 0b1111u, WMASK = 0b0011u, SHARED = 0u;
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal { T alpha; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA]}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[2], const Scal& sc) const {
+        e[0] = add_rn(e[0], mul_rn(sc.alpha, e[2]));
+        e[1] = add_rn(e[1], -mul_rn(sc.alpha, e[3]));
+        acc[0] += (double)mul_rn(e[1], e[1]);
+        acc[1] += (double)mul_rn(e[1], e[3]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        s.its += s.go;
+        s.s[S_DELTA] = (double)(T)tot[0];
+        s.s[S_RQ] = (double)(T)tot[1];
+        s.rsq = (double)(T)tot[0];
+    }
+    __device__ void finalize_all() const {}
+};
+
+// d = r - safe_div(rq * d, dq)
+template <typename T>
+struct AdDirection : FBase {
+    static constexpr int NA = 2;   // d, r
+    static constexpr unsigned RMASK = 0b11u, WMASK = 0b01u, SHARED = 0u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal { T rq, dq; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_RQ], (T)sys[b].s[S_DQ]}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal& sc) const {
+        const T t = mul_rn(sc.rq, e[0]);
+        const T u = sc.dq == T(0) ? T(0) : t / sc.dq;
+        e[0] = add_rn(e[1], -u);
+    }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// q = A d with d.q, d.r ; then progress check and the next pass's alpha = safe_div(d.r, d.q) * go
+template <typename T>
+struct AdDots : FBase {   // SpMV epilogue
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = true;
+    const T* d;
+    const T* r;
+    int64_t ld;
+    int rules;
+    int do_check;    // 0 for the product inside start(): the first check was already made
+    int count_fev;
+    __device__ void row(int b, int64_t i, T y, double (&acc)[2]) const {
+        const T dv = d[(int64_t)b * ld + i];
+        acc[0] += (double)mul_rn(dv, y);
+        acc[1] += (double)mul_rn(dv, r[(int64_t)b * ld + i]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const {
+        Sys& s = sys[b];
+        if (freeze && !always && !s.go) return;
+        if (count_fev) s.fev += s.go;
+        s.s[S_DQ] = (double)(T)tot[0];
+        s.s[S_DR] = (double)(T)tot[1];
+    }
+    __device__ void finalize_all() const {
+        if (do_check) check_all<T>(*this, rules);
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            volatile Sys* s = sys + b;
+            s->s[S_ALPHA] = s->go ? (double)safe_div((T)s->s[S_DR], (T)s->s[S_DQ]) : 0.0;
+        }
+        if (threadIdx.x == 0 && do_check) glob->pass = glob->pass + 1;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ BiCGstab primitives
+// out = a + sign * s[slot] * b
+template <typename T>
+struct Lin2 : FBase {
+    static constexpr int NA = 3;   // out, a, b
+    static constexpr unsigned RMASK = 0b110u, WMASK = 0b001u, SHARED = 0u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    int slot;
+    int sign;
+    struct Scal { T c; };
+    __device__ Scal load(int b) const { return Scal{(T)(sign * sys[b].s[slot])}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal& sc) const { e[0] = add_rn(e[1], mul_rn(sc.c, e[2])); }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// out = a .* w (w shared along the batch): Jacobi apply
+template <typename T>
+struct Scale : FBase {
+    static constexpr int NA = 3;   // out, a, w
+    static constexpr unsigned RMASK = 0b110u, WMASK = 0b001u, SHARED = 0b100u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal {};
+    __device__ Scal load(int) const { return Scal{}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal&) const { e[0] = mul_rn(e[1], e[2]); }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+enum BiStep {
+    BI_RHO = 0,      // rho1 = tot0; (j==0: its += go, rho0 = -omega rho0); beta = alpha rho1 / rho0; rho0 = rho1
+    BI_GAMMA,        // fev += go; alpha = rho0 / tot0
+    BI_NEXT,         // fev += go; if (j+1 < L) like BI_RHO with j+1
+    BI_TAU,          // tau[j] = tot0 / sigma[i]
+    BI_SIGMA,        // sigma[j] = tot0; gam_p[j] = tot1 / sigma[j]; j == L: MR coefficients
+    BI_FINAL,        // rsq = tot0 -> progress check
+    B1_RHO,          // its += go; rho = tot0; beta = rho / rho_prev * alpha / omega; rho_prev = rho
+    B1_ALPHA,        // fev += go; alpha = rho / tot0
+    B1_OMEGA,        // omega = tot0 / tot1
+    B1_FEV           // fev += go
+};
+
+template <typename T>
+__device__ __forceinline__ void bi_scalar_step(Sys& s, int step, int j, int i, int L, const double* tot) {
+    double* v = s.s;
+    switch (step) {
+        case BI_RHO: {
+            if (j == 0) {
+                s.its += s.go;
+                v[S_RHO0] = (double)(-(T)v[S_OMEGA] * (T)v[S_RHO0]);
+            }
+            const T rho1 = (T)tot[0];
+            v[S_RHO1] = (double)rho1;
+            v[S_BETA] = (double)((T)v[S_ALPHA] * rho1 / (T)v[S_RHO0]);
+            v[S_RHO0] = (double)rho1;
+            break;
+        }
+        case BI_GAMMA: {
+            s.fev += s.go;
+            v[S_GAMMA] = (double)(T)tot[0];
+            v[S_ALPHA] = (double)((T)v[S_RHO0] / (T)tot[0]);
+            break;
+        }
+        case BI_NEXT: {
+            s.fev += s.go;
+            if (j + 1 < L) {
+                const T rho1 = (T)tot[0];
+                v[S_RHO1] = (double)rho1;
+                v[S_BETA] = (double)((T)v[S_ALPHA] * rho1 / (T)v[S_RHO0]);
+                v[S_RHO0] = (double)rho1;
+            }
+            break;
+        }
+        case BI_TAU: {
+            v[S_TAU + j] = (double)((T)tot[0] / (T)v[S_SIGMA + i]);
+            break;
+        }
+        case BI_SIGMA: {
+            const T sig = (T)tot[0];
+            v[S_SIGMA + j] = (double)sig;
+            v[S_GAMP + j] = (double)((T)tot[1] / sig);
+            if (j == L) {   // MR part (tau rows are aliased in the reference: tau[i][j] == tau[j])
+                v[S_OMEGA] = v[S_GAM + L] = v[S_GAMP + L];
+                for (int jj = L - 1; jj >= 1; --jj) {
+                    T acc = T(0);
+                    for (int ii = jj + 1; ii <= L; ++ii) acc = acc + (T)v[S_TAU + ii] * (T)v[S_GAM + ii];
+                    v[S_GAM + jj] = (double)((T)v[S_GAMP + jj] - acc);
+                }
+                for (int jj = 1; jj < L; ++jj) {
+                    T acc = T(0);
+                    for (int ii = jj + 1; ii < L; ++ii) acc = acc + (T)v[S_TAU + ii] * (T)v[S_GAM + ii + 1];
+                    v[S_GAMPP + jj] = (double)((T)v[S_GAM + jj + 1] + acc);
+                }
+            }
+            break;
+        }
+        case BI_FINAL: {
+            s.rsq = (double)(T)tot[0];
+            break;
+        }
+        case B1_RHO: {
+            s.its += s.go;
+            const T rho = (T)tot[0];
+            v[S_RHO1] = (double)rho;
+            v[S_BETA] = (double)(rho / (T)v[S_RHOP] * (T)v[S_ALPHA] / (T)v[S_OMEGA]);
+            v[S_RHOP] = (double)rho;
+            break;
+        }
+        case B1_ALPHA: {
+            s.fev += s.go;
+            v[S_ALPHA] = (double)((T)v[S_RHO1] / (T)tot[0]);
+            break;
+        }
+        case B1_OMEGA: {
+            v[S_OMEGA] = (double)((T)tot[0] / (T)tot[1]);
+            break;
+        }
+        case B1_FEV: {
+            s.fev += s.go;
+            break;
+        }
+    }
+}
+
+// two dot products a0.b0, a1.b1 followed by a scalar step
+template <typename T>
+struct Dot2 : FBase {
+    static constexpr int NA = 4;   // a0, b0, a1, b1
+    static constexpr unsigned RMASK = 0b1111u, WMASK = 0u, SHARED = 0u;
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = true;
+    const void* v[NA];
+    int step, j, i, L, rules;
+    struct Scal {};
+    __device__ Scal load(int) const { return Scal{}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[2], const Scal&) const {
+        acc[0] += (double)mul_rn(e[0], e[1]);
+        acc[1] += (double)mul_rn(e[2], e[3]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const { bi_scalar_step<T>(sys[b], step, j, i, L, tot); }
+    __device__ void finalize_all() const {
+        if (step == BI_FINAL) {
+            check_all<T>(*this, rules);
+            if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+        }
+    }
+};
+
+// SpMV epilogue: dots y.w0 and (optional) y.w1, then a scalar step
+template <typename T>
+struct BiEpi : FBase {
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = false;
+    const T* w0;
+    const T* w1;   // may be null
+    int64_t ld;
+    int step, j, i, L;
+    __device__ void row(int b, int64_t k, T y, double (&acc)[2]) const {
+        acc[0] += (double)mul_rn(y, w0[(int64_t)b * ld + k]);
+        if (w1) acc[1] += (double)mul_rn(y, w1[(int64_t)b * ld + k]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const { bi_scalar_step<T>(sys[b], step, j, i, L, tot); }
+    __device__ void finalize_all() const {}
+};
+
+__global__ void k_collect(const Sys* __restrict__ sys, int batch, int32_t* its, int32_t* fev, uint8_t* conv, uint8_t* div) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (its) its[b] = sys[b].its;
+    if (fev) fev[b] = sys[b].fev;
+    if (conv) conv[b] = (uint8_t)sys[b].conv;
+    if (div) div[b] = (uint8_t)sys[b].div;
+}
+
+template <typename T>
+__global__ void k_fill(T* p, int64_t n, T value) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = value;
+}
+
+}  // namespace phb
+
+using namespace phb;
+
+// ================================================================================================== solver object
+struct phb200_solver {
+    const phb200_matrix* A;
+    const phb200_precond* M;
+    int method, L, dtype, pre;
+    int64_t batch, n;
+    // device bookkeeping (owned)
+    Sys* sys;
+    Glob* glob;
+    double* partials;
+    unsigned* tickets;
+    int* h_flag;               // pinned, 2 slots
+    cudaEvent_t ev[2];
+    // per-solve bindings
+    const void* Y;
+    void* X;
+    void* R;
+    char* ws;
+    size_t ws_bytes;
+    int started;
+    int64_t passes;            // loop passes enqueued so far
+    int64_t launches0;
+    long long launches;
+    // optional per-kernel timing (bench.py): events around the k-th kernel of every pass
+    int prof;
+    int prof_slot;             // index of the next kernel within the current pass
+    std::vector<cudaEvent_t>* prof_events;   // pairs (start, stop)
+    std::vector<int>* prof_slots;
+};
+
+namespace phb {
+
+// Upper bound of gridDim.x over every kernel of a solve: grid_x() hands out at most kTargetCtas CTAs per launch,
+// spread over the gridDim.y rows (systems, or tiles of kCsrBt systems in the streaming CSR kernel).
+static int max_blocks_for(int64_t batch) {
+    const int64_t rows = batch >= 8 * kCsrBt ? (batch + kCsrBt - 1) / kCsrBt : batch;
+    int64_t mb = kTargetCtas / (rows < 1 ? 1 : rows);
+    return (int)(mb < 1 ? 1 : mb);
+}
+
+static Ctx make_ctx(const phb200_solver* s) {
+    Ctx c;
+    c.sys = s->sys;
+    c.glob = s->glob;
+    c.red.partials = s->partials;
+    c.red.tickets = s->tickets;
+    c.red.max_blocks = max_blocks_for(s->batch);
+    c.batch = (int)s->batch;
+    return c;
+}
+
+template <class F>
+static void fill_base(F& f, const phb200_solver* s, bool always, bool freeze) {
+    Ctx c = make_ctx(s);
+    f.sys = c.sys;
+    f.glob = c.glob;
+    f.red = c.red;
+    f.batch = c.batch;
+    f.always = always ? 1 : 0;
+    f.freeze = freeze ? 1 : 0;
+}
+
+static int vectors_needed(int method, int L, int pre) {
+    switch (method) {
+        case PHB200_CG: return pre == PHB200_PRE_ILU ? 4 : 2;              // d, q (+ s, tmp)
+        case PHB200_CG_ADAPTIVE: return 2;                                   // d, q
+        case PHB200_CG_TORCH:
+        case PHB200_CG_ADAPTIVE_TORCH: return 3;                             // d, q, t
+        case PHB200_BICGSTAB:
+            if (L == 1) return 10;                                           // ones, u, p, ph, z, t, sl, tl, tmp, tmp2
+            return 2 * L + 4;                                                // shadow, uh[0..L], rh[1..L], pv, tmp
+    }
+    return 0;
+}
+
+template <typename T>
+struct Run {
+    phb200_solver* s;
+    cudaStream_t st;
+    int64_t n, ld;
+    int batch;
+    T* vec(int k) const { return (T*)s->ws + (int64_t)k * batch * ld; }
+    bool frozen() const { return s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE; }
+    int rules() const { return (s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH) ? RULES_TORCH : RULES_GENERIC; }
+    const T* invd() const { return s->pre == PHB200_PRE_JACOBI ? (const T*)s->M->inv_diag : nullptr; }
+
+    void prof_begin() {
+        if (!s->prof) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        s->prof_events->push_back(a);
+        s->prof_events->push_back(b);
+        s->prof_slots->push_back(s->prof_slot++);
+        cudaEventRecord(a, st);
+    }
+    void prof_end() {
+        if (s->prof) cudaEventRecord(s->prof_events->back(), st);
+    }
+    template <class P> int phase(const P& p) {
+        prof_begin();
+        int r = launch_phase<T, P>(p, n, ld, batch, st);
+        prof_end();
+        return r;
+    }
+    template <class E> int spmv(const T* x, T* y, const E& e) {
+        prof_begin();
+        int r = launch_spmv<T, E>(s->A, x, ld, y, ld, (const T*)nullptr, batch, e, st);
+        prof_end();
+        return r;
+    }
+
+    int lin2(T* out, const T* a, const T* b, int slot, int sign) {
+        Lin2<T> f;
+        fill_base(f, s, false, false);
+        f.v[0] = out; f.v[1] = a; f.v[2] = b;
+        f.slot = slot; f.sign = sign;
+        return phase(f);
+    }
+    int dot2(const T* a0, const T* b0, const T* a1, const T* b1, int step, int j, int i) {
+        Dot2<T> f;
+        fill_base(f, s, false, false);
+        f.v[0] = a0; f.v[1] = b0; f.v[2] = a1; f.v[3] = b1;
+        f.step = step; f.j = j; f.i = i; f.L = s->L; f.rules = RULES_GENERIC;
+        return phase(f);
+    }
+    int spmv_dot(const T* x, T* y, const T* w0, const T* w1, int step, int j) {
+        BiEpi<T> e;
+        fill_base(e, s, false, false);
+        e.w0 = w0; e.w1 = w1; e.ld = ld; e.step = step; e.j = j; e.i = 0; e.L = s->L;
+        return spmv(x, y, e);
+    }
+    // out = M^-1 in; returns the vector that holds the result (in itself without preconditioner)
+    int apply_pre(const T* in, T* out, T* tmp, const T** result) {
+        if (s->pre == PHB200_PRE_NONE) { *result = in; return PHB200_OK; }
+        if (s->pre == PHB200_PRE_JACOBI) {
+            Scale<T> f;
+            fill_base(f, s, false, false);
+            f.v[0] = out; f.v[1] = in; f.v[2] = s->M->inv_diag;
+            PHB_TRY(phase(f));
+            *result = out;
+            return PHB200_OK;
+        }
+        PHB_TRY(precond_apply(s->M, in, out, tmp, batch, ld, st));
+        *result = out;
+        return PHB200_OK;
+    }
+    int apply_inv_l(const T* in, T* out, const T** result) {
+        if (s->pre == PHB200_PRE_NONE) { *result = in; return PHB200_OK; }
+        if (s->pre == PHB200_PRE_JACOBI) {
+            Scale<T> f;
+            fill_base(f, s, false, false);
+            f.v[0] = out; f.v[1] = in; f.v[2] = s->M->inv_diag;
+            PHB_TRY(phase(f));
+            *result = out;
+            return PHB200_OK;
+        }
+        PHB_TRY(precond_apply_inv_l(s->M, in, out, batch, ld, st));
+        *result = out;
+        return PHB200_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------ start
+    int start(const T* Y, const T* X0, T* X, T* R, const T* rtol, const T* atol, const int32_t* max_iter) {
+        const int method = s->method;
+        if (X != X0) PHB_CUDA(cudaMemcpyAsync(X, X0, sizeof(T) * (size_t)batch * ld, cudaMemcpyDeviceToDevice, st));
+        PHB_CUDA(cudaMemsetAsync(s->tickets, 0, sizeof(unsigned) * (size_t)batch, st));
+        PHB_CUDA(cudaMemsetAsync(s->glob, 0, sizeof(Glob), st));
+        T* d = vec(0);
+        T* q = vec(1);
+        {   // q = A x0
+            PlainEpi<T> e;
+            fill_base(e, s, true, false);
+            PHB_TRY(spmv(X, q, e));
+        }
+        const bool bicg = method == PHB200_BICGSTAB;
+        const int tol_from_y = method == PHB200_CG ? 0 : 1;
+        if (s->pre == PHB200_PRE_ILU && method == PHB200_CG) {
+            Residual<T> r0;
+            fill_base(r0, s, true, false);
+            r0.v[0] = R; r0.v[1] = Y; r0.v[2] = q;
+            PHB_TRY(phase(r0));
+            T* sv = vec(2);
+            PHB_TRY(precond_apply(s->M, R, sv, vec(3), batch, ld, st));
+            InitResidual<T, 2> f;
+            fill_base(f, s, true, frozen());
+            f.v[0] = R; f.v[1] = Y; f.v[2] = sv; f.v[3] = d; f.v[4] = nullptr;
+            f.rtol = rtol; f.atol = atol; f.max_iter = max_iter; f.tol_from_y = tol_from_y; f.rules = rules(); f.bicg = 0;
+            PHB_TRY(phase(f));
+        } else if (s->pre == PHB200_PRE_JACOBI && method == PHB200_CG) {
+            InitResidual<T, 1> f;
+            fill_base(f, s, true, frozen());
+            f.v[0] = R; f.v[1] = Y; f.v[2] = q; f.v[3] = d; f.v[4] = s->M->inv_diag;
+            f.rtol = rtol; f.atol = atol; f.max_iter = max_iter; f.tol_from_y = tol_from_y; f.rules = rules(); f.bicg = 0;
+            PHB_TRY(phase(f));
+        } else {
+            // no preconditioner inside the initial direction (cg without M, cg_adaptive, torch paths, bicg: d = r)
+            InitResidual<T, 0> f;
+            fill_base(f, s, true, frozen());
+            f.v[0] = R; f.v[1] = Y; f.v[2] = q; f.v[3] = bicg ? (const void*)vec(0) : (const void*)d; f.v[4] = nullptr;
+            f.rtol = rtol; f.atol = atol; f.max_iter = max_iter; f.tol_from_y = tol_from_y; f.rules = rules(); f.bicg = bicg ? 1 : 0;
+            PHB_TRY(phase(f));
+        }
+        if (method == PHB200_CG_ADAPTIVE || method == PHB200_CG_ADAPTIVE_TORCH) {
+            AdDots<T> e;   // q = A d, d.q, d.r -> alpha of the first pass
+            fill_base(e, s, true, frozen());
+            e.d = d; e.r = R; e.ld = ld; e.rules = rules(); e.do_check = 0; e.count_fev = 0;
+            PHB_TRY(spmv(d, q, e));
+        }
+        if (bicg) {
+            // vec(0) = shadow residual (r0 for L >= 2, ones for L == 1); all other work vectors start at zero
+            const int nv = vectors_needed(method, s->L, s->pre);
+            PHB_CUDA(cudaMemsetAsync(vec(1), 0, sizeof(T) * (size_t)(nv - 1) * batch * ld, st));
+            if (s->L == 1) PHB_LAUNCH(k_fill<T>, kSMs * 4, kBlock, 0, st, vec(0), (int64_t)batch * ld, T(1));
+        }
+        return PHB200_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------ one pass
+    int pass_cg(T* X, T* R, const T* Y, bool refresh) {
+        T* d = vec(0);
+        T* q = vec(1);
+        const bool fr = frozen();
+        const bool torch = s->method == PHB200_CG_TORCH;
+        {
+            CgDq<T> e;
+            fill_base(e, s, false, fr);
+            e.d = d; e.ld = ld;
+            PHB_TRY(spmv(d, q, e));
+        }
+        if (torch && refresh) {
+            T* t = vec(2);
+            AxpyX<T> ax;
+            fill_base(ax, s, false, fr);
+            ax.v[0] = X; ax.v[1] = d;
+            PHB_TRY(phase(ax));
+            PlainEpi<T> pe;
+            fill_base(pe, s, false, fr);
+            PHB_TRY(spmv(X, t, pe));
+            RefreshResidual<T, false> rr;
+            fill_base(rr, s, false, fr);
+            rr.v[0] = R; rr.v[1] = Y; rr.v[2] = t; rr.v[3] = q; rr.rules = rules();
+            PHB_TRY(phase(rr));
+            CgDirection<T, 0> c;
+            fill_base(c, s, false, fr);
+            c.v[0] = d; c.v[1] = R; c.v[2] = nullptr;
+            return phase(c);
+        }
+        if (s->pre == PHB200_PRE_JACOBI) {
+            CgUpdate<T, 1> u;
+            fill_base(u, s, false, fr);
+            u.v[0] = X; u.v[1] = R; u.v[2] = d; u.v[3] = q; u.v[4] = s->M->inv_diag; u.rules = rules();
+            PHB_TRY(phase(u));
+            CgDirection<T, 1> c;
+            fill_base(c, s, false, fr);
+            c.v[0] = d; c.v[1] = R; c.v[2] = s->M->inv_diag;
+            return phase(c);
+        }
+        if (s->pre == PHB200_PRE_ILU) {
+            T* sv = vec(2);
+            CgUpdate<T, 2> u;
+            fill_base(u, s, false, fr);
+            u.v[0] = X; u.v[1] = R; u.v[2] = d; u.v[3] = q; u.v[4] = nullptr; u.rules = rules();
+            PHB_TRY(phase(u));
+            // the triangular solves run unconditionally (they do not know about any_go); harmless after the end
+            PHB_TRY(precond_apply(s->M, R, sv, vec(3), batch, ld, st));
+            CgDeltaDot<T> dd;
+            fill_base(dd, s, false, fr);
+            dd.v[0] = R; dd.v[1] = sv; dd.rules = rules();
+            PHB_TRY(phase(dd));
+            CgDirection<T, 0> c;
+            fill_base(c, s, false, fr);
+            c.v[0] = d; c.v[1] = sv; c.v[2] = nullptr;
+            return phase(c);
+        }
+        CgUpdate<T, 0> u;
+        fill_base(u, s, false, fr);
+        u.v[0] = X; u.v[1] = R; u.v[2] = d; u.v[3] = q; u.v[4] = nullptr; u.rules = rules();
+        PHB_TRY(phase(u));
+        CgDirection<T, 0> c;
+        fill_base(c, s, false, fr);
+        c.v[0] = d; c.v[1] = R; c.v[2] = nullptr;
+        return phase(c);
+    }
+
+    int pass_cg_adaptive(T* X, T* R, const T* Y, bool refresh) {
+        T* d = vec(0);
+        T* q = vec(1);
+        const bool fr = frozen();
+        if (s->method == PHB200_CG_ADAPTIVE_TORCH && refresh) {
+            T* t = vec(2);
+            AxpyX<T> ax;
+            fill_base(ax, s, false, fr);
+            ax.v[0] = X; ax.v[1] = d;
+            PHB_TRY(phase(ax));
+            PlainEpi<T> pe;
+            fill_base(pe, s, false, fr);
+            PHB_TRY(spmv(X, t, pe));
+            RefreshResidual<T, true> rr;
+            fill_base(rr, s, false, fr);
+            rr.v[0] = R; rr.v[1] = Y; rr.v[2] = t; rr.v[3] = q; rr.rules = rules();
+            PHB_TRY(phase(rr));
+        } else {
+            AdUpdate<T> u;
+            fill_base(u, s, false, fr);
+            u.v[0] = X; u.v[1] = R; u.v[2] = d; u.v[3] = q;
+            PHB_TRY(phase(u));
+        }
+        AdDirection<T> c;
+        fill_base(c, s, false, fr);
+        c.v[0] = d; c.v[1] = R;
+        PHB_TRY(phase(c));
+        AdDots<T> e;
+        fill_base(e, s, false, fr);
+        e.d = d; e.r = R; e.ld = ld; e.rules = rules(); e.do_check = 1; e.count_fev = 1;
+        return spmv(d, q, e);
+    }
+
+    // BiCGstab(L), L >= 2 (phiml/backend/_linalg.py:158-221).  vec: 0 shadow, 1..L+1 uh[0..L], L+2..2L+1 rh[1..L], 2L+2 pv, 2L+3 tmp
+    int pass_bicg_l(T* X, T* R) {
+        const int L = s->L;
+        const T* shadow = vec(0);
+        std::vector<T*> uh(L + 1), rh(L + 1);
+        for (int k = 0; k <= L; ++k) uh[k] = vec(1 + k);
+        rh[0] = R;
+        for (int k = 1; k <= L; ++k) rh[k] = vec(L + 1 + k);
+        T* pv = vec(2 * L + 2);
+        T* tmp = vec(2 * L + 3);
+        const T* pin = nullptr;
+        PHB_TRY(dot2(rh[0], shadow, rh[0], shadow, BI_RHO, 0, 0));
+        for (int j = 0; j < L; ++j) {
+            for (int i = 0; i <= j; ++i) PHB_TRY(lin2(uh[i], rh[i], uh[i], S_BETA, -1));
+            PHB_TRY(apply_pre(uh[j], pv, tmp, &pin));
+            PHB_TRY(spmv_dot(pin, uh[j + 1], shadow, nullptr, BI_GAMMA, j));
+            for (int i = 0; i <= j; ++i) PHB_TRY(lin2(rh[i], rh[i], uh[i + 1], S_ALPHA, -1));
+            PHB_TRY(apply_pre(rh[j], pv, tmp, &pin));
+            PHB_TRY(spmv_dot(pin, rh[j + 1], shadow, nullptr, BI_NEXT, j));
+            PHB_TRY(lin2(X, X, uh[0], S_ALPHA, +1));
+        }
+        for (int j = 1; j <= L; ++j) {
+            for (int i = 1; i < j; ++i) {
+                PHB_TRY(dot2(rh[j], rh[i], rh[j], rh[i], BI_TAU, j, i));
+                PHB_TRY(lin2(rh[j], rh[j], rh[i], S_TAU + j, -1));
+            }
+            PHB_TRY(dot2(rh[j], rh[j], rh[0], rh[j], BI_SIGMA, j, 0));
+        }
+        PHB_TRY(lin2(X, X, rh[0], S_GAM + 1, +1));
+        PHB_TRY(lin2(rh[0], rh[0], rh[L], S_GAMP + L, -1));
+        PHB_TRY(lin2(uh[0], uh[0], uh[L], S_GAM + L, -1));
+        for (int j = 1; j < L; ++j) {
+            PHB_TRY(lin2(uh[0], uh[0], uh[j], S_GAM + j, -1));
+            PHB_TRY(lin2(X, X, rh[j], S_GAMPP + j, +1));
+            PHB_TRY(lin2(rh[0], rh[0], rh[j], S_GAMP + j, -1));
+        }
+        return dot2(R, R, R, R, BI_FINAL, 0, 0);
+    }
+
+    // BiCGstab(1) (phiml/backend/_linalg.py:250-271).  vec: 0 ones, 1 u, 2 p, 3 ph, 4 z, 5 t, 6 sl, 7 tl, 8 tmp, 9 tmp2
+    int pass_bicg_1(T* X, T* R) {
+        const T* ones = vec(0);
+        T* u = vec(1);
+        T* p = vec(2);
+        T* ph = vec(3);
+        T* z = vec(4);
+        T* t = vec(5);
+        T* sl = vec(6);
+        T* tl = vec(7);
+        T* tmp = vec(8);
+        const T *php = nullptr, *zp = nullptr, *slp = nullptr, *tlp = nullptr;
+        PHB_TRY(dot2(ones, R, ones, R, B1_RHO, 0, 0));
+        PHB_TRY(lin2(p, p, u, S_OMEGA, -1));           // p - omega u
+        PHB_TRY(lin2(p, R, p, S_BETA, +1));            // r + beta (.)
+        PHB_TRY(apply_pre(p, ph, tmp, &php));
+        PHB_TRY(spmv_dot(php, u, ones, nullptr, B1_ALPHA, 0));
+        PHB_TRY(lin2(X, X, php, S_ALPHA, +1));         // h = x + alpha ph
+        PHB_TRY(lin2(R, R, u, S_ALPHA, -1));           // s = r - alpha u   (kept in R)
+        PHB_TRY(apply_inv_l(R, sl, &slp));
+        PHB_TRY(apply_pre(R, z, tmp, &zp));
+        PHB_TRY(spmv_dot(zp, t, ones, nullptr, B1_FEV, 0));
+        PHB_TRY(apply_inv_l(t, tl, &tlp));
+        PHB_TRY(dot2(tlp, slp, tlp, tlp, B1_OMEGA, 0, 0));
+        PHB_TRY(lin2(X, X, zp, S_OMEGA, +1));          // x = h + omega z
+        PHB_TRY(lin2(R, R, t, S_OMEGA, -1));           // r = s - omega t
+        return dot2(R, R, R, R, BI_FINAL, 0, 0);
+    }
+
+    int pass(bool refresh) {
+        T* X = (T*)s->X;
+        T* R = (T*)s->R;
+        const T* Y = (const T*)s->Y;
+        switch (s->method) {
+            case PHB200_CG:
+            case PHB200_CG_TORCH: return pass_cg(X, R, Y, refresh);
+            case PHB200_CG_ADAPTIVE:
+            case PHB200_CG_ADAPTIVE_TORCH: return pass_cg_adaptive(X, R, Y, refresh);
+            case PHB200_BICGSTAB: return s->L == 1 ? pass_bicg_1(X, R) : pass_bicg_l(X, R);
+        }
+        return PHB200_ERR_UNSUPPORTED;
+    }
+};
+
+template <typename T>
+static Run<T> make_run(phb200_solver* s, cudaStream_t st) {
+    Run<T> r;
+    r.s = s;
+    r.st = st;
+    r.n = s->n;
+    r.ld = s->n;
+    r.batch = (int)s->batch;
+    return r;
+}
+
+static int advance(phb200_solver* s, int n_iter, cudaStream_t st) {
+    for (int k = 0; k < n_iter; ++k) {
+        const int64_t pass_no = s->passes + 1;
+        const bool torch = s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH;
+        const bool refresh = torch && (pass_no % 20 == 0);
+        s->prof_slot = 0;
+        int r;
+        if (s->dtype == PHB200_F32) r = make_run<float>(s, st).pass(refresh);
+        else r = make_run<double>(s, st).pass(refresh);
+        if (r != PHB200_OK) return r;
+        s->passes = pass_no;
+    }
+    return PHB200_OK;
+}
+
+}  // namespace phb
+
+extern "C" {
+
+int phb200_solver_create(phb200_solver** out, const phb200_matrix* A, const phb200_precond* M, int method, int poly_order, int64_t batch) {
+    PHB_ARG(out && A, "null argument");
+    PHB_ARG(A->n_rows == A->n_cols, "matrix must be square");
+    PHB_ARG(batch >= 1 && batch <= 65535, "batch must be 1..65535, got %lld", (long long)batch);
+    PHB_ARG(method >= PHB200_CG && method <= PHB200_BICGSTAB, "unknown method %d", method);
+    PHB_ARG(!(A->kind == PHB200_MAT_CSR && A->transposed), "solver needs a plain CSR or stencil matrix (convert CSC natives first)");
+    if (method == PHB200_BICGSTAB) {
+        if (poly_order == 0) { set_error("Generic non-stabilized biCG not supported. Use 'scipy-biCG' instead"); return PHB200_ERR_UNSUPPORTED; }
+        PHB_ARG(poly_order >= 1 && poly_order <= 4, "biCG-stab(L) supports 1 <= L <= 4, got %d", poly_order);
+    } else {
+        poly_order = 0;
+    }
+    const int pre = M ? M->kind : PHB200_PRE_NONE;
+    if (M) PHB_ARG(M->n == A->n_rows && M->dtype == A->dtype, "preconditioner does not match the matrix");
+    if (method != PHB200_CG && method != PHB200_BICGSTAB && pre != PHB200_PRE_NONE) {
+        set_error("method %d takes no preconditioner (the reference falls back to 'CG')", method);
+        return PHB200_ERR_UNSUPPORTED;
+    }
+    phb200_solver* s = new phb200_solver();
+    memset(s, 0, sizeof(*s));
+    s->A = A;
+    s->M = M;
+    s->method = method;
+    s->L = poly_order;
+    s->dtype = A->dtype;
+    s->pre = pre;
+    s->batch = batch;
+    s->n = A->n_rows;
+    s->prof_events = new std::vector<cudaEvent_t>();
+    s->prof_slots = new std::vector<int>();
+    cudaError_t e = cudaMalloc(&s->sys, sizeof(Sys) * batch);
+    if (e == cudaSuccess) e = cudaMalloc(&s->glob, sizeof(Glob));
+    if (e == cudaSuccess) e = cudaMalloc(&s->partials, sizeof(double) * kMaxDots * (size_t)max_blocks_for(batch) * (size_t)batch);
+    if (e == cudaSuccess) e = cudaMalloc(&s->tickets, sizeof(unsigned) * batch);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_flag, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        set_error("solver allocation failed: %s", cudaGetErrorString(e));
+        phb200_solver_destroy(s);
+        return PHB200_ERR_CUDA;
+    }
+    *out = s;
+    return PHB200_OK;
+}
+
+size_t phb200_solver_workspace_bytes(const phb200_solver* s) {
+    if (!s) return 0;
+    const size_t w = s->dtype == PHB200_F32 ? 4 : 8;
+    return (size_t)vectors_needed(s->method, s->L, s->pre) * (size_t)s->batch * (size_t)s->n * w + 256;
+}
+
+int phb200_solver_start(phb200_solver* s, const void* Y, const void* X0, void* X, void* R, const void* rtol, const void* atol,
+                        const int32_t* max_iter, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && Y && X0 && X && R && rtol && atol && max_iter, "null argument");
+    if (workspace_bytes < phb200_solver_workspace_bytes(s) || (!workspace && workspace_bytes > 0)) {
+        set_error("workspace too small: need %zu bytes, got %zu", phb200_solver_workspace_bytes(s), workspace_bytes);
+        return PHB200_ERR_WORKSPACE;
+    }
+    PHB_ARG(((uintptr_t)workspace) % 256 == 0, "workspace must be 256-byte aligned");
+    s->Y = Y;
+    s->X = X;
+    s->R = R;
+    s->ws = (char*)workspace;
+    s->ws_bytes = workspace_bytes;
+    s->passes = 0;
+    s->launches0 = g_launches.load();
+    int r;
+    if (s->dtype == PHB200_F32) r = make_run<float>(s, st).start((const float*)Y, (const float*)X0, (float*)X, (float*)R, (const float*)rtol, (const float*)atol, max_iter);
+    else r = make_run<double>(s, st).start((const double*)Y, (const double*)X0, (double*)X, (double*)R, (const double*)rtol, (const double*)atol, max_iter);
+    s->started = r == PHB200_OK;
+    return r;
+}
+
+int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream_) {
+    PHB_ARG(s && s->started, "solver not started");
+    PHB_ARG(n_iter >= 0, "n_iter must be >= 0");
+    return advance(s, n_iter, (cudaStream_t)stream_);
+}
+
+int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && s->started && any_continue, "solver not started");
+    PHB_CUDA(cudaMemcpyAsync(&s->h_flag[0], &s->glob->any_go, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PHB_CUDA(cudaStreamSynchronize(st));
+    *any_continue = s->h_flag[0];
+    return PHB200_OK;
+}
+
+int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && s->started, "solver not started");
+    // The flag of chunk k is inspected while chunk k+1 is already queued, so the device never waits for the host.
+    int chunk = 4;
+    int slot = 0;
+    bool have_prev = false;
+    int64_t done = 0;
+    while (done < iteration_cap) {
+        const int n = (int)((iteration_cap - done) < chunk ? (iteration_cap - done) : chunk);
+        PHB_TRY(advance(s, n, st));
+        done += n;
+        PHB_CUDA(cudaMemcpyAsync(&s->h_flag[slot], &s->glob->any_go, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PHB_CUDA(cudaEventRecord(s->ev[slot], st));
+        if (have_prev) {
+            PHB_CUDA(cudaEventSynchronize(s->ev[slot ^ 1]));
+            if (s->h_flag[slot ^ 1] == 0) break;
+        }
+        have_prev = true;
+        slot ^= 1;
+        if (chunk < 32) chunk *= 2;
+    }
+    PHB_CUDA(cudaStreamSynchronize(st));
+    return PHB200_OK;
+}
+
+int phb200_solver_result(phb200_solver* s, int32_t* iterations, int32_t* function_evaluations, uint8_t* converged, uint8_t* diverged, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && s->started, "solver not started");
+    PHB_LAUNCH(k_collect, (unsigned)((s->batch + 255) / 256), 256, 0, st, s->sys, (int)s->batch, iterations, function_evaluations, converged, diverged);
+    return PHB200_OK;
+}
+
+int phb200_solver_stats(const phb200_solver* s, int64_t* passes_enqueued, int64_t* launches) {
+    PHB_ARG(s, "null solver");
+    if (passes_enqueued) *passes_enqueued = s->passes;
+    if (launches) *launches = (int64_t)(g_launches.load() - s->launches0);
+    return PHB200_OK;
+}
+
+int phb200_solver_profile(phb200_solver* s, int enable) {
+    PHB_ARG(s, "null solver");
+    s->prof = enable ? 1 : 0;
+    return PHB200_OK;
+}
+
+int phb200_solver_profile_read(phb200_solver* s, double* ms_per_slot, int64_t* count_per_slot, int max_slots, int* n_slots) {
+    PHB_ARG(s && ms_per_slot && count_per_slot && n_slots && max_slots > 0, "null argument");
+    for (int k = 0; k < max_slots; ++k) { ms_per_slot[k] = 0.0; count_per_slot[k] = 0; }
+    int used = 0;
+    for (size_t k = 0; k < s->prof_slots->size(); ++k) {
+        cudaEvent_t a = (*s->prof_events)[2 * k], b = (*s->prof_events)[2 * k + 1];
+        PHB_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        PHB_CUDA(cudaEventElapsedTime(&ms, a, b));
+        const int slot = (*s->prof_slots)[k];
+        if (slot < max_slots) {
+            ms_per_slot[slot] += ms;
+            count_per_slot[slot] += 1;
+            if (slot + 1 > used) used = slot + 1;
+        }
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    s->prof_events->clear();
+    s->prof_slots->clear();
+    *n_slots = used;
+    return PHB200_OK;
+}
+
+int phb200_solver_destroy(phb200_solver* s) {
+    if (!s) return PHB200_OK;
+    if (s->prof_events) {
+        for (cudaEvent_t e : *s->prof_events) cudaEventDestroy(e);
+        delete s->prof_events;
+        delete s->prof_slots;
+    }
+    if (s->sys) cudaFree(s->sys);
+    if (s->glob) cudaFree(s->glob);
+    if (s->partials) cudaFree(s->partials);
+    if (s->tickets) cudaFree(s->tickets);
+    if (s->h_flag) cudaFreeHost(s->h_flag);
+    if (s->ev[0]) cudaEventDestroy(s->ev[0]);
+    if (s->ev[1]) cudaEventDestroy(s->ev[1]);
+    delete s;
+    return PHB200_OK;
+}
+
+}  // extern "C"

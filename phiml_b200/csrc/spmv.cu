@@ -1,0 +1,359 @@
+// Matrix handles, stand-alone products, stencil detection and device-side CSR assembly.
+#include "spmv_kernels.cuh"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
+#include <vector>
+#include <mutex>
+#include <unordered_map>
+
+namespace phb {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int occupancy_of(const void* kernel) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) return it->second;
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, 0) != cudaSuccess || v < 1) {
+        cudaGetLastError();
+        v = 4;
+    }
+    cache[kernel] = v;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------- CSR analysis
+__global__ void k_csr_block_max(const int32_t* __restrict__ rowptr, int64_t n_rows, int* out) {
+    int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r0 = chunk * kCsrRows;
+    int v = 0;
+    if (r0 < n_rows) {
+        int64_t r1 = min(n_rows, r0 + kCsrRows);
+        v = rowptr[r1] - rowptr[r0];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_down_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+int csr_analyse(const phb200_matrix* m, cudaStream_t stream) {
+    if (m->analysed) return PHB200_OK;
+    int* d = nullptr;
+    PHB_CUDA(cudaMallocAsync(&d, sizeof(int), stream));
+    PHB_CUDA(cudaMemsetAsync(d, 0, sizeof(int), stream));
+    int64_t chunks = (m->csr.n_rows + kCsrRows - 1) / kCsrRows;
+    PHB_LAUNCH(k_csr_block_max, (unsigned)((chunks + 255) / 256), 256, 0, stream, m->csr.rowptr, m->csr.n_rows, d);
+    int h = 0;
+    PHB_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    PHB_CUDA(cudaFreeAsync(d, stream));
+    m->max_block_nnz = h;
+    m->analysed = 1;
+    return PHB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- transposed / COO
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_spmv_csr_scatter(CsrView A, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy) {
+    // arrays describe A^T: entry (r, c, v) of the arrays contributes v * x[r] to y[c]
+    const int b = blockIdx.y;
+    const T* __restrict__ val = (const T*)A.val;
+    for (int64_t r = (int64_t)blockIdx.x * kBlock + threadIdx.x; r < A.n_rows; r += (int64_t)gridDim.x * kBlock) {
+        const T xv = X[(int64_t)b * ldx + r];
+        for (int k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k) atomicAdd(&Y[(int64_t)b * ldy + A.col[k]], val[k] * xv);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_spmv_coo(const int64_t* __restrict__ row, const int64_t* __restrict__ col, const T* __restrict__ val,
+                                                     int64_t nnz, const T* __restrict__ X, int64_t ldx, T* __restrict__ Y, int64_t ldy) {
+    const int b = blockIdx.y;
+    for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * kBlock)
+        atomicAdd(&Y[(int64_t)b * ldy + row[k]], val[k] * X[(int64_t)b * ldx + col[k]]);
+}
+
+// ---------------------------------------------------------------------------------------------- stencil <-> CSR
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_stencil_verify(StencilDesc st, CsrView A, int* mismatch) {
+    const T* __restrict__ val = (const T*)A.val;
+    const int64_t ny = st.dims[1], nz = st.dims[2];
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+        int k = A.rowptr[i];
+        const int k1 = A.rowptr[i + 1];
+        bool ok = true;
+        for (int p = 0; p < st.npts; ++p) {
+            int64_t jx = ix + st.off[p][0], jy = iy + st.off[p][1], jz = iz + st.off[p][2];
+            if (jx < 0 || jx >= st.dims[0] || jy < 0 || jy >= ny || jz < 0 || jz >= nz) continue;
+            int64_t j = (jx * ny + jy) * nz + jz;
+            if (k >= k1 || A.col[k] != (int32_t)j || val[k] != (T)st.coef[p]) { ok = false; break; }
+            ++k;
+        }
+        if (!ok || k != k1) *mismatch = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_stencil_count(StencilDesc st, int64_t n, int32_t* __restrict__ counts) {
+    const int64_t ny = st.dims[1], nz = st.dims[2];
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i <= n; i += (int64_t)gridDim.x * kBlock) {
+        int c = 0;
+        if (i < n) {
+            const int64_t iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+            for (int p = 0; p < st.npts; ++p) {
+                int64_t jx = ix + st.off[p][0], jy = iy + st.off[p][1], jz = iz + st.off[p][2];
+                c += !(jx < 0 || jx >= st.dims[0] || jy < 0 || jy >= ny || jz < 0 || jz >= nz);
+            }
+        }
+        counts[i] = c;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_stencil_fill(StencilDesc st, int64_t n, const int32_t* __restrict__ rowptr,
+                                                         int32_t* __restrict__ col, T* __restrict__ val) {
+    const int64_t ny = st.dims[1], nz = st.dims[2];
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+        int k = rowptr[i];
+        for (int p = 0; p < st.npts; ++p) {
+            int64_t jx = ix + st.off[p][0], jy = iy + st.off[p][1], jz = iz + st.off[p][2];
+            if (jx < 0 || jx >= st.dims[0] || jy < 0 || jy >= ny || jz < 0 || jz >= nz) continue;
+            col[k] = (int32_t)((jx * ny + jy) * nz + jz);
+            val[k] = (T)st.coef[p];
+            ++k;
+        }
+    }
+}
+
+static int make_stencil(phb200_matrix** out, int rank, const int64_t* grid, int npts, const int32_t* offsets, const double* coeffs, int dtype) {
+    PHB_ARG(out && grid && offsets && coeffs, "null argument");
+    PHB_ARG(rank >= 1 && rank <= 3, "stencil rank must be 1..3, got %d", rank);
+    PHB_ARG(npts >= 1 && npts <= kMaxStencil, "stencil needs 1..%d points, got %d", kMaxStencil, npts);
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    phb200_matrix* m = new phb200_matrix();
+    memset(m, 0, sizeof(*m));
+    m->kind = PHB200_MAT_STENCIL;
+    m->dtype = dtype;
+    StencilDesc& st = m->st;
+    st.rank = rank;
+    st.npts = npts;
+    for (int d = 0; d < 3; ++d) st.dims[d] = 1;
+    for (int d = 0; d < rank; ++d) {
+        if (grid[d] < 1) { delete m; set_error("grid size must be positive"); return PHB200_ERR_ARG; }
+        st.dims[3 - rank + d] = grid[d];
+    }
+    struct Pt { int o[3]; double c; int64_t flat; };
+    std::vector<Pt> pts(npts);
+    for (int p = 0; p < npts; ++p) {
+        pts[p].o[0] = pts[p].o[1] = pts[p].o[2] = 0;
+        for (int d = 0; d < rank; ++d) pts[p].o[3 - rank + d] = offsets[p * rank + d];
+        pts[p].c = coeffs[p];
+        pts[p].flat = ((int64_t)pts[p].o[0] * st.dims[1] + pts[p].o[1]) * st.dims[2] + pts[p].o[2];
+    }
+    std::sort(pts.begin(), pts.end(), [](const Pt& a, const Pt& b) { return a.flat < b.flat; });
+    st.diag = -1;
+    for (int p = 0; p < npts; ++p) {
+        if (p > 0 && pts[p].flat == pts[p - 1].flat) { delete m; set_error("duplicate stencil offsets"); return PHB200_ERR_ARG; }
+        for (int d = 0; d < 3; ++d) {
+            st.off[p][d] = pts[p].o[d];
+        }
+        st.coef[p] = pts[p].c;
+        if (pts[p].o[0] == 0 && pts[p].o[1] == 0 && pts[p].o[2] == 0) st.diag = p;
+    }
+    m->n_rows = m->n_cols = st.dims[0] * st.dims[1] * st.dims[2];
+    m->nnz = -1;
+    *out = m;
+    return PHB200_OK;
+}
+
+}  // namespace phb
+
+using namespace phb;
+
+extern "C" {
+
+int phb200_version(void) { return PHB200_VERSION; }
+const char* phb200_last_error(void) { return g_err; }
+int64_t phb200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int phb200_matrix_csr(phb200_matrix** out, const int32_t* rowptr, const int32_t* col, const void* val,
+                      int64_t n_rows, int64_t n_cols, int64_t nnz, int dtype, int transposed) {
+    PHB_ARG(out && rowptr && (nnz == 0 || (col && val)), "null argument");
+    PHB_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && nnz < (1ll << 31) && n_rows < (1ll << 31) && n_cols < (1ll << 31), "CSR sizes must fit int32 (nnz=%lld)", (long long)nnz);
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    phb200_matrix* m = new phb200_matrix();
+    memset(m, 0, sizeof(*m));
+    m->kind = PHB200_MAT_CSR;
+    m->dtype = dtype;
+    m->transposed = transposed ? 1 : 0;
+    m->csr = CsrView{rowptr, col, val, n_rows, n_cols, nnz};
+    // logical shape of A (not of the stored arrays)
+    m->n_rows = transposed ? n_cols : n_rows;
+    m->n_cols = transposed ? n_rows : n_cols;
+    m->nnz = nnz;
+    *out = m;
+    return PHB200_OK;
+}
+
+int phb200_matrix_stencil(phb200_matrix** out, int rank, const int64_t* grid, int npts, const int32_t* offsets, const double* coeffs, int dtype) {
+    return make_stencil(out, rank, grid, npts, offsets, coeffs, dtype);
+}
+
+int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int rank, const int64_t* grid, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(out && csr && grid, "null argument");
+    PHB_ARG(csr->kind == PHB200_MAT_CSR && !csr->transposed, "stencil detection needs a plain CSR matrix");
+    PHB_ARG(rank >= 1 && rank <= 3, "rank must be 1..3");
+    int64_t dims[3] = {1, 1, 1};
+    int64_t n = 1;
+    for (int d = 0; d < rank; ++d) { dims[3 - rank + d] = grid[d]; n *= grid[d]; }
+    if (n != csr->csr.n_rows || n != csr->csr.n_cols) { set_error("grid volume %lld != matrix size %lld", (long long)n, (long long)csr->csr.n_rows); return PHB200_ERR_NOT_STENCIL; }
+    // candidate stencil = the row of the centre cell
+    const int64_t c[3] = {dims[0] / 2, dims[1] / 2, dims[2] / 2};
+    const int64_t ic = (c[0] * dims[1] + c[1]) * dims[2] + c[2];
+    int32_t rp[2];
+    PHB_CUDA(cudaMemcpyAsync(rp, csr->csr.rowptr + ic, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    const int npts = rp[1] - rp[0];
+    if (npts < 1 || npts > kMaxStencil) { set_error("centre row has %d entries", npts); return PHB200_ERR_NOT_STENCIL; }
+    int32_t cols[kMaxStencil];
+    double vals64[kMaxStencil];
+    float vals32[kMaxStencil];
+    PHB_CUDA(cudaMemcpyAsync(cols, csr->csr.col + rp[0], npts * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (csr->dtype == PHB200_F32) PHB_CUDA(cudaMemcpyAsync(vals32, (const float*)csr->csr.val + rp[0], npts * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    else PHB_CUDA(cudaMemcpyAsync(vals64, (const double*)csr->csr.val + rp[0], npts * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    int32_t offs[kMaxStencil * 3];
+    double coef[kMaxStencil];
+    for (int p = 0; p < npts; ++p) {
+        int64_t j = cols[p];
+        int64_t jz = j % dims[2], jy = (j / dims[2]) % dims[1], jx = j / (dims[2] * dims[1]);
+        const int64_t o3[3] = {jx - c[0], jy - c[1], jz - c[2]};
+        for (int d = 0; d < rank; ++d) offs[p * rank + d] = (int32_t)o3[3 - rank + d];
+        coef[p] = csr->dtype == PHB200_F32 ? (double)vals32[p] : vals64[p];
+    }
+    phb200_matrix* cand = nullptr;
+    int r = make_stencil(&cand, rank, grid, npts, offs, coef, csr->dtype);
+    if (r != PHB200_OK) return PHB200_ERR_NOT_STENCIL;
+    int* d_flag = nullptr;
+    PHB_CUDA(cudaMallocAsync(&d_flag, sizeof(int), stream));
+    PHB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
+    const unsigned gridx = (unsigned)grid_x((n + kBlock - 1) / kBlock, 1);
+    if (csr->dtype == PHB200_F32) PHB_LAUNCH(k_stencil_verify<float>, gridx, kBlock, 0, stream, cand->st, csr->csr, d_flag);
+    else PHB_LAUNCH(k_stencil_verify<double>, gridx, kBlock, 0, stream, cand->st, csr->csr, d_flag);
+    int h = 0;
+    PHB_CUDA(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    PHB_CUDA(cudaFreeAsync(d_flag, stream));
+    if (h) { delete cand; set_error("matrix is not a constant-coefficient ZERO-boundary stencil on this grid"); return PHB200_ERR_NOT_STENCIL; }
+    cand->nnz = csr->nnz;
+    *out = cand;
+    return PHB200_OK;
+}
+
+int phb200_stencil_nnz(const phb200_matrix* m, int64_t* nnz) {
+    PHB_ARG(m && nnz && m->kind == PHB200_MAT_STENCIL, "need a stencil matrix");
+    const StencilDesc& st = m->st;
+    int64_t total = 0;
+    for (int p = 0; p < st.npts; ++p) {
+        int64_t cnt = 1;
+        for (int d = 0; d < 3; ++d) {
+            int64_t a = st.off[p][d] < 0 ? -st.off[p][d] : st.off[p][d];
+            cnt *= (st.dims[d] - a > 0 ? st.dims[d] - a : 0);
+        }
+        total += cnt;
+    }
+    *nnz = total;
+    return PHB200_OK;
+}
+
+int phb200_stencil_to_csr(const phb200_matrix* m, int32_t* rowptr, int32_t* col, void* val, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(m && rowptr && col && val && m->kind == PHB200_MAT_STENCIL, "need a stencil matrix and output arrays");
+    int64_t nnz = 0;
+    PHB_TRY(phb200_stencil_nnz(m, &nnz));
+    PHB_ARG(nnz < (1ll << 31) && m->n_rows < (1ll << 31) - 1, "CSR with %lld entries does not fit int32 indices", (long long)nnz);
+    const int64_t n = m->n_rows;
+    const unsigned gridx = (unsigned)grid_x((n + kBlock) / kBlock, 1);
+    int32_t* counts = nullptr;
+    PHB_CUDA(cudaMallocAsync(&counts, (n + 1) * sizeof(int32_t), stream));
+    PHB_LAUNCH(k_stencil_count, gridx, kBlock, 0, stream, m->st, n, counts);
+    size_t tmp_bytes = 0;
+    PHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, rowptr, (int)(n + 1), stream));
+    void* tmp = nullptr;
+    PHB_CUDA(cudaMallocAsync(&tmp, tmp_bytes, stream));
+    PHB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, rowptr, (int)(n + 1), stream));
+    g_launches.fetch_add(2);
+    if (m->dtype == PHB200_F32) PHB_LAUNCH(k_stencil_fill<float>, gridx, kBlock, 0, stream, m->st, n, rowptr, col, (float*)val);
+    else PHB_LAUNCH(k_stencil_fill<double>, gridx, kBlock, 0, stream, m->st, n, rowptr, col, (double*)val);
+    PHB_CUDA(cudaFreeAsync(tmp, stream));
+    PHB_CUDA(cudaFreeAsync(counts, stream));
+    return PHB200_OK;
+}
+
+int phb200_matrix_info(const phb200_matrix* m, int* kind, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, int* dtype) {
+    PHB_ARG(m, "null matrix");
+    if (kind) *kind = m->kind;
+    if (n_rows) *n_rows = m->n_rows;
+    if (n_cols) *n_cols = m->n_cols;
+    if (dtype) *dtype = m->dtype;
+    if (nnz) {
+        if (m->kind == PHB200_MAT_STENCIL) PHB_TRY(phb200_stencil_nnz(m, nnz));
+        else *nnz = m->nnz;
+    }
+    return PHB200_OK;
+}
+
+int phb200_matrix_destroy(phb200_matrix* m) {
+    delete m;
+    return PHB200_OK;
+}
+
+int phb200_spmv(const phb200_matrix* A, const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(A && X && Y, "null argument");
+    PHB_ARG(batch >= 0 && batch <= 65535, "batch must be <= 65535, got %lld", (long long)batch);
+    PHB_ARG(ldx >= A->n_cols && ldy >= A->n_rows, "leading dimensions too small");
+    if (batch == 0 || A->n_rows == 0) return PHB200_OK;
+    if (A->kind == PHB200_MAT_CSR && A->transposed) {
+        const size_t w = A->dtype == PHB200_F32 ? 4 : 8;
+        PHB_CUDA(cudaMemset2DAsync(Y, ldy * w, 0, A->n_rows * w, batch, stream));
+        dim3 grid((unsigned)grid_x((A->csr.n_rows + kBlock - 1) / kBlock, batch), (unsigned)batch);
+        if (A->dtype == PHB200_F32) PHB_LAUNCH(k_spmv_csr_scatter<float>, grid, kBlock, 0, stream, A->csr, (const float*)X, ldx, (float*)Y, ldy);
+        else PHB_LAUNCH(k_spmv_csr_scatter<double>, grid, kBlock, 0, stream, A->csr, (const double*)X, ldx, (double*)Y, ldy);
+        return PHB200_OK;
+    }
+    if (A->dtype == PHB200_F32) {
+        NoEpi<float> epi{};
+        return launch_spmv<float>(A, (const float*)X, ldx, (float*)Y, ldy, (const float*)nullptr, (int)batch, epi, stream);
+    }
+    NoEpi<double> epi{};
+    return launch_spmv<double>(A, (const double*)X, ldx, (double*)Y, ldy, (const double*)nullptr, (int)batch, epi, stream);
+}
+
+int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int64_t nnz, int64_t n_rows, int64_t n_cols,
+                    const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, int dtype, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG((nnz == 0 || (row && col && val)) && X && Y, "null argument");
+    PHB_ARG(batch >= 0 && batch <= 65535, "batch must be <= 65535");
+    PHB_ARG(ldx >= n_cols && ldy >= n_rows, "leading dimensions too small");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    if (batch == 0 || nnz == 0) return PHB200_OK;
+    dim3 grid((unsigned)grid_x((nnz + kBlock - 1) / kBlock, batch), (unsigned)batch);
+    if (dtype == PHB200_F32) PHB_LAUNCH(k_spmv_coo<float>, grid, kBlock, 0, stream, row, col, (const float*)val, nnz, (const float*)X, ldx, (float*)Y, ldy);
+    else PHB_LAUNCH(k_spmv_coo<double>, grid, kBlock, 0, stream, row, col, (const double*)val, nnz, (const double*)X, ldx, (double*)Y, ldy);
+    return PHB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""
+Device matrices for the phb200 engine.
+
+Natives at the boundary are what the reference's torch backend produces
+(phiml/backend/torch/_torch_backend.py:857-896): ``torch.sparse_csr_tensor`` (crow int32/int64, col, values),
+``torch.sparse_csc_tensor`` (backward pass: CSR arrays of A^T) and ``torch.sparse_coo_tensor`` (int64 indices).
+``as_matrix`` wraps them without copying values; a matrix that turns out to be a constant-coefficient 5/7-point
+(or any <=16 point) ZERO-boundary stencil — what ``matrix_from_function`` emits for Laplace / central differences —
+is additionally recognised on the device and then runs through the stencil-specialised kernels.
+"""
+import ctypes
+from collections import OrderedDict
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _engine as E
+
+
+class Matrix:
+    """Owner of a ``phb200_matrix`` handle; keeps the tensors it views alive."""
+
+    def __init__(self, handle, dtype: torch.dtype, shape: Tuple[int, int], keep, kind: str, device):
+        self._h = handle
+        self.dtype = dtype
+        self.shape = tuple(int(s) for s in shape)
+        self._keep = keep
+        self.kind = kind          # 'csr' | 'csc' | 'stencil'
+        self.device = device
+        self.stencil: Optional['Matrix'] = None   # detected stencil twin of a CSR matrix
+        self._stencil_checked = False
+        self.grid = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h is not None and E._lib is not None:
+                E._lib.phb200_matrix_destroy(self._h)
+        except Exception:
+            pass
+        self._h = None
+
+    # --- constructors ---
+    @staticmethod
+    def csr(rowptr: torch.Tensor, col: torch.Tensor, values: torch.Tensor, shape, transposed=False) -> 'Matrix':
+        E.require_cuda(rowptr, col, values)
+        rowptr = rowptr.to(torch.int32).contiguous()
+        col = col.to(torch.int32).contiguous()
+        values = values.contiguous()
+        rows_stored = shape[1] if transposed else shape[0]
+        cols_stored = shape[0] if transposed else shape[1]
+        assert rowptr.numel() == rows_stored + 1, f"row pointer length {rowptr.numel()} does not match {rows_stored} rows"
+        h = ctypes.c_void_p()
+        E.check(E.lib().phb200_matrix_csr(ctypes.byref(h), E.ptr(rowptr), E.ptr(col), E.ptr(values), rows_stored, cols_stored,
+                                          values.numel(), E.dtype_code(values.dtype), 1 if transposed else 0))
+        m = Matrix(h, values.dtype, shape, (rowptr, col, values), 'csc' if transposed else 'csr', values.device)
+        m.rowptr, m.col, m.values = rowptr, col, values
+        return m
+
+    @staticmethod
+    def stencil_matrix(grid: Sequence[int], offsets: Sequence[Sequence[int]], coeffs: Sequence[float], dtype: torch.dtype, device='cuda') -> 'Matrix':
+        """Constant-coefficient stencil, ZERO boundaries.  ``offsets[p]`` = source - output cell, one int per grid dim."""
+        rank = len(grid)
+        g = (ctypes.c_int64 * rank)(*[int(v) for v in grid])
+        flat = [int(o) for off in offsets for o in off]
+        o = (ctypes.c_int32 * len(flat))(*flat)
+        c = (ctypes.c_double * len(coeffs))(*[float(v) for v in coeffs])
+        h = ctypes.c_void_p()
+        E.check(E.lib().phb200_matrix_stencil(ctypes.byref(h), rank, g, len(coeffs), o, c, E.dtype_code(dtype)))
+        n = int(np.prod(grid))
+        m = Matrix(h, dtype, (n, n), (), 'stencil', torch.device(device))
+        m.grid = tuple(int(v) for v in grid)
+        return m
+
+    # --- stencil recognition ---
+    def detect_stencil(self, grid: Optional[Sequence[int]] = None) -> Optional['Matrix']:
+        """Returns the stencil twin if every row matches bit for bit, else None.  ``grid`` defaults to an inference
+        from the neighbour offsets of a few probe rows (nearest-neighbour stencils on C-ordered grids)."""
+        if self.kind != 'csr' or self.shape[0] != self.shape[1] or self.shape[0] == 0:
+            return None
+        if self._stencil_checked and grid is None:
+            return self.stencil
+        if grid is None:
+            grid = _infer_grid(self)
+            self._stencil_checked = True
+        if grid is None:
+            return None
+        g = (ctypes.c_int64 * len(grid))(*[int(v) for v in grid])
+        h = ctypes.c_void_p()
+        try:
+            E.check(E.lib().phb200_stencil_from_csr(ctypes.byref(h), self._h, len(grid), g, E.stream_ptr(self.device)))
+        except E.NotAStencil:
+            return None
+        st = Matrix(h, self.dtype, self.shape, (), 'stencil', self.device)
+        st.grid = tuple(int(v) for v in grid)
+        self.stencil = st
+        return st
+
+    def nnz(self) -> int:
+        n = ctypes.c_int64()
+        E.check(E.lib().phb200_matrix_info(self._h, None, None, None, ctypes.byref(n), None))
+        return int(n.value)
+
+    def to_csr(self) -> 'Matrix':
+        """Stencil -> canonical CSR assembled on the device (byte-identical to the reference's compress())."""
+        assert self.kind == 'stencil'
+        n = self.shape[0]
+        nnz = self.nnz()
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=self.device)
+        col = torch.empty(nnz, dtype=torch.int32, device=self.device)
+        val = torch.empty(nnz, dtype=self.dtype, device=self.device)
+        E.check(E.lib().phb200_stencil_to_csr(self._h, E.ptr(rowptr), E.ptr(col), E.ptr(val), E.stream_ptr(self.device)))
+        return Matrix.csr(rowptr, col, val, self.shape)
+
+    # --- product ---
+    def matvec(self, x: torch.Tensor, use_stencil=True) -> torch.Tensor:
+        """(batch, cols) -> (batch, rows)"""
+        E.require_cuda(x)
+        assert x.dim() == 2 and x.shape[1] == self.shape[1], f"expected (batch, {self.shape[1]}), got {tuple(x.shape)}"
+        x = x.to(self.dtype).contiguous()
+        m = self.stencil if (use_stencil and self.stencil is not None) else self
+        y = torch.empty((x.shape[0], self.shape[0]), dtype=self.dtype, device=x.device)
+        for b0 in range(0, x.shape[0], 65535):
+            xb, yb = x[b0:b0 + 65535], y[b0:b0 + 65535]
+            E.check(E.lib().phb200_spmv(m._h, E.ptr(xb), E.ptr(yb), xb.shape[0], x.shape[1], y.shape[1], E.stream_ptr(x.device)))
+        return y
+
+
+def _infer_grid(m: Matrix) -> Optional[Tuple[int, ...]]:
+    """Grid shape from the positive neighbour offsets {1, nz, ny*nz} seen in a few rows around the middle."""
+    n = m.shape[0]
+    probes = sorted({n // 2, n // 3, min(n - 1, n // 2 + 1), 0})
+    rp = m.rowptr[torch.tensor([p for r in probes for p in (r, r + 1)], device=m.device)].cpu().numpy().reshape(-1, 2)
+    offs = set()
+    for r, (a, b) in zip(probes, rp):
+        if b - a > E_MAX_STENCIL:
+            return None
+        cols = m.col[a:b].cpu().numpy().astype(np.int64)
+        offs.update(int(c - r) for c in cols if c > r)
+    offs = sorted(offs)
+    if len(offs) == 0:
+        return (n,)
+    if len(offs) > 3 or offs[0] != 1:
+        return None
+    dims = []
+    prev = 1
+    for o in offs[1:]:
+        if o % prev != 0:
+            return None
+        dims.append(o // prev)
+        prev = o
+    if n % prev != 0:
+        return None
+    grid = tuple([n // prev] + dims[::-1])
+    return grid if int(np.prod(grid)) == n else None
+
+
+E_MAX_STENCIL = 16
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# natives -> Matrix, with a tiny identity cache so that repeated products / solves with one native do not repeat the
+# analysis (the cache holds references, so addresses cannot be recycled under it; in-place edits bump _version)
+# ----------------------------------------------------------------------------------------------------------------------
+
+_CACHE: 'OrderedDict[tuple, Matrix]' = OrderedDict()
+_CACHE_SIZE = 4
+
+
+def _cache_key(kind, a, b, c, shape):
+    return (kind, a.data_ptr(), b.data_ptr(), c.data_ptr(), a._version, b._version, c._version, tuple(shape), c.dtype, c.numel())
+
+
+def clear_cache():
+    _CACHE.clear()
+
+
+def as_matrix(native, detect_stencil=True, grid=None) -> Matrix:
+    """torch sparse CSR / CSC / COO tensor (or Matrix) -> Matrix.  COO is converted to CSR once (sorted, duplicates summed)."""
+    if isinstance(native, Matrix):
+        return native
+    if not isinstance(native, torch.Tensor):
+        raise TypeError(f"phb200 needs a torch sparse matrix, got {type(native)}")
+    E.require_cuda(native)
+    shape = tuple(native.shape)
+    if native.layout == torch.sparse_csr:
+        comps = ('csr', native.crow_indices(), native.col_indices(), native.values())
+    elif native.layout == torch.sparse_csc:
+        comps = ('csc', native.ccol_indices(), native.row_indices(), native.values())
+    elif native.layout == torch.sparse_coo:
+        comps = ('coo', native._indices(), native._indices(), native._values())
+    else:
+        raise TypeError("dense matrices are not on the phb200 path")
+    key = _cache_key(*comps, shape)
+    hit = _CACHE.get(key)
+    if hit is not None:
+        _CACHE.move_to_end(key)
+        return hit
+    kind, a, b, v = comps
+    if kind == 'coo':
+        csr = native.coalesce().to_sparse_csr()      # one-off format conversion at set-up, not on the hot path
+        m = Matrix.csr(csr.crow_indices(), csr.col_indices(), csr.values(), shape)
+        keep = (native, csr)
+    else:
+        m = Matrix.csr(a, b, v, shape, transposed=(kind == 'csc'))
+        keep = (native,)
+    m._keep = m._keep + keep
+    if detect_stencil and m.kind == 'csr':
+        m.detect_stencil(grid)
+    _CACHE[key] = m
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return m
+
+
+def plain_csr(m: Matrix) -> Matrix:
+    """CSC-native (arrays of A^T) -> CSR of A, via one transposition on the device (set-up cost, cached on the matrix)."""
+    if m.kind != 'csc':
+        return m
+    t = getattr(m, '_plain', None)
+    if t is None:
+        at = torch.sparse_csr_tensor(m.rowptr, m.col, m.values, (m.shape[1], m.shape[0]))
+        a = at.to_sparse_csc()                      # CSC of A^T == CSR of A
+        t = Matrix.csr(a.ccol_indices(), a.row_indices(), a.values(), m.shape)
+        t.detect_stencil()
+        m._plain = t
+    return t

