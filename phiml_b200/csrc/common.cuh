@@ -39,14 +39,17 @@ extern std::atomic<long long> g_launches;
         if (_r != PHB200_OK) return _r;                                                         \
     } while (0)
 
-// launch + count + check
+// launch + count + check.  PHB200_DEBUG_SYNC=1 synchronises after every launch and names the kernel that faulted.
+bool debug_sync();
 #define PHB_LAUNCH(kernel, grid, block, smem, stream, ...)                                      \
     do {                                                                                        \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                             \
         phb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
         cudaError_t _e = cudaPeekAtLastError();                                                 \
+        if (_e == cudaSuccess && phb::debug_sync()) _e = cudaStreamSynchronize(stream);         \
         if (_e != cudaSuccess) {                                                                \
-            phb::set_error("launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            phb::set_error("kernel %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            if (phb::debug_sync()) fprintf(stderr, "[phb200] kernel %s failed: %s (%s:%d)\n", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
             return PHB200_ERR_CUDA;                                                             \
         }                                                                                       \
     } while (0)
@@ -90,6 +93,13 @@ struct Reduce {
 template <typename T> struct Vec;
 template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
 template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+
+// separately rounded multiply / add (never contracted into an FMA): keeps row sums bit-identical to scipy's csr_matvec
+// and the vector updates on the reference's rounding sequence
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
 template <typename T> __device__ __forceinline__ T safe_div(T a, T b) { return b == T(0) ? T(0) : a / b; }
 
@@ -207,7 +217,12 @@ __device__ __forceinline__ void progress_check(Sys* sys, Glob* g, int batch, boo
         s->go = go;
         any |= go;
     }
-    any = __syncthreads_or(any);
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (any) atomicOr(&s_any, 1);
+    __syncthreads();
+    any = s_any;
     if (threadIdx.x == 0) {
         g->any_go = any;
         g->checks = g->checks + 1;

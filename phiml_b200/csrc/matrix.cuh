@@ -56,9 +56,8 @@ __device__ __forceinline__ T stencil_row(const StencilDesc& st, const T* __restr
         if (jx < 0 || jx >= st.dims[0] || jy < 0 || jy >= ny || jz < 0 || jz >= nz) continue;
         int64_t j = (jx * ny + jy) * nz + jz;
         T xv = x[j];
-        if (PRESCALE) xv = xv * scale[j];
-        T prod = (T)st.coef[p] * xv;
-        sum = sum + prod;
+        if (PRESCALE) xv = mul_rn(xv, scale[j]);
+        sum = add_rn(sum, mul_rn((T)st.coef[p], xv));
     }
     (void)i;
     return sum;

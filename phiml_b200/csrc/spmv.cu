@@ -3,6 +3,7 @@
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <vector>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -10,6 +11,15 @@ namespace phb {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+bool debug_sync() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PHB200_DEBUG_SYNC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -5,11 +5,6 @@
 
 namespace phb {
 
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-
 // Epilogue protocol ------------------------------------------------------------------------------------------
 //   ND            number of fused dot products (0: no reduction, no tickets)
 //   GLOBAL        whether a batch-wide finaliser (progress check) follows the per-system one
