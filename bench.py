@@ -228,11 +228,17 @@ def run_ours(args):
     solver.advance(60)
     prof = solver.profile_read()
     solver.profile(False)
-    names = ["spmv+dot (q=A d, d.q, alpha)", "update (x,r, M^-1 r, r.s, beta, convergence test)", "direction (d = M^-1 r + beta d)"]
-    model_bytes = [2 * N * w, 7 * N * w, 4 * N * w] if args.format == 'stencil' else [8 * csr.values.numel() + 4 * (N + 1) + 2 * N * w, 7 * N * w, 4 * N * w]
+    if args.format == 'stencil':
+        # fused two-kernel iteration on the recognised stencil: bytes the kernels must move
+        names = ["k_star: d=M^-1 r+beta d, x+=alpha d, q=A d, d.q (fused direction + SpMV + dot)",
+                 "k_phase<CgResid>: r-=alpha q, M^-1 r, r.s, beta, convergence test"]
+        model_bytes = [6 * N * w, 3 * N * w]
+    else:
+        names = ["k_spmv_csr_stream: q=A d, d.q, alpha", "k_phase<CgUpdate>: x,r update, M^-1 r, r.s, beta, convergence test", "k_phase<CgDirection>: d = M^-1 r + beta d"]
+        model_bytes = [8 * csr.values.numel() + 4 * (N + 1) + 2 * N * w, 7 * N * w, 4 * N * w]
     peak, peak_src = measured_peak()
     kernels = []
-    for k, (tot_ms, cnt) in enumerate(prof[:3]):
+    for k, (tot_ms, cnt) in enumerate(prof[:len(names)]):
         avg = tot_ms / max(cnt, 1)
         kernels.append({"kernel": names[k], "avg_ms": avg, "bytes": model_bytes[k], "gbs": model_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else None})
     dom = max(range(len(kernels)), key=lambda k: kernels[k]['avg_ms']) if kernels else None
@@ -242,9 +248,11 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": kd['kernel'], "achieved": kd['gbs'], "peak": peak, "unit": "GB/s", "frac": kd['gbs'] / peak,
                     "traffic": None, "peak_source": peak_src, "share_of_step": kd['avg_ms'] / sum(k_['avg_ms'] for k_ in kernels),
                     "kernels": kernels}
+    its_per_s = args.steps / (ms * 1e-3)
+    survey_bytes = 13 * N * w if args.format == 'stencil' else 8 * csr.values.numel() + 4 * (N + 1) + 13 * N * w   # SURVEY.md §8(d) canonical model
     iter_bytes = sum(model_bytes)
-    iteration = {"model_bytes": iter_bytes, "achieved_gbs": iter_bytes * (args.steps / (ms * 1e-3)) / 1e9,
-                 "frac_of_peak": iter_bytes * (args.steps / (ms * 1e-3)) / 1e9 / peak}
+    iteration = {"bytes_moved_by_design": iter_bytes, "achieved_gbs": iter_bytes * its_per_s / 1e9, "frac_of_peak": iter_bytes * its_per_s / 1e9 / peak,
+                 "survey_model_bytes": survey_bytes, "survey_model_gbs": survey_bytes * its_per_s / 1e9, "survey_model_frac_of_peak": survey_bytes * its_per_s / 1e9 / peak}
 
     # ---- end to end through the Backend-level call: pinned host y/x0 -> device, solve to rel_tol 1e-5, x -> host
     e2e = None
@@ -255,6 +263,12 @@ def run_ours(args):
         x_host = torch.empty((1, N), dtype=torch.float32).pin_memory()
         backend = pb.B200Backend(dev)
         e2e_its, e2e_s = 0, 0.0
+        parts = {"h2d": 0.0, "setup": 0.0, "solve": 0.0, "d2h": 0.0}
+
+        def tick():
+            torch.cuda.synchronize(dev)
+            return time.perf_counter()
+
         for rep in range(3):
             pb.clear_cache()
             torch.cuda.synchronize(dev)
@@ -263,24 +277,30 @@ def run_ours(args):
             t0 = time.perf_counter()
             yd = y_host.to(dev, non_blocking=True)
             x0d = x0_host.to(dev, non_blocking=True)
+            t1 = tick()
             m = pb.as_matrix(native, detect_stencil=(args.format == 'stencil'))
             p = backend.compute_preconditioner('jacobi', m)
+            t2 = tick()
             res = backend.linear_solve('CG', m, yd, x0d, [1e-5], [0.0], np.array([[5000]]), p, None)
+            t3 = tick()
             x_host.copy_(res.x, non_blocking=True)
             its = int(res.iterations.cpu()[0])
             conv = bool(res.converged.cpu()[0])
             torch.cuda.synchronize(dev)
-            dt = time.perf_counter() - t0
+            t4 = time.perf_counter()
+            dt = t4 - t0
             assert conv, "e2e solve did not converge"
             if rep > 0:
                 e2e_its += its
                 e2e_s += dt
+                for k_, v_ in zip(parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                    parts[k_] += v_ / 2
         if world > 1:
             t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t[0])
         e2e = {"value": world * e2e_its / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * N * w, "d2h_bytes_per_step": N * w + 6,
-               "iterations_per_solve": e2e_its // 2, "seconds_per_solve": e2e_s / 2,
+               "iterations_per_solve": e2e_its // 2, "seconds_per_solve": e2e_s / 2, "seconds_breakdown": parts,
                "call": "B200Backend.linear_solve('CG', csr_native, y, x0, rtol, atol, max_iter, jacobi) incl. stencil recognition + Jacobi set-up; matrix native resident on the device"}
 
     cpu = None

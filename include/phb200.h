@@ -112,7 +112,9 @@ int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int
 
 /* inv_diag[i] = 1 / A[i,i]  (caller-owned, n_rows elements of A's dtype). */
 int phb200_jacobi_setup(const phb200_matrix* A, void* inv_diag, void* stream);
-int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n, int dtype);
+/* `constant` != 0 promises that all entries of inv_diag are equal (constant-diagonal stencils): the fused stencil
+ * kernels then use the scalar and never read the vector. */
+int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n, int dtype, int constant);
 
 /* Exact ILU(0) on the pattern of a CSR matrix with sorted columns and a full diagonal.
  * lu_val (nnz elements, caller-owned) receives L (strict lower, unit diagonal implied) and U (upper incl. diagonal)

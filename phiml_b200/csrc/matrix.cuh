@@ -13,6 +13,11 @@ struct CsrView {
 
 // Constant-coefficient stencil with ZERO boundaries on a C-ordered grid (dims[0] slowest).  Points are sorted by
 // flattened offset so that a row accumulates in the same order as the canonical (sorted-column) CSR row does.
+struct StarDesc {       // centre + nearest neighbours per axis; see stencil_fast.cuh
+    int64_t nx, ny, nz;
+    double c0, cxm, cxp, cym, cyp, czm, czp;
+};
+
 struct StencilDesc {
     int rank, npts;
     int64_t dims[3];        // padded with leading 1s: always (nx, ny, nz)
@@ -29,6 +34,8 @@ struct phb200_matrix {
     int transposed;         // CSR arrays describe A^T
     phb::CsrView csr;
     phb::StencilDesc st;
+    int is_star;            // stencil qualifies for the plane-marching kernels (star shape, nz % 4 == 0)
+    phb::StarDesc star;
     // lazily computed CSR analysis
     mutable int analysed;
     mutable int64_t max_block_nnz;   // max entries of any 256-row block

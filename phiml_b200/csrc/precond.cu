@@ -240,7 +240,7 @@ int phb200_jacobi_setup(const phb200_matrix* A, void* inv_diag, void* stream_) {
     return PHB200_OK;
 }
 
-int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n, int dtype) {
+int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n, int dtype, int constant) {
     PHB_ARG(out && inv_diag && n >= 0, "null argument");
     PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
     phb200_precond* p = new phb200_precond();
@@ -249,6 +249,18 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
     p->dtype = dtype;
     p->n = n;
     p->inv_diag = inv_diag;
+    if (constant && n > 0) {   // one element tells the whole diagonal (blocking copy, set-up only)
+        float f = 0.f;
+        double d = 0.0;
+        cudaError_t e = dtype == PHB200_F32 ? cudaMemcpy(&f, inv_diag, sizeof(float), cudaMemcpyDeviceToHost) : cudaMemcpy(&d, inv_diag, sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            delete p;
+            set_error("reading the constant inverse diagonal failed: %s", cudaGetErrorString(e));
+            return PHB200_ERR_CUDA;
+        }
+        p->is_const = 1;
+        p->const_inv = dtype == PHB200_F32 ? (double)f : d;
+    }
     *out = p;
     return PHB200_OK;
 }

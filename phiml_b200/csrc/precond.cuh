@@ -17,6 +17,8 @@ struct phb200_precond {
     int dtype;
     int64_t n;
     const void* inv_diag;  // Jacobi (caller-owned)
+    int is_const;          // Jacobi: every entry of inv_diag equals const_inv (constant-diagonal stencils)
+    double const_inv;
     // ILU(0): factors share A's pattern; values in lu_val (caller-owned); diag_pos[i] = index of (i,i) in row i
     phb::CsrView lu;
     int32_t* diag_pos;     // device, owned

@@ -3,9 +3,11 @@
 // include/phb200.h); the loop of Backend.while_loop (phiml/backend/_backend.py:697-735) runs on the device: every
 // kernel starts with a test of Glob::any_go, per-system `go` flags freeze finished systems, the host only polls a
 // pinned flag every few passes.
-#include "phase.cuh"
+#include "dispatch.cuh"
+#include "star_tma.cuh"
 #include "precond.cuh"
 #include <vector>
+#include <stdlib.h>
 
 namespace phb {
 
@@ -223,6 +225,55 @@ struct CgDirection : FBase {
     __device__ void finalize(int, const double (&)[1]) const {}
     __device__ void finalize_all() const {}
 };
+
+// r -= alpha q ; s = M r ; delta' = r.s — second half of the fused stencil iteration (x is updated by the next k_star
+// pass together with the direction).  PRE: 0 none, 1 Jacobi vector, 3 Jacobi constant.
+template <typename T, int PRE>
+struct CgResid : FBase {
+    static constexpr int NA = 3;   // r, q, w
+    static constexpr unsigned RMASK = PRE == 1 ? 0b111u : 0b011u, WMASK = 0b001u, SHARED = 0b100u;
+    static constexpr int ND = 1;
+    static constexpr bool GLOBAL = true;
+    const void* v[NA];
+    T cinv;
+    int rules;
+    struct Scal { T alpha; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA]}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[1], const Scal& sc) const {
+        e[0] = add_rn(e[0], -mul_rn(sc.alpha, e[1]));
+        const T s = PRE == 1 ? mul_rn(e[0], e[2]) : (PRE == 3 ? mul_rn(e[0], cinv) : e[0]);
+        acc[0] += (double)mul_rn(e[0], s);
+    }
+    __device__ void finalize(int b, const double (&tot)[1]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        const T dold = (T)s.s[S_DELTA], dnew = (T)tot[0];
+        s.s[S_DELTA] = (double)dnew;
+        s.s[S_BETA] = (double)safe_div(dnew, dold);
+        s.rsq = (double)dnew;
+    }
+    __device__ void finalize_all() const {
+        check_all<T>(*this, rules);
+        if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+    }
+};
+
+// x += alpha d_cur for every system (pending update of the fused iteration), then alpha = 0
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_flush_x(T* __restrict__ X, const T* __restrict__ buf_a, const T* __restrict__ buf_b,
+                                                    const Sys* __restrict__ sys, const Glob* __restrict__ glob, int64_t n, int64_t ld) {
+    const int b = blockIdx.y;
+    const T alpha = (T)sys[b].s[S_ALPHA];
+    if (alpha == T(0)) return;
+    const T* __restrict__ d = ((glob->pass & 1) ? buf_b : buf_a) + (int64_t)b * ld;
+    T* __restrict__ x = X + (int64_t)b * ld;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) x[i] = add_rn(x[i], mul_rn(alpha, d[i]));
+}
+
+__global__ void k_zero_alpha(Sys* sys, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) sys[b].s[S_ALPHA] = 0.0;
+}
 
 // ------------------------------------------------------------------------------------------------ torch refresh pass
 // x += alpha d only
@@ -577,6 +628,9 @@ struct phb200_solver {
     int prof_slot;             // index of the next kernel within the current pass
     std::vector<cudaEvent_t>* prof_events;   // pairs (start, stop)
     std::vector<int>* prof_slots;
+    // TMA descriptors of r and the two direction buffers (fused stencil CG); valid for the vectors bound by start()
+    CUtensorMap tm_r, tm_a, tm_b;
+    int tma_ok;
 };
 
 namespace phb {
@@ -613,7 +667,7 @@ static void fill_base(F& f, const phb200_solver* s, bool always, bool freeze) {
 
 static int vectors_needed(int method, int L, int pre) {
     switch (method) {
-        case PHB200_CG: return pre == PHB200_PRE_ILU ? 4 : 2;              // d, q (+ s, tmp)
+        case PHB200_CG: return pre == PHB200_PRE_ILU ? 4 : 3;              // d, q, d' (fused ping-pong) | d, q, s, tmp
         case PHB200_CG_ADAPTIVE: return 2;                                   // d, q
         case PHB200_CG_TORCH:
         case PHB200_CG_ADAPTIVE_TORCH: return 3;                             // d, q, t
@@ -714,6 +768,12 @@ struct Run {
     // ------------------------------------------------------------------------------------------ start
     int start(const T* Y, const T* X0, T* X, T* R, const T* rtol, const T* atol, const int32_t* max_iter) {
         const int method = s->method;
+        s->tma_ok = 0;
+        if (fused() && !getenv("PHB200_NO_TMA")) {
+            const StarDesc& sd = s->A->star;
+            s->tma_ok = make_star_tmap(&s->tm_r, R, s->dtype, sd, batch, ld) && make_star_tmap(&s->tm_a, vec(0), s->dtype, sd, batch, ld) &&
+                        make_star_tmap(&s->tm_b, vec(2), s->dtype, sd, batch, ld);
+        }
         if (X != X0) PHB_CUDA(cudaMemcpyAsync(X, X0, sizeof(T) * (size_t)batch * ld, cudaMemcpyDeviceToDevice, st));
         PHB_CUDA(cudaMemsetAsync(s->tickets, 0, sizeof(unsigned) * (size_t)batch, st));
         PHB_CUDA(cudaMemsetAsync(s->glob, 0, sizeof(Glob), st));
@@ -767,8 +827,72 @@ struct Run {
         return PHB200_OK;
     }
 
+    // ------------------------------------------------------------------------------------------ fused stencil CG
+    // Jacobi / un-preconditioned 'CG' on a star stencil: two kernels per iteration (SURVEY §8d counts 13 N w of traffic
+    // for the three-phase form; this form moves 9 N w, +2 N w with a non-constant diagonal).
+    bool fused() const {
+        return s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU;
+    }
+    template <int PRE>
+    int pass_cg_fused_t(T* X, T* R) {
+        T* q = vec(1);
+        CgDirLoad<T, PRE> loader;
+        loader.r = R; loader.buf_a = vec(0); loader.buf_b = vec(2); loader.xvec = X;
+        loader.w = PRE == 1 ? (const T*)s->M->inv_diag : nullptr;
+        loader.cinv = PRE == 3 ? (T)s->M->const_inv : T(1);
+        loader.ld = ld; loader.glob = s->glob;
+        CgDq<T> e;
+        fill_base(e, s, false, true);
+        e.d = nullptr; e.ld = ld;
+        prof_begin();
+        int r;
+        if constexpr (PRE != 1) {
+            if (s->tma_ok) r = launch_tma<PRE>(X, q, loader.cinv, e);
+            else r = launch_star<T, CgDirLoad<T, PRE>, CgDq<T>, true>(s->A->star, loader, q, ld, batch, e, st);
+        } else {
+            r = launch_star<T, CgDirLoad<T, PRE>, CgDq<T>, true>(s->A->star, loader, q, ld, batch, e, st);
+        }
+        prof_end();
+        PHB_TRY(r);
+        CgResid<T, PRE> u;
+        fill_base(u, s, false, true);
+        u.v[0] = R; u.v[1] = q; u.v[2] = PRE == 1 ? s->M->inv_diag : nullptr;
+        u.cinv = loader.cinv; u.rules = RULES_GENERIC;
+        return phase(u);
+    }
+    template <int PRE>
+    int launch_tma(T* X, T* q, T cinv, const CgDq<T>& e) {
+        auto kernel = k_star_cg_tma<T, PRE, CgDq<T>>;
+        constexpr int smem = star_tma_smem<T>();
+        static int occ = 0;
+        if (occ == 0) {
+            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
+            occ = v;
+        }
+        dim3 grid;
+        int xchunk;
+        star_grid(s->A->star, batch, occ, grid, xchunk);
+        PHB_LAUNCH(kernel, grid, kBlock, smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, e);
+        return PHB200_OK;
+    }
+    int pass_cg_fused(T* X, T* R) {
+        if (s->pre == PHB200_PRE_NONE) return pass_cg_fused_t<0>(X, R);
+        if (s->M->is_const) return pass_cg_fused_t<3>(X, R);
+        return pass_cg_fused_t<1>(X, R);
+    }
+    // applies the pending x += alpha d after a batch of fused passes (x is then the true iterate)
+    int flush_x(T* X) {
+        dim3 grid((unsigned)grid_x((n + kBlock * 4 - 1) / (kBlock * 4), batch, 8), (unsigned)batch);
+        PHB_LAUNCH(k_flush_x<T>, grid, kBlock, 0, st, X, (const T*)vec(0), (const T*)vec(2), (const Sys*)s->sys, (const Glob*)s->glob, n, ld);
+        PHB_LAUNCH(k_zero_alpha, (unsigned)((batch + 255) / 256), 256, 0, st, s->sys, batch);
+        return PHB200_OK;
+    }
+
     // ------------------------------------------------------------------------------------------ one pass
     int pass_cg(T* X, T* R, const T* Y, bool refresh) {
+        if (fused()) return pass_cg_fused(X, R);
         T* d = vec(0);
         T* q = vec(1);
         const bool fr = frozen();
@@ -972,6 +1096,10 @@ static int advance(phb200_solver* s, int n_iter, cudaStream_t st) {
         else r = make_run<double>(s, st).pass(refresh);
         if (r != PHB200_OK) return r;
         s->passes = pass_no;
+    }
+    if (n_iter > 0) {
+        if (s->dtype == PHB200_F32) { auto run = make_run<float>(s, st); if (run.fused()) PHB_TRY(run.flush_x((float*)s->X)); }
+        else { auto run = make_run<double>(s, st); if (run.fused()) PHB_TRY(run.flush_x((double*)s->X)); }
     }
     return PHB200_OK;
 }

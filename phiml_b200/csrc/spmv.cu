@@ -1,5 +1,5 @@
 // Matrix handles, stand-alone products, stencil detection and device-side CSR assembly.
-#include "spmv_kernels.cuh"
+#include "dispatch.cuh"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <vector>
@@ -183,6 +183,7 @@ static int make_stencil(phb200_matrix** out, int rank, const int64_t* grid, int 
     }
     m->n_rows = m->n_cols = st.dims[0] * st.dims[1] * st.dims[2];
     m->nnz = -1;
+    m->is_star = star_from_stencil(st, m->star) ? 1 : 0;
     *out = m;
     return PHB200_OK;
 }

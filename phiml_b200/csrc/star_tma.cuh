@@ -1,0 +1,224 @@
+// Fused stencil CG iteration, first half, with TMA staging (sm_100a):
+//     d_new = M^-1 r + beta d_old   (tile + halo recomputed on chip, stored once)
+//     x    += alpha_prev d_old      (the previous iteration's pending update)
+//     q     = A d_new               (5/7-point star, ZERO boundaries)
+//     d_new . q  -> alpha           (deterministic cross-CTA reduction, scalar step in the last CTA)
+//
+// A CTA owns an (SY x SZ) tile of the y-z plane and marches over a chunk of x planes.  The r and d_old tiles INCLUDING
+// their one-cell halos are fetched by the TMA unit (cp.async.bulk.tensor.4d, one elected thread, mbarrier completion,
+// kStages planes in flight); out-of-domain halo cells are zero-filled by the TMA, which is exactly the ZERO boundary.
+// d_new planes live in a 4-deep ring in shared memory; x-neighbours of the product come from that ring.
+#pragma once
+#include <cuda.h>
+#include "stencil_fast.cuh"
+
+namespace phb {
+
+constexpr int kStages = 3;
+
+template <typename T> constexpr int tile_bytes() { return ((SROWS * SROW * (int)sizeof(T) + 127) / 128) * 128; }
+template <typename T> constexpr int star_tma_smem() { return (2 * kStages + 4) * tile_bytes<T>() + 8 * kStages + 128; }
+
+// ---- host: tensor maps -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+// (batch, nx, ny, nz) row-major vector set with leading dimension ld -> 4-D map with box (SROW, SROWS, 1, 1)
+inline bool make_star_tmap(CUtensorMap* out, const void* base, int dtype, const StarDesc& st, int64_t batch, int64_t ld) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t w = dtype == PHB200_F32 ? 4 : 8;
+    cuuint64_t dims[4] = {(cuuint64_t)st.nz, (cuuint64_t)st.ny, (cuuint64_t)st.nx, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)st.nz * w, (cuuint64_t)st.ny * st.nz * w, (cuuint64_t)ld * w};
+    cuuint32_t box[4] = {(cuuint32_t)SROW, (cuuint32_t)SROWS, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int k = 0; k < 3; ++k)
+        if (strides[k] % 16 != 0 || strides[k] >= (1ull << 40)) return false;
+    if (((uintptr_t)base) % 16 != 0) return false;
+    CUresult r = fn(out, dtype == PHB200_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ---- device: mbarrier / TMA wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a transfer that never completes traps (error surfaces on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+// PRE: 0 none, 3 Jacobi with constant inverse diagonal
+template <typename T, int PRE, class Epi>
+__global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_a,
+                                                        const __grid_constant__ CUtensorMap tm_b, StarDesc st, T* __restrict__ X, T* buf_a, T* buf_b,
+                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, Epi epi) {
+    if (epi.idle()) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TB = tile_bytes<T>();
+    constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    auto tile_r = [&](int stg) { return reinterpret_cast<T(*)[SROW]>(base + (size_t)(2 * stg) * TB); };
+    auto tile_d = [&](int stg) { return reinterpret_cast<T(*)[SROW]>(base + (size_t)(2 * stg + 1) * TB); };
+    auto plane = [&](int k) { return reinterpret_cast<T(*)[SROW]>(base + (size_t)(2 * kStages + (k & 3)) * TB); };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)(2 * kStages + 4) * TB);
+
+    const int b = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double acc[1] = {0.0};
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < kStages; ++k) mbar_init(smem_u32(&bars[k]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (!epi.skip(b)) {
+        const bool odd = (epi.glob->pass & 1) != 0;
+        const CUtensorMap* tm_old = odd ? &tm_b : &tm_a;
+        T* __restrict__ d_new = (odd ? buf_a : buf_b) + (int64_t)b * ld;
+        T* __restrict__ xb = X + (int64_t)b * ld;
+        T* __restrict__ qb = Q + (int64_t)b * ld;
+        const T beta = (T)epi.sys[b].s[1 /*S_BETA*/], alpha = (T)epi.sys[b].s[0 /*S_ALPHA*/];
+        const int64_t nx = st.nx, ny = st.ny, nz = st.nz;
+        const int tiles_z = (int)((nz + SZ - 1) / SZ), tiles_y = (int)((ny + SY - 1) / SY);
+        const int chunks = (int)((nx + xchunk - 1) / xchunk);
+        const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
+        const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
+        uint32_t g = 0;   // running index of issued/consumed planes -> stage and mbarrier phase
+
+        auto dir = [&](T rv, T dv) {
+            const T s = PRE == 3 ? mul_rn(rv, cinv) : rv;
+            return add_rn(s, mul_rn(beta, dv));
+        };
+
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
+            const int64_t x0 = (int64_t)ch * xchunk, x1 = min(nx, x0 + xchunk);
+            const int y0 = ty * SY, z0 = tz * SZ;
+            const int jy = y0 + warp, jz = z0 + 4 * lane;
+            const bool mine = jy < ny && jz < nz;
+            const int P = (int)(x1 - x0) + 2;   // planes x0-1 .. x1
+
+            auto issue = [&](uint32_t gi, int64_t px) {
+                const int stg = gi % kStages;
+                const uint32_t bar = smem_u32(&bars[stg]);
+                mbar_expect_tx(bar, kTxBytes);
+                tma_load_4d(smem_u32(tile_r(stg)), &tm_r, bar, z0 - 4, y0 - 1, (int)px, b);
+                tma_load_4d(smem_u32(tile_d(stg)), tm_old, bar, z0 - 4, y0 - 1, (int)px, b);
+            };
+
+            __syncthreads();   // everything of the previous item has been consumed
+            if (t == 0)
+                for (int k = 0; k < kStages && k < P; ++k) issue(g + k, x0 - 1 + k);
+            Quad<T> x_cur{{T(0), T(0), T(0), T(0)}};
+            for (int k = 0; k < P; ++k) {
+                const int64_t p = x0 - 1 + k;
+                const bool owned = mine && p >= x0 && p < x1;
+                const int64_t i = (p * ny + jy) * nz + jz;
+                // the x values of the next owned plane travel while this plane is processed
+                Quad<T> x_next{{T(0), T(0), T(0), T(0)}};
+                if (mine && p + 1 >= x0 && p + 1 < x1) x_next = ld4<T>(xb + i + ny * nz);
+                const int stg = (g + k) % kStages;
+                mbar_wait(smem_u32(&bars[stg]), ((g + k) / kStages) & 1u);
+                T(*rt)[SROW] = tile_r(stg);
+                T(*dt)[SROW] = tile_d(stg);
+                T(*pl)[SROW] = plane(k);
+                {
+                    const int c = 4 + 4 * lane;
+                    const Quad<T> rv = ld4<T>(&rt[warp + 1][c]), dv = ld4<T>(&dt[warp + 1][c]);
+                    Quad<T> dn;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
+                    st4(&pl[warp + 1][c], dn);
+                    if (owned) {
+                        st4(d_new + i, dn);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
+                        st4(xb + i, x_cur);
+                    }
+                    if (warp < 2) {   // halo rows
+                        const int hr = warp == 0 ? 0 : SY + 1;
+                        const Quad<T> rh = ld4<T>(&rt[hr][c]), dh = ld4<T>(&dt[hr][c]);
+                        Quad<T> hn;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e]);
+                        st4(&pl[hr][c], hn);
+                    }
+                    if (t >= 64 && t < 64 + 2 * SROWS) {   // halo columns
+                        const int row = (t - 64) >> 1, col = ((t - 64) & 1) ? 4 + SZ : 3;
+                        pl[row][col] = dir(rt[row][col], dt[row][col]);
+                    }
+                }
+                x_cur = x_next;
+                __syncthreads();   // plane k complete; stage `stg` fully read
+                if (t == 0 && k + kStages < P) issue(g + k + kStages, p + kStages);
+                if (k >= 2 && mine) {
+                    T(*pm)[SROW] = plane(k - 2);
+                    T(*pc)[SROW] = plane(k - 1);
+                    const int sr = warp + 1, c = 4 + 4 * lane;
+                    const Quad<T> ce = ld4<T>(&pc[sr][c]);
+                    const Quad<T> ym = ld4<T>(&pc[sr - 1][c]), yp = ld4<T>(&pc[sr + 1][c]);
+                    const Quad<T> xm = ld4<T>(&pm[sr][c]), xp = ld4<T>(&pl[sr][c]);
+                    const T left = pc[sr][c - 1], right = pc[sr][c + 4];
+                    Quad<T> out;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const T zm = e == 0 ? left : ce.v[e - 1];
+                        const T zp = e == 3 ? right : ce.v[e + 1];
+                        T sum = mul_rn(cxm, xm.v[e]);
+                        sum = add_rn(sum, mul_rn(cym, ym.v[e]));
+                        sum = add_rn(sum, mul_rn(czm, zm));
+                        sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                        sum = add_rn(sum, mul_rn(czp, zp));
+                        sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
+                        sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                        out.v[e] = sum;
+                        acc[0] += (double)mul_rn(ce.v[e], sum);
+                    }
+                    st4(qb + ((p - 1) * ny + jy) * nz + jz, out);
+                }
+            }
+            g += (uint32_t)P;
+        }
+    }
+    epilogue_tail(epi, acc, b, blockIdx.x, gridDim.x);
+}
+
+}  // namespace phb

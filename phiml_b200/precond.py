@@ -63,7 +63,8 @@ class JacobiPreconditioner(Preconditioner, _Handle):
         self.inv_diag = torch.empty(m.shape[0], dtype=m.dtype, device=m.device)
         E.check(E.lib().phb200_jacobi_setup(src.handle, E.ptr(self.inv_diag), E.stream_ptr(m.device)))
         h = ctypes.c_void_p()
-        E.check(E.lib().phb200_precond_jacobi(ctypes.byref(h), E.ptr(self.inv_diag), m.shape[0], E.dtype_code(m.dtype)))
+        # a stencil matrix has a constant diagonal: the fused kernels then take 1/diag as a scalar
+        E.check(E.lib().phb200_precond_jacobi(ctypes.byref(h), E.ptr(self.inv_diag), m.shape[0], E.dtype_code(m.dtype), 1 if src.kind == 'stencil' else 0))
         self._h = h
 
     def apply(self, vec):
