@@ -1,0 +1,142 @@
+"""
+PhiML plug-in: makes the phb200 path the implementation behind PhiML's *own* torch backend object, so that unmodified
+``phiml.math`` code (named batch dims, ``SolveTape``, ``NotConverged``/``Diverged``) runs on it.
+
+    import phiml_b200.phiml_plugin as plugin
+    plugin.install()          # once, after importing phiml
+
+What it does:
+
+* ``TORCH.__class__`` is switched to a subclass of ``TorchBackend`` (phiml/backend/torch/_torch_backend.py:19) that overrides
+  ``linear_solve`` / ``conjugate_gradient`` / ``conjugate_gradient_adaptive`` / ``bi_conjugate_gradient``,
+  ``mul_matrix_batched_vector``, ``mul_csr_dense``, ``mul_coo_dense`` and adds ``solve_triangular_sparse`` — the singleton identity is
+  kept (``get_backend('torch') is TORCH``) and ``TORCH.supports(Backend.solve_triangular_sparse)`` turns true, so
+  ``preconditioner='auto'`` selects ILU (phiml/math/_optimize.py:842-846).
+* ``phiml.math._optimize.compute_preconditioner`` (looked up as a module global at :644) is re-bound to a wrapper that adds
+  ``'jacobi'`` and builds ``'ilu'`` on the device for CUDA torch matrices.
+
+Calls whose operands are not CUDA torch tensors / torch sparse matrices (CPU tensors, dense matrices, matrix-free functions,
+``scipy-*`` methods, tracing) are outside the phb200 path and go to the reference's own ``TorchBackend`` implementation unchanged.
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from . import precond as _precond
+from . import solve as _solve
+from .sparse import Matrix
+
+_INSTALLED = {}
+
+
+def _is_sparse_cuda(m) -> bool:
+    if isinstance(m, Matrix):
+        return True
+    return isinstance(m, torch.Tensor) and m.layout != torch.strided and m.is_cuda
+
+
+def _on_path(lin, y) -> bool:
+    """True if this call belongs to the phb200 path: explicit sparse matrix and right-hand sides on a CUDA device, eager mode."""
+    if not _is_sparse_cuda(lin):
+        return False
+    if torch._C._get_tracing_state() is not None:
+        return False
+    return isinstance(y, torch.Tensor) and y.is_cuda
+
+
+def _own_pre(pre) -> bool:
+    return pre is None or isinstance(pre, (_precond.JacobiPreconditioner, _precond.IncompleteLU))
+
+
+def install():
+    """Idempotent.  Returns the patched ``TORCH`` backend object."""
+    if _INSTALLED:
+        return _INSTALLED['torch']
+    from phiml.backend import _backend as pb_backend
+    from phiml.backend._backend import SolveResult as PhiSolveResult, Preconditioner as PhiPreconditioner
+    from phiml.backend.torch import TORCH
+    from phiml.backend.torch._torch_backend import TorchBackend
+    import phiml.math._optimize as opt
+
+    def convert(r: _solve.SolveResult) -> PhiSolveResult:
+        return PhiSolveResult(r.method, r.x, r.residual, r.iterations, r.function_evaluations, r.converged, r.diverged, r.message)
+
+    class B200TorchBackend(TorchBackend):
+        """TorchBackend whose sparse linear-solve path runs on libphb200 (CUDA operands only)."""
+
+        # --- products ---
+        def mul_matrix_batched_vector(self, A, b):
+            if _is_sparse_cuda(A) and isinstance(b, torch.Tensor) and b.is_cuda and torch._C._get_tracing_state() is None:
+                A_, b_ = self.auto_cast(A, b) if isinstance(A, torch.Tensor) else (A, b)
+                return _solve.mul_matrix_batched_vector(A_, b_)
+            return TorchBackend.mul_matrix_batched_vector(self, A, b)
+
+        def mul_csr_dense(self, column_indices, row_pointers, values, shape, dense):
+            values_t, dense_t = self.as_tensor(values), self.as_tensor(dense)
+            if values_t.is_cuda and dense_t.is_cuda and torch._C._get_tracing_state() is None:
+                values_t, dense_t = self.auto_cast(values_t, dense_t, bool_to_int=True, int_to_float=True)
+                return _solve.mul_csr_dense(self.as_tensor(column_indices), self.as_tensor(row_pointers), values_t, shape, dense_t)
+            return TorchBackend.mul_csr_dense(self, column_indices, row_pointers, values, shape, dense)
+
+        def mul_coo_dense(self, indices, values, shape, dense):
+            values_t, dense_t = self.as_tensor(values), self.as_tensor(dense)
+            if values_t.is_cuda and dense_t.is_cuda and torch._C._get_tracing_state() is None:
+                values_t, dense_t = self.auto_cast(values_t, dense_t)
+                return _solve.mul_coo_dense(self.as_tensor(indices), values_t, shape, dense_t)
+            return TorchBackend.mul_coo_dense(self, indices, values, shape, dense)
+
+        # --- solves ---
+        def conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset):
+            if matrix_offset is None and _on_path(lin, y) and _own_pre(pre):
+                return convert(_solve.conjugate_gradient(lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, None))
+            return TorchBackend.conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset)
+
+        def conjugate_gradient_adaptive(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset):
+            if matrix_offset is None and _on_path(lin, y) and _own_pre(pre):
+                return convert(_solve.conjugate_gradient_adaptive(lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, None))
+            return TorchBackend.conjugate_gradient_adaptive(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset)
+
+        def bi_conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset, poly_order=2):
+            if matrix_offset is None and poly_order >= 1 and poly_order <= 4 and _on_path(lin, y) and _own_pre(pre):
+                return convert(_solve.bi_conjugate_gradient(lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, None, poly_order))
+            return TorchBackend.bi_conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset, poly_order)
+
+        def solve_triangular_sparse(self, matrix, rhs, lower: bool, unit_diagonal: bool):
+            if _is_sparse_cuda(matrix) and isinstance(rhs, torch.Tensor) and rhs.is_cuda:
+                return _solve.solve_triangular_sparse(matrix, rhs, lower, unit_diagonal)
+            raise NotImplementedError("sparse triangular solves run on CUDA torch tensors only (phb200); use the NumPy backend on the CPU")
+
+    # the device-side preconditioners must be accepted wherever PhiML checks the protocol type
+    for cls in (_precond.JacobiPreconditioner, _precond.IncompleteLU):
+        if PhiPreconditioner not in cls.__mro__:
+            try:
+                cls.__bases__ = cls.__bases__ + (PhiPreconditioner,)
+            except TypeError:
+                pass
+
+    original_compute = opt.compute_preconditioner
+
+    def compute_preconditioner(method, matrix, rank_deficiency=0, target_backend=None, solver=None):
+        from phiml.math._sparse import native_matrix, is_sparse
+        cuda_torch = target_backend is TORCH and is_sparse(matrix) and torch.cuda.is_available() and str(TORCH.get_default_device().device_type).upper() == 'GPU'
+        if method == 'jacobi':
+            if not cuda_torch:
+                raise NotImplementedError("preconditioner='jacobi' is provided by phb200 for sparse matrices on the CUDA torch backend only")
+            return _precond.JacobiPreconditioner(native_matrix(matrix, TORCH))
+        if method == 'ilu' and cuda_torch and not (solver or '').startswith('scipy-'):
+            return _precond.IncompleteLU(native_matrix(matrix, TORCH))
+        return original_compute(method, matrix, rank_deficiency=rank_deficiency, target_backend=target_backend, solver=solver)
+
+    TORCH.__class__ = B200TorchBackend
+    opt.compute_preconditioner = compute_preconditioner
+    _INSTALLED.update(torch=TORCH, original_class=TorchBackend, original_compute=original_compute, opt=opt)
+    return TORCH
+
+
+def uninstall():
+    if not _INSTALLED:
+        return
+    _INSTALLED['torch'].__class__ = _INSTALLED['original_class']
+    _INSTALLED['opt'].compute_preconditioner = _INSTALLED['original_compute']
+    _INSTALLED.clear()

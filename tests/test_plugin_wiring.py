@@ -1,0 +1,88 @@
+"""
+CPU suite, part 3 (authoring container only — needs /root/reference): the PhiML plug-in keeps the reference's own front end
+working and routes the path's calls to the phb200 boundary with the argument layout of SURVEY.md §8b.  The CUDA engine is
+replaced by the oracle HERE, in the test, to observe the plumbing without a GPU.
+"""
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture()
+def phiml_env():
+    if '/root/reference' not in sys.path:
+        sys.path.insert(0, '/root/reference')
+    import phiml  # noqa: F401
+    from phiml_b200 import phiml_plugin
+    torch_backend = phiml_plugin.install()
+    yield phiml_plugin, torch_backend
+    phiml_plugin.uninstall()
+
+
+def test_install_keeps_singleton_and_enables_triangular_solves(phiml_env):
+    plugin, TORCH = phiml_env
+    from phiml.backend._backend import Backend, get_backend
+    assert get_backend('torch') is TORCH
+    assert TORCH.supports(Backend.solve_triangular_sparse)
+    assert TORCH.supports(Backend.mul_csr_dense) and TORCH.supports(Backend.conjugate_gradient)
+    plugin.uninstall()
+    assert not TORCH.supports(Backend.solve_triangular_sparse)
+
+
+def test_cpu_operands_still_take_the_reference_path(phiml_env):
+    """tests/commit/math/test__optimize.py:62-70 must keep passing on CPU torch tensors (not the phb200 path)."""
+    from phiml import math
+    from phiml.math import spatial, Solve, extrapolation
+    plugin, TORCH = phiml_env
+    with TORCH:
+        y = math.ones(spatial(x=3))
+        x0 = math.zeros(spatial(x=3))
+        for method in ['CG', 'CG-adaptive', 'biCG-stab(1)']:
+            f = math.jit_compile_linear(lambda x: math.laplace(x, padding=extrapolation.ZERO))
+            x = math.solve_linear(f, y, Solve(method, 0, 1e-10, x0=x0))
+            np.testing.assert_allclose(x.numpy('x'), [-1.5, -2, -1.5], atol=1e-3)
+    with pytest.raises(NotImplementedError):
+        from phiml.math._optimize import compute_preconditioner
+        compute_preconditioner('jacobi', None, 0, None, 'CG')
+
+
+def test_front_end_reaches_the_boundary_with_reference_layout(phiml_env, monkeypatch):
+    """math.solve_linear -> Backend.linear_solve(method, native CSR, y (batch,N), x0, rtol (batch,), atol, max_iter (1,batch), pre)."""
+    import torch
+    import scipy.sparse as sp
+    from phiml import math
+    from phiml.math import spatial, batch, Solve, SolveTape, extrapolation
+    from oracle import krylov
+    from phiml_b200 import solve as host
+    plugin, TORCH = phiml_env
+    seen = {}
+
+    def fake_cg(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None):
+        seen.update(layout=lin.layout, crow_dtype=lin.crow_indices().dtype, y=tuple(y.shape), x0=tuple(x0.shape), rtol=tuple(np.shape(rtol)),
+                    max_iter=np.asarray(max_iter).shape, pre=pre, y_dtype=y.dtype)
+        a = sp.csr_matrix((lin.values().numpy(), lin.col_indices().numpy(), lin.crow_indices().numpy()), shape=tuple(lin.shape))
+        r = krylov.torch_fastpath_cg(a, y.numpy(), x0.numpy(), np.asarray(rtol), np.asarray(atol), np.asarray(max_iter))
+        t = torch.as_tensor
+        return host.SolveResult(r.method, t(r.x), t(r.residual), t(r.iterations), t(r.function_evaluations), t(r.converged), t(r.diverged), r.message)
+
+    monkeypatch.setattr(plugin, '_on_path', lambda lin, y: True)
+    monkeypatch.setattr(host, 'conjugate_gradient', fake_cg)
+    f = math.jit_compile_linear(lambda x: -math.laplace(x, padding=extrapolation.ZERO))
+    with TORCH, math.precision(32):
+        rng = np.random.default_rng(0)
+        y = math.tensor(rng.standard_normal((3, 16, 16)).astype(np.float32), batch('b'), spatial('x,y'))
+        solve = Solve('CG', 1e-5, 0, x0=math.zeros(spatial(x=16, y=16)), max_iterations=1000)
+        with SolveTape() as tape:
+            x = math.solve_linear(f, y, solve)
+        info = tape[solve]
+    assert seen['layout'] == torch.sparse_csr and seen['crow_dtype'] == torch.int32
+    assert seen['y'] == (3, 256) and seen['x0'] == (3, 256) and seen['rtol'] == (3,) and seen['max_iter'] == (1, 3)
+    assert seen['pre'] is None and seen['y_dtype'] == torch.float32
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'frontend.npz'))
+    np.testing.assert_allclose(x.numpy('b,x,y'), g['front/torch/cg16/x'], rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(info.iterations.numpy('b'), g['front/torch/cg16/iterations'])
+    assert info.method == str(g['front/torch/cg16/method'])
