@@ -95,6 +95,11 @@ int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int r
 int phb200_stencil_nnz(const phb200_matrix* stencil, int64_t* nnz);
 int phb200_stencil_to_csr(const phb200_matrix* stencil, int32_t* rowptr, int32_t* col, void* val, void* stream);
 
+/* Slab (row-partition) mode for multi-GPU solves of ONE system: the arrays span `grid[0]` planes (owned planes plus one
+ * halo plane per neighbour), but only planes [x_begin, x_end) are produced / updated / reduced over.  Halo planes are
+ * read like ordinary neighbours; the caller keeps them current (phiml_b200/multi_gpu.py exchanges them over NCCL). */
+int phb200_matrix_set_slab(phb200_matrix* m, int64_t x_begin, int64_t x_end);
+
 int phb200_matrix_info(const phb200_matrix* m, int* kind, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, int* dtype);
 int phb200_matrix_destroy(phb200_matrix* m);
 
@@ -152,6 +157,21 @@ size_t phb200_solver_workspace_bytes(const phb200_solver* s);
 int phb200_solver_start(phb200_solver* s, const void* Y, const void* X0, void* X, void* R,
                         const void* rtol, const void* atol, const int32_t* max_iter,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Batch sharding over several GPUs: the tolerance every system must reach is the minimum over the WHOLE batch
+ * (phiml/backend/_linalg.py:26-29).  After start(): read the local minimum (set = 0, *tol_min is a device double),
+ * all-reduce(min) it over the ranks, write it back (set = 1) — the first progress check is repeated with it. */
+int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream);
+
+/* Distributed (slab) mode: `totals` is a caller-owned device buffer of batch*4 doubles.  After set_dist, start() and every
+ * half iteration leave their LOCAL dot products in `totals` and stop; the caller all-reduces `totals` (sum) over the ranks
+ * and calls dist_step, which applies the scalar step on every rank identically:
+ *     start -> allreduce -> dist_step(10) [-> halo exchange of R and the direction buffer]
+ *     loop:   dist_step(0) -> allreduce -> dist_step(1) -> allreduce -> dist_step(2) -> halo exchange of R
+ *     end:    dist_step(20)   (applies the pending x update)
+ * Supported: 'CG' on a star stencil, no or constant-diagonal Jacobi preconditioner. */
+int phb200_solver_set_dist(phb200_solver* s, void* totals);
+int phb200_solver_dist_step(phb200_solver* s, int step, void* stream);
 
 /* Enqueue up to n_iter further iterations (asynchronous; iterations after all systems finished are skipped on
  * the device). */

@@ -30,6 +30,7 @@ SIGNATURES = {
     'phb200_stencil_from_csr': (c_int, [_PP, _P, c_int, POINTER(c_int64), _P]),
     'phb200_stencil_nnz': (c_int, [_P, POINTER(c_int64)]),
     'phb200_stencil_to_csr': (c_int, [_P, _P, _P, _P, _P]),
+    'phb200_matrix_set_slab': (c_int, [_P, c_int64, c_int64]),
     'phb200_matrix_info': (c_int, [_P, POINTER(c_int), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int)]),
     'phb200_matrix_destroy': (c_int, [_P]),
     'phb200_spmv': (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P]),
@@ -46,6 +47,9 @@ SIGNATURES = {
     'phb200_solver_create': (c_int, [_PP, _P, _P, c_int, c_int, c_int64]),
     'phb200_solver_workspace_bytes': (c_size_t, [_P]),
     'phb200_solver_start': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'phb200_solver_tol_min': (c_int, [_P, _P, c_int, _P]),
+    'phb200_solver_set_dist': (c_int, [_P, _P]),
+    'phb200_solver_dist_step': (c_int, [_P, c_int, _P]),
     'phb200_solver_advance': (c_int, [_P, c_int, _P]),
     'phb200_solver_run': (c_int, [_P, c_int64, _P]),
     'phb200_solver_poll': (c_int, [_P, POINTER(c_int), _P]),

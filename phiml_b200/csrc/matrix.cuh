@@ -14,7 +14,9 @@ struct CsrView {
 // Constant-coefficient stencil with ZERO boundaries on a C-ordered grid (dims[0] slowest).  Points are sorted by
 // flattened offset so that a row accumulates in the same order as the canonical (sorted-column) CSR row does.
 struct StarDesc {       // centre + nearest neighbours per axis; see stencil_fast.cuh
-    int64_t nx, ny, nz;
+    int64_t nx, ny, nz;     // extent of the arrays (for a slab: owned planes + one halo plane on each side)
+    int64_t xb, xe;         // planes [xb, xe) are produced; reads reach planes xb-1 and xe when they lie inside the array
+    int store_halo;         // slab mode: the fused CG kernel also stores d_new on the halo planes xb-1 and xe
     double c0, cxm, cxp, cym, cyp, czm, czp;
 };
 

@@ -21,6 +21,7 @@ struct Ctx {
     Glob* glob;
     Reduce red;
     int batch;
+    double* defer;   // non-null: store the per-system sums here instead of finalising (multi-GPU all-reduce in between)
 };
 
 // Phase protocol (in addition to the epilogue protocol of spmv_kernels.cuh)
@@ -29,7 +30,7 @@ struct Ctx {
 //   Scal load(b)       per-system scalars, read once per thread
 //   elem(e, acc, sc)   one element: e[a] in/out
 template <typename T, class P, int V>
-__global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld) {
+__global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, int64_t off) {
     if (p.idle()) return;
     const int b = blockIdx.y;
     constexpr int ND = AccSize<P>::N;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld) {
         const typename P::Scal sc = p.load(b);
         T* base[NA];
 #pragma unroll
-        for (int a = 0; a < NA; ++a) base[a] = (T*)p.v[a] + (((P::SHARED >> a) & 1u) ? (int64_t)0 : (int64_t)b * ld);
+        for (int a = 0; a < NA; ++a) base[a] = (T*)p.v[a] + off + (((P::SHARED >> a) & 1u) ? (int64_t)0 : (int64_t)b * ld);
         using VT = typename Vec<T>::type;
         for (int64_t i = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * V; i < n; i += (int64_t)gridDim.x * kBlock * V) {
             alignas(16) T e[NA][V];
@@ -77,18 +78,34 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld) {
 }
 
 template <typename T, class P>
-int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream) {
+int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0) {
     constexpr int V = Vec<T>::N;
-    bool aligned = (n % V == 0) && (ld % V == 0);
+    bool aligned = (n % V == 0) && (ld % V == 0) && (off % V == 0);
     for (int a = 0; a < P::NA; ++a) aligned = aligned && (((uintptr_t)p.v[a]) % 16 == 0);
     if (aligned) {
         dim3 grid((unsigned)grid_x((n / V + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, V>)), (unsigned)batch);
-        PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld);
+        PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld, off);
     } else {
         dim3 grid((unsigned)grid_x((n + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, 1>)), (unsigned)batch);
-        PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld);
+        PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld, off);
     }
     return PHB200_OK;
+}
+
+// Scalar step of a phase / epilogue functor applied to (all-reduced) sums: one CTA, thread b handles system b.
+template <class F>
+__global__ void __launch_bounds__(kBlock) k_finalize(F f, const double* __restrict__ totals) {
+    if (f.idle()) return;
+    constexpr int ND = AccSize<F>::N;
+    for (int b = threadIdx.x; b < f.batch; b += blockDim.x) {
+        double tot[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) tot[d] = totals[(size_t)b * kMaxDots + d];
+        f.finalize(b, tot);
+    }
+    __threadfence();
+    __syncthreads();
+    if constexpr (F::GLOBAL) f.finalize_all();
 }
 
 }  // namespace phb

@@ -582,6 +582,25 @@ struct BiEpi : FBase {
     __device__ void finalize_all() const {}
 };
 
+// multi-GPU batch sharding: install the batch-wide minimum tolerance and repeat the first progress check with it
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_recheck(FBase f, int rules, const double* __restrict__ tol_min, int adaptive) {
+    if (threadIdx.x == 0) {
+        f.glob->tol_min = *tol_min;
+        f.glob->checks = 0;
+        __threadfence();
+    }
+    __syncthreads();
+    check_all<T>(f, rules);
+    __syncthreads();
+    if (adaptive) {   // the first step size was computed from the flags of the local check
+        for (int b = threadIdx.x; b < f.batch; b += blockDim.x) {
+            volatile Sys* s = f.sys + b;
+            s->s[S_ALPHA] = s->go ? (double)safe_div((T)s->s[S_DR], (T)s->s[S_DQ]) : 0.0;
+        }
+    }
+}
+
 __global__ void k_collect(const Sys* __restrict__ sys, int batch, int32_t* its, int32_t* fev, uint8_t* conv, uint8_t* div) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
@@ -631,6 +650,12 @@ struct phb200_solver {
     // TMA descriptors of r and the two direction buffers (fused stencil CG); valid for the vectors bound by start()
     CUtensorMap tm_r, tm_a, tm_b;
     int tma_ok;
+    // slab / multi-GPU mode: kernels store local sums in `totals`, the host all-reduces, dist_step() finalises
+    double* totals;            // device, caller-owned (batch x kMaxDots doubles); non-null = distributed mode
+    const void* rtol;
+    const void* atol;
+    const int32_t* max_iter;
+    int64_t off, n_act;        // element range [off, off + n_act) of every vector that this rank owns (whole vector if not a slab)
 };
 
 namespace phb {
@@ -650,6 +675,7 @@ static Ctx make_ctx(const phb200_solver* s) {
     c.red.partials = s->partials;
     c.red.tickets = s->tickets;
     c.red.max_blocks = max_blocks_for(s->batch);
+    c.defer = nullptr;
     c.batch = (int)s->batch;
     return c;
 }
@@ -661,6 +687,7 @@ static void fill_base(F& f, const phb200_solver* s, bool always, bool freeze) {
     f.glob = c.glob;
     f.red = c.red;
     f.batch = c.batch;
+    f.defer = nullptr;
     f.always = always ? 1 : 0;
     f.freeze = freeze ? 1 : 0;
 }
@@ -685,6 +712,7 @@ struct Run {
     int64_t n, ld;
     int batch;
     T* vec(int k) const { return (T*)s->ws + (int64_t)k * batch * ld; }
+    double* defer() const { return s->totals; }
     bool frozen() const { return s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE; }
     int rules() const { return (s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH) ? RULES_TORCH : RULES_GENERIC; }
     const T* invd() const { return s->pre == PHB200_PRE_JACOBI ? (const T*)s->M->inv_diag : nullptr; }
@@ -704,9 +732,13 @@ struct Run {
     }
     template <class P> int phase(const P& p) {
         prof_begin();
-        int r = launch_phase<T, P>(p, n, ld, batch, st);
+        int r = launch_phase<T, P>(p, s->n_act, ld, batch, st, s->off);
         prof_end();
         return r;
+    }
+    template <class F> int finalize_only(const F& f) {
+        PHB_LAUNCH((k_finalize<F>), 1, kBlock, 0, st, f, (const double*)s->totals);
+        return PHB200_OK;
     }
     template <class E> int spmv(const T* x, T* y, const E& e) {
         prof_begin();
@@ -768,6 +800,7 @@ struct Run {
     // ------------------------------------------------------------------------------------------ start
     int start(const T* Y, const T* X0, T* X, T* R, const T* rtol, const T* atol, const int32_t* max_iter) {
         const int method = s->method;
+        s->rtol = rtol; s->atol = atol; s->max_iter = max_iter;
         s->tma_ok = 0;
         if (fused() && !getenv("PHB200_NO_TMA")) {
             const StarDesc& sd = s->A->star;
@@ -785,7 +818,6 @@ struct Run {
             PHB_TRY(spmv(X, q, e));
         }
         const bool bicg = method == PHB200_BICGSTAB;
-        const int tol_from_y = method == PHB200_CG ? 0 : 1;
         if (s->pre == PHB200_PRE_ILU && method == PHB200_CG) {
             Residual<T> r0;
             fill_base(r0, s, true, false);
@@ -793,24 +825,12 @@ struct Run {
             PHB_TRY(phase(r0));
             T* sv = vec(2);
             PHB_TRY(precond_apply(s->M, R, sv, vec(3), batch, ld, st));
-            InitResidual<T, 2> f;
-            fill_base(f, s, true, frozen());
-            f.v[0] = R; f.v[1] = Y; f.v[2] = sv; f.v[3] = d; f.v[4] = nullptr;
-            f.rtol = rtol; f.atol = atol; f.max_iter = max_iter; f.tol_from_y = tol_from_y; f.rules = rules(); f.bicg = 0;
-            PHB_TRY(phase(f));
+            PHB_TRY(phase(make_init<2>(R, Y, sv, d, false)));
         } else if (s->pre == PHB200_PRE_JACOBI && method == PHB200_CG) {
-            InitResidual<T, 1> f;
-            fill_base(f, s, true, frozen());
-            f.v[0] = R; f.v[1] = Y; f.v[2] = q; f.v[3] = d; f.v[4] = s->M->inv_diag;
-            f.rtol = rtol; f.atol = atol; f.max_iter = max_iter; f.tol_from_y = tol_from_y; f.rules = rules(); f.bicg = 0;
-            PHB_TRY(phase(f));
+            PHB_TRY(phase(make_init<1>(R, Y, q, d, false)));
         } else {
             // no preconditioner inside the initial direction (cg without M, cg_adaptive, torch paths, bicg: d = r)
-            InitResidual<T, 0> f;
-            fill_base(f, s, true, frozen());
-            f.v[0] = R; f.v[1] = Y; f.v[2] = q; f.v[3] = bicg ? (const void*)vec(0) : (const void*)d; f.v[4] = nullptr;
-            f.rtol = rtol; f.atol = atol; f.max_iter = max_iter; f.tol_from_y = tol_from_y; f.rules = rules(); f.bicg = bicg ? 1 : 0;
-            PHB_TRY(phase(f));
+            PHB_TRY(phase(make_init<0>(R, Y, q, bicg ? vec(0) : d, bicg)));
         }
         if (method == PHB200_CG_ADAPTIVE || method == PHB200_CG_ADAPTIVE_TORCH) {
             AdDots<T> e;   // q = A d, d.q, d.r -> alpha of the first pass
@@ -833,17 +853,32 @@ struct Run {
     bool fused() const {
         return s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU;
     }
+    CgDq<T> make_dq() {
+        CgDq<T> e;
+        fill_base(e, s, false, true);
+        e.d = nullptr; e.ld = ld;
+        e.defer = defer();
+        return e;
+    }
     template <int PRE>
-    int pass_cg_fused_t(T* X, T* R) {
+    CgResid<T, PRE> make_resid(T* R) {
+        CgResid<T, PRE> u;
+        fill_base(u, s, false, true);
+        u.v[0] = R; u.v[1] = vec(1); u.v[2] = PRE == 1 ? s->M->inv_diag : nullptr;
+        u.cinv = PRE == 3 ? (T)s->M->const_inv : T(1); u.rules = RULES_GENERIC;
+        u.defer = defer();
+        return u;
+    }
+    // first half: d = M^-1 r + beta d, x += alpha d_old, q = A d, d.q
+    template <int PRE>
+    int fused_first(T* X, T* R) {
         T* q = vec(1);
         CgDirLoad<T, PRE> loader;
         loader.r = R; loader.buf_a = vec(0); loader.buf_b = vec(2); loader.xvec = X;
         loader.w = PRE == 1 ? (const T*)s->M->inv_diag : nullptr;
         loader.cinv = PRE == 3 ? (T)s->M->const_inv : T(1);
         loader.ld = ld; loader.glob = s->glob;
-        CgDq<T> e;
-        fill_base(e, s, false, true);
-        e.d = nullptr; e.ld = ld;
+        CgDq<T> e = make_dq();
         prof_begin();
         int r;
         if constexpr (PRE != 1) {
@@ -853,12 +888,46 @@ struct Run {
             r = launch_star<T, CgDirLoad<T, PRE>, CgDq<T>, true>(s->A->star, loader, q, ld, batch, e, st);
         }
         prof_end();
-        PHB_TRY(r);
-        CgResid<T, PRE> u;
-        fill_base(u, s, false, true);
-        u.v[0] = R; u.v[1] = q; u.v[2] = PRE == 1 ? s->M->inv_diag : nullptr;
-        u.cinv = loader.cinv; u.rules = RULES_GENERIC;
-        return phase(u);
+        return r;
+    }
+    template <int PRE>
+    int pass_cg_fused_t(T* X, T* R) {
+        PHB_TRY(fused_first<PRE>(X, R));
+        return phase(make_resid<PRE>(R));
+    }
+    int fused_pre() const { return s->pre == PHB200_PRE_NONE ? 0 : (s->M->is_const ? 3 : 1); }
+    // host-driven halves for the multi-GPU slab mode: all-reduce of s->totals between the steps (multi_gpu.py)
+    int dist_step(int step) {
+        T* X = (T*)s->X;
+        T* R = (T*)s->R;
+        const int pre = fused_pre();
+        switch (step) {
+            case 0:   // first half, local sums -> totals
+                s->prof_slot = 0;
+                return pre == 0 ? fused_first<0>(X, R) : fused_first<3>(X, R);
+            case 1:   // alpha from the reduced d.q, then the residual half (local r.s -> totals)
+                PHB_TRY(finalize_only(make_dq()));
+                return pre == 0 ? phase(make_resid<0>(R)) : phase(make_resid<3>(R));
+            case 2:   // beta, delta, progress check from the reduced r.s
+                s->passes += 1;
+                return pre == 0 ? finalize_only(make_resid<0>(R)) : finalize_only(make_resid<3>(R));
+            case 10:  // scalar set-up after the all-reduce of the initial sums
+                return pre == 0 ? finalize_only(make_init<0>(R, (const T*)s->Y, vec(1), vec(0), false)) : finalize_only(make_init<3>(R, (const T*)s->Y, vec(1), vec(0), false));
+            case 20:
+                return flush_x(X);
+        }
+        set_error("unknown distributed step %d", step);
+        return PHB200_ERR_ARG;
+    }
+    template <int PRE>
+    InitResidual<T, PRE == 3 ? 1 : PRE> make_init(T* R, const T* Y, const T* third, T* d, bool bicg) {
+        InitResidual<T, PRE == 3 ? 1 : PRE> f;
+        fill_base(f, s, true, frozen());
+        f.v[0] = R; f.v[1] = Y; f.v[2] = third; f.v[3] = d; f.v[4] = (PRE == 1 || PRE == 3) ? s->M->inv_diag : nullptr;
+        f.rtol = (const T*)s->rtol; f.atol = (const T*)s->atol; f.max_iter = s->max_iter;
+        f.tol_from_y = s->method == PHB200_CG ? 0 : 1; f.rules = rules(); f.bicg = bicg ? 1 : 0;
+        f.defer = defer();
+        return f;
     }
     template <int PRE>
     int launch_tma(T* X, T* q, T cinv, const CgDq<T>& e) {
@@ -884,8 +953,8 @@ struct Run {
     }
     // applies the pending x += alpha d after a batch of fused passes (x is then the true iterate)
     int flush_x(T* X) {
-        dim3 grid((unsigned)grid_x((n + kBlock * 4 - 1) / (kBlock * 4), batch, 8), (unsigned)batch);
-        PHB_LAUNCH(k_flush_x<T>, grid, kBlock, 0, st, X, (const T*)vec(0), (const T*)vec(2), (const Sys*)s->sys, (const Glob*)s->glob, n, ld);
+        dim3 grid((unsigned)grid_x((s->n_act + kBlock * 4 - 1) / (kBlock * 4), batch, 8), (unsigned)batch);
+        PHB_LAUNCH(k_flush_x<T>, grid, kBlock, 0, st, X + s->off, (const T*)vec(0) + s->off, (const T*)vec(2) + s->off, (const Sys*)s->sys, (const Glob*)s->glob, s->n_act, ld);
         PHB_LAUNCH(k_zero_alpha, (unsigned)((batch + 255) / 256), 256, 0, st, s->sys, batch);
         return PHB200_OK;
     }
@@ -1136,6 +1205,12 @@ int phb200_solver_create(phb200_solver** out, const phb200_matrix* A, const phb2
     s->pre = pre;
     s->batch = batch;
     s->n = A->n_rows;
+    s->off = 0;
+    s->n_act = A->n_rows;
+    if (A->kind == PHB200_MAT_STENCIL && A->is_star) {
+        s->off = A->star.xb * A->star.ny * A->star.nz;
+        s->n_act = (A->star.xe - A->star.xb) * A->star.ny * A->star.nz;
+    }
     s->prof_events = new std::vector<cudaEvent_t>();
     s->prof_slots = new std::vector<int>();
     cudaError_t e = cudaMalloc(&s->sys, sizeof(Sys) * batch);
@@ -1183,8 +1258,42 @@ int phb200_solver_start(phb200_solver* s, const void* Y, const void* X0, void* X
     return r;
 }
 
+int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && s->started && tol_min, "solver not started");
+    if (!set) {
+        PHB_CUDA(cudaMemcpyAsync(tol_min, &s->glob->tol_min, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return PHB200_OK;
+    }
+    PHB_ARG(s->passes == 0, "the tolerance can only be replaced before the first pass");
+    FBase f;
+    fill_base(f, s, true, s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE);
+    const int rules = (s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH) ? RULES_TORCH : RULES_GENERIC;
+    const int adaptive = (s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH) ? 1 : 0;
+    if (s->dtype == PHB200_F32) PHB_LAUNCH(k_recheck<float>, 1, kBlock, 0, st, f, rules, (const double*)tol_min, adaptive);
+    else PHB_LAUNCH(k_recheck<double>, 1, kBlock, 0, st, f, rules, (const double*)tol_min, adaptive);
+    return PHB200_OK;
+}
+
+int phb200_solver_set_dist(phb200_solver* s, void* totals) {
+    PHB_ARG(s && !s->started, "set_dist must be called before start");
+    PHB_ARG(s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && (s->pre == PHB200_PRE_NONE || s->M->is_const),
+            "distributed mode supports 'CG' on a star stencil without or with constant-diagonal Jacobi preconditioner");
+    s->totals = (double*)totals;
+    return PHB200_OK;
+}
+
+int phb200_solver_dist_step(phb200_solver* s, int step, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && s->started && s->totals, "solver not started in distributed mode");
+    if (!s->tma_ok) { set_error("distributed mode needs the TMA path (tensor map creation failed)"); return PHB200_ERR_UNSUPPORTED; }
+    if (s->dtype == PHB200_F32) return make_run<float>(s, st).dist_step(step);
+    return make_run<double>(s, st).dist_step(step);
+}
+
 int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream_) {
     PHB_ARG(s && s->started, "solver not started");
+    PHB_ARG(!s->totals, "a distributed solver is advanced with phb200_solver_dist_step");
     PHB_ARG(n_iter >= 0, "n_iter must be >= 0");
     return advance(s, n_iter, (cudaStream_t)stream_);
 }
@@ -1201,6 +1310,7 @@ int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream_) {
 int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started, "solver not started");
+    PHB_ARG(!s->totals, "a distributed solver is advanced with phb200_solver_dist_step");
     // The flag of chunk k is inspected while chunk k+1 is already queued, so the device never waits for the host.
     int chunk = 4;
     int slot = 0;

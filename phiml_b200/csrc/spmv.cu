@@ -313,6 +313,15 @@ int phb200_stencil_to_csr(const phb200_matrix* m, int32_t* rowptr, int32_t* col,
     return PHB200_OK;
 }
 
+int phb200_matrix_set_slab(phb200_matrix* m, int64_t x_begin, int64_t x_end) {
+    PHB_ARG(m && m->kind == PHB200_MAT_STENCIL && m->is_star, "slab ranges need a star stencil with nz % 4 == 0");
+    PHB_ARG(x_begin >= 0 && x_begin < x_end && x_end <= m->star.nx, "bad slab range [%lld, %lld) for %lld planes", (long long)x_begin, (long long)x_end, (long long)m->star.nx);
+    m->star.xb = x_begin;
+    m->star.xe = x_end;
+    m->star.store_halo = (x_begin > 0 || x_end < m->star.nx) ? 1 : 0;
+    return PHB200_OK;
+}
+
 int phb200_matrix_info(const phb200_matrix* m, int* kind, int64_t* n_rows, int64_t* n_cols, int64_t* nnz, int* dtype) {
     PHB_ARG(m, "null matrix");
     if (kind) *kind = m->kind;

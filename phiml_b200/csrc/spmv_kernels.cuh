@@ -26,6 +26,7 @@ struct NoEpi {
     Glob* glob;
     Sys* sys;
     int batch;
+    double* defer;
 };
 
 // acc holds per-thread partial sums
@@ -34,9 +35,16 @@ __device__ __forceinline__ void epilogue_tail(const Epi& epi, double (&acc)[NDA]
     if constexpr (Epi::ND > 0) {
         bool last = reduce_system<Epi::ND>(acc, epi.red, b, bx, nbx);
         if (last) {
-            if (threadIdx.x == 0) epi.finalize(b, acc);
+            if (threadIdx.x == 0) {
+                if (epi.defer) {   // multi-GPU: hand the local sums to the host-driven all-reduce, finalise later
+#pragma unroll
+                    for (int d = 0; d < Epi::ND; ++d) epi.defer[(size_t)b * kMaxDots + d] = acc[d];
+                } else {
+                    epi.finalize(b, acc);
+                }
+            }
             if constexpr (Epi::GLOBAL) {
-                if (last_of_batch(epi.glob, epi.batch)) epi.finalize_all();
+                if (!epi.defer && last_of_batch(epi.glob, epi.batch)) epi.finalize_all();
             }
         }
     }
@@ -48,9 +56,16 @@ __device__ __forceinline__ void epilogue_tail_cta(const Epi& epi, double (&tot)[
     if constexpr (Epi::ND > 0) {
         bool last = system_reduce<Epi::ND>(tot, epi.red, b, bx, nbx);
         if (last) {
-            if (threadIdx.x == 0) epi.finalize(b, tot);
+            if (threadIdx.x == 0) {
+                if (epi.defer) {
+#pragma unroll
+                    for (int d = 0; d < Epi::ND; ++d) epi.defer[(size_t)b * kMaxDots + d] = tot[d];
+                } else {
+                    epi.finalize(b, tot);
+                }
+            }
             if constexpr (Epi::GLOBAL) {
-                if (last_of_batch(epi.glob, epi.batch)) epi.finalize_all();
+                if (!epi.defer && last_of_batch(epi.glob, epi.batch)) epi.finalize_all();
             }
         }
     }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         const T beta = (T)epi.sys[b].s[1 /*S_BETA*/], alpha = (T)epi.sys[b].s[0 /*S_ALPHA*/];
         const int64_t nx = st.nx, ny = st.ny, nz = st.nz;
         const int tiles_z = (int)((nz + SZ - 1) / SZ), tiles_y = (int)((ny + SY - 1) / SY);
-        const int chunks = (int)((nx + xchunk - 1) / xchunk);
+        const int chunks = (int)((st.xe - st.xb + xchunk - 1) / xchunk);
         const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
         uint32_t g = 0;   // running index of issued/consumed planes -> stage and mbarrier phase
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
 
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
             const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
-            const int64_t x0 = (int64_t)ch * xchunk, x1 = min(nx, x0 + xchunk);
+            const int64_t x0 = st.xb + (int64_t)ch * xchunk, x1 = min(st.xe, x0 + xchunk);
             const int y0 = ty * SY, z0 = tz * SZ;
             const int jy = y0 + warp, jz = z0 + 4 * lane;
             const bool mine = jy < ny && jz < nz;
@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
                         st4(xb + i, x_cur);
+                    } else if (st.store_halo && mine && (p == st.xb - 1 || p == st.xe) && p >= 0 && p < nx) {
+                        st4(d_new + i, dn);   // slab halo plane: keep the neighbour's direction up to date locally
                     }
                     if (warp < 2) {   // halo rows
                         const int hr = warp == 0 ? 0 : SY + 1;

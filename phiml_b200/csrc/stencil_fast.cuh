@@ -24,6 +24,7 @@ constexpr int SROWS = SY + 2;
 // host: is this stencil a star with nz % 4 == 0 (128-bit rows)?
 inline bool star_from_stencil(const StencilDesc& st, StarDesc& out) {
     out.nx = st.dims[0]; out.ny = st.dims[1]; out.nz = st.dims[2];
+    out.xb = 0; out.xe = out.nx; out.store_halo = 0;
     out.c0 = out.cxm = out.cxp = out.cym = out.cyp = out.czm = out.czp = 0.0;
     if (out.nz % 4 != 0) return false;
     for (int p = 0; p < st.npts; ++p) {
@@ -126,14 +127,14 @@ __global__ void __launch_bounds__(kBlock) k_star(StarDesc st, Loader loader, T* 
         const typename Loader::Ctx lc = loader.begin(b, epi.sys);
         const int64_t nx = st.nx, ny = st.ny, nz = st.nz;
         const int tiles_z = (int)((nz + SZ - 1) / SZ), tiles_y = (int)((ny + SY - 1) / SY);
-        const int chunks = (int)((nx + xchunk - 1) / xchunk);
+        const int chunks = (int)((st.xe - st.xb + xchunk - 1) / xchunk);
         const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
         T* __restrict__ yb = Y + (int64_t)b * ldy;
 
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
             const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
-            const int64_t x0 = (int64_t)ch * xchunk, x1 = min(nx, x0 + xchunk);
+            const int64_t x0 = st.xb + (int64_t)ch * xchunk, x1 = min(st.xe, x0 + xchunk);
             const int64_t y0 = (int64_t)ty * SY, z0 = (int64_t)tz * SZ;
             const int64_t jz = z0 + 4 * lane;
 
@@ -215,12 +216,13 @@ inline void star_grid(const StarDesc& st, int batch, int occ, dim3& grid, int& x
     const int64_t tiles = ((st.ny + SY - 1) / SY) * ((st.nz + SZ - 1) / SZ);
     int64_t resident = ((int64_t)kSMs * (occ < 1 ? 1 : (occ > 8 ? 8 : occ))) / (batch < 1 ? 1 : batch);
     if (resident < 1) resident = 1;
+    const int64_t planes = st.xe - st.xb;
     int64_t chunks = resident / tiles;
     if (chunks < 1) chunks = 1;
-    if (chunks > st.nx) chunks = st.nx;
-    xchunk = (int)((st.nx + chunks - 1) / chunks);
+    if (chunks > planes) chunks = planes;
+    xchunk = (int)((planes + chunks - 1) / chunks);
     if (xchunk < 1) xchunk = 1;
-    chunks = (st.nx + xchunk - 1) / xchunk;
+    chunks = (planes + xchunk - 1) / xchunk;
     int64_t items = chunks * tiles;
     int64_t gx = items < resident ? items : resident;
     if (gx < 1) gx = 1;

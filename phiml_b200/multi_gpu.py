@@ -1,0 +1,236 @@
+"""
+Multi-GPU drivers for the path.  One process per GPU (``torchrun``), ``torch.distributed`` for the plumbing
+(NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests).  The reference has no multi-GPU concept at all
+(README.md:78 "does not currently allow mapping operations onto multiple GPUs"), so this is new design:
+
+``solve_sharded``  independent systems (a batch of right-hand sides sharing one matrix, BASELINE config 3): the batch axis is
+                   cut into contiguous shards, every rank solves its shard with the ordinary device loop.  No collective
+                   inside the loop.  The only coupling the reference's semantics require is the batch-wide MINIMUM of the
+                   squared tolerances (the (batch,batch) broadcast of stop_on_l2, phiml/backend/_linalg.py:26-29): one scalar
+                   all-reduce(min) after the initial residual.
+
+``SlabCG``         ONE large system (north-star 1024^3 case): row partition in x-slabs.  Rank g owns planes [x_g, x_{g+1})
+                   and keeps one halo plane per neighbour.  Per CG iteration: two all-reduces of the per-system dot products
+                   (d.q and r.M^-1 r; the kernels leave the local sums in a device buffer and the scalar step runs identically on
+                   every rank afterwards) and one halo exchange of the residual (2 planes per rank over NVLink); the direction's
+                   halo planes are recomputed locally by the fused kernel, so they never travel.
+"""
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# partitioning helpers (pure host logic; covered by the gloo tests)
+# ----------------------------------------------------------------------------------------------------------------------
+
+def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``range(total)``: the first ``total % world`` ranks get one extra item."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def slab_bounds(nx: int, world: int, rank: int) -> Tuple[int, int]:
+    lo, hi = shard_bounds(nx, world, rank)
+    if hi - lo < 1:
+        raise ValueError(f"slab partition needs at least one plane per rank (nx={nx}, world={world})")
+    return lo, hi
+
+
+def exchange_halo_planes(ext: torch.Tensor, nxl: int, plane: int, rank: int, world: int, group=None):
+    """
+    ``ext`` is a (batch, (nxl+2)*plane) tensor: owned planes 1..nxl, halo planes 0 and nxl+1.  Sends the first / last owned
+    plane to the lower / upper neighbour and receives their boundary planes into the halos.  Physical boundaries keep zeros.
+    """
+    if world == 1:
+        return
+    v = ext.view(ext.shape[0], nxl + 2, plane)
+    ops, keep = [], []
+    if rank > 0:
+        lo_send = v[:, 1, :].contiguous()
+        lo_recv = torch.empty_like(lo_send)
+        ops += [dist.P2POp(dist.isend, lo_send, rank - 1, group), dist.P2POp(dist.irecv, lo_recv, rank - 1, group)]
+        keep.append((0, lo_recv))
+    if rank < world - 1:
+        hi_send = v[:, nxl, :].contiguous()
+        hi_recv = torch.empty_like(hi_send)
+        ops += [dist.P2POp(dist.isend, hi_send, rank + 1, group), dist.P2POp(dist.irecv, hi_recv, rank + 1, group)]
+        keep.append((nxl + 1, hi_recv))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for idx, buf in keep:
+        v[:, idx, :].copy_(buf)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# independent systems
+# ----------------------------------------------------------------------------------------------------------------------
+
+def solve_sharded(method: str, lin, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: np.ndarray, pre=None, group=None):
+    """
+    Every rank passes ITS shard of the right-hand sides (``shard_bounds`` gives the split).  Returns the local SolveResult.
+    Identical to one ``linear_solve`` over the whole batch: the tolerance every system has to reach is the minimum over ALL
+    ranks' systems, exactly as in the single-process reference.
+    """
+    from . import solve as host
+    from . import _engine as E
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return host.linear_solve(method, lin, y_local, x0_local, rtol, atol, max_iter, pre, None)
+    code, order, name = _method_code(method, pre, max_iter)
+    matrix, y, x0, rtol_t, atol_t, max_iter = host._prepare(lin, y_local, x0_local, rtol, atol, max_iter)
+    pre = host._device_pre(pre, matrix)
+    sm = matrix.stencil if matrix.stencil is not None else matrix
+    nb = y.shape[0]
+    mi = torch.as_tensor(np.broadcast_to(np.asarray(max_iter)[-1, :], (nb,)).astype(np.int32).copy(), device=y.device)
+    solver = host.DeviceSolver(sm, pre, code, order, nb)
+    solver.start(y, x0, rtol_t, atol_t, mi)
+    tol = solver.get_tol_min()                     # local minimum of max(rtol^2 * norm, atol^2)
+    dist.all_reduce(tol, op=dist.ReduceOp.MIN, group=group)
+    solver.set_tol_min(tol)                        # re-runs the first progress check with the global minimum
+    solver.run(int(np.max(max_iter)))
+    its, fev, conv, div = solver.result()
+    return host.SolveResult(name, solver.x, solver.r, its, fev, conv, div, [""] * nb)
+
+
+def _method_code(method: str, pre, max_iter):
+    from . import _engine as E
+    from .solve import BACKEND_NAME, _pre_str
+    single = np.asarray(max_iter).shape[0] == 1
+    if method == 'CG':
+        if pre or not single:
+            return E.CG, 0, f"Φ-ML CG ({BACKEND_NAME}) {_pre_str(pre)}"
+        return E.CG_TORCH, 0, "Φ-ML CG (PyTorch*)"
+    if method in ('auto', 'CG-adaptive'):
+        if pre:
+            return E.CG, 0, f"Φ-ML CG ({BACKEND_NAME}) {_pre_str(pre)}"
+        return (E.CG_ADAPTIVE_TORCH, 0, "Φ-ML CG (PyTorch*)") if single else (E.CG_ADAPTIVE, 0, f"Φ-ML CG-adaptive ({BACKEND_NAME}) ")
+    if method == 'biCG-stab':
+        return E.BICGSTAB, 1, f"Φ-ML biCG-stab {_pre_str(pre)}"
+    if method.startswith('biCG-stab('):
+        order = int(method[len('biCG-stab('):-1])
+        return E.BICGSTAB, order, (f"Φ-ML biCG-stab {_pre_str(pre)}" if order == 1 else f"Φ-ML biCG-stab({order}) ({BACKEND_NAME}) {_pre_str(pre)}")
+    raise NotImplementedError(f"Method '{method}' not supported for sharded solves.")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one system, x-slab row partition
+# ----------------------------------------------------------------------------------------------------------------------
+
+class SlabCG:
+    """
+    Jacobi- or un-preconditioned CG (the generic loop of phiml/backend/_linalg.py:52-90) for ONE star-stencil system whose grid
+    is split into x-slabs over the ranks of ``group``.
+
+    ``engine_factory(local_ext_grid, xb, xe)`` builds the per-rank engine; the default is the CUDA engine below, the CPU tests
+    inject a NumPy engine with the same five steps to exercise partitioning, halo exchange and the collective sequence with gloo.
+    """
+
+    def __init__(self, grid: Sequence[int], offsets, coeffs, dtype: torch.dtype, jacobi: bool = True, device=None, group=None, engine_factory=None):
+        assert len(grid) == 3, "slab partition is for 3-D grids (x is the partitioned axis)"
+        self.grid = tuple(int(g) for g in grid)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.x_lo, self.x_hi = slab_bounds(self.grid[0], self.world, self.rank)
+        self.nxl = self.x_hi - self.x_lo
+        self.plane = self.grid[1] * self.grid[2]
+        self.dtype = dtype
+        self.device = device
+        ext_grid = (self.nxl + 2, self.grid[1], self.grid[2])
+        factory = engine_factory or (lambda g, xb, xe: CudaSlabEngine(g, xb, xe, offsets, coeffs, dtype, jacobi, device))
+        self.engine = factory(ext_grid, 1, self.nxl + 1)
+
+    # local (batch, nxl*plane) <-> extended (batch, (nxl+2)*plane) with zero halos
+    def extend(self, v: torch.Tensor) -> torch.Tensor:
+        out = torch.zeros((v.shape[0], (self.nxl + 2) * self.plane), dtype=v.dtype, device=v.device)
+        out[:, self.plane:(self.nxl + 1) * self.plane] = v
+        return out
+
+    def interior(self, ext: torch.Tensor) -> torch.Tensor:
+        return ext[:, self.plane:(self.nxl + 1) * self.plane]
+
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _halo(self, ext: torch.Tensor):
+        exchange_halo_planes(ext, self.nxl, self.plane, self.rank, self.world, self.group)
+
+    def solve(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, poll_every: int = 16, fixed_iterations: Optional[int] = None):
+        """
+        ``y_local``/``x0_local``: this rank's slab, shape (batch, nxl*ny*nz).  Returns (x_local, residual_local, iterations,
+        function_evaluations, converged, diverged) — the scalars are identical on every rank.
+        ``fixed_iterations`` runs exactly that many iterations without polling (throughput measurements).
+        """
+        eng = self.engine
+        y_ext, x_ext = self.extend(y_local), self.extend(x0_local)
+        self._halo(x_ext)                                   # A x0 needs the neighbours' boundary planes
+        eng.start(y_ext, x_ext, rtol, atol, max_iter)       # local sums of r.s, y.y, r.r -> eng.totals
+        self._allreduce(eng.totals)
+        eng.step(10)                                        # tolerances, first progress check (identical on all ranks)
+        self._halo(eng.r)
+        self._halo(eng.d0)                                  # d_0 = M^-1 r_0 including the halo planes
+        done = 0
+        limit = fixed_iterations if fixed_iterations is not None else max_iter
+        while done < limit:
+            n = min(poll_every, limit - done)
+            for _ in range(n):
+                eng.step(0)                                 # d, x, q = A d, local d.q
+                self._allreduce(eng.totals)
+                eng.step(1)                                 # alpha ; r -= alpha q, local r.M^-1 r
+                self._allreduce(eng.totals)
+                eng.step(2)                                 # beta, delta, progress check
+                self._halo(eng.r)
+            done += n
+            if fixed_iterations is None and not eng.any_continue():
+                break
+        eng.step(20)                                        # pending x += alpha d
+        its, fev, conv, div = eng.result()
+        return self.interior(eng.x), self.interior(eng.r), its, fev, conv, div
+
+
+class CudaSlabEngine:
+    """The five steps on libphb200 (phb200_matrix_set_slab + phb200_solver_set_dist / _dist_step)."""
+
+    def __init__(self, ext_grid, xb, xe, offsets, coeffs, dtype, jacobi, device):
+        import ctypes
+        from . import _engine as E
+        from .sparse import Matrix
+        from .precond import JacobiPreconditioner
+        self.E = E
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.matrix = Matrix.stencil_matrix(ext_grid, offsets, coeffs, dtype, self.device)
+        E.check(E.lib().phb200_matrix_set_slab(self.matrix.handle, xb, xe))
+        self.pre = JacobiPreconditioner(self.matrix) if jacobi else None
+        self.solver = None
+
+    def start(self, y_ext, x_ext, rtol, atol, max_iter):
+        from .solve import DeviceSolver
+        E = self.E
+        nb = y_ext.shape[0]
+        dev = y_ext.device
+        self.totals = torch.zeros(nb * 4, dtype=torch.float64, device=dev)
+        self.solver = DeviceSolver(self.matrix, self.pre, E.CG, 0, nb)
+        E.check(E.lib().phb200_solver_set_dist(self.solver._h, E.ptr(self.totals)))
+        rt = torch.as_tensor(rtol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
+        at = torch.as_tensor(atol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
+        mi = torch.full((nb,), int(max_iter), dtype=torch.int32, device=dev)
+        self.solver.start(y_ext, x_ext, rt, at, mi, zero_init=True)
+        n_ext = y_ext.shape[1]
+        self.x, self.r = self.solver.x, self.solver.r
+        ws = self.solver.workspace
+        self.d0 = ws[: nb * n_ext * y_ext.element_size()].view(y_ext.dtype).view(nb, n_ext)   # work vector 0 = first direction buffer
+
+    def step(self, code: int):
+        E = self.E
+        E.check(E.lib().phb200_solver_dist_step(self.solver._h, code, E.stream_ptr(self.x.device)))
+
+    def any_continue(self) -> bool:
+        return self.solver.any_continue()
+
+    def result(self):
+        return self.solver.result()

@@ -54,12 +54,13 @@ class DeviceSolver:
         self.workspace = None
         self._keep = ()
 
-    def start(self, y, x0, rtol, atol, max_iter):
+    def start(self, y, x0, rtol, atol, max_iter, zero_init=False):
         dev = y.device
-        self.x = torch.empty_like(y)
-        self.r = torch.empty_like(y)
+        alloc = torch.zeros_like if zero_init else torch.empty_like     # slab mode: halo planes must start as zeros
+        self.x = alloc(y)
+        self.r = alloc(y)
         nbytes = int(E.lib().phb200_solver_workspace_bytes(self._h))
-        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.workspace = (torch.zeros if zero_init else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
         self._keep = (y, x0, rtol, atol, max_iter)
         E.check(E.lib().phb200_solver_start(self._h, E.ptr(y), E.ptr(x0), E.ptr(self.x), E.ptr(self.r), E.ptr(rtol), E.ptr(atol), E.ptr(max_iter),
                                             E.ptr(self.workspace), nbytes, E.stream_ptr(dev)))
@@ -84,6 +85,15 @@ class DeviceSolver:
         div = torch.empty(nb, dtype=torch.uint8, device=dev)
         E.check(E.lib().phb200_solver_result(self._h, E.ptr(its), E.ptr(fev), E.ptr(conv), E.ptr(div), E.stream_ptr(dev)))
         return its, fev, conv.bool(), div.bool()
+
+    def get_tol_min(self) -> torch.Tensor:
+        t = torch.empty(1, dtype=torch.float64, device=self.x.device)
+        E.check(E.lib().phb200_solver_tol_min(self._h, E.ptr(t), 0, E.stream_ptr(self.x.device)))
+        return t
+
+    def set_tol_min(self, t: torch.Tensor):
+        self._keep = self._keep + (t,)
+        E.check(E.lib().phb200_solver_tol_min(self._h, E.ptr(t), 1, E.stream_ptr(self.x.device)))
 
     def profile(self, enable: bool):
         E.check(E.lib().phb200_solver_profile(self._h, 1 if enable else 0))

@@ -1,0 +1,90 @@
+"""
+Multi-GPU slab CG check + throughput (run under torchrun, one rank per GPU):
+
+    torchrun --nproc-per-node N scripts/run_slab.py --n 256 --check          # parity against a single-GPU solve on rank 0
+    torchrun --nproc-per-node N scripts/run_slab.py --n 1024 --iters 100     # strong-scaling throughput (fixed iterations)
+
+Prints one JSON line from rank 0.
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+import phiml_b200 as pb
+from phiml_b200.multi_gpu import SlabCG
+from oracle.assemble import laplace_shifts
+
+p = argparse.ArgumentParser()
+p.add_argument('--n', type=int, default=256)
+p.add_argument('--iters', type=int, default=100)
+p.add_argument('--warmup', type=int, default=10)
+p.add_argument('--check', action='store_true')
+a = p.parse_args()
+world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); lr = int(os.environ.get('LOCAL_RANK', '0'))
+torch.cuda.set_device(lr); dev = torch.device('cuda', lr)
+if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+n = a.n; grid = (n, n, n); plane = n * n
+shifts = laplace_shifts(3); offsets = [s for s, _ in shifts]; coeffs = [c for _, c in shifts]
+cg = SlabCG(grid, offsets, coeffs, torch.float32, jacobi=True, device=dev)
+gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
+out = {"n": n, "world": world}
+if a.check:
+    # same right-hand side everywhere: generated per global plane index so that any partition sees identical data
+    y_full = None
+    if rank == 0:
+        y_full = torch.as_tensor(np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32), device=dev)
+    y_loc = torch.empty((1, cg.nxl * plane), dtype=torch.float32, device=dev)
+    if world > 1:
+        if rank == 0:
+            for r in range(1, world):
+                from phiml_b200.multi_gpu import slab_bounds
+                lo, hi = slab_bounds(n, world, r)
+                dist.send(y_full[:, lo * plane:hi * plane].contiguous(), r)
+            y_loc.copy_(y_full[:, :cg.nxl * plane])
+        else:
+            dist.recv(y_loc, 0)
+    else:
+        y_loc.copy_(y_full)
+    x, r_, its, fev, conv, div = cg.solve(y_loc, torch.zeros_like(y_loc), [1e-5], [0.0], 5000)
+    out.update(iterations=int(its[0]), converged=bool(conv[0]))
+    xs = [torch.empty((1, (slab_bounds(n, world, r)[1] - slab_bounds(n, world, r)[0]) * plane), dtype=torch.float32, device=dev) for r in range(world)] if world > 1 and rank == 0 else None
+    if world > 1:
+        if rank == 0:
+            xs[0].copy_(x)
+            for r in range(1, world):
+                dist.recv(xs[r], r)
+            x_all = torch.cat(xs, dim=1)
+        else:
+            dist.send(x.contiguous(), 0)
+    else:
+        x_all = x
+    if rank == 0:
+        st = pb.Matrix.stencil_matrix(grid, offsets, coeffs, torch.float32, dev)
+        ref = pb.generic_conjugate_gradient(st, y_full, torch.zeros_like(y_full), [1e-5], [0.0], np.array([[5000]]), pb.JacobiPreconditioner(st))
+        out.update(ref_iterations=int(ref.iterations[0]), rel_err=float((x_all - ref.x).abs().max() / ref.x.abs().max()),
+                   true_residual=float((y_full - st.matvec(x_all)).norm() / y_full.norm()))
+else:
+    y_loc = torch.randn((1, cg.nxl * plane), dtype=torch.float32, device=dev, generator=gen)
+    x0 = torch.zeros_like(y_loc)
+    cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=a.warmup)
+    torch.cuda.synchronize(dev)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=a.iters)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
+    # the timed solve includes its own start-up (initial residual, 2 halo exchanges); report per-iteration over the whole call
+    N = n ** 3
+    out.update(iters=a.iters, ms_total=ms, iterations_per_s=a.iters / (ms * 1e-3), bytes_design_per_it=9 * N * 4,
+               agg_gbs_design=9 * N * 4 * a.iters / (ms * 1e-3) / 1e9, halo_bytes_per_rank_per_it=2 * plane * 4)
+if rank == 0:
+    print(json.dumps(out))
+if world > 1:
+    dist.destroy_process_group()

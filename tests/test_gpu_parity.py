@@ -357,3 +357,43 @@ def test_full_size_256_cubed_jacobi_cg():
     assert torch.equal(csr.matvec(x1, use_stencil=False), st.matvec(x1))
     res_csr = pb.generic_conjugate_gradient(csr, y, torch.zeros_like(y), [1e-5], [0.0], np.array([[5000]]), pb.JacobiPreconditioner(csr))
     assert abs(int(res_csr.iterations[0]) - 553) <= 2
+
+
+# ------------------------------------------------------------------------------------------------- multi-GPU building blocks
+
+def test_slab_engine_single_rank_equals_plain_solve():
+    """SlabCG on one rank (extended array with two zero halo planes, host-driven half steps, deferred finalisation) must
+    reproduce the ordinary device loop: same iterations, same iterate."""
+    from phiml_b200.multi_gpu import SlabCG
+    grid = (24, 16, 32)
+    shifts = shifts_for('poisson', 3, np.float32)
+    offsets, coeffs = [s for s, _ in shifts], [float(c) for _, c in shifts]
+    n = int(np.prod(grid))
+    y = torch.as_tensor(np.random.default_rng(0).standard_normal((2, n)).astype(np.float32), device=DEV)
+    st = pb.Matrix.stencil_matrix(grid, offsets, coeffs, torch.float32, DEV)
+    ref = pb.generic_conjugate_gradient(st, y, torch.zeros_like(y), [1e-5, 1e-5], [0.0, 0.0], np.array([[1000, 1000]]), pb.JacobiPreconditioner(st))
+    cg = SlabCG(grid, offsets, coeffs, torch.float32, jacobi=True, device=DEV)
+    x, r, its, fev, conv, div = cg.solve(y, torch.zeros_like(y), [1e-5, 1e-5], [0.0, 0.0], 1000, poll_every=5)
+    assert torch.equal(its, ref.iterations) and torch.equal(fev, ref.function_evaluations)
+    assert bool(conv.all()) and not bool(div.any())
+    assert float((x - ref.x).abs().max() / ref.x.abs().max()) < 1e-6
+    assert float((r - ref.residual).abs().max()) < 1e-5 * float(y.abs().max())
+
+
+def test_batch_minimum_tolerance_can_be_replaced_before_the_first_pass():
+    """Hook used by multi_gpu.solve_sharded: installing a smaller (global) tolerance makes the local systems iterate longer."""
+    case, csr, y, x0, rtol, atol, max_iter = case_inputs('p32_batch8_f32')
+    m = pb.as_matrix(dev_csr(csr))
+    yd = torch.as_tensor(y, device=DEV)
+    base = pb.generic_conjugate_gradient(m, yd, torch.zeros_like(yd), rtol, atol, max_iter)
+    solver = pb.DeviceSolver(m.stencil, None, E.CG, 0, yd.shape[0])
+    solver.start(yd, torch.zeros_like(yd), torch.as_tensor(rtol, device=DEV), torch.as_tensor(atol, device=DEV), torch.full((yd.shape[0],), 5000, dtype=torch.int32, device=DEV))
+    t = solver.get_tol_min()
+    solver.set_tol_min(t.clone())
+    solver.run(5000)
+    assert torch.equal(solver.result()[0], base.iterations)
+    solver2 = pb.DeviceSolver(m.stencil, None, E.CG, 0, yd.shape[0])
+    solver2.start(yd, torch.zeros_like(yd), torch.as_tensor(rtol, device=DEV), torch.as_tensor(atol, device=DEV), torch.full((yd.shape[0],), 5000, dtype=torch.int32, device=DEV))
+    solver2.set_tol_min(t * 1e-4)
+    solver2.run(5000)
+    assert bool((solver2.result()[0] > base.iterations).all())
