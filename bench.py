@@ -177,9 +177,17 @@ def run_ours(args):
     w = 4
     shifts = laplace_shifts(3)
     stencil = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [c for _, c in shifts], torch.float32, dev)
-    csr = stencil.to_csr()                  # the native the torch backend would hold (device-side assembly, bit-exact)
-    native = torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape)
-    if args.format == 'stencil':
+    too_big_for_csr = stencil.nnz() >= 2 ** 31      # int32 CSR (the reference's native) cannot hold it: stencil handle only
+    if too_big_for_csr:
+        assert args.format == 'stencil'
+        args.no_e2e = True
+        csr, native, matrix, solver_matrix = None, None, stencil, stencil
+    else:
+        csr = stencil.to_csr()              # the native the torch backend would hold (device-side assembly, bit-exact)
+        native = torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape)
+    if too_big_for_csr:
+        pass
+    elif args.format == 'stencil':
         matrix = pb.as_matrix(native)       # recognised as a stencil on the device
         assert matrix.stencil is not None, "stencil recognition failed"
         solver_matrix = matrix.stencil

@@ -1,8 +1,8 @@
 """
 Multi-GPU slab CG check + throughput (run under torchrun, one rank per GPU):
 
-    torchrun --nproc-per-node N scripts/run_slab.py --n 256 --check          # parity against a single-GPU solve on rank 0
-    torchrun --nproc-per-node N scripts/run_slab.py --n 1024 --iters 100     # strong-scaling throughput (fixed iterations)
+    torchrun --nproc-per-node N scripts/run_slab.py --size 256 --check          # parity against a single-GPU solve on rank 0
+    torchrun --nproc-per-node N scripts/run_slab.py --size 1024 --iters 100     # strong-scaling throughput (fixed iterations)
 
 Prints one JSON line from rank 0.
 """
@@ -15,7 +15,7 @@ from phiml_b200.multi_gpu import SlabCG
 from oracle.assemble import laplace_shifts
 
 p = argparse.ArgumentParser()
-p.add_argument('--n', type=int, default=256)
+p.add_argument('--size', dest='n', type=int, default=256)
 p.add_argument('--iters', type=int, default=100)
 p.add_argument('--warmup', type=int, default=10)
 p.add_argument('--check', action='store_true')
@@ -67,23 +67,28 @@ if a.check:
 else:
     y_loc = torch.randn((1, cg.nxl * plane), dtype=torch.float32, device=dev, generator=gen)
     x0 = torch.zeros_like(y_loc)
-    cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=a.warmup)
-    torch.cuda.synchronize(dev)
-    if world > 1: dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=a.iters)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
-    # the timed solve includes its own start-up (initial residual, 2 halo exchanges); report per-iteration over the whole call
+    def timed(iters):
+        torch.cuda.synchronize(dev)
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=iters)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t[0])
+        return ms
+    timed(a.warmup)
+    # a solve call = set-up (extended arrays, initial residual, 2 halo exchanges) + iterations: the slope between two
+    # iteration counts is the per-iteration time, the intercept the set-up
+    ms1, ms2 = timed(a.iters), timed(2 * a.iters)
+    per_it = (ms2 - ms1) / a.iters
     N = n ** 3
-    out.update(iters=a.iters, ms_total=ms, iterations_per_s=a.iters / (ms * 1e-3), bytes_design_per_it=9 * N * 4,
-               agg_gbs_design=9 * N * 4 * a.iters / (ms * 1e-3) / 1e9, halo_bytes_per_rank_per_it=2 * plane * 4)
+    out.update(iters=[a.iters, 2 * a.iters], ms_total=[ms1, ms2], ms_per_iteration=per_it, setup_ms=ms1 - per_it * a.iters, iterations_per_s=1e3 / per_it,
+               bytes_design_per_it=9 * N * 4, agg_gbs_design=9 * N * 4 / (per_it * 1e-3) / 1e9, agg_gbs_survey_model=13 * N * 4 / (per_it * 1e-3) / 1e9,
+               halo_bytes_per_rank_per_it=2 * plane * 4)
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
