@@ -123,8 +123,11 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
 
 /* Exact ILU(0) on the pattern of a CSR matrix with sorted columns and a full diagonal.
  * lu_val (nnz elements, caller-owned) receives L (strict lower, unit diagonal implied) and U (upper incl. diagonal)
- * in A's own pattern.  The handle keeps the dependency-level schedule used by factorisation and both solves. */
-int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, void* stream);
+ * in A's own pattern.  The handle keeps the dependency-level schedule used by factorisation and both solves; both run
+ * sync-free in ONE launch each (rows wait on per-row completion flags; PHB200_TRSV=levels selects one launch per level).
+ * If A was recognised as a star stencil, pass the stencil handle: the levels are then computed analytically on the
+ * device instead of from a host copy of the pattern. */
+int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, const phb200_matrix* stencil_twin /* may be NULL */, void* stream);
 /* number of dependency levels of the lower / upper solve (diagnostics) */
 int phb200_precond_levels(const phb200_precond* p, int64_t* lower_levels, int64_t* upper_levels);
 

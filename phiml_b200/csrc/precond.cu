@@ -1,6 +1,7 @@
 // Preconditioners: Jacobi set-up, exact ILU(0) with a level schedule, level-scheduled sparse triangular solves.
 #include "phase.cuh"
 #include "precond.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <vector>
 #include <stdlib.h>
 
@@ -28,6 +29,69 @@ __global__ void __launch_bounds__(kBlock) k_jacobi_const(T* __restrict__ inv_dia
 // ---------------------------------------------------------------------------------------------- level schedule
 // level(i) = 1 + max level of the rows i depends on (columns < i for a lower, > i for an upper solve).  Rows of one
 // level are independent.  The analysis runs once per matrix on the host (O(nnz)), the schedule lives on the device.
+__global__ void __launch_bounds__(kBlock) k_pad_order(const int32_t* __restrict__ order, int64_t n, const int32_t* __restrict__ level_ptr, const int64_t* __restrict__ pad_ptr,
+                                                      int32_t n_levels, int32_t* __restrict__ order_pad) {
+    for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < n; k += (int64_t)gridDim.x * kBlock) {
+        int lo = 0, hi = n_levels;   // level l with level_ptr[l] <= k < level_ptr[l+1]
+        while (lo + 1 < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (level_ptr[mid] <= k) lo = mid;
+            else hi = mid;
+        }
+        order_pad[pad_ptr[lo] + (k - level_ptr[lo])] = order[k];
+    }
+}
+
+// p->order holds the rows sorted by level; level_ptr (host) the level boundaries.  Builds the device tables.
+static int finish_plan(phb200_trsv_plan* p, const std::vector<int32_t>& level_ptr, cudaStream_t stream) {
+    const int64_t n = p->n;
+    const int32_t n_levels = (int32_t)level_ptr.size() - 1;
+    p->n_levels = n_levels;
+    std::vector<int64_t> pad_ptr(n_levels + 1, 0);
+    int32_t max_rows = 0;
+    for (int32_t l = 0; l < n_levels; ++l) {
+        const int32_t cnt = level_ptr[l + 1] - level_ptr[l];
+        if (cnt > max_rows) max_rows = cnt;
+        pad_ptr[l + 1] = pad_ptr[l] + ((cnt + 31) / 32) * 32;
+    }
+    p->max_level_rows = max_rows;
+    p->npad = pad_ptr[n_levels];
+    p->epoch = 0;
+    p->h_level_ptr = (int32_t*)malloc(sizeof(int32_t) * (n_levels + 1));
+    memcpy(p->h_level_ptr, level_ptr.data(), sizeof(int32_t) * (n_levels + 1));
+    int64_t* d_pad_ptr = nullptr;
+    cudaError_t e = cudaMalloc(&p->level_ptr, sizeof(int32_t) * (n_levels + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->order_pad, sizeof(int32_t) * (p->npad > 0 ? p->npad : 1));
+    const int64_t nwarps = p->npad / 32;
+    std::vector<int32_t> warp_level((size_t)(nwarps > 0 ? nwarps : 1), 0), level_warps((size_t)(n_levels > 0 ? n_levels : 1), 0);
+    for (int32_t l = 0; l < n_levels; ++l) {
+        level_warps[l] = (int32_t)((pad_ptr[l + 1] - pad_ptr[l]) / 32);
+        for (int64_t w = pad_ptr[l] / 32; w < pad_ptr[l + 1] / 32; ++w) warp_level[w] = l;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&p->warp_level, sizeof(int32_t) * warp_level.size());
+    if (e == cudaSuccess) e = cudaMalloc(&p->level_warps, sizeof(int32_t) * level_warps.size());
+    if (e == cudaSuccess) e = cudaMalloc(&p->level_cnt, sizeof(unsigned long long) * level_warps.size());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->warp_level, warp_level.data(), sizeof(int32_t) * warp_level.size(), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->level_warps, level_warps.data(), sizeof(int32_t) * level_warps.size(), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->level_cnt, 0, sizeof(unsigned long long) * level_warps.size(), stream);
+    if (e == cudaSuccess) e = cudaMalloc(&d_pad_ptr, sizeof(int64_t) * (n_levels + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->level_ptr, level_ptr.data(), sizeof(int32_t) * (n_levels + 1), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pad_ptr, pad_ptr.data(), sizeof(int64_t) * (n_levels + 1), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->order_pad, 0xFF, sizeof(int32_t) * (p->npad > 0 ? p->npad : 1), stream);
+    if (e == cudaSuccess && n > 0) {
+        k_pad_order<<<(unsigned)grid_x((n + kBlock - 1) / kBlock, 1), kBlock, 0, stream>>>(p->order, n, p->level_ptr, d_pad_ptr, n_levels, p->order_pad);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // pad_ptr (host vector) must outlive the copy
+    if (d_pad_ptr) cudaFree(d_pad_ptr);
+    if (e != cudaSuccess) {
+        set_error("level schedule upload failed: %s", cudaGetErrorString(e));
+        return PHB200_ERR_CUDA;
+    }
+    return PHB200_OK;
+}
+
 static int build_plan(phb200_trsv_plan** out, const CsrView& A, int lower, cudaStream_t stream) {
     const int64_t n = A.n_rows;
     std::vector<int32_t> rowptr(n + 1), col((size_t)A.nnz);
@@ -66,18 +130,90 @@ static int build_plan(phb200_trsv_plan** out, const CsrView& A, int lower, cudaS
     memset(p, 0, sizeof(*p));
     p->lower = lower;
     p->n = n;
-    p->n_levels = n_levels;
-    p->max_level_rows = max_rows;
-    p->h_level_ptr = (int32_t*)malloc(sizeof(int32_t) * (n_levels + 1));
-    memcpy(p->h_level_ptr, level_ptr.data(), sizeof(int32_t) * (n_levels + 1));
     cudaError_t e = cudaMalloc(&p->order, sizeof(int32_t) * (n > 0 ? n : 1));
-    if (e == cudaSuccess) e = cudaMalloc(&p->level_ptr, sizeof(int32_t) * (n_levels + 1));
     if (e == cudaSuccess) e = cudaMemcpy(p->order, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(p->level_ptr, level_ptr.data(), sizeof(int32_t) * (n_levels + 1), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("level schedule upload failed: %s", cudaGetErrorString(e));
         phb200_sptrsv_plan_destroy(p);
         return PHB200_ERR_CUDA;
+    }
+    int r = finish_plan(p, level_ptr, stream);
+    if (r != PHB200_OK) {
+        phb200_sptrsv_plan_destroy(p);
+        return r;
+    }
+    *out = p;
+    return PHB200_OK;
+}
+
+// ---- device-side analysis for star stencils: level = sum of the indices along the axes that carry a dependency ------
+__global__ void __launch_bounds__(kBlock) k_star_levels(StarDesc st, int lower, int32_t* __restrict__ level, int32_t* __restrict__ row) {
+    const int64_t n = st.nx * st.ny * st.nz;
+    const bool dx = lower ? st.cxm != 0.0 : st.cxp != 0.0, dy = lower ? st.cym != 0.0 : st.cyp != 0.0, dz = lower ? st.czm != 0.0 : st.czp != 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t iz = i % st.nz, iy = (i / st.nz) % st.ny, ix = i / (st.nz * st.ny);
+        int64_t l = 0;
+        if (dx) l += lower ? ix : st.nx - 1 - ix;
+        if (dy) l += lower ? iy : st.ny - 1 - iy;
+        if (dz) l += lower ? iz : st.nz - 1 - iz;
+        level[i] = (int32_t)l;
+        row[i] = (int32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_level_starts(const int32_t* __restrict__ sorted_level, int64_t n, int32_t n_levels, int32_t* __restrict__ level_ptr) {
+    const int l = blockIdx.x * kBlock + threadIdx.x;
+    if (l > n_levels) return;
+    int64_t lo = 0, hi = n;   // first k with sorted_level[k] >= l
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_level[mid] < l) lo = mid + 1;
+        else hi = mid;
+    }
+    level_ptr[l] = (int32_t)lo;
+}
+
+int build_plan_star(phb200_trsv_plan** out, const StarDesc& st, int lower, cudaStream_t stream) {
+    const int64_t n = st.nx * st.ny * st.nz;
+    const bool dx = lower ? st.cxm != 0.0 : st.cxp != 0.0, dy = lower ? st.cym != 0.0 : st.cyp != 0.0, dz = lower ? st.czm != 0.0 : st.czp != 0.0;
+    const int64_t n_levels = 1 + (dx ? st.nx - 1 : 0) + (dy ? st.ny - 1 : 0) + (dz ? st.nz - 1 : 0);
+    phb200_trsv_plan* p = new phb200_trsv_plan();
+    memset(p, 0, sizeof(*p));
+    p->lower = lower;
+    p->n = n;
+    int32_t *lev = nullptr, *row = nullptr, *lev_sorted = nullptr, *d_level_ptr = nullptr;
+    void* tmp = nullptr;
+    int r = PHB200_OK;
+    std::vector<int32_t> level_ptr(n_levels + 1);
+    do {
+        cudaError_t e = cudaMalloc(&p->order, sizeof(int32_t) * (n > 0 ? n : 1));
+        if (e == cudaSuccess) e = cudaMallocAsync(&lev, sizeof(int32_t) * n, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&row, sizeof(int32_t) * n, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&lev_sorted, sizeof(int32_t) * n, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&d_level_ptr, sizeof(int32_t) * (n_levels + 1), stream);
+        if (e != cudaSuccess) { set_error("level analysis allocation failed: %s", cudaGetErrorString(e)); r = PHB200_ERR_CUDA; break; }
+        k_star_levels<<<(unsigned)grid_x((n + kBlock - 1) / kBlock, 1), kBlock, 0, stream>>>(st, lower, lev, row);
+        int bits = 1;
+        while ((1ll << bits) < n_levels) ++bits;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lev, lev_sorted, row, p->order, (int)n, 0, bits, stream);
+        if (cudaMallocAsync(&tmp, tmp_bytes, stream) != cudaSuccess) { set_error("sort scratch allocation failed"); r = PHB200_ERR_CUDA; break; }
+        cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lev, lev_sorted, row, p->order, (int)n, 0, bits, stream);   // stable: rows ascending inside a level
+        k_level_starts<<<(unsigned)((n_levels + 1 + kBlock - 1) / kBlock), kBlock, 0, stream>>>(lev_sorted, n, (int32_t)n_levels, d_level_ptr);
+        g_launches.fetch_add(4);
+        e = cudaMemcpyAsync(level_ptr.data(), d_level_ptr, sizeof(int32_t) * (n_levels + 1), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { set_error("level analysis failed: %s", cudaGetErrorString(e)); r = PHB200_ERR_CUDA; break; }
+        r = finish_plan(p, level_ptr, stream);
+    } while (0);
+    if (lev) cudaFreeAsync(lev, stream);
+    if (row) cudaFreeAsync(row, stream);
+    if (lev_sorted) cudaFreeAsync(lev_sorted, stream);
+    if (d_level_ptr) cudaFreeAsync(d_level_ptr, stream);
+    if (tmp) cudaFreeAsync(tmp, stream);
+    if (r != PHB200_OK) {
+        phb200_sptrsv_plan_destroy(p);
+        return r;
     }
     *out = p;
     return PHB200_OK;
@@ -104,8 +240,160 @@ __global__ void __launch_bounds__(kBlock) k_trsv_level(CsrView A, const int32_t*
     X[(int64_t)b * ld + i] = unit_diagonal ? acc : acc / diag;
 }
 
+// ---- single-launch execution ----------------------------------------------------------------------------------------
+// Rows sorted by level, levels padded to warp multiples: warp w owns 32 rows of ONE level l.  Lane 0 polls a per-level
+// counter until every warp of level l-1 has finished (by induction all earlier levels are then complete), the warp computes
+// its rows and adds 1 to the counter of level l (one atomic per warp).  All waited-for warps sit at smaller warp indices,
+// i.e. were dispatched earlier, so the chain always advances; one 8-byte poll per warp keeps the L2 quiet (per-row flags
+// polled by every thread saturate it).  Counters accumulate over solves (target = epoch * warps of the level): no reset.
+// A wait that lasts longer than ~2 s traps instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ int g_trsv_max_ns = 1024;   // tuning knobs (PHB200_TRSV_NS / PHB200_TRSV_FENCE), set once from the host
+__device__ int g_trsv_fence_all = 1;
+__device__ __forceinline__ void wait_level(const unsigned long long* cnt, const int32_t* __restrict__ level_warps, int level, int epoch) {
+    const int max_ns = g_trsv_max_ns, fence_all = g_trsv_fence_all;
+    if (level > 0 && (threadIdx.x & 31) == 0) {
+        const unsigned long long target = (unsigned long long)epoch * (unsigned long long)level_warps[level - 1];
+        if (ld_relaxed_u64(cnt + level - 1) < target) {
+            const long long t0 = clock64();
+            unsigned ns = 32;
+            while (ld_relaxed_u64(cnt + level - 1) < target) {
+                if (max_ns > 0) __nanosleep(ns);
+                if ((int)ns < max_ns) ns *= 2;
+                if (clock64() - t0 > 4000000000ll) __trap();
+            }
+        }
+        if (!fence_all) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncwarp();
+    if (fence_all) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+__device__ __forceinline__ void publish_level(unsigned long long* cnt, int level) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence();
+        atomicAdd(cnt + level, 1ull);
+    }
+}
+
+template <typename T, bool LOWER>
+__global__ void __launch_bounds__(kBlock) k_trsv_syncfree(CsrView A, const int32_t* __restrict__ order_pad, int64_t npad, int unit_diagonal,
+                                                          const T* __restrict__ B, T* X, int64_t ld, int batch, const int32_t* __restrict__ warp_level,
+                                                          const int32_t* __restrict__ level_warps, unsigned long long* level_cnt, int epoch) {
+    const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (k >= npad) return;
+    const int level = warp_level[k >> 5];
+    const int i = order_pad[k];
+    const T* __restrict__ val = (const T*)A.val;
+    // Everything that does not depend on other rows is fetched BEFORE the wait: the row's entries (up to kPre of them in
+    // registers) and its right-hand side.  After the wait only the x gathers remain, issued back to back (one L2 latency).
+    constexpr int kPre = 8;
+    int cols[kPre];
+    T vals[kPre];
+    int e0 = 0, e1 = 0;
+    T rhs0 = T(0);
+    T diag = T(1);
+    if (i >= 0) {
+        e0 = A.rowptr[i];
+        e1 = A.rowptr[i + 1];
+        rhs0 = B[i];
+#pragma unroll
+        for (int p = 0; p < kPre; ++p) {
+            const bool in = e0 + p < e1;
+            cols[p] = in ? A.col[e0 + p] : -1;
+            vals[p] = in ? val[e0 + p] : T(0);
+        }
+#pragma unroll
+        for (int p = 0; p < kPre; ++p) {
+            if (cols[p] == i) diag = vals[p];
+            if (cols[p] >= 0 && !(LOWER ? (cols[p] < i) : (cols[p] > i))) cols[p] = -1;   // keep dependencies only
+        }
+    }
+    wait_level(level_cnt, level_warps, level, epoch);
+    if (i >= 0) {
+        for (int b = 0; b < batch; ++b) {
+            T acc = b == 0 ? rhs0 : B[(int64_t)b * ld + i];
+            const T* xb = X + (int64_t)b * ld;
+            T xs[kPre];
+#pragma unroll
+            for (int p = 0; p < kPre; ++p) xs[p] = cols[p] >= 0 ? __ldcg(xb + cols[p]) : T(0);   // written by other SMs: read through L2
+#pragma unroll
+            for (int p = 0; p < kPre; ++p) acc -= vals[p] * xs[p];
+            for (int e = e0 + kPre; e < e1; ++e) {   // rows longer than kPre entries
+                const int j = A.col[e];
+                if (LOWER ? (j < i) : (j > i)) acc -= val[e] * __ldcg(xb + j);
+                else if (j == i) diag = val[e];
+            }
+            X[(int64_t)b * ld + i] = unit_diagonal ? acc : acc / diag;
+        }
+    }
+    publish_level(level_cnt, level);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_ilu0_syncfree(CsrView A, T* lu, const int32_t* __restrict__ diag_pos, const int32_t* __restrict__ order_pad,
+                                                          int64_t npad, const int32_t* __restrict__ warp_level, const int32_t* __restrict__ level_warps,
+                                                          unsigned long long* level_cnt, int epoch) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= npad) return;
+    const int level = warp_level[t >> 5];
+    const int i = order_pad[t];
+    wait_level(level_cnt, level_warps, level, epoch);
+    if (i >= 0) {
+        const int beg = A.rowptr[i], end = A.rowptr[i + 1];
+        for (int p = beg; p < end; ++p) {
+            const int k = A.col[p];
+            if (k >= i) break;
+            const int dk = diag_pos[k];
+            const T lik = lu[p] / __ldcg(lu + dk);
+            lu[p] = lik;
+            int q = dk + 1;
+            const int qend = A.rowptr[k + 1];
+            int c = p + 1;
+            while (q < qend && c < end) {
+                const int jq = A.col[q], jc = A.col[c];
+                if (jq == jc) {
+                    lu[c] = lu[c] - lik * __ldcg(lu + q);
+                    ++q;
+                    ++c;
+                } else if (jq < jc) {
+                    ++q;
+                } else {
+                    ++c;
+                }
+            }
+        }
+    }
+    publish_level(level_cnt, level);
+}
+
+static bool use_level_launches() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PHB200_TRSV");
+        v = (e && strcmp(e, "levels") == 0) ? 1 : 0;
+        const char* ns = getenv("PHB200_TRSV_NS");
+        const char* fa = getenv("PHB200_TRSV_FENCE");
+        if (ns) { int x = atoi(ns); cudaMemcpyToSymbol(g_trsv_max_ns, &x, sizeof(int)); }
+        if (fa) { int x = atoi(fa); cudaMemcpyToSymbol(g_trsv_fence_all, &x, sizeof(int)); }
+    }
+    return v == 1;
+}
+
 template <typename T>
 static int trsv(const CsrView& A, const phb200_trsv_plan* plan, int lower, int unit_diagonal, const T* B, T* X, int64_t batch, int64_t ld, cudaStream_t stream) {
+    if (!use_level_launches()) {
+        if (plan->npad == 0) return PHB200_OK;
+        const int epoch = ++const_cast<phb200_trsv_plan*>(plan)->epoch;
+        const unsigned grid = (unsigned)((plan->npad + kBlock - 1) / kBlock);
+        if (lower) PHB_LAUNCH((k_trsv_syncfree<T, true>), grid, kBlock, 0, stream, A, plan->order_pad, plan->npad, unit_diagonal, B, X, ld, (int)batch, plan->warp_level, plan->level_warps, plan->level_cnt, epoch);
+        else PHB_LAUNCH((k_trsv_syncfree<T, false>), grid, kBlock, 0, stream, A, plan->order_pad, plan->npad, unit_diagonal, B, X, ld, (int)batch, plan->warp_level, plan->level_warps, plan->level_cnt, epoch);
+        return PHB200_OK;
+    }
     for (int64_t l = 0; l < plan->n_levels; ++l) {
         const int r0 = plan->h_level_ptr[l], r1 = plan->h_level_ptr[l + 1];
         if (r1 == r0) continue;
@@ -164,6 +452,12 @@ template <typename T>
 static int ilu0_factor(const phb200_precond* p, cudaStream_t stream) {
     const phb200_trsv_plan* plan = p->plan_l;
     T* lu = (T*)p->lu.val;
+    if (!use_level_launches()) {
+        if (plan->npad == 0) return PHB200_OK;
+        const int epoch = ++const_cast<phb200_trsv_plan*>(plan)->epoch;
+        PHB_LAUNCH(k_ilu0_syncfree<T>, (unsigned)((plan->npad + kBlock - 1) / kBlock), kBlock, 0, stream, p->lu, lu, p->diag_pos, plan->order_pad, plan->npad, plan->warp_level, plan->level_warps, plan->level_cnt, epoch);
+        return PHB200_OK;
+    }
     for (int64_t l = 0; l < plan->n_levels; ++l) {
         const int r0 = plan->h_level_ptr[l], r1 = plan->h_level_ptr[l + 1];
         if (r1 == r0) continue;
@@ -265,7 +559,7 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
     return PHB200_OK;
 }
 
-int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, void* stream_) {
+int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, const phb200_matrix* stencil_twin, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PHB_ARG(out && A && lu_val, "null argument");
     PHB_ARG(A->kind == PHB200_MAT_CSR && !A->transposed, "ILU(0) needs a plain CSR matrix");
@@ -293,9 +587,11 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
         cudaMemcpyAsync(&h, d_missing, sizeof(int), cudaMemcpyDeviceToHost, stream);
         if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("diagonal search failed: %s", cudaGetErrorString(cudaGetLastError())); r = PHB200_ERR_CUDA; break; }
         if (h) { set_error("All diagonal elements must be present in sparse matrix."); r = PHB200_ERR_ARG; break; }
-        r = build_plan(&p->plan_l, A->csr, 1, stream);
+        // a recognised star stencil has analytic dependency levels (computed on the device, no host copy of the pattern)
+        const bool star = stencil_twin && stencil_twin->kind == PHB200_MAT_STENCIL && stencil_twin->is_star && stencil_twin->n_rows == A->n_rows;
+        r = star ? build_plan_star(&p->plan_l, stencil_twin->star, 1, stream) : build_plan(&p->plan_l, A->csr, 1, stream);
         if (r != PHB200_OK) break;
-        r = build_plan(&p->plan_u, A->csr, 0, stream);
+        r = star ? build_plan_star(&p->plan_u, stencil_twin->star, 0, stream) : build_plan(&p->plan_u, A->csr, 0, stream);
         if (r != PHB200_OK) break;
         r = A->dtype == PHB200_F32 ? ilu0_factor<float>(p, stream) : ilu0_factor<double>(p, stream);
     } while (0);
@@ -353,6 +649,10 @@ int phb200_sptrsv(const phb200_matrix* T, const phb200_trsv_plan* plan, int lowe
 int phb200_sptrsv_plan_destroy(phb200_trsv_plan* p) {
     if (!p) return PHB200_OK;
     if (p->order) cudaFree(p->order);
+    if (p->order_pad) cudaFree(p->order_pad);
+    if (p->warp_level) cudaFree(p->warp_level);
+    if (p->level_warps) cudaFree(p->level_warps);
+    if (p->level_cnt) cudaFree(p->level_cnt);
     if (p->level_ptr) cudaFree(p->level_ptr);
     if (p->h_level_ptr) free(p->h_level_ptr);
     delete p;

@@ -10,6 +10,13 @@ struct phb200_trsv_plan {
     int32_t* level_ptr;    // device: n_levels+1 offsets into order
     int32_t* h_level_ptr;  // host copy
     int32_t max_level_rows;
+    // sync-free execution: every level padded to a multiple of 32 rows (-1 = no row), so a warp never spans two levels
+    int32_t* order_pad;    // device
+    int64_t npad;
+    int32_t* warp_level;   // device: level of every 32-row chunk of order_pad
+    int32_t* level_warps;  // device: number of 32-row chunks per level
+    unsigned long long* level_cnt;   // device: chunks of the level finished so far, accumulated over all solves (epoch * level_warps when complete)
+    int epoch;             // host-side counter, bumped per kernel
 };
 
 struct phb200_precond {
@@ -29,6 +36,7 @@ struct phb200_precond {
 namespace phb {
 
 // out = M^-1 in for (batch, ld) vectors; tmp is a scratch vector set of the same shape (ILU only).
+int build_plan_star(phb200_trsv_plan** out, const StarDesc& st, int lower, cudaStream_t stream);
 int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp, int64_t batch, int64_t ld, cudaStream_t stream);
 // out = L^-1 in (ILU) / D^-1 in (Jacobi) — Preconditioner.apply_inv_l
 int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int64_t batch, int64_t ld, cudaStream_t stream);

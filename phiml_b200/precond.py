@@ -92,7 +92,8 @@ class IncompleteLU(Preconditioner, _Handle):
         self.source = source
         self.lu = torch.empty_like(m.values)
         h = ctypes.c_void_p()
-        E.check(E.lib().phb200_precond_ilu0(ctypes.byref(h), m.handle, E.ptr(self.lu), E.stream_ptr(m.device)))
+        twin = m.stencil.handle if m.stencil is not None else None
+        E.check(E.lib().phb200_precond_ilu0(ctypes.byref(h), m.handle, E.ptr(self.lu), twin, E.stream_ptr(m.device)))
         self._h = h
 
     @property
