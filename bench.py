@@ -51,6 +51,17 @@ def measured_peak():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def ncu_traffic(fmt, n):
+    """DRAM bytes per launch of the two kernels of the iteration from the committed ncu --set full capture (256^3 only)."""
+    if n != 256:
+        return {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            return json.load(f).get(fmt, {})
+    except Exception:
+        return {}
+
+
 def workload_config(n, fmt, n_gpus):
     return {"workload": f"3D Poisson {n}^3 7-point Laplacian (ZERO padding), Jacobi-preconditioned CG fp32, rel_tol 1e-5",
             "matrix": "stencil-specialised kernels (auto-detected from the CSR native)" if fmt == 'stencil' else "general CSR int32",
@@ -246,15 +257,19 @@ def run_ours(args):
         model_bytes = [8 * csr.values.numel() + 4 * (N + 1) + 2 * N * w, 7 * N * w, 4 * N * w]
     peak, peak_src = measured_peak()
     kernels = []
+    traffic = ncu_traffic(args.format, n)
+    tkeys = ['k_star', 'k_phase'] if args.format == 'stencil' else []
     for k, (tot_ms, cnt) in enumerate(prof[:len(names)]):
         avg = tot_ms / max(cnt, 1)
-        kernels.append({"kernel": names[k], "avg_ms": avg, "bytes": model_bytes[k], "gbs": model_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else None})
+        tr = traffic.get(tkeys[k]) if k < len(tkeys) else None
+        kernels.append({"kernel": names[k], "avg_ms": avg, "bytes": model_bytes[k], "gbs": model_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else None,
+                        "traffic": (tr['dram_read'] + tr['dram_write']) if tr else None})
     dom = max(range(len(kernels)), key=lambda k: kernels[k]['avg_ms']) if kernels else None
     roofline = None
     if dom is not None:
         kd = kernels[dom]
         roofline = {"bound": "hbm", "kernel": kd['kernel'], "achieved": kd['gbs'], "peak": peak, "unit": "GB/s", "frac": kd['gbs'] / peak,
-                    "traffic": None, "peak_source": peak_src, "share_of_step": kd['avg_ms'] / sum(k_['avg_ms'] for k_ in kernels),
+                    "traffic": kd['traffic'], "traffic_source": "ncu --set full capture (cold L2), profiles/ncu_traffic.json" if kd['traffic'] else None, "peak_source": peak_src, "share_of_step": kd['avg_ms'] / sum(k_['avg_ms'] for k_ in kernels),
                     "kernels": kernels}
     its_per_s = args.steps / (ms * 1e-3)
     survey_bytes = 13 * N * w if args.format == 'stencil' else 8 * csr.values.numel() + 4 * (N + 1) + 13 * N * w   # SURVEY.md §8(d) canonical model
