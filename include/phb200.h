@@ -184,6 +184,14 @@ int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream);
  * iterations, never once per iteration.  Synchronises the stream before returning. */
 int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream);
 
+/* Small systems (N*3 vectors fit into the shared memory of one CTA or one cluster of <= 8 CTAs; 'CG' on a star stencil,
+ * no or constant-diagonal Jacobi preconditioner): phb200_solver_run executes the whole Krylov loop of a system inside ONE
+ * kernel, iterate/direction on chip, HBM touched once per solve.  PHB200_OPT_RESIDENT: -1 a cost model decides (default),
+ * 0 never, 1 whenever the system fits.  PHB200_OPT_RESIDENT_USED (read-only via *previous): did the last run() use it. */
+#define PHB200_OPT_RESIDENT 1
+#define PHB200_OPT_RESIDENT_USED 2
+int phb200_solver_option(phb200_solver* s, int option, int value, int* previous /* may be NULL */);
+
 /* *any_continue = 1 while at least one system is still iterating.  Synchronises the stream. */
 int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream);
 

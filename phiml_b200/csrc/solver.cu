@@ -6,6 +6,7 @@
 #include "dispatch.cuh"
 #include "star_tma.cuh"
 #include "precond.cuh"
+#include "resident.cuh"
 #include <vector>
 #include <stdlib.h>
 
@@ -78,6 +79,7 @@ struct InitResidual : FBase {
         s.go = 1;
         s.conv = s.div = 0;
         s.max_iter = max_iter[b];
+        s.pad0 = 0;   // passes made by this system (resident kernels)
         for (int k = 0; k < 40; ++k) s.s[k] = 0.0;
         s.s[S_DELTA] = (double)(tol_from_y ? rr : delta0);
         s.s[S_YY] = (double)yy;
@@ -655,6 +657,8 @@ struct phb200_solver {
     const void* rtol;
     const void* atol;
     const int32_t* max_iter;
+    int resident;              // PHB200_OPT_RESIDENT: -1 cost model decides, 0 never, 1 whenever the system fits on chip
+    int resident_used;         // 1 if the last run() went through the resident kernel
     int64_t off, n_act;        // element range [off, off + n_act) of every vector that this rank owns (whole vector if not a slab)
 };
 
@@ -1143,6 +1147,121 @@ struct Run {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ resident (on-chip) CG
+// Eligibility and launch geometry of k_cg_resident for this solver; false -> streaming kernels.
+template <typename T>
+static bool resident_plan(const phb200_solver* s, int& cs, int& lpc, size_t& smem) {
+    int mode = s->resident;
+    if (mode < 0) { const char* e = getenv("PHB200_RESIDENT"); if (e && (e[0] == '0' || e[0] == '1')) mode = e[0] - '0'; }
+    if (mode == 0) return false;
+    if (!(s->method == PHB200_CG || s->method == PHB200_CG_TORCH)) return false;
+    if (s->A->kind != PHB200_MAT_STENCIL || !s->A->is_star || s->totals) return false;
+    if (s->pre == PHB200_PRE_ILU || (s->pre == PHB200_PRE_JACOBI && !s->M->is_const)) return false;
+    const StarDesc& st = s->A->star;
+    if (st.xb != 0 || st.xe != st.nx || st.store_halo) return false;
+    if (st.nz % 4 != 0 || st.nz > (1 << 20) || st.nx * st.ny > (1 << 20)) return false;
+    const int64_t lines = st.nx * st.ny, qpl = st.nz / res_pack<T>(), cap_quads = (int64_t)kResThreads * kResQpt;
+    for (int c = 1; c <= kResMaxCluster; c *= 2) {
+        const int64_t l = (lines + c - 1) / c;
+        const size_t bytes = res_smem_bytes<T>((int)l, (int)st.nz);
+        if (l * qpl <= cap_quads && bytes <= 225 * 1024) {
+            // cost model: one on-chip iteration of a cluster ~1 us; a streaming pass moves 9 vectors at ~5 TB/s, >= 25 us
+            const int64_t ncl = kSMs / c;
+            const double t_res = (double)((s->batch + ncl - 1) / ncl) * 1.0e-6;
+            const double t_str = fmax(25e-6, 9.0 * (double)s->batch * (double)s->n * sizeof(T) / 5e12);
+            if (t_res > t_str && mode != 1) return false;
+            cs = c; lpc = (int)l; smem = bytes;
+            return true;
+        }
+    }
+    return false;
+}
+
+template <typename T, int PRE, bool RANK3, bool CLUSTER>
+static int launch_resident_t(const ResArgs& a, const ResCoef<T>& cf, size_t smem, cudaStream_t st) {
+    auto kernel = k_cg_resident<T, PRE, RANK3, CLUSTER>;
+    static bool attr = false;
+    if (!attr) {
+        PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        attr = true;
+    }
+    const int ncl_max = kSMs / a.cs;
+    const int ncl = a.batch < ncl_max ? a.batch : ncl_max;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(ncl * a.cs));
+    cfg.blockDim = dim3(kResThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)a.cs;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CLUSTER ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a, cf);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e == cudaSuccess && debug_sync()) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        set_error("kernel k_cg_resident failed: %s", cudaGetErrorString(e));
+        return PHB200_ERR_CUDA;
+    }
+    return PHB200_OK;
+}
+
+template <typename T>
+static int launch_resident(const phb200_solver* s, const ResArgs& a, size_t smem, cudaStream_t st) {
+    const bool rank3 = a.nx > 1, cl = a.cs > 1, jac = s->pre == PHB200_PRE_JACOBI;
+    const StarDesc& sd = s->A->star;
+    ResCoef<T> cf;
+    cf.c0 = (T)sd.c0; cf.cxm = (T)sd.cxm; cf.cxp = (T)sd.cxp; cf.cym = (T)sd.cym; cf.cyp = (T)sd.cyp; cf.czm = (T)sd.czm; cf.czp = (T)sd.czp;
+    cf.cinv = jac ? (T)s->M->const_inv : T(1);
+    if (jac) {
+        if (rank3) return cl ? launch_resident_t<T, 3, true, true>(a, cf, smem, st) : launch_resident_t<T, 3, true, false>(a, cf, smem, st);
+        return cl ? launch_resident_t<T, 3, false, true>(a, cf, smem, st) : launch_resident_t<T, 3, false, false>(a, cf, smem, st);
+    }
+    if (rank3) return cl ? launch_resident_t<T, 0, true, true>(a, cf, smem, st) : launch_resident_t<T, 0, true, false>(a, cf, smem, st);
+    return cl ? launch_resident_t<T, 0, false, true>(a, cf, smem, st) : launch_resident_t<T, 0, false, false>(a, cf, smem, st);
+}
+
+// Whole solve on chip.  Generic rules: systems are independent, one launch.  torch rules: finished systems keep
+// iterating (and are refreshed) until the LAST one is finished, so the state of every system is needed at the common
+// final pass P = first pass at which nobody continues.  Round k runs every system to the first pass >= lb_k after which
+// it stops; lb_{k+1} = max pass reached; done when all systems sit at the same pass (no pass before it can be the end,
+// because the system that got there last was still iterating).  Usually two rounds.
+template <typename T>
+static int run_resident(phb200_solver* s, int64_t cap, int cs, int lpc, size_t smem, cudaStream_t st) {
+    ResArgs a;
+    a.nx = (int)s->A->star.nx; a.ny = (int)s->A->star.ny; a.nz = (int)s->A->star.nz;
+    a.X = s->X; a.R = s->R; a.D = s->ws; a.Y = s->Y;
+    a.ld = s->n;
+    a.batch = (int)s->batch;
+    a.sys = s->sys; a.glob = s->glob;
+    a.torch_rules = s->method == PHB200_CG_TORCH ? 1 : 0;
+    a.lb = 0;
+    a.cap = (int)(cap > 0x3fffffff ? 0x3fffffff : cap);
+    a.lpc = lpc; a.cs = cs;
+    int* d_out = nullptr;
+    PHB_CUDA(cudaMallocAsync(&d_out, 2 * sizeof(int), st));
+    int r = PHB200_OK;
+    for (int round = 0; round < 64; ++round) {
+        r = launch_resident<T>(s, a, smem, st);
+        if (r != PHB200_OK) break;
+        k_res_round<<<1, kBlock, 0, st>>>(s->sys, (int)s->batch, a.cap, s->glob, d_out);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaMemcpyAsync(s->h_flag, d_out, 2 * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+            set_error("resident CG failed: %s", cudaGetErrorString(cudaGetLastError()));
+            r = PHB200_ERR_CUDA;
+            break;
+        }
+        s->passes = s->h_flag[0];
+        if (!a.torch_rules || s->h_flag[1]) break;
+        a.lb = s->h_flag[0];
+    }
+    cudaFreeAsync(d_out, st);
+    return r;
+}
+
 template <typename T>
 static Run<T> make_run(phb200_solver* s, cudaStream_t st) {
     Run<T> r;
@@ -1207,6 +1326,7 @@ int phb200_solver_create(phb200_solver** out, const phb200_matrix* A, const phb2
     s->n = A->n_rows;
     s->off = 0;
     s->n_act = A->n_rows;
+    s->resident = -1;
     if (A->kind == PHB200_MAT_STENCIL && A->is_star) {
         s->off = A->star.xb * A->star.ny * A->star.nz;
         s->n_act = (A->star.xe - A->star.xb) * A->star.ny * A->star.nz;
@@ -1298,6 +1418,21 @@ int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream_) {
     return advance(s, n_iter, (cudaStream_t)stream_);
 }
 
+int phb200_solver_option(phb200_solver* s, int option, int value, int* previous) {
+    PHB_ARG(s, "null solver");
+    if (option == PHB200_OPT_RESIDENT) {
+        if (previous) *previous = s->resident;
+        if (value >= -1 && value <= 1) s->resident = value;
+        return PHB200_OK;
+    }
+    if (option == PHB200_OPT_RESIDENT_USED) {
+        if (previous) *previous = s->resident_used;
+        return PHB200_OK;
+    }
+    set_error("unknown solver option %d", option);
+    return PHB200_ERR_ARG;
+}
+
 int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started && any_continue, "solver not started");
@@ -1311,6 +1446,13 @@ int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started, "solver not started");
     PHB_ARG(!s->totals, "a distributed solver is advanced with phb200_solver_dist_step");
+    if (s->passes == 0) {   // small systems: the whole loop on chip (resident.cuh)
+        int cs = 0, lpc = 0;
+        size_t smem = 0;
+        s->resident_used = 0;
+        if (s->dtype == PHB200_F32 && resident_plan<float>(s, cs, lpc, smem)) { s->resident_used = 1; return run_resident<float>(s, iteration_cap, cs, lpc, smem, st); }
+        if (s->dtype == PHB200_F64 && resident_plan<double>(s, cs, lpc, smem)) { s->resident_used = 1; return run_resident<double>(s, iteration_cap, cs, lpc, smem, st); }
+    }
     // The flag of chunk k is inspected while chunk k+1 is already queued, so the device never waits for the host.
     int chunk = 4;
     int slot = 0;

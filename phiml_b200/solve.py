@@ -39,6 +39,12 @@ class SolveResult:
 
 BACKEND_NAME = 'torch'     # the name the reference's method strings carry for this backend
 
+# 'auto': a cost model picks the on-chip (resident) CG kernel for small systems; 'never' / 'always' (when it fits) for tests
+RESIDENT = {'mode': 'auto'}
+_RESIDENT_CODE = {'auto': -1, 'never': 0, 'always': 1}
+OPT_RESIDENT, OPT_RESIDENT_USED = 1, 2
+LAST_RUN = {'resident': False}     # diagnostics of the most recent solve (tests, bench)
+
 
 def _pre_str(pre) -> str:
     return f"with preconditioner '{pre}'" if pre is not None else "with preconditioner 'none'"
@@ -53,6 +59,17 @@ class DeviceSolver:
         E.check(E.lib().phb200_solver_create(ctypes.byref(self._h), matrix.handle, pre.handle if pre is not None else None, method, poly_order, batch))
         self.workspace = None
         self._keep = ()
+        self.option(OPT_RESIDENT, _RESIDENT_CODE[RESIDENT['mode']])
+
+    def option(self, key: int, value: int = -2) -> int:
+        """Sets (value >= -1) or reads (value = -2) an integer solver option; returns the previous / current value."""
+        prev = ctypes.c_int()
+        E.check(E.lib().phb200_solver_option(self._h, key, value, ctypes.byref(prev)))
+        return int(prev.value)
+
+    @property
+    def resident_used(self) -> bool:
+        return bool(self.option(OPT_RESIDENT_USED))
 
     def start(self, y, x0, rtol, atol, max_iter, zero_init=False):
         dev = y.device
@@ -179,6 +196,7 @@ def _run_slab(code, poly_order, matrix, y, x0, rtol, atol, max_iter, pre):
     solver.start(y, x0, rtol, atol, mi_dev)
     if max_iter.shape[0] == 1:
         solver.run(int(np.max(max_iter)))
+        LAST_RUN['resident'] = solver.resident_used
         its, fev, conv, div = solver.result()
         return solver.x, solver.r, its, fev, conv, div
     # --- trajectory recording (Backend.while_loop with a list of checkpoints, _backend.py:722-735) ---

@@ -24,6 +24,17 @@ def dev_csr(csr, dtype=None):
     return torch.sparse_csr_tensor(torch.as_tensor(csr.indptr, device=DEV), torch.as_tensor(csr.indices, device=DEV), torch.as_tensor(vals, device=DEV), csr.shape)
 
 
+class streaming_kernels:
+    """Keeps solves on the streaming kernels (no on-chip CG) for tests that compare two streaming drivers bit for bit."""
+    def __enter__(self):
+        from phiml_b200 import solve as S
+        self.S, self.prev = S, S.RESIDENT['mode']
+        S.RESIDENT['mode'] = 'never'
+
+    def __exit__(self, *exc):
+        self.S.RESIDENT['mode'] = self.prev
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return np.max(np.abs(a - b), axis=-1) / np.maximum(np.max(np.abs(b), axis=-1), 1e-300)
@@ -198,6 +209,71 @@ def test_solve_matches_reference(name, use_stencil):
     assert np.all(np.linalg.norm((true_res - res.residual.cpu().numpy()).astype(np.float64), axis=1) / scale <= (1e-9 if f64 else 2e-4))
 
 
+RESIDENT_CASES = ['p128_cg_f64_default', 'p128_cg_f32_default', 'p128_cg_f64_torch', 'p128_cg_f32_torch', 'p128_jacobi_f64', 'p16_cg_f64', 'p16_cg_f32',
+                  'p32c_cg_f32', 'p32c_jacobi_f32', 'p32_batch8_f32', 'p32_quirk_f32', 'p32_quirk_f64_torch', 'p32_zero_rhs_f32', 'p32_maxiter_f32']
+
+
+@pytest.mark.parametrize('name', RESIDENT_CASES)
+def test_resident_kernel_matches_streaming_kernels(name):
+    """The on-chip CG (csrc/resident.cuh: one CTA / cluster per system, whole loop in one kernel) against the streaming
+    two-kernels-per-iteration path on the same inputs: same flags, iterations within +-1 (only the summation tree of the
+    dot products differs), x to solver tolerance; and both against the reference's golden record."""
+    from phiml_b200 import solve as S
+    g = golden('solves')
+    out = {}
+    for mode in ('never', 'always'):
+        S.RESIDENT['mode'] = mode
+        try:
+            case, csr, y, res = run_case(name)
+        finally:
+            S.RESIDENT['mode'] = 'auto'
+        assert S.LAST_RUN['resident'] == (mode == 'always'), f"resident kernel {'not ' if mode == 'always' else ''}used"
+        out[mode] = res
+    a, b = out['never'], out['always']
+    ia, ib = a.iterations.cpu().numpy().astype(int), b.iterations.cpu().numpy().astype(int)
+    assert np.max(np.abs(ia - ib)) <= 1, (ia, ib)
+    fa, fb = a.function_evaluations.cpu().numpy().astype(int), b.function_evaluations.cpu().numpy().astype(int)
+    assert np.max(np.abs(fa - fb)) <= 2, (fa, fb)
+    assert torch.equal(a.converged, b.converged) and torch.equal(a.diverged, b.diverged)
+    tol = (1e-10 if y.dtype == np.float64 else 1e-5)
+    if not np.array_equal(ia, ib):
+        tol = max(tol, 30 * case['rtol'])
+    assert np.all(rel_err(b.x.cpu().numpy(), a.x.cpu().numpy()) <= 50 * tol)
+    ref_it = g[f"solve/{name}/iterations"].astype(int)
+    assert np.max(np.abs(ib - ref_it)) <= 2
+    true_res = y - np.stack([csr.dot(v) for v in b.x.cpu().numpy()])
+    scale = np.maximum(np.linalg.norm(y.astype(np.float64), axis=1), 1e-30)
+    assert np.all(np.linalg.norm((true_res - b.residual.cpu().numpy()).astype(np.float64), axis=1) / scale <= (1e-9 if y.dtype == np.float64 else 2e-4))
+
+
+def test_resident_torch_rules_large_batch_common_final_pass():
+    """torch_sparse_cg keeps finished systems in the loop until the last one is done (refresh every 20th pass counts a
+    function evaluation for ALL systems): the resident rounds must land every system on the same final pass."""
+    from phiml_b200 import solve as S
+    csr = oracle_matrix('poisson', (32, 32), 'float32')
+    nb = 300
+    rng = np.random.default_rng(12)
+    y = (rng.standard_normal((nb, csr.shape[0])) * rng.uniform(0.5, 2.0, (nb, 1))).astype(np.float32)
+    yd = torch.as_tensor(y, device=DEV)
+    nat = dev_csr(csr)
+    out = {}
+    for mode in ('never', 'always'):
+        S.RESIDENT['mode'] = mode
+        try:
+            out[mode] = pb.linear_solve('CG', nat, yd, torch.zeros_like(yd), [1e-5] * nb, [0.0] * nb, np.full((1, nb), 1000), None, None)
+        finally:
+            S.RESIDENT['mode'] = 'auto'
+        assert S.LAST_RUN['resident'] == (mode == 'always')
+    a, b = out['never'], out['always']
+    assert bool(b.converged.all()) and not bool(b.diverged.any())
+    assert int((a.iterations - b.iterations).abs().max()) <= 1
+    # fev - iterations = 1 + number of refresh passes up to the COMMON final pass -> one value for the whole batch
+    extra = (b.function_evaluations - b.iterations).unique()
+    assert extra.numel() == 1 and int(extra[0]) == 1 + int(b.iterations.max()) // 20
+    assert int(((a.function_evaluations - a.iterations) - (b.function_evaluations - b.iterations)).abs().max()) <= 1
+    assert float((a.x - b.x).abs().max() / a.x.abs().max()) < 1e-3
+
+
 @pytest.mark.parametrize('name', ['p16_cg_f32', 'p8x6x5_jacobi_f32', 'p32_quirk_f32', 'a8x6x5_bicg2_f64', 'a8x6x5_bicg1_jacobi_f64', 'p128_cgadaptive_f32'])
 def test_solve_matches_oracle_on_same_inputs(name):
     """Direct CUDA-vs-oracle comparison (the oracle itself is pinned to the reference in test_oracle_golden.py)."""
@@ -277,7 +353,8 @@ def test_trajectory_recording():
     case, csr, y, x0, rtol, atol, _ = case_inputs('p16_cg_f32')
     nat = dev_csr(csr)
     yd = torch.as_tensor(y, device=DEV)
-    full = pb.generic_conjugate_gradient(nat, yd, torch.zeros_like(yd), rtol, atol, np.array([[1000, 1000]]))
+    with streaming_kernels():
+        full = pb.generic_conjugate_gradient(nat, yd, torch.zeros_like(yd), rtol, atol, np.array([[1000, 1000]]))
     n_it = int(full.iterations.max())
     cps = np.tile(np.arange(n_it + 5)[:, None], (1, 2))
     trj = pb.linear_solve('CG', nat, yd, torch.zeros_like(yd), rtol, atol, cps, None, None)
@@ -371,7 +448,8 @@ def test_slab_engine_single_rank_equals_plain_solve():
     n = int(np.prod(grid))
     y = torch.as_tensor(np.random.default_rng(0).standard_normal((2, n)).astype(np.float32), device=DEV)
     st = pb.Matrix.stencil_matrix(grid, offsets, coeffs, torch.float32, DEV)
-    ref = pb.generic_conjugate_gradient(st, y, torch.zeros_like(y), [1e-5, 1e-5], [0.0, 0.0], np.array([[1000, 1000]]), pb.JacobiPreconditioner(st))
+    with streaming_kernels():
+        ref = pb.generic_conjugate_gradient(st, y, torch.zeros_like(y), [1e-5, 1e-5], [0.0, 0.0], np.array([[1000, 1000]]), pb.JacobiPreconditioner(st))
     cg = SlabCG(grid, offsets, coeffs, torch.float32, jacobi=True, device=DEV)
     x, r, its, fev, conv, div = cg.solve(y, torch.zeros_like(y), [1e-5, 1e-5], [0.0, 0.0], 1000, poll_every=5)
     assert torch.equal(its, ref.iterations) and torch.equal(fev, ref.function_evaluations)
