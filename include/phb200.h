@@ -128,6 +128,10 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
  * If A was recognised as a star stencil, pass the stencil handle: the levels are then computed analytically on the
  * device instead of from a host copy of the pattern. */
 int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, const phb200_matrix* stencil_twin /* may be NULL */, void* stream);
+/* *star_wavefront = 1 if the triangular solves of an ILU preconditioner run as the structured wavefront of
+ * csrc/star_trsv.cuh (factors of a recognised star stencil; 3 N w bytes per solve) instead of the CSR level solves.
+ * The environment variable PHB200_TRSV=csr disables the wavefront form at set-up. */
+int phb200_precond_info(const phb200_precond* p, int* kind, int* star_wavefront);
 /* number of dependency levels of the lower / upper solve (diagnostics) */
 int phb200_precond_levels(const phb200_precond* p, int64_t* lower_levels, int64_t* upper_levels);
 

@@ -1,6 +1,7 @@
 // Preconditioners: Jacobi set-up, exact ILU(0) with a level schedule, level-scheduled sparse triangular solves.
 #include "phase.cuh"
 #include "precond.cuh"
+#include "star_trsv.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <vector>
 #include <stdlib.h>
@@ -466,6 +467,85 @@ static int ilu0_factor(const phb200_precond* p, cudaStream_t stream) {
     return PHB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- star wavefront solves
+template <typename T, bool LOWER>
+static int star_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, int64_t ld, cudaStream_t stream) {
+    const StarDesc& st = p->star;
+    StarTrsvArgs a;
+    a.nx = (int)st.nx; a.ny = (int)st.ny; a.nz = (int)st.nz;
+    int tx_pref = 8;
+    if (const char* e = getenv("PHB200_TRSV_TX")) { const int v = atoi(e); if (v >= 1 && v <= kTrMaxTX) tx_pref = v; }
+    a.tx = (int)(st.nx < tx_pref ? st.nx : tx_pref);
+    a.nsx = (a.nx + a.tx - 1) / a.tx;
+    a.nsy = (a.ny + 31) / 32;
+    a.nch = (a.nz + kTrZC - 1) / kTrZC;
+    a.batch = (int)batch;
+    a.ld = ld;
+    a.rd = p->rd;
+    a.B = B;
+    a.X = X;
+    const int64_t need = batch * a.nsx * a.nsy;
+    if (need > p->tr_flag_cap) {   // first use / larger batch: fresh counters (all solves so far have completed in stream order)
+        PHB_CUDA(cudaStreamSynchronize(stream));
+        if (p->tr_flags) cudaFree(p->tr_flags);
+        p->tr_flags = nullptr;
+        PHB_CUDA(cudaMalloc(&p->tr_flags, sizeof(unsigned long long) * need));
+        PHB_CUDA(cudaMemsetAsync(p->tr_flags, 0, sizeof(unsigned long long) * need, stream));
+        p->tr_flag_cap = need;
+        p->tr_epoch = 0;
+    }
+    a.flags = p->tr_flags;
+    a.epoch_base = p->tr_epoch;
+    p->tr_epoch += (unsigned long long)a.nch;
+    a.ticket = p->tr_ticket;
+    constexpr int W = tr_warps<T>();
+    a.n_ctas = (unsigned)((need + W - 1) / W);
+    a.cx = LOWER ? st.cxm : st.cxp;
+    a.cy = LOWER ? st.cym : st.cyp;
+    a.cz = LOWER ? st.czm : st.czp;
+    auto kernel = k_star_trsv<T, LOWER>;
+    constexpr size_t smem = trsv_warp_smem<T>() * W;
+    static bool attr = false;
+    if (!attr) {
+        PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    PHB_LAUNCH(kernel, a.n_ctas, W * 32, smem, stream, a);
+    return PHB200_OK;
+}
+
+template <typename T>
+static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t stream) {
+    const StarDesc& st = twin->star;
+    // closed form needs distinct, non-aliasing offsets: nz >= 4 (star kernels need nz % 4 == 0 anyway), ny != 2 in 3-D
+    if (st.nz < 4 || st.nz % 4 != 0) return PHB200_OK;
+    if (st.nx > 1 && st.ny < 3) return PHB200_OK;
+    if (st.xb != 0 || st.xe != st.nx) return PHB200_OK;
+    if (st.nx > 0x3fffffff / 8 || st.nx * st.ny * st.nz != p->n) return PHB200_OK;
+    const char* e = getenv("PHB200_TRSV");
+    if (e && (strcmp(e, "levels") == 0 || strcmp(e, "csr") == 0)) return PHB200_OK;
+    int* d_ok = nullptr;
+    PHB_CUDA(cudaMalloc(&p->rd, sizeof(T) * (size_t)p->n));
+    PHB_CUDA(cudaMalloc(&p->tr_ticket, sizeof(unsigned)));
+    PHB_CUDA(cudaMemsetAsync(p->tr_ticket, 0, sizeof(unsigned), stream));
+    PHB_CUDA(cudaMallocAsync(&d_ok, sizeof(int), stream));
+    int one = 1;
+    PHB_CUDA(cudaMemcpyAsync(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
+    PHB_LAUNCH(k_star_ilu_check<T>, (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1), kBlock, 0, stream, p->lu, (const T*)p->lu.val, p->diag_pos, st, (T*)p->rd, d_ok);
+    int ok = 0;
+    PHB_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    PHB_CUDA(cudaFreeAsync(d_ok, stream));
+    if (ok) {
+        p->star = st;
+        p->star_mode = 1;
+    } else {
+        cudaFree(p->rd);
+        p->rd = nullptr;
+    }
+    return PHB200_OK;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_scale_rows(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ w, int64_t n, int64_t ld) {
     const int b = blockIdx.y;
@@ -481,6 +561,11 @@ int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int6
         return PHB200_OK;
     }
     if (p->kind == PHB200_PRE_ILU) {
+        if (p->star_mode) {
+            phb200_precond* q = const_cast<phb200_precond*>(p);   // counters / epoch are bookkeeping
+            if (p->dtype == PHB200_F32) return star_trsv_launch<float, true>(q, (const float*)in, (float*)out, batch, ld, stream);
+            return star_trsv_launch<double, true>(q, (const double*)in, (double*)out, batch, ld, stream);
+        }
         if (p->dtype == PHB200_F32) return trsv<float>(p->lu, p->plan_l, 1, 1, (const float*)in, (float*)out, batch, ld, stream);
         return trsv<double>(p->lu, p->plan_l, 1, 1, (const double*)in, (double*)out, batch, ld, stream);
     }
@@ -494,6 +579,11 @@ int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp,
         // out = U^-1 (L^-1 in); the upper solve may run in place, so `tmp` is not needed
         (void)tmp;
         PHB_TRY(precond_apply_inv_l(p, in, out, batch, ld, stream));
+        if (p->star_mode) {
+            phb200_precond* q = const_cast<phb200_precond*>(p);
+            if (p->dtype == PHB200_F32) return star_trsv_launch<float, false>(q, (const float*)out, (float*)out, batch, ld, stream);
+            return star_trsv_launch<double, false>(q, (const double*)out, (double*)out, batch, ld, stream);
+        }
         if (p->dtype == PHB200_F32) return trsv<float>(p->lu, p->plan_u, 0, 0, (const float*)out, (float*)out, batch, ld, stream);
         return trsv<double>(p->lu, p->plan_u, 0, 0, (const double*)out, (double*)out, batch, ld, stream);
     }
@@ -594,6 +684,8 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
         r = star ? build_plan_star(&p->plan_u, stencil_twin->star, 0, stream) : build_plan(&p->plan_u, A->csr, 0, stream);
         if (r != PHB200_OK) break;
         r = A->dtype == PHB200_F32 ? ilu0_factor<float>(p, stream) : ilu0_factor<double>(p, stream);
+        if (r != PHB200_OK) break;
+        if (star) r = A->dtype == PHB200_F32 ? star_setup<float>(p, stencil_twin, stream) : star_setup<double>(p, stencil_twin, stream);
     } while (0);
     if (d_missing) cudaFreeAsync(d_missing, stream);
     if (r != PHB200_OK) {
@@ -601,6 +693,13 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
         return r;
     }
     *out = p;
+    return PHB200_OK;
+}
+
+int phb200_precond_info(const phb200_precond* p, int* kind, int* star_wavefront) {
+    PHB_ARG(p, "null preconditioner");
+    if (kind) *kind = p->kind;
+    if (star_wavefront) *star_wavefront = p->star_mode;
     return PHB200_OK;
 }
 
@@ -669,6 +768,9 @@ int phb200_precond_apply(const phb200_precond* p, const void* in, void* out, int
 int phb200_precond_destroy(phb200_precond* p) {
     if (!p) return PHB200_OK;
     if (p->diag_pos) cudaFree(p->diag_pos);
+    if (p->rd) cudaFree(p->rd);
+    if (p->tr_flags) cudaFree(p->tr_flags);
+    if (p->tr_ticket) cudaFree(p->tr_ticket);
     phb200_sptrsv_plan_destroy(p->plan_l);
     phb200_sptrsv_plan_destroy(p->plan_u);
     delete p;

@@ -31,6 +31,14 @@ struct phb200_precond {
     int32_t* diag_pos;     // device, owned
     phb200_trsv_plan* plan_l;
     phb200_trsv_plan* plan_u;
+    // star-stencil wavefront solves (star_trsv.cuh): reciprocal pivots + block counters; star_mode 0 = CSR level solves
+    int star_mode;
+    phb::StarDesc star;
+    void* rd;                          // device, owned: 1 / U_ii
+    unsigned long long* tr_flags;      // device, owned
+    int64_t tr_flag_cap;               // counters allocated
+    unsigned* tr_ticket;               // device, owned
+    unsigned long long tr_epoch;       // host: value all counters of a finished launch stand at
 };
 
 namespace phb {

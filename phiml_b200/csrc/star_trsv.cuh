@@ -1,0 +1,368 @@
+// Triangular solves with the ILU(0) factors of a constant-coefficient star stencil (5/7-point, ZERO boundaries) as a
+// pipelined, skewed wavefront — the structured replacement of the level-scheduled CSR solve (precond.cu) for what
+// matrix_from_function emits (BASELINE config 4).
+//
+// For such a matrix the factors are fully described by the pivots d_i = U_ii:  U_ij = A_ij (j > i) and
+// L_ik = A_ik / d_k (k < i), because no update of ILU(0) touches an off-diagonal entry (k_star_ilu_check verifies this
+// bit for bit on the actual factors before the path is used).  With rd = 1/d:
+//     lower:  t_i = b_i - a_xm w_{i-sx} - a_ym w_{i-sy} - a_zm w_{i-sz},  w_i = t_i rd_i          (output t = L^-1 b)
+//     upper:  x_i = (t_i - a_xp x_{i+sx} - a_yp x_{i+sy} - a_zp x_{i+sz}) rd_i                    (output x = U^-1 t)
+// i.e. 3 N w bytes per solve (rhs, rd, result) instead of 8 nnz_T + ... of the CSR form, and no index traffic at all.
+// (The products are rounded as a (x/d) instead of (a/d) x, and the final division is a multiplication with the rounded
+// reciprocal: a few ulp away from the CSR solve — the ILU parity bar is "+-2 iterations", see DESIGN.md.)
+//
+// Parallelisation.  A WARP owns a block of TX x-planes x 32 rows (y) and sweeps z in chunks of ZC = 16: lane t = row,
+// and lane t runs t steps behind lane t-1 (skew), so the y-neighbour arrives by one shuffle per step, the z-neighbour
+// is the lane's previous result, and the x-neighbour is the lane's own result of the previous plane (ring in shared
+// memory).  rhs / rd tiles are staged with cp.async three planes ahead; results are written back as whole tiles.
+// Blocks depend on their -x and -y neighbours chunk by chunk: block (sx, sy) may sweep chunk c after (sx-1, sy) and
+// (sx, sy-1) have published chunk c (release/acquire on one monotone counter per block: no reset between solves).
+// The critical path is (nx/TX + ny/32 + nz/16) chunk sweeps of ~TX*16 steps of ~40 cycles each instead of
+// (nx+ny+nz) global level synchronisations.  The upper solve is the same sweep in mirrored coordinates.
+// Blocks are claimed through a ticket counter in dependency order, so a waiting block only ever waits for blocks that
+// are already running: no deadlock even when the grid exceeds the resident CTAs.
+#pragma once
+#include "matrix.cuh"
+
+namespace phb {
+
+constexpr int kTrZC = 16;          // z elements per chunk
+constexpr int kTrStages = 8;       // staged planes (rhs + rd tiles); power of two
+constexpr int kTrRing = 4;         // planes kept in the result / hand-over streams; power of two
+constexpr int kTrMaxTX = 16;       // planes per block (upper bound)
+template <typename T> constexpr int tr_warps() { return sizeof(T) == 4 ? 4 : 2; }   // warps (= blocks of the sweep) per CTA
+
+struct StarTrsvArgs {
+    int nx, ny, nz;
+    int tx;                 // planes per block
+    int nsx, nsy, nch;      // blocks along x, y; chunks along z
+    int batch;
+    int64_t ld;
+    const void* rd;         // reciprocal pivots, N elements
+    const void* B;          // right-hand sides (batch, ld)
+    void* X;                // results (batch, ld); may alias B
+    unsigned long long* flags;   // [batch][nsx][nsy] monotone chunk counters
+    unsigned long long epoch_base;   // counters stood at this value * ... see launch: target = base + c + 1
+    unsigned* ticket;       // work counter (reset by the last CTA)
+    unsigned n_ctas;
+    double cx, cy, cz;      // coefficients towards the dependencies (-x,-y,-z for the lower, +x,+y,+z for the upper solve)
+};
+
+template <typename T> constexpr size_t trsv_warp_smem() {
+    // tiles: stages x {rhs, rd} x 32 x ZC ; ring (passed values) and out (lower only): kTrRing x 32 x ZC each ; yrow TX x ZC ; zp 2 x TX x 32
+    return sizeof(T) * ((size_t)kTrStages * 2 * 32 * kTrZC + 2 * (size_t)kTrRing * 32 * kTrZC + (size_t)kTrMaxTX * kTrZC + 2 * (size_t)kTrMaxTX * 32);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// polling load: relaxed (an acquire load costs an L1 invalidation — CCTL.IVALL — per poll); ONE fence follows the wait
+__device__ __forceinline__ unsigned long long ld_poll_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// 16 bytes of T from global memory through L2 (data written by other SMs in this launch)
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { float v[4]; };
+template <> struct Vec16<double> { double v[2]; };
+__device__ __forceinline__ Vec16<float> ldcg16(const float* p) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    return Vec16<float>{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ Vec16<double> ldcg16(const double* p) {
+    const double2 t = __ldcg(reinterpret_cast<const double2*>(p));
+    return Vec16<double>{{t.x, t.y}};
+}
+
+template <typename T, bool LOWER>
+__global__ void __launch_bounds__(tr_warps<T>() * 32) k_star_trsv(const StarTrsvArgs a) {
+    constexpr int ZC = kTrZC, V = 16 / (int)sizeof(T);   // V elements per 16 bytes
+    constexpr int GPR = ZC / V;                         // 16-byte groups per tile row
+    constexpr int W = (int)sizeof(T);
+    constexpr int TS = kTrStages * ZC, RS = kTrRing * ZC;            // stream lengths per lane (elements): tiles, ring
+    constexpr unsigned TMASK = TS * W - 1, RMASK = RS * W - 1;      // byte masks (powers of two)
+    static_assert((TS & (TS - 1)) == 0 && (RS & (RS - 1)) == 0 && ZC == 16, "stream lengths must be powers of two");
+    extern __shared__ __align__(16) unsigned char trsv_smem[];
+    __shared__ unsigned s_ticket;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const unsigned cta = s_ticket;
+    if (threadIdx.x == 0 && cta == a.n_ctas - 1) *a.ticket = 0u;   // every CTA has drawn: ready for the next launch
+
+    // Per-lane STREAMS: lane t keeps the data of its row as a circular buffer indexed by the stream position of an
+    // element, pos(pl, z') = +-(pl * ZC + z') (mirrored for the upper solve so that physical z stays ascending inside a
+    // 16-byte group): every step moves every lane's position by one element, banks never collide (lane stride = power
+    // of two >= 32 words, positions differ by the skew).
+    unsigned char* base = trsv_smem + (size_t)warp * trsv_warp_smem<T>();
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(base);
+    const uint32_t tb_a = sb;                                   // rhs tiles   [32][TS]
+    const uint32_t tr_a = tb_a + 32 * TS * W;                   // rd tiles    [32][TS]
+    const uint32_t rg_a = tr_a + 32 * TS * W;                   // ring        [32][RS]  values handed to the next plane
+    const uint32_t ob_a = rg_a + 32 * RS * W;                   // out         [32][RS]  results (lower solve: t, not w)
+    T* yrow = reinterpret_cast<T*>(base + (size_t)(2 * 32 * TS + 2 * 32 * RS) * W);   // [TX*ZC] stream of the row above (lane 0)
+    T* zp = yrow + kTrMaxTX * ZC;                               // [2][TX][32] values at the last z' of the previous chunk
+
+    const int64_t task = (int64_t)cta * tr_warps<T>() + warp;
+    const int64_t n_tasks = (int64_t)a.batch * a.nsx * a.nsy;
+    if (task >= n_tasks) return;
+    const int sy = (int)(task % a.nsy), sx = (int)((task / a.nsy) % a.nsx), b = (int)(task / ((int64_t)a.nsy * a.nsx));
+    const int nx = a.nx, ny = a.ny, nz = a.nz, tx = a.tx;
+    const int x0 = sx * tx, npl = min(tx, nx - x0);       // logical planes [x0, x0 + npl)
+    const int y0 = sy * 32;
+    const bool row_ok = y0 + lane < ny;
+    const T cx = (T)a.cx, cy = (T)a.cy, cz = (T)a.cz;
+    const T* __restrict__ rd = (const T*)a.rd;
+    const T* Bb = (const T*)a.B + (int64_t)b * a.ld;
+    T* Xb = (T*)a.X + (int64_t)b * a.ld;
+    unsigned long long* my_flag = a.flags + ((int64_t)b * a.nsx + sx) * a.nsy + sy;
+    const unsigned long long* flag_x = sx > 0 ? my_flag - a.nsy : nullptr;
+    const unsigned long long* flag_y = sy > 0 ? my_flag - 1 : nullptr;
+
+    auto px = [&](int lx) { return LOWER ? lx : nx - 1 - lx; };
+    auto py = [&](int ly) { return LOWER ? ly : ny - 1 - ly; };
+    // chunk c covers logical z' in [c ZC, c ZC + ZC); its tile rows hold the physical z range [seg0, seg0 + ZC)
+    auto seg0 = [&](int c) { return LOWER ? c * ZC : nz - (c + 1) * ZC; };
+    // first stream position of local plane pl (physical column 0 of its tile): pl*ZC for the lower, -pl*ZC for the upper solve
+    auto plane_pos = [&](int pl) { return LOWER ? pl * ZC : -pl * ZC; };
+
+    // ---- cp.async of the rhs / rd tiles of local plane pl (chunk c)
+    auto issue_plane = [&](int c, int pl) {
+        if (pl < npl) {
+            const uint32_t slot = ((uint32_t)(plane_pos(pl) * W)) & TMASK;
+            const int64_t plane_off = (int64_t)px(x0 + pl) * ny;
+            const int z0 = seg0(c);
+#pragma unroll
+            for (int i = 0; i < (32 * GPR) / 32; ++i) {
+                const int k = i * 32 + lane;
+                const int row = k / GPR, g = k % GPR;
+                const int zph = z0 + g * V;
+                const bool ok = (y0 + row < ny) && zph >= 0 && zph < nz;
+                const int64_t off = ok ? ((plane_off + py(y0 + row)) * nz + zph) : 0;
+                const uint32_t d = tb_a + (uint32_t)(row * TS * W) + slot + (uint32_t)(g * 16);
+                cp_async16(d, Bb + off, ok);
+                cp_async16(d + 32 * TS * W, rd + off, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    // copies the finished local plane dpl from the out / ring stream to global memory, 16 bytes per lane and group
+    auto drain = [&](int c, int dpl) {
+        const uint32_t src = (LOWER ? ob_a : rg_a) + (((uint32_t)(plane_pos(dpl) * W)) & RMASK);
+        const int64_t plane_off = (int64_t)px(x0 + dpl) * ny;
+        const int z0 = seg0(c);
+#pragma unroll
+        for (int i = 0; i < (32 * GPR) / 32; ++i) {
+            const int k = i * 32 + lane;
+            const int row = k / GPR, g = k % GPR;
+            const int zph = z0 + g * V;
+            if ((y0 + row < ny) && zph >= 0 && zph < nz) {
+                const int64_t off = ((plane_off + py(y0 + row)) * nz + zph);
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + (uint32_t)(row * RS * W + g * 16)) : "memory");
+                *reinterpret_cast<uint4*>(Xb + off) = v;
+            }
+        }
+    };
+    auto lds = [&](uint32_t addr) -> T {
+        T v;
+        if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+        return v;
+    };
+    auto sts = [&](uint32_t addr, T v) {
+        if constexpr (sizeof(T) == 4) asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+        else asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+    };
+
+    const unsigned long long target0 = a.epoch_base;
+    unsigned long long seen_x = 0, seen_y = 0;
+    const uint32_t lane_t = (uint32_t)(lane * TS * W), lane_r = (uint32_t)(lane * RS * W);
+    for (int c = 0; c < a.nch; ++c) {
+        // tiles of the first planes do not depend on anybody: start them before waiting
+#pragma unroll
+        for (int q = 0; q < kTrStages - 2; ++q) issue_plane(c, q);
+        // ---- wait for the -x and -y blocks to have published chunk c
+        if (lane == 0) {
+            const unsigned long long need = target0 + (unsigned long long)c + 1ull;
+            const long long t0 = clock64();
+            unsigned ns = 32;
+            auto wait_for = [&](const unsigned long long* flag, unsigned long long& seen) {
+                while (seen < need) {
+                    seen = ld_poll_u64(flag);
+                    if (seen < need) {
+                        __nanosleep(ns);
+                        if (ns < 1024) ns *= 2;
+                        if (clock64() - t0 > 6000000000ll) __trap();
+                    }
+                }
+            };
+            if (flag_x) wait_for(flag_x, seen_x);
+            if (flag_y) wait_for(flag_y, seen_y);
+        }
+        __syncwarp();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        const int z0 = seg0(c);
+        const int zcnt = min(ZC, nz - c * ZC);     // logical z' of this chunk: [0, zcnt)
+        // ---- boundary values handed over by other blocks (w = t * rd for the lower solve, x for the upper one)
+        auto handed = [&](int64_t off) -> Vec16<T> {
+            Vec16<T> val = ldcg16(Xb + off);
+            if (LOWER) {
+                const Vec16<T> rv = ldcg16(rd + off);
+#pragma unroll
+                for (int e = 0; e < V; ++e) val.v[e] = val.v[e] * rv.v[e];
+            }
+            return val;
+        };
+        {   // plane x0-1 -> ring positions of local plane -1
+            const uint32_t slot = ((uint32_t)(plane_pos(-1) * W)) & RMASK;
+#pragma unroll
+            for (int i = 0; i < (32 * GPR) / 32; ++i) {
+                const int k = i * 32 + lane;
+                const int row = k / GPR, g = k % GPR;
+                const int zph = z0 + g * V;
+                Vec16<T> val;
+#pragma unroll
+                for (int e = 0; e < V; ++e) val.v[e] = T(0);
+                if (sx > 0 && (y0 + row < ny) && zph >= 0 && zph < nz) val = handed(((int64_t)px(x0 - 1) * ny + py(y0 + row)) * nz + zph);
+#pragma unroll
+                for (int e = 0; e < V; ++e) sts(rg_a + (uint32_t)(row * RS * W) + slot + (uint32_t)((g * V + e) * W), val.v[e]);
+            }
+            // row y0-1 of every plane of the block -> yrow stream (position relative to the block's first position)
+            for (int k = lane; k < npl * GPR; k += 32) {
+                const int pl = k / GPR, g = k % GPR;
+                const int zph = z0 + g * V;
+                Vec16<T> val;
+#pragma unroll
+                for (int e = 0; e < V; ++e) val.v[e] = T(0);
+                if (sy > 0 && zph >= 0 && zph < nz) val = handed(((int64_t)px(x0 + pl) * ny + py(y0 - 1)) * nz + zph);
+                // stream index of (pl, column g*V+e): lower pl*ZC + col; upper (npl-1-pl)*ZC + col (ascending memory as positions fall)
+                const int idx = (LOWER ? pl : npl - 1 - pl) * ZC + g * V;
+#pragma unroll
+                for (int e = 0; e < V; ++e) yrow[idx + e] = val.v[e];
+            }
+            if (c == 0)
+                for (int k = lane; k < 2 * kTrMaxTX * 32; k += 32) zp[k] = T(0);
+        }
+        __syncwarp();
+        const T* zp_in = zp + (c & 1) * kTrMaxTX * 32;
+        T* zp_out = zp + ((c + 1) & 1) * kTrMaxTX * 32;
+
+        // ---- the skewed sweep: at step s lane t handles stream element e = s - t = pl * ZC + z'; its operands sit at
+        // stream position pos(e) = e (lower) / ZC-1-e (upper).  Operands of element e+1 are fetched while element e goes
+        // through its shuffle -> fma chain.
+        const int total = npl * ZC;
+        const int n_steps = total + 31;
+        int e_next = -lane;
+        T o_b = T(0), o_r = T(0), o_x = T(0), o_y = T(0), o_z = T(0);
+        bool o_act = false;
+        auto fetch = [&]() {
+            const int e = e_next;
+            const int zl = e & (ZC - 1);
+            o_act = (unsigned)e < (unsigned)total && row_ok && zl < zcnt;
+            const int pos = LOWER ? e : ZC - 1 - e;
+            const uint32_t ta = tb_a + lane_t + (((uint32_t)(pos * W)) & TMASK);
+            const uint32_t ra = rg_a + lane_r + (((uint32_t)((pos + (LOWER ? -ZC : ZC)) * W)) & RMASK);   // same column, previous plane
+            if (o_act) {
+                o_b = lds(ta);
+                o_r = lds(ta + 32 * TS * W);
+                o_x = lds(ra);
+                if (lane == 0) o_y = yrow[LOWER ? e : total - 1 - e];
+                if (zl == 0) o_z = zp_in[(e >> 4) * 32 + lane];
+            }
+            e_next = e + 1;
+        };
+        cp_async_wait<kTrStages - 3>();      // plane 0 has landed
+        __syncwarp();
+        fetch();
+        T prev = T(0);           // value this lane handed on in the previous step (its z'-1 neighbour)
+        for (int s = 0; s < n_steps; ++s) {
+            if ((s & (ZC - 1)) == ZC - 1) {     // uniform point: next plane's tiles, drain a finished plane, prefetch a later one
+                cp_async_wait<kTrStages - 4>();   // planes <= s/ZC + 1 have landed (lane 0 fetches from plane s/ZC + 1 below)
+                __syncwarp();
+                const int dpl = s / ZC - 2;     // every lane has finished this plane (lane 31 at step dpl*ZC + ZC-1 + 31 = s - 1)
+                if (dpl >= 0 && dpl < npl) drain(c, dpl);
+                __syncwarp();
+                issue_plane(c, s / ZC + kTrStages - 2);
+            }
+            const int e = e_next - 1;           // current element
+            const T bv = o_b, rv = o_r, xm = o_x, yv = o_y, zv = o_z;
+            const bool act = o_act;
+            fetch();
+            const T up = __shfl_up_sync(0xffffffffu, prev, 1);
+            T pass = T(0);
+            if (act) {
+                const int zl = e & (ZC - 1);
+                const int pos = LOWER ? e : ZC - 1 - e;
+                const uint32_t wa = lane_r + (((uint32_t)(pos * W)) & RMASK);
+                const T zm = zl == 0 ? zv : prev;
+                T acc = fma_t<T>(-cx, xm, bv);
+                acc = fma_t<T>(-cz, zm, acc);
+                acc = fma_t<T>(-cy, lane == 0 ? yv : up, acc);
+                pass = acc * rv;
+                sts(rg_a + wa, pass);
+                if (LOWER) sts(ob_a + wa, acc);
+                if (zl == zcnt - 1) zp_out[(e >> 4) * 32 + lane] = pass;
+            }
+            prev = pass;
+        }
+        // planes that were not drained inside the loop
+        __syncwarp();
+        {
+            const int last_uniform = ((n_steps / ZC) * ZC) - 1;                 // last s with (s & 15) == 15, or -1
+            const int drained = last_uniform >= 0 ? last_uniform / ZC - 2 : -1;  // planes 0..drained are out
+            for (int dpl = max(0, drained + 1); dpl < npl; ++dpl) drain(c, dpl);
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        // ---- publish chunk c
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u64(my_flag, target0 + (unsigned long long)c + 1ull);
+    }
+}
+
+// rd[i] = 1 / lu[diag(i)] and a bit-for-bit check that the factors have the closed form described above
+// (ok[0] = 0 otherwise).  One thread per row of the CSR factor storage.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_star_ilu_check(CsrView A, const T* __restrict__ lu, const int32_t* __restrict__ diag_pos, StarDesc st,
+                                                           T* __restrict__ rdv, int* ok) {
+    const int64_t n = A.n_rows;
+    const int64_t sxo = st.ny * st.nz, syo = st.nz;
+    const T cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
+    bool good = true;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const int dp = diag_pos[i];
+        rdv[i] = T(1) / lu[dp];
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+            const int64_t j = A.col[p];
+            const int64_t off = j - i;
+            const T v = lu[p];
+            if (off == 0) continue;
+            T expect;
+            if (off < 0) {
+                const T a = off == -sxo ? cxm : (off == -syo ? cym : (off == -1 ? czm : T(NAN)));
+                expect = a / lu[diag_pos[j]];
+            } else {
+                expect = off == sxo ? cxp : (off == syo ? cyp : (off == 1 ? czp : T(NAN)));
+            }
+            if (!(v == expect)) good = false;
+        }
+    }
+    if (!good) *ok = 0;
+}
+
+}  // namespace phb

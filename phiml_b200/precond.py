@@ -97,6 +97,13 @@ class IncompleteLU(Preconditioner, _Handle):
         self._h = h
 
     @property
+    def star_wavefront(self) -> bool:
+        """True if the triangular solves run as the structured wavefront (csrc/star_trsv.cuh) instead of CSR level solves."""
+        kind, star = ctypes.c_int(), ctypes.c_int()
+        E.check(E.lib().phb200_precond_info(self._h, ctypes.byref(kind), ctypes.byref(star)))
+        return bool(star.value)
+
+    @property
     def levels(self):
         lo, up = ctypes.c_int64(), ctypes.c_int64()
         E.check(E.lib().phb200_precond_levels(self._h, ctypes.byref(lo), ctypes.byref(up)))

@@ -401,6 +401,36 @@ def test_ilu_and_triangular_solves(key):
     assert lo == up == sum(grid) - len(grid) + 1      # hyperplanes i+j+k = c of the natural ordering
 
 
+@pytest.mark.parametrize('op,grid,dt,nb', [('poisson', (20, 37, 44), 'float64', 2), ('poisson', (9, 70, 20), 'float32', 1), ('advdiff', (17, 33, 36), 'float64', 3),
+                                           ('poisson', (50, 36), 'float64', 2), ('advdiff', (40, 64), 'float32', 1), ('poisson', (64, 64, 64), 'float32', 1),
+                                           ('poisson', (3, 3, 4), 'float64', 1), ('poisson', (1, 8), 'float64', 1)])
+def test_star_wavefront_triangular_solves_match_csr_level_solves(op, grid, dt, nb, monkeypatch):
+    """ILU(0) apply through the structured wavefront (star_trsv.cuh: pivots only, skewed warps, block counters) against
+    the general CSR level-scheduled solves on the same factors, and against the oracle's SciPy triangular solves."""
+    from oracle import precond as op_
+    csr = oracle_matrix(op, grid, dt)
+    rng = np.random.default_rng(21)
+    rhs = rng.standard_normal((nb, csr.shape[0])).astype(dt)
+    v = torch.as_tensor(rhs, device=DEV)
+    ilu_star = pb.IncompleteLU(dev_csr(csr))
+    assert ilu_star.star_wavefront, "star stencil factors must take the wavefront path"
+    monkeypatch.setenv('PHB200_TRSV', 'csr')
+    pb.clear_cache()
+    ilu_csr = pb.IncompleteLU(dev_csr(csr))
+    monkeypatch.delenv('PHB200_TRSV')
+    assert not ilu_csr.star_wavefront
+    assert torch.equal(ilu_star.lu, ilu_csr.lu)
+    tol = 1e-12 if dt == 'float64' else 2e-5
+    for rep in range(3):      # repeated solves reuse the monotone block counters
+        a, b = ilu_star.apply(v).cpu().numpy(), ilu_csr.apply(v).cpu().numpy()
+        scale = np.abs(b).max()
+        assert np.abs(a - b).max() <= tol * scale, f"wavefront differs from the CSR solves by {np.abs(a - b).max() / scale}"
+    if csr.shape[0] <= 50000:     # the oracle's sequential IKJ is a Python loop
+        Lx, Ux = op_.ilu0_exact(csr.astype(np.float64))
+        ref = op_.IncompleteLU(Lx, Ux).apply(rhs.astype(np.float64))
+        assert np.abs(a - ref).max() <= (1e-11 if dt == 'float64' else 1e-4) * np.abs(ref).max()
+
+
 def test_jacobi_equals_plain_cg_for_constant_diagonal():
     """for constant-diagonal Poisson, Jacobi-CG is plain CG up to scaling -> same iteration count."""
     case, csr, y, x0, rtol, atol, max_iter = case_inputs('p32c_cg_f32')
