@@ -514,6 +514,61 @@ static int star_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     return PHB200_OK;
 }
 
+template <typename T, bool LOWER>
+static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, int64_t ld, cudaStream_t stream) {
+    const StarDesc& st = p->star;
+    ScanTrsvArgs a;
+    a.nx = (int)st.nx; a.ny = (int)st.ny; a.nz = (int)st.nz;
+    a.ni = (a.nx + kScT - 1) / kScT;
+    a.nj = (a.ny + kScT - 1) / kScT;
+    a.nch = (a.nz + kScZ - 1) / kScZ;
+    a.batch = (int)batch;
+    a.ld = ld;
+    a.rd = p->rd;
+    a.B = B;
+    a.X = X;
+    const int64_t need = batch * a.ni * a.nj;
+    if (need > p->tr_flag_cap) {
+        PHB_CUDA(cudaStreamSynchronize(stream));
+        if (p->tr_flags) cudaFree(p->tr_flags);
+        p->tr_flags = nullptr;
+        PHB_CUDA(cudaMalloc(&p->tr_flags, sizeof(unsigned long long) * need));
+        PHB_CUDA(cudaMemsetAsync(p->tr_flags, 0, sizeof(unsigned long long) * need, stream));
+        p->tr_flag_cap = need;
+        p->tr_epoch = 0;
+    }
+    a.flags = p->tr_flags;
+    a.epoch_base = p->tr_epoch;
+    p->tr_epoch += (unsigned long long)a.nch;
+    a.ticket = p->tr_ticket;
+    a.n_ctas = (unsigned)need;
+    a.order = p->sc_order;
+    a.cx = LOWER ? st.cxm : st.cxp;
+    a.cy = LOWER ? st.cym : st.cyp;
+    a.cz = LOWER ? st.czm : st.czp;
+    auto kernel = k_star_trsv_scan<T, LOWER>;
+    constexpr size_t smem = scan_smem_bytes<T>();
+    static bool attr = false;
+    if (!attr) {
+        PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    PHB_LAUNCH(kernel, a.n_ctas, kScT * 32, smem, stream, a);
+    return PHB200_OK;
+}
+
+static int scan_order_setup(phb200_precond* p, const StarDesc& st, cudaStream_t stream) {
+    const int ni = (int)((st.nx + kScT - 1) / kScT), nj = (int)((st.ny + kScT - 1) / kScT);
+    std::vector<int32_t> order;
+    order.reserve((size_t)ni * nj);
+    for (int dg = 0; dg < ni + nj - 1; ++dg)
+        for (int i = dg < nj ? 0 : dg - nj + 1; i <= dg && i < ni; ++i) order.push_back(i * nj + (dg - i));
+    PHB_CUDA(cudaMalloc(&p->sc_order, sizeof(int32_t) * order.size()));
+    PHB_CUDA(cudaMemcpyAsync(p->sc_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    return PHB200_OK;
+}
+
 template <typename T>
 static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t stream) {
     const StarDesc& st = twin->star;
@@ -538,7 +593,8 @@ static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t
     PHB_CUDA(cudaFreeAsync(d_ok, stream));
     if (ok) {
         p->star = st;
-        p->star_mode = 1;
+        p->star_mode = (e && strcmp(e, "skew") == 0) ? 1 : 2;
+        if (p->star_mode == 2) PHB_TRY(scan_order_setup(p, st, stream));
     } else {
         cudaFree(p->rd);
         p->rd = nullptr;
@@ -563,6 +619,10 @@ int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int6
     if (p->kind == PHB200_PRE_ILU) {
         if (p->star_mode) {
             phb200_precond* q = const_cast<phb200_precond*>(p);   // counters / epoch are bookkeeping
+            if (p->star_mode == 2) {
+                if (p->dtype == PHB200_F32) return scan_trsv_launch<float, true>(q, (const float*)in, (float*)out, batch, ld, stream);
+                return scan_trsv_launch<double, true>(q, (const double*)in, (double*)out, batch, ld, stream);
+            }
             if (p->dtype == PHB200_F32) return star_trsv_launch<float, true>(q, (const float*)in, (float*)out, batch, ld, stream);
             return star_trsv_launch<double, true>(q, (const double*)in, (double*)out, batch, ld, stream);
         }
@@ -581,6 +641,10 @@ int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp,
         PHB_TRY(precond_apply_inv_l(p, in, out, batch, ld, stream));
         if (p->star_mode) {
             phb200_precond* q = const_cast<phb200_precond*>(p);
+            if (p->star_mode == 2) {
+                if (p->dtype == PHB200_F32) return scan_trsv_launch<float, false>(q, (const float*)out, (float*)out, batch, ld, stream);
+                return scan_trsv_launch<double, false>(q, (const double*)out, (double*)out, batch, ld, stream);
+            }
             if (p->dtype == PHB200_F32) return star_trsv_launch<float, false>(q, (const float*)out, (float*)out, batch, ld, stream);
             return star_trsv_launch<double, false>(q, (const double*)out, (double*)out, batch, ld, stream);
         }
@@ -771,6 +835,7 @@ int phb200_precond_destroy(phb200_precond* p) {
     if (p->rd) cudaFree(p->rd);
     if (p->tr_flags) cudaFree(p->tr_flags);
     if (p->tr_ticket) cudaFree(p->tr_ticket);
+    if (p->sc_order) cudaFree(p->sc_order);
     phb200_sptrsv_plan_destroy(p->plan_l);
     phb200_sptrsv_plan_destroy(p->plan_u);
     delete p;

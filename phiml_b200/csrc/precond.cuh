@@ -31,8 +31,10 @@ struct phb200_precond {
     int32_t* diag_pos;     // device, owned
     phb200_trsv_plan* plan_l;
     phb200_trsv_plan* plan_u;
-    // star-stencil wavefront solves (star_trsv.cuh): reciprocal pivots + block counters; star_mode 0 = CSR level solves
+    // star-stencil wavefront solves (star_trsv.cuh): reciprocal pivots + block counters; star_mode 0 = CSR level solves,
+    // 1 = skewed warps, 2 = row scans
     int star_mode;
+    int32_t* sc_order;                 // device, owned: tiles of the row-scan kernel in dependency (anti-diagonal) order
     phb::StarDesc star;
     void* rd;                          // device, owned: 1 / U_ii
     unsigned long long* tr_flags;      // device, owned

@@ -365,4 +365,183 @@ __global__ void __launch_bounds__(kBlock) k_star_ilu_check(CsrView A, const T* _
     if (!good) *ok = 0;
 }
 
+// ====================================================================================================================
+// Second formulation: ROW SCANS.  The z recurrence of one row chunk (32 consecutive z') is a first-order linear
+// recurrence w_z = A_z + B_z w_{z-1} (A = rd g, B = -c_z rd, g = b - c_x w_x - c_y w_y) and is solved by ONE warp with a
+// 5-step shuffle scan; lanes are z, so every global access is a coalesced 128-byte line and nothing is skewed.  A CTA of
+// 8 warps owns a tile of 8 planes x 8 rows and walks over the z chunks; inside a chunk the 64 rows are done along the
+// anti-diagonals ix + iy = d (15 levels, <= 8 independent rows per level = one per warp).  Tiles hand their last plane /
+// last row to the +x / +y tile chunk by chunk through monotone counters, so the critical path is
+// (nx/8 + ny/8 + nz/32) chunk times of 15 short levels instead of (nx/TX + nz/16) sweeps of ~16 TX serial steps.
+// (The scan changes the rounding sequence of the recurrence — a few ulp, like the reciprocal pivots.)
+// ====================================================================================================================
+constexpr int kScT = 8;            // tile edge (planes and rows)
+constexpr int kScZ = 32;           // z elements per chunk = lanes
+constexpr int kScStages = 3;       // staged chunks of rhs / rd
+
+struct ScanTrsvArgs {
+    int nx, ny, nz;
+    int ni, nj, nch;        // tiles along x, y; chunks along z
+    int batch;
+    int64_t ld;
+    const void* rd;
+    const void* B;
+    void* X;
+    unsigned long long* flags;      // [batch][ni][nj]
+    unsigned long long epoch_base;
+    unsigned* ticket;
+    unsigned n_ctas;
+    const int32_t* order;   // [ni*nj] tile ids (i * nj + j) sorted by anti-diagonal: a tile's dependencies come first
+    double cx, cy, cz;
+};
+
+template <typename T> constexpr size_t scan_smem_bytes() {
+    return sizeof(T) * ((size_t)kScStages * 2 * kScT * kScT * kScZ + (size_t)(kScT + 1) * (kScT + 1) * kScZ + kScT * kScT);
+}
+
+template <typename T, bool LOWER>
+__global__ void __launch_bounds__(kScT * 32) k_star_trsv_scan(const ScanTrsvArgs a) {
+    constexpr int TT = kScT, ZC = kScZ, V = 16 / (int)sizeof(T), GPR = ZC / V, NST = kScStages;
+    extern __shared__ __align__(16) unsigned char scan_smem[];
+    __shared__ unsigned s_ticket;
+    T* sB = reinterpret_cast<T*>(scan_smem);                   // [NST][TT][TT][ZC]
+    T* sR = sB + NST * TT * TT * ZC;                           // [NST][TT][TT][ZC]
+    T* sW = sR + NST * TT * TT * ZC;                           // [TT+1][TT+1][ZC]   handed-on values incl. plane -1 and row -1
+    T* sC = sW + (TT + 1) * (TT + 1) * ZC;                     // [TT][TT]           carry: value at the last z' of the previous chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const unsigned cta = s_ticket;
+    if (tid == 0 && cta == a.n_ctas - 1) *a.ticket = 0u;
+    const int n_tiles = a.ni * a.nj;
+    const int b = (int)(cta / (unsigned)n_tiles);
+    const int tile = a.order[cta % (unsigned)n_tiles];
+    const int ti = tile / a.nj, tj = tile % a.nj;
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int x0 = ti * TT, y0 = tj * TT;
+    const T cx = (T)a.cx, cy = (T)a.cy, cz = (T)a.cz;
+    const T* __restrict__ rd = (const T*)a.rd;
+    const T* Bb = (const T*)a.B + (int64_t)b * a.ld;
+    T* Xb = (T*)a.X + (int64_t)b * a.ld;
+    unsigned long long* my_flag = a.flags + ((int64_t)b * a.ni + ti) * a.nj + tj;
+    const unsigned long long* flag_x = ti > 0 ? my_flag - a.nj : nullptr;
+    const unsigned long long* flag_y = tj > 0 ? my_flag - 1 : nullptr;
+    auto px = [&](int lx) { return LOWER ? lx : nx - 1 - lx; };
+    auto py = [&](int ly) { return LOWER ? ly : ny - 1 - ly; };
+    auto seg0 = [&](int c) { return LOWER ? c * ZC : nz - (c + 1) * ZC; };
+    const int col = LOWER ? lane : ZC - 1 - lane;              // tile column of this lane's z'
+
+    auto issue_chunk = [&](int c) {
+        if (c < a.nch) {
+            const int st = c % NST, z0 = seg0(c);
+#pragma unroll
+            for (int i = 0; i < (TT * TT * GPR) / (TT * 32); ++i) {
+                const int k = i * TT * 32 + tid;
+                const int row = k / GPR, g = k % GPR;
+                const int ixl = row / TT, iyl = row % TT;
+                const int zph = z0 + g * V;
+                const bool ok = (x0 + ixl < nx) && (y0 + iyl < ny) && zph >= 0 && zph < nz;
+                const int64_t off = ok ? (((int64_t)px(x0 + ixl) * ny + py(y0 + iyl)) * nz + zph) : 0;
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(sB + ((st * TT + ixl) * TT + iyl) * ZC + g * V);
+                cp_async16(d, Bb + off, ok);
+                cp_async16(d + (uint32_t)(NST * TT * TT * ZC * sizeof(T)), rd + off, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    issue_chunk(0);
+    issue_chunk(1);
+    for (int k = tid; k < TT * TT; k += TT * 32) sC[k] = T(0);
+    const unsigned long long target0 = a.epoch_base;
+    unsigned long long seen_x = 0, seen_y = 0;
+
+    for (int c = 0; c < a.nch; ++c) {
+        // ---- dependencies: the -x and -y tiles have published chunk c
+        if (tid == 0) {
+            const unsigned long long need = target0 + (unsigned long long)c + 1ull;
+            const long long t0 = clock64();
+            unsigned ns = 32;
+            auto wait_for = [&](const unsigned long long* flag, unsigned long long& seen) {
+                while (seen < need) {
+                    seen = ld_poll_u64(flag);
+                    if (seen < need) {
+                        __nanosleep(ns);
+                        if (ns < 128) ns *= 2;
+                        if (clock64() - t0 > 6000000000ll) __trap();
+                    }
+                }
+            };
+            if (flag_x) wait_for(flag_x, seen_x);
+            if (flag_y) wait_for(flag_y, seen_y);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+        cp_async_wait<1>();          // chunk c has landed (c+1 may still be in flight)
+        __syncthreads();
+        issue_chunk(c + 2);          // its stage held chunk c-1: everybody is done with it
+        const int z0 = seg0(c);
+        const int zl = c * ZC + lane;                            // logical z' of this lane
+        const bool z_ok = zl < nz;
+        const int zph = LOWER ? zl : nz - 1 - zl;
+        // ---- boundary rows handed over by the neighbour tiles: plane -1 (rows 0..7) and row -1 (planes 0..7)
+        for (int r = warp; r < 2 * TT; r += TT) {
+            const bool xside = r < TT;
+            const int k = xside ? r : r - TT;
+            const int gx = xside ? x0 - 1 : x0 + k, gy = xside ? y0 + k : y0 - 1;
+            T v = T(0);
+            if (gx >= 0 && gy >= 0 && gx < nx && gy < ny && z_ok) {
+                const int64_t off = ((int64_t)px(gx) * ny + py(gy)) * nz + zph;
+                v = __ldcg(Xb + off);
+                if (LOWER) v = v * __ldcg(rd + off);
+            }
+            sW[((xside ? 0 : k + 1) * (TT + 1) + (xside ? k + 1 : 0)) * ZC + col] = v;
+        }
+        __syncthreads();
+        (void)z0;
+        const int st = c % NST;
+        // ---- the 64 rows of the chunk along the anti-diagonals ix + iy = d
+#pragma unroll 1
+        for (int d = 0; d < 2 * TT - 1; ++d) {
+            const int ix_lo = d > TT - 1 ? d - (TT - 1) : 0;
+            const int cnt = (d < TT ? d : TT - 1) - ix_lo + 1;
+            if (warp < cnt) {
+                const int ixl = ix_lo + warp, iyl = d - ixl;
+                if (x0 + ixl < nx && y0 + iyl < ny) {
+                    const T bv = sB[((st * TT + ixl) * TT + iyl) * ZC + col], rv = sR[((st * TT + ixl) * TT + iyl) * ZC + col];
+                    const T wx = sW[(ixl * (TT + 1) + iyl + 1) * ZC + col], wy = sW[((ixl + 1) * (TT + 1) + iyl) * ZC + col];
+                    const T carry = sC[ixl * TT + iyl];
+                    T g = fma_t<T>(-cx, wx, bv);
+                    g = fma_t<T>(-cy, wy, g);
+                    T A = z_ok ? g * rv : T(0), Bc = z_ok ? -cz * rv : T(0);
+#pragma unroll
+                    for (int k = 1; k < 32; k <<= 1) {
+                        const T Ap = __shfl_up_sync(0xffffffffu, A, k), Bp = __shfl_up_sync(0xffffffffu, Bc, k);
+                        if (lane >= k) {
+                            A = fma_t<T>(Bc, Ap, A);
+                            Bc = Bc * Bp;
+                        }
+                    }
+                    const T w = fma_t<T>(Bc, carry, A);
+                    T out = w;
+                    if (LOWER) {   // the lower solve returns t = g - c_z w_{z-1}, not w = t rd
+                        T wp = __shfl_up_sync(0xffffffffu, w, 1);
+                        if (lane == 0) wp = carry;
+                        out = fma_t<T>(-cz, wp, g);
+                    }
+                    sW[((ixl + 1) * (TT + 1) + iyl + 1) * ZC + col] = w;
+                    if (z_ok) Xb[((int64_t)px(x0 + ixl) * ny + py(y0 + iyl)) * nz + zph] = out;
+                    const int last = min(ZC, nz - c * ZC) - 1;
+                    if (lane == last) sC[ixl * TT + iyl] = w;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- publish chunk c (all global stores of the CTA are ordered before the counter by fence + barrier above)
+        if (tid == 0) {
+            __threadfence();
+            st_release_u64(my_flag, target0 + (unsigned long long)c + 1ull);
+        }
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace phb
