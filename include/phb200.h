@@ -180,6 +180,18 @@ int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream
 int phb200_solver_set_dist(phb200_solver* s, void* totals);
 int phb200_solver_dist_step(phb200_solver* s, int step, void* stream);
 
+/* Callback-driven distributed mode: EVERY method ('CG', 'CG-adaptive', torch rules, 'biCG-stab(L)'; no / Jacobi
+ * preconditioner) on a star stencil in slab mode.  The loop stays inside the library (start / advance / run as usual);
+ * wherever the algorithm has a global reduction the kernel leaves the rank-local sums in `totals` (batch*4 doubles) and
+ * the library calls `allreduce(totals, count, stream, user)` — the caller sums over the ranks (ncclAllReduce on `stream`;
+ * phiml_b200/multi_gpu.py uses torch.distributed) — then applies the scalar step identically on every rank; before every
+ * product it calls `halo(vec, stream, user)` so that the caller refreshes the two halo planes of the (batch, ld) extended
+ * array `vec` (NVLink P2P / NCCL send-recv).  Callbacks return 0 on success.  BiCGstab(2): 9 reductions + 4 halo exchanges
+ * per iteration (BASELINE config 5). */
+typedef int (*phb200_allreduce_fn)(void* totals, int64_t count, void* stream, void* user);
+typedef int (*phb200_halo_fn)(void* vec, void* stream, void* user);
+int phb200_solver_set_dist_callbacks(phb200_solver* s, void* totals, phb200_allreduce_fn allreduce, phb200_halo_fn halo, void* user);
+
 /* Enqueue up to n_iter further iterations (asynchronous; iterations after all systems finished are skipped on
  * the device). */
 int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream);

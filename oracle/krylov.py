@@ -174,7 +174,7 @@ def cg_adaptive(lin, y, x0, rtol, atol, max_iter, pre=None, name="numpy") -> Ora
     its = np.zeros(nb, np.int32)
     fev = np.ones(nb, np.int32)
     rsq = rowdot(r, r)
-    check = StopOnL2(np.sum(y ** 2, -1), rtol, atol, max_iter)
+    check = StopOnL2(rowdot(y, y)[:, 0], rtol, atol, max_iter)
     go, conv, div = check(its, rsq)
 
     def body(go, x, d, q, r, its, fev, _c, _d):
@@ -218,7 +218,7 @@ def bicgstab_l(lin, y, x0, rtol, atol, max_iter, pre=None, poly_order=2, name="n
     r_shadow = r
     its = np.zeros(nb, np.int32)
     fev = np.ones(nb, np.int32)
-    check = StopOnL2(np.sum(y ** 2, -1), rtol, atol, max_iter)
+    check = StopOnL2(rowdot(y, y)[:, 0], rtol, atol, max_iter)
     go, conv, div = check(its, rowdot(r, r))
     one = np.ones((nb, 1), y.dtype)
     zero = np.zeros((nb, 1), y.dtype)
@@ -301,7 +301,7 @@ def bicgstab_1(lin, y, x0, rtol, atol, max_iter, pre=None) -> OracleResult:
     shadow = np.ones_like(x)
     its = np.zeros(nb, np.int32)
     fev = np.ones(nb, np.int32)
-    check = StopOnL2(np.sum(y ** 2, -1), rtol, atol, max_iter)
+    check = StopOnL2(rowdot(y, y)[:, 0], rtol, atol, max_iter)
     go, conv, div = check(its, rowdot(r, r))
     one = np.ones((nb, 1), y.dtype)
     rho_prev, rho, omega, alpha = one, one, one, np.zeros((nb, 1), y.dtype)

@@ -657,6 +657,10 @@ struct phb200_solver {
     const void* rtol;
     const void* atol;
     const int32_t* max_iter;
+    // callback-driven distributed mode (any method): the library calls these between its kernels
+    phb200_allreduce_fn ar_cb;
+    phb200_halo_fn halo_cb;
+    void* cb_user;
     int resident;              // PHB200_OPT_RESIDENT: -1 cost model decides, 0 never, 1 whenever the system fits on chip
     int resident_used;         // 1 if the last run() went through the resident kernel
     int64_t off, n_act;        // element range [off, off + n_act) of every vector that this rank owns (whole vector if not a slab)
@@ -734,7 +738,25 @@ struct Run {
     void prof_end() {
         if (s->prof) cudaEventRecord(s->prof_events->back(), st);
     }
+    bool cb_mode() const { return s->ar_cb != nullptr; }
+    // all-reduce of the deferred local sums over the ranks, then the scalar step on every rank identically
+    template <class F> int reduce_and_finalize(const F& f) {
+        const int rc = s->ar_cb(s->totals, (int64_t)batch * kMaxDots, (void*)st, s->cb_user);
+        if (rc != 0) { set_error("all-reduce callback failed (%d)", rc); return PHB200_ERR_CUDA; }
+        return finalize_only(f);
+    }
     template <class P> int phase(const P& p) {
+        if constexpr (P::ND > 0) {
+            if (cb_mode()) {
+                P q = p;
+                q.defer = s->totals;
+                prof_begin();
+                int r = launch_phase<T, P>(q, s->n_act, ld, batch, st, s->off);
+                prof_end();
+                if (r != PHB200_OK) return r;
+                return reduce_and_finalize(q);
+            }
+        }
         prof_begin();
         int r = launch_phase<T, P>(p, s->n_act, ld, batch, st, s->off);
         prof_end();
@@ -745,6 +767,19 @@ struct Run {
         return PHB200_OK;
     }
     template <class E> int spmv(const T* x, T* y, const E& e) {
+        if (cb_mode()) {
+            const int rc = s->halo_cb((void*)x, (void*)st, s->cb_user);   // the neighbours' boundary planes of the input vector
+            if (rc != 0) { set_error("halo callback failed (%d)", rc); return PHB200_ERR_CUDA; }
+            if constexpr (E::ND > 0) {
+                E q = e;
+                q.defer = s->totals;
+                prof_begin();
+                int r = launch_spmv<T, E>(s->A, x, ld, y, ld, (const T*)nullptr, batch, q, st);
+                prof_end();
+                if (r != PHB200_OK) return r;
+                return reduce_and_finalize(q);
+            }
+        }
         prof_begin();
         int r = launch_spmv<T, E>(s->A, x, ld, y, ld, (const T*)nullptr, batch, e, st);
         prof_end();
@@ -855,7 +890,7 @@ struct Run {
     // Jacobi / un-preconditioned 'CG' on a star stencil: two kernels per iteration (SURVEY §8d counts 13 N w of traffic
     // for the three-phase form; this form moves 9 N w, +2 N w with a non-constant diagonal).
     bool fused() const {
-        return s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU;
+        return s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && !cb_mode();
     }
     CgDq<T> make_dq() {
         CgDq<T> e;
@@ -1403,9 +1438,21 @@ int phb200_solver_set_dist(phb200_solver* s, void* totals) {
     return PHB200_OK;
 }
 
+int phb200_solver_set_dist_callbacks(phb200_solver* s, void* totals, phb200_allreduce_fn allreduce, phb200_halo_fn halo, void* user) {
+    PHB_ARG(s && !s->started, "set_dist_callbacks must be called before start");
+    PHB_ARG(totals && allreduce && halo, "null argument");
+    PHB_ARG(s->A->kind == PHB200_MAT_STENCIL && s->A->is_star, "distributed solves need a star stencil in slab mode (phb200_matrix_set_slab)");
+    PHB_ARG(s->pre != PHB200_PRE_ILU, "ILU across slabs is a pipeline along x and is not supported in distributed mode");
+    s->totals = (double*)totals;
+    s->ar_cb = allreduce;
+    s->halo_cb = halo;
+    s->cb_user = user;
+    return PHB200_OK;
+}
+
 int phb200_solver_dist_step(phb200_solver* s, int step, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    PHB_ARG(s && s->started && s->totals, "solver not started in distributed mode");
+    PHB_ARG(s && s->started && s->totals && !s->ar_cb, "solver not started in (step-driven) distributed mode");
     if (!s->tma_ok) { set_error("distributed mode needs the TMA path (tensor map creation failed)"); return PHB200_ERR_UNSUPPORTED; }
     if (s->dtype == PHB200_F32) return make_run<float>(s, st).dist_step(step);
     return make_run<double>(s, st).dist_step(step);
@@ -1413,7 +1460,7 @@ int phb200_solver_dist_step(phb200_solver* s, int step, void* stream_) {
 
 int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream_) {
     PHB_ARG(s && s->started, "solver not started");
-    PHB_ARG(!s->totals, "a distributed solver is advanced with phb200_solver_dist_step");
+    PHB_ARG(!s->totals || s->ar_cb, "a step-driven distributed solver is advanced with phb200_solver_dist_step");
     PHB_ARG(n_iter >= 0, "n_iter must be >= 0");
     return advance(s, n_iter, (cudaStream_t)stream_);
 }
@@ -1445,7 +1492,7 @@ int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream_) {
 int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started, "solver not started");
-    PHB_ARG(!s->totals, "a distributed solver is advanced with phb200_solver_dist_step");
+    PHB_ARG(!s->totals || s->ar_cb, "a step-driven distributed solver is advanced with phb200_solver_dist_step");
     if (s->passes == 0) {   // small systems: the whole loop on chip (resident.cuh)
         int cs = 0, lpc = 0;
         size_t smem = 0;

@@ -234,3 +234,138 @@ class CudaSlabEngine:
 
     def result(self):
         return self.solver.result()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one system, x-slab row partition, ANY method of the device loop (BASELINE config 5: BiCGstab(2) across 8 GPUs)
+# ----------------------------------------------------------------------------------------------------------------------
+
+class SlabSolver:
+    """
+    ``Backend.linear_solve`` for ONE star-stencil system split into x-slabs over the ranks of ``group``: 'CG', 'CG-adaptive',
+    'biCG-stab', 'biCG-stab(L)' with no or Jacobi preconditioner, generic (NumPy-flavour) rules.
+
+    The Krylov loop stays inside the engine; the engine calls back into ``allreduce(totals)`` wherever the algorithm has a
+    global reduction (rank-local sums -> sums over all ranks, then the scalar step runs identically everywhere) and into
+    ``halo(vec)`` before every product (boundary planes of the input vector from the two slab neighbours).
+    ``engine_factory(ext_grid, xb, xe)`` builds the per-rank engine: the CUDA engine below (libphb200's callback-driven
+    distributed mode), or the CPU test double of tests/_slab_engine.py in the gloo tests.
+    """
+
+    def __init__(self, grid: Sequence[int], offsets, coeffs, dtype: torch.dtype, method: str = 'biCG-stab(2)', jacobi: bool = False,
+                 device=None, group=None, engine_factory=None):
+        assert len(grid) == 3, "slab partition is for 3-D grids (x is the partitioned axis)"
+        self.grid = tuple(int(g) for g in grid)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.x_lo, self.x_hi = slab_bounds(self.grid[0], self.world, self.rank)
+        self.nxl = self.x_hi - self.x_lo
+        self.plane = self.grid[1] * self.grid[2]
+        self.dtype = dtype
+        self.method = method
+        self.counts = {'allreduce': 0, 'halo': 0}
+        ext_grid = (self.nxl + 2, self.grid[1], self.grid[2])
+        factory = engine_factory or (lambda g, xb, xe: CudaCallbackEngine(g, xb, xe, offsets, coeffs, dtype, method, jacobi, device))
+        self.engine = factory(ext_grid, 1, self.nxl + 1)
+
+    extend = SlabCG.extend
+    interior = SlabCG.interior
+
+    def _allreduce(self, t: torch.Tensor):
+        self.counts['allreduce'] += 1
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _halo(self, ext: torch.Tensor):
+        self.counts['halo'] += 1
+        exchange_halo_planes(ext, self.nxl, self.plane, self.rank, self.world, self.group)
+
+    def solve(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, fixed_iterations: Optional[int] = None):
+        """Returns (x_local, residual_local, iterations, function_evaluations, converged, diverged); scalars identical on all ranks."""
+        y_ext, x_ext = self.extend(y_local), self.extend(x0_local)
+        x, r, its, fev, conv, div = self.engine.solve(y_ext, x_ext, rtol, atol, int(max_iter), self._allreduce, self._halo, fixed_iterations)
+        return self.interior(x), self.interior(r), its, fev, conv, div
+
+
+class CudaCallbackEngine:
+    """libphb200's callback-driven distributed mode (phb200_solver_set_dist_callbacks) behind the SlabSolver engine interface."""
+
+    def __init__(self, ext_grid, xb, xe, offsets, coeffs, dtype, method, jacobi, device):
+        from . import _engine as E
+        from .sparse import Matrix
+        from .precond import JacobiPreconditioner
+        self.E = E
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.matrix = Matrix.stencil_matrix(ext_grid, offsets, coeffs, dtype, self.device)
+        E.check(E.lib().phb200_matrix_set_slab(self.matrix.handle, xb, xe))
+        self.pre = JacobiPreconditioner(self.matrix) if jacobi else None
+        self.method = method
+
+    def solve(self, y_ext, x_ext, rtol, atol, max_iter, allreduce, halo, fixed_iterations=None):
+        import ctypes
+        from .solve import DeviceSolver
+        E = self.E
+        nb, n_ext = y_ext.shape
+        dev = y_ext.device
+        code, order, _ = _method_code(self.method, self.pre, np.array([[max_iter]]))
+        if code == E.CG_TORCH:
+            code = E.CG                    # generic rules: the torch fast path has no distributed meaning of its own
+        if code == E.CG_ADAPTIVE_TORCH:
+            code = E.CG_ADAPTIVE
+        totals = torch.zeros(nb * 4, dtype=torch.float64, device=dev)
+        solver = DeviceSolver(self.matrix, self.pre, code, order, nb)
+        rt = torch.as_tensor(rtol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
+        at = torch.as_tensor(atol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
+        mi = torch.full((nb,), int(max_iter), dtype=torch.int32, device=dev)
+        views = {}          # device address -> tensor view of one (batch, n_ext) vector
+        errors = []
+
+        def view_of(ptr):
+            v = views.get(ptr)
+            if v is None:
+                for base in (solver.x, solver.r, x_ext):
+                    if base.data_ptr() == ptr:
+                        v = base
+                ws = solver.workspace
+                off = ptr - ws.data_ptr()
+                if v is None and 0 <= off < ws.numel():
+                    v = ws[off: off + nb * n_ext * y_ext.element_size()].view(y_ext.dtype).view(nb, n_ext)
+                if v is None:
+                    raise RuntimeError(f"halo callback for an unknown vector at {ptr:#x}")
+                views[ptr] = v
+            return v
+
+        @ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p)
+        def ar_cb(ptr, count, stream, user):
+            try:
+                allreduce(totals)
+                return 0
+            except Exception as exc:           # an exception must not unwind through C
+                errors.append(exc)
+                return 1
+
+        @ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+        def halo_cb(ptr, stream, user):
+            try:
+                halo(view_of(ptr))
+                return 0
+            except Exception as exc:
+                errors.append(exc)
+                return 1
+
+        E.check(E.lib().phb200_solver_set_dist_callbacks(solver._h, E.ptr(totals), ar_cb, halo_cb, None))
+        halo(x_ext)                                 # A x0 needs the neighbours' boundary planes (start() copies x0 incl. halos)
+        try:
+            solver.start(y_ext, x_ext, rt, at, mi, zero_init=True)
+            if fixed_iterations is not None:
+                solver.advance(int(fixed_iterations))
+            else:
+                solver.run(int(max_iter))
+        except Exception:
+            if errors:
+                raise errors[0]
+            raise
+        its, fev, conv, div = solver.result()
+        self.last_solver = solver
+        return solver.x, solver.r, its, fev, conv, div

@@ -118,3 +118,53 @@ class CpuSlabEngine:
 
     def result(self):
         return self.its, self.fev, self.conv, self.div
+
+
+class CpuCallbackEngine:
+    """
+    TEST DOUBLE of phiml_b200.multi_gpu.CudaCallbackEngine: runs the ORACLE's Krylov loops (oracle/krylov.py) on this rank's
+    slab with the two callbacks of the distributed mode — ``halo(vec)`` before every product, ``allreduce(totals)`` for every
+    dot product — so that the gloo tests exercise SlabSolver's partitioning, halo exchange and reduction plumbing for any method.
+    """
+
+    def __init__(self, ext_grid, xb, xe, offsets, coeffs, dtype, method, jacobi):
+        self.base = CpuSlabEngine(ext_grid, xb, xe, offsets, coeffs, dtype, jacobi)
+        self.method, self.jacobi, self.dtype = method, jacobi, dtype
+
+    def solve(self, y_ext, x_ext, rtol, atol, max_iter, allreduce, halo, fixed_iterations=None):
+        from oracle import krylov, precond
+        base = self.base
+        nb = y_ext.shape[0]
+        g = base.g
+
+        def embed(v_own):
+            ext = torch.zeros((nb, g[0] * g[1] * g[2]), dtype=self.dtype)
+            ext.view(nb, *g)[:, base.xb:base.xe] = torch.as_tensor(v_own).view(nb, base.xe - base.xb, g[1], g[2])
+            return ext
+
+        def lin(v_own):
+            ext = embed(v_own)
+            halo(ext)
+            return base._own(base._apply(ext)).numpy()
+
+        def rowdot(a, b):
+            t = torch.as_tensor(np.sum(a * b, axis=-1, keepdims=True), dtype=torch.float64).reshape(-1).clone()
+            allreduce(t)
+            return t.numpy().reshape(nb, 1).astype(a.dtype)
+
+        class Jac:
+            def apply(self_, v): return v * np.asarray(base.cinv, dtype=v.dtype)
+            apply_inv_l = apply
+            def apply_inv_u(self_, v): return v
+            def __repr__(self_): return "jacobi"
+
+        saved = krylov.rowdot
+        krylov.rowdot = rowdot
+        try:
+            np_dt = np.float64 if self.dtype == torch.float64 else np.float32
+            res = krylov.linear_solve(self.method, lin, base._own(y_ext).numpy(), base._own(x_ext).numpy(), np.asarray(rtol, np_dt), np.asarray(atol, np_dt),
+                                      np.full((1, nb), max_iter), Jac() if self.jacobi else None, flavour='numpy')
+        finally:
+            krylov.rowdot = saved
+        return (embed(res.x), embed(res.residual), torch.as_tensor(res.iterations), torch.as_tensor(res.function_evaluations),
+                torch.as_tensor(res.converged), torch.as_tensor(res.diverged))

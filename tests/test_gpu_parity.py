@@ -488,6 +488,40 @@ def test_slab_engine_single_rank_equals_plain_solve():
     assert float((r - ref.residual).abs().max()) < 1e-5 * float(y.abs().max())
 
 
+@pytest.mark.parametrize('method,jacobi,dt', [('biCG-stab(2)', False, 'float64'), ('biCG-stab(2)', False, 'float32'), ('biCG-stab', True, 'float64'),
+                                              ('CG-adaptive', False, 'float64'), ('biCG-stab(3)', False, 'float64')])
+def test_callback_distributed_mode_single_rank_equals_plain_solve(method, jacobi, dt):
+    """SlabSolver on one rank (extended array with zero halo planes; every reduction goes kernel -> totals -> all-reduce
+    callback -> k_finalize, every product is preceded by the halo callback) must reproduce the ordinary device loop."""
+    from phiml_b200.multi_gpu import SlabSolver
+    from _cases import ADVDIFF
+    from oracle.assemble import advdiff_shifts, laplace_shifts
+    grid = (24, 16, 32)
+    npdt = np.float64 if dt == 'float64' else np.float32
+    tdt = torch.float64 if dt == 'float64' else torch.float32
+    shifts = laplace_shifts(3) if method == 'CG-adaptive' else advdiff_shifts(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], npdt)
+    offsets, coeffs = [s for s, _ in shifts], [float(c) for _, c in shifts]
+    n = int(np.prod(grid))
+    y = torch.as_tensor(np.random.default_rng(0).standard_normal((2, n)).astype(npdt), device=DEV)
+    st = pb.Matrix.stencil_matrix(grid, offsets, coeffs, tdt, DEV)
+    rtol = [1e-10, 1e-10] if dt == 'float64' else [1e-5, 1e-5]
+    pre = pb.JacobiPreconditioner(st) if jacobi else None
+    with streaming_kernels():
+        if method == 'CG-adaptive':
+            ref = pb.generic_conjugate_gradient_adaptive(st, y, torch.zeros_like(y), rtol, [0.0, 0.0], np.array([[1000, 1000]]))
+        else:
+            ref = pb.linear_solve(method, st, y, torch.zeros_like(y), rtol, [0.0, 0.0], np.array([[1000, 1000]]), pre, None)
+    sol = SlabSolver(grid, offsets, coeffs, tdt, method=method, jacobi=jacobi, device=DEV)
+    x, r, its, fev, conv, div = sol.solve(y, torch.zeros_like(y), rtol, [0.0, 0.0], 1000)
+    assert torch.equal(its, ref.iterations) and torch.equal(fev, ref.function_evaluations)
+    assert torch.equal(conv, ref.converged) and torch.equal(div, ref.diverged)
+    if method != 'biCG-stab(3)':
+        assert bool(conv.all())
+    assert sol.counts['halo'] >= int(fev.max()) and sol.counts['allreduce'] >= int(its.max())
+    # same kernels, same reduction order on one rank -> identical iterate
+    assert torch.equal(x, ref.x) and torch.equal(r, ref.residual)
+
+
 def test_batch_minimum_tolerance_can_be_replaced_before_the_first_pass():
     """Hook used by multi_gpu.solve_sharded: installing a smaller (global) tolerance makes the local systems iterate longer."""
     case, csr, y, x0, rtol, atol, max_iter = case_inputs('p32_batch8_f32')

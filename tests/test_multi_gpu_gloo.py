@@ -80,3 +80,58 @@ def test_slab_cg_two_ranks_matches_single_process_oracle(tmp_path):
     np.testing.assert_array_equal(parts[0]['fev'], parts[0]['its'] + 1)
     scale = np.abs(ref.x).max(axis=1, keepdims=True)
     assert np.max(np.abs(x - ref.x) / scale) < 1e-7      # rel_tol 1e-8; the stopping iteration may differ by one
+
+
+def _worker_any_method(rank, world, port, grid, method, jacobi, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from phiml_b200.multi_gpu import SlabSolver
+        from _slab_engine import CpuCallbackEngine
+        from _cases import ADVDIFF
+        from oracle.assemble import advdiff_shifts
+        shifts = advdiff_shifts(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float64)
+        offsets, coeffs = [s for s, _ in shifts], [float(c) for _, c in shifts]
+        dtype = torch.float64
+        sol = SlabSolver(grid, offsets, coeffs, dtype, method=method, jacobi=jacobi, group=None,
+                         engine_factory=lambda g, xb, xe: CpuCallbackEngine(g, xb, xe, offsets, coeffs, dtype, method, jacobi))
+        n = int(np.prod(grid))
+        y = np.random.default_rng(3).standard_normal((2, n))
+        plane = grid[1] * grid[2]
+        y_loc = torch.as_tensor(y[:, sol.x_lo * plane: sol.x_hi * plane].copy())
+        x, r, its, fev, conv, div = sol.solve(y_loc, torch.zeros_like(y_loc), [1e-10, 1e-10], [0.0, 0.0], 500)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=x.numpy(), r=r.numpy(), its=its.numpy(), fev=fev.numpy(), conv=conv.numpy(), div=div.numpy(),
+                 lo=sol.x_lo, hi=sol.x_hi, n_allreduce=sol.counts['allreduce'], n_halo=sol.counts['halo'])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('method,jacobi', [('biCG-stab(2)', False), ('biCG-stab', True), ('CG-adaptive', False)])
+def test_slab_solver_two_ranks_any_method_matches_single_process_oracle(tmp_path, method, jacobi):
+    """BASELINE config 5 in miniature: nonsymmetric advection-diffusion, row-partitioned over 2 ranks, halo exchange before
+    every product, all-reduce for every dot product; the result must be the single-process solve."""
+    from oracle import krylov, precond
+    from _util import oracle_matrix
+    grid = (9, 6, 8)
+    port = 29900 + (os.getpid() % 300) + (7 if jacobi else 0) + len(method)
+    mp.spawn(_worker_any_method, args=(2, port, grid, method, jacobi, str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(2)]
+    assert parts[0]['lo'] == 0 and parts[0]['hi'] == parts[1]['lo'] and parts[1]['hi'] == grid[0]
+    x = np.concatenate([p['x'] for p in parts], axis=1)
+    csr = oracle_matrix('advdiff', grid, 'float64')
+    n = csr.shape[0]
+    y = np.random.default_rng(3).standard_normal((2, n))
+    ref = krylov.linear_solve(method, csr, y, np.zeros_like(y), np.float64([1e-10, 1e-10]), np.float64([0, 0]), np.array([[500, 500]]),
+                              precond.Jacobi(csr) if jacobi else None, flavour='numpy')
+    for p in parts:
+        np.testing.assert_array_equal(p['its'], parts[0]['its'])
+        np.testing.assert_array_equal(p['fev'], parts[0]['fev'])
+        assert p['conv'].all() and not p['div'].any()
+        assert p['n_allreduce'] == parts[0]['n_allreduce'] and p['n_halo'] == parts[0]['n_halo'] and p['n_halo'] >= int(parts[0]['fev'].max())
+    assert np.max(np.abs(parts[0]['its'].astype(int) - ref.iterations.astype(int))) <= 1
+    scale = np.abs(ref.x).max(axis=1, keepdims=True)
+    assert np.max(np.abs(x - ref.x) / scale) < 1e-8
