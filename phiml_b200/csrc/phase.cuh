@@ -16,6 +16,17 @@ __device__ __forceinline__ void static_for(F&& f) {
     static_for_impl(f, std::make_integer_sequence<int, N>{});
 }
 
+// Optional traversal order of a phase kernel.  plane == 0: plain index order.  Otherwise the vector is seen as x-planes of
+// `plane` elements grouped into chunks of `xchunk` planes (the decomposition of the plane-marching stencil kernel that ran
+// just before), and every chunk is walked from its LAST plane to its first, all chunks side by side: the kernel first touches
+// what the stencil kernel touched last (still in the 126 MB L2) and leaves the chunk heads — where the next stencil pass
+// starts — for the end.
+struct PhaseOrder {
+    int64_t plane;
+    int xchunk, chunks;
+    int64_t planes;
+};
+
 struct Ctx {
     Sys* sys;
     Glob* glob;
@@ -30,7 +41,7 @@ struct Ctx {
 //   Scal load(b)       per-system scalars, read once per thread
 //   elem(e, acc, sc)   one element: e[a] in/out
 template <typename T, class P, int V>
-__global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, int64_t off) {
+__global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, int64_t off, PhaseOrder ord) {
     if (p.idle()) return;
     const int b = blockIdx.y;
     constexpr int ND = AccSize<P>::N;
@@ -44,50 +55,82 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
 #pragma unroll
         for (int a = 0; a < NA; ++a) base[a] = (T*)p.v[a] + off + (((P::SHARED >> a) & 1u) ? (int64_t)0 : (int64_t)b * ld);
         using VT = typename Vec<T>::type;
-        for (int64_t i = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * V; i < n; i += (int64_t)gridDim.x * kBlock * V) {
-            alignas(16) T e[NA][V];
-            static_for<NA>([&](auto A) {
-                constexpr int a = decltype(A)::value;
-                if constexpr (((P::RMASK >> a) & 1u) != 0) {
-                    if constexpr (V == 1) e[a][0] = base[a][i];
-                    else *reinterpret_cast<VT*>(&e[a][0]) = *reinterpret_cast<const VT*>(base[a] + i);
-                } else {
+        const int64_t n_log = ord.plane == 0 ? n : (int64_t)ord.chunks * ord.xchunk * ord.plane;
+        const int64_t per_step = (int64_t)ord.chunks * ord.plane;
+        // two groups of V elements per trip: all loads of both groups are issued before the first use (bytes in flight),
+        // the groups are then processed in index order, so the per-thread summation order is that of the plain loop
+        constexpr int U = 1;   // groups per trip (2 measured slower: registers 32 -> 40 cost a resident CTA per SM)
+        const int64_t stride = (int64_t)gridDim.x * kBlock * V;
+        for (int64_t j0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * V; j0 < n_log; j0 += U * stride) {
+            int64_t idx[U];
+            bool ok[U];
 #pragma unroll
-                    for (int l = 0; l < V; ++l) e[a][l] = T(0);
+            for (int u = 0; u < U; ++u) {
+                const int64_t j = j0 + u * stride;
+                ok[u] = j < n_log;
+                idx[u] = j;
+                if (ord.plane != 0 && ok[u]) {
+                    const int64_t tau = j / per_step, rem = j - tau * per_step;
+                    const int64_t c = rem / ord.plane, o = rem - c * ord.plane;
+                    const int64_t x0 = c * ord.xchunk, x1 = min(ord.planes, x0 + ord.xchunk);
+                    const int64_t px = x1 - 1 - tau;
+                    ok[u] = px >= x0;
+                    idx[u] = px * ord.plane + o;
                 }
-            });
-#pragma unroll
-            for (int l = 0; l < V; ++l) {
-                T el[NA];
-#pragma unroll
-                for (int a = 0; a < NA; ++a) el[a] = e[a][l];
-                p.elem(el, acc, sc);
-#pragma unroll
-                for (int a = 0; a < NA; ++a) e[a][l] = el[a];
             }
-            static_for<NA>([&](auto A) {
-                constexpr int a = decltype(A)::value;
-                if constexpr (((P::WMASK >> a) & 1u) != 0) {
-                    if constexpr (V == 1) base[a][i] = e[a][0];
-                    else *reinterpret_cast<VT*>(base[a] + i) = *reinterpret_cast<const VT*>(&e[a][0]);
+            alignas(16) T e[U][NA][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                static_for<NA>([&](auto A) {
+                    constexpr int a = decltype(A)::value;
+                    if constexpr (((P::RMASK >> a) & 1u) != 0) {
+                        if (ok[u]) {
+                            if constexpr (V == 1) e[u][a][0] = base[a][idx[u]];
+                            else *reinterpret_cast<VT*>(&e[u][a][0]) = *reinterpret_cast<const VT*>(base[a] + idx[u]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int l = 0; l < V; ++l) e[u][a][l] = T(0);
+                    }
+                });
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+#pragma unroll
+                for (int l = 0; l < V; ++l) {
+                    T el[NA];
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) el[a] = e[u][a][l];
+                    p.elem(el, acc, sc);
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) e[u][a][l] = el[a];
                 }
-            });
+                static_for<NA>([&](auto A) {
+                    constexpr int a = decltype(A)::value;
+                    if constexpr (((P::WMASK >> a) & 1u) != 0) {
+                        if constexpr (V == 1) base[a][idx[u]] = e[u][a][0];
+                        else *reinterpret_cast<VT*>(base[a] + idx[u]) = *reinterpret_cast<const VT*>(&e[u][a][0]);
+                    }
+                });
+            }
         }
     }
     epilogue_tail(p, acc, b, blockIdx.x, gridDim.x);
 }
 
 template <typename T, class P>
-int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0) {
+int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0, PhaseOrder ord = PhaseOrder{0, 0, 0, 0}) {
     constexpr int V = Vec<T>::N;
     bool aligned = (n % V == 0) && (ld % V == 0) && (off % V == 0);
     for (int a = 0; a < P::NA; ++a) aligned = aligned && (((uintptr_t)p.v[a]) % 16 == 0);
+    if (ord.plane % V != 0) ord.plane = 0;
     if (aligned) {
         dim3 grid((unsigned)grid_x((n / V + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, V>)), (unsigned)batch);
-        PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld, off);
+        PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld, off, ord);
     } else {
         dim3 grid((unsigned)grid_x((n + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, 1>)), (unsigned)batch);
-        PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld, off);
+        PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld, off, PhaseOrder{0, 0, 0, 0});
     }
     return PHB200_OK;
 }

@@ -652,6 +652,7 @@ struct phb200_solver {
     // TMA descriptors of r and the two direction buffers (fused stencil CG); valid for the vectors bound by start()
     CUtensorMap tm_r, tm_a, tm_b;
     int tma_ok;
+    int tma_occ;               // resident CTAs per SM of the TMA stencil kernel (decides its x-chunking)
     // slab / multi-GPU mode: kernels store local sums in `totals`, the host all-reduces, dist_step() finalises
     double* totals;            // device, caller-owned (batch x kMaxDots doubles); non-null = distributed mode
     const void* rtol;
@@ -929,10 +930,32 @@ struct Run {
         prof_end();
         return r;
     }
+    // the residual half walks the chunks of the stencil kernel backwards (PhaseOrder): L2 reuse of q and r
+    PhaseOrder resid_order() {
+        PhaseOrder o{0, 0, 0, 0};
+        static int mode = -1;
+        if (mode < 0) { const char* e = getenv("PHB200_PHASE_ORDER"); mode = (e && e[0] == '1') ? 1 : 0; }   // off by default: measured neutral without L2 eviction hints
+        if (!mode || !s->tma_ok) return o;
+        dim3 grid;
+        int xchunk;
+        star_grid(s->A->star, batch, s->tma_occ > 0 ? s->tma_occ : 1, grid, xchunk);
+        const StarDesc& sd = s->A->star;
+        o.plane = sd.ny * sd.nz;
+        o.xchunk = xchunk;
+        o.planes = sd.xe - sd.xb;
+        o.chunks = (int)((o.planes + xchunk - 1) / xchunk);
+        return o;
+    }
+    template <class P> int phase_ordered(const P& p, const PhaseOrder& ord) {
+        prof_begin();
+        int r = launch_phase<T, P>(p, s->n_act, ld, batch, st, s->off, ord);
+        prof_end();
+        return r;
+    }
     template <int PRE>
     int pass_cg_fused_t(T* X, T* R) {
         PHB_TRY(fused_first<PRE>(X, R));
-        return phase(make_resid<PRE>(R));
+        return phase_ordered(make_resid<PRE>(R), resid_order());
     }
     int fused_pre() const { return s->pre == PHB200_PRE_NONE ? 0 : (s->M->is_const ? 3 : 1); }
     // host-driven halves for the multi-GPU slab mode: all-reduce of s->totals between the steps (multi_gpu.py)
@@ -946,7 +969,7 @@ struct Run {
                 return pre == 0 ? fused_first<0>(X, R) : fused_first<3>(X, R);
             case 1:   // alpha from the reduced d.q, then the residual half (local r.s -> totals)
                 PHB_TRY(finalize_only(make_dq()));
-                return pre == 0 ? phase(make_resid<0>(R)) : phase(make_resid<3>(R));
+                return pre == 0 ? phase_ordered(make_resid<0>(R), resid_order()) : phase_ordered(make_resid<3>(R), resid_order());
             case 2:   // beta, delta, progress check from the reduced r.s
                 s->passes += 1;
                 return pre == 0 ? finalize_only(make_resid<0>(R)) : finalize_only(make_resid<3>(R));
@@ -979,6 +1002,7 @@ struct Run {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
             occ = v;
         }
+        s->tma_occ = occ;
         dim3 grid;
         int xchunk;
         star_grid(s->A->star, batch, occ, grid, xchunk);
