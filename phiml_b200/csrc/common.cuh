@@ -54,6 +54,30 @@ bool debug_sync();
         }                                                                                       \
     } while (0)
 
+// Launch with programmatic dependent launch (PDL): the grid may become resident while the previous kernel of the stream is
+// still draining; the kernel orders itself behind it with griddepcontrol.wait (pdl_wait) before touching its results.
+bool pdl_enabled();
+#define PHB_LAUNCH_PDL(kernel, grid, block, smem, strm, ...)                                  \
+    do {                                                                                        \
+        cudaLaunchConfig_t _cfg = {};                                                           \
+        _cfg.gridDim = (grid);                                                                  \
+        _cfg.blockDim = (block);                                                                \
+        _cfg.dynamicSmemBytes = (smem);                                                         \
+        _cfg.stream = (strm);                                                                   \
+        cudaLaunchAttribute _at[1];                                                             \
+        _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                         \
+        _at[0].val.programmaticStreamSerializationAllowed = 1;                                  \
+        _cfg.attrs = _at;                                                                       \
+        _cfg.numAttrs = phb::pdl_enabled() ? 1 : 0;                                             \
+        cudaError_t _e = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                        \
+        phb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        if (_e == cudaSuccess && phb::debug_sync()) _e = cudaStreamSynchronize(strm);           \
+        if (_e != cudaSuccess) {                                                                \
+            phb::set_error("kernel %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PHB200_ERR_CUDA;                                                             \
+        }                                                                                       \
+    } while (0)
+
 constexpr int kSMs = 148;          // B200
 constexpr int kBlock = 256;        // threads per CTA for all streaming kernels
 constexpr int kMaxDots = 4;        // fused dot products per kernel
@@ -231,5 +255,12 @@ __device__ __forceinline__ void progress_check(Sys* sys, Glob* g, int batch, boo
 }
 
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+// PDL: wait until every kernel launched before this one on the stream has completed and its writes are visible (a no-op
+// for an ordinary launch); then let the NEXT kernel of the stream start getting resident.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 }  // namespace phb

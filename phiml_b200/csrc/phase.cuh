@@ -42,6 +42,7 @@ struct Ctx {
 //   elem(e, acc, sc)   one element: e[a] in/out
 template <typename T, class P, int V>
 __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, int64_t off, PhaseOrder ord) {
+    pdl_wait();
     if (p.idle()) return;
     const int b = blockIdx.y;
     constexpr int ND = AccSize<P>::N;
@@ -120,14 +121,15 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
 }
 
 template <typename T, class P>
-int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0, PhaseOrder ord = PhaseOrder{0, 0, 0, 0}) {
+int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0, PhaseOrder ord = PhaseOrder{0, 0, 0, 0}, bool pdl = false) {
     constexpr int V = Vec<T>::N;
     bool aligned = (n % V == 0) && (ld % V == 0) && (off % V == 0);
     for (int a = 0; a < P::NA; ++a) aligned = aligned && (((uintptr_t)p.v[a]) % 16 == 0);
     if (ord.plane % V != 0) ord.plane = 0;
     if (aligned) {
         dim3 grid((unsigned)grid_x((n / V + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, V>)), (unsigned)batch);
-        PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld, off, ord);
+        if (pdl) PHB_LAUNCH_PDL((k_phase<T, P, V>), grid, dim3(kBlock), 0, stream, p, n, ld, off, ord);
+        else PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld, off, ord);
     } else {
         dim3 grid((unsigned)grid_x((n + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, 1>)), (unsigned)batch);
         PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld, off, PhaseOrder{0, 0, 0, 0});

@@ -948,7 +948,7 @@ struct Run {
     }
     template <class P> int phase_ordered(const P& p, const PhaseOrder& ord) {
         prof_begin();
-        int r = launch_phase<T, P>(p, s->n_act, ld, batch, st, s->off, ord);
+        int r = launch_phase<T, P>(p, s->n_act, ld, batch, st, s->off, ord, true);
         prof_end();
         return r;
     }
@@ -1006,7 +1006,7 @@ struct Run {
         dim3 grid;
         int xchunk;
         star_grid(s->A->star, batch, occ, grid, xchunk);
-        PHB_LAUNCH(kernel, grid, kBlock, smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, e);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, e);
         return PHB200_OK;
     }
     int pass_cg_fused(T* X, T* R) {

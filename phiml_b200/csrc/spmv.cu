@@ -21,6 +21,15 @@ bool debug_sync() {
     return v == 1;
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PHB200_PDL");   // off by default: measured 6 % SLOWER on the 2-kernel CG iteration (256^3)
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -89,7 +89,6 @@ template <typename T, int PRE, class Epi>
 __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_a,
                                                         const __grid_constant__ CUtensorMap tm_b, StarDesc st, T* __restrict__ X, T* buf_a, T* buf_b,
                                                         T* __restrict__ Q, T cinv, int64_t ld, int xchunk, Epi epi) {
-    if (epi.idle()) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TB = tile_bytes<T>();
     constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
@@ -108,6 +107,8 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();                    // everything above overlaps the tail of the previous kernel (PDL launch)
+    if (epi.idle()) return;
 
     if (!epi.skip(b)) {
         const bool odd = (epi.glob->pass & 1) != 0;
