@@ -528,13 +528,14 @@ static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     a.B = B;
     a.X = X;
     const int64_t need = batch * a.ni * a.nj;
-    if (need > p->tr_flag_cap) {
+    const int64_t n_flags = need * kScT;      // the dataflow kernel keeps one counter per tile row, the barrier kernel uses the first of each tile... of its own layout
+    if (n_flags > p->tr_flag_cap) {
         PHB_CUDA(cudaStreamSynchronize(stream));
         if (p->tr_flags) cudaFree(p->tr_flags);
         p->tr_flags = nullptr;
-        PHB_CUDA(cudaMalloc(&p->tr_flags, sizeof(unsigned long long) * need));
-        PHB_CUDA(cudaMemsetAsync(p->tr_flags, 0, sizeof(unsigned long long) * need, stream));
-        p->tr_flag_cap = need;
+        PHB_CUDA(cudaMalloc(&p->tr_flags, sizeof(unsigned long long) * n_flags));
+        PHB_CUDA(cudaMemsetAsync(p->tr_flags, 0, sizeof(unsigned long long) * n_flags, stream));
+        p->tr_flag_cap = n_flags;
         p->tr_epoch = 0;
     }
     a.flags = p->tr_flags;
@@ -543,9 +544,22 @@ static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     a.ticket = p->tr_ticket;
     a.n_ctas = (unsigned)need;
     a.order = p->sc_order;
+    a.dbg = nullptr;
+    if (const char* e = getenv("PHB200_TRSV_DBG")) a.dbg = (unsigned long long*)strtoull(e, nullptr, 0);
     a.cx = LOWER ? st.cxm : st.cxp;
     a.cy = LOWER ? st.cym : st.cyp;
     a.cz = LOWER ? st.czm : st.czp;
+    if (p->star_mode == 3) {
+        auto kernel = k_star_trsv_flow<T, LOWER>;
+        constexpr size_t smem = flow_smem_bytes<T>();
+        static bool attr = false;
+        if (!attr) {
+            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        PHB_LAUNCH(kernel, a.n_ctas, kScT * 32, smem, stream, a);
+        return PHB200_OK;
+    }
     auto kernel = k_star_trsv_scan<T, LOWER>;
     constexpr size_t smem = scan_smem_bytes<T>();
     static bool attr = false;
@@ -593,8 +607,8 @@ static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t
     PHB_CUDA(cudaFreeAsync(d_ok, stream));
     if (ok) {
         p->star = st;
-        p->star_mode = (e && strcmp(e, "skew") == 0) ? 1 : 2;
-        if (p->star_mode == 2) PHB_TRY(scan_order_setup(p, st, stream));
+        p->star_mode = (e && strcmp(e, "skew") == 0) ? 1 : ((e && strcmp(e, "flow") == 0) ? 3 : 2);
+        if (p->star_mode >= 2) PHB_TRY(scan_order_setup(p, st, stream));
     } else {
         cudaFree(p->rd);
         p->rd = nullptr;
@@ -619,7 +633,7 @@ int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int6
     if (p->kind == PHB200_PRE_ILU) {
         if (p->star_mode) {
             phb200_precond* q = const_cast<phb200_precond*>(p);   // counters / epoch are bookkeeping
-            if (p->star_mode == 2) {
+            if (p->star_mode >= 2) {
                 if (p->dtype == PHB200_F32) return scan_trsv_launch<float, true>(q, (const float*)in, (float*)out, batch, ld, stream);
                 return scan_trsv_launch<double, true>(q, (const double*)in, (double*)out, batch, ld, stream);
             }
@@ -641,7 +655,7 @@ int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp,
         PHB_TRY(precond_apply_inv_l(p, in, out, batch, ld, stream));
         if (p->star_mode) {
             phb200_precond* q = const_cast<phb200_precond*>(p);
-            if (p->star_mode == 2) {
+            if (p->star_mode >= 2) {
                 if (p->dtype == PHB200_F32) return scan_trsv_launch<float, false>(q, (const float*)out, (float*)out, batch, ld, stream);
                 return scan_trsv_launch<double, false>(q, (const double*)out, (double*)out, batch, ld, stream);
             }

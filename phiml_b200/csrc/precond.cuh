@@ -32,7 +32,7 @@ struct phb200_precond {
     phb200_trsv_plan* plan_l;
     phb200_trsv_plan* plan_u;
     // star-stencil wavefront solves (star_trsv.cuh): reciprocal pivots + block counters; star_mode 0 = CSR level solves,
-    // 1 = skewed warps, 2 = row scans
+    // 1 = skewed warps, 2 = row scans with CTA barriers (default), 3 = row scans as a warp dataflow
     int star_mode;
     int32_t* sc_order;                 // device, owned: tiles of the row-scan kernel in dependency (anti-diagonal) order
     phb::StarDesc star;

@@ -391,6 +391,7 @@ struct ScanTrsvArgs {
     unsigned long long epoch_base;
     unsigned* ticket;
     unsigned n_ctas;
+    unsigned long long* dbg;   // optional timestamps (globaltimer ns) of one warp: [tile][chunk][6]
     const int32_t* order;   // [ni*nj] tile ids (i * nj + j) sorted by anti-diagonal: a tile's dependencies come first
     double cx, cy, cz;
 };
@@ -540,6 +541,208 @@ __global__ void __launch_bounds__(kScT * 32) k_star_trsv_scan(const ScanTrsvArgs
             __threadfence();
             st_release_u64(my_flag, target0 + (unsigned long long)c + 1ull);
         }
+    }
+    cp_async_wait<0>();
+}
+
+
+// ====================================================================================================================
+// Third formulation: ROW SCANS AS A DATAFLOW.  Same tiles (8 planes x 8 rows), same warp scan per row chunk, but no CTA
+// barriers: warp w owns ROW w of the tile and walks its 8 planes chunk after chunk.  The x neighbour of a task is the warp's
+// own previous result (a register), the y neighbour comes from warp w-1 through a ring in shared memory guarded by a
+// per-warp task counter, rhs / rd tiles are staged per warp (cp.async, two chunks ahead).  The 8 warps form a systolic
+// pipeline (warp w one task behind warp w-1) that runs seamlessly from chunk to chunk.  Across tiles every warp publishes
+// "my row has finished chunk c" (one release per 8 tasks); warp w of the +x tile waits for warp w, warp 0 of the +y tile
+// waits for warp 7.
+// ====================================================================================================================
+constexpr int kFlRing = 16;        // y hand-over ring (tasks) per warp
+constexpr int kFlStages = 3;
+
+template <typename T> constexpr size_t flow_smem_bytes() {
+    return sizeof(T) * ((size_t)kScT * kFlStages * 2 * kScT * kScZ + (size_t)kScT * kFlRing * kScZ) + 64;
+}
+
+template <typename T, bool LOWER>
+__global__ void __launch_bounds__(kScT * 32) k_star_trsv_flow(const ScanTrsvArgs a) {
+    constexpr int TT = kScT, ZC = kScZ, V = 16 / (int)sizeof(T), GPR = ZC / V, NST = kFlStages, RING = kFlRing;
+    extern __shared__ __align__(16) unsigned char flow_smem[];
+    __shared__ unsigned s_ticket;
+    __shared__ volatile int s_done[TT];            // tasks finished by warp w (monotone over the whole launch)
+    T* tiles = reinterpret_cast<T*>(flow_smem);                  // [TT warps][NST][2][TT planes][ZC]
+    T* ringy = tiles + (size_t)TT * NST * 2 * TT * ZC;           // [TT warps][RING][ZC]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    if (tid < TT) s_done[tid] = 0;
+    __syncthreads();
+    const unsigned cta = s_ticket;
+    if (tid == 0 && cta == a.n_ctas - 1) *a.ticket = 0u;
+    const int n_tiles = a.ni * a.nj;
+    const int b = (int)(cta / (unsigned)n_tiles);
+    const int tile = a.order[cta % (unsigned)n_tiles];
+    const int ti = tile / a.nj, tj = tile % a.nj;
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int x0 = ti * TT, y0 = tj * TT;
+    const int npl = min(TT, nx - x0);
+    const int gy = y0 + warp;                      // logical row of this warp
+    if (gy >= ny) return;                          // rows beyond the domain: nobody depends on them
+    const bool last_row = (warp == TT - 1) || (gy + 1 >= ny);
+    const T cx = (T)a.cx, cy = (T)a.cy, cz = (T)a.cz;
+    const T* __restrict__ rd = (const T*)a.rd;
+    const T* Bb = (const T*)a.B + (int64_t)b * a.ld;
+    T* Xb = (T*)a.X + (int64_t)b * a.ld;
+    // one counter per tile ROW: [batch][ni][nj][TT]
+    unsigned long long* my_flags = a.flags + (((int64_t)b * a.ni + ti) * a.nj + tj) * TT;
+    const unsigned long long* flag_x = ti > 0 ? my_flags - (int64_t)a.nj * TT + warp : nullptr;                 // same row of the -x tile
+    const unsigned long long* flag_y = (tj > 0 && warp == 0) ? my_flags - TT + (TT - 1) : nullptr;            // last row of the -y tile
+    auto px = [&](int lx) { return LOWER ? lx : nx - 1 - lx; };
+    auto py = [&](int ly) { return LOWER ? ly : ny - 1 - ly; };
+    auto seg0 = [&](int c) { return LOWER ? c * ZC : nz - (c + 1) * ZC; };
+    const int col = LOWER ? lane : ZC - 1 - lane;
+    T* my_tiles = tiles + (size_t)warp * NST * 2 * TT * ZC;
+    T* my_ring = ringy + (size_t)warp * RING * ZC;
+    const T* up_ring = ringy + (size_t)(warp > 0 ? warp - 1 : 0) * RING * ZC;
+    const int64_t row_off = (int64_t)py(gy) * nz;
+
+    auto issue_chunk = [&](int c) {
+        if (c < a.nch) {
+            const int st = c % NST, z0 = seg0(c);
+#pragma unroll
+            for (int i = 0; i < (TT * GPR) / 32; ++i) {
+                const int k = i * 32 + lane;
+                const int ixl = k / GPR, g = k % GPR;
+                const int zph = z0 + g * V;
+                const bool ok = ixl < npl && zph >= 0 && zph < nz;
+                const int64_t off = ok ? ((int64_t)px(x0 + ixl) * ny * nz + row_off + zph) : 0;
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(my_tiles + ((st * 2 + 0) * TT + ixl) * ZC + g * V);
+                cp_async16(d, Bb + off, ok);
+                cp_async16(d + (uint32_t)(TT * ZC * sizeof(T)), rd + off, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    auto spin_global = [&](const unsigned long long* flag, unsigned long long need) {
+        if (lane == 0) {
+            const long long t0 = clock64();
+            unsigned ns = 20;
+            while (ld_poll_u64(flag) < need) {
+                __nanosleep(ns);
+                if (ns < 160) ns *= 2;
+                if (clock64() - t0 > 6000000000ll) __trap();
+            }
+        }
+        __syncwarp();
+    };
+    auto spin_shared = [&](int w, int need) {
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while (s_done[w] < need) {
+                __nanosleep(20);
+                if (clock64() - t0 > 6000000000ll) __trap();
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+    };
+
+    issue_chunk(0);
+    issue_chunk(1);
+    const unsigned long long target0 = a.epoch_base;
+    T cprev[TT];                                   // this lane's value of the previous chunk, per plane (carry source)
+#pragma unroll
+    for (int i = 0; i < TT; ++i) cprev[i] = T(0);
+    int task = 0;                                  // tasks finished by this warp
+    for (int c = 0; c < a.nch; ++c) {
+        const int zl = c * ZC + lane;
+        const bool z_ok = zl < nz;
+        const int zph = LOWER ? zl : nz - 1 - zl;
+        const int last_prev = ZC - 1;              // previous chunks are always full
+        auto stamp = [&](int k) {
+            if (a.dbg && warp == 0 && lane == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                a.dbg[((size_t)tile * a.nch + c) * 6 + k] = t;
+            }
+        };
+        stamp(0);
+        issue_chunk(c + 2);          // its stage held chunk c-1, which this warp has finished
+        // ---- cross-tile dependencies of this chunk
+        const unsigned long long need = target0 + (unsigned long long)c + 1ull;
+        if (flag_x) spin_global(flag_x, need);
+        if (flag_y) spin_global(flag_y, need);
+        stamp(1);
+        if (flag_x || flag_y) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        stamp(2);
+        auto handed = [&](int gx_, int gy_) -> T {
+            T v = T(0);
+            if (z_ok) {
+                const int64_t off = ((int64_t)px(gx_) * ny + py(gy_)) * nz + zph;
+                v = __ldcg(Xb + off);
+                if (LOWER) v = v * __ldcg(rd + off);
+            }
+            return v;
+        };
+        T xprev = ti > 0 ? handed(x0 - 1, gy) : T(0);          // plane x0-1, own row
+        T yb[TT];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) yb[i] = (flag_y && i < npl) ? handed(x0 + i, y0 - 1) : T(0);
+        cp_async_wait<2>();          // chunks <= c have landed (c+1, c+2 may be in flight)
+        __syncwarp();
+        if (a.dbg && warp == 0 && lane == 0) { volatile T sink = xprev + yb[0]; (void)sink; }
+        stamp(3);
+        const int st = c % NST;
+#pragma unroll
+        for (int ixl = 0; ixl < TT; ++ixl) {
+            if (ixl < npl) {
+                const T bv = my_tiles[((st * 2 + 0) * TT + ixl) * ZC + col], rv = my_tiles[((st * 2 + 1) * TT + ixl) * ZC + col];
+                // the B half of the scan depends on the pivots only: done before waiting for the y neighbour
+                T Bs[5];
+                T Bc = z_ok ? -cz * rv : T(0);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    Bs[k] = Bc;
+                    const T Bp = __shfl_up_sync(0xffffffffu, Bc, 1 << k);
+                    if (lane >= (1 << k)) Bc = Bc * Bp;
+                }
+                const T carry = c == 0 ? T(0) : __shfl_sync(0xffffffffu, cprev[ixl], last_prev);
+                const T g0 = fma_t<T>(-cx, xprev, bv);
+                T wy = yb[ixl];
+                if (warp > 0) {
+                    spin_shared(warp - 1, task + 1);
+                    wy = up_ring[(task % RING) * ZC + col];
+                }
+                const T g = fma_t<T>(-cy, wy, g0);
+                T A = z_ok ? g * rv : T(0);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const T Ap = __shfl_up_sync(0xffffffffu, A, 1 << k);
+                    if (lane >= (1 << k)) A = fma_t<T>(Bs[k], Ap, A);
+                }
+                const T w = fma_t<T>(Bc, carry, A);
+                T out = w;
+                if (LOWER) {
+                    T wp = __shfl_up_sync(0xffffffffu, w, 1);
+                    if (lane == 0) wp = carry;
+                    out = fma_t<T>(-cz, wp, g);
+                }
+                if (z_ok) Xb[(int64_t)px(x0 + ixl) * ny * nz + row_off + zph] = out;
+                if (!last_row) {
+                    // the ring slot is free once warp+1 has consumed task - RING
+                    if (task >= RING) spin_shared(warp + 1, task - RING + 1);
+                    my_ring[(task % RING) * ZC + col] = w;
+                    __threadfence_block();
+                    __syncwarp();
+                }
+                task += 1;
+                if (lane == 0) s_done[warp] = task;
+                xprev = w;
+                cprev[ixl] = w;
+            }
+        }
+        // ---- publish "row `warp` of this tile has finished chunk c"
+        __syncwarp();
+        stamp(4);
+        if (lane == 0) st_release_u64(my_flags + warp, need);    // release orders the warp's stores (via __syncwarp) before the counter
+        stamp(5);
     }
     cp_async_wait<0>();
 }
