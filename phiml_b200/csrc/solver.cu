@@ -584,6 +584,88 @@ struct BiEpi : FBase {
     __device__ void finalize_all() const {}
 };
 
+// K independent updates in one pass (BiCGstab(L) inner loops), same arithmetic as K separate Lin2 launches:
+//   MODE 0: t_i = s_i + c t_i      (uh[i] = rh[i] - beta uh[i])
+//   MODE 1: t_i = t_i + c s_i      (rh[i] = rh[i] - alpha uh[i+1]);  WITH_X adds x = x + cx u  (x += alpha uh[0])
+// vectors: t_0, s_0, t_1, s_1, ... [, x, u]
+template <typename T, int K, int MODE, bool WITH_X>
+struct LinMulti : FBase {
+    static constexpr int NA = 2 * K + (WITH_X ? 2 : 0);
+    static constexpr unsigned RMASK = (1u << NA) - 1u;
+    static constexpr unsigned WMASK = (K >= 1 ? 1u : 0u) | (K >= 2 ? 4u : 0u) | (K >= 3 ? 16u : 0u) | (WITH_X ? (1u << (2 * K)) : 0u);
+    static constexpr unsigned SHARED = 0u;
+    static constexpr int ND = 0;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    int slot, sign, xslot, xsign;
+    struct Scal { T c, cx; };
+    __device__ Scal load(int b) const { return Scal{(T)(sign * sys[b].s[slot]), WITH_X ? (T)(xsign * sys[b].s[xslot]) : T(0)}; }
+    __device__ void elem(T (&e)[NA], double (&)[1], const Scal& sc) const {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if (MODE == 0) e[2 * i] = add_rn(e[2 * i + 1], mul_rn(sc.c, e[2 * i]));
+            else e[2 * i] = add_rn(e[2 * i], mul_rn(sc.c, e[2 * i + 1]));
+        }
+        if (WITH_X) e[2 * K] = add_rn(e[2 * K], mul_rn(sc.cx, e[2 * K + 1]));
+    }
+    __device__ void finalize(int, const double (&)[1]) const {}
+    __device__ void finalize_all() const {}
+};
+
+// t = t + c s, then the two dot products of the BI_SIGMA step on the updated t:  t.t and p.t   (vectors t, s, p)
+template <typename T>
+struct LinSigma : FBase {
+    static constexpr int NA = 3;
+    static constexpr unsigned RMASK = 0b111u, WMASK = 0b001u, SHARED = 0u;
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    int slot, sign, j, L;
+    struct Scal { T c; };
+    __device__ Scal load(int b) const { return Scal{(T)(sign * sys[b].s[slot])}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[2], const Scal& sc) const {
+        e[0] = add_rn(e[0], mul_rn(sc.c, e[1]));
+        acc[0] += (double)mul_rn(e[0], e[0]);
+        acc[1] += (double)mul_rn(e[2], e[0]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const { bi_scalar_step<T>(sys[b], BI_SIGMA, j, 0, L, tot); }
+    __device__ void finalize_all() const {}
+};
+
+// Last block of a BiCGstab(2) pass in one sweep (six Lin2 launches + the final dot of the unfused form, same order of
+// operations per element): vectors x, rh0, rh1, rh2, uh0, uh1, uh2
+template <typename T>
+struct BiFinal2 : FBase {
+    static constexpr int NA = 7;
+    static constexpr unsigned RMASK = 0b1111111u, WMASK = 0b0010011u, SHARED = 0u;
+    static constexpr int ND = 1;
+    static constexpr bool GLOBAL = true;
+    const void* v[NA];
+    int rules;
+    struct Scal { T g1, gp2, g2, gpp1, gp1; };
+    __device__ Scal load(int b) const {
+        const double* q = sys[b].s;
+        return Scal{(T)q[S_GAM + 1], (T)(-q[S_GAMP + 2]), (T)(-q[S_GAM + 2]), (T)q[S_GAMPP + 1], (T)(-q[S_GAMP + 1])};
+    }
+    __device__ void elem(T (&e)[NA], double (&acc)[1], const Scal& sc) const {
+        e[0] = add_rn(e[0], mul_rn(sc.g1, e[1]));        // x   += gam[1]    rh0
+        e[1] = add_rn(e[1], mul_rn(sc.gp2, e[3]));       // rh0 -= gam_p[2]  rh2
+        e[4] = add_rn(e[4], mul_rn(sc.g2, e[6]));        // uh0 -= gam[2]    uh2
+        e[4] = add_rn(e[4], mul_rn(-sc.g1, e[5]));       // uh0 -= gam[1]    uh1
+        e[0] = add_rn(e[0], mul_rn(sc.gpp1, e[2]));      // x   += gam_pp[1] rh1
+        e[1] = add_rn(e[1], mul_rn(sc.gp1, e[2]));       // rh0 -= gam_p[1]  rh1
+        acc[0] += (double)mul_rn(e[1], e[1]);
+    }
+    __device__ void finalize(int b, const double (&tot)[1]) const {
+        double t2[2] = {tot[0], tot[0]};
+        bi_scalar_step<T>(sys[b], BI_FINAL, 0, 0, 2, t2);
+    }
+    __device__ void finalize_all() const {
+        check_all<T>(*this, rules);
+        if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+    }
+};
+
 // multi-GPU batch sharding: install the batch-wide minimum tolerance and repeat the first progress check with it
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_recheck(FBase f, int rules, const double* __restrict__ tol_min, int adaptive) {
@@ -1123,9 +1205,26 @@ struct Run {
         return spmv(d, q, e);
     }
 
+    // fused helpers of the BiCGstab(L) pass (fall back to single Lin2 launches beyond 3 pairs)
+    template <int K, int MODE, bool WITH_X>
+    int lin_multi(T* const* t, T* const* sv, int slot, int sign, T* X, const T* u, int xslot, int xsign) {
+        LinMulti<T, K, MODE, WITH_X> f;
+        fill_base(f, s, false, false);
+        for (int i = 0; i < K; ++i) { f.v[2 * i] = t[i]; f.v[2 * i + 1] = sv[i]; }
+        if (WITH_X) { f.v[2 * K] = X; f.v[2 * K + 1] = u; }
+        f.slot = slot; f.sign = sign; f.xslot = xslot; f.xsign = xsign;
+        return phase(f);
+    }
+    static bool bicg_fused_enabled() {
+        static int v = -1;
+        if (v < 0) { const char* e = getenv("PHB200_BICG_FUSED"); v = (e && e[0] == '0') ? 0 : 1; }
+        return v == 1;
+    }
+
     // BiCGstab(L), L >= 2 (phiml/backend/_linalg.py:158-221).  vec: 0 shadow, 1..L+1 uh[0..L], L+2..2L+1 rh[1..L], 2L+2 pv, 2L+3 tmp
     int pass_bicg_l(T* X, T* R) {
         const int L = s->L;
+        const bool fuse = bicg_fused_enabled();
         const T* shadow = vec(0);
         std::vector<T*> uh(L + 1), rh(L + 1);
         for (int k = 0; k <= L; ++k) uh[k] = vec(1 + k);
@@ -1136,20 +1235,43 @@ struct Run {
         const T* pin = nullptr;
         PHB_TRY(dot2(rh[0], shadow, rh[0], shadow, BI_RHO, 0, 0));
         for (int j = 0; j < L; ++j) {
-            for (int i = 0; i <= j; ++i) PHB_TRY(lin2(uh[i], rh[i], uh[i], S_BETA, -1));
+            // uh[i] = rh[i] - beta uh[i], i <= j
+            if (fuse && j == 0) PHB_TRY((lin_multi<1, 0, false>(&uh[0], &rh[0], S_BETA, -1, nullptr, nullptr, 0, 0)));
+            else if (fuse && j == 1) PHB_TRY((lin_multi<2, 0, false>(&uh[0], &rh[0], S_BETA, -1, nullptr, nullptr, 0, 0)));
+            else if (fuse && j == 2) PHB_TRY((lin_multi<3, 0, false>(&uh[0], &rh[0], S_BETA, -1, nullptr, nullptr, 0, 0)));
+            else for (int i = 0; i <= j; ++i) PHB_TRY(lin2(uh[i], rh[i], uh[i], S_BETA, -1));
             PHB_TRY(apply_pre(uh[j], pv, tmp, &pin));
             PHB_TRY(spmv_dot(pin, uh[j + 1], shadow, nullptr, BI_GAMMA, j));
-            for (int i = 0; i <= j; ++i) PHB_TRY(lin2(rh[i], rh[i], uh[i + 1], S_ALPHA, -1));
+            // rh[i] = rh[i] - alpha uh[i+1], i <= j ; x += alpha uh[0] (independent of the product below: done in the same sweep)
+            if (fuse && j == 0) PHB_TRY((lin_multi<1, 1, true>(&rh[0], &uh[1], S_ALPHA, -1, X, uh[0], S_ALPHA, +1)));
+            else if (fuse && j == 1) PHB_TRY((lin_multi<2, 1, true>(&rh[0], &uh[1], S_ALPHA, -1, X, uh[0], S_ALPHA, +1)));
+            else if (fuse && j == 2) PHB_TRY((lin_multi<3, 1, true>(&rh[0], &uh[1], S_ALPHA, -1, X, uh[0], S_ALPHA, +1)));
+            else for (int i = 0; i <= j; ++i) PHB_TRY(lin2(rh[i], rh[i], uh[i + 1], S_ALPHA, -1));
             PHB_TRY(apply_pre(rh[j], pv, tmp, &pin));
             PHB_TRY(spmv_dot(pin, rh[j + 1], shadow, nullptr, BI_NEXT, j));
-            PHB_TRY(lin2(X, X, uh[0], S_ALPHA, +1));
+            if (!(fuse && j <= 2)) PHB_TRY(lin2(X, X, uh[0], S_ALPHA, +1));
         }
         for (int j = 1; j <= L; ++j) {
             for (int i = 1; i < j; ++i) {
                 PHB_TRY(dot2(rh[j], rh[i], rh[j], rh[i], BI_TAU, j, i));
-                PHB_TRY(lin2(rh[j], rh[j], rh[i], S_TAU + j, -1));
+                if (fuse && i == j - 1) {   // last orthogonalisation step: fused with the sigma / gamma' dots
+                    LinSigma<T> f;
+                    fill_base(f, s, false, false);
+                    f.v[0] = rh[j]; f.v[1] = rh[i]; f.v[2] = rh[0];
+                    f.slot = S_TAU + j; f.sign = -1; f.j = j; f.L = L;
+                    PHB_TRY(phase(f));
+                } else {
+                    PHB_TRY(lin2(rh[j], rh[j], rh[i], S_TAU + j, -1));
+                }
             }
-            PHB_TRY(dot2(rh[j], rh[j], rh[0], rh[j], BI_SIGMA, j, 0));
+            if (!(fuse && j >= 2)) PHB_TRY(dot2(rh[j], rh[j], rh[0], rh[j], BI_SIGMA, j, 0));
+        }
+        if (fuse && L == 2) {
+            BiFinal2<T> f;
+            fill_base(f, s, false, false);
+            f.v[0] = X; f.v[1] = rh[0]; f.v[2] = rh[1]; f.v[3] = rh[2]; f.v[4] = uh[0]; f.v[5] = uh[1]; f.v[6] = uh[2];
+            f.rules = RULES_GENERIC;
+            return phase(f);
         }
         PHB_TRY(lin2(X, X, rh[0], S_GAM + 1, +1));
         PHB_TRY(lin2(rh[0], rh[0], rh[L], S_GAMP + L, -1));
