@@ -199,6 +199,8 @@ def as_matrix(native, detect_stencil=True, grid=None) -> Matrix:
     hit = _CACHE.get(key)
     if hit is not None:
         _CACHE.move_to_end(key)
+        if detect_stencil and hit.kind == 'csr' and (grid is not None or not hit._stencil_checked):
+            hit.detect_stencil(grid)          # cached without recognition (detect_stencil=False) earlier
         return hit
     kind, a, b, v = comps
     if kind == 'coo':
