@@ -69,18 +69,21 @@ def exchange_halo_planes(ext: torch.Tensor, nxl: int, plane: int, rank: int, wor
 # independent systems
 # ----------------------------------------------------------------------------------------------------------------------
 
-def solve_sharded(method: str, lin, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: np.ndarray, pre=None, group=None):
+def solve_sharded(method: str, lin, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: np.ndarray, pre=None, group=None, generic_rules: bool = False):
     """
     Every rank passes ITS shard of the right-hand sides (``shard_bounds`` gives the split).  Returns the local SolveResult.
     Identical to one ``linear_solve`` over the whole batch: the tolerance every system has to reach is the minimum over ALL
-    ranks' systems, exactly as in the single-process reference.
+    ranks' systems, exactly as in the single-process reference.  ``generic_rules`` selects the generic loops of
+    phiml/backend/_linalg.py (what the NumPy backend runs) instead of the torch fast-path rules for un-preconditioned CG.
     """
     from . import solve as host
     from . import _engine as E
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world == 1:
-        return host.linear_solve(method, lin, y_local, x0_local, rtol, atol, max_iter, pre, None)
     code, order, name = _method_code(method, pre, max_iter)
+    if generic_rules and code == E.CG_TORCH:
+        code, name = E.CG, f"Φ-ML CG ({host.BACKEND_NAME}) {host._pre_str(pre)}"
+    if generic_rules and code == E.CG_ADAPTIVE_TORCH:
+        code, name = E.CG_ADAPTIVE, f"Φ-ML CG-adaptive ({host.BACKEND_NAME}) "
     matrix, y, x0, rtol_t, atol_t, max_iter = host._prepare(lin, y_local, x0_local, rtol, atol, max_iter)
     pre = host._device_pre(pre, matrix)
     sm = matrix.stencil if matrix.stencil is not None else matrix
@@ -88,10 +91,12 @@ def solve_sharded(method: str, lin, y_local: torch.Tensor, x0_local: torch.Tenso
     mi = torch.as_tensor(np.broadcast_to(np.asarray(max_iter)[-1, :], (nb,)).astype(np.int32).copy(), device=y.device)
     solver = host.DeviceSolver(sm, pre, code, order, nb)
     solver.start(y, x0, rtol_t, atol_t, mi)
-    tol = solver.get_tol_min()                     # local minimum of max(rtol^2 * norm, atol^2)
-    dist.all_reduce(tol, op=dist.ReduceOp.MIN, group=group)
-    solver.set_tol_min(tol)                        # re-runs the first progress check with the global minimum
+    if world > 1:
+        tol = solver.get_tol_min()                 # local minimum of max(rtol^2 * norm, atol^2)
+        dist.all_reduce(tol, op=dist.ReduceOp.MIN, group=group)
+        solver.set_tol_min(tol)                    # re-runs the first progress check with the global minimum
     solver.run(int(np.max(max_iter)))
+    host.LAST_RUN['resident'] = solver.resident_used
     its, fev, conv, div = solver.result()
     return host.SolveResult(name, solver.x, solver.r, its, fev, conv, div, [""] * nb)
 
