@@ -1075,7 +1075,13 @@ struct Run {
     }
     template <int PRE>
     int launch_tma(T* X, T* q, T cinv, const CgDq<T>& e) {
-        auto kernel = k_star_cg_tma<T, PRE, CgDq<T>>;
+        const StarDesc& sd = s->A->star;
+        const bool unit = sd.cxm == -1.0 && sd.cxp == -1.0 && sd.cym == -1.0 && sd.cyp == -1.0 && sd.czm == -1.0 && sd.czp == -1.0;
+        return unit ? launch_tma_t<PRE, true>(X, q, cinv, e) : launch_tma_t<PRE, false>(X, q, cinv, e);
+    }
+    template <int PRE, bool UNIT>
+    int launch_tma_t(T* X, T* q, T cinv, const CgDq<T>& e) {
+        auto kernel = k_star_cg_tma<T, PRE, CgDq<T>, UNIT>;
         constexpr int smem = star_tma_smem<T>();
         static int occ = 0;
         if (occ == 0) {

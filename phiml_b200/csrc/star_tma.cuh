@@ -85,7 +85,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 
 // PRE: 0 none, 3 Jacobi with constant inverse diagonal
-template <typename T, int PRE, class Epi>
+template <typename T, int PRE, class Epi, bool UNIT>
 __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_a,
                                                         const __grid_constant__ CUtensorMap tm_b, StarDesc st, T* __restrict__ X, T* buf_a, T* buf_b,
                                                         T* __restrict__ Q, T cinv, int64_t ld, int xchunk, Epi epi) {
@@ -93,9 +93,6 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
     constexpr int TB = tile_bytes<T>();
     constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    auto tile_r = [&](int stg) { return reinterpret_cast<T(*)[SROW]>(base + (size_t)(2 * stg) * TB); };
-    auto tile_d = [&](int stg) { return reinterpret_cast<T(*)[SROW]>(base + (size_t)(2 * stg + 1) * TB); };
-    auto plane = [&](int k) { return reinterpret_cast<T(*)[SROW]>(base + (size_t)(2 * kStages + (k & 3)) * TB); };
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)(2 * kStages + 4) * TB);
 
     const int b = blockIdx.y;
@@ -122,12 +119,21 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         const int chunks = (int)((st.xe - st.xb + xchunk - 1) / xchunk);
         const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
-        uint32_t g = 0;   // running index of issued/consumed planes -> stage and mbarrier phase
 
         auto dir = [&](T rv, T dv) {
             const T s = PRE == 3 ? mul_rn(rv, cinv) : rv;
             return add_rn(s, mul_rn(beta, dv));
         };
+
+        // running state instead of per-plane index arithmetic: TMA stage + its mbarrier phase bits, byte offsets of the
+        // tile pair and of the three live planes of the d_new ring, element offset of the current plane in global memory
+        unsigned char* const tiles0 = base;
+        unsigned char* const planes0 = base + (size_t)(2 * kStages) * TB;
+        const int64_t pstride = ny * nz;
+        const int c = 4 + 4 * lane;            // interior column of this lane in a shared-memory row
+        const int sr = warp + 1;               // interior row of this warp
+        uint32_t stg = 0, phase_bits = 0;      // next stage to be consumed; bit s = parity the next wait on stage s expects
+        uint32_t issue_stg = 0;                // next stage to be filled (thread 0)
 
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
             const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
@@ -136,45 +142,48 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
             const int jy = y0 + warp, jz = z0 + 4 * lane;
             const bool mine = jy < ny && jz < nz;
             const int P = (int)(x1 - x0) + 2;   // planes x0-1 .. x1
+            const bool halo_lo = st.store_halo && mine && x0 == st.xb && x0 - 1 >= 0;      // slab halo planes: keep the
+            const bool halo_hi = st.store_halo && mine && x1 == st.xe && x1 < nx;          // neighbour's direction current
 
-            auto issue = [&](uint32_t gi, int64_t px) {
-                const int stg = gi % kStages;
-                const uint32_t bar = smem_u32(&bars[stg]);
+            auto issue = [&](int px) {
+                const uint32_t bar = smem_u32(&bars[issue_stg]);
+                unsigned char* tr = tiles0 + (size_t)(2 * issue_stg) * TB;
                 mbar_expect_tx(bar, kTxBytes);
-                tma_load_4d(smem_u32(tile_r(stg)), &tm_r, bar, z0 - 4, y0 - 1, (int)px, b);
-                tma_load_4d(smem_u32(tile_d(stg)), tm_old, bar, z0 - 4, y0 - 1, (int)px, b);
+                tma_load_4d(smem_u32(tr), &tm_r, bar, z0 - 4, y0 - 1, px, b);
+                tma_load_4d(smem_u32(tr + TB), tm_old, bar, z0 - 4, y0 - 1, px, b);
+                issue_stg = issue_stg + 1 == kStages ? 0 : issue_stg + 1;
             };
 
             __syncthreads();   // everything of the previous item has been consumed
             if (t == 0)
-                for (int k = 0; k < kStages && k < P; ++k) issue(g + k, x0 - 1 + k);
+                for (int k = 0; k < kStages && k < P; ++k) issue((int)x0 - 1 + k);
             Quad<T> x_cur{{T(0), T(0), T(0), T(0)}};
+            int64_t off = ((x0 - 1) * ny + jy) * nz + jz;      // element offset of (plane x0-1, jy, jz); advanced per plane
+            uint32_t pl_off = 0, pc_off = 3 * TB, pm_off = 2 * TB;   // byte offsets of planes k, k-1, k-2 in the ring
             for (int k = 0; k < P; ++k) {
-                const int64_t p = x0 - 1 + k;
-                const bool owned = mine && p >= x0 && p < x1;
-                const int64_t i = (p * ny + jy) * nz + jz;
+                const bool owned = mine && k >= 1 && k <= P - 2;
                 // the x values of the next owned plane travel while this plane is processed
                 Quad<T> x_next{{T(0), T(0), T(0), T(0)}};
-                if (mine && p + 1 >= x0 && p + 1 < x1) x_next = ld4<T>(xb + i + ny * nz);
-                const int stg = (g + k) % kStages;
-                mbar_wait(smem_u32(&bars[stg]), ((g + k) / kStages) & 1u);
-                T(*rt)[SROW] = tile_r(stg);
-                T(*dt)[SROW] = tile_d(stg);
-                T(*pl)[SROW] = plane(k);
+                if (mine && k <= P - 3) x_next = ld4<T>(xb + off + pstride);
+                mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
+                phase_bits ^= 1u << stg;
+                T(*rt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg) * TB);
+                T(*dt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg + 1) * TB);
+                T(*pl)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pl_off);
+                stg = stg + 1 == kStages ? 0 : stg + 1;
                 {
-                    const int c = 4 + 4 * lane;
-                    const Quad<T> rv = ld4<T>(&rt[warp + 1][c]), dv = ld4<T>(&dt[warp + 1][c]);
+                    const Quad<T> rv = ld4<T>(&rt[sr][c]), dv = ld4<T>(&dt[sr][c]);
                     Quad<T> dn;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
-                    st4(&pl[warp + 1][c], dn);
+                    st4(&pl[sr][c], dn);
                     if (owned) {
-                        st4(d_new + i, dn);
+                        st4(d_new + off, dn);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
-                        st4(xb + i, x_cur);
-                    } else if (st.store_halo && mine && (p == st.xb - 1 || p == st.xe) && p >= 0 && p < nx) {
-                        st4(d_new + i, dn);   // slab halo plane: keep the neighbour's direction up to date locally
+                        st4(xb + off, x_cur);
+                    } else if ((k == 0 && halo_lo) || (k == P - 1 && halo_hi)) {
+                        st4(d_new + off, dn);
                     }
                     if (warp < 2) {   // halo rows
                         const int hr = warp == 0 ? 0 : SY + 1;
@@ -190,35 +199,53 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                     }
                 }
                 x_cur = x_next;
-                __syncthreads();   // plane k complete; stage `stg` fully read
-                if (t == 0 && k + kStages < P) issue(g + k + kStages, p + kStages);
+                __syncthreads();   // plane k complete; its stage fully read
+                if (t == 0 && k + kStages < P) issue((int)x0 - 1 + k + kStages);
                 if (k >= 2 && mine) {
-                    T(*pm)[SROW] = plane(k - 2);
-                    T(*pc)[SROW] = plane(k - 1);
-                    const int sr = warp + 1, c = 4 + 4 * lane;
+                    T(*pm)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pm_off);
+                    T(*pc)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pc_off);
                     const Quad<T> ce = ld4<T>(&pc[sr][c]);
                     const Quad<T> ym = ld4<T>(&pc[sr - 1][c]), yp = ld4<T>(&pc[sr + 1][c]);
                     const Quad<T> xm = ld4<T>(&pm[sr][c]), xp = ld4<T>(&pl[sr][c]);
                     const T left = pc[sr][c - 1], right = pc[sr][c + 4];
                     Quad<T> out;
+                    T part = T(0);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const T zm = e == 0 ? left : ce.v[e - 1];
                         const T zp = e == 3 ? right : ce.v[e + 1];
-                        T sum = mul_rn(cxm, xm.v[e]);
-                        sum = add_rn(sum, mul_rn(cym, ym.v[e]));
-                        sum = add_rn(sum, mul_rn(czm, zm));
-                        sum = add_rn(sum, mul_rn(c0, ce.v[e]));
-                        sum = add_rn(sum, mul_rn(czp, zp));
-                        sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
-                        sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                        T sum;
+                        if constexpr (UNIT) {      // all six neighbour coefficients are -1: c*v == -v exactly, no multiply needed
+                            sum = -xm.v[e];
+                            sum = add_rn(sum, -ym.v[e]);
+                            sum = add_rn(sum, -zm);
+                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                            sum = add_rn(sum, -zp);
+                            sum = add_rn(sum, -yp.v[e]);
+                            sum = add_rn(sum, -xp.v[e]);
+                        } else {
+                            sum = mul_rn(cxm, xm.v[e]);
+                            sum = add_rn(sum, mul_rn(cym, ym.v[e]));
+                            sum = add_rn(sum, mul_rn(czm, zm));
+                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                            sum = add_rn(sum, mul_rn(czp, zp));
+                            sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
+                            sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                        }
                         out.v[e] = sum;
-                        acc[0] += (double)mul_rn(ce.v[e], sum);
+                        const T pr = mul_rn(ce.v[e], sum);
+                        part = e == 0 ? pr : add_rn(part, pr);
                     }
-                    st4(qb + ((p - 1) * ny + jy) * nz + jz, out);
+                    acc[0] += (double)part;        // the four products of a quad are added in T before they join the double sum
+                    st4(qb + off - pstride, out);
                 }
+                off += pstride;
+                const uint32_t tmp_off = pm_off;   // rotate the ring: k-1 -> k-2, k -> k-1, next plane reuses the slot after k-2's
+                pm_off = pc_off;
+                pc_off = pl_off;
+                pl_off = pl_off + TB == 4 * TB ? 0 : pl_off + TB;
+                (void)tmp_off;
             }
-            g += (uint32_t)P;
         }
     }
     epilogue_tail(epi, acc, b, blockIdx.x, gridDim.x);
