@@ -40,6 +40,7 @@ struct ResArgs {
     void* X;
     void* R;
     void* D;
+    void* Q;       // q = A d (adaptive variant: carried across launches)
     const void* Y;
     int64_t ld;
     int batch;
@@ -53,7 +54,7 @@ struct ResArgs {
 };
 
 template <typename T> constexpr int res_pack() { return 16 / (int)sizeof(T); }
-template <typename T> inline size_t res_smem_bytes(int lpc, int nz) { return (size_t)3 * lpc * nz * sizeof(T) + 2 * 32 * sizeof(double) + 16; }
+template <typename T> inline size_t res_smem_bytes(int lpc, int nz) { return (size_t)3 * lpc * nz * sizeof(T) + 6 * 32 * sizeof(double) + 16; }
 
 template <typename T> struct Pack;
 template <> struct Pack<float> { float v[4]; };
@@ -127,7 +128,9 @@ __device__ __forceinline__ double butterfly_sum(double v) {
 // flags of a pack
 constexpr unsigned RF_VALID = 1u, RF_YM = 2u, RF_YP = 4u, RF_XM = 8u, RF_XP = 16u, RF_Z0 = 32u, RF_ZN = 64u, RF_LO = 128u /* first */, RF_HI = 256u /* last line of the CTA */;
 
-template <typename T, int PRE, bool RANK3, bool CLUSTER>
+// ALG 0: cg / torch_sparse_cg;  ALG 1: cg_adaptive / torch_sparse_cg_adaptive (phiml/backend/_linalg.py:93-128,
+// phiml/backend/torch/_torch_backend.py:1385-1413; no preconditioner)
+template <typename T, int PRE, bool RANK3, bool CLUSTER, int ALG>
 __global__ void __launch_bounds__(kResThreads, 1) k_cg_resident(const ResArgs a, const ResCoef<T> cf) {
     constexpr int V = res_pack<T>();
     constexpr int QPT = kResQpt;
@@ -210,34 +213,35 @@ __global__ void __launch_bounds__(kResThreads, 1) k_cg_resident(const ResArgs a,
 #pragma unroll
     for (int e = 0; e < V; ++e) zero.v[e] = T(0);
     // neighbour loads: own CTA through ld.shared, a peer's line through ld.shared::cluster
-    auto yload = [&](int k, bool minus) -> Pack<T> {
+    auto yload = [&](int k, bool minus, uint32_t boff) -> Pack<T> {
         const unsigned f = fl[k];
         if constexpr (CLUSTER) {
-            if (f & (minus ? RF_LO : RF_HI)) return ldc_pack((minus ? rem_lo : rem_hi) + (f >> 9), T(0));
+            if (f & (minus ? RF_LO : RF_HI)) return ldc_pack((minus ? rem_lo : rem_hi) + (f >> 9) + boff, T(0));
         }
-        return lds_pack(minus ? own[k] - line_bytes : own[k] + line_bytes, T(0));
+        return lds_pack((minus ? own[k] - line_bytes : own[k] + line_bytes) + boff, T(0));
     };
-    auto xload = [&](uint32_t addr) -> Pack<T> {
+    auto xload = [&](uint32_t addr, uint32_t boff) -> Pack<T> {
         if constexpr (CLUSTER) {
-            if (addr - d_a >= vec_bytes) return ldc_pack(addr, T(0));   // mapa'd addresses lie outside the own window range
+            if (addr - d_a >= vec_bytes) return ldc_pack(addr + boff, T(0));   // mapa'd addresses lie outside the own window range
         }
-        return lds_pack(addr, T(0));
+        return lds_pack(addr + boff, T(0));
     };
 
-    // y = A v for pack k, v in the direction buffer (own + peers), centre pack `ce`; same summation order as k_star
-    auto stencil = [&](int k, const Pack<T>& ce) -> Pack<T> {
+    // y = A v for pack k, v in the buffer at byte offset `boff` from the direction buffer (own + peers), centre pack `ce`;
+    // same summation order as k_star
+    auto stencil_at = [&](int k, const Pack<T>& ce, uint32_t boff) -> Pack<T> {
         const unsigned f = fl[k];
         const T up = __shfl_up_sync(0xffffffffu, ce.v[V - 1], 1), dn = __shfl_down_sync(0xffffffffu, ce.v[0], 1);
         Pack<T> out = zero;
         if (f & RF_VALID) {
-            const T left = (f & RF_Z0) ? T(0) : (lane == 0 ? lds_one(own[k] - W, T(0)) : up);
-            const T right = (f & RF_ZN) ? T(0) : (lane == 31 ? lds_one(own[k] + V * W, T(0)) : dn);
-            const Pack<T> ym = (f & RF_YM) ? yload(k, true) : zero;
-            const Pack<T> yp = (f & RF_YP) ? yload(k, false) : zero;
+            const T left = (f & RF_Z0) ? T(0) : (lane == 0 ? lds_one(own[k] + boff - W, T(0)) : up);
+            const T right = (f & RF_ZN) ? T(0) : (lane == 31 ? lds_one(own[k] + boff + V * W, T(0)) : dn);
+            const Pack<T> ym = (f & RF_YM) ? yload(k, true, boff) : zero;
+            const Pack<T> yp = (f & RF_YP) ? yload(k, false, boff) : zero;
             Pack<T> xm = zero, xp = zero;
             if constexpr (RANK3) {
-                if (f & RF_XM) xm = xload(a_xm[k]);
-                if (f & RF_XP) xp = xload(a_xp[k]);
+                if (f & RF_XM) xm = xload(a_xm[k], boff);
+                if (f & RF_XP) xp = xload(a_xp[k], boff);
             }
 #pragma unroll
             for (int e = 0; e < V; ++e) {
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(kResThreads, 1) k_cg_resident(const ResArgs a,
         }
         return out;
     };
+    auto stencil = [&](int k, const Pack<T>& ce) -> Pack<T> { return stencil_at(k, ce, 0u); };
     // sum of the V products of a pack, added to the double accumulator
     auto dot_pack = [&](const Pack<T>& u, const Pack<T>& v, double& acc) {
         T p = mul_rn(u.v[0], v.v[0]);
@@ -285,6 +290,32 @@ __global__ void __launch_bounds__(kResThreads, 1) k_cg_resident(const ResArgs a,
         return tot;
     };
 
+    // two sums with one barrier (adaptive variant); slots 2*32.. of the reduction scratch
+    auto reduce2 = [&](double& v0, double& v1) {
+        v0 = butterfly_sum(v0);
+        v1 = butterfly_sum(v1);
+        if (lane == 0) {
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(red_a + ((par * 2 + 0) * 32 + warp) * 8 + 512), "d"(v0) : "memory");
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(red_a + ((par * 2 + 1) * 32 + warp) * 8 + 512), "d"(v1) : "memory");
+        }
+        barrier();
+        double t0 = 0.0, t1 = 0.0;
+        if constexpr (CLUSTER) {
+#pragma unroll
+            for (int c = 0; c < kResMaxCluster; ++c)
+                if (c < cs) {
+                    t0 += butterfly_sum(ldc_f64(red_peer[c] + ((par * 2 + 0) * 32 + lane) * 8 + 512));
+                    t1 += butterfly_sum(ldc_f64(red_peer[c] + ((par * 2 + 1) * 32 + lane) * 8 + 512));
+                }
+        } else {
+            t0 = butterfly_sum(lds_one(red_a + ((par * 2 + 0) * 32 + lane) * 8 + 512, 0.0));
+            t1 = butterfly_sum(lds_one(red_a + ((par * 2 + 1) * 32 + lane) * 8 + 512, 0.0));
+        }
+        par ^= 1u;
+        v0 = t0;
+        v1 = t1;
+    };
+
     const int n_clusters = (int)gridDim.x / cs;
     const T tol = (T)a.glob->tol_min;
     for (int b = (int)blockIdx.x / cs; b < a.batch; b += n_clusters) {
@@ -301,6 +332,137 @@ __global__ void __launch_bounds__(kResThreads, 1) k_cg_resident(const ResArgs a,
         T* __restrict__ Rg = (T*)a.R + base;
         T* __restrict__ Dg = (T*)a.D + base;
         const T* __restrict__ Yg = (const T*)a.Y + base;
+        if constexpr (ALG == 1) {
+            // ---------------- cg_adaptive: x += alpha d ; r -= alpha q ; d = r - (r.q / d.q) d ; q = A d ; alpha = d.r / d.q
+            T* __restrict__ Qg = (T*)a.Q + base;
+            T alpha = (T)S.s[0 /*S_ALPHA*/];
+            T dr = (T)S.s[4 /*S_DR*/], rqv = (T)S.s[5 /*S_RQ*/];
+            Pack<T> r[QPT];
+#pragma unroll
+            for (int k = 0; k < QPT; ++k) {
+                r[k] = zero;
+                if (fl[k] & RF_VALID) {
+                    const int o = (int)((own[k] - d_a) / W);
+                    sts_pack(own[k] + x_off, ldg_pack<T>(Xg + o));
+                    r[k] = ldg_pack<T>(Rg + o);
+                    sts_pack(own[k], ldg_pack<T>(Dg + o));
+                    sts_pack(own[k] + q_off, ldg_pack<T>(Qg + o));
+                }
+            }
+            while (!stop_now()) {
+                pass += 1;
+                const bool refresh = a.torch_rules && (pass % 20 == 0);
+                double p0 = 0.0, p1 = 0.0;
+                if (refresh) {   // x += alpha d first, then r = y - A x needs every CTA's x
+#pragma unroll
+                    for (int k = 0; k < QPT; ++k) {
+                        if (fl[k] & RF_VALID) {
+                            const Pack<T> dv = lds_pack(own[k], T(0));
+                            Pack<T> xv = lds_pack(own[k] + x_off, T(0));
+#pragma unroll
+                            for (int e = 0; e < V; ++e) xv.v[e] = add_rn(xv.v[e], mul_rn(alpha, dv.v[e]));
+                            sts_pack(own[k] + x_off, xv);
+                        }
+                    }
+                    barrier();
+                }
+#pragma unroll
+                for (int k = 0; k < QPT; ++k) {
+                    Pack<T> tv = zero;
+                    if (refresh) tv = stencil_at(k, (fl[k] & RF_VALID) ? lds_pack(own[k] + x_off, T(0)) : zero, x_off);
+                    if (fl[k] & RF_VALID) {
+                        const Pack<T> qv = lds_pack(own[k] + q_off, T(0));
+                        if (refresh) {
+                            const Pack<T> yv = ldg_pack<T>(Yg + (int)((own[k] - d_a) / W));
+#pragma unroll
+                            for (int e = 0; e < V; ++e) r[k].v[e] = add_rn(yv.v[e], -tv.v[e]);
+                        } else {
+                            const Pack<T> dv = lds_pack(own[k], T(0));
+                            Pack<T> xv = lds_pack(own[k] + x_off, T(0));
+#pragma unroll
+                            for (int e = 0; e < V; ++e) {
+                                xv.v[e] = add_rn(xv.v[e], mul_rn(alpha, dv.v[e]));
+                                r[k].v[e] = add_rn(r[k].v[e], -mul_rn(alpha, qv.v[e]));
+                            }
+                            sts_pack(own[k] + x_off, xv);
+                        }
+                        dot_pack(r[k], r[k], p0);
+                        dot_pack(r[k], qv, p1);
+                    }
+                }
+                reduce2(p0, p1);
+                if (refresh) fev += 1;
+                its += go;
+                delta = (T)p0;
+                rqv = (T)p1;
+                rsq = (double)delta;
+                // ---- direction d = r - (rq d) / dq   (the barrier of the reduction ordered every read of d before this)
+#pragma unroll
+                for (int k = 0; k < QPT; ++k) {
+                    if (fl[k] & RF_VALID) {
+                        Pack<T> dv = lds_pack(own[k], T(0));
+#pragma unroll
+                        for (int e = 0; e < V; ++e) {
+                            const T tt = mul_rn(rqv, dv.v[e]);
+                            const T u = dq == T(0) ? T(0) : tt / dq;
+                            dv.v[e] = add_rn(r[k].v[e], -u);
+                        }
+                        sts_pack(own[k], dv);
+                    }
+                }
+                barrier();
+                // ---- q = A d ; d.q, d.r
+                p0 = 0.0;
+                p1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < QPT; ++k) {
+                    const Pack<T> ce = (fl[k] & RF_VALID) ? lds_pack(own[k], T(0)) : zero;
+                    const Pack<T> qv = stencil(k, ce);
+                    if (fl[k] & RF_VALID) {
+                        sts_pack(own[k] + q_off, qv);
+                        dot_pack(ce, qv, p0);
+                        dot_pack(ce, r[k], p1);
+                    }
+                }
+                reduce2(p0, p1);
+                fev += go;
+                dq = (T)p0;
+                dr = (T)p1;
+                const T rq_ = (T)fabs(rsq);
+                const bool cv = rq_ <= tol;
+                const T ratio = rq_ / rsq0;
+                const bool dvg = a.torch_rules ? ((ratio > T(100)) && its >= 8) : (((ratio > T(1e5)) && its >= 8) || !isfinite(rq_));
+                conv = cv;
+                div = dvg;
+                go = (!cv && !dvg && its < max_iter) ? 1 : 0;
+                alpha = go ? safe_div(dr, dq) : T(0);
+            }
+#pragma unroll
+            for (int k = 0; k < QPT; ++k) {
+                if (fl[k] & RF_VALID) {
+                    const int o = (int)((own[k] - d_a) / W);
+                    stg_pack(Xg + o, lds_pack(own[k] + x_off, T(0)));
+                    stg_pack(Rg + o, r[k]);
+                    stg_pack(Dg + o, lds_pack(own[k], T(0)));
+                    stg_pack(Qg + o, lds_pack(own[k] + q_off, T(0)));
+                }
+            }
+            if (rank == 0 && t == 0) {
+                S.s[0 /*S_ALPHA*/] = (double)alpha;
+                S.s[2 /*S_DELTA*/] = (double)delta;
+                S.s[3 /*S_DQ*/] = (double)dq;
+                S.s[4 /*S_DR*/] = (double)dr;
+                S.s[5 /*S_RQ*/] = (double)rqv;
+                S.rsq = rsq;
+                S.its = its;
+                S.fev = fev;
+                S.go = go;
+                S.conv = conv;
+                S.div = div;
+                S.pad0 = pass;
+            }
+            barrier();
+        } else {
         Pack<T> r[QPT];
 #pragma unroll
         for (int k = 0; k < QPT; ++k) {
@@ -429,6 +591,7 @@ __global__ void __launch_bounds__(kResThreads, 1) k_cg_resident(const ResArgs a,
             S.pad0 = pass;
         }
         barrier();   // nobody overwrites its direction buffer for the next system while a peer still reads it
+        }
     }
 }
 

@@ -1341,7 +1341,9 @@ static bool resident_plan(const phb200_solver* s, int& cs, int& lpc, size_t& sme
     int mode = s->resident;
     if (mode < 0) { const char* e = getenv("PHB200_RESIDENT"); if (e && (e[0] == '0' || e[0] == '1')) mode = e[0] - '0'; }
     if (mode == 0) return false;
-    if (!(s->method == PHB200_CG || s->method == PHB200_CG_TORCH)) return false;
+    const bool adaptive = s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH;
+    if (!(s->method == PHB200_CG || s->method == PHB200_CG_TORCH || adaptive)) return false;
+    if (adaptive && s->pre != PHB200_PRE_NONE) return false;
     if (s->A->kind != PHB200_MAT_STENCIL || !s->A->is_star || s->totals) return false;
     if (s->pre == PHB200_PRE_ILU || (s->pre == PHB200_PRE_JACOBI && !s->M->is_const)) return false;
     const StarDesc& st = s->A->star;
@@ -1364,9 +1366,9 @@ static bool resident_plan(const phb200_solver* s, int& cs, int& lpc, size_t& sme
     return false;
 }
 
-template <typename T, int PRE, bool RANK3, bool CLUSTER>
+template <typename T, int PRE, bool RANK3, bool CLUSTER, int ALG = 0>
 static int launch_resident_t(const ResArgs& a, const ResCoef<T>& cf, size_t smem, cudaStream_t st) {
-    auto kernel = k_cg_resident<T, PRE, RANK3, CLUSTER>;
+    auto kernel = k_cg_resident<T, PRE, RANK3, CLUSTER, ALG>;
     static bool attr = false;
     if (!attr) {
         PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
@@ -1403,6 +1405,10 @@ static int launch_resident(const phb200_solver* s, const ResArgs& a, size_t smem
     ResCoef<T> cf;
     cf.c0 = (T)sd.c0; cf.cxm = (T)sd.cxm; cf.cxp = (T)sd.cxp; cf.cym = (T)sd.cym; cf.cyp = (T)sd.cyp; cf.czm = (T)sd.czm; cf.czp = (T)sd.czp;
     cf.cinv = jac ? (T)s->M->const_inv : T(1);
+    if (s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH) {
+        if (rank3) return cl ? launch_resident_t<T, 0, true, true, 1>(a, cf, smem, st) : launch_resident_t<T, 0, true, false, 1>(a, cf, smem, st);
+        return cl ? launch_resident_t<T, 0, false, true, 1>(a, cf, smem, st) : launch_resident_t<T, 0, false, false, 1>(a, cf, smem, st);
+    }
     if (jac) {
         if (rank3) return cl ? launch_resident_t<T, 3, true, true>(a, cf, smem, st) : launch_resident_t<T, 3, true, false>(a, cf, smem, st);
         return cl ? launch_resident_t<T, 3, false, true>(a, cf, smem, st) : launch_resident_t<T, 3, false, false>(a, cf, smem, st);
@@ -1421,10 +1427,11 @@ static int run_resident(phb200_solver* s, int64_t cap, int cs, int lpc, size_t s
     ResArgs a;
     a.nx = (int)s->A->star.nx; a.ny = (int)s->A->star.ny; a.nz = (int)s->A->star.nz;
     a.X = s->X; a.R = s->R; a.D = s->ws; a.Y = s->Y;
+    a.Q = s->ws + (size_t)s->batch * (size_t)s->n * sizeof(T);      // work vector 1
     a.ld = s->n;
     a.batch = (int)s->batch;
     a.sys = s->sys; a.glob = s->glob;
-    a.torch_rules = s->method == PHB200_CG_TORCH ? 1 : 0;
+    a.torch_rules = (s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH) ? 1 : 0;
     a.lb = 0;
     a.cap = (int)(cap > 0x3fffffff ? 0x3fffffff : cap);
     a.lpc = lpc; a.cs = cs;

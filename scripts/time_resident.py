@@ -50,6 +50,10 @@ if 'cfg1' in which:
 if 'cfg3' in which:
     run('cfg3 4096 x 128^2 fp32 CG generic', (128, 128), torch.float32, 4096, E.CG, 1e-5, 0.0)
     run('cfg3 4096 x 128^2 fp32 CG torch rules', (128, 128), torch.float32, 4096, E.CG_TORCH, 1e-5, 0.0)
+if 'auto' in which:     # PhiML's default method ('auto' -> CG-adaptive, torch rules)
+    run('128^2 fp32 auto (CG-adaptive torch rules) B=1', (128, 128), torch.float32, 1, E.CG_ADAPTIVE_TORCH, 1e-5, 0.0)
+    run('128^2 fp64 auto (CG-adaptive torch rules) B=1', (128, 128), torch.float64, 1, E.CG_ADAPTIVE_TORCH, 1e-10, 0.0)
+    run('256 x 128^2 fp32 auto (CG-adaptive torch rules)', (128, 128), torch.float32, 256, E.CG_ADAPTIVE_TORCH, 1e-5, 0.0)
 if 'small3d' in which:
     run('32^3 fp32 CG generic B=64', (32, 32, 32), torch.float32, 64, E.CG, 1e-5, 0.0)
     run('24^3 fp32 CG generic B=512', (24, 24, 24), torch.float32, 512, E.CG, 1e-5, 0.0)

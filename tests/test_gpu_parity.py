@@ -209,7 +209,7 @@ def test_solve_matches_reference(name, use_stencil):
     assert np.all(np.linalg.norm((true_res - res.residual.cpu().numpy()).astype(np.float64), axis=1) / scale <= (1e-9 if f64 else 2e-4))
 
 
-RESIDENT_CASES = ['p128_cg_f64_default', 'p128_cg_f32_default', 'p128_cg_f64_torch', 'p128_cg_f32_torch', 'p128_jacobi_f64', 'p16_cg_f64', 'p16_cg_f32',
+RESIDENT_CASES = ['p128_auto_f64', 'p128_auto_f32_torch', 'p128_cgadaptive_f32', 'p128_cg_f64_default', 'p128_cg_f32_default', 'p128_cg_f64_torch', 'p128_cg_f32_torch', 'p128_jacobi_f64', 'p16_cg_f64', 'p16_cg_f32',
                   'p32c_cg_f32', 'p32c_jacobi_f32', 'p32_batch8_f32', 'p32_quirk_f32', 'p32_quirk_f64_torch', 'p32_zero_rhs_f32', 'p32_maxiter_f32']
 
 
@@ -246,7 +246,8 @@ def test_resident_kernel_matches_streaming_kernels(name):
     assert np.all(np.linalg.norm((true_res - b.residual.cpu().numpy()).astype(np.float64), axis=1) / scale <= (1e-9 if y.dtype == np.float64 else 2e-4))
 
 
-def test_resident_torch_rules_large_batch_common_final_pass():
+@pytest.mark.parametrize('method', ['CG', 'auto'])
+def test_resident_torch_rules_large_batch_common_final_pass(method):
     """torch_sparse_cg keeps finished systems in the loop until the last one is done (refresh every 20th pass counts a
     function evaluation for ALL systems): the resident rounds must land every system on the same final pass."""
     from phiml_b200 import solve as S
@@ -260,7 +261,7 @@ def test_resident_torch_rules_large_batch_common_final_pass():
     for mode in ('never', 'always'):
         S.RESIDENT['mode'] = mode
         try:
-            out[mode] = pb.linear_solve('CG', nat, yd, torch.zeros_like(yd), [1e-5] * nb, [0.0] * nb, np.full((1, nb), 1000), None, None)
+            out[mode] = pb.linear_solve(method, nat, yd, torch.zeros_like(yd), [1e-5] * nb, [0.0] * nb, np.full((1, nb), 1000), None, None)
         finally:
             S.RESIDENT['mode'] = 'auto'
         assert S.LAST_RUN['resident'] == (mode == 'always')
