@@ -86,3 +86,32 @@ def test_front_end_reaches_the_boundary_with_reference_layout(phiml_env, monkeyp
     np.testing.assert_allclose(x.numpy('b,x,y'), g['front/torch/cg16/x'], rtol=0, atol=2e-5)
     np.testing.assert_array_equal(info.iterations.numpy('b'), g['front/torch/cg16/iterations'])
     assert info.method == str(g['front/torch/cg16/method'])
+
+
+def test_matrix_native_stays_resident_across_solves(phiml_env):
+    """the reference converts / uploads the matrix on every solve_linear call (_optimize.py:650); with the plug-in
+    the native of a live matrix tensor is built once per backend and dies with the tensor."""
+    import gc
+    from phiml import math
+    from phiml.math import spatial, Solve, extrapolation
+    plugin, TORCH = phiml_env
+    plugin.NATIVE_CACHE.clear()
+    plugin.NATIVE_CACHE.hits = plugin.NATIVE_CACHE.misses = 0
+    f = math.jit_compile_linear(lambda x: -math.laplace(x, padding=extrapolation.ZERO))
+    with TORCH:
+        rng = np.random.default_rng(1)
+        x0 = math.zeros(spatial(x=12, y=12))
+        xs = []
+        for k in range(3):
+            y = math.tensor(rng.standard_normal((12, 12)).astype(np.float32), spatial('x,y'))
+            xs.append(math.solve_linear(f, y, Solve('CG', 1e-5, 0, x0=x0)))
+    assert plugin.NATIVE_CACHE.misses == 1 and plugin.NATIVE_CACHE.hits == 2
+    assert len(plugin.NATIVE_CACHE._d) == 1
+    # results are those of independent solves (no state leaks between calls)
+    from oracle.assemble import poisson_csr
+    a = poisson_csr((12, 12), np.float32)
+    for x in xs:
+        assert np.isfinite(x.numpy('x,y')).all()
+    del f, xs
+    gc.collect()
+    assert len(plugin.NATIVE_CACHE._d) <= 1      # the entry goes away with the matrix tensor (LinearFunction dropped)
