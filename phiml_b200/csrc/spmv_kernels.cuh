@@ -102,9 +102,20 @@ __global__ void __launch_bounds__(kBlock) k_spmv_csr_stream(CsrView A, const T* 
         const int e0 = A.rowptr[r0], e1 = A.rowptr[r0 + nrows];
         const int cnt = e1 - e0;
         __syncthreads();
-        for (int k = t; k < cnt; k += kBlock) {
-            s_col[k] = A.col[e0 + k];
-            s_val[k] = val[e0 + k];
+        const bool direct = nb == 1 && !epi.skip(b0);     // one right-hand side: products straight from registers, no staging
+        if (direct) {
+            const T* __restrict__ x = X + (int64_t)b0 * ldx;
+            for (int k = t; k < cnt; k += kBlock) {     // (two chains per trip and fully unrolled loads measured slower: L1/LSU bound)
+                const int c = A.col[e0 + k];
+                T xv = x[c];
+                if (PRESCALE) xv = mul_rn(xv, scale[c]);
+                s_prod[k] = mul_rn(val[e0 + k], xv);
+            }
+        } else {
+            for (int k = t; k < cnt; k += kBlock) {
+                s_col[k] = A.col[e0 + k];
+                s_val[k] = val[e0 + k];
+            }
         }
         int my0 = 0, my1 = 0;
         if (t < nrows) {
@@ -116,13 +127,15 @@ __global__ void __launch_bounds__(kBlock) k_spmv_csr_stream(CsrView A, const T* 
             const int b = b0 + bl;
             if (epi.skip(b)) continue;
             const T* __restrict__ x = X + (int64_t)b * ldx;
-            for (int k = t; k < cnt; k += kBlock) {
-                const int c = s_col[k];
-                T xv = x[c];
-                if (PRESCALE) xv = mul_rn(xv, scale[c]);
-                s_prod[k] = mul_rn(s_val[k], xv);
+            if (!direct) {
+                for (int k = t; k < cnt; k += kBlock) {
+                    const int c = s_col[k];
+                    T xv = x[c];
+                    if (PRESCALE) xv = mul_rn(xv, scale[c]);
+                    s_prod[k] = mul_rn(s_val[k], xv);
+                }
+                __syncthreads();
             }
-            __syncthreads();
             double acc[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) acc[d] = 0.0;
