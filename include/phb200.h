@@ -180,6 +180,16 @@ int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream
 int phb200_solver_set_dist(phb200_solver* s, void* totals);
 int phb200_solver_dist_step(phb200_solver* s, int step, void* stream);
 
+/* Fused halo exchange for the step-driven mode (one process per GPU): after phb200_solver_set_dist, hand the solver the
+ * addresses of the slab neighbours' halo planes of THEIR residual arrays (device memory of the peer GPUs, mapped with
+ * phb200_ipc_export / phb200_ipc_open = cudaIpcGet/OpenMemHandle).  The residual kernel (dist_step 1) then writes its first / last
+ * owned plane there itself — coalesced stores over NVLink inside the kernel that produces them — and no separate exchange of R
+ * follows dist_step(2).  The all-reduce between dist_step(1) and dist_step(2) orders the writes before the neighbours' next read. */
+int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, int64_t ld_lower, void* upper_neighbour_halo, int64_t ld_upper);
+int phb200_ipc_export(const void* dev_ptr, void* handle64 /* 64 bytes out */, int64_t* offset /* of dev_ptr inside its allocation */);
+int phb200_ipc_open(const void* handle64, void** base_ptr /* mapping of the peer's allocation */);
+int phb200_ipc_close(void* base_ptr);
+
 /* Callback-driven distributed mode: EVERY method ('CG', 'CG-adaptive', torch rules, 'biCG-stab(L)'; no / Jacobi
  * preconditioner) on a star stencil in slab mode.  The loop stays inside the library (start / advance / run as usual);
  * wherever the algorithm has a global reduction the kernel leaves the rank-local sums in `totals` (batch*4 doubles) and

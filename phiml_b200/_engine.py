@@ -39,6 +39,10 @@ SIGNATURES = {
     'phb200_precond_jacobi': (c_int, [_PP, _P, c_int64, c_int, c_int]),
     'phb200_precond_ilu0': (c_int, [_PP, _P, _P, _P, _P]),
     'phb200_solver_set_dist_callbacks': (c_int, [_P, _P, _P, _P, _P]),
+    'phb200_solver_set_peer_halos': (c_int, [_P, _P, c_int64, _P, c_int64]),
+    'phb200_ipc_export': (c_int, [_P, _P, POINTER(c_int64)]),
+    'phb200_ipc_open': (c_int, [_P, _PP]),
+    'phb200_ipc_close': (c_int, [_P]),
     'phb200_solver_option': (c_int, [_P, c_int, c_int, POINTER(c_int)]),
     'phb200_precond_info': (c_int, [_P, POINTER(c_int), POINTER(c_int)]),
     'phb200_precond_levels': (c_int, [_P, POINTER(c_int64), POINTER(c_int64)]),

@@ -4,6 +4,7 @@
 #include "spmv_kernels.cuh"
 
 #include <utility>
+#include <type_traits>
 
 namespace phb {
 
@@ -26,6 +27,18 @@ struct PhaseOrder {
     int xchunk, chunks;
     int64_t planes;
 };
+
+// Slab mode, fused halo exchange: a phase functor that defines `peer` (PeerHalo) makes k_phase ALSO store array 0 on the first /
+// last owned plane into the slab neighbours' halo planes (their memory, mapped through CUDA IPC: plain coalesced stores over
+// NVLink), so no separate exchange step follows the kernel.
+struct PeerHalo {
+    void* lo;          // neighbour below: its upper halo plane of the same vector (null: physical boundary / not a slab)
+    void* hi;          // neighbour above: its lower halo plane
+    int64_t plane;     // elements per plane
+    int64_t ld_lo, ld_hi;   // leading dimensions (elements per system) of the neighbours' arrays
+};
+template <class P, class = void> struct HasPeer : std::false_type {};
+template <class P> struct HasPeer<P, std::void_t<decltype(std::declval<P>().peer)>> : std::true_type {};
 
 struct Ctx {
     Sys* sys;
@@ -114,6 +127,20 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
                         else *reinterpret_cast<VT*>(base[a] + idx[u]) = *reinterpret_cast<const VT*>(&e[u][a][0]);
                     }
                 });
+                if constexpr (HasPeer<P>::value) {     // first / last owned plane of array 0 -> the neighbours' halo planes
+                    const PeerHalo& ph = p.peer;
+                    const int64_t i = idx[u];
+                    if (ph.lo && i < ph.plane) {
+                        T* dst = (T*)ph.lo + (int64_t)b * ph.ld_lo + i;
+                        if constexpr (V == 1) dst[0] = e[u][0][0];
+                        else *reinterpret_cast<VT*>(dst) = *reinterpret_cast<const VT*>(&e[u][0][0]);
+                    }
+                    if (ph.hi && i >= n - ph.plane) {
+                        T* dst = (T*)ph.hi + (int64_t)b * ph.ld_hi + (i - (n - ph.plane));
+                        if constexpr (V == 1) dst[0] = e[u][0][0];
+                        else *reinterpret_cast<VT*>(dst) = *reinterpret_cast<const VT*>(&e[u][0][0]);
+                    }
+                }
             }
         }
     }

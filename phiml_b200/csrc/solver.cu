@@ -239,6 +239,7 @@ struct CgResid : FBase {
     const void* v[NA];
     T cinv;
     int rules;
+    PeerHalo peer;     // slab mode: the new residual's boundary planes also go to the neighbours' halo planes
     struct Scal { T alpha; };
     __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA]}; }
     __device__ void elem(T (&e)[NA], double (&acc)[1], const Scal& sc) const {
@@ -744,6 +745,9 @@ struct phb200_solver {
     phb200_allreduce_fn ar_cb;
     phb200_halo_fn halo_cb;
     void* cb_user;
+    void* peer_lo;             // slab mode: the neighbours' halo planes of R (CUDA IPC mappings), see phb200_solver_set_peer_halos
+    void* peer_hi;
+    int64_t peer_ld_lo, peer_ld_hi;
     int resident;              // PHB200_OPT_RESIDENT: -1 cost model decides, 0 never, 1 whenever the system fits on chip
     int resident_used;         // 1 if the last run() went through the resident kernel
     int64_t off, n_act;        // element range [off, off + n_act) of every vector that this rank owns (whole vector if not a slab)
@@ -989,6 +993,7 @@ struct Run {
         u.v[0] = R; u.v[1] = vec(1); u.v[2] = PRE == 1 ? s->M->inv_diag : nullptr;
         u.cinv = PRE == 3 ? (T)s->M->const_inv : T(1); u.rules = RULES_GENERIC;
         u.defer = defer();
+        u.peer = PeerHalo{s->peer_lo, s->peer_hi, s->A->kind == PHB200_MAT_STENCIL ? s->A->star.ny * s->A->star.nz : 0, s->peer_ld_lo, s->peer_ld_hi};
         return u;
     }
     // first half: d = M^-1 r + beta d, x += alpha d_old, q = A d, d.q
@@ -1606,6 +1611,15 @@ int phb200_solver_set_dist_callbacks(phb200_solver* s, void* totals, phb200_allr
     s->ar_cb = allreduce;
     s->halo_cb = halo;
     s->cb_user = user;
+    return PHB200_OK;
+}
+
+int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, int64_t ld_lower, void* upper_neighbour_halo, int64_t ld_upper) {
+    PHB_ARG(s && s->totals && !s->ar_cb, "peer halos belong to the step-driven distributed mode (phb200_solver_set_dist)");
+    s->peer_lo = lower_neighbour_halo;
+    s->peer_hi = upper_neighbour_halo;
+    s->peer_ld_lo = ld_lower;
+    s->peer_ld_hi = ld_upper;
     return PHB200_OK;
 }
 

@@ -1,4 +1,5 @@
 // Matrix handles, stand-alone products, stencil detection and device-side CSR assembly.
+#include <cuda.h>
 #include "dispatch.cuh"
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
@@ -206,6 +207,44 @@ extern "C" {
 int phb200_version(void) { return PHB200_VERSION; }
 const char* phb200_last_error(void) { return g_err; }
 int64_t phb200_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ---- CUDA IPC: lets the slab neighbours (one process per GPU) store halo planes straight into each other's vectors
+int phb200_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset) {
+    PHB_ARG(dev_ptr && handle64 && offset, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            set_error("cuMemGetAddressRange not available");
+            return PHB200_ERR_CUDA;
+        }
+        fn = (RangeFn)p;
+    }
+    if (fn(&base, &size, (CUdeviceptr)dev_ptr) != CUDA_SUCCESS) { set_error("cuMemGetAddressRange failed"); return PHB200_ERR_CUDA; }
+    cudaIpcMemHandle_t h;
+    PHB_CUDA(cudaIpcGetMemHandle(&h, (void*)base));
+    memcpy(handle64, &h, 64);
+    *offset = (int64_t)((CUdeviceptr)dev_ptr - base);
+    return PHB200_OK;
+}
+
+int phb200_ipc_open(const void* handle64, void** base_ptr) {
+    PHB_ARG(handle64 && base_ptr, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PHB_CUDA(cudaIpcOpenMemHandle(base_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PHB200_OK;
+}
+
+int phb200_ipc_close(void* base_ptr) {
+    if (base_ptr) PHB_CUDA(cudaIpcCloseMemHandle(base_ptr));
+    return PHB200_OK;
+}
 
 int phb200_matrix_csr(phb200_matrix** out, const int32_t* rowptr, const int32_t* col, const void* val,
                       int64_t n_rows, int64_t n_cols, int64_t nnz, int dtype, int transposed) {

@@ -165,13 +165,19 @@ class SlabCG:
     def _halo(self, ext: torch.Tensor):
         exchange_halo_planes(ext, self.nxl, self.plane, self.rank, self.world, self.group)
 
-    def solve(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, poll_every: int = 16, fixed_iterations: Optional[int] = None):
+    def solve(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, poll_every: int = 16, fixed_iterations: Optional[int] = None,
+              peer_halos: Optional[bool] = None):
         """
         ``y_local``/``x0_local``: this rank's slab, shape (batch, nxl*ny*nz).  Returns (x_local, residual_local, iterations,
         function_evaluations, converged, diverged) — the scalars are identical on every rank.
         ``fixed_iterations`` runs exactly that many iterations without polling (throughput measurements).
+        ``peer_halos``: the residual kernel writes its boundary planes straight into the neighbours' halo planes (CUDA IPC over
+        NVLink) instead of a separate NCCL send/recv step per iteration; default: whenever the engine supports it.
         """
         eng = self.engine
+        use_peer = self.world > 1 and hasattr(eng, 'open_peer_halos') and (peer_halos is None or peer_halos)
+        if peer_halos and not use_peer and self.world > 1:
+            raise RuntimeError("this engine has no peer-memory halo exchange")
         y_ext, x_ext = self.extend(y_local), self.extend(x0_local)
         self._halo(x_ext)                                   # A x0 needs the neighbours' boundary planes
         eng.start(y_ext, x_ext, rtol, atol, max_iter)       # local sums of r.s, y.y, r.r -> eng.totals
@@ -179,6 +185,9 @@ class SlabCG:
         eng.step(10)                                        # tolerances, first progress check (identical on all ranks)
         self._halo(eng.r)
         self._halo(eng.d0)                                  # d_0 = M^-1 r_0 including the halo planes
+        if use_peer:
+            eng.open_peer_halos(self.rank, self.world, self.nxl, self.plane, self.group)
+        self.peer_halos_active = use_peer
         done = 0
         limit = fixed_iterations if fixed_iterations is not None else max_iter
         while done < limit:
@@ -189,12 +198,15 @@ class SlabCG:
                 eng.step(1)                                 # alpha ; r -= alpha q, local r.M^-1 r
                 self._allreduce(eng.totals)
                 eng.step(2)                                 # beta, delta, progress check
-                self._halo(eng.r)
+                if not use_peer:
+                    self._halo(eng.r)                       # (peer mode: step(1) already stored the planes at the neighbours)
             done += n
             if fixed_iterations is None and not eng.any_continue():
                 break
         eng.step(20)                                        # pending x += alpha d
         its, fev, conv, div = eng.result()
+        if use_peer:
+            eng.close_peer_halos(self.group)
         return self.interior(eng.x), self.interior(eng.r), its, fev, conv, div
 
 
@@ -233,6 +245,42 @@ class CudaSlabEngine:
     def step(self, code: int):
         E = self.E
         E.check(E.lib().phb200_solver_dist_step(self.solver._h, code, E.stream_ptr(self.x.device)))
+
+    # --- fused halo exchange: map the neighbours' residual arrays (CUDA IPC) and let the residual kernel store into them ---
+    def open_peer_halos(self, rank, world, nxl, plane, group=None):
+        import ctypes
+        E = self.E
+        handle = (ctypes.c_ubyte * 64)()
+        offset = ctypes.c_int64()
+        E.check(E.lib().phb200_ipc_export(E.ptr(self.r), handle, ctypes.byref(offset)))
+        mine = (bytes(handle), int(offset.value), int(nxl))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        w = self.r.element_size()
+        self._peer_bases = []
+        ptrs, lds = [None, None], [0, 0]
+        for side, nb in ((0, rank - 1), (1, rank + 1)):
+            if nb < 0 or nb >= world:
+                continue
+            h, off, nxl_nb = everyone[nb]
+            base = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            E.check(E.lib().phb200_ipc_open(buf, ctypes.byref(base)))
+            self._peer_bases.append(base)
+            halo_plane = nxl_nb + 1 if side == 0 else 0         # the lower neighbour's upper halo plane / the upper neighbour's lower one
+            ptrs[side] = ctypes.c_void_p(base.value + off + halo_plane * plane * w)
+            lds[side] = (nxl_nb + 2) * plane
+        E.check(E.lib().phb200_solver_set_peer_halos(self.solver._h, ptrs[0], lds[0], ptrs[1], lds[1]))
+
+    def close_peer_halos(self, group=None):
+        E = self.E
+        torch.cuda.synchronize(self.x.device)
+        if dist.is_initialized():
+            dist.barrier(group=group)            # nobody unmaps while a neighbour's kernel may still store
+        E.check(E.lib().phb200_solver_set_peer_halos(self.solver._h, None, 0, None, 0))
+        for base in getattr(self, '_peer_bases', []):
+            E.check(E.lib().phb200_ipc_close(base))
+        self._peer_bases = []
 
     def any_continue(self) -> bool:
         return self.solver.any_continue()
