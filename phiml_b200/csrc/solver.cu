@@ -364,6 +364,32 @@ struct AdUpdate : FBase {
     __device__ void finalize_all() const {}
 };
 
+// r -= alpha q ; dots r.r, r.q — residual half of the fused adaptive iteration (x is updated by the stencil kernel that follows)
+template <typename T>
+struct AdResid : FBase {
+    static constexpr int NA = 2;   // r, q
+    static constexpr unsigned RMASK = 0b11u, WMASK = 0b01u, SHARED = 0u;
+    static constexpr int ND = 2;
+    static constexpr bool GLOBAL = false;
+    const void* v[NA];
+    struct Scal { T alpha; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA]}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[2], const Scal& sc) const {
+        e[0] = add_rn(e[0], -mul_rn(sc.alpha, e[1]));
+        acc[0] += (double)mul_rn(e[0], e[0]);
+        acc[1] += (double)mul_rn(e[0], e[1]);
+    }
+    __device__ void finalize(int b, const double (&tot)[2]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        s.its += s.go;
+        s.s[S_DELTA] = (double)(T)tot[0];
+        s.s[S_RQ] = (double)(T)tot[1];
+        s.rsq = (double)(T)tot[0];
+    }
+    __device__ void finalize_all() const {}
+};
+
 // d = r - safe_div(rq * d, dq)
 template <typename T>
 struct AdDirection : FBase {
@@ -790,9 +816,9 @@ static void fill_base(F& f, const phb200_solver* s, bool always, bool freeze) {
 static int vectors_needed(int method, int L, int pre) {
     switch (method) {
         case PHB200_CG: return pre == PHB200_PRE_ILU ? 4 : 3;              // d, q, d' (fused ping-pong) | d, q, s, tmp
-        case PHB200_CG_ADAPTIVE: return 2;                                   // d, q
-        case PHB200_CG_TORCH:
-        case PHB200_CG_ADAPTIVE_TORCH: return 3;                             // d, q, t
+        case PHB200_CG_ADAPTIVE: return 3;                                   // d, q, d' (fused ping-pong)
+        case PHB200_CG_TORCH: return 3;                                      // d, q, t
+        case PHB200_CG_ADAPTIVE_TORCH: return 4;                             // d, q, d', t
         case PHB200_BICGSTAB:
             if (L == 1) return 10;                                           // ones, u, p, ph, z, t, sl, tl, tmp, tmp2
             return 2 * L + 4;                                                // shadow, uh[0..L], rh[1..L], pv, tmp
@@ -928,7 +954,7 @@ struct Run {
         const int method = s->method;
         s->rtol = rtol; s->atol = atol; s->max_iter = max_iter;
         s->tma_ok = 0;
-        if (fused() && !getenv("PHB200_NO_TMA")) {
+        if ((fused() || fused_adaptive()) && !getenv("PHB200_NO_TMA")) {
             const StarDesc& sd = s->A->star;
             s->tma_ok = make_star_tmap(&s->tm_r, R, s->dtype, sd, batch, ld) && make_star_tmap(&s->tm_a, vec(0), s->dtype, sd, batch, ld) &&
                         make_star_tmap(&s->tm_b, vec(2), s->dtype, sd, batch, ld);
@@ -978,6 +1004,13 @@ struct Run {
     // for the three-phase form; this form moves 9 N w, +2 N w with a non-constant diagonal).
     bool fused() const {
         return s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && !cb_mode();
+    }
+    // 'CG-adaptive' / 'auto' on a star stencil: residual kernel + TMA stencil kernel (direction, x update, product, d.q, d.r)
+    bool fused_adaptive() const {
+        static int on = -1;
+        if (on < 0) { const char* e = getenv("PHB200_ADAPTIVE_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
+        return on && (s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH) && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star &&
+               s->pre == PHB200_PRE_NONE && !cb_mode() && !s->totals;
     }
     CgDq<T> make_dq() {
         CgDq<T> e;
@@ -1099,7 +1132,7 @@ struct Run {
         dim3 grid;
         int xchunk;
         star_grid(s->A->star, batch, occ, grid, xchunk);
-        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, e);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e);
         return PHB200_OK;
     }
     int pass_cg_fused(T* X, T* R) {
@@ -1183,12 +1216,67 @@ struct Run {
         return phase(c);
     }
 
+    template <bool UNIT>
+    int launch_tma_adaptive(T* X, T* q, int apply_x, const AdDots<T>& e) {
+        auto kernel = k_star_cg_tma<T, 0, AdDots<T>, UNIT, 1>;
+        constexpr int smem = star_tma_smem<T>();
+        static int occ = 0;
+        if (occ == 0) {
+            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
+            occ = v;
+        }
+        s->tma_occ = occ;
+        dim3 grid;
+        int xchunk;
+        star_grid(s->A->star, batch, occ, grid, xchunk);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, apply_x, e);
+        return PHB200_OK;
+    }
+    int pass_cg_adaptive_fused(T* X, T* R, const T* Y, bool refresh) {
+        T* q = vec(1);
+        const bool fr = frozen();
+        T* dcur = (s->passes & 1) ? vec(2) : vec(0);      // direction of the previous pass (ping-pong parity = passes made)
+        int apply_x = 1;
+        if (s->method == PHB200_CG_ADAPTIVE_TORCH && refresh) {
+            T* t = vec(3);
+            AxpyX<T> ax;
+            fill_base(ax, s, false, fr);
+            ax.v[0] = X; ax.v[1] = dcur;
+            PHB_TRY(phase(ax));
+            PlainEpi<T> pe;
+            fill_base(pe, s, false, fr);
+            PHB_TRY(spmv(X, t, pe));
+            RefreshResidual<T, true> rr;
+            fill_base(rr, s, false, fr);
+            rr.v[0] = R; rr.v[1] = Y; rr.v[2] = t; rr.v[3] = q; rr.rules = rules();
+            PHB_TRY(phase(rr));
+            apply_x = 0;                                  // x already carries alpha d
+        } else {
+            AdResid<T> u;
+            fill_base(u, s, false, fr);
+            u.v[0] = R; u.v[1] = q;
+            PHB_TRY(phase(u));
+        }
+        AdDots<T> e;
+        fill_base(e, s, false, fr);
+        e.d = nullptr; e.r = nullptr; e.ld = ld; e.rules = rules(); e.do_check = 1; e.count_fev = 1;
+        const StarDesc& sd = s->A->star;
+        const bool unit = sd.cxm == -1.0 && sd.cxp == -1.0 && sd.cym == -1.0 && sd.cyp == -1.0 && sd.czm == -1.0 && sd.czp == -1.0;
+        prof_begin();
+        const int r = unit ? launch_tma_adaptive<true>(X, q, apply_x, e) : launch_tma_adaptive<false>(X, q, apply_x, e);
+        prof_end();
+        return r;
+    }
+
     int pass_cg_adaptive(T* X, T* R, const T* Y, bool refresh) {
+        if (fused_adaptive() && s->tma_ok) return pass_cg_adaptive_fused(X, R, Y, refresh);
         T* d = vec(0);
         T* q = vec(1);
         const bool fr = frozen();
         if (s->method == PHB200_CG_ADAPTIVE_TORCH && refresh) {
-            T* t = vec(2);
+            T* t = vec(3);
             AxpyX<T> ax;
             fill_base(ax, s, false, fr);
             ax.v[0] = X; ax.v[1] = d;

@@ -85,10 +85,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 
 // PRE: 0 none, 3 Jacobi with constant inverse diagonal
-template <typename T, int PRE, class Epi, bool UNIT>
+// ALG 0: CG direction d = M^-1 r + beta d ; ALG 1: CG-adaptive direction d = r - (r.q / d.q) d with the second dot d.r
+template <typename T, int PRE, class Epi, bool UNIT, int ALG = 0>
 __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_a,
                                                         const __grid_constant__ CUtensorMap tm_b, StarDesc st, T* __restrict__ X, T* buf_a, T* buf_b,
-                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, Epi epi) {
+                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, int apply_x, Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TB = tile_bytes<T>();
     constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
@@ -97,7 +98,10 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
 
     const int b = blockIdx.y;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    double acc[1] = {0.0};
+    constexpr int NDA = AccSize<Epi>::N;
+    double acc[NDA];
+#pragma unroll
+    for (int dd = 0; dd < NDA; ++dd) acc[dd] = 0.0;
     if (t == 0) {
 #pragma unroll
         for (int k = 0; k < kStages; ++k) mbar_init(smem_u32(&bars[k]), 1);
@@ -120,9 +124,16 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
 
+        const T ad_rq = (T)epi.sys[b].s[5 /*S_RQ*/], ad_dq = (T)epi.sys[b].s[3 /*S_DQ*/];
         auto dir = [&](T rv, T dv) {
-            const T s = PRE == 3 ? mul_rn(rv, cinv) : rv;
-            return add_rn(s, mul_rn(beta, dv));
+            if constexpr (ALG == 1) {      // AdDirection: d = r - safe_div(rq * d, dq)
+                const T tt = mul_rn(ad_rq, dv);
+                const T u = ad_dq == T(0) ? T(0) : tt / ad_dq;
+                return add_rn(rv, -u);
+            } else {
+                const T s = PRE == 3 ? mul_rn(rv, cinv) : rv;
+                return add_rn(s, mul_rn(beta, dv));
+            }
         };
 
         // running state instead of per-plane index arithmetic: TMA stage + its mbarrier phase bits, byte offsets of the
@@ -158,30 +169,35 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
             if (t == 0)
                 for (int k = 0; k < kStages && k < P; ++k) issue((int)x0 - 1 + k);
             Quad<T> x_cur{{T(0), T(0), T(0), T(0)}};
+            Quad<T> r_prev{{T(0), T(0), T(0), T(0)}};          // r of the plane whose product is formed next (ALG 1: d.r)
             int64_t off = ((x0 - 1) * ny + jy) * nz + jz;      // element offset of (plane x0-1, jy, jz); advanced per plane
             uint32_t pl_off = 0, pc_off = 3 * TB, pm_off = 2 * TB;   // byte offsets of planes k, k-1, k-2 in the ring
             for (int k = 0; k < P; ++k) {
                 const bool owned = mine && k >= 1 && k <= P - 2;
                 // the x values of the next owned plane travel while this plane is processed
                 Quad<T> x_next{{T(0), T(0), T(0), T(0)}};
-                if (mine && k <= P - 3) x_next = ld4<T>(xb + off + pstride);
+                if (apply_x && mine && k <= P - 3) x_next = ld4<T>(xb + off + pstride);
                 mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
                 phase_bits ^= 1u << stg;
                 T(*rt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg) * TB);
                 T(*dt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg + 1) * TB);
                 T(*pl)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pl_off);
                 stg = stg + 1 == kStages ? 0 : stg + 1;
+                Quad<T> rv_keep{{T(0), T(0), T(0), T(0)}};
                 {
                     const Quad<T> rv = ld4<T>(&rt[sr][c]), dv = ld4<T>(&dt[sr][c]);
+                    rv_keep = rv;
                     Quad<T> dn;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
                     st4(&pl[sr][c], dn);
                     if (owned) {
                         st4(d_new + off, dn);
+                        if (apply_x) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
-                        st4(xb + off, x_cur);
+                            for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
+                            st4(xb + off, x_cur);
+                        }
                     } else if ((k == 0 && halo_lo) || (k == P - 1 && halo_hi)) {
                         st4(d_new + off, dn);
                     }
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                     const Quad<T> xm = ld4<T>(&pm[sr][c]), xp = ld4<T>(&pl[sr][c]);
                     const T left = pc[sr][c - 1], right = pc[sr][c + 4];
                     Quad<T> out;
-                    T part = T(0);
+                    T part = T(0), part_r = T(0);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const T zm = e == 0 ? left : ce.v[e - 1];
@@ -235,11 +251,17 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                         out.v[e] = sum;
                         const T pr = mul_rn(ce.v[e], sum);
                         part = e == 0 ? pr : add_rn(part, pr);
+                        if constexpr (ALG == 1) {
+                            const T prr = mul_rn(ce.v[e], r_prev.v[e]);
+                            part_r = e == 0 ? prr : add_rn(part_r, prr);
+                        }
                     }
                     acc[0] += (double)part;        // the four products of a quad are added in T before they join the double sum
+                    if constexpr (ALG == 1) acc[1] += (double)part_r;
                     st4(qb + off - pstride, out);
                 }
                 off += pstride;
+                r_prev = rv_keep;
                 const uint32_t tmp_off = pm_off;   // rotate the ring: k-1 -> k-2, k -> k-1, next plane reuses the slot after k-2's
                 pm_off = pc_off;
                 pc_off = pl_off;

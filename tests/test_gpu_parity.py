@@ -290,6 +290,36 @@ def test_solve_matches_oracle_on_same_inputs(name):
     assert np.all(rel_err(res.x.cpu().numpy(), ora.x) <= tol)
 
 
+@pytest.mark.parametrize('flavour,dt', [('numpy', 'float64'), ('torch', 'float32'), ('torch', 'float64')])
+def test_fused_adaptive_cg_3d_matches_oracle(flavour, dt):
+    """'CG-adaptive' / 'auto' on a 3-D star stencil runs as residual kernel + TMA stencil kernel (direction, x update, product,
+    d.q and d.r in one pass); compared with the oracle's cg_adaptive / torch_sparse_cg_adaptive on the same inputs, incl. a
+    refresh pass (> 20 iterations) for the torch rules."""
+    from oracle import krylov
+    grid = (24, 20, 28)
+    csr = oracle_matrix('poisson', grid, dt)
+    y = np.random.default_rng(9).standard_normal((2, csr.shape[0])).astype(dt)
+    rtol = np.asarray([1e-10, 1e-10] if dt == 'float64' else [1e-5, 1e-5], dt)
+    atol = np.zeros(2, dt)
+    ora = krylov.linear_solve('CG-adaptive', csr, y, np.zeros_like(y), rtol, atol, np.array([[1000, 1000]]), None, flavour=flavour)
+    m = pb.as_matrix(dev_csr(csr))
+    assert m.stencil is not None
+    yd = torch.as_tensor(y, device=DEV)
+    with streaming_kernels():
+        if flavour == 'torch':
+            res = pb.linear_solve('CG-adaptive', m, yd, torch.zeros_like(yd), rtol, atol, np.array([[1000, 1000]]), None, None)
+        else:
+            res = pb.generic_conjugate_gradient_adaptive(m, yd, torch.zeros_like(yd), rtol, atol, np.array([[1000, 1000]]))
+    assert int(ora.iterations.max()) > 20
+    assert np.max(np.abs(res.iterations.cpu().numpy().astype(int) - ora.iterations.astype(int))) <= 2
+    assert np.max(np.abs(res.function_evaluations.cpu().numpy().astype(int) - ora.function_evaluations.astype(int))) <= 3
+    np.testing.assert_array_equal(res.converged.cpu().numpy(), ora.converged)
+    tol = 1e-10 if dt == 'float64' else 1e-5
+    if not np.array_equal(res.iterations.cpu().numpy(), ora.iterations):
+        tol = 30 * float(rtol[0])
+    assert np.all(rel_err(res.x.cpu().numpy(), ora.x) <= tol)
+
+
 def test_reference_known_answers():
     """tests/commit/math/test__optimize.py:62-78 (x = [-1.5,-2,-1.5], batched RHS) and :95-112 (iterations == 2)."""
     csr = (oracle_matrix('poisson', (3,), 'float32') * -1.0).tocsr()
