@@ -264,16 +264,19 @@ struct CgResid : FBase {
 // x += alpha d_cur for every system (pending update of the fused iteration), then alpha = 0
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_flush_x(T* __restrict__ X, const T* __restrict__ buf_a, const T* __restrict__ buf_b,
-                                                    const Sys* __restrict__ sys, const Glob* __restrict__ glob, int64_t n, int64_t ld) {
+                                                    const Sys* __restrict__ sys, const Glob* __restrict__ glob, int64_t n, int64_t ld, int flip) {
     const int b = blockIdx.y;
+    if (flip && glob->any_go == 0) return;     // mid-pass flush of a pass that is skipped (everything finished): stays pending
     const T alpha = (T)sys[b].s[S_ALPHA];
     if (alpha == T(0)) return;
-    const T* __restrict__ d = ((glob->pass & 1) ? buf_b : buf_a) + (int64_t)b * ld;
+    // flip: called in the middle of a pass (torch refresh), the pass counter does not yet include the direction just written
+    const T* __restrict__ d = ((((glob->pass & 1) != 0) != (flip != 0)) ? buf_b : buf_a) + (int64_t)b * ld;
     T* __restrict__ x = X + (int64_t)b * ld;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) x[i] = add_rn(x[i], mul_rn(alpha, d[i]));
 }
 
-__global__ void k_zero_alpha(Sys* sys, int batch) {
+__global__ void k_zero_alpha(Sys* sys, int batch, const Glob* glob, int only_if_active) {
+    if (only_if_active && glob->any_go == 0) return;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < batch) sys[b].s[S_ALPHA] = 0.0;
 }
@@ -817,7 +820,7 @@ static int vectors_needed(int method, int L, int pre) {
     switch (method) {
         case PHB200_CG: return pre == PHB200_PRE_ILU ? 4 : 3;              // d, q, d' (fused ping-pong) | d, q, s, tmp
         case PHB200_CG_ADAPTIVE: return 3;                                   // d, q, d' (fused ping-pong)
-        case PHB200_CG_TORCH: return 3;                                      // d, q, t
+        case PHB200_CG_TORCH: return 4;                                      // d, q, d' (fused ping-pong) | t, t
         case PHB200_CG_ADAPTIVE_TORCH: return 4;                             // d, q, d', t
         case PHB200_BICGSTAB:
             if (L == 1) return 10;                                           // ones, u, p, ph, z, t, sl, tl, tmp, tmp2
@@ -1003,7 +1006,10 @@ struct Run {
     // Jacobi / un-preconditioned 'CG' on a star stencil: two kernels per iteration (SURVEY §8d counts 13 N w of traffic
     // for the three-phase form; this form moves 9 N w, +2 N w with a non-constant diagonal).
     bool fused() const {
-        return s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && !cb_mode();
+        static int torch_on = -1;
+        if (torch_on < 0) { const char* e = getenv("PHB200_CG_TORCH_FUSED"); torch_on = (e && e[0] == '0') ? 0 : 1; }
+        const bool cg = s->method == PHB200_CG || (torch_on && s->method == PHB200_CG_TORCH && s->pre == PHB200_PRE_NONE && !s->totals);
+        return cg && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && !cb_mode();
     }
     // 'CG-adaptive' / 'auto' on a star stencil: residual kernel + TMA stencil kernel (direction, x update, product, d.q, d.r)
     bool fused_adaptive() const {
@@ -1014,7 +1020,7 @@ struct Run {
     }
     CgDq<T> make_dq() {
         CgDq<T> e;
-        fill_base(e, s, false, true);
+        fill_base(e, s, false, frozen());
         e.d = nullptr; e.ld = ld;
         e.defer = defer();
         return e;
@@ -1022,9 +1028,9 @@ struct Run {
     template <int PRE>
     CgResid<T, PRE> make_resid(T* R) {
         CgResid<T, PRE> u;
-        fill_base(u, s, false, true);
+        fill_base(u, s, false, frozen());
         u.v[0] = R; u.v[1] = vec(1); u.v[2] = PRE == 1 ? s->M->inv_diag : nullptr;
-        u.cinv = PRE == 3 ? (T)s->M->const_inv : T(1); u.rules = RULES_GENERIC;
+        u.cinv = PRE == 3 ? (T)s->M->const_inv : T(1); u.rules = rules();
         u.defer = defer();
         u.peer = PeerHalo{s->peer_lo, s->peer_hi, s->A->kind == PHB200_MAT_STENCIL ? s->A->star.ny * s->A->star.nz : 0, s->peer_ld_lo, s->peer_ld_hi};
         return u;
@@ -1135,22 +1141,35 @@ struct Run {
         PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e);
         return PHB200_OK;
     }
-    int pass_cg_fused(T* X, T* R) {
+    int pass_cg_fused(T* X, T* R, const T* Y, bool refresh) {
+        if (s->method == PHB200_CG_TORCH && refresh) {
+            // torch_sparse_cg every 20th pass: x += alpha d, r = y - A x instead of r -= alpha q (_torch_backend.py:1371-1373)
+            PHB_TRY(fused_first<0>(X, R));                  // d, pending x update, q = A d, alpha
+            PHB_TRY(flush_x(X, 1));                         // x += alpha d NOW (and alpha = 0: nothing stays pending)
+            T* t = vec(3);
+            PlainEpi<T> pe;
+            fill_base(pe, s, false, false);
+            PHB_TRY(spmv(X, t, pe));
+            RefreshResidual<T, false> rr;
+            fill_base(rr, s, false, false);
+            rr.v[0] = R; rr.v[1] = Y; rr.v[2] = t; rr.v[3] = vec(1); rr.rules = rules();
+            return phase(rr);
+        }
         if (s->pre == PHB200_PRE_NONE) return pass_cg_fused_t<0>(X, R);
         if (s->M->is_const) return pass_cg_fused_t<3>(X, R);
         return pass_cg_fused_t<1>(X, R);
     }
     // applies the pending x += alpha d after a batch of fused passes (x is then the true iterate)
-    int flush_x(T* X) {
+    int flush_x(T* X, int flip = 0) {
         dim3 grid((unsigned)grid_x((s->n_act + kBlock * 4 - 1) / (kBlock * 4), batch, 8), (unsigned)batch);
-        PHB_LAUNCH(k_flush_x<T>, grid, kBlock, 0, st, X + s->off, (const T*)vec(0) + s->off, (const T*)vec(2) + s->off, (const Sys*)s->sys, (const Glob*)s->glob, s->n_act, ld);
-        PHB_LAUNCH(k_zero_alpha, (unsigned)((batch + 255) / 256), 256, 0, st, s->sys, batch);
+        PHB_LAUNCH(k_flush_x<T>, grid, kBlock, 0, st, X + s->off, (const T*)vec(0) + s->off, (const T*)vec(2) + s->off, (const Sys*)s->sys, (const Glob*)s->glob, s->n_act, ld, flip);
+        PHB_LAUNCH(k_zero_alpha, (unsigned)((batch + 255) / 256), 256, 0, st, s->sys, batch, (const Glob*)s->glob, flip);
         return PHB200_OK;
     }
 
     // ------------------------------------------------------------------------------------------ one pass
     int pass_cg(T* X, T* R, const T* Y, bool refresh) {
-        if (fused()) return pass_cg_fused(X, R);
+        if (fused()) return pass_cg_fused(X, R, Y, refresh);
         T* d = vec(0);
         T* q = vec(1);
         const bool fr = frozen();

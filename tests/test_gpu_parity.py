@@ -320,6 +320,24 @@ def test_fused_adaptive_cg_3d_matches_oracle(flavour, dt):
     assert np.all(rel_err(res.x.cpu().numpy(), ora.x) <= tol)
 
 
+@pytest.mark.parametrize('method', ['CG', 'auto'])
+def test_torch_rules_streaming_kernels_leave_a_consistent_iterate_128_cubed(method):
+    """The fused torch-rules passes defer the x update by one pass and flush it in the middle of every 20th (refresh) pass; passes
+    queued after the last system finished are skipped on the device and must leave the pending update for the final flush
+    (regression: 128^3 converges at pass 297 with refresh pass 300 already queued).  Size-independent check: the returned
+    residual is y - A x of the returned x to rounding, and x satisfies the requested tolerance."""
+    n = 128
+    shifts = shifts_for('poisson', 3, np.float32)
+    st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [float(c) for _, c in shifts], torch.float32, DEV)
+    y = torch.as_tensor(np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32), device=DEV)
+    with streaming_kernels():
+        res = pb.linear_solve(method, st, y, torch.zeros_like(y), [1e-5], [0.0], np.array([[5000]]), None, None)
+    assert bool(res.converged[0]) and abs(int(res.iterations[0]) - 297) <= 2
+    true_r = y - st.matvec(res.x)
+    assert float((true_r - res.residual).norm() / y.norm()) < 3e-6
+    assert float(true_r.norm() / y.norm()) < 1.2e-5
+
+
 def test_reference_known_answers():
     """tests/commit/math/test__optimize.py:62-78 (x = [-1.5,-2,-1.5], batched RHS) and :95-112 (iterations == 2)."""
     csr = (oracle_matrix('poisson', (3,), 'float32') * -1.0).tocsr()
