@@ -186,6 +186,14 @@ int phb200_solver_dist_step(phb200_solver* s, int step, void* stream);
  * owned plane there itself — coalesced stores over NVLink inside the kernel that produces them — and no separate exchange of R
  * follows dist_step(2).  The all-reduce between dist_step(1) and dist_step(2) orders the writes before the neighbours' next read. */
 int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, int64_t ld_lower, void* upper_neighbour_halo, int64_t ld_upper);
+/* In-kernel all-reduce for the step-driven mode: every rank allocates a zero-filled mailbox of phb200_peer_mailbox_bytes(world,
+ * batch) bytes, maps the mailboxes of all ranks (CUDA IPC) and passes the `world` device addresses (its own at index `rank`)
+ * BEFORE start().  The kernels then all-reduce their dot products themselves over NVLink peer memory (stores into every rank's
+ * mailbox, release/acquire at system scope, sum in rank order) and apply the scalar step at once: a CG iteration is
+ * dist_step(0), dist_step(1), dist_step(2) = two kernels, no NCCL call and no separate finalize launch (dist_step(2) and (10)
+ * only keep the host's pass count).  Up to 8 ranks. */
+int phb200_solver_set_peer_reduce(phb200_solver* s, void* const* mailboxes, int world, int rank, void* stream);
+size_t phb200_peer_mailbox_bytes(int world, int64_t batch);
 int phb200_ipc_export(const void* dev_ptr, void* handle64 /* 64 bytes out */, int64_t* offset /* of dev_ptr inside its allocation */);
 int phb200_ipc_open(const void* handle64, void** base_ptr /* mapping of the peer's allocation */);
 int phb200_ipc_close(void* base_ptr);

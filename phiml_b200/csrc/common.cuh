@@ -106,10 +106,27 @@ struct Glob {
     int pad[3];
 };
 
+// All-reduce over the slab ranks INSIDE the kernel that produced the local sums (one process per GPU, peer memory mapped through
+// CUDA IPC): the finishing thread of a system stores its sums into every rank's mailbox (NVLink peer stores, release at system
+// scope), waits until the mailboxes of its own GPU hold the sums of all ranks for this reduction, and adds them in rank order —
+// the same value on every rank — before the ordinary scalar step.  Two slots per (rank, system) are enough: nobody can be two
+// reductions ahead of a peer.
+struct PeerMail {
+    double v[kMaxDots];
+    unsigned long long seq;
+    unsigned long long pad[3];
+};
+struct PeerReduce {
+    PeerMail* mail[8];             // mailbox array of every rank: [2][world][batch]
+    unsigned long long* seq;       // [batch] reductions made so far (this GPU)
+    int world, rank, batch;
+};
+
 struct Reduce {
     double* partials;      // [batch][max_blocks][kMaxDots]
     unsigned* tickets;     // [batch]
     int max_blocks;
+    const PeerReduce* peer;   // non-null: multi-GPU slab mode with in-kernel all-reduce
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -167,7 +184,8 @@ __device__ __forceinline__ bool system_reduce(double (&tot)[ND], const Reduce& r
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) mine[(size_t)bx * kMaxDots + d] = tot[d];
-        __threadfence();
+        if (red.peer) __threadfence_system();   // this CTA's stores into peer GPUs (halo planes) precede the in-kernel all-reduce
+        else __threadfence();
         unsigned t = atomicAdd(&red.tickets[b], 1u);
         s_last = (t == (unsigned)nbx - 1u);
     }
@@ -188,6 +206,40 @@ __device__ __forceinline__ bool system_reduce(double (&tot)[ND], const Reduce& r
         red.tickets[b] = 0u;
     }
     return true;
+}
+
+// thread 0 of the finishing CTA of system b: tot (local sums) -> sums over all ranks
+template <int ND>
+__device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, int b, double (&tot)[ND]) {
+    const unsigned long long s = pr.seq[b] + 1ull;
+    pr.seq[b] = s;
+    const size_t par = (size_t)(s & 1ull);
+    const size_t mine = (par * pr.world + pr.rank) * pr.batch + b;
+    for (int p = 0; p < pr.world; ++p) {
+        volatile PeerMail* m = pr.mail[p] + mine;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) m->v[d] = tot[d];
+    }
+    __threadfence_system();
+    for (int p = 0; p < pr.world; ++p)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&(pr.mail[p] + mine)->seq), "l"(s) : "memory");
+    double sum[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) sum[d] = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < pr.world; ++r) {
+        const PeerMail* m = pr.mail[pr.rank] + (par * pr.world + r) * pr.batch + b;
+        unsigned long long got = 0;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&m->seq) : "memory");
+            if (got == s) break;
+            if (clock64() - t0 > 8000000000ll) __trap();
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) sum[d] += ((volatile const PeerMail*)m)->v[d];
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) tot[d] = sum[d];
 }
 
 // Per-thread accumulators -> CTA sum -> system_reduce.

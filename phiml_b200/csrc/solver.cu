@@ -774,6 +774,8 @@ struct phb200_solver {
     phb200_allreduce_fn ar_cb;
     phb200_halo_fn halo_cb;
     void* cb_user;
+    PeerReduce* peer_reduce;   // device table for the in-kernel all-reduce (phb200_solver_set_peer_reduce); owned
+    unsigned long long* peer_seq;   // device, owned
     void* peer_lo;             // slab mode: the neighbours' halo planes of R (CUDA IPC mappings), see phb200_solver_set_peer_halos
     void* peer_hi;
     int64_t peer_ld_lo, peer_ld_hi;
@@ -799,6 +801,7 @@ static Ctx make_ctx(const phb200_solver* s) {
     c.red.partials = s->partials;
     c.red.tickets = s->tickets;
     c.red.max_blocks = max_blocks_for(s->batch);
+    c.red.peer = s->peer_reduce;
     c.defer = nullptr;
     c.batch = (int)s->batch;
     return c;
@@ -836,7 +839,7 @@ struct Run {
     int64_t n, ld;
     int batch;
     T* vec(int k) const { return (T*)s->ws + (int64_t)k * batch * ld; }
-    double* defer() const { return s->totals; }
+    double* defer() const { return s->peer_reduce ? nullptr : s->totals; }   // in-kernel all-reduce: nothing is deferred
     bool frozen() const { return s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE; }
     int rules() const { return (s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH) ? RULES_TORCH : RULES_GENERIC; }
     const T* invd() const { return s->pre == PHB200_PRE_JACOBI ? (const T*)s->M->inv_diag : nullptr; }
@@ -1094,12 +1097,14 @@ struct Run {
                 s->prof_slot = 0;
                 return pre == 0 ? fused_first<0>(X, R) : fused_first<3>(X, R);
             case 1:   // alpha from the reduced d.q, then the residual half (local r.s -> totals)
-                PHB_TRY(finalize_only(make_dq()));
+                if (!s->peer_reduce) PHB_TRY(finalize_only(make_dq()));
                 return pre == 0 ? phase_ordered(make_resid<0>(R), resid_order()) : phase_ordered(make_resid<3>(R), resid_order());
             case 2:   // beta, delta, progress check from the reduced r.s
                 s->passes += 1;
+                if (s->peer_reduce) return PHB200_OK;     // done inside the residual kernel
                 return pre == 0 ? finalize_only(make_resid<0>(R)) : finalize_only(make_resid<3>(R));
             case 10:  // scalar set-up after the all-reduce of the initial sums
+                if (s->peer_reduce) return PHB200_OK;     // done inside the initial-residual kernel
                 return pre == 0 ? finalize_only(make_init<0>(R, (const T*)s->Y, vec(1), vec(0), false)) : finalize_only(make_init<3>(R, (const T*)s->Y, vec(1), vec(0), false));
             case 20:
                 return flush_x(X);
@@ -1730,6 +1735,28 @@ int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, i
     return PHB200_OK;
 }
 
+int phb200_solver_set_peer_reduce(phb200_solver* s, void* const* mailboxes, int world, int rank, void* stream_) {
+    PHB_ARG(s && s->totals && !s->ar_cb && !s->started, "peer reduce belongs to the step-driven distributed mode and is set before start");
+    PHB_ARG(mailboxes && world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad world / rank (at most 8 ranks)");
+    cudaStream_t st = (cudaStream_t)stream_;
+    PeerReduce h;
+    memset(&h, 0, sizeof(h));
+    for (int p = 0; p < world; ++p) {
+        PHB_ARG(mailboxes[p], "null mailbox");
+        h.mail[p] = (PeerMail*)mailboxes[p];
+    }
+    h.world = world; h.rank = rank; h.batch = (int)s->batch;
+    if (!s->peer_seq) PHB_CUDA(cudaMalloc(&s->peer_seq, sizeof(unsigned long long) * s->batch));
+    PHB_CUDA(cudaMemsetAsync(s->peer_seq, 0, sizeof(unsigned long long) * s->batch, st));
+    h.seq = s->peer_seq;
+    if (!s->peer_reduce) PHB_CUDA(cudaMalloc(&s->peer_reduce, sizeof(PeerReduce)));
+    PHB_CUDA(cudaMemcpyAsync(s->peer_reduce, &h, sizeof(PeerReduce), cudaMemcpyHostToDevice, st));
+    PHB_CUDA(cudaStreamSynchronize(st));      // `h` is a stack object
+    return PHB200_OK;
+}
+
+size_t phb200_peer_mailbox_bytes(int world, int64_t batch) { return sizeof(PeerMail) * 2 * (size_t)world * (size_t)batch; }
+
 int phb200_solver_dist_step(phb200_solver* s, int step, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started && s->totals && !s->ar_cb, "solver not started in (step-driven) distributed mode");
@@ -1854,6 +1881,8 @@ int phb200_solver_destroy(phb200_solver* s) {
         delete s->prof_events;
         delete s->prof_slots;
     }
+    if (s->peer_reduce) cudaFree(s->peer_reduce);
+    if (s->peer_seq) cudaFree(s->peer_seq);
     if (s->sys) cudaFree(s->sys);
     if (s->glob) cudaFree(s->glob);
     if (s->partials) cudaFree(s->partials);

@@ -166,22 +166,29 @@ class SlabCG:
         exchange_halo_planes(ext, self.nxl, self.plane, self.rank, self.world, self.group)
 
     def solve(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, poll_every: int = 16, fixed_iterations: Optional[int] = None,
-              peer_halos: Optional[bool] = None):
+              peer_halos: Optional[bool] = None, peer_reduce: Optional[bool] = None):
         """
         ``y_local``/``x0_local``: this rank's slab, shape (batch, nxl*ny*nz).  Returns (x_local, residual_local, iterations,
         function_evaluations, converged, diverged) — the scalars are identical on every rank.
         ``fixed_iterations`` runs exactly that many iterations without polling (throughput measurements).
         ``peer_halos``: the residual kernel writes its boundary planes straight into the neighbours' halo planes (CUDA IPC over
         NVLink) instead of a separate NCCL send/recv step per iteration; default: whenever the engine supports it.
+        ``peer_reduce``: the kernels all-reduce their dot products themselves through mailboxes in peer memory (no NCCL call and no
+        finalize launch inside the loop: an iteration is two kernels); default: whenever the engine supports it.
         """
         eng = self.engine
         use_peer = self.world > 1 and hasattr(eng, 'open_peer_halos') and (peer_halos is None or peer_halos)
         if peer_halos and not use_peer and self.world > 1:
             raise RuntimeError("this engine has no peer-memory halo exchange")
+        use_pr = self.world > 1 and self.world <= 8 and hasattr(eng, 'peer_reduce_cfg') and (peer_reduce is None or peer_reduce)
+        if hasattr(eng, 'peer_reduce_cfg'):
+            eng.peer_reduce_cfg = (self.rank, self.world, self.group) if use_pr else None
+        self.peer_reduce_active = use_pr
+        reduce_ = (lambda t: None) if use_pr else self._allreduce
         y_ext, x_ext = self.extend(y_local), self.extend(x0_local)
         self._halo(x_ext)                                   # A x0 needs the neighbours' boundary planes
         eng.start(y_ext, x_ext, rtol, atol, max_iter)       # local sums of r.s, y.y, r.r -> eng.totals
-        self._allreduce(eng.totals)
+        reduce_(eng.totals)
         eng.step(10)                                        # tolerances, first progress check (identical on all ranks)
         self._halo(eng.r)
         self._halo(eng.d0)                                  # d_0 = M^-1 r_0 including the halo planes
@@ -194,9 +201,9 @@ class SlabCG:
             n = min(poll_every, limit - done)
             for _ in range(n):
                 eng.step(0)                                 # d, x, q = A d, local d.q
-                self._allreduce(eng.totals)
+                reduce_(eng.totals)
                 eng.step(1)                                 # alpha ; r -= alpha q, local r.M^-1 r
-                self._allreduce(eng.totals)
+                reduce_(eng.totals)
                 eng.step(2)                                 # beta, delta, progress check
                 if not use_peer:
                     self._halo(eng.r)                       # (peer mode: step(1) already stored the planes at the neighbours)
@@ -205,7 +212,7 @@ class SlabCG:
                 break
         eng.step(20)                                        # pending x += alpha d
         its, fev, conv, div = eng.result()
-        if use_peer:
+        if use_peer or use_pr:
             eng.close_peer_halos(self.group)
         return self.interior(eng.x), self.interior(eng.r), its, fev, conv, div
 
@@ -224,6 +231,33 @@ class CudaSlabEngine:
         E.check(E.lib().phb200_matrix_set_slab(self.matrix.handle, xb, xe))
         self.pre = JacobiPreconditioner(self.matrix) if jacobi else None
         self.solver = None
+        self.peer_reduce_cfg = None        # (rank, world, group): in-kernel all-reduce through peer-memory mailboxes
+        self._peer_bases = []
+
+    def _setup_peer_reduce(self, nb, dev):
+        """Mailboxes: allocate + zero, exchange CUDA IPC handles, map every rank's, hand the table to the solver (before start)."""
+        import ctypes
+        E = self.E
+        rank, world, group = self.peer_reduce_cfg
+        nbytes = int(E.lib().phb200_peer_mailbox_bytes(world, nb))
+        self.mailbox = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)                     # zero-filled before anybody learns the address
+        handle = (ctypes.c_ubyte * 64)()
+        offset = ctypes.c_int64()
+        E.check(E.lib().phb200_ipc_export(E.ptr(self.mailbox), handle, ctypes.byref(offset)))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (bytes(handle), int(offset.value)), group=group)
+        table = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                table[r] = self.mailbox.data_ptr()
+                continue
+            base = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][0])
+            E.check(E.lib().phb200_ipc_open(buf, ctypes.byref(base)))
+            self._peer_bases.append(base)
+            table[r] = base.value + everyone[r][1]
+        E.check(E.lib().phb200_solver_set_peer_reduce(self.solver._h, table, world, rank, E.stream_ptr(dev)))
 
     def start(self, y_ext, x_ext, rtol, atol, max_iter):
         from .solve import DeviceSolver
@@ -233,6 +267,8 @@ class CudaSlabEngine:
         self.totals = torch.zeros(nb * 4, dtype=torch.float64, device=dev)
         self.solver = DeviceSolver(self.matrix, self.pre, E.CG, 0, nb)
         E.check(E.lib().phb200_solver_set_dist(self.solver._h, E.ptr(self.totals)))
+        if self.peer_reduce_cfg is not None:
+            self._setup_peer_reduce(nb, dev)
         rt = torch.as_tensor(rtol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
         at = torch.as_tensor(atol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
         mi = torch.full((nb,), int(max_iter), dtype=torch.int32, device=dev)
@@ -257,7 +293,6 @@ class CudaSlabEngine:
         everyone = [None] * world
         dist.all_gather_object(everyone, mine, group=group)
         w = self.r.element_size()
-        self._peer_bases = []
         ptrs, lds = [None, None], [0, 0]
         for side, nb in ((0, rank - 1), (1, rank + 1)):
             if nb < 0 or nb >= world:

@@ -19,6 +19,7 @@ p.add_argument('--size', dest='n', type=int, default=256)
 p.add_argument('--iters', type=int, default=100)
 p.add_argument('--warmup', type=int, default=10)
 p.add_argument('--check', action='store_true')
+p.add_argument('--nccl-reduce', action='store_true', help='NCCL all-reduce of the dot products instead of the in-kernel peer-memory all-reduce')
 p.add_argument('--nccl-halos', action='store_true', help='separate NCCL send/recv halo exchange instead of peer-memory stores from the residual kernel')
 a = p.parse_args()
 world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0')); lr = int(os.environ.get('LOCAL_RANK', '0'))
@@ -29,7 +30,7 @@ n = a.n; grid = (n, n, n); plane = n * n
 shifts = laplace_shifts(3); offsets = [s for s, _ in shifts]; coeffs = [c for _, c in shifts]
 cg = SlabCG(grid, offsets, coeffs, torch.float32, jacobi=True, device=dev)
 gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
-out = {"n": n, "world": world, "halo_exchange": "nccl send/recv" if a.nccl_halos or world == 1 else "peer-memory stores from the residual kernel (CUDA IPC)"}
+out = {"n": n, "world": world, "all_reduce": "nccl" if a.nccl_reduce or world == 1 else "in-kernel, peer-memory mailboxes", "halo_exchange": "nccl send/recv" if a.nccl_halos or world == 1 else "peer-memory stores from the residual kernel (CUDA IPC)"}
 if a.check:
     # same right-hand side everywhere: generated per global plane index so that any partition sees identical data
     y_full = None
@@ -47,7 +48,7 @@ if a.check:
             dist.recv(y_loc, 0)
     else:
         y_loc.copy_(y_full)
-    x, r_, its, fev, conv, div = cg.solve(y_loc, torch.zeros_like(y_loc), [1e-5], [0.0], 5000, peer_halos=(False if a.nccl_halos else None))
+    x, r_, its, fev, conv, div = cg.solve(y_loc, torch.zeros_like(y_loc), [1e-5], [0.0], 5000, peer_halos=(False if a.nccl_halos else None), peer_reduce=(False if a.nccl_reduce else None))
     out.update(iterations=int(its[0]), converged=bool(conv[0]))
     xs = [torch.empty((1, (slab_bounds(n, world, r)[1] - slab_bounds(n, world, r)[0]) * plane), dtype=torch.float32, device=dev) for r in range(world)] if world > 1 and rank == 0 else None
     if world > 1:
@@ -74,7 +75,7 @@ else:
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=iters, peer_halos=(False if a.nccl_halos else None))
+        cg.solve(y_loc, x0, [0.0], [0.0], 2 ** 30, fixed_iterations=iters, peer_halos=(False if a.nccl_halos else None), peer_reduce=(False if a.nccl_reduce else None))
         e1.record()
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1)
