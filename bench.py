@@ -277,6 +277,36 @@ def run_ours(args):
     iteration = {"bytes_moved_by_design": iter_bytes, "achieved_gbs": iter_bytes * its_per_s / 1e9, "frac_of_peak": iter_bytes * its_per_s / 1e9 / peak,
                  "survey_model_bytes": survey_bytes, "survey_model_gbs": survey_bytes * its_per_s / 1e9, "survey_model_frac_of_peak": survey_bytes * its_per_s / 1e9 / peak}
 
+    # ---- stand-alone products (BASELINE metric: "SpMV HBM GB/s (% of peak)"): y = A x through phb200_spmv, device-resident
+    spmv = None
+    if rank == 0:
+        def time_matvec(mat, use_stencil, reps=50):
+            # phb200_spmv called directly (the Python wrapper costs more host time than the 25 us stencil kernel runs)
+            m_ = mat.stencil if (use_stencil and mat.stencil is not None) else mat
+            xv = torch.randn((1, N), dtype=torch.float32, device=dev, generator=gen)
+            yv = torch.empty_like(xv)
+            lib, sp = E.lib(), E.stream_ptr(dev)
+            call = lambda: E.check(lib.phb200_spmv(m_.handle, E.ptr(xv), E.ptr(yv), 1, N, N, sp))
+            for _ in range(5):
+                call()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                call()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+        spmv = {}
+        ms_st = time_matvec(stencil, True)
+        b_st = 2 * N * w
+        spmv["stencil"] = {"ms": ms_st, "algorithmic_bytes": b_st, "gbs": b_st / ms_st / 1e6, "frac_of_peak": b_st / ms_st / 1e6 / peak}
+        if not too_big_for_csr:
+            nnz = int(csr.values.numel())
+            ms_csr = time_matvec(matrix, False)
+            b_csr = 8 * nnz + 4 * (N + 1) + 2 * N * w
+            spmv["csr"] = {"ms": ms_csr, "algorithmic_bytes": b_csr, "gbs": b_csr / ms_csr / 1e6, "frac_of_peak": b_csr / ms_csr / 1e6 / peak}
+
     # ---- end to end through the Backend-level call: pinned host y/x0 -> device, solve to rel_tol 1e-5, x -> host
     e2e = None
     if not args.no_e2e:
@@ -336,7 +366,7 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "config": workload_config(n, args.format, world), "clocks": clocks.summary(), "e2e": e2e,
-               "gpu_launches": launches, "roofline": roofline, "iteration": iteration, "cpu_baseline": cpu, "impl": "phb200"}
+               "gpu_launches": launches, "roofline": roofline, "iteration": iteration, "spmv": spmv, "cpu_baseline": cpu, "impl": "phb200"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -1,6 +1,6 @@
 // Host-side choice of the SpMV kernel for a matrix handle (used by phb200_spmv and by the Krylov loops).
 #pragma once
-#include "stencil_fast.cuh"
+#include "star_tma.cuh"
 
 namespace phb {
 
@@ -9,6 +9,9 @@ template <typename T, class Epi>
 int launch_spmv(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t ldy, const T* scale, int batch,
                 const Epi& epi, cudaStream_t stream) {
     if (A->kind == PHB200_MAT_STENCIL && A->is_star && !scale) {
+        bool used = false;     // TMA-staged product first; falls back when no tensor map can be built for X
+        PHB_TRY((launch_star_spmv_tma<T, Epi>(A->star, X, ldx, Y, ldy, batch, A->dtype, epi, stream, &used)));
+        if (used) return PHB200_OK;
         PlainLoad<T> loader{X, ldx};
         return launch_star<T, PlainLoad<T>, Epi, false>(A->star, loader, Y, ldy, batch, epi, stream);
     }

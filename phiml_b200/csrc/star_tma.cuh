@@ -273,4 +273,155 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
     epilogue_tail(epi, acc, b, blockIdx.x, gridDim.x);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Plain product y = A x on a star stencil with TMA staging: the x tiles (with halo, zero-filled outside the domain) ARE the
+// plane ring — kSpStages planes per CTA in flight, one barrier per plane, any epilogue (dots of BiCGstab, none for phb200_spmv).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSpStages = 5;
+template <typename T> constexpr int star_spmv_smem() { return kSpStages * tile_bytes<T>() + 8 * kSpStages + 128; }
+
+template <typename T, class Epi, bool UNIT>
+__global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant__ CUtensorMap tm_x, StarDesc st, T* __restrict__ Y, int64_t ldy, int xchunk, Epi epi) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TB = tile_bytes<T>();
+    constexpr int S = kSpStages;
+    constexpr uint32_t kTx = (uint32_t)(SROWS * SROW * sizeof(T));
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)S * TB);
+    const int b = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    constexpr int NDA = AccSize<Epi>::N;
+    double acc[NDA];
+#pragma unroll
+    for (int d = 0; d < NDA; ++d) acc[d] = 0.0;
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) mbar_init(smem_u32(&bars[k]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();
+    if (epi.idle()) return;
+    if (!epi.skip(b)) {
+        T* __restrict__ yb = Y + (int64_t)b * ldy;
+        const int64_t ny = st.ny, nz = st.nz;
+        const int tiles_z = (int)((nz + SZ - 1) / SZ), tiles_y = (int)((ny + SY - 1) / SY);
+        const int chunks = (int)((st.xe - st.xb + xchunk - 1) / xchunk);
+        const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
+        const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
+        const int64_t pstride = ny * nz;
+        const int c = 4 + 4 * lane, sr = warp + 1;
+        uint32_t stg = 0, phase_bits = 0, issue_stg = 0;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
+            const int64_t x0 = st.xb + (int64_t)ch * xchunk, x1 = min(st.xe, x0 + xchunk);
+            const int y0 = ty * SY, z0 = tz * SZ;
+            const int jy = y0 + warp, jz = z0 + 4 * lane;
+            const bool mine = jy < ny && jz < nz;
+            const int P = (int)(x1 - x0) + 2;   // planes x0-1 .. x1
+            auto issue = [&](int px) {
+                const uint32_t bar = smem_u32(&bars[issue_stg]);
+                mbar_expect_tx(bar, kTx);
+                tma_load_4d(smem_u32(base + (size_t)issue_stg * TB), &tm_x, bar, z0 - 4, y0 - 1, px, b);
+                issue_stg = issue_stg + 1 == S ? 0 : issue_stg + 1;
+            };
+            __syncthreads();   // every stage of the previous item has been consumed
+            if (t == 0)
+                for (int k = 0; k < S - 1 && k < P; ++k) issue((int)x0 - 1 + k);
+            int64_t off = (x0 * ny + jy) * nz + jz;              // element offset of the first OUTPUT plane
+            uint32_t s_m = 0, s_c = 0;                           // stages of planes k-2, k-1
+            for (int k = 0; k < P; ++k) {
+                mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
+                phase_bits ^= 1u << stg;
+                const uint32_t s_p = stg;
+                stg = stg + 1 == S ? 0 : stg + 1;
+                if (k >= 2 && mine) {
+                    T(*pm)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_m * TB);
+                    T(*pc)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_c * TB);
+                    T(*pp)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_p * TB);
+                    const Quad<T> ce = ld4<T>(&pc[sr][c]);
+                    const Quad<T> ym = ld4<T>(&pc[sr - 1][c]), yp = ld4<T>(&pc[sr + 1][c]);
+                    const Quad<T> xm = ld4<T>(&pm[sr][c]), xp = ld4<T>(&pp[sr][c]);
+                    const T left = pc[sr][c - 1], right = pc[sr][c + 4];
+                    Quad<T> out;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const T zm = e == 0 ? left : ce.v[e - 1];
+                        const T zp = e == 3 ? right : ce.v[e + 1];
+                        T sum;
+                        if constexpr (UNIT) {
+                            sum = -xm.v[e];
+                            sum = add_rn(sum, -ym.v[e]);
+                            sum = add_rn(sum, -zm);
+                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                            sum = add_rn(sum, -zp);
+                            sum = add_rn(sum, -yp.v[e]);
+                            sum = add_rn(sum, -xp.v[e]);
+                        } else {
+                            sum = mul_rn(cxm, xm.v[e]);
+                            sum = add_rn(sum, mul_rn(cym, ym.v[e]));
+                            sum = add_rn(sum, mul_rn(czm, zm));
+                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                            sum = add_rn(sum, mul_rn(czp, zp));
+                            sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
+                            sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                        }
+                        out.v[e] = sum;
+                    }
+                    st4(yb + off, out);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) epi.row(b, off + e, out.v[e], acc);
+                    off += pstride;
+                }
+                __syncthreads();   // the stage of plane k-2 is free; plane k-1, k stay
+                // planes in flight: k+1 .. k+S-2 have been issued; the freed stage takes plane k+S-1
+                if (t == 0 && k >= 1 && k + S - 2 < P) issue((int)x0 - 1 + k + S - 2);
+                s_m = s_c;
+                s_c = s_p;
+            }
+        }
+    }
+    epilogue_tail(epi, acc, b, blockIdx.x, gridDim.x);
+}
+
+template <typename T, class Epi>
+int launch_star_spmv_tma(const StarDesc& st, const T* X, int64_t ldx, T* Y, int64_t ldy, int batch, int dtype, const Epi& epi, cudaStream_t stream, bool* used) {
+    *used = false;
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("PHB200_SPMV_TMA"); disabled = (e && e[0] == '0') ? 1 : 0; }
+    if (disabled) return PHB200_OK;
+    CUtensorMap tm;
+    if (!make_star_tmap(&tm, X, dtype, st, batch, ldx)) return PHB200_OK;
+    const bool unit = st.cxm == -1.0 && st.cxp == -1.0 && st.cym == -1.0 && st.cyp == -1.0 && st.czm == -1.0 && st.czp == -1.0;
+    constexpr int smem = star_spmv_smem<T>();
+    dim3 grid;
+    int xchunk;
+    if (unit) {
+        auto kernel = k_star_spmv_tma<T, Epi, true>;
+        static int occ = 0;
+        if (occ == 0) {
+            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
+            occ = v;
+        }
+        star_grid(st, batch, occ, grid, xchunk);
+        PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
+    } else {
+        auto kernel = k_star_spmv_tma<T, Epi, false>;
+        static int occ = 0;
+        if (occ == 0) {
+            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
+            occ = v;
+        }
+        star_grid(st, batch, occ, grid, xchunk);
+        PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
+    }
+    *used = true;
+    return PHB200_OK;
+}
+
 }  // namespace phb
