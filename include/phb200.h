@@ -11,6 +11,7 @@
  *   phb200_spmv / phb200_spmv_coo      Backend.mul_matrix_batched_vector  phiml/backend/torch/_torch_backend.py:541-547
  *                                      Backend.mul_csr_dense              phiml/backend/torch/_torch_backend.py:912-922
  *                                      Backend.mul_coo_dense              phiml/backend/_backend.py:1303-1328
+ *   phb200_matrix_gradient_*           implicit_gradient_solve (dm)       phiml/math/_optimize.py:785-817
  *   phb200_matrix_csr                  TorchBackend.csr_matrix/csc_matrix phiml/backend/torch/_torch_backend.py:869-896
  *   phb200_stencil_* / _assemble_*     tracer_to_coo + compress           phiml/math/_lin_trace.py:750-807, phiml/math/_sparse.py:347-390
  *   phb200_solver_* (PHB200_CG)        cg + stop_on_l2                    phiml/backend/_linalg.py:23-90
@@ -112,6 +113,16 @@ int phb200_spmv(const phb200_matrix* A, const void* X, void* Y, int64_t batch, i
  * Y must be zero-filled by the caller; accumulation by atomics (order not deterministic). */
 int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int64_t nnz, int64_t n_rows, int64_t n_cols,
                     const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, int dtype, void* stream);
+
+/* Matrix gradient of the implicit-gradient (adjoint) step, phiml/math/_optimize.py:803-807 (`dm_values = dy[row] * x[col]`,
+ * negated and summed over the batch): out[k] = -sum_b DY[b,row[k]] * X[b,col[k]] for every stored entry k, in entry order.
+ * DY = solution of the adjoint solve A^T dy = dx (phb200_solver_* on the transposed matrix), X = forward solution.
+ * COO form: int64 coordinates as torch stores them; CSR form: int32 pointers / columns (entry order = CSR order, which is
+ * what CompressedSparseMatrix.decompress() yields, _optimize.py:800-801). */
+int phb200_matrix_gradient_coo(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n_rows, int64_t n_cols, const void* DY, const void* X,
+                               int64_t batch, int64_t ld_dy, int64_t ld_x, void* out, int dtype, void* stream);
+int phb200_matrix_gradient_csr(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols, int64_t nnz, const void* DY, const void* X,
+                               int64_t batch, int64_t ld_dy, int64_t ld_x, void* out, int dtype, void* stream);
 
 /* ------------------------------------------------------------- preconditioners --------------------------- */
 

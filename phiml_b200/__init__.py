@@ -12,5 +12,6 @@ from .solve import (SolveResult, linear_solve, conjugate_gradient, conjugate_gra
                     generic_conjugate_gradient, generic_conjugate_gradient_adaptive, mul_matrix_batched_vector, mul_csr_dense, mul_coo_dense,
                     solve_triangular_sparse, solve_triangular, DeviceSolver)
 from .backend import B200Backend
+from . import adjoint
 
 __all__ = [n for n in dir() if not n.startswith('_')]

@@ -103,6 +103,50 @@ __global__ void __launch_bounds__(kBlock) k_spmv_coo(const int64_t* __restrict__
         atomicAdd(&Y[(int64_t)b * ldy + row[k]], val[k] * X[(int64_t)b * ldx + col[k]]);
 }
 
+// ---------------------------------------------------------------------------------------------- matrix gradient
+// Sampled outer product of the implicit-gradient step (phiml/math/_optimize.py:803-807):
+//   dm[k] = -sum_b dy[b,row[k]] * x[b,col[k]]     on the stored entries, batch summed in order, products rounded separately.
+// COO form: int64 coordinates as torch stores them.  CSR form: a CTA walks chunks of kBlock rows, stages their row pointers in
+// shared memory and finds the row of an entry by bisection, so entries are read and written coalesced.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_matrix_gradient_coo(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t nnz,
+                                                                 const T* __restrict__ DY, int64_t ld_dy, const T* __restrict__ X, int64_t ld_x, int batch,
+                                                                 T* __restrict__ out) {
+    for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * kBlock) {
+        const int64_t r = row[k], c = col[k];
+        T acc = T(0);
+        for (int b = 0; b < batch; ++b) acc = add_rn(acc, mul_rn(DY[(int64_t)b * ld_dy + r], X[(int64_t)b * ld_x + c]));
+        out[k] = -acc;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_matrix_gradient_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
+                                                                 const T* __restrict__ DY, int64_t ld_dy, const T* __restrict__ X, int64_t ld_x, int batch,
+                                                                 T* __restrict__ out) {
+    __shared__ int32_t ptr[kBlock + 1];
+    const int64_t chunks = (n_rows + kBlock - 1) / kBlock;
+    for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int64_t r0 = ch * kBlock;
+        const int nr = (int)min((int64_t)kBlock, n_rows - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i <= nr; i += kBlock) ptr[i] = rowptr[r0 + i];
+        __syncthreads();
+        const int32_t p0 = ptr[0], p1 = ptr[nr];
+        for (int32_t k = p0 + (int32_t)threadIdx.x; k < p1; k += kBlock) {
+            int lo = 0, hi = nr;                 // largest i with ptr[i] <= k
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (ptr[mid] <= k) lo = mid; else hi = mid;
+            }
+            const int64_t r = r0 + lo, c = col[k];
+            T acc = T(0);
+            for (int b = 0; b < batch; ++b) acc = add_rn(acc, mul_rn(DY[(int64_t)b * ld_dy + r], X[(int64_t)b * ld_x + c]));
+            out[k] = -acc;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- stencil <-> CSR
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_stencil_verify(StencilDesc st, CsrView A, int* mismatch) {
@@ -421,6 +465,35 @@ int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int
     dim3 grid((unsigned)grid_x((nnz + kBlock - 1) / kBlock, batch), (unsigned)batch);
     if (dtype == PHB200_F32) PHB_LAUNCH(k_spmv_coo<float>, grid, kBlock, 0, stream, row, col, (const float*)val, nnz, (const float*)X, ldx, (float*)Y, ldy);
     else PHB_LAUNCH(k_spmv_coo<double>, grid, kBlock, 0, stream, row, col, (const double*)val, nnz, (const double*)X, ldx, (double*)Y, ldy);
+    return PHB200_OK;
+}
+
+int phb200_matrix_gradient_coo(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n_rows, int64_t n_cols, const void* DY, const void* X,
+                               int64_t batch, int64_t ld_dy, int64_t ld_x, void* out, int dtype, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(nnz == 0 || (row && col && DY && X && out), "null argument");
+    PHB_ARG(batch >= 0 && batch <= 65535, "batch must be <= 65535");
+    PHB_ARG(ld_dy >= n_rows && ld_x >= n_cols, "leading dimensions too small");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    if (nnz == 0) return PHB200_OK;
+    dim3 grid((unsigned)grid_x((nnz + kBlock - 1) / kBlock, 1));
+    if (dtype == PHB200_F32) PHB_LAUNCH(k_matrix_gradient_coo<float>, grid, kBlock, 0, stream, row, col, nnz, (const float*)DY, ld_dy, (const float*)X, ld_x, (int)batch, (float*)out);
+    else PHB_LAUNCH(k_matrix_gradient_coo<double>, grid, kBlock, 0, stream, row, col, nnz, (const double*)DY, ld_dy, (const double*)X, ld_x, (int)batch, (double*)out);
+    return PHB200_OK;
+}
+
+int phb200_matrix_gradient_csr(const int32_t* rowptr, const int32_t* col, int64_t n_rows, int64_t n_cols, int64_t nnz, const void* DY, const void* X,
+                               int64_t batch, int64_t ld_dy, int64_t ld_x, void* out, int dtype, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(nnz == 0 || (rowptr && col && DY && X && out), "null argument");
+    PHB_ARG(nnz <= 2147483647LL, "CSR natives hold at most 2^31-1 entries (int32 pointers)");
+    PHB_ARG(batch >= 0 && batch <= 65535, "batch must be <= 65535");
+    PHB_ARG(ld_dy >= n_rows && ld_x >= n_cols, "leading dimensions too small");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    if (nnz == 0 || n_rows == 0) return PHB200_OK;
+    dim3 grid((unsigned)grid_x((n_rows + kBlock - 1) / kBlock, 1));
+    if (dtype == PHB200_F32) PHB_LAUNCH(k_matrix_gradient_csr<float>, grid, kBlock, 0, stream, rowptr, col, n_rows, (const float*)DY, ld_dy, (const float*)X, ld_x, (int)batch, (float*)out);
+    else PHB_LAUNCH(k_matrix_gradient_csr<double>, grid, kBlock, 0, stream, rowptr, col, n_rows, (const double*)DY, ld_dy, (const double*)X, ld_x, (int)batch, (double*)out);
     return PHB200_OK;
 }
 

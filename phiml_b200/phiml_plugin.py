@@ -169,7 +169,11 @@ def install():
             return None, None
         if isinstance(values, torch.Tensor) and values.requires_grad:
             return None, None
-        return values, (type(matrix).__name__, id(indices), id(pointers), str(matrix.shape))
+        # which dims are compressed / how the coordinate columns are labelled distinguishes A from the transposed view the backward
+        # pass builds by renaming dims over the SAME arrays (transpose_matrix, _optimize.py:823-833)
+        layout = (repr(getattr(matrix, '_compressed_dims', None)), repr(getattr(matrix, '_uncompressed_dims', None)),
+                  repr(getattr(matrix, '_dense_shape', None)), repr(matrix._indices.shape))
+        return values, (type(matrix).__name__, id(indices), id(pointers), repr(matrix.shape)) + layout
 
     def native_matrix(value, target_backend):
         """phiml.math._sparse.native_matrix with residency: one conversion / upload per live matrix and backend."""

@@ -74,6 +74,7 @@ class Matrix:
         n = int(np.prod(grid))
         m = Matrix(h, dtype, (n, n), (), 'stencil', torch.device(device))
         m.grid = tuple(int(v) for v in grid)
+        m.spec = ([tuple(int(o) for o in off) for off in offsets], [float(v) for v in coeffs])
         return m
 
     # --- stencil recognition ---
@@ -212,11 +213,31 @@ def as_matrix(native, detect_stencil=True, grid=None) -> Matrix:
         keep = (native,)
     m._keep = m._keep + keep
     if detect_stencil and m.kind == 'csr':
-        m.detect_stencil(grid)
+        if m.detect_stencil(grid) is None and kind == 'coo':
+            _detect_ignoring_stored_zeros(m, grid)
     _CACHE[key] = m
     while len(_CACHE) > _CACHE_SIZE:
         _CACHE.popitem(last=False)
     return m
+
+
+def _detect_ignoring_stored_zeros(m: Matrix, grid=None):
+    """COO natives whose values carry gradients (solve_linear(..., grad_for_f=True)) keep the boundary entries of a ZERO-padded
+    stencil as stored zeros at the wrapped positions (the tracer cannot drop traced values).  They do not change a product, so
+    the stencil twin — used for products only — is looked for on the matrix without them; the CSR itself keeps its pattern
+    (ILU(0) is defined on it)."""
+    nz = m.values != 0
+    if bool(nz.all()):
+        return None
+    rows = torch.repeat_interleave(torch.arange(m.shape[0], device=m.device), (m.rowptr[1:] - m.rowptr[:-1]).to(torch.int64))
+    counts = torch.zeros(m.shape[0] + 1, dtype=torch.int64, device=m.device)
+    counts[1:] = torch.cumsum(torch.bincount(rows[nz], minlength=m.shape[0]), 0)
+    pruned = Matrix.csr(counts.to(torch.int32), m.col[nz], m.values[nz], m.shape)
+    st = pruned.detect_stencil(grid)
+    if st is not None:
+        m.stencil = st
+        m._keep = m._keep + (pruned,)
+    return st
 
 
 def plain_csr(m: Matrix) -> Matrix:

@@ -187,8 +187,113 @@ def golden_frontend(out):
             print(key, info.method, out[key + '/iterations'], out[key + '/function_evaluations'])
 
 
+def advdiff_k(x, k):
+    rank = x.shape.spatial_rank
+    u = math.wrap(list(ADVDIFF['velocity'][:rank]), channel(gradient=','.join(DIMS[:rank])))
+    g = math.spatial_gradient(x, padding=extrapolation.ZERO, difference='central', stack_dim=channel(gradient=','.join(DIMS[:rank])))
+    return x + ADVDIFF['c'] * math.sum(g * u, 'gradient') - k * ADVDIFF['nu'] * math.laplace(x, padding=extrapolation.ZERO)
+
+
+ADJOINT_CASES = {   # name: (grid, precision, method, rtol, batch, seed, grad_for_f)
+    'adj_a8x6x8_bicg2_f64': ((8, 6, 8), 64, 'biCG-stab(2)', 1e-10, 2, 5, True),
+    'adj_a8x6x8_bicg2_f32': ((8, 6, 8), 32, 'biCG-stab(2)', 1e-5, 2, 5, True),
+    'adj_a12x10_bicg1_f64': ((12, 10), 64, 'biCG-stab(1)', 1e-10, 3, 6, True),
+    'adj_a12x8x4_bicg2_f64_tight': ((12, 8, 4), 64, 'biCG-stab(2)', 1e-12, 1, 7, True),
+    # without grad_for_f the matrix is constant: compressed natives (CSR forward, CSC = arrays of A^T backward)
+    'adj_a8x6x8_bicg2_f64_const': ((8, 6, 8), 64, 'biCG-stab(2)', 1e-10, 2, 5, False),
+    'adj_a16x12_bicg2_f32_const': ((16, 12), 32, 'biCG-stab(2)', 1e-5, 2, 8, False),
+}
+
+
+def golden_adjoint(out):
+    """Backward pass of math.solve_linear(..., grad_for_f=True) on the reference's torch backend (CPU): what reaches
+    Backend.linear_solve in the backward pass (layout of A^T, right-hand side dx = dL/dx), its result dy = dL/dy, and the matrix
+    gradient dm on the stored entries (_optimize.py:785-817), recorded where the reference builds it (``matrix._with_values``)."""
+    from phiml.math import _sparse
+    TORCH = get_backend('torch')
+    for name, (grid, prec, method, rtol, nb, seed, grad_f) in ADJOINT_CASES.items():
+        rec = {'dm': [], 'calls': []}
+        orig_with = _sparse.SparseCoordinateTensor._with_values
+        orig_ls = TORCH.__class__.linear_solve
+
+        def spy_with(self, new_values, **kw):
+            rec['dm'].append((self, new_values))
+            return orig_with(self, new_values, **kw)
+
+        def spy_ls(self, meth, lin, y, x0, rtol_, atol_, max_iter, pre, matrix_offset):
+            r = orig_ls(self, meth, lin, y, x0, rtol_, atol_, max_iter, pre, matrix_offset)
+            rec['calls'].append((meth, str(lin.layout), lin, y.detach().numpy().copy(), r.x.detach().numpy().copy(), np.asarray(r.iterations).copy()))
+            return r
+        _sparse.SparseCoordinateTensor._with_values = spy_with
+        TORCH.__class__.linear_solve = spy_ls
+        try:
+            with TORCH, math.precision(prec):
+                dt = np.float64 if prec == 64 else np.float32
+                f = math.jit_compile_linear(advdiff_k)
+                rng = np.random.default_rng(seed)
+                names = ','.join(DIMS[:len(grid)])
+                y = math.tensor(rng.standard_normal((nb,) + grid).astype(dt), batch('b'), spatial(names))
+                x0 = math.zeros(spatial(**{DIMS[i]: g for i, g in enumerate(grid)}))
+
+                def loss(y, k):
+                    x = math.solve_linear(f, y, Solve(method, rtol, 0, x0=x0, max_iterations=1000), k=k, grad_for_f=grad_f)
+                    return math.l2_loss(x), x
+                if grad_f:
+                    (l, x), (dy, dk) = math.gradient(loss, 'y,k', get_output=True)(y, math.tensor(1.))
+                else:
+                    (l, x), dy = math.gradient(loss, 'y', get_output=True)(y, 1.)
+                    dk = math.tensor(0.)
+        finally:
+            _sparse.SparseCoordinateTensor._with_values = orig_with
+            TORCH.__class__.linear_solve = orig_ls
+        with math.precision(prec):      # Tensor.numpy() converts to the CURRENT precision
+            _adjoint_record(out, name, rec, x, dy, dk, grid, names, nb, grad_f)
+
+
+def _adjoint_record(out, name, rec, x, dy, dk, grid, names, nb, grad_f):
+    assert len(rec['calls']) == 2, len(rec['calls'])
+    fwd, bwd = rec['calls']
+    key = f"adjoint/{name}"
+    order = 'b,' + names
+    out[key + '/x'] = x.numpy(order).reshape(nb, -1)
+    out[key + '/dy'] = dy.numpy(order).reshape(nb, -1)
+    out[key + '/dk'] = np.asarray(dk.numpy())
+    out[key + '/forward_layout'] = fwd[1]
+    out[key + '/backward_layout'] = bwd[1]
+    out[key + '/backward_rhs'] = bwd[3]                 # = dL/dx = x for the l2 loss
+    out[key + '/backward_iterations'] = bwd[5]
+    out[key + '/forward_iterations'] = fwd[5]
+    # the matrices as they arrived at the boundary (COO natives, int64 indices, as torch stores them)
+    import torch
+    for tag, lin in (('forward', fwd[2]), ('backward', bwd[2])):
+        lin = lin.detach()
+        if lin.layout == torch.sparse_coo:
+            parts = dict(indices=lin._indices(), values=lin._values())
+        elif lin.layout == torch.sparse_csr:
+            parts = dict(crow=lin.crow_indices(), col=lin.col_indices(), values=lin.values())
+        else:
+            parts = dict(ccol=lin.ccol_indices(), row=lin.row_indices(), values=lin.values())
+        for pn, pv in parts.items():
+            out[key + f'/{tag}_{pn}'] = pv.numpy()
+    if not grad_f:
+        print(key, fwd[1], bwd[1], fwd[5], bwd[5])
+        return
+    # the matrix gradient, entry by entry, and the entry coordinates it refers to
+    dm_entries = [(m, v) for m, v in rec['dm'] if v.shape.volume == fwd[2]._values().numel()]
+    m, v = dm_entries[-1]
+    n = int(np.prod(grid))
+    idx = np.asarray(m._indices.native([m._indices.shape.non_channel, m._indices.shape.channel]))
+    rank = len(grid)
+    col = np.ravel_multi_index(tuple(idx[:, i] for i in range(rank)), grid)         # dual (~x,~y,..) first: tracer_to_coo label order
+    row = np.ravel_multi_index(tuple(idx[:, rank + i] for i in range(rank)), grid)
+    out[key + '/dm'] = np.asarray(v.numpy())
+    out[key + '/dm_row'] = row.astype(np.int64)
+    out[key + '/dm_col'] = col.astype(np.int64)
+    print(key, fwd[1], bwd[1], fwd[5], bwd[5], 'dk', float(out[key + '/dk']), 'dm', out[key + '/dm'].shape)
+
+
 def main():
-    groups = {'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend}
+    groups = {'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}

@@ -115,3 +115,54 @@ def test_matrix_native_stays_resident_across_solves(phiml_env):
     del f, xs
     gc.collect()
     assert len(plugin.NATIVE_CACHE._d) <= 1      # the entry goes away with the matrix tensor (LinearFunction dropped)
+
+
+def test_backward_pass_reaches_the_boundary_with_the_transposed_native(phiml_env, monkeypatch):
+    """math.gradient through solve_linear runs implicit_gradient_solve (_optimize.py:785-817); with the plug-in both
+    solves arrive at phb200's host entry — forward with the CSR native, backward with the SAME arrays as a CSC native (A^T)."""
+    import torch
+    import scipy.sparse as sp
+    from phiml import math
+    from phiml.math import spatial, batch, channel, Solve
+    from oracle import krylov
+    from phiml_b200 import solve as host
+    from _util import ADJOINT_CASES, ADVDIFF, adjoint_golden
+    plugin, TORCH = phiml_env
+    name = 'adj_a8x6x8_bicg2_f64_const'
+    grid, dt, method, rtol, nb, seed, _ = ADJOINT_CASES[name]
+    rec, mats = adjoint_golden(name)
+    seen = []
+
+    def fake_bicg(lin, y, x0, rtol_, atol_, max_iter, pre=None, matrix_offset=None, poly_order=2):
+        if lin.layout == torch.sparse_csr:
+            a = sp.csr_matrix((lin.values().numpy(), lin.col_indices().numpy(), lin.crow_indices().numpy()), shape=tuple(lin.shape))
+        else:
+            a = sp.csc_matrix((lin.values().numpy(), lin.row_indices().numpy(), lin.ccol_indices().numpy()), shape=tuple(lin.shape)).tocsr()
+        seen.append((str(lin.layout), lin.values().data_ptr(), tuple(y.shape), poly_order))
+        r = krylov.bicgstab_l(a, y.detach().numpy(), x0.detach().numpy(), np.asarray(rtol_), np.asarray(atol_), np.asarray(max_iter), None, poly_order, 'torch')
+        t = torch.as_tensor
+        return host.SolveResult(r.method, t(r.x), t(r.residual), t(r.iterations), t(r.function_evaluations), t(r.converged), t(r.diverged), r.message)
+
+    monkeypatch.setattr(plugin, '_on_path', lambda lin, y: True)
+    monkeypatch.setattr(host, 'bi_conjugate_gradient', fake_bicg)
+
+    def advdiff(x):
+        u = math.wrap(list(ADVDIFF['velocity']), channel(gradient='x,y,z'))
+        g = math.spatial_gradient(x, padding=math.extrapolation.ZERO, difference='central', stack_dim=channel(gradient='x,y,z'))
+        return x + ADVDIFF['c'] * math.sum(g * u, 'gradient') - ADVDIFF['nu'] * math.laplace(x, padding=math.extrapolation.ZERO)
+
+    with TORCH, math.precision(64):
+        f = math.jit_compile_linear(advdiff)
+        y = math.tensor(np.random.default_rng(seed).standard_normal((nb,) + grid), batch('b'), spatial('x,y,z'))
+        x0 = math.zeros(spatial(x=grid[0], y=grid[1], z=grid[2]))
+
+        def loss(y):
+            x = math.solve_linear(f, y, Solve(method, rtol, 0, x0=x0, max_iterations=1000))
+            return math.l2_loss(x), x
+        (l, x), dy = math.gradient(loss, 'y', get_output=True)(y)
+        dy_np, x_np = dy.numpy('b,x,y,z').reshape(nb, -1), x.numpy('b,x,y,z').reshape(nb, -1)
+    assert [s[0] for s in seen] == ['torch.sparse_csr', 'torch.sparse_csc']
+    assert seen[0][1] == seen[1][1], "the backward native must view the forward arrays (zero copy transposition)"
+    assert seen[0][2] == seen[1][2] == (nb, 384) and seen[1][3] == 2
+    np.testing.assert_allclose(x_np, rec['x'], rtol=0, atol=1e-8 * np.abs(rec['x']).max())
+    np.testing.assert_allclose(dy_np, rec['dy'], rtol=0, atol=1e-8 * np.abs(rec['dy']).max())
