@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(kBlock) k_spmv_coo(const int64_t* __restrict__
 // ---------------------------------------------------------------------------------------------- matrix gradient
 // Sampled outer product of the implicit-gradient step (phiml/math/_optimize.py:803-807):
 //   dm[k] = -sum_b dy[b,row[k]] * x[b,col[k]]     on the stored entries, batch summed in order, products rounded separately.
-// COO form: int64 coordinates as torch stores them.  CSR form: a CTA walks chunks of kBlock rows, stages their row pointers in
-// shared memory and finds the row of an entry by bisection, so entries are read and written coalesced.
+// COO form: int64 coordinates as torch stores them.  CSR form: a CTA walks chunks of kBlock rows; thread t labels the entries of
+// row t with the byte t in shared memory, then all threads walk the chunk's entries coalesced (index traffic 4 B instead of 16 B
+// per entry).
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_matrix_gradient_coo(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t nnz,
                                                                  const T* __restrict__ DY, int64_t ld_dy, const T* __restrict__ X, int64_t ld_x, int batch,
@@ -120,29 +121,43 @@ __global__ void __launch_bounds__(kBlock) k_matrix_gradient_coo(const int64_t* _
     }
 }
 
+constexpr int kGradWindow = 8192;   // entries per window of the CSR matrix-gradient kernel (row offsets as bytes in shared memory)
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_matrix_gradient_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_rows,
                                                                  const T* __restrict__ DY, int64_t ld_dy, const T* __restrict__ X, int64_t ld_x, int batch,
                                                                  T* __restrict__ out) {
-    __shared__ int32_t ptr[kBlock + 1];
+    static_assert(kBlock <= 256, "row offsets inside a chunk are stored as bytes");
+    __shared__ uint8_t rowof[kGradWindow];
+    __shared__ int32_t ends[2];
+    __shared__ T dys[kBlock];
     const int64_t chunks = (n_rows + kBlock - 1) / kBlock;
+    const int t = threadIdx.x;
     for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
         const int64_t r0 = ch * kBlock;
         const int nr = (int)min((int64_t)kBlock, n_rows - r0);
+        // thread t owns row r0 + t: it labels the row's entries, window by window (rows longer than a window span several)
+        const int32_t mine0 = t < nr ? rowptr[r0 + t] : 0, mine1 = t < nr ? rowptr[r0 + t + 1] : 0;
+        if (t == 0) ends[0] = mine0;
+        if (t == nr - 1) ends[1] = mine1;
+        if (batch == 1 && t < nr) dys[t] = DY[r0 + t];     // one right-hand side: dy of the chunk's rows comes from shared memory
         __syncthreads();
-        for (int i = threadIdx.x; i <= nr; i += kBlock) ptr[i] = rowptr[r0 + i];
-        __syncthreads();
-        const int32_t p0 = ptr[0], p1 = ptr[nr];
-        for (int32_t k = p0 + (int32_t)threadIdx.x; k < p1; k += kBlock) {
-            int lo = 0, hi = nr;                 // largest i with ptr[i] <= k
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (ptr[mid] <= k) lo = mid; else hi = mid;
+        const int32_t p0 = ends[0], p1 = ends[1];
+        __syncthreads();      // ends[] is rewritten for the next chunk
+        for (int32_t w0 = p0; w0 < p1; w0 += kGradWindow) {
+            const int32_t w1 = min(p1, w0 + kGradWindow);
+            for (int32_t k = max(mine0, w0); k < min(mine1, w1); ++k) rowof[k - w0] = (uint8_t)t;
+            __syncthreads();
+            for (int32_t k = w0 + t; k < w1; k += kBlock) {
+                const int lr = rowof[k - w0];
+                const int64_t r = r0 + lr, c = col[k];
+                T acc = T(0);
+                if (batch == 1) acc = add_rn(acc, mul_rn(dys[lr], X[c]));
+                else
+                    for (int b = 0; b < batch; ++b) acc = add_rn(acc, mul_rn(DY[(int64_t)b * ld_dy + r], X[(int64_t)b * ld_x + c]));
+                out[k] = -acc;
             }
-            const int64_t r = r0 + lo, c = col[k];
-            T acc = T(0);
-            for (int b = 0; b < batch; ++b) acc = add_rn(acc, mul_rn(DY[(int64_t)b * ld_dy + r], X[(int64_t)b * ld_x + c]));
-            out[k] = -acc;
+            __syncthreads();
         }
     }
 }
