@@ -8,6 +8,7 @@
 #include "precond.cuh"
 #include "resident.cuh"
 #include <vector>
+#include <mutex>
 #include <stdlib.h>
 
 namespace phb {
@@ -745,6 +746,9 @@ struct phb200_solver {
     double* partials;
     unsigned* tickets;
     int* h_flag;               // pinned, 2 slots
+    void* scratch;             // one device block holding sys / glob / partials / tickets (recycled through g_scratch_pool)
+    size_t scratch_bytes;
+    int device;
     cudaEvent_t ev[2];
     // per-solve bindings
     const void* Y;
@@ -1605,6 +1609,72 @@ static int advance(phb200_solver* s, int n_iter, cudaStream_t st) {
 
 }  // namespace phb
 
+// Solver scratch (per-system scalars, reduction partials, tickets, the pinned poll flag and its events) is recycled between solver
+// objects: a create / destroy pair per solve_linear call cost ~8 ms of cudaMalloc / cudaMallocHost / cudaFree on a process that
+// holds GBs of torch allocations — 10 % of a 256^3 solve.  At most kPoolMax blocks are kept; a block is reused for requests
+// between a quarter of and its full size.
+struct ScratchBlock {
+    void* dev;
+    size_t bytes;
+    int* h_flag;
+    cudaEvent_t ev[2];
+    int device;
+};
+constexpr size_t kPoolMax = 4;
+static std::mutex g_pool_mu;
+static std::vector<ScratchBlock> g_scratch_pool;
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static cudaError_t scratch_acquire(size_t bytes, int device, ScratchBlock* out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        for (size_t i = 0; i < g_scratch_pool.size(); ++i) {
+            const ScratchBlock& b = g_scratch_pool[i];
+            if (b.device == device && b.bytes >= bytes && b.bytes / 4 <= bytes) {
+                *out = b;
+                g_scratch_pool.erase(g_scratch_pool.begin() + (long)i);
+                return cudaSuccess;
+            }
+        }
+    }
+    ScratchBlock b{};
+    b.bytes = bytes;
+    b.device = device;
+    cudaError_t e = cudaMalloc(&b.dev, bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&b.h_flag, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        if (b.dev) cudaFree(b.dev);
+        if (b.h_flag) cudaFreeHost(b.h_flag);
+        if (b.ev[0]) cudaEventDestroy(b.ev[0]);
+        if (b.ev[1]) cudaEventDestroy(b.ev[1]);
+        return e;
+    }
+    *out = b;
+    return cudaSuccess;
+}
+
+static void scratch_release(const ScratchBlock& b) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur == b.device) {
+        // same guarantee cudaFree gave: nothing queued by the old owner still uses the block when the next owner gets it
+        if (cudaDeviceSynchronize() == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(g_pool_mu);
+            if (g_scratch_pool.size() < kPoolMax) {
+                g_scratch_pool.push_back(b);
+                return;
+            }
+        }
+    }
+    cudaFree(b.dev);
+    cudaFreeHost(b.h_flag);
+    cudaEventDestroy(b.ev[0]);
+    cudaEventDestroy(b.ev[1]);
+}
+
 extern "C" {
 
 int phb200_solver_create(phb200_solver** out, const phb200_matrix* A, const phb200_precond* M, int method, int poly_order, int64_t batch) {
@@ -1644,13 +1714,23 @@ int phb200_solver_create(phb200_solver** out, const phb200_matrix* A, const phb2
     }
     s->prof_events = new std::vector<cudaEvent_t>();
     s->prof_slots = new std::vector<int>();
-    cudaError_t e = cudaMalloc(&s->sys, sizeof(Sys) * batch);
-    if (e == cudaSuccess) e = cudaMalloc(&s->glob, sizeof(Glob));
-    if (e == cudaSuccess) e = cudaMalloc(&s->partials, sizeof(double) * kMaxDots * (size_t)max_blocks_for(batch) * (size_t)batch);
-    if (e == cudaSuccess) e = cudaMalloc(&s->tickets, sizeof(unsigned) * batch);
-    if (e == cudaSuccess) e = cudaMallocHost(&s->h_flag, 2 * sizeof(int));
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[0], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[1], cudaEventDisableTiming);
+    const size_t b_sys = align256(sizeof(Sys) * (size_t)batch), b_glob = align256(sizeof(Glob));
+    const size_t b_part = align256(sizeof(double) * kMaxDots * (size_t)max_blocks_for(batch) * (size_t)batch), b_tick = align256(sizeof(unsigned) * (size_t)batch);
+    ScratchBlock blk{};
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e == cudaSuccess) e = scratch_acquire(b_sys + b_glob + b_part + b_tick, s->device, &blk);
+    if (e == cudaSuccess) {
+        char* base = (char*)blk.dev;
+        s->scratch = blk.dev;
+        s->scratch_bytes = blk.bytes;
+        s->sys = (Sys*)base;
+        s->glob = (Glob*)(base + b_sys);
+        s->partials = (double*)(base + b_sys + b_glob);
+        s->tickets = (unsigned*)(base + b_sys + b_glob + b_part);
+        s->h_flag = blk.h_flag;
+        s->ev[0] = blk.ev[0];
+        s->ev[1] = blk.ev[1];
+    }
     if (e != cudaSuccess) {
         set_error("solver allocation failed: %s", cudaGetErrorString(e));
         phb200_solver_destroy(s);
@@ -1883,13 +1963,10 @@ int phb200_solver_destroy(phb200_solver* s) {
     }
     if (s->peer_reduce) cudaFree(s->peer_reduce);
     if (s->peer_seq) cudaFree(s->peer_seq);
-    if (s->sys) cudaFree(s->sys);
-    if (s->glob) cudaFree(s->glob);
-    if (s->partials) cudaFree(s->partials);
-    if (s->tickets) cudaFree(s->tickets);
-    if (s->h_flag) cudaFreeHost(s->h_flag);
-    if (s->ev[0]) cudaEventDestroy(s->ev[0]);
-    if (s->ev[1]) cudaEventDestroy(s->ev[1]);
+    if (s->scratch) {
+        ScratchBlock blk{s->scratch, s->scratch_bytes, s->h_flag, {s->ev[0], s->ev[1]}, s->device};
+        scratch_release(blk);
+    }
     delete s;
     return PHB200_OK;
 }
