@@ -114,6 +114,13 @@ int phb200_spmv(const phb200_matrix* A, const void* X, void* Y, int64_t batch, i
 int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int64_t nnz, int64_t n_rows, int64_t n_cols,
                     const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, int dtype, void* stream);
 
+/* CSR of A^T from the CSR of A (= reading the arrays of a CSC native, TorchBackend.csc_matrix _torch_backend.py:885-896, the layout the
+ * backward solve receives, phiml/math/_optimize.py:823-833, as the plain CSR the solver kernels take).  Rows of the result are
+ * sorted by column; values are moved, not changed.  t_rowptr: n_cols+1, t_col / t_val: nnz.  Temporaries (12 bytes per entry +
+ * sort scratch) come from the stream-ordered pool and are released before returning. */
+int phb200_csr_transpose(const int32_t* rowptr, const int32_t* col, const void* val, int64_t n_rows, int64_t n_cols, int64_t nnz, int dtype,
+                         int32_t* t_rowptr, int32_t* t_col, void* t_val, void* stream);
+
 /* Matrix gradient of the implicit-gradient (adjoint) step, phiml/math/_optimize.py:803-807 (`dm_values = dy[row] * x[col]`,
  * negated and summed over the batch): out[k] = -sum_b DY[b,row[k]] * X[b,col[k]] for every stored entry k, in entry order.
  * DY = solution of the adjoint solve A^T dy = dx (phb200_solver_* on the transposed matrix), X = forward solution.

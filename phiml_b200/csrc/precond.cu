@@ -669,6 +669,29 @@ int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp,
     return PHB200_ERR_UNSUPPORTED;
 }
 
+
+// ---------------------------------------------------------------------------------------------- CSR transposition
+// A^T of a CSR matrix as CSR (= the CSC arrays of A): stable radix sort of the entry numbers by column (entries of one column
+// keep their row order, so the rows of A^T come out sorted), row starts by bisection on the sorted keys, then one gather pass.
+__global__ void __launch_bounds__(kBlock) k_iota(int32_t* __restrict__ out, int64_t n) {
+    for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < n; k += (int64_t)gridDim.x * kBlock) out[k] = (int32_t)k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_transpose_fill(const int32_t* __restrict__ rowptr, int64_t n_rows, const T* __restrict__ val, const int32_t* __restrict__ perm,
+                                                            int64_t nnz, int32_t* __restrict__ t_col, T* __restrict__ t_val) {
+    for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * kBlock) {
+        const int32_t k = perm[j];
+        int64_t lo = 0, hi = n_rows;          // largest r with rowptr[r] <= k
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] <= k) lo = mid; else hi = mid;
+        }
+        t_col[j] = (int32_t)lo;
+        t_val[j] = val[k];
+    }
+}
+
 }  // namespace phb
 
 using namespace phb;
@@ -854,6 +877,45 @@ int phb200_precond_destroy(phb200_precond* p) {
     phb200_sptrsv_plan_destroy(p->plan_u);
     delete p;
     return PHB200_OK;
+}
+
+int phb200_csr_transpose(const int32_t* rowptr, const int32_t* col, const void* val, int64_t n_rows, int64_t n_cols, int64_t nnz, int dtype,
+                         int32_t* t_rowptr, int32_t* t_col, void* t_val, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(rowptr && t_rowptr && (nnz == 0 || (col && val && t_col && t_val)), "null argument");
+    PHB_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && nnz <= 2147483647LL && n_cols <= 2147483646LL, "sizes out of range for int32 CSR");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    if (nnz == 0) {
+        PHB_CUDA(cudaMemsetAsync(t_rowptr, 0, sizeof(int32_t) * (size_t)(n_cols + 1), stream));
+        return PHB200_OK;
+    }
+    int32_t *iota = nullptr, *keys = nullptr, *perm = nullptr;
+    void* tmp = nullptr;
+    int r = PHB200_OK;
+    do {
+        cudaError_t e = cudaMallocAsync(&iota, sizeof(int32_t) * (size_t)nnz, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&keys, sizeof(int32_t) * (size_t)nnz, stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&perm, sizeof(int32_t) * (size_t)nnz, stream);
+        if (e != cudaSuccess) { set_error("transposition scratch allocation failed: %s", cudaGetErrorString(e)); r = PHB200_ERR_CUDA; break; }
+        k_iota<<<(unsigned)grid_x((nnz + kBlock - 1) / kBlock, 1), kBlock, 0, stream>>>(iota, nnz);
+        int bits = 1;
+        while ((1ll << bits) < n_cols) ++bits;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, col, keys, iota, perm, (int)nnz, 0, bits, stream);
+        if (cudaMallocAsync(&tmp, tmp_bytes, stream) != cudaSuccess) { set_error("sort scratch allocation failed"); r = PHB200_ERR_CUDA; break; }
+        cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, col, keys, iota, perm, (int)nnz, 0, bits, stream);   // stable: rows ascending inside a column
+        k_level_starts<<<(unsigned)((n_cols + 1 + kBlock - 1) / kBlock), kBlock, 0, stream>>>(keys, nnz, (int32_t)n_cols, t_rowptr);
+        const unsigned grid = (unsigned)grid_x((nnz + kBlock - 1) / kBlock, 1);
+        if (dtype == PHB200_F32) k_transpose_fill<float><<<grid, kBlock, 0, stream>>>(rowptr, n_rows, (const float*)val, perm, nnz, t_col, (float*)t_val);
+        else k_transpose_fill<double><<<grid, kBlock, 0, stream>>>(rowptr, n_rows, (const double*)val, perm, nnz, t_col, (double*)t_val);
+        g_launches.fetch_add(5);
+        if (cudaGetLastError() != cudaSuccess) { set_error("transposition launch failed"); r = PHB200_ERR_CUDA; break; }
+    } while (0);
+    if (iota) cudaFreeAsync(iota, stream);
+    if (keys) cudaFreeAsync(keys, stream);
+    if (perm) cudaFreeAsync(perm, stream);
+    if (tmp) cudaFreeAsync(tmp, stream);
+    return r;
 }
 
 }  // extern "C"

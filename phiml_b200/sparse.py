@@ -246,9 +246,13 @@ def plain_csr(m: Matrix) -> Matrix:
         return m
     t = getattr(m, '_plain', None)
     if t is None:
-        at = torch.sparse_csr_tensor(m.rowptr, m.col, m.values, (m.shape[1], m.shape[0]))
-        a = at.to_sparse_csc()                      # CSC of A^T == CSR of A
-        t = Matrix.csr(a.ccol_indices(), a.row_indices(), a.values(), m.shape)
+        rows_stored, nnz = m.shape[1], int(m.values.numel())          # the stored arrays are the CSR of A^T
+        rowptr = torch.empty(m.shape[0] + 1, dtype=torch.int32, device=m.device)
+        col = torch.empty(nnz, dtype=torch.int32, device=m.device)
+        val = torch.empty(nnz, dtype=m.dtype, device=m.device)
+        E.check(E.lib().phb200_csr_transpose(E.ptr(m.rowptr), E.ptr(m.col), E.ptr(m.values), rows_stored, m.shape[0], nnz, E.dtype_code(m.dtype),
+                                             E.ptr(rowptr), E.ptr(col), E.ptr(val), E.stream_ptr(m.device)))
+        t = Matrix.csr(rowptr, col, val, m.shape)
         t.detect_stencil()
         m._plain = t
     return t

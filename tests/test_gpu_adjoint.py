@@ -160,3 +160,36 @@ def test_autograd_function_against_dense_autograd(layout):
     np.testing.assert_allclose(x.detach().cpu().numpy(), xd.detach().cpu().numpy(), rtol=0, atol=1e-10)
     np.testing.assert_allclose(y.grad.cpu().numpy(), yd.grad.cpu().numpy(), rtol=0, atol=1e-9 * float(yd.grad.abs().max()))
     np.testing.assert_allclose(v.grad.cpu().numpy(), vd.grad.cpu().numpy(), rtol=0, atol=1e-9 * float(vd.grad.abs().max()))
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float64'])
+def test_native_transposition_is_bit_exact(dt):
+    """phb200_csr_transpose (used once per CSC native of a backward pass): indices and values equal SciPy's, rows sorted."""
+    import ctypes
+    import scipy.sparse as sp
+    from phiml_b200 import _engine as E
+    rng = np.random.default_rng(31)
+    for rows, cols, density in [(700, 500, 0.02), (64, 3000, 0.01), (1, 17, 0.5), (300, 300, 0.0)]:
+        a = sp.random(rows, cols, density=density, random_state=rng, format='csr', dtype=np.dtype(dt))
+        a.sort_indices()
+        ref = a.T.tocsr()
+        ref.sort_indices()
+        t = lambda v: torch.as_tensor(np.ascontiguousarray(v), device=DEV)
+        rp, ci, va = t(a.indptr.astype(np.int32)), t(a.indices.astype(np.int32)), t(a.data)
+        o_rp = torch.empty(cols + 1, dtype=torch.int32, device=DEV)
+        o_ci = torch.empty(a.nnz, dtype=torch.int32, device=DEV)
+        o_va = torch.empty(a.nnz, dtype=va.dtype, device=DEV)
+        E.check(E.lib().phb200_csr_transpose(E.ptr(rp), E.ptr(ci), E.ptr(va), rows, cols, a.nnz, E.dtype_code(va.dtype), E.ptr(o_rp), E.ptr(o_ci), E.ptr(o_va), E.stream_ptr(DEV)))
+        np.testing.assert_array_equal(o_rp.cpu().numpy(), ref.indptr)
+        np.testing.assert_array_equal(o_ci.cpu().numpy(), ref.indices)
+        np.testing.assert_array_equal(o_va.cpu().numpy(), ref.data)
+    # through the host path: CSC native -> plain CSR
+    a = sp.random(400, 400, density=0.03, random_state=rng, format='csc', dtype=np.dtype(dt))
+    a.sort_indices()
+    nat = torch.sparse_csc_tensor(torch.as_tensor(a.indptr, device=DEV), torch.as_tensor(a.indices, device=DEV), torch.as_tensor(a.data, device=DEV), a.shape)
+    m = plain_csr(pb.as_matrix(nat))
+    ref = a.tocsr()
+    ref.sort_indices()
+    np.testing.assert_array_equal(m.rowptr.cpu().numpy(), ref.indptr)
+    np.testing.assert_array_equal(m.col.cpu().numpy(), ref.indices)
+    np.testing.assert_array_equal(m.values.cpu().numpy(), ref.data)
