@@ -16,6 +16,26 @@ namespace phb {
 void set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launches;
 
+// Temporaries of the set-up calls come from the device's stream-ordered pool.  By default that pool hands its memory back to
+// the OS at every synchronisation, so each call paid fresh allocations (milliseconds on a process holding GBs); the release
+// threshold is raised once per device so the temporaries are recycled.
+inline cudaError_t phb_malloc_async(void** p, size_t bytes, cudaStream_t stream) {
+    static std::atomic<unsigned> configured{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 32 && !(configured.load(std::memory_order_relaxed) & (1u << dev))) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        cudaGetLastError();
+        configured.fetch_or(1u << dev, std::memory_order_relaxed);
+    }
+    return cudaMallocAsync(p, bytes, stream);
+}
+template <typename P>
+inline cudaError_t phb_malloc_async(P** p, size_t bytes, cudaStream_t stream) { return phb_malloc_async((void**)p, bytes, stream); }
+
 #define PHB_CUDA(expr)                                                                          \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \

@@ -188,17 +188,17 @@ int build_plan_star(phb200_trsv_plan** out, const StarDesc& st, int lower, cudaS
     std::vector<int32_t> level_ptr(n_levels + 1);
     do {
         cudaError_t e = cudaMalloc(&p->order, sizeof(int32_t) * (n > 0 ? n : 1));
-        if (e == cudaSuccess) e = cudaMallocAsync(&lev, sizeof(int32_t) * n, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(&row, sizeof(int32_t) * n, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(&lev_sorted, sizeof(int32_t) * n, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(&d_level_ptr, sizeof(int32_t) * (n_levels + 1), stream);
+        if (e == cudaSuccess) e = phb_malloc_async(&lev, sizeof(int32_t) * n, stream);
+        if (e == cudaSuccess) e = phb_malloc_async(&row, sizeof(int32_t) * n, stream);
+        if (e == cudaSuccess) e = phb_malloc_async(&lev_sorted, sizeof(int32_t) * n, stream);
+        if (e == cudaSuccess) e = phb_malloc_async(&d_level_ptr, sizeof(int32_t) * (n_levels + 1), stream);
         if (e != cudaSuccess) { set_error("level analysis allocation failed: %s", cudaGetErrorString(e)); r = PHB200_ERR_CUDA; break; }
         k_star_levels<<<(unsigned)grid_x((n + kBlock - 1) / kBlock, 1), kBlock, 0, stream>>>(st, lower, lev, row);
         int bits = 1;
         while ((1ll << bits) < n_levels) ++bits;
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lev, lev_sorted, row, p->order, (int)n, 0, bits, stream);
-        if (cudaMallocAsync(&tmp, tmp_bytes, stream) != cudaSuccess) { set_error("sort scratch allocation failed"); r = PHB200_ERR_CUDA; break; }
+        if (phb_malloc_async(&tmp, tmp_bytes, stream) != cudaSuccess) { set_error("sort scratch allocation failed"); r = PHB200_ERR_CUDA; break; }
         cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lev, lev_sorted, row, p->order, (int)n, 0, bits, stream);   // stable: rows ascending inside a level
         k_level_starts<<<(unsigned)((n_levels + 1 + kBlock - 1) / kBlock), kBlock, 0, stream>>>(lev_sorted, n, (int32_t)n_levels, d_level_ptr);
         g_launches.fetch_add(4);
@@ -597,7 +597,7 @@ static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t
     PHB_CUDA(cudaMalloc(&p->rd, sizeof(T) * (size_t)p->n));
     PHB_CUDA(cudaMalloc(&p->tr_ticket, sizeof(unsigned)));
     PHB_CUDA(cudaMemsetAsync(p->tr_ticket, 0, sizeof(unsigned), stream));
-    PHB_CUDA(cudaMallocAsync(&d_ok, sizeof(int), stream));
+    PHB_CUDA(phb_malloc_async(&d_ok, sizeof(int), stream));
     int one = 1;
     PHB_CUDA(cudaMemcpyAsync(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
     PHB_LAUNCH(k_star_ilu_check<T>, (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1), kBlock, 0, stream, p->lu, (const T*)p->lu.val, p->diag_pos, st, (T*)p->rd, d_ok);
@@ -713,7 +713,7 @@ int phb200_jacobi_setup(const phb200_matrix* A, void* inv_diag, void* stream_) {
     }
     // the diagonal of A^T is the diagonal of A, so transposed views need no special case
     int* d_missing = nullptr;
-    PHB_CUDA(cudaMallocAsync(&d_missing, sizeof(int), stream));
+    PHB_CUDA(phb_malloc_async(&d_missing, sizeof(int), stream));
     PHB_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int), stream));
     if (A->dtype == PHB200_F32) PHB_LAUNCH(k_jacobi_csr<float>, gridx, kBlock, 0, stream, A->csr, (float*)inv_diag, d_missing);
     else PHB_LAUNCH(k_jacobi_csr<double>, gridx, kBlock, 0, stream, A->csr, (double*)inv_diag, d_missing);
@@ -767,7 +767,7 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
     int* d_missing = nullptr;
     do {
         if (cudaMalloc(&p->diag_pos, sizeof(int32_t) * (p->n > 0 ? p->n : 1)) != cudaSuccess) { set_error("cudaMalloc failed"); r = PHB200_ERR_CUDA; break; }
-        if (cudaMallocAsync(&d_missing, sizeof(int), stream) != cudaSuccess) { set_error("cudaMallocAsync failed"); r = PHB200_ERR_CUDA; break; }
+        if (phb_malloc_async(&d_missing, sizeof(int), stream) != cudaSuccess) { set_error("cudaMallocAsync failed"); r = PHB200_ERR_CUDA; break; }
         cudaMemsetAsync(d_missing, 0, sizeof(int), stream);
         if (lu_val != A->csr.val) cudaMemcpyAsync(lu_val, A->csr.val, w * A->nnz, cudaMemcpyDeviceToDevice, stream);
         const unsigned gridx = (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1);
@@ -893,16 +893,16 @@ int phb200_csr_transpose(const int32_t* rowptr, const int32_t* col, const void* 
     void* tmp = nullptr;
     int r = PHB200_OK;
     do {
-        cudaError_t e = cudaMallocAsync(&iota, sizeof(int32_t) * (size_t)nnz, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(&keys, sizeof(int32_t) * (size_t)nnz, stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(&perm, sizeof(int32_t) * (size_t)nnz, stream);
+        cudaError_t e = phb_malloc_async(&iota, sizeof(int32_t) * (size_t)nnz, stream);
+        if (e == cudaSuccess) e = phb_malloc_async(&keys, sizeof(int32_t) * (size_t)nnz, stream);
+        if (e == cudaSuccess) e = phb_malloc_async(&perm, sizeof(int32_t) * (size_t)nnz, stream);
         if (e != cudaSuccess) { set_error("transposition scratch allocation failed: %s", cudaGetErrorString(e)); r = PHB200_ERR_CUDA; break; }
         k_iota<<<(unsigned)grid_x((nnz + kBlock - 1) / kBlock, 1), kBlock, 0, stream>>>(iota, nnz);
         int bits = 1;
         while ((1ll << bits) < n_cols) ++bits;
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, col, keys, iota, perm, (int)nnz, 0, bits, stream);
-        if (cudaMallocAsync(&tmp, tmp_bytes, stream) != cudaSuccess) { set_error("sort scratch allocation failed"); r = PHB200_ERR_CUDA; break; }
+        if (phb_malloc_async(&tmp, tmp_bytes, stream) != cudaSuccess) { set_error("sort scratch allocation failed"); r = PHB200_ERR_CUDA; break; }
         cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, col, keys, iota, perm, (int)nnz, 0, bits, stream);   // stable: rows ascending inside a column
         k_level_starts<<<(unsigned)((n_cols + 1 + kBlock - 1) / kBlock), kBlock, 0, stream>>>(keys, nnz, (int32_t)n_cols, t_rowptr);
         const unsigned grid = (unsigned)grid_x((nnz + kBlock - 1) / kBlock, 1);

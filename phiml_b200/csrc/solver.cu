@@ -1557,7 +1557,7 @@ static int run_resident(phb200_solver* s, int64_t cap, int cs, int lpc, size_t s
     a.cap = (int)(cap > 0x3fffffff ? 0x3fffffff : cap);
     a.lpc = lpc; a.cs = cs;
     int* d_out = nullptr;
-    PHB_CUDA(cudaMallocAsync(&d_out, 2 * sizeof(int), st));
+    PHB_CUDA(phb_malloc_async(&d_out, 2 * sizeof(int), st));
     int r = PHB200_OK;
     for (int round = 0; round < 64; ++round) {
         r = launch_resident<T>(s, a, smem, st);

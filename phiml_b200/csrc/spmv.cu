@@ -70,7 +70,7 @@ __global__ void k_csr_block_max(const int32_t* __restrict__ rowptr, int64_t n_ro
 int csr_analyse(const phb200_matrix* m, cudaStream_t stream) {
     if (m->analysed) return PHB200_OK;
     int* d = nullptr;
-    PHB_CUDA(cudaMallocAsync(&d, sizeof(int), stream));
+    PHB_CUDA(phb_malloc_async(&d, sizeof(int), stream));
     PHB_CUDA(cudaMemsetAsync(d, 0, sizeof(int), stream));
     int64_t chunks = (m->csr.n_rows + kCsrRows - 1) / kCsrRows;
     PHB_LAUNCH(k_csr_block_max, (unsigned)((chunks + 255) / 256), 256, 0, stream, m->csr.rowptr, m->csr.n_rows, d);
@@ -365,7 +365,7 @@ int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int r
     int r = make_stencil(&cand, rank, grid, npts, offs, coef, csr->dtype);
     if (r != PHB200_OK) return PHB200_ERR_NOT_STENCIL;
     int* d_flag = nullptr;
-    PHB_CUDA(cudaMallocAsync(&d_flag, sizeof(int), stream));
+    PHB_CUDA(phb_malloc_async(&d_flag, sizeof(int), stream));
     PHB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), stream));
     const unsigned gridx = (unsigned)grid_x((n + kBlock - 1) / kBlock, 1);
     if (csr->dtype == PHB200_F32) PHB_LAUNCH(k_stencil_verify<float>, gridx, kBlock, 0, stream, cand->st, csr->csr, d_flag);
@@ -405,12 +405,12 @@ int phb200_stencil_to_csr(const phb200_matrix* m, int32_t* rowptr, int32_t* col,
     const int64_t n = m->n_rows;
     const unsigned gridx = (unsigned)grid_x((n + kBlock) / kBlock, 1);
     int32_t* counts = nullptr;
-    PHB_CUDA(cudaMallocAsync(&counts, (n + 1) * sizeof(int32_t), stream));
+    PHB_CUDA(phb_malloc_async(&counts, (n + 1) * sizeof(int32_t), stream));
     PHB_LAUNCH(k_stencil_count, gridx, kBlock, 0, stream, m->st, n, counts);
     size_t tmp_bytes = 0;
     PHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, rowptr, (int)(n + 1), stream));
     void* tmp = nullptr;
-    PHB_CUDA(cudaMallocAsync(&tmp, tmp_bytes, stream));
+    PHB_CUDA(phb_malloc_async(&tmp, tmp_bytes, stream));
     PHB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, rowptr, (int)(n + 1), stream));
     g_launches.fetch_add(2);
     if (m->dtype == PHB200_F32) PHB_LAUNCH(k_stencil_fill<float>, gridx, kBlock, 0, stream, m->st, n, rowptr, col, (float*)val);
