@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TB = tile_bytes<T>();
     constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
-    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // 128-byte aligned start inside the dynamic window, by pointer arithmetic on the shared array (an integer round trip makes
+    // the compiler forget the address space: every tile access became a generic LD.E / ST.E with 64-bit address arithmetic)
+    unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)(2 * kStages + 4) * TB);
 
     const int b = blockIdx.y;
@@ -287,7 +289,9 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
     constexpr int TB = tile_bytes<T>();
     constexpr int S = kSpStages;
     constexpr uint32_t kTx = (uint32_t)(SROWS * SROW * sizeof(T));
-    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // 128-byte aligned start inside the dynamic window, by pointer arithmetic on the shared array (an integer round trip makes
+    // the compiler forget the address space: every tile access became a generic LD.E / ST.E with 64-bit address arithmetic)
+    unsigned char* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)S * TB);
     const int b = blockIdx.y;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
