@@ -99,13 +99,14 @@ def cpu_iterations_per_second(n, warmup, steps):
     a = cpu_poisson_csr(n)
     y = np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32)
     trace = TimedTrace()
-    total = warmup + steps
+    w = max(1, warmup)            # the trace is stamped at the END of every iteration: the timed region starts at the end of iteration w
+    total = w + steps
     krylov.cg(a, y, np.zeros_like(y), np.float32([1e-5]), np.float32([0]), np.array([[total]]), precond.Jacobi(a), trace=trace)
     ts = [t['t'] for t in trace]
     done = len(ts)
-    w = min(warmup, max(0, done - 2))
-    its = done - 1 - w
-    dt = ts[-1] - ts[w]
+    w = min(w, max(1, done - 1))
+    its = done - w                # == steps unless the solve converged earlier
+    dt = ts[-1] - ts[w - 1]
     return its / dt, its, dt
 
 
@@ -173,7 +174,7 @@ def run_ours(args):
     import torch.distributed as dist
     import phiml_b200 as pb
     from phiml_b200 import _engine as E
-    from oracle.assemble import laplace_shifts
+    from phiml_b200 import stencils
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -186,7 +187,7 @@ def run_ours(args):
 
     n, N = args.n, args.n ** 3
     w = 4
-    shifts = laplace_shifts(3)
+    shifts = stencils.neg_laplace_pairs(3)
     stencil = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [c for _, c in shifts], torch.float32, dev)
     too_big_for_csr = stencil.nnz() >= 2 ** 31      # int32 CSR (the reference's native) cannot hold it: stencil handle only
     if too_big_for_csr:
@@ -381,7 +382,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps = min(args.steps, 40)
-    warm = min(args.warmup, 5)
+    warm = max(1, min(args.warmup, 5))
     t0 = time.perf_counter()
     v, its, dt = cpu_iterations_per_second(args.n, warm, steps)
     out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": its, "warmup": warm, "ms_per_step": dt / its * 1e3,

@@ -8,8 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import phiml_b200 as pb
-from oracle.assemble import laplace_shifts, advdiff_shifts
-from _cases import ADVDIFF
+from phiml_b200 import stencils
+ADVDIFF = stencils.ADVDIFF
 
 p = argparse.ArgumentParser()
 p.add_argument('configs', nargs='*', default=['cfg1', 'cfg3', 'cfg4', 'cfg5'])
@@ -36,14 +36,14 @@ def timed(fn, reps=2):
 
 for cfg in a.configs:
     if cfg == 'cfg1':   # 2-D 128x128 CG fp64 (reference: 488 iterations at default tolerances, 0.14-0.19 s on the CPU)
-        st = stencil((128, 128), laplace_shifts(2), torch.float64)
+        st = stencil((128, 128), stencils.neg_laplace_pairs(2), torch.float64)
         y = torch.as_tensor(np.random.default_rng(0).standard_normal((1, 128 * 128)), device=dev)
         res, dt = timed(lambda: pb.generic_conjugate_gradient(st, y, torch.zeros_like(y), [1e-12], [1e-12], np.array([[5000]])))
         print(json.dumps({"config": "cfg1 2D 128^2 CG fp64 default tol", "iterations": res.iterations.tolist(), "reference_iterations": 488, "seconds": dt,
                           "iterations_per_s": float(res.iterations.max()) / dt}))
     elif cfg == 'cfg3':  # batch x 128^2 fp32 CG, shared matrix (reference B=4096: 384 s, per-system iterations 236..299)
         B = a.batch
-        st = stencil((128, 128), laplace_shifts(2), torch.float32)
+        st = stencil((128, 128), stencils.neg_laplace_pairs(2), torch.float32)
         y = torch.as_tensor(np.random.default_rng(0).standard_normal((B, 128 * 128)).astype(np.float32), device=dev)
         res, dt = timed(lambda: pb.generic_conjugate_gradient(st, y, torch.zeros_like(y), [1e-5] * B, [0.0] * B, np.full((1, B), 5000)))
         its = res.iterations.cpu().numpy()
@@ -53,7 +53,7 @@ for cfg in a.configs:
                           "gbs_survey_model_13SNw": 13 * B * N * 4 * float(its.max()) / dt / 1e9}))
     elif cfg == 'cfg4':  # ILU(0)-CG fp32 (reference at 128^3: 97 iterations, 40.5 s in the loop)
         n = a.n4
-        st = stencil((n, n, n), laplace_shifts(3), torch.float32)
+        st = stencil((n, n, n), stencils.neg_laplace_pairs(3), torch.float32)
         t0 = time.perf_counter(); csr = st.to_csr(); nat = torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape); m = pb.as_matrix(nat)
         torch.cuda.synchronize(); t1 = time.perf_counter()
         ilu = pb.IncompleteLU(m); torch.cuda.synchronize(); t2 = time.perf_counter()
@@ -63,7 +63,7 @@ for cfg in a.configs:
                           "assemble_s": t1 - t0, "factor_s": t2 - t1, "solve_s": dt, "iterations_per_s": float(res.iterations.max()) / dt}))
     elif cfg == 'cfg5':  # nonsymmetric advection-diffusion, biCG-stab(2) fp32
         n = a.n5
-        st = stencil((n, n, n), advdiff_shifts(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float32), torch.float32)
+        st = stencil((n, n, n), stencils.advection_diffusion_pairs(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float32), torch.float32)
         y = torch.as_tensor(np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32), device=dev)
         res, dt = timed(lambda: pb.linear_solve('biCG-stab(2)', st, y, torch.zeros_like(y), [1e-5], [0.0], np.array([[5000]]), None, None))
         r_true = float((y - st.matvec(res.x)).norm() / y.norm())

@@ -4,11 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import phiml_b200 as pb
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 
 dev = torch.device('cuda:0')
 n = 256; N = n ** 3
-shifts = laplace_shifts(3)
+shifts = stencils.neg_laplace_pairs(3)
 st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [float(c) for _, c in shifts], torch.float32, dev)
 csr = st.to_csr()
 native = torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape)

@@ -13,7 +13,7 @@ import numpy as np, torch, torch.distributed as dist
 import phiml_b200 as pb
 from phiml_b200 import solve as S
 from phiml_b200.multi_gpu import solve_sharded, shard_bounds
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 
 p = argparse.ArgumentParser()
 p.add_argument('--batch', type=int, default=4096)
@@ -26,7 +26,7 @@ torch.cuda.set_device(lr); dev = torch.device('cuda', lr)
 if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 n, B = a.n, a.batch
-sh = laplace_shifts(2)
+sh = stencils.neg_laplace_pairs(2)
 st = pb.Matrix.stencil_matrix((n, n), [s for s, _ in sh], [c for _, c in sh], torch.float32, dev)
 lo, hi = shard_bounds(B, world, rank)
 y_all = np.random.default_rng(0).standard_normal((B, n * n)).astype(np.float32)     # same data on every rank; each takes its shard

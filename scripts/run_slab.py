@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch, torch.distributed as dist
 import phiml_b200 as pb
 from phiml_b200.multi_gpu import SlabCG
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 
 p = argparse.ArgumentParser()
 p.add_argument('--size', dest='n', type=int, default=256)
@@ -27,7 +27,7 @@ torch.cuda.set_device(lr); dev = torch.device('cuda', lr)
 if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 n = a.n; grid = (n, n, n); plane = n * n
-shifts = laplace_shifts(3); offsets = [s for s, _ in shifts]; coeffs = [c for _, c in shifts]
+shifts = stencils.neg_laplace_pairs(3); offsets = [s for s, _ in shifts]; coeffs = [c for _, c in shifts]
 cg = SlabCG(grid, offsets, coeffs, torch.float32, jacobi=True, device=dev)
 gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
 out = {"n": n, "world": world, "all_reduce": "nccl" if a.nccl_reduce or world == 1 else "in-kernel, peer-memory mailboxes", "halo_exchange": "nccl send/recv" if a.nccl_halos or world == 1 else "peer-memory stores from the residual kernel (CUDA IPC)"}

@@ -14,8 +14,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch, torch.distributed as dist
 import phiml_b200 as pb
 from phiml_b200.multi_gpu import SlabSolver, slab_bounds
-from oracle.assemble import advdiff_shifts, laplace_shifts
-from _cases import ADVDIFF
+from phiml_b200 import stencils
+ADVDIFF = stencils.ADVDIFF
 
 p = argparse.ArgumentParser()
 p.add_argument('--size', dest='n', type=int, default=256)
@@ -31,7 +31,7 @@ torch.cuda.set_device(lr); dev = torch.device('cuda', lr)
 if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 n = a.n; grid = (n, n, n); plane = n * n
-shifts = advdiff_shifts(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float32) if a.op == 'advdiff' else laplace_shifts(3)
+shifts = stencils.advection_diffusion_pairs(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float32) if a.op == 'advdiff' else stencils.neg_laplace_pairs(3)
 offsets = [s for s, _ in shifts]; coeffs = [float(c) for _, c in shifts]
 sol = SlabSolver(grid, offsets, coeffs, torch.float32, method=a.method, jacobi=a.jacobi, device=dev)
 out = {"n": n, "world": world, "method": a.method, "op": a.op, "jacobi": a.jacobi}

@@ -3,11 +3,11 @@ sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
 import phiml_b200 as pb
 from phiml_b200 import _engine as E, solve as S
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 dev = torch.device("cuda", 0)
 S.RESIDENT['mode'] = 'never'
 n = 256
-sh = laplace_shifts(3)
+sh = stencils.neg_laplace_pairs(3)
 st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in sh], [float(c) for _, c in sh], torch.float32, dev)
 y = torch.as_tensor(np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32), device=dev)
 for method, code in (("CG (torch rules)", E.CG_TORCH), ("auto (torch rules)", E.CG_ADAPTIVE_TORCH), ("CG-adaptive (generic)", E.CG_ADAPTIVE)):

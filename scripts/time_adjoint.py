@@ -10,8 +10,8 @@ import numpy as np, torch
 import phiml_b200 as pb
 from phiml_b200 import adjoint
 from phiml_b200.sparse import plain_csr
-from oracle.assemble import advdiff_shifts
-from _cases import ADVDIFF
+from phiml_b200 import stencils
+ADVDIFF = stencils.ADVDIFF
 
 p = argparse.ArgumentParser()
 p.add_argument('--size', dest='n', type=int, default=256)
@@ -19,7 +19,7 @@ a = p.parse_args()
 dev = torch.device('cuda:0')
 n = a.n; N = n ** 3
 peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs', 6552.3) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6552.3
-shifts = advdiff_shifts(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float32)
+shifts = stencils.advection_diffusion_pairs(3, ADVDIFF['velocity'], ADVDIFF['c'], ADVDIFF['nu'], np.float32)
 st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [float(c) for _, c in shifts], torch.float32, dev)
 csr = st.to_csr()
 nat = torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape)

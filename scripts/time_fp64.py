@@ -5,11 +5,11 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import phiml_b200 as pb
 from phiml_b200 import _engine as E
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 dev = torch.device("cuda", 0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 for dt in (torch.float64, torch.float32):
-    sh = laplace_shifts(3)
+    sh = stencils.neg_laplace_pairs(3)
     st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in sh], [float(c) for _, c in sh], dt, dev)
     pre = pb.JacobiPreconditioner(st)
     y = torch.randn(1, n ** 3, device=dev, dtype=dt)

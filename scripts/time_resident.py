@@ -5,13 +5,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 import phiml_b200 as pb
 from phiml_b200 import _engine as E, solve as S
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 
 dev = torch.device('cuda', 0)
 
 
 def stencil(grid, dtype):
-    sh = laplace_shifts(len(grid))
+    sh = stencils.neg_laplace_pairs(len(grid))
     return pb.Matrix.stencil_matrix(grid, [s for s, _ in sh], [c for _, c in sh], dtype, dev)
 
 

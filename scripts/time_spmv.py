@@ -5,12 +5,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 import phiml_b200 as pb
 from phiml_b200 import _engine as E
-from oracle.assemble import laplace_shifts
+from phiml_b200 import stencils
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device('cuda:0'); N = n ** 3
-shifts = laplace_shifts(3)
+shifts = stencils.neg_laplace_pairs(3)
 st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [float(c) for _, c in shifts], torch.float32, dev)
 x = torch.randn((1, N), device=dev); y = torch.empty_like(x)
 for m in (st,) + ((st.to_csr(),) if 'csr' in sys.argv else ()):

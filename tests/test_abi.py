@@ -62,3 +62,18 @@ def test_missing_library_raises(tmp_path):
     from phiml_b200 import _engine as E
     with pytest.raises(E.EngineError):
         E.load(str(tmp_path / 'nope.so'))
+
+
+def test_workload_stencil_tables_equal_the_oracle_tables():
+    """bench.py / scripts take their operators from phiml_b200.stencils (product side); same points, order and coefficient bits
+    as the oracle's tables, which are pinned to the reference's assembly (tests/test_oracle_golden.py::test_assembly_bit_exact)."""
+    import numpy as np
+    from phiml_b200 import stencils
+    from oracle.assemble import advdiff_shifts, laplace_shifts
+    for rank in (1, 2, 3):
+        assert stencils.neg_laplace_pairs(rank) == [(s, float(c)) for s, c in laplace_shifts(rank)]
+        for dt in (np.float32, np.float64):
+            ours = stencils.advection_diffusion_pairs(rank, stencils.ADVDIFF['velocity'], stencils.ADVDIFF['c'], stencils.ADVDIFF['nu'], dt)
+            assert ours == [(s, float(c)) for s, c in advdiff_shifts(rank, (1.0, 0.5, 0.25), 0.3, 0.2, dt)]
+    from _cases import ADVDIFF
+    assert ADVDIFF == stencils.ADVDIFF
