@@ -883,7 +883,7 @@ int phb200_csr_transpose(const int32_t* rowptr, const int32_t* col, const void* 
                          int32_t* t_rowptr, int32_t* t_col, void* t_val, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PHB_ARG(rowptr && t_rowptr && (nnz == 0 || (col && val && t_col && t_val)), "null argument");
-    PHB_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && nnz <= 2147483647LL && n_cols <= 2147483646LL, "sizes out of range for int32 CSR");
+    PHB_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && nnz <= 2147483647LL && n_cols <= 2147483647LL - 2 * kBlock, "sizes out of range for int32 CSR");
     PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
     if (nnz == 0) {
         PHB_CUDA(cudaMemsetAsync(t_rowptr, 0, sizeof(int32_t) * (size_t)(n_cols + 1), stream));
