@@ -77,6 +77,17 @@ bool debug_sync();
 // Launch with programmatic dependent launch (PDL): the grid may become resident while the previous kernel of the stream is
 // still draining; the kernel orders itself behind it with griddepcontrol.wait (pdl_wait) before touching its results.
 bool pdl_enabled();
+// Optional L2 residency hint for the launches that go through PHB_LAUNCH_PDL (the two kernels of the fused CG iteration):
+// accesses inside [base, base + bytes) are marked persisting with probability `hit`, everything else streaming
+// (cudaLaunchAttributeAccessPolicyWindow).  base == nullptr: no hint.  Set by the solver when PHB200_L2_PERSIST=1 (experimental,
+// off by default: not measured yet); the window is q, which the stencil kernel writes and the residual kernel reads next.
+struct L2Window {
+    void* base;
+    size_t bytes;
+    float hit;
+};
+L2Window& l2_window();
+L2Window l2_persist_window(void* base, size_t bytes);
 #define PHB_LAUNCH_PDL(kernel, grid, block, smem, strm, ...)                                  \
     do {                                                                                        \
         cudaLaunchConfig_t _cfg = {};                                                           \
@@ -84,11 +95,25 @@ bool pdl_enabled();
         _cfg.blockDim = (block);                                                                \
         _cfg.dynamicSmemBytes = (smem);                                                         \
         _cfg.stream = (strm);                                                                   \
-        cudaLaunchAttribute _at[1];                                                             \
-        _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                         \
-        _at[0].val.programmaticStreamSerializationAllowed = 1;                                  \
+        cudaLaunchAttribute _at[2];                                                             \
+        unsigned _na = 0;                                                                       \
+        if (phb::pdl_enabled()) {                                                               \
+            _at[_na].id = cudaLaunchAttributeProgrammaticStreamSerialization;                   \
+            _at[_na].val.programmaticStreamSerializationAllowed = 1;                            \
+            ++_na;                                                                              \
+        }                                                                                       \
+        const phb::L2Window& _win = phb::l2_window();                                           \
+        if (_win.base) {                                                                        \
+            _at[_na].id = cudaLaunchAttributeAccessPolicyWindow;                                \
+            _at[_na].val.accessPolicyWindow.base_ptr = _win.base;                               \
+            _at[_na].val.accessPolicyWindow.num_bytes = _win.bytes;                             \
+            _at[_na].val.accessPolicyWindow.hitRatio = _win.hit;                                \
+            _at[_na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;             \
+            _at[_na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;             \
+            ++_na;                                                                              \
+        }                                                                                       \
         _cfg.attrs = _at;                                                                       \
-        _cfg.numAttrs = phb::pdl_enabled() ? 1 : 0;                                             \
+        _cfg.numAttrs = _na;                                                                    \
         cudaError_t _e = cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__);                        \
         phb::g_launches.fetch_add(1, std::memory_order_relaxed);                                \
         if (_e == cudaSuccess && phb::debug_sync()) _e = cudaStreamSynchronize(strm);           \

@@ -1087,8 +1087,12 @@ struct Run {
     }
     template <int PRE>
     int pass_cg_fused_t(T* X, T* R) {
-        PHB_TRY(fused_first<PRE>(X, R));
-        return phase_ordered(make_resid<PRE>(R), resid_order());
+        // experimental (PHB200_L2_PERSIST=1): keep q, written by the first half and read by the second, in the persisting part of L2
+        l2_window() = l2_persist_window(vec(1), sizeof(T) * (size_t)batch * (size_t)ld);
+        int r = fused_first<PRE>(X, R);
+        if (r == PHB200_OK) r = phase_ordered(make_resid<PRE>(R), resid_order());
+        l2_window() = L2Window{nullptr, 0, 0.f};
+        return r;
     }
     int fused_pre() const { return s->pre == PHB200_PRE_NONE ? 0 : (s->M->is_const ? 3 : 1); }
     // host-driven halves for the multi-GPU slab mode: all-reduce of s->totals between the steps (multi_gpu.py)

@@ -31,6 +31,38 @@ bool pdl_enabled() {
     return v == 1;
 }
 
+L2Window& l2_window() {
+    static thread_local L2Window w{nullptr, 0, 0.f};
+    return w;
+}
+
+// PHB200_L2_PERSIST=1 (experimental): sizes the persisting part of L2 once per device and returns the window for `bytes` at `base`;
+// {nullptr} when the option is off or the device has no persisting L2.
+L2Window l2_persist_window(void* base, size_t bytes) {
+    static int mode = -1;
+    static size_t carve = 0, max_window = 0;
+    if (mode < 0) {
+        const char* e = getenv("PHB200_L2_PERSIST");
+        mode = (e && e[0] == '1') ? 1 : 0;
+        if (mode) {
+            int dev = 0;
+            cudaDeviceProp prop;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                carve = (size_t)prop.persistingL2CacheMaxSize;
+                max_window = (size_t)prop.accessPolicyMaxWindowSize;
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); mode = 0; }
+            } else {
+                cudaGetLastError();
+                mode = 0;
+            }
+        }
+    }
+    if (!mode || !base || bytes == 0) return L2Window{nullptr, 0, 0.f};
+    const size_t win = bytes < max_window ? bytes : max_window;
+    const float hit = win <= carve ? 1.0f : (float)((double)carve / (double)win);
+    return L2Window{base, win, hit};
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
