@@ -212,6 +212,9 @@ int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, i
  * only keep the host's pass count).  Up to 8 ranks. */
 int phb200_solver_set_peer_reduce(phb200_solver* s, void* const* mailboxes, int world, int rank, void* stream);
 size_t phb200_peer_mailbox_bytes(int world, int64_t batch);
+/* With BOTH peer halos and the in-kernel all-reduce installed nothing of an iteration needs the host: enqueue n_iter whole
+ * iterations (dist_step 0, 1, 2 each) in one call — two kernels per iteration back to back on the stream. */
+int phb200_solver_dist_advance(phb200_solver* s, int n_iter, void* stream);
 int phb200_ipc_export(const void* dev_ptr, void* handle64 /* 64 bytes out */, int64_t* offset /* of dev_ptr inside its allocation */);
 int phb200_ipc_open(const void* handle64, void** base_ptr /* mapping of the peer's allocation */);
 int phb200_ipc_close(void* base_ptr);

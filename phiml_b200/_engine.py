@@ -45,6 +45,7 @@ SIGNATURES = {
     'phb200_solver_set_peer_halos': (c_int, [_P, _P, c_int64, _P, c_int64]),
     'phb200_solver_set_peer_reduce': (c_int, [_P, POINTER(c_void_p), c_int, c_int, _P]),
     'phb200_peer_mailbox_bytes': (c_size_t, [c_int, c_int64]),
+    'phb200_solver_dist_advance': (c_int, [_P, c_int, _P]),
     'phb200_ipc_export': (c_int, [_P, _P, POINTER(c_int64)]),
     'phb200_ipc_open': (c_int, [_P, _PP]),
     'phb200_ipc_close': (c_int, [_P]),

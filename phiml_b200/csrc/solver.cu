@@ -1849,6 +1849,21 @@ int phb200_solver_dist_step(phb200_solver* s, int step, void* stream_) {
     return make_run<double>(s, st).dist_step(step);
 }
 
+int phb200_solver_dist_advance(phb200_solver* s, int n_iter, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PHB_ARG(s && s->started && s->totals && !s->ar_cb, "solver not started in (step-driven) distributed mode");
+    PHB_ARG(s->peer_reduce && (s->peer_lo || s->peer_hi), "dist_advance needs the in-kernel all-reduce and the peer-memory halo stores (set_peer_reduce, set_peer_halos)");
+    PHB_ARG(n_iter >= 0, "n_iter must be >= 0");
+    if (!s->tma_ok) { set_error("distributed mode needs the TMA path (tensor map creation failed)"); return PHB200_ERR_UNSUPPORTED; }
+    for (int k = 0; k < n_iter; ++k) {
+        for (int step = 0; step < 3; ++step) {
+            const int r = s->dtype == PHB200_F32 ? make_run<float>(s, st).dist_step(step) : make_run<double>(s, st).dist_step(step);
+            if (r != PHB200_OK) return r;
+        }
+    }
+    return PHB200_OK;
+}
+
 int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream_) {
     PHB_ARG(s && s->started, "solver not started");
     PHB_ARG(!s->totals || s->ar_cb, "a step-driven distributed solver is advanced with phb200_solver_dist_step");

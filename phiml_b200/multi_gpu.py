@@ -165,6 +165,55 @@ class SlabCG:
     def _halo(self, ext: torch.Tensor):
         exchange_halo_planes(ext, self.nxl, self.plane, self.rank, self.world, self.group)
 
+    def begin(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, peer_halos: Optional[bool] = None, peer_reduce: Optional[bool] = None):
+        """Set-up of one solve: extended arrays, initial residual, tolerances, first halos, peer-memory mappings.  Follow with
+        ``iterate`` (any number of times) and ``finish``.  See ``solve`` for the arguments."""
+        eng = self.engine
+        use_peer = self.world > 1 and hasattr(eng, 'open_peer_halos') and (peer_halos is None or peer_halos)
+        if peer_halos and not use_peer and self.world > 1:
+            raise RuntimeError("this engine has no peer-memory halo exchange")
+        use_pr = self.world > 1 and self.world <= 8 and hasattr(eng, 'peer_reduce_cfg') and (peer_reduce is None or peer_reduce)
+        if hasattr(eng, 'peer_reduce_cfg'):
+            eng.peer_reduce_cfg = (self.rank, self.world, self.group) if use_pr else None
+        self.peer_reduce_active = use_pr
+        self._reduce = (lambda t: None) if use_pr else self._allreduce
+        y_ext, x_ext = self.extend(y_local), self.extend(x0_local)
+        self._halo(x_ext)                                   # A x0 needs the neighbours' boundary planes
+        eng.start(y_ext, x_ext, rtol, atol, max_iter)       # local sums of r.s, y.y, r.r -> eng.totals
+        self._reduce(eng.totals)
+        eng.step(10)                                        # tolerances, first progress check (identical on all ranks)
+        self._halo(eng.r)
+        self._halo(eng.d0)                                  # d_0 = M^-1 r_0 including the halo planes
+        if use_peer:
+            eng.open_peer_halos(self.rank, self.world, self.nxl, self.plane, self.group)
+        self.peer_halos_active = use_peer
+        self.iterations_enqueued = 0
+
+    def iterate(self, n: int):
+        """Enqueues ``n`` CG iterations.  With peer-memory halos AND the in-kernel all-reduce an iteration needs nothing from the
+        host: the engine queues all of them in one call (two kernels per iteration, no NCCL, no Python in between)."""
+        eng = self.engine
+        if self.peer_halos_active and self.peer_reduce_active and hasattr(eng, 'advance'):
+            eng.advance(n)
+        else:
+            for _ in range(n):
+                eng.step(0)                                 # d, x, q = A d, local d.q
+                self._reduce(eng.totals)
+                eng.step(1)                                 # alpha ; r -= alpha q, local r.M^-1 r
+                self._reduce(eng.totals)
+                eng.step(2)                                 # beta, delta, progress check
+                if not self.peer_halos_active:
+                    self._halo(eng.r)                       # (peer mode: step(1) already stored the planes at the neighbours)
+        self.iterations_enqueued += n
+
+    def finish(self):
+        eng = self.engine
+        eng.step(20)                                        # pending x += alpha d
+        its, fev, conv, div = eng.result()
+        if self.peer_halos_active or self.peer_reduce_active:
+            eng.close_peer_halos(self.group)
+        return self.interior(eng.x), self.interior(eng.r), its, fev, conv, div
+
     def solve(self, y_local: torch.Tensor, x0_local: torch.Tensor, rtol, atol, max_iter: int, poll_every: int = 16, fixed_iterations: Optional[int] = None,
               peer_halos: Optional[bool] = None, peer_reduce: Optional[bool] = None):
         """
@@ -176,45 +225,18 @@ class SlabCG:
         ``peer_reduce``: the kernels all-reduce their dot products themselves through mailboxes in peer memory (no NCCL call and no
         finalize launch inside the loop: an iteration is two kernels); default: whenever the engine supports it.
         """
-        eng = self.engine
-        use_peer = self.world > 1 and hasattr(eng, 'open_peer_halos') and (peer_halos is None or peer_halos)
-        if peer_halos and not use_peer and self.world > 1:
-            raise RuntimeError("this engine has no peer-memory halo exchange")
-        use_pr = self.world > 1 and self.world <= 8 and hasattr(eng, 'peer_reduce_cfg') and (peer_reduce is None or peer_reduce)
-        if hasattr(eng, 'peer_reduce_cfg'):
-            eng.peer_reduce_cfg = (self.rank, self.world, self.group) if use_pr else None
-        self.peer_reduce_active = use_pr
-        reduce_ = (lambda t: None) if use_pr else self._allreduce
-        y_ext, x_ext = self.extend(y_local), self.extend(x0_local)
-        self._halo(x_ext)                                   # A x0 needs the neighbours' boundary planes
-        eng.start(y_ext, x_ext, rtol, atol, max_iter)       # local sums of r.s, y.y, r.r -> eng.totals
-        reduce_(eng.totals)
-        eng.step(10)                                        # tolerances, first progress check (identical on all ranks)
-        self._halo(eng.r)
-        self._halo(eng.d0)                                  # d_0 = M^-1 r_0 including the halo planes
-        if use_peer:
-            eng.open_peer_halos(self.rank, self.world, self.nxl, self.plane, self.group)
-        self.peer_halos_active = use_peer
-        done = 0
+        self.begin(y_local, x0_local, rtol, atol, max_iter, peer_halos, peer_reduce)
         limit = fixed_iterations if fixed_iterations is not None else max_iter
+        done = 0
+        chunk = poll_every
         while done < limit:
-            n = min(poll_every, limit - done)
-            for _ in range(n):
-                eng.step(0)                                 # d, x, q = A d, local d.q
-                reduce_(eng.totals)
-                eng.step(1)                                 # alpha ; r -= alpha q, local r.M^-1 r
-                reduce_(eng.totals)
-                eng.step(2)                                 # beta, delta, progress check
-                if not use_peer:
-                    self._halo(eng.r)                       # (peer mode: step(1) already stored the planes at the neighbours)
+            n = min(chunk, limit - done)
+            self.iterate(n)
             done += n
-            if fixed_iterations is None and not eng.any_continue():
+            if fixed_iterations is None and not self.engine.any_continue():
                 break
-        eng.step(20)                                        # pending x += alpha d
-        its, fev, conv, div = eng.result()
-        if use_peer or use_pr:
-            eng.close_peer_halos(self.group)
-        return self.interior(eng.x), self.interior(eng.r), its, fev, conv, div
+            chunk = min(2 * chunk, 64)
+        return self.finish()
 
 
 class CudaSlabEngine:
@@ -281,6 +303,11 @@ class CudaSlabEngine:
     def step(self, code: int):
         E = self.E
         E.check(E.lib().phb200_solver_dist_step(self.solver._h, code, E.stream_ptr(self.x.device)))
+
+    def advance(self, n: int):
+        """n whole iterations in one library call (needs peer halos + in-kernel all-reduce)."""
+        E = self.E
+        E.check(E.lib().phb200_solver_dist_advance(self.solver._h, int(n), E.stream_ptr(self.x.device)))
 
     # --- fused halo exchange: map the neighbours' residual arrays (CUDA IPC) and let the residual kernel store into them ---
     def open_peer_halos(self, rank, world, nxl, plane, group=None):

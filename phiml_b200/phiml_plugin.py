@@ -42,7 +42,8 @@ class _IdentityCache:
         self.max_entries = max_entries
         self.hits = self.misses = 0
 
-    def get(self, obj, extra, make):
+    def get(self, obj, extra, make, pins=()):
+        """``pins``: objects whose ids are part of ``extra``; the entry holds them so that their ids cannot be recycled under it."""
         import weakref
         key = (id(obj), extra)
         hit = self._d.get(key)
@@ -57,7 +58,7 @@ class _IdentityCache:
             return value                      # not weak-referenceable: no caching
         if len(self._d) >= self.max_entries:
             self._d.pop(next(iter(self._d)))
-        self._d[key] = (ref, value)
+        self._d[key] = (ref, value, pins)
         return value
 
     def clear(self):
@@ -160,41 +161,48 @@ def install():
         """(object whose life time bounds the cache entry, key part) of a constant sparse matrix tensor, or (None, None).
         PhiML re-wraps the matrix tensor on every call (custom-gradient plumbing); the natives below the wrappers are stable."""
         if not getattr(matrix, 'available', False) or torch._C._get_tracing_state() is not None:
-            return None, None
+            return None, None, ()
         try:
             values = matrix._values._native
             indices = matrix._indices._native
             pointers = getattr(getattr(matrix, '_pointers', None), '_native', None)
         except AttributeError:
-            return None, None
+            return None, None, ()
         if isinstance(values, torch.Tensor) and values.requires_grad:
-            return None, None
+            return None, None, ()
         # which dims are compressed / how the coordinate columns are labelled distinguishes A from the transposed view the backward
         # pass builds by renaming dims over the SAME arrays (transpose_matrix, _optimize.py:823-833)
         layout = (repr(getattr(matrix, '_compressed_dims', None)), repr(getattr(matrix, '_uncompressed_dims', None)),
                   repr(getattr(matrix, '_dense_shape', None)), repr(matrix._indices.shape))
-        return values, (type(matrix).__name__, id(indices), id(pointers), repr(matrix.shape)) + layout
+        # in-place edits of the arrays (an optimizer step under no_grad, .copy_) bump torch's version counters: a stale native or
+        # stale factors must not be served for them
+        versions = tuple(getattr(t, '_version', None) for t in (values, indices, pointers))
+        return values, (type(matrix).__name__, id(indices), id(pointers), repr(matrix.shape), versions) + layout, (indices, pointers)
 
     def native_matrix(value, target_backend):
         """phiml.math._sparse.native_matrix with residency: one conversion / upload per live matrix and backend."""
-        obj, key = anchor(value)
+        obj, key, pins = anchor(value)
         if target_backend is None or obj is None:
             return original_native(value, target_backend)
-        return NATIVE_CACHE.get(obj, (target_backend.name,) + key, lambda: original_native(value, target_backend))
+        return NATIVE_CACHE.get(obj, (target_backend.name,) + key, lambda: original_native(value, target_backend), pins)
 
     def compute_preconditioner(method, matrix, rank_deficiency=0, target_backend=None, solver=None):
         from phiml.math._sparse import is_sparse
         cuda_torch = target_backend is TORCH and is_sparse(matrix) and torch.cuda.is_available() and str(TORCH.get_default_device().device_type).upper() == 'GPU'
+        if method == 'auto' and cuda_torch and solver not in ('direct', 'scipy-direct') and not (solver or '').startswith('scipy-'):
+            # the reference resolves 'auto' INSIDE its own function (_optimize.py:838-854: 'ilu' whenever the backend has sparse
+            # triangular solves, which the patched backend does) and would go on to its CPU sweeps; resolve it here instead
+            method = 'ilu'
         if method == 'jacobi':
             if not cuda_torch:
                 raise NotImplementedError("preconditioner='jacobi' is provided by phb200 for sparse matrices on the CUDA torch backend only")
             make = lambda: _precond.JacobiPreconditioner(native_matrix(matrix, TORCH))
-            obj, key = anchor(matrix)
-            return PRECOND_CACHE.get(obj, ('jacobi',) + key, make) if obj is not None else make()
+            obj, key, pins = anchor(matrix)
+            return PRECOND_CACHE.get(obj, ('jacobi',) + key, make, pins) if obj is not None else make()
         if method == 'ilu' and cuda_torch and not (solver or '').startswith('scipy-'):
             make = lambda: _precond.IncompleteLU(native_matrix(matrix, TORCH))
-            obj, key = anchor(matrix)
-            return PRECOND_CACHE.get(obj, ('ilu',) + key, make) if obj is not None else make()
+            obj, key, pins = anchor(matrix)
+            return PRECOND_CACHE.get(obj, ('ilu',) + key, make, pins) if obj is not None else make()
         return original_compute(method, matrix, rank_deficiency=rank_deficiency, target_backend=target_backend, solver=solver)
 
     TORCH.__class__ = B200TorchBackend

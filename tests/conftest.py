@@ -11,12 +11,13 @@ for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "reference: needs /root/reference (authoring container only)")
+    config.addinivalue_line("markers", "reference: needs a copy of the reference (baseline/_ref or /root/reference)")
 
 
 def pytest_collection_modifyitems(config, items):
-    have_ref = os.path.isdir('/root/reference/phiml')
-    skip_ref = pytest.mark.skip(reason="/root/reference not present")
+    from _phiml import reference_path
+    have_ref = reference_path() is not None
+    skip_ref = pytest.mark.skip(reason="no copy of the reference (baseline/_ref or /root/reference)")
     for item in items:
         if 'reference' in item.keywords and not have_ref:
             item.add_marker(skip_ref)

@@ -167,24 +167,95 @@ def golden_ilu(out):
 
 
 def golden_frontend(out):
-    """A few results through the full math.solve_linear front end (named dims, SolveTape, exceptions)."""
+    """Results through the full math.solve_linear front end (named dims, SolveTape, exceptions) on the reference's own backends."""
+    from phiml.math import NotConverged
     f = math.jit_compile_linear(neg_laplace)
+    f_adv = math.jit_compile_linear(advdiff)
+
+    def record(key, x, info, order):
+        out[key + '/x'] = x.numpy(order)
+        out[key + '/iterations'] = info.iterations.numpy(order.split(',')[0]) if order.startswith('b') else np.asarray(info.iterations.numpy())
+        out[key + '/function_evaluations'] = info.function_evaluations.numpy(order.split(',')[0]) if order.startswith('b') else np.asarray(info.function_evaluations.numpy())
+        out[key + '/method'] = info.method
+        print(key, info.method, out[key + '/iterations'], out[key + '/function_evaluations'])
+
     for backend_name in ('numpy', 'torch'):
         backend = get_backend(backend_name)
         with backend, math.precision(32):
             rng = np.random.default_rng(0)
             y = math.tensor(rng.standard_normal((3, 16, 16)).astype(np.float32), batch('b'), spatial('x,y'))
             x0 = math.zeros(spatial(x=16, y=16))
-            solve = Solve('CG', 1e-5, 0, x0=x0, max_iterations=1000)
+            for tag, method in (('cg16', 'CG'), ('auto16', 'auto')):
+                solve = Solve(method, 1e-5, 0, x0=x0, max_iterations=1000)
+                with SolveTape() as tape:
+                    x = math.solve_linear(f, y, solve)
+                record(f"front/{backend_name}/{tag}", x, tape[solve], 'b,x,y')
+        with backend, math.precision(64):
+            rng = np.random.default_rng(5)
+            y = math.tensor(rng.standard_normal((2, 8, 6, 8)), batch('b'), spatial('x,y,z'))
+            x0 = math.zeros(spatial(x=8, y=6, z=8))
+            solve = Solve('biCG-stab(2)', 1e-10, 0, x0=x0, max_iterations=1000)
             with SolveTape() as tape:
+                x = math.solve_linear(f_adv, y, solve)
+            record(f"front/{backend_name}/bicg2_adv", x, tape[solve], 'b,x,y,z')
+    # preconditioned solves: only the NumPy backend has sparse triangular solves (Backend.solve_triangular_sparse)
+    with NUMPY:
+        for prec, rtol, dt in ((32, 1e-5, np.float32), (64, 1e-10, np.float64)):
+            with math.precision(prec):
+                rng = np.random.default_rng(0)
+                y = math.tensor(rng.standard_normal((3, 16, 16)).astype(dt), batch('b'), spatial('x,y'))
+                x0 = math.zeros(spatial(x=16, y=16))
+                for tag, pre in (('ilu16', 'ilu'), ('autopre16', 'auto')):
+                    solve = Solve('CG', rtol, 0, x0=x0, max_iterations=1000, preconditioner=pre)
+                    with SolveTape() as tape:
+                        x = math.solve_linear(f, y, solve)
+                    record(f"front/numpy/{tag}_f{prec}", x, tape[solve], 'b,x,y')
+                rng = np.random.default_rng(2)
+                y3 = math.tensor(rng.standard_normal((2, 8, 8, 8)).astype(dt), batch('b'), spatial('x,y,z'))
+                x03 = math.zeros(spatial(x=8, y=8, z=8))
+                solve = Solve('CG', rtol, 0, x0=x03, max_iterations=1000, preconditioner='ilu')
+                with SolveTape() as tape:
+                    x = math.solve_linear(f, y3, solve)
+                record(f"front/numpy/ilu8c_f{prec}", x, tape[solve], 'b,x,y,z')
+                # Jacobi has no name in the reference: its generic cg driven with the 5-line preconditioner object (SURVEY 8c)
+                m, csr, _, _ = build('poisson', (16, 16), dt)
+                yn = y.numpy('b,x,y').reshape(3, -1)
+                ret = NUMPY.linear_solve('CG', csr, yn, np.zeros_like(yn), np.full(3, rtol, dt), np.zeros(3, dt), np.full((1, 3), 1000), RefJacobi(csr), None)
+                key = f"front/numpy/jacobi16_f{prec}"
+                out[key + '/x'] = ret.x.reshape(3, 16, 16)
+                out[key + '/iterations'] = ret.iterations
+                out[key + '/function_evaluations'] = ret.function_evaluations
+                out[key + '/method'] = ret.method
+                print(key, ret.method, ret.iterations)
+        # trajectory recording (Backend.while_loop with one checkpoint per iteration, _backend.py:722-735)
+        with math.precision(64):
+            rng = np.random.default_rng(8)
+            y = math.tensor(rng.standard_normal((2, 12, 12)), batch('b'), spatial('x,y'))
+            x0 = math.zeros(spatial(x=12, y=12))
+            solve = Solve('CG', 1e-10, 0, x0=x0, max_iterations=60)
+            with SolveTape(record_trajectories=True) as tape:
                 x = math.solve_linear(f, y, solve)
             info = tape[solve]
-            key = f"front/{backend_name}/cg16"
-            out[key + '/x'] = x.numpy('b,x,y')
-            out[key + '/iterations'] = info.iterations.numpy('b')
-            out[key + '/function_evaluations'] = info.function_evaluations.numpy('b')
-            out[key + '/method'] = info.method
-            print(key, info.method, out[key + '/iterations'], out[key + '/function_evaluations'])
+            key = "front/numpy/trj12"
+            out[key + '/x'] = info.x.numpy('trajectory,b,x,y')
+            out[key + '/residual'] = info.residual.numpy('trajectory,b,x,y')
+            out[key + '/iterations'] = info.iterations.numpy('trajectory,b')
+            out[key + '/function_evaluations'] = info.function_evaluations.numpy('trajectory,b')
+            out[key + '/converged'] = info.converged.numpy('trajectory,b')
+            out[key + '/final_x'] = x.numpy('b,x,y')
+            print(key, out[key + '/x'].shape, out[key + '/iterations'][-1])
+        # failure semantics: max_iterations reached -> NotConverged with the partial result attached
+        with math.precision(32):
+            rng = np.random.default_rng(0)
+            y = math.tensor(rng.standard_normal((3, 16, 16)).astype(np.float32), batch('b'), spatial('x,y'))
+            solve = Solve('CG', 1e-5, 0, x0=math.zeros(spatial(x=16, y=16)), max_iterations=5)
+            try:
+                math.solve_linear(f, y, solve)
+                raise AssertionError("expected NotConverged")
+            except NotConverged as exc:
+                out["front/numpy/notconverged5/x"] = exc.result.x.numpy('b,x,y')
+                out["front/numpy/notconverged5/iterations"] = exc.result.iterations.numpy('b')
+                print("front/numpy/notconverged5", out["front/numpy/notconverged5/iterations"])
 
 
 def advdiff_k(x, k):

@@ -1,5 +1,5 @@
 """
-CPU suite, part 3 (authoring container only — needs /root/reference): the PhiML plug-in keeps the reference's own front end
+CPU suite, part 3 (needs a copy of the reference: baseline/_ref or /root/reference): the PhiML plug-in keeps the reference's own front end
 working and routes the path's calls to the phb200 boundary with the argument layout of SURVEY.md §8b.  The CUDA engine is
 replaced by the oracle HERE, in the test, to observe the plumbing without a GPU.
 """
@@ -13,9 +13,8 @@ pytestmark = pytest.mark.reference
 
 @pytest.fixture()
 def phiml_env():
-    if '/root/reference' not in sys.path:
-        sys.path.insert(0, '/root/reference')
-    import phiml  # noqa: F401
+    from _phiml import import_phiml
+    assert import_phiml() is not None
     from phiml_b200 import phiml_plugin
     torch_backend = phiml_plugin.install()
     yield phiml_plugin, torch_backend
