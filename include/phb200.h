@@ -21,7 +21,8 @@
  *                 (PHB200_BICGSTAB)    bicg / bicg_stab_first_order       phiml/backend/_linalg.py:131-274
  *                                      Backend.while_loop (device-side)   phiml/backend/_backend.py:697-735
  *   phb200_jacobi_setup                NEW ('jacobi' is absent from compute_preconditioner, phiml/math/_optimize.py:836-880)
- *   phb200_ilu0_*                      incomplete_lu_coo (its fixed point)phiml/backend/_linalg.py:524-594
+ *   phb200_precond_ilu_sweeps          incomplete_lu_coo                  phiml/backend/_linalg.py:524-594
+ *   phb200_precond_ilu0                its fixed point (exact ILU(0))
  *   phb200_sptrsv                      Backend.solve_triangular_sparse    phiml/backend/_backend.py:1580-1586, _numpy_backend.py:579-580
  */
 #ifndef PHB200_H
@@ -146,6 +147,15 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
  * If A was recognised as a star stencil, pass the stencil handle: the levels are then computed analytically on the
  * device instead of from a host copy of the pattern. */
 int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, const phb200_matrix* stencil_twin /* may be NULL */, void* stream);
+/* The reference's own ILU: `sweeps` Jacobi-style fixed-point sweeps on the stored pattern (incomplete_lu_coo,
+ * phiml/backend/_linalg.py:524-594; compute_preconditioner picks sweeps = ceil(sqrt(d n^(1/d))), d = (nnz/n - 1)/2,
+ * phiml/math/_optimize.py:855-869), i.e. the factors behind the reference's 'ilu (iter=k)'.  Every entry is an independent
+ * gather + multiply-add over the previous iterate, so a sweep is one embarrassingly parallel kernel.  `safe` != 0 uses
+ * divide_no_nan for the lower entries (rank-deficient matrices, _linalg.py:576).  lu_val must not alias A's values.
+ * Same handle, same solves as phb200_precond_ilu0; on a recognised star stencil the structured wavefront solves stay
+ * available (L is then described by the diagonal of the sweep before the last, U by the last one). */
+int phb200_precond_ilu_sweeps(phb200_precond** out, const phb200_matrix* A, void* lu_val, int sweeps, int safe,
+                              const phb200_matrix* stencil_twin /* may be NULL */, void* stream);
 /* *star_wavefront = 1 if the triangular solves of an ILU preconditioner run as the structured wavefront of
  * csrc/star_trsv.cuh (factors of a recognised star stencil; 3 N w bytes per solve) instead of the CSR level solves.
  * The environment variable PHB200_TRSV=csr disables the wavefront form at set-up. */
@@ -183,9 +193,14 @@ int phb200_solver_start(phb200_solver* s, const void* Y, const void* X0, void* X
                         const void* rtol, const void* atol, const int32_t* max_iter,
                         void* workspace, size_t workspace_bytes, void* stream);
 
-/* Batch sharding over several GPUs: the tolerance every system must reach is the minimum over the WHOLE batch
- * (phiml/backend/_linalg.py:26-29).  After start(): read the local minimum (set = 0, *tol_min is a device double),
- * all-reduce(min) it over the ranks, write it back (set = 1) — the first progress check is repeated with it. */
+/* Batch sharding over several GPUs (or a batch split over several solver objects): the tolerance every system must reach
+ * couples the WHOLE batch (phiml/backend/_linalg.py:26-29) — it is the minimum over all systems, and for the generic
+ * cg_adaptive / bicg loops it is relative to the SUM of |y_b|^2 over all systems (stop_on_l2 sums the (batch,) vector it
+ * receives once more).  `vals` is a device array of two doubles {tol_min, yy_sum}.  After start():
+ *   set = 0  read the local pair;
+ *   set = 2  install yy_sum summed over all shards: tolerances and the local minimum are recomputed (no-op for methods whose
+ *            tolerance is per system: PHB200_CG and the torch fast paths); read again afterwards;
+ *   set = 1  install tol_min reduced (min) over all shards — the first progress check is repeated with it. */
 int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream);
 
 /* Distributed (slab) mode: `totals` is a caller-owned device buffer of batch*4 doubles.  After set_dist, start() and every

@@ -143,6 +143,7 @@ struct Sys {
 
 struct Glob {
     double tol_min;    // minimum squared tolerance over the batch (the (batch,batch) broadcast of stop_on_l2)
+    double yy_sum;     // sum over the batch of |y_b|^2 (generic cg_adaptive / bicg: the reference's tolerance is relative to it)
     int any_go;        // 1 while at least one system iterates
     int checks;        // progress checks performed so far (0 -> first check semantics)
     int pass;          // loop passes executed (torch fast path: true-residual refresh every 20th pass)

@@ -467,6 +467,139 @@ static int ilu0_factor(const phb200_precond* p, cudaStream_t stream) {
     return PHB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- ILU fixed-point sweeps
+// incomplete_lu_coo (phiml/backend/_linalg.py:524-594; T.K. Huckle, "Parallel approximate LU factorizations"): Jacobi-style
+// sweeps on the stored pattern.  State lu: diagonal + strict upper = U, strict lower = L.
+//   init  (:555-556)   lu = A on the diagonal, A_ij / A_jj below it, 0 above
+//   sweep (:573-577)   s_ij = sum_{k < min(i,j)} L_ik U_kj  (entries present in the pattern, OLD values, ascending k — the order
+//                      in which strict_lu_mm_pattern_coo enumerates the matches; products and sums rounded separately)
+//                      lower: (A_ij - s_ij) / lu_old[j,j]   (divide_no_nan when `safe`);   else: A_ij - s_ij
+// All entries are updated simultaneously from the previous iterate, so two buffers alternate.  One thread per row; rows have
+// sorted columns, the partner entry (k, j) is found by bisection in row k's upper part.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_ilu_sweep_init(CsrView A, const int32_t* __restrict__ diag_pos, T* __restrict__ lu) {
+    const T* __restrict__ a = (const T*)A.val;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock) {
+        for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
+            const int j = A.col[p];
+            lu[p] = j == (int)i ? a[p] : (j < (int)i ? a[p] / a[diag_pos[j]] : T(0));
+        }
+    }
+}
+
+// Sum of the products in the order NumPy's einsum adds them (the reference computes s_ij with
+// einsum('bnkc,bnkc->bnc', ...) over K = half_density padded slots, _linalg.py:575): 128-bit SIMD lanes (V = 2 doubles / 4
+// floats; slot t goes to lane t mod V), whole groups of 4 vectors are chained last-to-first, the remaining vectors first-to-last,
+// then the lanes are added horizontally ((l0 + l1) + (l2 + l3)); multiply and add are rounded separately (no FMA in the SSE
+// baseline).  Reproducing the order makes the factors BIT-identical to the reference's (tests/test_gpu_parity.py checks
+// it against factors recorded from the reference).  Padded slots hold zero products and change nothing.
+constexpr int kIluMaxTerms = 32;
+template <typename T>
+__device__ __forceinline__ T einsum_order_sum(const T* pr, int cnt, int K) {
+    constexpr int V = sizeof(T) == 8 ? 2 : 4;
+    T lane[V];
+#pragma unroll
+    for (int l = 0; l < V; ++l) lane[l] = T(0);
+    const int nvec = (cnt + V - 1) / V;
+    const int full = (K / (4 * V)) * 4;
+    for (int g = 0; g < full && g < nvec; g += 4)
+        for (int v = g + 3; v >= g; --v) {
+            if (v >= nvec) continue;
+#pragma unroll
+            for (int l = 0; l < V; ++l) { const int t = v * V + l; if (t < cnt) lane[l] = add_rn(lane[l], pr[t]); }
+        }
+    for (int v = full; v < nvec; ++v) {
+#pragma unroll
+        for (int l = 0; l < V; ++l) { const int t = v * V + l; if (t < cnt) lane[l] = add_rn(lane[l], pr[t]); }
+    }
+    if constexpr (V == 2) return add_rn(lane[0], lane[1]);
+    else return add_rn(add_rn(lane[0], lane[1]), add_rn(lane[2], lane[3]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_ilu_sweep(CsrView A, const int32_t* __restrict__ diag_pos, const T* __restrict__ lu_old, T* __restrict__ lu_new, int safe, int K) {
+    const T* __restrict__ a = (const T*)A.val;
+    const int32_t* __restrict__ col = A.col;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock) {
+        const int beg = A.rowptr[i], end = A.rowptr[i + 1];
+        for (int p = beg; p < end; ++p) {
+            const int j = col[p];
+            const int m = j < (int)i ? j : (int)i;
+            T pr[kIluMaxTerms];
+            int cnt = 0;
+            T s_over = T(0);      // rows with more matches than kIluMaxTerms: the rest is added in ascending order
+            for (int q = beg; q < end; ++q) {
+                const int k = col[q];
+                if (k >= m) break;
+                int lo = diag_pos[k] + 1, hi = A.rowptr[k + 1];      // strict upper part of row k, sorted
+                const int rend = hi;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (col[mid] < j) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < rend && col[lo] == j) {
+                    const T prod = mul_rn(lu_old[lo], lu_old[q]);
+                    if (cnt < kIluMaxTerms) pr[cnt++] = prod;
+                    else s_over = add_rn(s_over, prod);
+                }
+            }
+            const T s = add_rn(einsum_order_sum<T>(pr, cnt, K), s_over);
+            const T rest = add_rn(a[p], -s);
+            if (j < (int)i) {
+                const T d = lu_old[diag_pos[j]];
+                lu_new[p] = (safe && d == T(0)) ? T(0) : rest / d;
+            } else {
+                lu_new[p] = rest;
+            }
+        }
+    }
+}
+
+// half_density of strict_lu_mm_pattern_coo (_linalg.py:617): max(strict-lower entries in a row, strict-upper entries in a column)
+__global__ void __launch_bounds__(kBlock) k_ilu_half_density(CsrView A, const int32_t* __restrict__ diag_pos, int32_t* __restrict__ col_upper, int* __restrict__ out, int phase) {
+    int best = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < A.n_rows; i += (int64_t)gridDim.x * kBlock) {
+        if (phase == 0) {
+            const int lower = diag_pos[i] - A.rowptr[i];
+            if (lower > best) best = lower;
+            for (int p = diag_pos[i] + 1; p < A.rowptr[i + 1]; ++p) atomicAdd(&col_upper[A.col[p]], 1);
+        } else if (col_upper[i] > best) {
+            best = col_upper[i];
+        }
+    }
+    if (best > 0) atomicMax(out, best);
+}
+
+// returns the iterate before the last sweep in *prev (pool memory, caller frees with cudaFreeAsync) — the star check needs it
+template <typename T>
+static int ilu_sweeps_factor(const phb200_precond* p, const CsrView& A, int sweeps, int safe, T** prev, cudaStream_t stream) {
+    T* out = (T*)p->lu.val;
+    T* tmp = nullptr;
+    int32_t* col_upper = nullptr;
+    int* d_k = nullptr;
+    PHB_CUDA(phb_malloc_async(&tmp, sizeof(T) * (size_t)(A.nnz > 0 ? A.nnz : 1), stream));
+    *prev = tmp;
+    const unsigned grid = (unsigned)grid_x((A.n_rows + kBlock - 1) / kBlock, 1);
+    PHB_CUDA(phb_malloc_async(&col_upper, sizeof(int32_t) * (size_t)(A.n_rows > 0 ? A.n_rows : 1), stream));
+    PHB_CUDA(phb_malloc_async(&d_k, sizeof(int), stream));
+    PHB_CUDA(cudaMemsetAsync(col_upper, 0, sizeof(int32_t) * (size_t)(A.n_rows > 0 ? A.n_rows : 1), stream));
+    PHB_CUDA(cudaMemsetAsync(d_k, 0, sizeof(int), stream));
+    PHB_LAUNCH(k_ilu_half_density, grid, kBlock, 0, stream, A, p->diag_pos, col_upper, d_k, 0);
+    PHB_LAUNCH(k_ilu_half_density, grid, kBlock, 0, stream, A, p->diag_pos, col_upper, d_k, 1);
+    int K = 0;
+    PHB_CUDA(cudaMemcpyAsync(&K, d_k, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    PHB_CUDA(cudaFreeAsync(col_upper, stream));
+    PHB_CUDA(cudaFreeAsync(d_k, stream));
+    // the last sweep must write `out`: sweep s (1-based) writes buf[(sweeps - s) & 1], the initial state sits in buf[sweeps & 1]
+    T* buf[2] = {out, tmp};
+    PHB_LAUNCH(k_ilu_sweep_init<T>, grid, kBlock, 0, stream, A, p->diag_pos, buf[sweeps & 1]);
+    for (int s = 1; s <= sweeps; ++s)
+        PHB_LAUNCH(k_ilu_sweep<T>, grid, kBlock, 0, stream, A, p->diag_pos, (const T*)buf[(sweeps - s + 1) & 1], buf[(sweeps - s) & 1], safe, K);
+    return PHB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- star wavefront solves
 template <typename T, bool LOWER>
 static int star_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, int64_t ld, cudaStream_t stream) {
@@ -481,7 +614,7 @@ static int star_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     a.nch = (a.nz + kTrZC - 1) / kTrZC;
     a.batch = (int)batch;
     a.ld = ld;
-    a.rd = p->rd;
+    a.rd = LOWER ? p->rd_l : p->rd;
     a.B = B;
     a.X = X;
     const int64_t need = batch * a.nsx * a.nsy;
@@ -524,7 +657,7 @@ static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     a.nch = (a.nz + kScZ - 1) / kScZ;
     a.batch = (int)batch;
     a.ld = ld;
-    a.rd = p->rd;
+    a.rd = LOWER ? p->rd_l : p->rd;
     a.B = B;
     a.X = X;
     const int64_t need = batch * a.ni * a.nj;
@@ -584,7 +717,7 @@ static int scan_order_setup(phb200_precond* p, const StarDesc& st, cudaStream_t 
 }
 
 template <typename T>
-static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t stream) {
+static int star_setup(phb200_precond* p, const phb200_matrix* twin, const T* lu_prev, cudaStream_t stream) {
     const StarDesc& st = twin->star;
     // closed form needs distinct, non-aliasing offsets: nz >= 4 (star kernels need nz % 4 == 0 anyway), ny != 2 in 3-D
     if (st.nz < 4 || st.nz % 4 != 0) return PHB200_OK;
@@ -595,12 +728,15 @@ static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t
     if (e && (strcmp(e, "levels") == 0 || strcmp(e, "csr") == 0)) return PHB200_OK;
     int* d_ok = nullptr;
     PHB_CUDA(cudaMalloc(&p->rd, sizeof(T) * (size_t)p->n));
+    p->rd_l = p->rd;
+    if (lu_prev) PHB_CUDA(cudaMalloc(&p->rd_l, sizeof(T) * (size_t)p->n));
     PHB_CUDA(cudaMalloc(&p->tr_ticket, sizeof(unsigned)));
     PHB_CUDA(cudaMemsetAsync(p->tr_ticket, 0, sizeof(unsigned), stream));
     PHB_CUDA(phb_malloc_async(&d_ok, sizeof(int), stream));
     int one = 1;
     PHB_CUDA(cudaMemcpyAsync(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
-    PHB_LAUNCH(k_star_ilu_check<T>, (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1), kBlock, 0, stream, p->lu, (const T*)p->lu.val, p->diag_pos, st, (T*)p->rd, d_ok);
+    PHB_LAUNCH(k_star_ilu_check<T>, (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1), kBlock, 0, stream, p->lu, (const T*)p->lu.val, lu_prev ? lu_prev : (const T*)p->lu.val,
+               p->diag_pos, st, (T*)p->rd, (T*)p->rd_l, d_ok);
     int ok = 0;
     PHB_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, stream));
     PHB_CUDA(cudaStreamSynchronize(stream));
@@ -610,8 +746,9 @@ static int star_setup(phb200_precond* p, const phb200_matrix* twin, cudaStream_t
         p->star_mode = (e && strcmp(e, "skew") == 0) ? 1 : ((e && strcmp(e, "flow") == 0) ? 3 : 2);
         if (p->star_mode >= 2) PHB_TRY(scan_order_setup(p, st, stream));
     } else {
+        if (p->rd_l != p->rd) cudaFree(p->rd_l);
         cudaFree(p->rd);
-        p->rd = nullptr;
+        p->rd = p->rd_l = nullptr;
     }
     return PHB200_OK;
 }
@@ -750,11 +887,11 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
     return PHB200_OK;
 }
 
-int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, const phb200_matrix* stencil_twin, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+static int ilu_create(phb200_precond** out, const phb200_matrix* A, void* lu_val, int sweeps, int safe, const phb200_matrix* stencil_twin, cudaStream_t stream) {
     PHB_ARG(out && A && lu_val, "null argument");
     PHB_ARG(A->kind == PHB200_MAT_CSR && !A->transposed, "ILU(0) needs a plain CSR matrix");
     PHB_ARG(A->n_rows == A->n_cols, "incomplete_lu_coo only implemented for square matrices");
+    PHB_ARG(lu_val != A->csr.val || sweeps < 0, "the sweeps read the matrix values: lu_val must not alias them");
     const size_t w = A->dtype == PHB200_F32 ? 4 : 8;
     phb200_precond* p = new phb200_precond();
     memset(p, 0, sizeof(*p));
@@ -763,13 +900,15 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
     p->n = A->n_rows;
     p->lu = A->csr;
     p->lu.val = lu_val;
+    p->sweeps = sweeps;
     int r = PHB200_OK;
     int* d_missing = nullptr;
+    void* prev = nullptr;
     do {
         if (cudaMalloc(&p->diag_pos, sizeof(int32_t) * (p->n > 0 ? p->n : 1)) != cudaSuccess) { set_error("cudaMalloc failed"); r = PHB200_ERR_CUDA; break; }
         if (phb_malloc_async(&d_missing, sizeof(int), stream) != cudaSuccess) { set_error("cudaMallocAsync failed"); r = PHB200_ERR_CUDA; break; }
         cudaMemsetAsync(d_missing, 0, sizeof(int), stream);
-        if (lu_val != A->csr.val) cudaMemcpyAsync(lu_val, A->csr.val, w * A->nnz, cudaMemcpyDeviceToDevice, stream);
+        if (sweeps < 0 && lu_val != A->csr.val) cudaMemcpyAsync(lu_val, A->csr.val, w * A->nnz, cudaMemcpyDeviceToDevice, stream);
         const unsigned gridx = (unsigned)grid_x((p->n + kBlock - 1) / kBlock, 1);
         if (A->dtype == PHB200_F32) k_diag_pos<float><<<gridx, kBlock, 0, stream>>>(A->csr, p->diag_pos, d_missing);
         else k_diag_pos<double><<<gridx, kBlock, 0, stream>>>(A->csr, p->diag_pos, d_missing);
@@ -784,17 +923,31 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
         if (r != PHB200_OK) break;
         r = star ? build_plan_star(&p->plan_u, stencil_twin->star, 0, stream) : build_plan(&p->plan_u, A->csr, 0, stream);
         if (r != PHB200_OK) break;
-        r = A->dtype == PHB200_F32 ? ilu0_factor<float>(p, stream) : ilu0_factor<double>(p, stream);
+        if (sweeps < 0) {
+            r = A->dtype == PHB200_F32 ? ilu0_factor<float>(p, stream) : ilu0_factor<double>(p, stream);
+        } else {
+            r = A->dtype == PHB200_F32 ? ilu_sweeps_factor<float>(p, A->csr, sweeps, safe, (float**)&prev, stream) : ilu_sweeps_factor<double>(p, A->csr, sweeps, safe, (double**)&prev, stream);
+        }
         if (r != PHB200_OK) break;
-        if (star) r = A->dtype == PHB200_F32 ? star_setup<float>(p, stencil_twin, stream) : star_setup<double>(p, stencil_twin, stream);
+        if (star) r = A->dtype == PHB200_F32 ? star_setup<float>(p, stencil_twin, (const float*)prev, stream) : star_setup<double>(p, stencil_twin, (const double*)prev, stream);
     } while (0);
     if (d_missing) cudaFreeAsync(d_missing, stream);
+    if (prev) cudaFreeAsync(prev, stream);
     if (r != PHB200_OK) {
         phb200_precond_destroy(p);
         return r;
     }
     *out = p;
     return PHB200_OK;
+}
+
+int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_val, const phb200_matrix* stencil_twin, void* stream_) {
+    return ilu_create(out, A, lu_val, -1, 0, stencil_twin, (cudaStream_t)stream_);
+}
+
+int phb200_precond_ilu_sweeps(phb200_precond** out, const phb200_matrix* A, void* lu_val, int sweeps, int safe, const phb200_matrix* stencil_twin, void* stream_) {
+    PHB_ARG(sweeps >= 1, "incomplete_lu_coo needs at least one sweep, got %d", sweeps);
+    return ilu_create(out, A, lu_val, sweeps, safe ? 1 : 0, stencil_twin, (cudaStream_t)stream_);
 }
 
 int phb200_precond_info(const phb200_precond* p, int* kind, int* star_wavefront) {
@@ -869,6 +1022,7 @@ int phb200_precond_apply(const phb200_precond* p, const void* in, void* out, int
 int phb200_precond_destroy(phb200_precond* p) {
     if (!p) return PHB200_OK;
     if (p->diag_pos) cudaFree(p->diag_pos);
+    if (p->rd_l && p->rd_l != p->rd) cudaFree(p->rd_l);
     if (p->rd) cudaFree(p->rd);
     if (p->tr_flags) cudaFree(p->tr_flags);
     if (p->tr_ticket) cudaFree(p->tr_ticket);

@@ -37,6 +37,9 @@ struct phb200_precond {
     int32_t* sc_order;                 // device, owned: tiles of the row-scan kernel in dependency (anti-diagonal) order
     phb::StarDesc star;
     void* rd;                          // device, owned: 1 / U_ii
+    void* rd_l;                        // device: reciprocal pivots that define L (L_ik = A_ik rd_l[k]); == rd for the exact factors,
+                                       // owned and distinct for fixed-point sweeps (there L lags the diagonal by one sweep)
+    int sweeps;                        // -1: exact ILU(0); k >= 1: k fixed-point sweeps of incomplete_lu_coo
     unsigned long long* tr_flags;      // device, owned
     int64_t tr_flag_cap;               // counters allocated
     unsigned* tr_ticket;               // device, owned

@@ -10,6 +10,7 @@
 #include <vector>
 #include <mutex>
 #include <stdlib.h>
+#include <stddef.h>
 
 namespace phb {
 
@@ -33,6 +34,17 @@ __device__ __forceinline__ void check_all(const FBase& f, int rules) {
     progress_check<T>(f.sys, f.glob, f.batch, rules == RULES_TORCH, f.freeze != 0);
 }
 
+// tolerances of the batch-sum rule: tol_b = max(rtol_b^2 * sum_over_batch |y|^2, atol_b^2); all threads of one CTA
+template <typename T>
+__device__ __forceinline__ void apply_batch_sum(Sys* sys, int batch, const T* rtol, const T* atol, double yy_sum) {
+    const T norm = (T)yy_sum;
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+        const T rt = rtol[b], at = atol[b];
+        const T t1 = rt * rt * norm, t2 = at * at;
+        ((volatile Sys*)sys)[b].tol = (double)(t1 > t2 ? t1 : (t2 >= t1 ? t2 : (T)NAN));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ initial residual
 // r = y - q (q = A x0), s = M r, d = s.  Dots: r.s, y.y, r.r.  Sets up tolerances (minimum over the batch) and runs
 // the first progress check.  PRE: 0 none, 1 Jacobi (inv_diag), 2 external (r and s already computed).
@@ -51,6 +63,10 @@ struct InitResidual : FBase {
     int tol_from_y;    // 0: tolerance relative to |r0.M^-1 r0| and monitor r.M^-1 r (generic cg); 1: |y|^2 and r.r
     int rules;
     int bicg;
+    // generic cg_adaptive / bicg / bicg_stab_first_order hand stop_on_l2 the (batch,) vector sum(y**2, -1), which stop_on_l2 sums
+    // AGAIN over its last axis (phiml/backend/_linalg.py:26): the tolerance of every system is relative to the sum of |y_b|^2
+    // over the WHOLE batch.  (cg passes a (batch,1) array and the torch fast paths do their own per-system test.)
+    __device__ bool batch_sum_rule() const { return tol_from_y && rules == RULES_GENERIC; }
     struct Scal {};
     __device__ Scal load(int) const { return Scal{}; }
     __device__ void elem(T (&e)[NA], double (&acc)[ND], const Scal&) const {
@@ -90,6 +106,20 @@ struct InitResidual : FBase {
     }
     __device__ void finalize_all() const {
         __shared__ double s_min[kBlock];
+        {   // sum of |y_b|^2 over the batch (kept for batch sharding, where the sum runs over all ranks' systems)
+            double part = 0.0;
+            for (int b = threadIdx.x; b < batch; b += blockDim.x) part += ((volatile Sys*)sys)[b].s[S_YY];
+            s_min[threadIdx.x] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int k = 0; k < (int)blockDim.x; ++k) tot += s_min[k];
+                glob->yy_sum = tot;
+            }
+            __syncthreads();
+            if (batch_sum_rule()) apply_batch_sum(sys, batch, rtol, atol, ((volatile Glob*)glob)->yy_sum);
+            __syncthreads();
+        }
         double m = INFINITY;
         bool nan = false;
         for (int b = threadIdx.x; b < batch; b += blockDim.x) {
@@ -697,11 +727,39 @@ struct BiFinal2 : FBase {
     }
 };
 
-// multi-GPU batch sharding: install the batch-wide minimum tolerance and repeat the first progress check with it
+// multi-GPU batch sharding (or a batch split over several solver objects): mode 2 installs the sum of |y|^2 over ALL systems
+// (vals[1]), recomputes this shard's tolerances under the batch-sum rule and its local minimum; mode 1 installs the batch-wide
+// minimum tolerance (vals[0]) and repeats the first progress check with it.
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_recheck(FBase f, int rules, const double* __restrict__ tol_min, int adaptive) {
+__global__ void __launch_bounds__(kBlock) k_recheck(FBase f, int rules, const double* __restrict__ vals, int adaptive, int mode, const T* rtol, const T* atol, int sum_rule) {
+    if (mode == 2) {
+        if (!sum_rule) return;
+        __shared__ double s_min[kBlock];
+        apply_batch_sum<T>(f.sys, f.batch, rtol, atol, vals[1]);
+        __syncthreads();
+        double m = INFINITY;
+        bool nan = false;
+        for (int b = threadIdx.x; b < f.batch; b += blockDim.x) {
+            const double t = ((volatile Sys*)f.sys)[b].tol;
+            if (t != t) nan = true;
+            else m = fmin(m, t);
+        }
+        s_min[threadIdx.x] = nan ? NAN : m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double mm = INFINITY;
+            bool anynan = false;
+            for (int k = 0; k < (int)blockDim.x; ++k) {
+                if (s_min[k] != s_min[k]) anynan = true;
+                else mm = fmin(mm, s_min[k]);
+            }
+            f.glob->tol_min = anynan ? NAN : mm;
+            f.glob->yy_sum = vals[1];
+        }
+        return;
+    }
     if (threadIdx.x == 0) {
-        f.glob->tol_min = *tol_min;
+        f.glob->tol_min = vals[0];
         f.glob->checks = 0;
         __threadfence();
     }
@@ -1777,16 +1835,19 @@ int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started && tol_min, "solver not started");
     if (!set) {
-        PHB_CUDA(cudaMemcpyAsync(tol_min, &s->glob->tol_min, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        static_assert(offsetof(Glob, yy_sum) == offsetof(Glob, tol_min) + sizeof(double), "tol_min and yy_sum are read as one pair");
+        PHB_CUDA(cudaMemcpyAsync(tol_min, &s->glob->tol_min, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
         return PHB200_OK;
     }
+    PHB_ARG(set == 1 || set == 2, "set must be 0 (read), 1 (install the minimum tolerance) or 2 (install the batch-wide sum of |y|^2)");
     PHB_ARG(s->passes == 0, "the tolerance can only be replaced before the first pass");
     FBase f;
     fill_base(f, s, true, s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE);
     const int rules = (s->method == PHB200_CG_TORCH || s->method == PHB200_CG_ADAPTIVE_TORCH) ? RULES_TORCH : RULES_GENERIC;
     const int adaptive = (s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH) ? 1 : 0;
-    if (s->dtype == PHB200_F32) PHB_LAUNCH(k_recheck<float>, 1, kBlock, 0, st, f, rules, (const double*)tol_min, adaptive);
-    else PHB_LAUNCH(k_recheck<double>, 1, kBlock, 0, st, f, rules, (const double*)tol_min, adaptive);
+    const int sum_rule = (s->method != PHB200_CG && rules == RULES_GENERIC) ? 1 : 0;
+    if (s->dtype == PHB200_F32) PHB_LAUNCH(k_recheck<float>, 1, kBlock, 0, st, f, rules, (const double*)tol_min, adaptive, set, (const float*)s->rtol, (const float*)s->atol, sum_rule);
+    else PHB_LAUNCH(k_recheck<double>, 1, kBlock, 0, st, f, rules, (const double*)tol_min, adaptive, set, (const double*)s->rtol, (const double*)s->atol, sum_rule);
     return PHB200_OK;
 }
 

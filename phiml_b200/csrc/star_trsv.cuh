@@ -335,11 +335,13 @@ __global__ void __launch_bounds__(tr_warps<T>() * 32) k_star_trsv(const StarTrsv
     }
 }
 
-// rd[i] = 1 / lu[diag(i)] and a bit-for-bit check that the factors have the closed form described above
-// (ok[0] = 0 otherwise).  One thread per row of the CSR factor storage.
+// rd[i] = 1 / lu[diag(i)] and a bit-for-bit check that the factors have the closed form described above.
+// `lu_prev` (fixed-point sweeps, phiml/backend/_linalg.py:573-577): the iterate BEFORE the last sweep; the last sweep computed
+// L_ik = (A_ik - 0) / lu_prev[diag(k)], so L is described by the reciprocals of THAT diagonal (rdv_l), U by the final one (rdv).
+// Exact factors: lu_prev == lu, rdv_l == rdv.
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_star_ilu_check(CsrView A, const T* __restrict__ lu, const int32_t* __restrict__ diag_pos, StarDesc st,
-                                                           T* __restrict__ rdv, int* ok) {
+__global__ void __launch_bounds__(kBlock) k_star_ilu_check(CsrView A, const T* __restrict__ lu, const T* __restrict__ lu_prev, const int32_t* __restrict__ diag_pos, StarDesc st,
+                                                           T* __restrict__ rdv, T* __restrict__ rdv_l, int* ok) {
     const int64_t n = A.n_rows;
     const int64_t sxo = st.ny * st.nz, syo = st.nz;
     const T cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(kBlock) k_star_ilu_check(CsrView A, const T* _
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
         const int dp = diag_pos[i];
         rdv[i] = T(1) / lu[dp];
+        if (rdv_l != rdv) rdv_l[i] = T(1) / lu_prev[dp];
         for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; ++p) {
             const int64_t j = A.col[p];
             const int64_t off = j - i;
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(kBlock) k_star_ilu_check(CsrView A, const T* _
             T expect;
             if (off < 0) {
                 const T a = off == -sxo ? cxm : (off == -syo ? cym : (off == -1 ? czm : T(NAN)));
-                expect = a / lu[diag_pos[j]];
+                expect = a / lu_prev[diag_pos[j]];
             } else {
                 expect = off == sxo ? cxp : (off == syo ? cyp : (off == 1 ? czp : T(NAN)));
             }

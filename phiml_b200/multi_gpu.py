@@ -92,9 +92,10 @@ def solve_sharded(method: str, lin, y_local: torch.Tensor, x0_local: torch.Tenso
     solver = host.DeviceSolver(sm, pre, code, order, nb)
     solver.start(y, x0, rtol_t, atol_t, mi)
     if world > 1:
-        tol = solver.get_tol_min()                 # local minimum of max(rtol^2 * norm, atol^2)
-        dist.all_reduce(tol, op=dist.ReduceOp.MIN, group=group)
-        solver.set_tol_min(tol)                    # re-runs the first progress check with the global minimum
+        # batch-wide stopping rule: sum of |y|^2 over ALL ranks' systems (generic cg_adaptive / bicg), then the minimum tolerance;
+        # the first progress check is repeated with it
+        ops = {'sum': dist.ReduceOp.SUM, 'min': dist.ReduceOp.MIN}
+        host.combine_tolerances([solver], lambda t, op: dist.all_reduce(t, op=ops[op], group=group))
     solver.run(int(np.max(max_iter)))
     host.LAST_RUN['resident'] = solver.resident_used
     its, fev, conv, div = solver.result()

@@ -200,9 +200,11 @@ def install():
             obj, key, pins = anchor(matrix)
             return PRECOND_CACHE.get(obj, ('jacobi',) + key, make, pins) if obj is not None else make()
         if method == 'ilu' and cuda_torch and not (solver or '').startswith('scipy-'):
-            make = lambda: _precond.IncompleteLU(native_matrix(matrix, TORCH))
+            rd = np.asarray(rank_deficiency.numpy() if hasattr(rank_deficiency, 'numpy') else rank_deficiency)
+            safe = bool(np.any(rd > 0))                     # factor_ilu(matrix, iterations, safe=(rank_deficiency > 0).any), _optimize.py:869
+            make = lambda: _precond.IncompleteLU(native_matrix(matrix, TORCH), safe=safe, rank_deficiency=rd)
             obj, key, pins = anchor(matrix)
-            return PRECOND_CACHE.get(obj, ('ilu',) + key, make, pins) if obj is not None else make()
+            return PRECOND_CACHE.get(obj, ('ilu', safe) + key, make, pins) if obj is not None else make()
         return original_compute(method, matrix, rank_deficiency=rank_deficiency, target_backend=target_backend, solver=solver)
 
     TORCH.__class__ = B200TorchBackend

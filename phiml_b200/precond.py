@@ -4,10 +4,11 @@ Preconditioners of the phb200 path, mirroring the reference protocol ``Precondit
 
 * ``JacobiPreconditioner`` — NEW; ``compute_preconditioner`` of the reference knows only 'auto' | 'ilu' | 'cluster'
   (phiml/math/_optimize.py:836-880).
-* ``IncompleteLU`` — device counterpart of phiml/backend/_linalg.py:455-487.  The factors are the exact ILU(0) of the
-  stored pattern, i.e. the fixed point the reference's sweep iteration (``incomplete_lu_coo``, _linalg.py:524-594)
-  converges to; the triangular solves are level-scheduled on the GPU (the reference's torch backend has none:
-  ``solve_triangular_sparse`` raises, _backend.py:1580-1581).
+* ``IncompleteLU`` — device counterpart of phiml/backend/_linalg.py:455-487.  By default the factors are the reference's own:
+  the fixed-point sweeps of ``incomplete_lu_coo`` (_linalg.py:524-594) with the sweep count of ``compute_preconditioner``
+  (phiml/math/_optimize.py:855-869), one gather-multiply-add kernel per sweep; ``sweeps='exact'`` gives the fixed point itself
+  (exact ILU(0)).  The triangular solves run on the GPU (the reference's torch backend has none: ``solve_triangular_sparse``
+  raises, _backend.py:1580-1581): structured wavefronts on recognised star stencils, level-scheduled CSR solves otherwise.
 """
 import ctypes
 from typing import Optional
@@ -80,21 +81,45 @@ class JacobiPreconditioner(Preconditioner, _Handle):
         return "jacobi"
 
 
-class IncompleteLU(Preconditioner, _Handle):
-    """Exact ILU(0) on the matrix' own pattern with level-scheduled solves.  ``lu`` holds L (strict lower, unit diagonal
-    implied) and U (upper incl. diagonal) in A's CSR layout."""
+def ilu_sweeps(n: int, nnz: int) -> int:
+    """Number of fixed-point sweeps ``compute_preconditioner`` picks in eager mode (phiml/math/_optimize.py:855-869)."""
+    import math
+    d = (nnz / n - 1) / 2
+    if d < 1:
+        return 1
+    return int(math.ceil(math.sqrt(d * n ** (1 / d))))
 
-    def __init__(self, matrix, source: str = "exact"):
+
+class IncompleteLU(Preconditioner, _Handle):
+    """ILU on the matrix' own pattern with the triangular solves on the GPU.  ``lu`` holds L (strict lower, unit diagonal
+    implied) and U (upper incl. diagonal) in A's CSR layout.
+
+    ``sweeps``: ``None`` — the reference's own factors: ``ilu_sweeps(n, nnz)`` fixed-point sweeps of ``incomplete_lu_coo``
+    (phiml/backend/_linalg.py:524-594), reported as ``'ilu (iter=k)'`` like the reference's; an int — that many sweeps;
+    ``'exact'`` — the fixed point itself (sequential-equivalent ILU(0), level-scheduled), reported as ``'ilu (exact)'``.
+    ``safe``: ``divide_no_nan`` for the lower entries (rank-deficient matrices, _linalg.py:576)."""
+
+    def __init__(self, matrix, sweeps=None, safe: bool = False, rank_deficiency=0):
         _Handle.__init__(self)
         m = plain_csr(as_matrix(matrix))
         assert m.kind == 'csr' and m.shape[0] == m.shape[1], "incomplete_lu_coo only implemented for square matrices"
         self.matrix = m
-        self.source = source
+        self.rank_deficiency = rank_deficiency
+        self.lower_unit_diagonal, self.upper_unit_diagonal = True, False
         self.lu = torch.empty_like(m.values)
         h = ctypes.c_void_p()
         twin = m.stencil.handle if m.stencil is not None else None
-        E.check(E.lib().phb200_precond_ilu0(ctypes.byref(h), m.handle, E.ptr(self.lu), twin, E.stream_ptr(m.device)))
+        if sweeps == 'exact':
+            self.sweeps = None
+            self.source = "exact"
+            E.check(E.lib().phb200_precond_ilu0(ctypes.byref(h), m.handle, E.ptr(self.lu), twin, E.stream_ptr(m.device)))
+        else:
+            self.sweeps = int(sweeps) if sweeps is not None else ilu_sweeps(m.shape[0], int(m.values.numel()))
+            self.source = f"iter={self.sweeps}"
+            E.check(E.lib().phb200_precond_ilu_sweeps(ctypes.byref(h), m.handle, E.ptr(self.lu), self.sweeps, 1 if safe else 0, twin, E.stream_ptr(m.device)))
         self._h = h
+        self._factors = None
+        self._factors_t = None
 
     @property
     def star_wavefront(self) -> bool:
@@ -112,6 +137,8 @@ class IncompleteLU(Preconditioner, _Handle):
     def factors(self):
         """(L, U) as torch sparse CSR tensors: L with explicit unit diagonal, U including the diagonal — the layout
         ``incomplete_lu_coo`` returns."""
+        if self._factors is not None:
+            return self._factors
         m = self.matrix
         n = m.shape[0]
         rows = torch.repeat_interleave(torch.arange(n, device=m.device, dtype=torch.int64), (m.rowptr[1:] - m.rowptr[:-1]).to(torch.int64))
@@ -121,13 +148,34 @@ class IncompleteLU(Preconditioner, _Handle):
         keep_l = lower | diag
         L = torch.sparse_coo_tensor(torch.stack([rows[keep_l], cols[keep_l]]), l_val[keep_l], m.shape).coalesce().to_sparse_csr()
         U = torch.sparse_coo_tensor(torch.stack([rows[~lower], cols[~lower]]), self.lu[~lower], m.shape).coalesce().to_sparse_csr()
-        return L, U
+        self._factors = (L, U)
+        return self._factors
+
+    @property
+    def lower(self):
+        return self.factors()[0]
+
+    @property
+    def upper(self):
+        return self.factors()[1]
 
     def apply(self, vec):
         vec = vec.to(self.matrix.dtype).contiguous()
         out = torch.empty_like(vec)
         E.check(E.lib().phb200_precond_apply(self._h, E.ptr(vec), E.ptr(out), vec.shape[0], vec.shape[1], E.stream_ptr(vec.device)))
         return out
+
+    def apply_transposed(self, vec):
+        """(LU)^-T vec = L^-T (U^-T vec), phiml/backend/_linalg.py:481-485: a lower solve with U^T followed by an upper solve with
+        L^T; the transposed factors are built once on the device (phb200_csr_transpose)."""
+        from .solve import solve_triangular_sparse
+        if self._factors_t is None:
+            L, U = self.factors()
+            self._factors_t = (plain_csr(as_matrix(torch.sparse_csc_tensor(L.crow_indices(), L.col_indices(), L.values(), tuple(L.shape)), detect_stencil=False)),
+                               plain_csr(as_matrix(torch.sparse_csc_tensor(U.crow_indices(), U.col_indices(), U.values(), tuple(U.shape)), detect_stencil=False)))
+        Lt, Ut = self._factors_t
+        intermediate = solve_triangular_sparse(Ut, vec, lower=True, unit_diagonal=self.upper_unit_diagonal)
+        return solve_triangular_sparse(Lt, intermediate, lower=False, unit_diagonal=self.lower_unit_diagonal)
 
     def apply_inv_l(self, vec):
         from .solve import solve_triangular_sparse
@@ -141,12 +189,17 @@ class IncompleteLU(Preconditioner, _Handle):
         return f"ilu ({self.source})"
 
 
-def compute_preconditioner(method: Optional[str], matrix, **_ignored) -> Optional[Preconditioner]:
-    """'jacobi' | 'ilu' | None on a native matrix (torch sparse tensor or Matrix)."""
+def compute_preconditioner(method: Optional[str], matrix, rank_deficiency=0, **_ignored) -> Optional[Preconditioner]:
+    """'jacobi' | 'ilu' | 'ilu-exact' | 'auto' | None on a native matrix (torch sparse tensor or Matrix).  'auto' resolves to 'ilu'
+    as in the reference for backends with sparse triangular solves (phiml/math/_optimize.py:838-846); 'ilu' builds the
+    reference's own factors (fixed-point sweeps, eager sweep count); ``safe`` sweeps when a rank deficiency is declared (:869)."""
     if method is None:
         return None
     if method == 'jacobi':
         return JacobiPreconditioner(matrix)
-    if method == 'ilu':
-        return IncompleteLU(matrix)
+    if method in ('ilu', 'auto'):
+        import numpy as np
+        return IncompleteLU(matrix, safe=bool(np.any(np.asarray(rank_deficiency) > 0)), rank_deficiency=rank_deficiency)
+    if method == 'ilu-exact':
+        return IncompleteLU(matrix, sweeps='exact')
     raise NotImplementedError(f"preconditioner '{method}' is not on the phb200 path")

@@ -103,12 +103,21 @@ class DeviceSolver:
         E.check(E.lib().phb200_solver_result(self._h, E.ptr(its), E.ptr(fev), E.ptr(conv), E.ptr(div), E.stream_ptr(dev)))
         return its, fev, conv.bool(), div.bool()
 
-    def get_tol_min(self) -> torch.Tensor:
-        t = torch.empty(1, dtype=torch.float64, device=self.x.device)
+    def get_tol(self) -> torch.Tensor:
+        """Device pair {minimum squared tolerance of this solver's systems, sum of |y_b|^2 over them} (after start())."""
+        t = torch.empty(2, dtype=torch.float64, device=self.x.device)
         E.check(E.lib().phb200_solver_tol_min(self._h, E.ptr(t), 0, E.stream_ptr(self.x.device)))
         return t
 
+    get_tol_min = get_tol
+
+    def set_yy_sum(self, t: torch.Tensor):
+        """Installs t[1] = sum of |y_b|^2 over ALL systems of a batch that is split over several solvers / ranks."""
+        self._keep = self._keep + (t,)
+        E.check(E.lib().phb200_solver_tol_min(self._h, E.ptr(t), 2, E.stream_ptr(self.x.device)))
+
     def set_tol_min(self, t: torch.Tensor):
+        """Installs t[0] = minimum tolerance over ALL systems; repeats the first progress check."""
         self._keep = self._keep + (t,)
         E.check(E.lib().phb200_solver_tol_min(self._h, E.ptr(t), 1, E.stream_ptr(self.x.device)))
 
@@ -180,12 +189,45 @@ def _run(code: int, poly_order: int, name: str, matrix, y, x0, rtol, atol, max_i
         x, r, its, fev, conv, div = _run_slab(code, poly_order, solver_matrix, y, x0, rtol, atol, max_iter, pre)
         return SolveResult(name, x, r, its, fev, conv, div, [""] * nb)
     assert max_iter.shape[0] == 1, "trajectories are limited to 65535 systems"
-    parts = []
-    for b0 in range(0, nb, 65535):       # gridDim.y limit; one solver per slab of systems
+    # gridDim.y limit: one solver per slab of systems.  The stopping rule couples the whole batch (minimum tolerance; for the
+    # generic cg_adaptive / bicg loops the sum of |y|^2 over the batch), so the slabs are started first, the two quantities are
+    # combined over them — as multi_gpu.solve_sharded does over ranks — and only then do the loops run.
+    solvers = []
+    for b0 in range(0, nb, 65535):
         sl = slice(b0, min(nb, b0 + 65535))
-        parts.append(_run_slab(code, poly_order, solver_matrix, y[sl], x0[sl], rtol[sl], atol[sl], max_iter[:, sl] if max_iter.shape[1] > 1 else max_iter, pre))
+        mi = max_iter[:, sl] if max_iter.shape[1] > 1 else max_iter
+        mi_last = np.broadcast_to(mi[-1, :], (sl.stop - sl.start,))
+        mi_dev = torch.as_tensor(np.ascontiguousarray(mi_last).astype(np.int32), device=y.device)
+        solver = DeviceSolver(solver_matrix, pre, code, poly_order, sl.stop - sl.start)
+        solver.start(y[sl], x0[sl], rtol[sl], atol[sl], mi_dev)
+        solvers.append(solver)
+    combine_tolerances(solvers)
+    parts = []
+    for solver in solvers:
+        solver.run(int(np.max(max_iter)))
+        parts.append((solver.x, solver.r, *solver.result()))
+    LAST_RUN['resident'] = solvers[-1].resident_used
     x, r, its, fev, conv, div = [torch.cat(p, dim=0) for p in zip(*parts)]
     return SolveResult(name, x, r, its, fev, conv, div, [""] * nb)
+
+
+def combine_tolerances(solvers, all_reduce=None):
+    """Started solvers that together hold ONE batch: make every one of them stop on the batch-wide rule of stop_on_l2
+    (phiml/backend/_linalg.py:26-29).  ``all_reduce(tensor, op)`` with op 'sum' | 'min' additionally combines over ranks."""
+    pairs = [s.get_tol() for s in solvers]
+    total = torch.stack(pairs).sum(dim=0)
+    if all_reduce is not None:
+        all_reduce(total, 'sum')
+    for s in solvers:
+        s.set_yy_sum(total)
+    pairs = [s.get_tol() for s in solvers]
+    least = torch.stack(pairs).min(dim=0).values
+    if torch.isnan(torch.stack(pairs)[:, 0]).any():
+        least[0] = float('nan')
+    if all_reduce is not None:
+        all_reduce(least, 'min')
+    for s in solvers:
+        s.set_tol_min(least)
 
 
 def _run_slab(code, poly_order, matrix, y, x0, rtol, atol, max_iter, pre):

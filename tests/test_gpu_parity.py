@@ -189,17 +189,16 @@ def test_solve_matches_reference(name, use_stencil):
     x = res.x.cpu().numpy()
     f64 = y.dtype == np.float64
     tol = 1e-10 if f64 else 1e-5
-    if case.get('pre') == 'ilu' or (case['method'].startswith('biCG') and not f64) or not np.array_equal(its, ref_it):
-        # exact ILU(0) vs the reference's unconverged sweeps / chaotic fp32 BiCGstab / a different stopping iteration:
-        # both answers satisfy the requested residual tolerance, so compare at that level
+    if not np.array_equal(its, ref_it):
+        # a different stopping iteration (within the +-2 above): both answers satisfy the requested residual tolerance, so they
+        # can only be compared at that level.  With equal iteration counts the north-star tolerance applies unchanged — ILU
+        # included: the device builds the reference's own factors (same sweeps, same summation order).
         tol = max(tol, 30 * case['rtol'])
     err = rel_err(x[:, sample_index(x.shape[1])], g[key + '/x_sample'])
     assert np.all(err <= tol), f"x differs from the reference by {err} (tolerance {tol})"
     if key + '/x' in g.files:
         assert np.all(rel_err(x, g[key + '/x']) <= tol)
-    expected = str(g[key + '/method']).replace('(numpy)', '(torch)')
-    if case.get('pre') == 'ilu':
-        expected = expected.split("'ilu")[0] + "'ilu (exact)'"
+    expected = str(g[key + '/method']).replace('(numpy)', '(torch)')      # incl. the reference's 'ilu (iter=k)'
     assert res.method == expected
     if case['method'] in ('biCG-stab(3)', 'biCG-stab(4)'):
         return   # the reference's aliased tau table (_linalg.py:159) breaks the residual recurrence for L >= 3; reproduced as is
@@ -417,6 +416,70 @@ def test_trajectory_recording():
 # ---------------------------------------------------------------------------------------------------- preconditioners
 
 @pytest.mark.parametrize('key', sorted({k.rsplit('/', 1)[0] for k in golden('ilu').files}))
+def test_ilu_sweeps_reproduce_the_reference_factors_bit_for_bit(key):
+    """phb200_precond_ilu_sweeps against factors recorded from the reference's factor_ilu (incomplete_lu_coo, k sweeps):
+    same pattern, same values to the last bit (the kernel adds the products in the order NumPy's einsum does)."""
+    g = golden('ilu')
+    _, grid, s = key.split('/')
+    grid = tuple(map(int, grid.split('x')))
+    csr = oracle_matrix('poisson', grid, np.float64)
+    ilu = pb.IncompleteLU(dev_csr(csr), sweeps=int(s[1:]))
+    assert repr(ilu) == f"ilu (iter={int(s[1:])})"
+    L, U = ilu.factors()
+    for mine, nm in ((L, 'L'), (U, 'U')):
+        np.testing.assert_array_equal(mine.crow_indices().cpu().numpy(), g[f'{key}/{nm}_indptr'])
+        np.testing.assert_array_equal(mine.col_indices().cpu().numpy(), g[f'{key}/{nm}_indices'])
+        np.testing.assert_array_equal(mine.values().cpu().numpy(), g[f'{key}/{nm}_data'])
+    # apply = U^-1 L^-1 on these factors against the reference's spsolve_triangular results (structured wavefront solves when the
+    # grid qualifies, CSR level solves otherwise)
+    rhs = np.random.default_rng(3).standard_normal((2, csr.shape[0]))
+    v = torch.as_tensor(rhs, device=DEV)
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import spsolve_triangular
+    Lr = sp.csr_matrix((g[f'{key}/L_data'], g[f'{key}/L_indices'], g[f'{key}/L_indptr']), shape=csr.shape)
+    Ur = sp.csr_matrix((g[f'{key}/U_data'], g[f'{key}/U_indices'], g[f'{key}/U_indptr']), shape=csr.shape)
+    ref = spsolve_triangular(Ur, spsolve_triangular(Lr, rhs.T, lower=True, unit_diagonal=True), lower=False).T
+    np.testing.assert_allclose(ilu.apply(v).cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ilu.apply_inv_l(v).cpu().numpy(), g[f'{key}/solve_L'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ilu.apply_inv_u(v).cpu().numpy(), g[f'{key}/solve_U'], rtol=1e-12, atol=1e-12)
+    # apply_transposed = L^-T U^-T (phiml/backend/_linalg.py:481-485)
+    ref_t = spsolve_triangular(Lr.T.tocsr(), spsolve_triangular(Ur.T.tocsr(), rhs.T, lower=True, unit_diagonal=False), lower=False, unit_diagonal=True).T
+    np.testing.assert_allclose(ilu.apply_transposed(v).cpu().numpy(), ref_t, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float64'])
+@pytest.mark.parametrize('op,grid', [('poisson', (12, 8, 8)), ('advdiff', (7, 9, 8)), ('poisson', (24, 20))])
+def test_ilu_sweeps_match_the_oracle_sweeps(op, grid, dt):
+    """Same check against the oracle's restatement of incomplete_lu_coo (pinned to the reference in test_oracle_golden.py), fp32
+    and nonsymmetric included; the default sweep count is the reference's eager heuristic (_optimize.py:855-869)."""
+    from oracle import precond as op_
+    csr = oracle_matrix(op, grid, dt)
+    k = op_.ilu_sweeps(csr.shape[0], csr.nnz)
+    Lx, Ux = op_.ilu_fixed_point(csr, k)
+    ilu = pb.IncompleteLU(dev_csr(csr))
+    assert ilu.sweeps == k and repr(ilu) == f"ilu (iter={k})"
+    L, U = ilu.factors()
+    tol = 1e-14 if dt == 'float64' else 1e-6      # the oracle multiplies with SciPy's sparse product (another summation order)
+    for mine, ex in ((L, Lx), (U, Ux)):
+        ex.sort_indices()
+        np.testing.assert_array_equal(mine.col_indices().cpu().numpy(), ex.indices)
+        np.testing.assert_allclose(mine.values().cpu().numpy(), ex.data, rtol=tol, atol=tol)
+
+
+def test_ilu_safe_sweeps_on_a_rank_deficient_matrix():
+    """safe=True (divide_no_nan, _linalg.py:576): a zero pivot yields zeros instead of NaN/inf in L."""
+    import scipy.sparse as sp
+    a = sp.csr_matrix(np.array([[1., 1, 0], [1, 1, 1], [0, 1, 2]]))      # second pivot becomes 0
+    from oracle import precond as op_
+    Lx, Ux = op_.ilu_fixed_point(a, 3, safe=True)
+    ilu = pb.IncompleteLU(dev_csr(a), sweeps=3, safe=True)
+    L, U = ilu.factors()
+    assert torch.isfinite(L.values()).all()
+    np.testing.assert_allclose(L.values().cpu().numpy(), Lx.data, rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(U.values().cpu().numpy(), Ux.data, rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.parametrize('key', sorted({k.rsplit('/', 1)[0] for k in golden('ilu').files}))
 def test_ilu_and_triangular_solves(key):
     g = golden('ilu')
     _, grid, s = key.split('/')
@@ -424,7 +487,8 @@ def test_ilu_and_triangular_solves(key):
     csr = oracle_matrix('poisson', grid, np.float64)
     from oracle import precond as op
     Lx, Ux = op.ilu0_exact(csr)
-    ilu = pb.IncompleteLU(dev_csr(csr))
+    ilu = pb.IncompleteLU(dev_csr(csr), sweeps='exact')
+    assert repr(ilu) == "ilu (exact)"
     L, U = ilu.factors()
     for mine, ex in ((L, Lx), (U, Ux)):
         ex.sort_indices()
@@ -453,7 +517,8 @@ def test_ilu_and_triangular_solves(key):
 @pytest.mark.parametrize('op,grid,dt,nb', [('poisson', (20, 37, 44), 'float64', 2), ('poisson', (9, 70, 20), 'float32', 1), ('advdiff', (17, 33, 36), 'float64', 3),
                                            ('poisson', (50, 36), 'float64', 2), ('advdiff', (40, 64), 'float32', 1), ('poisson', (64, 64, 64), 'float32', 1),
                                            ('poisson', (3, 3, 4), 'float64', 1), ('poisson', (1, 8), 'float64', 1)])
-def test_star_wavefront_triangular_solves_match_csr_level_solves(op, grid, dt, nb, monkeypatch):
+@pytest.mark.parametrize('sweeps', ['exact', None, 3], ids=['exact', 'reference-sweeps', '3-sweeps'])
+def test_star_wavefront_triangular_solves_match_csr_level_solves(op, grid, dt, nb, sweeps, monkeypatch):
     """ILU(0) apply through the structured wavefront (star_trsv.cuh: pivots only, skewed warps, block counters) against
     the general CSR level-scheduled solves on the same factors, and against the oracle's SciPy triangular solves."""
     from oracle import precond as op_
@@ -461,11 +526,11 @@ def test_star_wavefront_triangular_solves_match_csr_level_solves(op, grid, dt, n
     rng = np.random.default_rng(21)
     rhs = rng.standard_normal((nb, csr.shape[0])).astype(dt)
     v = torch.as_tensor(rhs, device=DEV)
-    ilu_star = pb.IncompleteLU(dev_csr(csr))
+    ilu_star = pb.IncompleteLU(dev_csr(csr), sweeps=sweeps)
     assert ilu_star.star_wavefront, "star stencil factors must take the wavefront path"
     monkeypatch.setenv('PHB200_TRSV', 'csr')
     pb.clear_cache()
-    ilu_csr = pb.IncompleteLU(dev_csr(csr))
+    ilu_csr = pb.IncompleteLU(dev_csr(csr), sweeps=sweeps)
     monkeypatch.delenv('PHB200_TRSV')
     assert not ilu_csr.star_wavefront
     assert torch.equal(ilu_star.lu, ilu_csr.lu)
@@ -475,7 +540,8 @@ def test_star_wavefront_triangular_solves_match_csr_level_solves(op, grid, dt, n
         scale = np.abs(b).max()
         assert np.abs(a - b).max() <= tol * scale, f"wavefront differs from the CSR solves by {np.abs(a - b).max() / scale}"
     if csr.shape[0] <= 50000:     # the oracle's sequential IKJ is a Python loop
-        Lx, Ux = op_.ilu0_exact(csr.astype(np.float64))
+        k = ilu_star.sweeps
+        Lx, Ux = op_.ilu0_exact(csr.astype(np.float64)) if sweeps == 'exact' else op_.ilu_fixed_point(csr.astype(np.float64), k)
         ref = op_.IncompleteLU(Lx, Ux).apply(rhs.astype(np.float64))
         assert np.abs(a - ref).max() <= (1e-11 if dt == 'float64' else 1e-4) * np.abs(ref).max()
 
@@ -640,3 +706,62 @@ def test_batch_minimum_tolerance_can_be_replaced_before_the_first_pass():
     solver2.set_tol_min(t * 1e-4)
     solver2.run(5000)
     assert bool((solver2.result()[0] > base.iterations).all())
+
+
+@pytest.mark.parametrize('method,op,grid,dt', [('biCG-stab(2)', 'advdiff', (8, 6, 8), 'float64'), ('biCG-stab', 'advdiff', (8, 6, 8), 'float64'),
+                                               ('CG-adaptive', 'poisson', (12, 12), 'float64'), ('biCG-stab(2)', 'advdiff', (8, 6, 8), 'float32')])
+def test_generic_rules_tolerance_is_relative_to_the_batch_sum_of_rhs_norms(method, op, grid, dt):
+    """cg_adaptive / bicg / bicg_stab_first_order pass the (batch,) vector sum(y**2, -1) to stop_on_l2, which sums it AGAIN over
+    its last axis (phiml/backend/_linalg.py:26): every system's tolerance is relative to the sum of |y_b|^2 over the whole batch.
+    12 right-hand sides of very different magnitude: iteration counts must EQUAL the oracle's (a per-system tolerance would make
+    the small systems iterate far longer)."""
+    from oracle import krylov
+    csr = oracle_matrix(op, grid, dt)
+    nb = 12
+    rng = np.random.default_rng(31)
+    y = (rng.standard_normal((nb, csr.shape[0])) * (10.0 ** rng.uniform(-3, 1, (nb, 1)))).astype(dt)
+    rt = 1e-10 if dt == 'float64' else 1e-5
+    rtol, atol, max_iter = np.full(nb, rt, dt), np.zeros(nb, dt), np.full((1, nb), 1000)
+    ora = krylov.linear_solve(method, csr, y, np.zeros_like(y), rtol, atol, max_iter, None, flavour='numpy')
+    m = pb.as_matrix(dev_csr(csr))
+    yd = torch.as_tensor(y, device=DEV)
+    if method == 'CG-adaptive':
+        res = pb.generic_conjugate_gradient_adaptive(m, yd, torch.zeros_like(yd), rtol, atol, max_iter)
+    else:
+        res = pb.linear_solve(method, m, yd, torch.zeros_like(yd), rtol, atol, max_iter, None, None)
+    its = res.iterations.cpu().numpy()
+    if dt == 'float64':
+        np.testing.assert_array_equal(its, ora.iterations)
+    else:
+        assert np.max(np.abs(its.astype(int) - ora.iterations.astype(int))) <= 1
+    np.testing.assert_array_equal(res.converged.cpu().numpy(), ora.converged)
+    assert len(set(its.tolist())) > 1, "probe too weak: all systems stop together anyway"
+    # a per-system tolerance would need clearly more iterations for the smallest right-hand side
+    small = int(np.argmin(np.linalg.norm(y, axis=1)))
+    alone = pb.linear_solve(method, m, yd[small:small + 1], torch.zeros_like(yd[:1]), rtol[:1], atol[:1], max_iter[:, :1], None, None) if method != 'CG-adaptive' else \
+        pb.generic_conjugate_gradient_adaptive(m, yd[small:small + 1], torch.zeros_like(yd[:1]), rtol[:1], atol[:1], max_iter[:, :1])
+    assert int(alone.iterations[0]) > int(its[small])
+
+
+def test_batch_wide_rule_is_shared_by_solver_chunks():
+    """A batch that is split over several solver objects (gridDim.y limit, or ranks in solve_sharded) must stop on the rule of the
+    WHOLE batch: combine_tolerances over two half-batch solvers reproduces the unsplit solve."""
+    from phiml_b200.solve import combine_tolerances
+    csr = oracle_matrix('advdiff', (8, 6, 8), 'float64')
+    nb = 10
+    rng = np.random.default_rng(32)
+    y = torch.as_tensor(rng.standard_normal((nb, csr.shape[0])) * (10.0 ** rng.uniform(-3, 1, (nb, 1))), device=DEV)
+    m = pb.as_matrix(dev_csr(csr))
+    rtol, atol = torch.full((nb,), 1e-10, dtype=torch.float64, device=DEV), torch.zeros(nb, dtype=torch.float64, device=DEV)
+    whole = pb.linear_solve('biCG-stab(2)', m, y, torch.zeros_like(y), rtol, atol, np.full((1, nb), 1000), None, None)
+    solvers = []
+    for sl in (slice(0, 4), slice(4, nb)):
+        s = pb.DeviceSolver(m.stencil, None, E.BICGSTAB, 2, sl.stop - sl.start)
+        s.start(y[sl].contiguous(), torch.zeros_like(y[sl]), rtol[sl].contiguous(), atol[sl].contiguous(), torch.full((sl.stop - sl.start,), 1000, dtype=torch.int32, device=DEV))
+        solvers.append(s)
+    combine_tolerances(solvers)
+    for s in solvers:
+        s.run(1000)
+    its = torch.cat([s.result()[0] for s in solvers])
+    assert torch.equal(its, whole.iterations)
+    assert torch.equal(torch.cat([s.x for s in solvers]), whole.x)
