@@ -153,14 +153,15 @@ struct Glob {
 };
 
 // All-reduce over the slab ranks INSIDE the kernel that produced the local sums (one process per GPU, peer memory mapped through
-// CUDA IPC): the finishing thread of a system stores its sums into every rank's mailbox (NVLink peer stores, release at system
-// scope), waits until the mailboxes of its own GPU hold the sums of all ranks for this reduction, and adds them in rank order —
-// the same value on every rank — before the ordinary scalar step.  Two slots per (rank, system) are enough: nobody can be two
-// reductions ahead of a peer.
+// CUDA IPC): the finishing thread of a system stores its sums into every rank's mailbox (NVLink peer stores), waits until the
+// mailboxes of its own GPU hold the sums of all ranks for this reduction, and adds them in rank order — the same value on every
+// rank — before the ordinary scalar step.  The messages are SELF-VALIDATING (the "LL" scheme of collective libraries): every
+// 8-byte word carries 32 bits of payload and the 32-bit sequence number of the reduction, and an 8-byte store is single-copy
+// atomic, so no fence or release/acquire pair orders payload against flag: all words of all peers leave back to back (one NVLink
+// latency in total), the receiver polls until every word shows the expected sequence number.  Two slots per (rank, system) are
+// enough: nobody can be two reductions ahead of a peer.
 struct PeerMail {
-    double v[kMaxDots];
-    unsigned long long seq;
-    unsigned long long pad[3];
+    unsigned long long w[2 * kMaxDots];   // w[2d] = lo32(v_d) << 32 | seq32, w[2d+1] = hi32(v_d) << 32 | seq32
 };
 struct PeerReduce {
     PeerMail* mail[8];             // mailbox array of every rank: [2][world][batch]
@@ -173,6 +174,7 @@ struct Reduce {
     unsigned* tickets;     // [batch]
     int max_blocks;
     const PeerReduce* peer;   // non-null: multi-GPU slab mode with in-kernel all-reduce
+    int peer_data;            // this kernel also stores data (halo planes) into peer memory: fences at system scope around the all-reduce
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -230,7 +232,7 @@ __device__ __forceinline__ bool system_reduce(double (&tot)[ND], const Reduce& r
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) mine[(size_t)bx * kMaxDots + d] = tot[d];
-        if (red.peer) __threadfence_system();   // this CTA's stores into peer GPUs (halo planes) precede the in-kernel all-reduce
+        if (red.peer && red.peer_data) __threadfence_system();   // this CTA's stores into peer GPUs (halo planes) precede the in-kernel all-reduce
         else __threadfence();
         unsigned t = atomicAdd(&red.tickets[b], 1u);
         s_last = (t == (unsigned)nbx - 1u);
@@ -254,36 +256,48 @@ __device__ __forceinline__ bool system_reduce(double (&tot)[ND], const Reduce& r
     return true;
 }
 
-// thread 0 of the finishing CTA of system b: tot (local sums) -> sums over all ranks
+// thread 0 of the finishing CTA of system b: tot (local sums) -> sums over all ranks.  `ordered_data`: this kernel also stored
+// DATA into peer memory (halo planes) that the peers read after the reduction: one system-scope fence orders it (cumulatively:
+// the other CTAs fenced before drawing their tickets) before the messages, and the receiver fences after the last poll.
 template <int ND>
-__device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, int b, double (&tot)[ND]) {
+__device__ __forceinline__ void peer_allreduce(const PeerReduce& pr, int b, double (&tot)[ND], bool ordered_data = true) {
     const unsigned long long s = pr.seq[b] + 1ull;
     pr.seq[b] = s;
+    const unsigned long long tag = s & 0xffffffffull;
     const size_t par = (size_t)(s & 1ull);
     const size_t mine = (par * pr.world + pr.rank) * pr.batch + b;
-    for (int p = 0; p < pr.world; ++p) {
-        volatile PeerMail* m = pr.mail[p] + mine;
+    unsigned long long word[2 * ND];
 #pragma unroll
-        for (int d = 0; d < ND; ++d) m->v[d] = tot[d];
+    for (int d = 0; d < ND; ++d) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[d]);
+        word[2 * d] = ((bits & 0xffffffffull) << 32) | tag;
+        word[2 * d + 1] = (bits & 0xffffffff00000000ull) | tag;
     }
-    __threadfence_system();
-    for (int p = 0; p < pr.world; ++p)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&(pr.mail[p] + mine)->seq), "l"(s) : "memory");
+    if (ordered_data) __threadfence_system();
+    for (int p = 0; p < pr.world; ++p) {
+        unsigned long long* m = (pr.mail[p] + mine)->w;
+#pragma unroll
+        for (int k = 0; k < 2 * ND; ++k) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(m + k), "l"(word[k]) : "memory");
+    }
     double sum[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) sum[d] = 0.0;
     const long long t0 = clock64();
     for (int r = 0; r < pr.world; ++r) {
-        const PeerMail* m = pr.mail[pr.rank] + (par * pr.world + r) * pr.batch + b;
-        unsigned long long got = 0;
-        while (true) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(&m->seq) : "memory");
-            if (got == s) break;
-            if (clock64() - t0 > 8000000000ll) __trap();
-        }
+        const unsigned long long* m = (pr.mail[pr.rank] + (par * pr.world + r) * pr.batch + b)->w;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) sum[d] += ((volatile const PeerMail*)m)->v[d];
+        for (int d = 0; d < ND; ++d) {
+            unsigned long long lo = 0, hi = 0;
+            while (true) {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(lo) : "l"(m + 2 * d) : "memory");
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(hi) : "l"(m + 2 * d + 1) : "memory");
+                if ((lo & 0xffffffffull) == tag && (hi & 0xffffffffull) == tag) break;
+                if (clock64() - t0 > 8000000000ll) __trap();
+            }
+            sum[d] += __longlong_as_double((long long)((hi & 0xffffffff00000000ull) | (lo >> 32)));
+        }
     }
+    if (ordered_data) __threadfence_system();
 #pragma unroll
     for (int d = 0; d < ND; ++d) tot[d] = sum[d];
 }

@@ -1,6 +1,7 @@
 // Host-side choice of the SpMV kernel for a matrix handle (used by phb200_spmv and by the Krylov loops).
 #pragma once
 #include "star_tma.cuh"
+#include "csr_bulk.cuh"
 
 namespace phb {
 
@@ -29,6 +30,9 @@ int launch_spmv(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t l
     }
     PHB_TRY(csr_analyse(A, stream));
     if (A->max_block_nnz <= kCsrCap) {
+        bool used = false;     // matrix stream staged by the TMA unit (csr_bulk.cuh); falls back when the arrays are not 16-byte aligned
+        PHB_TRY((launch_csr_bulk<T, Epi>(A, X, ldx, Y, ldy, scale, batch, epi, stream, &used)));
+        if (used) return PHB200_OK;
         // few right-hand sides: one per CTA row for parallelism; many: tiles of kCsrBt share the staged matrix chunk
         const int bt = batch >= 8 * kCsrBt ? kCsrBt : 1;
         const int rows = (batch + bt - 1) / bt;

@@ -864,6 +864,7 @@ static Ctx make_ctx(const phb200_solver* s) {
     c.red.tickets = s->tickets;
     c.red.max_blocks = max_blocks_for(s->batch);
     c.red.peer = s->peer_reduce;
+    c.red.peer_data = 0;
     c.defer = nullptr;
     c.batch = (int)s->batch;
     return c;
@@ -1098,6 +1099,7 @@ struct Run {
         u.cinv = PRE == 3 ? (T)s->M->const_inv : T(1); u.rules = rules();
         u.defer = defer();
         u.peer = PeerHalo{s->peer_lo, s->peer_hi, s->A->kind == PHB200_MAT_STENCIL ? s->A->star.ny * s->A->star.nz : 0, s->peer_ld_lo, s->peer_ld_hi};
+        u.red.peer_data = (s->peer_lo || s->peer_hi) ? 1 : 0;      // halo planes go to peer memory: system-scope fences around the all-reduce
         return u;
     }
     // first half: d = M^-1 r + beta d, x += alpha d_old, q = A d, d.q

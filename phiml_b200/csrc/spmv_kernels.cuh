@@ -40,7 +40,7 @@ __device__ __forceinline__ void epilogue_tail(const Epi& epi, double (&acc)[NDA]
 #pragma unroll
                     for (int d = 0; d < Epi::ND; ++d) epi.defer[(size_t)b * kMaxDots + d] = acc[d];
                 } else {
-                    if (epi.red.peer) peer_allreduce<Epi::ND>(*epi.red.peer, b, acc);   // multi-GPU: sums over the ranks, in the kernel
+                    if (epi.red.peer) peer_allreduce<Epi::ND>(*epi.red.peer, b, acc, epi.red.peer_data != 0);   // multi-GPU: sums over the ranks, in the kernel
                     epi.finalize(b, acc);
                 }
             }
@@ -62,7 +62,7 @@ __device__ __forceinline__ void epilogue_tail_cta(const Epi& epi, double (&tot)[
 #pragma unroll
                     for (int d = 0; d < Epi::ND; ++d) epi.defer[(size_t)b * kMaxDots + d] = tot[d];
                 } else {
-                    if (epi.red.peer) peer_allreduce<Epi::ND>(*epi.red.peer, b, tot);
+                    if (epi.red.peer) peer_allreduce<Epi::ND>(*epi.red.peer, b, tot, epi.red.peer_data != 0);
                     epi.finalize(b, tot);
                 }
             }

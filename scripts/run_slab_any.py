@@ -66,8 +66,12 @@ if a.check:
         pre = pb.JacobiPreconditioner(st) if a.jacobi else None
         from phiml_b200 import solve as S
         S.RESIDENT['mode'] = 'never'
-        ref = pb.linear_solve(a.method, st, y_full, torch.zeros_like(y_full), [1e-5], [0.0], np.array([[5000]]), pre, None) if a.method.startswith('biCG') else \
-            pb.generic_conjugate_gradient(st, y_full, torch.zeros_like(y_full), [1e-5], [0.0], np.array([[5000]]), pre)
+        if a.method.startswith('biCG'):
+            ref = pb.linear_solve(a.method, st, y_full, torch.zeros_like(y_full), [1e-5], [0.0], np.array([[5000]]), pre, None)
+        elif a.method in ('CG-adaptive', 'auto') and not a.jacobi:
+            ref = pb.generic_conjugate_gradient_adaptive(st, y_full, torch.zeros_like(y_full), [1e-5], [0.0], np.array([[5000]]))
+        else:
+            ref = pb.generic_conjugate_gradient(st, y_full, torch.zeros_like(y_full), [1e-5], [0.0], np.array([[5000]]), pre)
         out.update(ref_iterations=int(ref.iterations[0]), rel_err_vs_single_gpu=float((x_all - ref.x).abs().max() / ref.x.abs().max()),
                    true_residual=float((y_full - st.matvec(x_all)).norm() / y_full.norm()), ref_true_residual=float((y_full - st.matvec(ref.x)).norm() / y_full.norm()))
 else:
