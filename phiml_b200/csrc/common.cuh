@@ -232,8 +232,7 @@ __device__ __forceinline__ bool system_reduce(double (&tot)[ND], const Reduce& r
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) mine[(size_t)bx * kMaxDots + d] = tot[d];
-        if (red.peer && red.peer_data) __threadfence_system();   // this CTA's stores into peer GPUs (halo planes) precede the in-kernel all-reduce
-        else __threadfence();
+        __threadfence();     // (stores into peer GPUs were fenced at system scope by the threads that made them, phase.cuh)
         unsigned t = atomicAdd(&red.tickets[b], 1u);
         s_last = (t == (unsigned)nbx - 1u);
     }

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
     double acc[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+    bool wrote_peer = false;      // this thread stored into a slab neighbour's memory
     if (!p.skip(b)) {
         const typename P::Scal sc = p.load(b);
         T* base[NA];
@@ -131,11 +132,13 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
                     const PeerHalo& ph = p.peer;
                     const int64_t i = idx[u];
                     if (ph.lo && i < ph.plane) {
+                        wrote_peer = true;
                         T* dst = (T*)ph.lo + (int64_t)b * ph.ld_lo + i;
                         if constexpr (V == 1) dst[0] = e[u][0][0];
                         else *reinterpret_cast<VT*>(dst) = *reinterpret_cast<const VT*>(&e[u][0][0]);
                     }
                     if (ph.hi && i >= n - ph.plane) {
+                        wrote_peer = true;
                         T* dst = (T*)ph.hi + (int64_t)b * ph.ld_hi + (i - (n - ph.plane));
                         if constexpr (V == 1) dst[0] = e[u][0][0];
                         else *reinterpret_cast<VT*>(dst) = *reinterpret_cast<const VT*>(&e[u][0][0]);
@@ -144,6 +147,10 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
             }
         }
     }
+    // peer stores are ordered before the in-kernel all-reduce by the threads that made them (system scope); the CTA barrier of the
+    // block reduction and the gpu-scope fence + ticket of thread 0 carry the order on (fences are cumulative), the finishing
+    // thread adds one system-scope fence before it sends its messages (peer_allreduce, ordered_data)
+    if (wrote_peer) __threadfence_system();
     epilogue_tail(p, acc, b, blockIdx.x, gridDim.x);
 }
 
