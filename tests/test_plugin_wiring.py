@@ -165,3 +165,90 @@ def test_backward_pass_reaches_the_boundary_with_the_transposed_native(phiml_env
     assert seen[0][2] == seen[1][2] == (nb, 384) and seen[1][3] == 2
     np.testing.assert_allclose(x_np, rec['x'], rtol=0, atol=1e-8 * np.abs(rec['x']).max())
     np.testing.assert_allclose(dy_np, rec['dy'], rtol=0, atol=1e-8 * np.abs(rec['dy']).max())
+
+
+def test_tracer_bridge_builds_the_reference_matrix(phiml_env):
+    """the bridge from ShiftLinTracer.val to the assembler returns the SAME CompressedSparseMatrix as the reference's
+    tracer_to_coo + compress_rows (dims, int32 indices / pointers, values, rank) for constant-coefficient ZERO-boundary operators and
+    leaves everything else (periodic, zero-gradient = variable diagonal) to the reference.  Arrays come from the oracle HERE (no GPU);
+    on the device they come from phb200_stencil_to_csr, pinned byte for byte by test_device_assembly_bit_exact."""
+    import torch
+    from phiml import math
+    from phiml.math import spatial, channel, extrapolation
+    from phiml.math._lin_trace import matrix_from_function
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly
+    from oracle.assemble import stencil_csr
+    from _util import ADVDIFF
+
+    def neg_laplace(x): return -math.laplace(x, padding=extrapolation.ZERO)
+    def periodic(x): return -math.laplace(x, padding=extrapolation.PERIODIC)
+    def zero_gradient(x): return -math.laplace(x, padding=extrapolation.ZERO_GRADIENT)
+
+    def advdiff(x):
+        dims = 'xyz'[:x.shape.spatial_rank]
+        u = math.wrap(list(ADVDIFF['velocity'][:len(dims)]), channel(gradient=','.join(dims)))
+        g = math.spatial_gradient(x, padding=extrapolation.ZERO, difference='central', stack_dim=channel(gradient=','.join(dims)))
+        return x + ADVDIFF['c'] * math.sum(g * u, 'gradient') - ADVDIFF['nu'] * math.laplace(x, padding=extrapolation.ZERO)
+
+    def oracle_assemble(grid, offsets, coeffs, dtype):
+        csr = stencil_csr(grid, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    bridged = lt.tracer_to_coo            # the plug-in's wrapper (not eligible here: no GPU)
+    original = phiml_env[0]._INSTALLED['original_t2c']
+    try:
+        for prec in (32, 64):
+            for f, shape, expect in ((neg_laplace, dict(x=6, y=5), True), (neg_laplace, dict(x=5, y=4, z=8), True), (advdiff, dict(x=6, y=5, z=4), True),
+                                     (neg_laplace, dict(x=9), True), (periodic, dict(x=6, y=5), False), (zero_gradient, dict(x=6, y=5), False)):
+                with math.precision(prec):
+                    x0 = math.zeros(spatial(**shape))
+                    lt.tracer_to_coo = original
+                    ref, _ = matrix_from_function(f, x0, auto_compress=True)
+                    assembly.STATS.update(device_assemblies=0, fallbacks=0)
+                    lt.tracer_to_coo = assembly.make_tracer_to_coo(original, lambda: True, oracle_assemble)
+                    mine, _ = matrix_from_function(f, x0, auto_compress=True)
+                assert (assembly.STATS['device_assemblies'] == 1) == expect, (f.__name__, assembly.STATS)
+                assert type(mine) is type(ref) and mine.shape == ref.shape
+                assert mine._compressed_dims == ref._compressed_dims and mine._uncompressed_dims == ref._uncompressed_dims
+                for name, dim in (('_indices', 'sp_entries'), ('_pointers', 'pointers'), ('_values', 'sp_entries')):
+                    a, b = np.asarray(getattr(mine, name).native(dim)), getattr(ref, name).numpy(dim)
+                    assert a.dtype == b.dtype and np.array_equal(a, b), (f.__name__, name)
+                assert float(mine._matrix_rank) == float(ref._matrix_rank)
+    finally:
+        lt.tracer_to_coo = bridged
+
+
+def test_front_end_solves_on_the_bridged_matrix(phiml_env):
+    """math.solve_linear with a jit_compile_linear function whose matrix came through the bridge (torch CPU natives here) gives the
+    reference's result: the bridged CompressedSparseMatrix is a drop-in for everything downstream (native_matrix, packing, SolveTape)."""
+    import os
+    import torch
+    from phiml import math
+    from phiml.math import spatial, batch, Solve, SolveTape, extrapolation
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly
+    from oracle.assemble import stencil_csr
+    plugin, TORCH = phiml_env
+
+    def oracle_assemble(grid, offsets, coeffs, dtype):
+        csr = stencil_csr(grid, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    bridged = lt.tracer_to_coo
+    lt.tracer_to_coo = assembly.make_tracer_to_coo(plugin._INSTALLED['original_t2c'], lambda: True, oracle_assemble)
+    try:
+        assembly.STATS.update(device_assemblies=0, fallbacks=0)
+        f = math.jit_compile_linear(lambda x: -math.laplace(x, padding=extrapolation.ZERO))
+        with TORCH, math.precision(32):
+            y = math.tensor(np.random.default_rng(0).standard_normal((3, 16, 16)).astype(np.float32), batch('b'), spatial('x,y'))
+            solve = Solve('CG', 1e-5, 0, x0=math.zeros(spatial(x=16, y=16)), max_iterations=1000)
+            with SolveTape() as tape:
+                x = math.solve_linear(f, y, solve)
+            info = tape[solve]
+        assert assembly.STATS['device_assemblies'] == 1
+    finally:
+        lt.tracer_to_coo = bridged
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'frontend.npz'))
+    np.testing.assert_allclose(x.numpy('b,x,y'), g['front/torch/cg16/x'], rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(info.iterations.numpy('b'), g['front/torch/cg16/iterations'])
