@@ -88,6 +88,7 @@ struct L2Window {
 };
 L2Window& l2_window();
 L2Window l2_persist_window(void* base, size_t bytes);
+int l2_persist_mode();   // 0 off, 1 window on q, 2 window on r
 #define PHB_LAUNCH_PDL(kernel, grid, block, smem, strm, ...)                                  \
     do {                                                                                        \
         cudaLaunchConfig_t _cfg = {};                                                           \
@@ -369,6 +370,27 @@ template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ld
 
 // PDL: wait until every kernel launched before this one on the stream has completed and its writes are visible (a no-op
 // for an ordinary launch); then let the NEXT kernel of the stream start getting resident.
+// L2 eviction-priority policies (createpolicy) and 16-byte global accesses that carry one.  kind: 0 plain, 1 evict_last (keep), 2 evict_first
+// (stream).  Used by the fused CG pair to keep the residual in the 126 MB L2 between its three accesses per iteration.
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld16_hint(const void* ptr, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st16_hint(void* ptr, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void pdl_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -26,6 +26,7 @@ struct PhaseOrder {
     int64_t plane;
     int xchunk, chunks;
     int64_t planes;
+    unsigned keep_mask = 0, stream_mask = 0;   // vectors whose 16-byte accesses carry an L2 evict_last / evict_first policy
 };
 
 // Slab mode, fused halo exchange: a phase functor that defines `peer` (PeerHalo) makes k_phase ALSO store array 0 on the first /
@@ -70,6 +71,8 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
 #pragma unroll
         for (int a = 0; a < NA; ++a) base[a] = (T*)p.v[a] + off + (((P::SHARED >> a) & 1u) ? (int64_t)0 : (int64_t)b * ld);
         using VT = typename Vec<T>::type;
+        const bool hinted = (ord.keep_mask | ord.stream_mask) != 0 && sizeof(VT) == 16;
+        const uint64_t pol_keep = hinted ? l2_policy_keep() : 0, pol_stream = hinted ? l2_policy_stream() : 0;
         const int64_t n_log = ord.plane == 0 ? n : (int64_t)ord.chunks * ord.xchunk * ord.plane;
         const int64_t per_step = (int64_t)ord.chunks * ord.plane;
         // two groups of V elements per trip: all loads of both groups are issued before the first use (bytes in flight),
@@ -101,6 +104,8 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
                     if constexpr (((P::RMASK >> a) & 1u) != 0) {
                         if (ok[u]) {
                             if constexpr (V == 1) e[u][a][0] = base[a][idx[u]];
+                            else if (hinted && (((ord.keep_mask | ord.stream_mask) >> a) & 1u))
+                                *reinterpret_cast<uint4*>(&e[u][a][0]) = ld16_hint(base[a] + idx[u], ((ord.keep_mask >> a) & 1u) ? pol_keep : pol_stream);
                             else *reinterpret_cast<VT*>(&e[u][a][0]) = *reinterpret_cast<const VT*>(base[a] + idx[u]);
                         }
                     } else {
@@ -125,6 +130,8 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
                     constexpr int a = decltype(A)::value;
                     if constexpr (((P::WMASK >> a) & 1u) != 0) {
                         if constexpr (V == 1) base[a][idx[u]] = e[u][a][0];
+                        else if (hinted && (((ord.keep_mask | ord.stream_mask) >> a) & 1u))
+                            st16_hint(base[a] + idx[u], *reinterpret_cast<const uint4*>(&e[u][a][0]), ((ord.keep_mask >> a) & 1u) ? pol_keep : pol_stream);
                         else *reinterpret_cast<VT*>(base[a] + idx[u]) = *reinterpret_cast<const VT*>(&e[u][a][0]);
                     }
                 });
@@ -155,18 +162,19 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
 }
 
 template <typename T, class P>
-int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0, PhaseOrder ord = PhaseOrder{0, 0, 0, 0}, bool pdl = false) {
+int launch_phase(const P& p, int64_t n, int64_t ld, int batch, cudaStream_t stream, int64_t off = 0, PhaseOrder ord = PhaseOrder{}, bool pdl = false) {
     constexpr int V = Vec<T>::N;
     bool aligned = (n % V == 0) && (ld % V == 0) && (off % V == 0);
     for (int a = 0; a < P::NA; ++a) aligned = aligned && (((uintptr_t)p.v[a]) % 16 == 0);
     if (ord.plane % V != 0) ord.plane = 0;
+    if (sizeof(T) * V != 16) ord.keep_mask = ord.stream_mask = 0;
     if (aligned) {
         dim3 grid((unsigned)grid_x((n / V + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, V>)), (unsigned)batch);
         if (pdl) PHB_LAUNCH_PDL((k_phase<T, P, V>), grid, dim3(kBlock), 0, stream, p, n, ld, off, ord);
         else PHB_LAUNCH((k_phase<T, P, V>), grid, kBlock, 0, stream, p, n, ld, off, ord);
     } else {
         dim3 grid((unsigned)grid_x((n + kBlock - 1) / kBlock, batch, occupancy(k_phase<T, P, 1>)), (unsigned)batch);
-        PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld, off, PhaseOrder{0, 0, 0, 0});
+        PHB_LAUNCH((k_phase<T, P, 1>), grid, kBlock, 0, stream, p, n, ld, off, PhaseOrder{});
     }
     return PHB200_OK;
 }

@@ -1125,9 +1125,11 @@ struct Run {
     }
     // the residual half walks the chunks of the stencil kernel backwards (PhaseOrder): L2 reuse of q and r
     PhaseOrder resid_order() {
-        PhaseOrder o{0, 0, 0, 0};
+        PhaseOrder o{};
         static int mode = -1;
         if (mode < 0) { const char* e = getenv("PHB200_PHASE_ORDER"); mode = (e && e[0] == '1') ? 1 : 0; }   // off by default: measured neutral without L2 eviction hints
+        o.keep_mask = l2_hints(1);
+        o.stream_mask = l2_hints(2);
         if (!mode || !s->tma_ok) return o;
         dim3 grid;
         int xchunk;
@@ -1139,6 +1141,16 @@ struct Run {
         o.chunks = (int)((o.planes + xchunk - 1) / xchunk);
         return o;
     }
+    // PHB200_L2_HINTS=<stencil kernel bits, hex>,<residual kernel keep mask>,<residual kernel stream mask>  (see star_tma.cuh, phase.cuh)
+    static unsigned l2_hints(int which) {
+        static unsigned v[3] = {0, 0, 0};
+        static bool parsed = false;
+        if (!parsed) {
+            parsed = true;
+            if (const char* e = getenv("PHB200_L2_HINTS")) sscanf(e, "%x,%x,%x", &v[0], &v[1], &v[2]);
+        }
+        return v[which];
+    }
     template <class P> int phase_ordered(const P& p, const PhaseOrder& ord) {
         prof_begin();
         int r = launch_phase<T, P>(p, s->n_act, ld, batch, st, s->off, ord, true);
@@ -1147,9 +1159,15 @@ struct Run {
     }
     template <int PRE>
     int pass_cg_fused_t(T* X, T* R) {
-        // experimental (PHB200_L2_PERSIST=1): keep q, written by the first half and read by the second, in the persisting part of L2
-        l2_window() = l2_persist_window(vec(1), sizeof(T) * (size_t)batch * (size_t)ld);
+        // experimental (PHB200_L2_PERSIST=q|r): keep q (written by the first half, read by the second) or r (read by both halves,
+        // rewritten by the second) in the persisting part of L2
+        const int l2m = l2_persist_mode();
+        static int which = -1;      // PHB200_L2_WHICH: 1 stencil kernel only, 2 residual kernel only, 3 both (default)
+        if (which < 0) { const char* e = getenv("PHB200_L2_WHICH"); which = e ? atoi(e) : 3; }
+        const L2Window win = l2m ? l2_persist_window(l2m == 2 ? (void*)R : (void*)vec(1), sizeof(T) * (size_t)batch * (size_t)ld) : L2Window{nullptr, 0, 0.f};
+        if (which & 1) l2_window() = win;
         int r = fused_first<PRE>(X, R);
+        l2_window() = (which & 2) ? win : L2Window{nullptr, 0, 0.f};
         if (r == PHB200_OK) r = phase_ordered(make_resid<PRE>(R), resid_order());
         l2_window() = L2Window{nullptr, 0, 0.f};
         return r;
@@ -1211,7 +1229,7 @@ struct Run {
         dim3 grid;
         int xchunk;
         star_grid(s->A->star, batch, occ, grid, xchunk);
-        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e, l2_hints(0));
         return PHB200_OK;
     }
     int pass_cg_fused(T* X, T* R, const T* Y, bool refresh) {
@@ -1323,7 +1341,7 @@ struct Run {
         dim3 grid;
         int xchunk;
         star_grid(s->A->star, batch, occ, grid, xchunk);
-        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, apply_x, e);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, apply_x, e, 0u);
         return PHB200_OK;
     }
     int pass_cg_adaptive_fused(T* X, T* R, const T* Y, bool refresh) {

@@ -36,28 +36,38 @@ L2Window& l2_window() {
     return w;
 }
 
-// PHB200_L2_PERSIST=1 (experimental): sizes the persisting part of L2 once per device and returns the window for `bytes` at `base`;
-// {nullptr} when the option is off or the device has no persisting L2.
-L2Window l2_persist_window(void* base, size_t bytes) {
+// PHB200_L2_PERSIST=q|r (experimental; 1 = q): sizes the persisting part of L2 once per device and returns the window for `bytes` at
+// `base`; {nullptr} when the option is off or the device has no persisting L2.
+int l2_persist_mode() {
     static int mode = -1;
-    static size_t carve = 0, max_window = 0;
     if (mode < 0) {
         const char* e = getenv("PHB200_L2_PERSIST");
-        mode = (e && e[0] == '1') ? 1 : 0;
-        if (mode) {
+        mode = !e ? 0 : (e[0] == '1' || e[0] == 'q') ? 1 : e[0] == 'r' ? 2 : 0;
+    }
+    return mode;
+}
+
+L2Window l2_persist_window(void* base, size_t bytes) {
+    static int ready = -1;
+    static size_t carve = 0, max_window = 0;
+    if (ready < 0) {
+        ready = 0;
+        if (l2_persist_mode()) {
             int dev = 0;
             cudaDeviceProp prop;
             if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
                 carve = (size_t)prop.persistingL2CacheMaxSize;
+                if (const char* f = getenv("PHB200_L2_CARVE_MB")) carve = std::min(carve, (size_t)atoll(f) << 20);
                 max_window = (size_t)prop.accessPolicyMaxWindowSize;
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); mode = 0; }
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) ready = 1;
+                else cudaGetLastError();
+                if (getenv("PHB200_L2_VERBOSE")) fprintf(stderr, "[phb200] L2 %d MB, persisting max %zu MB (carve %zu MB), window max %zu MB\n", prop.l2CacheSize >> 20, (size_t)prop.persistingL2CacheMaxSize >> 20, carve >> 20, max_window >> 20);
             } else {
                 cudaGetLastError();
-                mode = 0;
             }
         }
     }
-    if (!mode || !base || bytes == 0) return L2Window{nullptr, 0, 0.f};
+    if (ready != 1 || !base || bytes == 0) return L2Window{nullptr, 0, 0.f};
     const size_t win = bytes < max_window ? bytes : max_window;
     const float hit = win <= carve ? 1.0f : (float)((double)carve / (double)win);
     return L2Window{base, win, hit};

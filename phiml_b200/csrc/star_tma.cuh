@@ -84,12 +84,38 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+                 : "memory");
+}
+template <typename T> __device__ __forceinline__ Quad<T> ld4_hint(const T* p, uint64_t pol) {
+    Quad<T> q;
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<uint4*>(&q.v[0]) = ld16_hint(p, pol);
+    } else {
+        *reinterpret_cast<uint4*>(&q.v[0]) = ld16_hint(p, pol);
+        *reinterpret_cast<uint4*>(&q.v[2]) = ld16_hint(p + 2, pol);
+    }
+    return q;
+}
+template <typename T> __device__ __forceinline__ void st4_hint(T* p, const Quad<T>& q, uint64_t pol) {
+    if constexpr (sizeof(T) == 4) {
+        st16_hint(p, *reinterpret_cast<const uint4*>(&q.v[0]), pol);
+    } else {
+        st16_hint(p, *reinterpret_cast<const uint4*>(&q.v[0]), pol);
+        st16_hint(p + 2, *reinterpret_cast<const uint4*>(&q.v[2]), pol);
+    }
+}
+
+// L2 hint bits of k_star_cg_tma (two bits per stream: 0 plain, 1 keep = evict_last, 2 stream = evict_first):
+//   bits 0-1 r (TMA loads), 2-3 d_old (TMA loads), 4-5 x (loads and stores), 6-7 d_new (stores), 8-9 q (stores)
 // PRE: 0 none, 3 Jacobi with constant inverse diagonal
 // ALG 0: CG direction d = M^-1 r + beta d ; ALG 1: CG-adaptive direction d = r - (r.q / d.q) d with the second dot d.r
 template <typename T, int PRE, class Epi, bool UNIT, int ALG = 0>
 __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_a,
                                                         const __grid_constant__ CUtensorMap tm_b, StarDesc st, T* __restrict__ X, T* buf_a, T* buf_b,
-                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, int apply_x, Epi epi) {
+                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, int apply_x, Epi epi, unsigned l2h = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TB = tile_bytes<T>();
     constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
@@ -126,6 +152,9 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
 
+        const uint64_t pol_keep = l2h ? l2_policy_keep() : 0, pol_stream = l2h ? l2_policy_stream() : 0;
+        auto pol_of = [&](unsigned sh) { return ((l2h >> sh) & 3u) == 1u ? pol_keep : pol_stream; };
+        auto has = [&](unsigned sh) { return ((l2h >> sh) & 3u) != 0u; };
         const T ad_rq = (T)epi.sys[b].s[5 /*S_RQ*/], ad_dq = (T)epi.sys[b].s[3 /*S_DQ*/];
         auto dir = [&](T rv, T dv) {
             if constexpr (ALG == 1) {      // AdDirection: d = r - safe_div(rq * d, dq)
@@ -162,8 +191,10 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 const uint32_t bar = smem_u32(&bars[issue_stg]);
                 unsigned char* tr = tiles0 + (size_t)(2 * issue_stg) * TB;
                 mbar_expect_tx(bar, kTxBytes);
-                tma_load_4d(smem_u32(tr), &tm_r, bar, z0 - 4, y0 - 1, px, b);
-                tma_load_4d(smem_u32(tr + TB), tm_old, bar, z0 - 4, y0 - 1, px, b);
+                if (has(0)) tma_load_4d_hint(smem_u32(tr), &tm_r, bar, z0 - 4, y0 - 1, px, b, pol_of(0));
+                else tma_load_4d(smem_u32(tr), &tm_r, bar, z0 - 4, y0 - 1, px, b);
+                if (has(2)) tma_load_4d_hint(smem_u32(tr + TB), tm_old, bar, z0 - 4, y0 - 1, px, b, pol_of(2));
+                else tma_load_4d(smem_u32(tr + TB), tm_old, bar, z0 - 4, y0 - 1, px, b);
                 issue_stg = issue_stg + 1 == kStages ? 0 : issue_stg + 1;
             };
 
@@ -178,7 +209,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 const bool owned = mine && k >= 1 && k <= P - 2;
                 // the x values of the next owned plane travel while this plane is processed
                 Quad<T> x_next{{T(0), T(0), T(0), T(0)}};
-                if (apply_x && mine && k <= P - 3) x_next = ld4<T>(xb + off + pstride);
+                if (apply_x && mine && k <= P - 3) x_next = has(4) ? ld4_hint<T>(xb + off + pstride, pol_of(4)) : ld4<T>(xb + off + pstride);
                 mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
                 phase_bits ^= 1u << stg;
                 T(*rt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg) * TB);
@@ -194,11 +225,13 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                     for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
                     st4(&pl[sr][c], dn);
                     if (owned) {
-                        st4(d_new + off, dn);
+                        if (has(6)) st4_hint(d_new + off, dn, pol_of(6));
+                        else st4(d_new + off, dn);
                         if (apply_x) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
-                            st4(xb + off, x_cur);
+                            if (has(4)) st4_hint(xb + off, x_cur, pol_of(4));
+                            else st4(xb + off, x_cur);
                         }
                     } else if ((k == 0 && halo_lo) || (k == P - 1 && halo_hi)) {
                         st4(d_new + off, dn);
@@ -260,7 +293,8 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                     }
                     acc[0] += (double)part;        // the four products of a quad are added in T before they join the double sum
                     if constexpr (ALG == 1) acc[1] += (double)part_r;
-                    st4(qb + off - pstride, out);
+                    if (has(8)) st4_hint(qb + off - pstride, out, pol_of(8));
+                    else st4(qb + off - pstride, out);
                 }
                 off += pstride;
                 r_prev = rv_keep;
