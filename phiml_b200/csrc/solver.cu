@@ -1133,7 +1133,8 @@ struct Run {
         if (!mode || !s->tma_ok) return o;
         dim3 grid;
         int xchunk;
-        star_grid(s->A->star, batch, s->tma_occ > 0 ? s->tma_occ : 1, grid, xchunk);
+        star_grid_balanced(s->A->star, batch, s->tma_occ > 0 ? s->tma_occ : 1, grid, xchunk);
+        if (xchunk <= 0) return o;          // balanced decomposition: no common chunk structure to walk backwards
         const StarDesc& sd = s->A->star;
         o.plane = sd.ny * sd.nz;
         o.xchunk = xchunk;
@@ -1143,7 +1144,10 @@ struct Run {
     }
     // PHB200_L2_HINTS=<stencil kernel bits, hex>,<residual kernel keep mask>,<residual kernel stream mask>  (see star_tma.cuh, phase.cuh)
     static unsigned l2_hints(int which) {
-        static unsigned v[3] = {0, 0, 0};
+        // default: the residual kernel keeps r (evict_last: the next stencil pass reads it) and streams q (evict_first: dead after this read) —
+        // measured -2.7 % per iteration at 256^3, neutral at 512^3 / 128^3; evict_first on d_old / x / d' in the stencil kernel gains 4 % at 256^3
+        // but costs 6 % at 512^3 (halo rows of the neighbouring tiles leave L2 too early) — profiles/r02_l2_residency_experiments.jsonl
+        static unsigned v[3] = {0, 1, 2};
         static bool parsed = false;
         if (!parsed) {
             parsed = true;
@@ -1228,7 +1232,7 @@ struct Run {
         s->tma_occ = occ;
         dim3 grid;
         int xchunk;
-        star_grid(s->A->star, batch, occ, grid, xchunk);
+        star_grid_balanced(s->A->star, batch, occ, grid, xchunk);
         PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e, l2_hints(0));
         return PHB200_OK;
     }
@@ -1340,7 +1344,7 @@ struct Run {
         s->tma_occ = occ;
         dim3 grid;
         int xchunk;
-        star_grid(s->A->star, batch, occ, grid, xchunk);
+        star_grid_balanced(s->A->star, batch, occ, grid, xchunk);
         PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, apply_x, e, 0u);
         return PHB200_OK;
     }

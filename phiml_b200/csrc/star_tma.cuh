@@ -48,8 +48,12 @@ inline bool make_star_tmap(CUtensorMap* out, const void* base, int dtype, const 
     for (int k = 0; k < 3; ++k)
         if (strides[k] % 16 != 0 || strides[k] >= (1ull << 40)) return false;
     if (((uintptr_t)base) % 16 != 0) return false;
+    static int promo = -1;            // PHB200_TMA_PROMO: 0 none, 1 64 B, 2 128 B (default), 3 256 B
+    if (promo < 0) { const char* e = getenv("PHB200_TMA_PROMO"); promo = e ? atoi(e) : 2; }
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     CUresult r = fn(out, dtype == PHB200_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -83,6 +87,51 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
                  "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+
+// Work decomposition of the plane-marching kernels.  xchunk > 0: items = (x-chunk of xchunk planes) x (y-z tile), grid-stride.
+// xchunk <= 0 (balanced): the tiles x planes space, ordered tile-major, is cut into gridDim.x equal ranges; a CTA walks its range as one
+// or two x-segments (the range may run over the end of a tile's column into the next tile).  With 64 tiles and 444 resident CTAs
+// (256^3, 3 CTAs per SM) equal chunks can only use 6 x 64 = 384 CTAs — 60 SM slots stay empty; equal ranges fill every slot.
+struct SegIter {
+    int64_t x0, x1;
+    int ty, tz;
+    int64_t u, u_end, planes, xb;
+    int64_t item, items;
+    int xchunk, tiles_y, tiles_z;
+    __device__ SegIter(const StarDesc& st, int xchunk_, int tiles_y_, int tiles_z_) : xchunk(xchunk_), tiles_y(tiles_y_), tiles_z(tiles_z_) {
+        planes = st.xe - st.xb;
+        xb = st.xb;
+        if (xchunk <= 0) {
+            const int64_t W = (int64_t)tiles_y * tiles_z * planes;
+            u = W * (int64_t)blockIdx.x / gridDim.x;
+            u_end = W * ((int64_t)blockIdx.x + 1) / gridDim.x;
+        } else {
+            item = blockIdx.x;
+            items = ((planes + xchunk - 1) / xchunk) * tiles_y * tiles_z;
+        }
+    }
+    __device__ bool next() {
+        if (xchunk <= 0) {
+            if (u >= u_end) return false;
+            const int64_t tile = u / planes, xs = u - tile * planes;
+            const int64_t len = min(planes - xs, u_end - u);
+            tz = (int)(tile % tiles_z);
+            ty = (int)(tile / tiles_z);
+            x0 = xb + xs;
+            x1 = x0 + len;
+            u += len;
+            return true;
+        }
+        if (item >= items) return false;
+        tz = (int)(item % tiles_z);
+        ty = (int)((item / tiles_z) % tiles_y);
+        const int64_t ch = item / ((int64_t)tiles_z * tiles_y);
+        x0 = xb + ch * xchunk;
+        x1 = min(xb + planes, x0 + xchunk);
+        item += gridDim.x;
+        return true;
+    }
+};
 
 __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t pol) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
@@ -148,8 +197,6 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         const T beta = (T)epi.sys[b].s[1 /*S_BETA*/], alpha = (T)epi.sys[b].s[0 /*S_ALPHA*/];
         const int64_t nx = st.nx, ny = st.ny, nz = st.nz;
         const int tiles_z = (int)((nz + SZ - 1) / SZ), tiles_y = (int)((ny + SY - 1) / SY);
-        const int chunks = (int)((st.xe - st.xb + xchunk - 1) / xchunk);
-        const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
 
         const uint64_t pol_keep = l2h ? l2_policy_keep() : 0, pol_stream = l2h ? l2_policy_stream() : 0;
@@ -177,9 +224,10 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         uint32_t stg = 0, phase_bits = 0;      // next stage to be consumed; bit s = parity the next wait on stage s expects
         uint32_t issue_stg = 0;                // next stage to be filled (thread 0)
 
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-            const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
-            const int64_t x0 = st.xb + (int64_t)ch * xchunk, x1 = min(st.xe, x0 + xchunk);
+        SegIter seg(st, xchunk, tiles_y, tiles_z);
+        while (seg.next()) {
+            const int tz = seg.tz, ty = seg.ty;
+            const int64_t x0 = seg.x0, x1 = seg.x1;
             const int y0 = ty * SY, z0 = tz * SZ;
             const int jy = y0 + warp, jz = z0 + 4 * lane;
             const bool mine = jy < ny && jz < nz;
@@ -345,15 +393,14 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
         T* __restrict__ yb = Y + (int64_t)b * ldy;
         const int64_t ny = st.ny, nz = st.nz;
         const int tiles_z = (int)((nz + SZ - 1) / SZ), tiles_y = (int)((ny + SY - 1) / SY);
-        const int chunks = (int)((st.xe - st.xb + xchunk - 1) / xchunk);
-        const int64_t items = (int64_t)chunks * tiles_y * tiles_z;
         const T c0 = (T)st.c0, cxm = (T)st.cxm, cxp = (T)st.cxp, cym = (T)st.cym, cyp = (T)st.cyp, czm = (T)st.czm, czp = (T)st.czp;
         const int64_t pstride = ny * nz;
         const int c = 4 + 4 * lane, sr = warp + 1;
         uint32_t stg = 0, phase_bits = 0, issue_stg = 0;
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-            const int tz = (int)(item % tiles_z), ty = (int)((item / tiles_z) % tiles_y), ch = (int)(item / ((int64_t)tiles_z * tiles_y));
-            const int64_t x0 = st.xb + (int64_t)ch * xchunk, x1 = min(st.xe, x0 + xchunk);
+        SegIter seg(st, xchunk, tiles_y, tiles_z);
+        while (seg.next()) {
+            const int tz = seg.tz, ty = seg.ty;
+            const int64_t x0 = seg.x0, x1 = seg.x1;
             const int y0 = ty * SY, z0 = tz * SZ;
             const int jy = y0 + warp, jz = z0 + 4 * lane;
             const bool mine = jy < ny && jz < nz;
@@ -444,7 +491,7 @@ int launch_star_spmv_tma(const StarDesc& st, const T* X, int64_t ldx, T* Y, int6
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
             occ = v;
         }
-        star_grid(st, batch, occ, grid, xchunk);
+        star_grid_balanced(st, batch, occ, grid, xchunk);
         PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
     } else {
         auto kernel = k_star_spmv_tma<T, Epi, false>;
@@ -455,7 +502,7 @@ int launch_star_spmv_tma(const StarDesc& st, const T* X, int64_t ldx, T* Y, int6
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
             occ = v;
         }
-        star_grid(st, batch, occ, grid, xchunk);
+        star_grid_balanced(st, batch, occ, grid, xchunk);
         PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
     }
     *used = true;

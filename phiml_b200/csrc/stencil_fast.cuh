@@ -218,6 +218,9 @@ inline void star_grid(const StarDesc& st, int batch, int occ, dim3& grid, int& x
     if (resident < 1) resident = 1;
     const int64_t planes = st.xe - st.xb;
     int64_t chunks = resident / tiles;
+    static int max_chunks = -1;       // PHB200_STAR_CHUNKS: upper bound on the number of x-chunks (fewer chunks = fewer DRAM fronts)
+    if (max_chunks < 0) { const char* e = getenv("PHB200_STAR_CHUNKS"); max_chunks = e ? atoi(e) : 0; }
+    if (max_chunks > 0 && chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     if (chunks > planes) chunks = planes;
     xchunk = (int)((planes + chunks - 1) / chunks);
@@ -226,6 +229,26 @@ inline void star_grid(const StarDesc& st, int batch, int occ, dim3& grid, int& x
     int64_t items = chunks * tiles;
     int64_t gx = items < resident ? items : resident;
     if (gx < 1) gx = 1;
+    grid = dim3((unsigned)gx, (unsigned)batch);
+}
+
+// Balanced decomposition for the TMA kernels (SegIter in star_tma.cuh): every resident CTA slot gets an equal share of the
+// tiles x planes space; xchunk = 0 tells the kernel.  Off by default (PHB200_STAR_BALANCED=1 enables it): measured SLOWER than
+// equal x-chunks marched in lockstep (256^3: 81 vs 74 us, 512^3: 693 vs 608 us) although it fills all 444 CTA slots instead of 384 / 256 —
+// neighbouring tiles no longer sit on the same x-plane at the same time, so halo rows miss L2 and DRAM sees many more open fronts.
+inline void star_grid_balanced(const StarDesc& st, int batch, int occ, dim3& grid, int& xchunk) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("PHB200_STAR_BALANCED"); enabled = (e && e[0] == '1') ? 1 : 0; }
+    if (!enabled) { star_grid(st, batch, occ, grid, xchunk); return; }
+    const int64_t tiles = ((st.ny + SY - 1) / SY) * ((st.nz + SZ - 1) / SZ);
+    int64_t resident = ((int64_t)kSMs * (occ < 1 ? 1 : (occ > 8 ? 8 : occ))) / (batch < 1 ? 1 : batch);
+    if (resident < 1) resident = 1;
+    const int64_t work = tiles * (st.xe - st.xb);
+    // a range shorter than ~4 planes is mostly halo planes: use fewer CTAs then
+    int64_t gx = resident;
+    if (gx > work / 4) gx = work / 4;
+    if (gx < 1) gx = 1;
+    xchunk = 0;
     grid = dim3((unsigned)gx, (unsigned)batch);
 }
 
