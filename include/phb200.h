@@ -23,6 +23,7 @@
  *   phb200_jacobi_setup                NEW ('jacobi' is absent from compute_preconditioner, phiml/math/_optimize.py:836-880)
  *   phb200_precond_ilu_sweeps          incomplete_lu_coo                  phiml/backend/_linalg.py:524-594
  *   phb200_precond_ilu0                its fixed point (exact ILU(0))
+ *   phb200_precond_cluster             ExplicitClusterSolve.apply          phiml/backend/_linalg.py:734-766
  *   phb200_sptrsv                      Backend.solve_triangular_sparse    phiml/backend/_backend.py:1580-1586, _numpy_backend.py:579-580
  */
 #ifndef PHB200_H
@@ -60,6 +61,7 @@ extern "C" {
 #define PHB200_PRE_NONE 0
 #define PHB200_PRE_JACOBI 1
 #define PHB200_PRE_ILU 2
+#define PHB200_PRE_CLUSTER 3
 
 /* matrix kinds */
 #define PHB200_MAT_CSR 0
@@ -156,6 +158,14 @@ int phb200_precond_ilu0(phb200_precond** out, const phb200_matrix* A, void* lu_v
  * available (L is then described by the diagonal of the sweep before the last, U by the last one). */
 int phb200_precond_ilu_sweeps(phb200_precond** out, const phb200_matrix* A, void* lu_val, int sweeps, int safe,
                               const phb200_matrix* stencil_twin /* may be NULL */, void* stream);
+/* The reference's 'cluster' preconditioner (ExplicitClusterSolve, phiml/backend/_linalg.py:734-766; built by explicit_coarse /
+ * coarse_explicit_preconditioner_coo, phiml/math/_optimize.py:942-971, _linalg.py:769-799): M^-1 v = P C^-1 R v + (v - P (R v / size)),
+ * R = sum over the elements of a cluster (batched_bincount), C^-1 = dense inverse of the cluster_count^2 coarse matrix, P = gather by
+ * cluster.  All arrays are caller-owned device memory: cluster_of (n, int32), members (n, int32: element indices grouped by cluster,
+ * ascending inside a cluster), member_ptr (cluster_count + 1), inv_coarse (cluster_count^2, row-major) and cluster_size (cluster_count)
+ * in the vector dtype.  Application = three kernels: segmented sums (deterministic order), dense coarse product, prolongation + correction. */
+int phb200_precond_cluster(phb200_precond** out, const int32_t* cluster_of, const int32_t* members, const int32_t* member_ptr, int64_t n,
+                           int cluster_count, const void* inv_coarse, const void* cluster_size, int dtype);
 /* *star_wavefront = 1 if the triangular solves of an ILU preconditioner run as the structured wavefront of
  * csrc/star_trsv.cuh (factors of a recognised star stencil; 3 N w bytes per solve) instead of the CSR level solves.
  * The environment variable PHB200_TRSV=csr disables the wavefront form at set-up. */

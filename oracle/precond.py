@@ -146,3 +146,42 @@ class IncompleteLU:
 
     def __repr__(self):
         return f"ilu ({self.source})"
+
+
+def cluster_assignment(grid, cluster_count: int = 3 ** 6, dtype=np.float64):
+    """Cell -> cluster map of ``explicit_coarse`` for grid matrices (phiml/math/_optimize.py:947-960): one cluster per cell when the
+    grid has no more cells than clusters, else a box decomposition with ``round(size * (count / volume)^(1/rank))`` clusters per axis,
+    cluster coordinate = int(index / size * clusters_along_axis) evaluated in the working precision.  Returns (clusters int32 (N,), count)."""
+    grid = tuple(int(g) for g in grid)
+    n = int(np.prod(grid))
+    if cluster_count >= n:
+        return np.arange(n, dtype=np.int32), n
+    by_axis = np.round(np.asarray(grid) * (cluster_count / n) ** (1 / len(grid))).astype(np.int32)
+    ft = np.dtype(dtype).type
+    coords = [(np.arange(g).astype(ft) / ft(g) * ft(c)).astype(np.int32) for g, c in zip(grid, by_axis)]
+    mesh = np.meshgrid(*coords, indexing='ij')
+    clusters = np.ravel_multi_index([m.reshape(-1) for m in mesh], tuple(int(c) for c in by_axis)).astype(np.int32)
+    return clusters, int(np.prod(by_axis))
+
+
+class Cluster:
+    """ExplicitClusterSolve (phiml/backend/_linalg.py:734-766) with the parts of coarse_explicit_preconditioner_coo (:769-799):
+    coarse matrix = entries summed by (cluster of row, cluster of column), inverted densely with NumPy."""
+
+    def __init__(self, csr: sp.csr_matrix, clusters: np.ndarray, cluster_count: int):
+        self.clusters, self.cluster_count = clusters, cluster_count
+        coo = csr.tocoo()
+        coarse = np.zeros((cluster_count, cluster_count), csr.dtype)
+        np.add.at(coarse, (clusters[coo.row], clusters[coo.col]), coo.data)
+        self.inv_coarse = np.linalg.inv(coarse)
+        self.cluster_size = np.bincount(clusters, minlength=cluster_count).astype(csr.dtype)
+
+    def apply(self, v):
+        coarse = np.stack([np.bincount(self.clusters, weights=row, minlength=self.cluster_count) for row in v])
+        delta = v - (coarse / self.cluster_size)[:, self.clusters]
+        solution = (self.inv_coarse @ coarse.T).T
+        return (solution[:, self.clusters] + delta).astype(v.dtype)
+
+    def apply_inv_l(self, v): return v
+    def apply_inv_u(self, v): return self.apply(v)
+    def __repr__(self): return f"cluster ({self.cluster_count})"

@@ -7,7 +7,7 @@ mirror of the reference's Backend operator interface (solve.py, backend.py, prec
 """
 from ._engine import EngineError, load as load_library, launch_count
 from .sparse import Matrix, as_matrix, clear_cache
-from .precond import Preconditioner, JacobiPreconditioner, IncompleteLU, compute_preconditioner
+from .precond import Preconditioner, JacobiPreconditioner, IncompleteLU, ClusterPreconditioner, compute_preconditioner
 from .solve import (SolveResult, linear_solve, conjugate_gradient, conjugate_gradient_adaptive, bi_conjugate_gradient,
                     generic_conjugate_gradient, generic_conjugate_gradient_adaptive, mul_matrix_batched_vector, mul_csr_dense, mul_coo_dense,
                     solve_triangular_sparse, solve_triangular, DeviceSolver)

@@ -109,8 +109,36 @@ def build_compressed(info: dict, natives):
     indices = wrap(col, instance('sp_entries'))
     pointers = wrap(rowptr, instance('pointers'))
     vals = reshaped_tensor(values, [instance('sp_entries')], convert=False)
-    return CompressedSparseMatrix(indices, pointers, vals, info['src_shape'], info['out_shape'], True, uncompressed_indices=None,
-                                  uncompressed_indices_perm=None, m_rank=info['m_rank'])
+    m = CompressedSparseMatrix(indices, pointers, vals, info['src_shape'], info['out_shape'], True, uncompressed_indices=None,
+                               uncompressed_indices_perm=None, m_rank=info['m_rank'])
+    m._phb200_device_assembled = True      # a constant, like the reference's NumPy-backed matrix (phiml_plugin.attach_gradient_solve)
+    register_owner(m, values)
+    return m
+
+
+# PhiML hands constants around as detached copies (stop_gradient in key_from_args, phiml/math/_functional.py:147): new tensor objects over
+# the SAME storage on every call.  The residency caches of the plug-in need one stable object per matrix to tie their entries to:
+# the bridged matrix itself (kept alive by the LinearFunction that traced it), found again through the address of its value array.
+_OWNERS = {}
+
+
+def register_owner(matrix, values):
+    import weakref
+    key = int(values.data_ptr())
+    _OWNERS[key] = weakref.ref(matrix, lambda _r, k=key: _OWNERS.pop(k, None))
+
+
+def owner_of(values):
+    """The live bridged matrix whose value array shares storage (address, version, size) with ``values``, or None."""
+    try:
+        ref = _OWNERS.get(int(values.data_ptr()))
+    except Exception:
+        return None
+    m = ref() if ref is not None else None
+    if m is None:
+        return None
+    own = m._values._native
+    return m if (own.data_ptr() == values.data_ptr() and own._version == values._version and own.numel() == values.numel() and own.dtype == values.dtype) else None
 
 
 STATS = {'device_assemblies': 0, 'fallbacks': 0}

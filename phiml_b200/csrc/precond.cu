@@ -760,6 +760,76 @@ __global__ void __launch_bounds__(kBlock) k_scale_rows(const T* __restrict__ in,
         out[(int64_t)b * ld + i] = mul_rn(in[(int64_t)b * ld + i], w[i]);
 }
 
+// ---------------------------------------------------------------------------------------------- 'cluster' preconditioner
+// ExplicitClusterSolve.apply (phiml/backend/_linalg.py:741-753):  coarse = bincount(clusters, weights=vec);  delta = vec - (coarse / size)[clusters];
+// result = (inv_coarse @ coarse)[clusters] + delta.
+// k_cluster_restrict: one CTA per (cluster, system); members are summed in a fixed order (thread-strided partial sums in double, then a
+// shared-memory tree), so the result does not depend on scheduling — the reference's bincount adds in element order, torch's with atomics.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_cluster_restrict(const T* __restrict__ in, int64_t ld, const int32_t* __restrict__ members, const int32_t* __restrict__ ptr,
+                                                              int count, T* __restrict__ coarse) {
+    __shared__ double part[kBlock];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const T* v = in + (int64_t)b * ld;
+    double acc = 0.0;
+    for (int j = ptr[c] + threadIdx.x; j < ptr[c + 1]; j += kBlock) acc += (double)v[members[j]];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = kBlock / 2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) coarse[(int64_t)b * count + c] = (T)part[0];
+}
+
+// coarse_solution = inv_coarse @ coarse: one warp per (row, system), lanes stride over the row, sums in double
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_cluster_coarse_solve(const T* __restrict__ inv, const T* __restrict__ coarse, int count, T* __restrict__ sol) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (kBlock / 32) + warp, b = blockIdx.y;
+    if (i >= count) return;
+    const T* row = inv + (int64_t)i * count;
+    const T* cv = coarse + (int64_t)b * count;
+    double acc = 0.0;
+    for (int j = lane; j < count; j += 32) acc += (double)row[j] * (double)cv[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sol[(int64_t)b * count + i] = (T)acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_cluster_prolong(const T* __restrict__ in, T* __restrict__ out, int64_t n, int64_t ld, const int32_t* __restrict__ cl_of,
+                                                             const T* __restrict__ coarse, const T* __restrict__ sol, const T* __restrict__ size, int count) {
+    const int b = blockIdx.y;
+    const T* cv = coarse + (int64_t)b * count;
+    const T* sv = sol + (int64_t)b * count;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const int c = cl_of[i];
+        const T mean = cv[c] / size[c];
+        const T delta = add_rn(in[(int64_t)b * ld + i], -mean);
+        out[(int64_t)b * ld + i] = add_rn(sv[c], delta);
+    }
+}
+
+template <typename T>
+static int cluster_apply(const phb200_precond* p, const T* in, T* out, int64_t batch, int64_t ld, cudaStream_t stream) {
+    phb200_precond* q = const_cast<phb200_precond*>(p);     // scratch is bookkeeping
+    if (batch > q->cl_batch_cap) {
+        if (q->cl_scratch) PHB_CUDA(cudaFree(q->cl_scratch));
+        q->cl_scratch = nullptr;
+        PHB_CUDA(cudaMalloc(&q->cl_scratch, sizeof(T) * 2 * (size_t)batch * (size_t)p->cl_count));
+        q->cl_batch_cap = batch;
+    }
+    T* coarse = (T*)q->cl_scratch;
+    T* sol = coarse + (size_t)batch * p->cl_count;
+    const int C = p->cl_count;
+    PHB_LAUNCH(k_cluster_restrict<T>, dim3((unsigned)C, (unsigned)batch), kBlock, 0, stream, in, ld, p->cl_members, p->cl_ptr, C, coarse);
+    PHB_LAUNCH(k_cluster_coarse_solve<T>, dim3((unsigned)((C + kBlock / 32 - 1) / (kBlock / 32)), (unsigned)batch), kBlock, 0, stream, (const T*)p->cl_inv, (const T*)coarse, C, sol);
+    dim3 grid((unsigned)grid_x((p->n + kBlock - 1) / kBlock, batch), (unsigned)batch);
+    PHB_LAUNCH(k_cluster_prolong<T>, grid, kBlock, 0, stream, in, out, p->n, ld, p->cl_of, (const T*)coarse, (const T*)sol, (const T*)p->cl_size, C);
+    return PHB200_OK;
+}
+
 int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int64_t batch, int64_t ld, cudaStream_t stream) {
     if (p->kind == PHB200_PRE_JACOBI) {
         dim3 grid((unsigned)grid_x((p->n + kBlock - 1) / kBlock, batch), (unsigned)batch);
@@ -779,6 +849,11 @@ int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int6
         }
         if (p->dtype == PHB200_F32) return trsv<float>(p->lu, p->plan_l, 1, 1, (const float*)in, (float*)out, batch, ld, stream);
         return trsv<double>(p->lu, p->plan_l, 1, 1, (const double*)in, (double*)out, batch, ld, stream);
+    }
+    if (p->kind == PHB200_PRE_CLUSTER) {          // ExplicitClusterSolve.apply_inv_l: identity (_linalg.py:758-759)
+        const size_t w = p->dtype == PHB200_F32 ? 4 : 8;
+        if (in != out) PHB_CUDA(cudaMemcpy2DAsync(out, (size_t)ld * w, in, (size_t)ld * w, (size_t)p->n * w, (size_t)batch, cudaMemcpyDeviceToDevice, stream));
+        return PHB200_OK;
     }
     set_error("preconditioner kind %d has no apply_inv_l", p->kind);
     return PHB200_ERR_UNSUPPORTED;
@@ -801,6 +876,10 @@ int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp,
         }
         if (p->dtype == PHB200_F32) return trsv<float>(p->lu, p->plan_u, 0, 0, (const float*)out, (float*)out, batch, ld, stream);
         return trsv<double>(p->lu, p->plan_u, 0, 0, (const double*)out, (double*)out, batch, ld, stream);
+    }
+    if (p->kind == PHB200_PRE_CLUSTER) {
+        if (p->dtype == PHB200_F32) return cluster_apply<float>(p, (const float*)in, (float*)out, batch, ld, stream);
+        return cluster_apply<double>(p, (const double*)in, (double*)out, batch, ld, stream);
     }
     set_error("preconditioner kind %d cannot be applied", p->kind);
     return PHB200_ERR_UNSUPPORTED;
@@ -883,6 +962,26 @@ int phb200_precond_jacobi(phb200_precond** out, const void* inv_diag, int64_t n,
         p->is_const = 1;
         p->const_inv = dtype == PHB200_F32 ? (double)f : d;
     }
+    *out = p;
+    return PHB200_OK;
+}
+
+int phb200_precond_cluster(phb200_precond** out, const int32_t* cluster_of, const int32_t* members, const int32_t* member_ptr, int64_t n,
+                           int cluster_count, const void* inv_coarse, const void* cluster_size, int dtype) {
+    PHB_ARG(out && cluster_of && members && member_ptr && inv_coarse && cluster_size, "null argument");
+    PHB_ARG(n >= 1 && cluster_count >= 1 && cluster_count <= 65535, "need 1 <= cluster_count <= 65535, got %d", cluster_count);
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    phb200_precond* p = new phb200_precond();
+    memset(p, 0, sizeof(*p));
+    p->kind = PHB200_PRE_CLUSTER;
+    p->dtype = dtype;
+    p->n = n;
+    p->cl_of = cluster_of;
+    p->cl_members = members;
+    p->cl_ptr = member_ptr;
+    p->cl_inv = inv_coarse;
+    p->cl_size = cluster_size;
+    p->cl_count = cluster_count;
     *out = p;
     return PHB200_OK;
 }
@@ -1027,6 +1126,7 @@ int phb200_precond_destroy(phb200_precond* p) {
     if (p->tr_flags) cudaFree(p->tr_flags);
     if (p->tr_ticket) cudaFree(p->tr_ticket);
     if (p->sc_order) cudaFree(p->sc_order);
+    if (p->cl_scratch) cudaFree(p->cl_scratch);
     phb200_sptrsv_plan_destroy(p->plan_l);
     phb200_sptrsv_plan_destroy(p->plan_u);
     delete p;

@@ -44,6 +44,15 @@ struct phb200_precond {
     int64_t tr_flag_cap;               // counters allocated
     unsigned* tr_ticket;               // device, owned
     unsigned long long tr_epoch;       // host: value all counters of a finished launch stand at
+    // explicit coarse ('cluster') preconditioner, phiml/backend/_linalg.py:734-766 — all arrays caller-owned
+    const int32_t* cl_of;              // cluster of every element
+    const int32_t* cl_members;         // element indices grouped by cluster
+    const int32_t* cl_ptr;             // cl_count + 1 offsets into cl_members
+    const void* cl_inv;                // cl_count x cl_count inverse coarse matrix, row-major
+    const void* cl_size;               // cluster sizes in the vector dtype
+    int cl_count;
+    void* cl_scratch;                  // owned: 2 x cl_batch_cap x cl_count values (coarse vector, coarse solution)
+    int64_t cl_batch_cap;
 };
 
 namespace phb {

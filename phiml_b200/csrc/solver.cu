@@ -882,9 +882,12 @@ static void fill_base(F& f, const phb200_solver* s, bool always, bool freeze) {
     f.freeze = freeze ? 1 : 0;
 }
 
+// preconditioners applied by kernels of their own between the phases of a pass (not fusable into the stencil / phase kernels)
+static inline bool pre_applied(int pre) { return pre == PHB200_PRE_ILU || pre == PHB200_PRE_CLUSTER; }
+
 static int vectors_needed(int method, int L, int pre) {
     switch (method) {
-        case PHB200_CG: return pre == PHB200_PRE_ILU ? 4 : 3;              // d, q, d' (fused ping-pong) | d, q, s, tmp
+        case PHB200_CG: return pre_applied(pre) ? 4 : 3;              // d, q, d' (fused ping-pong) | d, q, s, tmp
         case PHB200_CG_ADAPTIVE: return 3;                                   // d, q, d' (fused ping-pong)
         case PHB200_CG_TORCH: return 4;                                      // d, q, d' (fused ping-pong) | t, t
         case PHB200_CG_ADAPTIVE_TORCH: return 4;                             // d, q, d', t
@@ -1039,7 +1042,7 @@ struct Run {
             PHB_TRY(spmv(X, q, e));
         }
         const bool bicg = method == PHB200_BICGSTAB;
-        if (s->pre == PHB200_PRE_ILU && method == PHB200_CG) {
+        if (pre_applied(s->pre) && method == PHB200_CG) {
             Residual<T> r0;
             fill_base(r0, s, true, false);
             r0.v[0] = R; r0.v[1] = Y; r0.v[2] = q;
@@ -1075,7 +1078,7 @@ struct Run {
         static int torch_on = -1;
         if (torch_on < 0) { const char* e = getenv("PHB200_CG_TORCH_FUSED"); torch_on = (e && e[0] == '0') ? 0 : 1; }
         const bool cg = s->method == PHB200_CG || (torch_on && s->method == PHB200_CG_TORCH && s->pre == PHB200_PRE_NONE && !s->totals);
-        return cg && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && !cb_mode();
+        return cg && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && !pre_applied(s->pre) && !cb_mode();
     }
     // 'CG-adaptive' / 'auto' on a star stencil: residual kernel + TMA stencil kernel (direction, x update, product, d.q, d.r)
     bool fused_adaptive() const {
@@ -1303,7 +1306,7 @@ struct Run {
             c.v[0] = d; c.v[1] = R; c.v[2] = s->M->inv_diag;
             return phase(c);
         }
-        if (s->pre == PHB200_PRE_ILU) {
+        if (pre_applied(s->pre)) {
             T* sv = vec(2);
             CgUpdate<T, 2> u;
             fill_base(u, s, false, fr);
@@ -1552,7 +1555,7 @@ static bool resident_plan(const phb200_solver* s, int& cs, int& lpc, size_t& sme
     if (!(s->method == PHB200_CG || s->method == PHB200_CG_TORCH || adaptive)) return false;
     if (adaptive && s->pre != PHB200_PRE_NONE) return false;
     if (s->A->kind != PHB200_MAT_STENCIL || !s->A->is_star || s->totals) return false;
-    if (s->pre == PHB200_PRE_ILU || (s->pre == PHB200_PRE_JACOBI && !s->M->is_const)) return false;
+    if (pre_applied(s->pre) || (s->pre == PHB200_PRE_JACOBI && !s->M->is_const)) return false;
     const StarDesc& st = s->A->star;
     if (st.xb != 0 || st.xe != st.nx || st.store_halo) return false;
     if (st.nz % 4 != 0 || st.nz > (1 << 20) || st.nx * st.ny > (1 << 20)) return false;
@@ -1877,7 +1880,7 @@ int phb200_solver_tol_min(phb200_solver* s, void* tol_min, int set, void* stream
 
 int phb200_solver_set_dist(phb200_solver* s, void* totals) {
     PHB_ARG(s && !s->started, "set_dist must be called before start");
-    PHB_ARG(s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && s->pre != PHB200_PRE_ILU && (s->pre == PHB200_PRE_NONE || s->M->is_const),
+    PHB_ARG(s->method == PHB200_CG && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && !pre_applied(s->pre) && (s->pre == PHB200_PRE_NONE || s->M->is_const),
             "distributed mode supports 'CG' on a star stencil without or with constant-diagonal Jacobi preconditioner");
     s->totals = (double*)totals;
     return PHB200_OK;
@@ -1887,7 +1890,7 @@ int phb200_solver_set_dist_callbacks(phb200_solver* s, void* totals, phb200_allr
     PHB_ARG(s && !s->started, "set_dist_callbacks must be called before start");
     PHB_ARG(totals && allreduce && halo, "null argument");
     PHB_ARG(s->A->kind == PHB200_MAT_STENCIL && s->A->is_star, "distributed solves need a star stencil in slab mode (phb200_matrix_set_slab)");
-    PHB_ARG(s->pre != PHB200_PRE_ILU, "ILU across slabs is a pipeline along x and is not supported in distributed mode");
+    PHB_ARG(!pre_applied(s->pre), "ILU across slabs is a pipeline along x (and 'cluster' a global coarse solve): not supported in distributed mode");
     s->totals = (double*)totals;
     s->ar_cb = allreduce;
     s->halo_cb = halo;

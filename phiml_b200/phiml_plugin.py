@@ -71,6 +71,7 @@ class _IdentityCache:
 
 NATIVE_CACHE = _IdentityCache()
 PRECOND_CACHE = _IdentityCache()
+DM_STATS = {'device': 0, 'reference': 0}      # matrix gradients of backward passes computed by the kernel / by the reference's rule
 
 
 def _is_sparse_cuda(m) -> bool:
@@ -88,8 +89,20 @@ def _on_path(lin, y) -> bool:
     return isinstance(y, torch.Tensor) and y.is_cuda
 
 
+def _device_tensor(t) -> bool:
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
+def _traceable(lin, y) -> bool:
+    """True while ``torch.jit.trace`` is recording (``math.jit_compile``) and the operands are a torch sparse matrix / tensors on CUDA:
+    the solve then goes through the registered operator ``phb200::linear_solve`` and becomes one node of the traced graph."""
+    if torch._C._get_tracing_state() is None:
+        return False
+    return isinstance(lin, torch.Tensor) and lin.layout != torch.strided and lin.is_cuda and isinstance(y, torch.Tensor) and y.is_cuda
+
+
 def _own_pre(pre) -> bool:
-    return pre is None or isinstance(pre, (_precond.JacobiPreconditioner, _precond.IncompleteLU))
+    return pre is None or isinstance(pre, (_precond.JacobiPreconditioner, _precond.IncompleteLU, _precond.ClusterPreconditioner))
 
 
 def install():
@@ -101,9 +114,16 @@ def install():
     from phiml.backend.torch import TORCH
     from phiml.backend.torch._torch_backend import TorchBackend
     import phiml.math._optimize as opt
+    from . import assembly
 
     def convert(r: _solve.SolveResult) -> PhiSolveResult:
         return PhiSolveResult(r.method, r.x, r.residual, r.iterations, r.function_evaluations, r.converged, r.diverged, r.message)
+
+    def traced(kind, method, lin, y, x0, rtol, atol, max_iter, pre, poly_order=2):
+        from . import torch_op
+        parts = torch_op.traced_linear_solve(method, lin, y, x0, rtol, atol, max_iter, pre)
+        name = _solve.method_string(kind, pre, np.asarray(max_iter).shape[0] > 1, poly_order, traced=True)
+        return PhiSolveResult(name, *parts, [""] * int(y.shape[0]))
 
     class B200TorchBackend(TorchBackend):
         """TorchBackend whose sparse linear-solve path runs on libphb200 (CUDA operands only)."""
@@ -131,16 +151,23 @@ def install():
 
         # --- solves ---
         def conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset):
+            if matrix_offset is None and _traceable(lin, y) and _own_pre(pre):
+                return traced('CG', 'CG', lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre)
             if matrix_offset is None and _on_path(lin, y) and _own_pre(pre):
                 return convert(_solve.conjugate_gradient(lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, None))
             return TorchBackend.conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset)
 
         def conjugate_gradient_adaptive(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset):
+            if matrix_offset is None and _traceable(lin, y) and _own_pre(pre):
+                return traced('CG-adaptive', 'CG-adaptive', lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre)
             if matrix_offset is None and _on_path(lin, y) and _own_pre(pre):
                 return convert(_solve.conjugate_gradient_adaptive(lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, None))
             return TorchBackend.conjugate_gradient_adaptive(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset)
 
         def bi_conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset, poly_order=2):
+            if matrix_offset is None and poly_order >= 1 and poly_order <= 4 and _traceable(lin, y) and _own_pre(pre):
+                method = 'biCG-stab' if poly_order == 1 else f'biCG-stab({poly_order})'
+                return traced('biCG-stab', method, lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, poly_order)
             if matrix_offset is None and poly_order >= 1 and poly_order <= 4 and _on_path(lin, y) and _own_pre(pre):
                 return convert(_solve.bi_conjugate_gradient(lin, self.to_float(y), self.to_float(x0), rtol, atol, max_iter, pre, None, poly_order))
             return TorchBackend.bi_conjugate_gradient(self, lin, y, x0, rtol, atol, max_iter, pre, matrix_offset, poly_order)
@@ -151,7 +178,7 @@ def install():
             raise NotImplementedError("sparse triangular solves run on CUDA torch tensors only (phb200); use the NumPy backend on the CPU")
 
     # the device-side preconditioners must be accepted wherever PhiML checks the protocol type
-    for cls in (_precond.JacobiPreconditioner, _precond.IncompleteLU):
+    for cls in (_precond.JacobiPreconditioner, _precond.IncompleteLU, _precond.ClusterPreconditioner):
         if PhiPreconditioner not in cls.__mro__:
             try:
                 cls.__bases__ = cls.__bases__ + (PhiPreconditioner,)
@@ -181,7 +208,17 @@ def install():
         # in-place edits of the arrays (an optimizer step under no_grad, .copy_) bump torch's version counters: a stale native or
         # stale factors must not be served for them
         versions = tuple(getattr(t, '_version', None) for t in (values, indices, pointers))
-        return values, (type(matrix).__name__, id(indices), id(pointers), repr(matrix.shape), versions) + layout, (indices, pointers)
+
+        def ident(t):      # torch tensors by storage address (detached copies share it), anything else by object identity
+            return ('t', int(t.data_ptr()), int(t.numel())) if isinstance(t, torch.Tensor) else ('o', id(t))
+        obj = values
+        if isinstance(values, torch.Tensor):
+            # device-assembled constants arrive as detached copies (new objects over the same storage on every call): tie the
+            # entry to the bridged matrix that owns the storage
+            owner = assembly.owner_of(values)
+            if owner is not None:
+                obj = owner
+        return obj, (type(matrix).__name__, ident(indices), ident(pointers), repr(matrix.shape), versions) + layout, (indices, pointers)
 
     def native_matrix(value, target_backend):
         """phiml.math._sparse.native_matrix with residency: one conversion / upload per live matrix and backend."""
@@ -206,9 +243,36 @@ def install():
         if method == 'ilu' and cuda_torch and not (solver or '').startswith('scipy-'):
             rd = np.asarray(rank_deficiency.numpy() if hasattr(rank_deficiency, 'numpy') else rank_deficiency)
             safe = bool(np.any(rd > 0))                     # factor_ilu(matrix, iterations, safe=(rank_deficiency > 0).any), _optimize.py:869
-            make = lambda: _precond.IncompleteLU(native_matrix(matrix, TORCH), safe=safe, rank_deficiency=rd)
+            sweeps = None                                   # eager rule: ceil(sqrt(d n^(1/d))), precond.ilu_sweeps
+            if opt._TRACING_JIT and getattr(matrix, 'available', False):
+                # "high-quality preconditioner when jit-compiling with constant matrix" (_optimize.py:863-865): ceil(n^(1/d)) sweeps
+                import math as _m
+                from phiml.math import dual as _dual
+                from phiml.math._sparse import stored_values as _stored
+                n_ = _dual(matrix).volume
+                d_ = (_stored(matrix).shape.volume / n_ - 1) / 2
+                if d_ >= 1:
+                    sweeps = int(_m.ceil(n_ ** (1 / d_)))
+            make = lambda: _precond.IncompleteLU(native_matrix(matrix, TORCH), sweeps=sweeps, safe=safe, rank_deficiency=rd)
             obj, key, pins = anchor(matrix)
-            return PRECOND_CACHE.get(obj, ('ilu', safe) + key, make, pins) if obj is not None else make()
+            return PRECOND_CACHE.get(obj, ('ilu', safe, sweeps) + key, make, pins) if obj is not None else make()
+        if method == 'cluster' and cuda_torch and not (solver or '').startswith('scipy-') and torch._C._get_tracing_state() is None:
+            # ExplicitClusterSolve would be applied by ~8 backend ops per iteration from Python; here the parts go into the device
+            # preconditioner that the Krylov loop applies itself.  Grid matrices: the parts are built on the device from the native
+            # (precond.ClusterPreconditioner.from_matrix restates explicit_coarse / coarse_explicit_preconditioner_coo, _optimize.py:942-971,
+            # _linalg.py:769-799 — the reference's own builder needs the COO form, which a device-assembled matrix never had and which
+            # CompressedSparseMatrix.decompress cannot rebuild for rank > 1, _sparse.py:895-903); anything else: the reference builds them.
+            def make():
+                from phiml.math import spatial, instance
+                axes = spatial(matrix)
+                if axes and not instance(matrix):
+                    return _precond.ClusterPreconditioner.from_matrix(native_matrix(matrix, TORCH), grid=tuple(int(v) for v in axes.sizes))
+                ref = original_compute(method, matrix, rank_deficiency=rank_deficiency, target_backend=target_backend, solver=solver)
+                dev = TORCH.get_default_device().ref
+                t = lambda a: torch.as_tensor(a).to(dev)
+                return _precond.ClusterPreconditioner(t(ref.inv_coarse_matrix), t(ref.clusters).reshape(-1), int(ref.cluster_count), t(ref.cluster_size))
+            obj, key, pins = anchor(matrix)
+            return PRECOND_CACHE.get(obj, ('cluster',) + key, make, pins) if obj is not None else make()
         return original_compute(method, matrix, rank_deficiency=rank_deficiency, target_backend=target_backend, solver=solver)
 
     # constant-coefficient ZERO-boundary operators go from the tracer straight to the device assembler
@@ -226,10 +290,102 @@ def install():
 
     lin_trace.tracer_to_coo = assembly.make_tracer_to_coo(original_t2c, wants_device_matrix, assemble)
 
+    # ---- backward pass: phiml.math._optimize.attach_gradient_solve is looked up as a module global by solve_linear (:670)
+    original_attach = opt.attach_gradient_solve
+
+    def device_matrix_gradient(matrix, like_dy, x):
+        """Prepares ``dm`` of implicit_gradient_solve (_optimize.py:798-807) as ONE kernel (phb200_matrix_gradient_coo: both gathers, the
+        product, the batch sum and the negation).  Returns ``compute(dy) -> dm`` or None when the operands are not on the phb200 path
+        (then the reference's own rule runs).  ``like_dy`` has the dims of dy (the forward right-hand side)."""
+        from phiml.math import dual, instance
+        from phiml.math._sparse import CompressedSparseMatrix, SparseCoordinateTensor
+        from phiml.math._tensors import reshaped_native, reshaped_tensor, Tensor as PhiTensor
+        from phiml.math._tree import disassemble_tree, variable_attributes
+        from phiml.math._magic_ops import value_attributes
+        if torch._C._get_tracing_state() is not None:
+            return None
+        coo = matrix.decompress() if isinstance(matrix, CompressedSparseMatrix) else matrix
+        if not isinstance(coo, SparseCoordinateTensor):
+            return None
+
+        def single_tensor(tree, attr_type):
+            try:
+                _, tensors = disassemble_tree(tree, cache=False, attr_type=attr_type)
+            except Exception:
+                return None
+            return tensors[0] if len(tensors) == 1 and isinstance(tensors[0], PhiTensor) else None
+
+        y_t, x_t = single_tensor(like_dy, value_attributes), single_tensor(x, variable_attributes)
+        if y_t is None or x_t is None or x_t.default_backend is not TORCH:
+            return None
+        ind_batch, channels, indices, _values, shape = coo._native_coo_components(dual, matrix=True)
+        entries = instance(coo._values)
+        if not ind_batch.is_empty or not channels.is_empty or entries.rank != 1:
+            return None
+        row_names = coo._dense_shape.non_dual.names
+        col_names = tuple(n.lstrip('~') for n in coo._dense_shape.dual.names)
+        if any(n not in y_t.shape for n in row_names) or any(n not in x_t.shape for n in col_names):
+            return None
+        extra = y_t.shape.without(row_names) & x_t.shape.without(col_names)      # what the reference sums over (:806)
+        if any(n in coo.shape for n in extra.names):
+            return None
+        x_n = reshaped_native(x_t, [extra, x_t.shape.only(col_names, reorder=True)], force_expand=True)
+        if not _device_tensor(x_n):
+            return None
+        idx = torch.as_tensor(indices).to(x_n.device)
+        rows_cols = torch.stack([idx[0, :, 0], idx[0, :, 1]]).to(torch.int64)
+
+        def compute(dy):
+            from . import adjoint
+            dy_t = single_tensor(dy, value_attributes)
+            dy_n = reshaped_native(dy_t, [extra, dy_t.shape.only(row_names, reorder=True)], force_expand=True)
+            dt = torch.float64 if torch.float64 in (dy_n.dtype, x_n.dtype) else torch.float32
+            native = torch.sparse_coo_tensor(rows_cols, torch.empty(rows_cols.shape[1], dtype=dt, device=x_n.device), shape)
+            out = adjoint.matrix_gradient(native, dy_n.detach().to(dt), x_n.detach().to(dt))
+            DM_STATS['device'] += 1
+            return coo._with_values(reshaped_tensor(out, [entries], convert=False))
+        return compute
+
+    def attach_gradient_solve(forward_solve, auxiliary_args, matrix_adjoint):
+        aux = [a for a in auxiliary_args.split(',') if a]
+        if not matrix_adjoint:
+            normal = original_attach(forward_solve, auxiliary_args, matrix_adjoint)
+            if 'matrix' in aux:
+                return normal
+            # A device-assembled matrix (assembly.build_compressed) is torch-backed, so the reference would treat it as a differentiable
+            # input (auxiliary only "if matrix.backend == NUMPY", _optimize.py:670) although it is the same constant the reference holds in
+            # NumPy arrays.  Constants must stay auxiliary: that is what keeps jit-compiled solves (one tensor argument, the right-hand
+            # side) and the per-matrix caches working.
+            constant = original_attach(forward_solve, auxiliary_args + ',matrix', matrix_adjoint)
+
+            def dispatch(y, solve, matrix, **kwargs):
+                return (constant if getattr(matrix, '_phb200_device_assembled', False) else normal)(y, solve, matrix, **kwargs)
+            return dispatch
+
+        reference_rule = original_attach(forward_solve, auxiliary_args, matrix_adjoint)      # complete reference behaviour, used as it is
+
+        def backward(fwd_args: dict, x, dx):
+            compute_dm = device_matrix_gradient(fwd_args['matrix'], fwd_args['y'], x) if 'matrix' in fwd_args else None
+            if compute_dm is None:
+                DM_STATS['reference'] += 1
+                return reference_rule.gradient(fwd_args, x, dx)
+            # the steps of implicit_gradient_solve (_optimize.py:786-797): adjoint solve on the transposed matrix with Solve.gradient_solve
+            solve, matrix = fwd_args['solve'], fwd_args['matrix']
+            transposed = opt.transpose_matrix(matrix, solve.x0.shape, fwd_args['y'].shape)
+            grad_solve = solve.gradient_solve
+            grad_solve = opt.copy_with(grad_solve, x0=grad_solve.x0 if grad_solve.x0 is not None else opt.zeros_like(fwd_args['y']))
+            fwd_args.pop('is_backprop', None)
+            dy = solve_with_grad(dx, grad_solve, transposed, is_backprop=True, **fwd_args)
+            return {'y': dy, 'matrix': compute_dm(dy)}
+
+        solve_with_grad = opt.custom_gradient(forward_solve, backward, auxiliary_args=auxiliary_args)
+        return solve_with_grad
+
     TORCH.__class__ = B200TorchBackend
     opt.compute_preconditioner = compute_preconditioner
     opt.native_matrix = native_matrix
-    _INSTALLED.update(torch=TORCH, original_class=TorchBackend, original_compute=original_compute, original_native=original_native, opt=opt,
+    opt.attach_gradient_solve = attach_gradient_solve
+    _INSTALLED.update(torch=TORCH, original_class=TorchBackend, original_compute=original_compute, original_native=original_native, opt=opt, original_attach=original_attach,
                       lin_trace=lin_trace, original_t2c=original_t2c)
     return TORCH
 
@@ -240,6 +396,7 @@ def uninstall():
     _INSTALLED['torch'].__class__ = _INSTALLED['original_class']
     _INSTALLED['opt'].compute_preconditioner = _INSTALLED['original_compute']
     _INSTALLED['opt'].native_matrix = _INSTALLED['original_native']
+    _INSTALLED['opt'].attach_gradient_solve = _INSTALLED['original_attach']
     _INSTALLED['lin_trace'].tracer_to_coo = _INSTALLED['original_t2c']
     NATIVE_CACHE.clear()
     PRECOND_CACHE.clear()

@@ -105,6 +105,7 @@ class IncompleteLU(Preconditioner, _Handle):
         assert m.kind == 'csr' and m.shape[0] == m.shape[1], "incomplete_lu_coo only implemented for square matrices"
         self.matrix = m
         self.rank_deficiency = rank_deficiency
+        self.safe = bool(safe)
         self.lower_unit_diagonal, self.upper_unit_diagonal = True, False
         self.lu = torch.empty_like(m.values)
         h = ctypes.c_void_p()
@@ -189,8 +190,93 @@ class IncompleteLU(Preconditioner, _Handle):
         return f"ilu ({self.source})"
 
 
+def cluster_assignment(grid, cluster_count: int, dtype: torch.dtype, device) -> tuple:
+    """Cell -> cluster map of ``explicit_coarse`` for grid matrices (phiml/math/_optimize.py:947-960) built on the device: one cluster
+    per cell if the grid has no more cells than clusters, else boxes with ``round(size * (count / volume)^(1/rank))`` clusters per axis;
+    the cluster coordinate is ``int(index / size * clusters_along_axis)`` evaluated in the working precision, like the reference."""
+    import numpy as np
+    grid = tuple(int(g) for g in grid)
+    n = int(np.prod(grid))
+    if cluster_count >= n:
+        return torch.arange(n, dtype=torch.int32, device=device), n
+    by_axis = np.round(np.asarray(grid) * (cluster_count / n) ** (1 / len(grid))).astype(np.int32)
+    clusters = torch.zeros(grid, dtype=torch.int64, device=device)
+    for axis, (g, c) in enumerate(zip(grid, by_axis)):
+        coord = (torch.arange(g, device=device).to(dtype) / torch.tensor(g, dtype=dtype, device=device) * torch.tensor(int(c), dtype=dtype, device=device)).to(torch.int32).to(torch.int64)
+        shape = [1] * len(grid)
+        shape[axis] = g
+        clusters = clusters * int(c) + coord.reshape(shape)
+    return clusters.reshape(-1).to(torch.int32), int(np.prod(by_axis))
+
+
+class ClusterPreconditioner(Preconditioner, _Handle):
+    """Device counterpart of ``ExplicitClusterSolve`` (phiml/backend/_linalg.py:734-766), the reference's 'cluster' preconditioner:
+    ``M^-1 v = P C^-1 R v + (v - P (R v / size))`` with R = sums over the cells of a cluster, C = coarse matrix (entries of A summed by
+    cluster of row / column), P = gather by cluster.  It is applied inside the device-resident Krylov loop by three kernels
+    (phb200_precond_cluster).  The parts are those the reference's object holds: ``inv_coarse_matrix (C, C)``, ``clusters (N,)``,
+    ``cluster_count``, ``cluster_size (C,)``; ``from_matrix`` builds them like ``explicit_coarse`` / ``coarse_explicit_preconditioner_coo``
+    (:769-799; the dense inverse is taken with NumPy on the host, as the reference does on every backend)."""
+
+    def __init__(self, inv_coarse_matrix: torch.Tensor, clusters: torch.Tensor, cluster_count: int, cluster_size: torch.Tensor):
+        _Handle.__init__(self)
+        E.require_cuda(inv_coarse_matrix, clusters, cluster_size)
+        dt = inv_coarse_matrix.dtype
+        assert dt in (torch.float32, torch.float64)
+        self.cluster_count = int(cluster_count)
+        self.inv_coarse_matrix = inv_coarse_matrix.contiguous()
+        self.clusters = clusters.reshape(-1).to(torch.int32).contiguous()
+        self.cluster_size = cluster_size.to(dt).contiguous()
+        assert tuple(self.inv_coarse_matrix.shape) == (self.cluster_count, self.cluster_count) and self.cluster_size.numel() == self.cluster_count
+        n = int(self.clusters.numel())
+        # cells grouped by cluster, ascending inside a cluster (the order bincount adds them in)
+        self.members = torch.argsort(self.clusters.to(torch.int64), stable=True).to(torch.int32).contiguous()
+        counts = torch.bincount(self.clusters.to(torch.int64), minlength=self.cluster_count)
+        self.member_ptr = torch.zeros(self.cluster_count + 1, dtype=torch.int32, device=self.clusters.device)
+        self.member_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        h = ctypes.c_void_p()
+        E.check(E.lib().phb200_precond_cluster(ctypes.byref(h), E.ptr(self.clusters), E.ptr(self.members), E.ptr(self.member_ptr), n, self.cluster_count,
+                                               E.ptr(self.inv_coarse_matrix), E.ptr(self.cluster_size), E.dtype_code(dt)))
+        self._h = h
+
+    @classmethod
+    def from_matrix(cls, matrix, grid=None, cluster_count: int = 3 ** 6):
+        import numpy as np
+        m = plain_csr(as_matrix(matrix))
+        assert m.kind == 'csr' and m.shape[0] == m.shape[1]
+        if grid is None:
+            grid = m.stencil.grid if m.stencil is not None else (m.shape[0],)
+        assert int(np.prod(grid)) == m.shape[0], f"grid {grid} does not match a matrix with {m.shape[0]} rows"
+        clusters, count = cluster_assignment(grid, cluster_count, m.dtype, m.device)
+        rows = torch.repeat_interleave(torch.arange(m.shape[0], device=m.device, dtype=torch.int64), (m.rowptr[1:] - m.rowptr[:-1]).to(torch.int64))
+        cl = clusters.to(torch.int64)
+        lin = cl[rows] * count + cl[m.col.to(torch.int64)]
+        coarse = torch.zeros(count * count, dtype=torch.float64, device=m.device).index_add_(0, lin, m.values.to(torch.float64))
+        coarse = coarse.reshape(count, count).to(m.dtype)
+        inv = torch.as_tensor(np.linalg.inv(coarse.cpu().numpy()), device=m.device)        # "inverting matrix ... using NumPy", _linalg.py:793-795
+        size = torch.bincount(cl, minlength=count).to(m.dtype)
+        return cls(inv, clusters, count, size)
+
+    def apply(self, vec):
+        vec = vec.to(self.inv_coarse_matrix.dtype).contiguous()
+        out = torch.empty_like(vec)
+        E.check(E.lib().phb200_precond_apply(self._h, E.ptr(vec), E.ptr(out), vec.shape[0], vec.shape[1], E.stream_ptr(vec.device)))
+        return out
+
+    def apply_transposed(self, vec):
+        raise NotImplementedError      # as the reference (_linalg.py:755-756)
+
+    def apply_inv_l(self, vec):
+        return vec
+
+    def apply_inv_u(self, vec):
+        return self.apply(vec)
+
+    def __repr__(self):
+        return f"cluster ({self.cluster_count})"
+
+
 def compute_preconditioner(method: Optional[str], matrix, rank_deficiency=0, **_ignored) -> Optional[Preconditioner]:
-    """'jacobi' | 'ilu' | 'ilu-exact' | 'auto' | None on a native matrix (torch sparse tensor or Matrix).  'auto' resolves to 'ilu'
+    """'jacobi' | 'ilu' | 'ilu-exact' | 'cluster' | 'auto' | None on a native matrix (torch sparse tensor or Matrix).  'auto' resolves to 'ilu'
     as in the reference for backends with sparse triangular solves (phiml/math/_optimize.py:838-846); 'ilu' builds the
     reference's own factors (fixed-point sweeps, eager sweep count); ``safe`` sweeps when a rank deficiency is declared (:869)."""
     if method is None:
@@ -202,4 +288,6 @@ def compute_preconditioner(method: Optional[str], matrix, rank_deficiency=0, **_
         return IncompleteLU(matrix, safe=bool(np.any(np.asarray(rank_deficiency) > 0)), rank_deficiency=rank_deficiency)
     if method == 'ilu-exact':
         return IncompleteLU(matrix, sweeps='exact')
+    if method == 'cluster':
+        return ClusterPreconditioner.from_matrix(matrix, grid=_ignored.get('grid'))
     raise NotImplementedError(f"preconditioner '{method}' is not on the phb200 path")

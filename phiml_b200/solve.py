@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _engine as E
-from .precond import IncompleteLU, JacobiPreconditioner, Preconditioner
+from .precond import ClusterPreconditioner, IncompleteLU, JacobiPreconditioner, Preconditioner
 from .sparse import Matrix, as_matrix, plain_csr
 
 
@@ -48,6 +48,21 @@ LAST_RUN = {'resident': False}     # diagnostics of the most recent solve (tests
 
 def _pre_str(pre) -> str:
     return f"with preconditioner '{pre}'" if pre is not None else "with preconditioner 'none'"
+
+
+def method_string(kind: str, pre, trajectory: bool, poly_order: int = 2, traced: bool = False) -> str:
+    """``SolveResult.method`` exactly as the reference's torch backend words it (phiml/backend/torch/_torch_backend.py:946,963;
+    phiml/backend/_linalg.py:90,128,224,274).  ``kind``: 'CG' | 'CG-adaptive' | 'biCG-stab'."""
+    fast = "TorchScript" if traced else "PyTorch*"
+    if kind == 'CG-adaptive' and pre:
+        kind = 'CG'                                   # cg_adaptive falls back to cg when a preconditioner is given (_linalg.py:97-99)
+    if kind == 'CG':
+        return f"Φ-ML CG ({BACKEND_NAME}) {_pre_str(pre)}" if (trajectory or pre) else f"Φ-ML CG ({fast})"
+    if kind == 'CG-adaptive':
+        return f"Φ-ML CG-adaptive ({BACKEND_NAME}) " if trajectory else f"Φ-ML CG ({fast})"
+    if kind == 'biCG-stab':
+        return f"Φ-ML biCG-stab {_pre_str(pre)}" if poly_order == 1 else f"Φ-ML biCG-stab({poly_order}) ({BACKEND_NAME}) {_pre_str(pre)}"
+    raise NotImplementedError(kind)
 
 
 class DeviceSolver:
@@ -175,10 +190,10 @@ def _prepare(lin, y, x0, rtol, atol, max_iter):
 def _device_pre(pre, matrix):
     if pre is None:
         return None
-    if isinstance(pre, (JacobiPreconditioner, IncompleteLU)):
+    if isinstance(pre, (JacobiPreconditioner, IncompleteLU, ClusterPreconditioner)):
         return pre
     raise NotImplementedError(f"preconditioner {type(pre).__name__} cannot run inside the fused device loop; "
-                              f"use phiml_b200.compute_preconditioner('jacobi'|'ilu', matrix)")
+                              f"use phiml_b200.compute_preconditioner('jacobi'|'ilu'|'cluster', matrix)")
 
 
 def _run(code: int, poly_order: int, name: str, matrix, y, x0, rtol, atol, max_iter: np.ndarray, pre) -> SolveResult:
@@ -265,8 +280,8 @@ def conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset
     matrix, y, x0, rtol, atol, max_iter = _prepare(lin, y, x0, rtol, atol, max_iter)
     if max_iter.shape[0] > 1 or pre:
         pre = _device_pre(pre, matrix)
-        return _run(E.CG, 0, f"Φ-ML CG ({BACKEND_NAME}) {_pre_str(pre)}", matrix, y, x0, rtol, atol, max_iter, pre)
-    return _run(E.CG_TORCH, 0, "Φ-ML CG (PyTorch*)", matrix, y, x0, rtol, atol, max_iter, None)
+        return _run(E.CG, 0, method_string('CG', pre, True), matrix, y, x0, rtol, atol, max_iter, pre)
+    return _run(E.CG_TORCH, 0, method_string('CG', None, False), matrix, y, x0, rtol, atol, max_iter, None)
 
 
 def conjugate_gradient_adaptive(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None) -> SolveResult:
@@ -276,8 +291,8 @@ def conjugate_gradient_adaptive(lin, y, x0, rtol, atol, max_iter, pre=None, matr
         return conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre, matrix_offset)
     matrix, y, x0, rtol, atol, max_iter = _prepare(lin, y, x0, rtol, atol, max_iter)
     if max_iter.shape[0] > 1:
-        return _run(E.CG_ADAPTIVE, 0, f"Φ-ML CG-adaptive ({BACKEND_NAME}) ", matrix, y, x0, rtol, atol, max_iter, None)
-    return _run(E.CG_ADAPTIVE_TORCH, 0, "Φ-ML CG (PyTorch*)", matrix, y, x0, rtol, atol, max_iter, None)
+        return _run(E.CG_ADAPTIVE, 0, method_string('CG-adaptive', None, True), matrix, y, x0, rtol, atol, max_iter, None)
+    return _run(E.CG_ADAPTIVE_TORCH, 0, method_string('CG-adaptive', None, False), matrix, y, x0, rtol, atol, max_iter, None)
 
 
 def bi_conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None, poly_order=2) -> SolveResult:
@@ -288,10 +303,7 @@ def bi_conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_off
     if pre and poly_order > 1:
         warnings.warn(f"Φ-ML biCG-stab({poly_order}) with preconditioner is experimental and may diverge.", RuntimeWarning)
     pre = _device_pre(pre, matrix)
-    if poly_order == 1:
-        name = f"Φ-ML biCG-stab {_pre_str(pre)}"
-    else:
-        name = f"Φ-ML biCG-stab({poly_order}) ({BACKEND_NAME}) {_pre_str(pre)}"
+    name = method_string('biCG-stab', pre, False, poly_order)
     return _run(E.BICGSTAB, poly_order, name, matrix, y, x0, rtol, atol, max_iter, pre)
 
 

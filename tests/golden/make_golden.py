@@ -363,8 +363,48 @@ def _adjoint_record(out, name, rec, x, dy, dk, grid, names, nb, grad_f):
     print(key, fwd[1], bwd[1], fwd[5], bwd[5], 'dk', float(out[key + '/dk']), 'dm', out[key + '/dm'].shape)
 
 
+CLUSTER_CASES = {            # name: (op, grid, dtype, right-hand sides, seed, method)
+    'c40x36_f64': ('poisson', (40, 36), np.float64, 2, 0, 'CG'),
+    'c16x12x20_f32': ('poisson', (16, 12, 20), np.float32, 2, 1, 'CG'),
+    'c12x10_f64_small': ('poisson', (12, 10), np.float64, 1, 2, 'CG'),          # fewer cells than 3^6 clusters: one cluster per cell
+    'c20x14x10_adv_f64': ('advdiff', (20, 14, 10), np.float64, 2, 3, 'biCG-stab(2)'),
+}
+
+
+def golden_cluster(out):
+    """The reference's 'cluster' preconditioner (explicit_coarse -> ExplicitClusterSolve, phiml/math/_optimize.py:942-971,
+    phiml/backend/_linalg.py:734-799) on its NumPy backend: parts, one application, and solves driven with it."""
+    from phiml.math._optimize import compute_preconditioner
+    for name, (op, grid, dtype, nb, seed, method) in CLUSTER_CASES.items():
+        prec = 64 if dtype == np.float64 else 32
+        key = f"cluster/{name}"
+        with math.precision(prec):
+            m, csr, _, _ = build(op, grid, dtype)
+            pre = compute_preconditioner('cluster', m, target_backend=NUMPY, solver=method)
+            out[key + '/clusters'] = np.asarray(pre.clusters).astype(np.int32)
+            out[key + '/cluster_count'] = np.int64(pre.cluster_count)
+            out[key + '/cluster_size'] = np.asarray(pre.cluster_size)
+            inv = np.asarray(pre.inv_coarse_matrix)
+            out[key + '/inv_coarse'] = inv if inv.shape[0] <= 128 else inv[::7, ::5]      # strided sample keeps the fixture small
+            rng = np.random.default_rng(seed)
+            v = rng.standard_normal((nb, csr.shape[0])).astype(dtype)
+            out[key + '/apply'] = np.asarray(pre.apply(v))
+            y = rng.standard_normal((nb, csr.shape[0])).astype(dtype)
+            rtol = np.asarray([1e-10 if prec == 64 else 1e-5] * nb, dtype)
+            with NUMPY:
+                r = NUMPY.linear_solve(method, csr, y, np.zeros_like(y), rtol, np.zeros(nb, dtype), np.array([[1000] * nb]), pre, None)
+                r0 = NUMPY.linear_solve(method, csr, y, np.zeros_like(y), rtol, np.zeros(nb, dtype), np.array([[1000] * nb]), None, None)
+            out[key + '/x'] = np.asarray(r.x)
+            out[key + '/iterations'] = np.asarray(r.iterations)
+            out[key + '/function_evaluations'] = np.asarray(r.function_evaluations)
+            out[key + '/converged'] = np.asarray(r.converged)
+            out[key + '/method'] = np.asarray(r.method)
+            out[key + '/iterations_without'] = np.asarray(r0.iterations)
+            print(key, repr(pre), r.method, r.iterations, 'without:', r0.iterations, out[key + '/inv_coarse'].dtype, out[key + '/cluster_size'].dtype, out[key + '/clusters'].shape)
+
+
 def main():
-    groups = {'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}

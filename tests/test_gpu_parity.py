@@ -765,3 +765,67 @@ def test_batch_wide_rule_is_shared_by_solver_chunks():
     its = torch.cat([s.result()[0] for s in solvers])
     assert torch.equal(its, whole.iterations)
     assert torch.equal(torch.cat([s.x for s in solvers]), whole.x)
+
+
+# ------------------------------------------------------------------------------------------------ 'cluster' preconditioner
+
+CLUSTER_CASES = {'c40x36_f64': ('poisson', (40, 36), 'float64', 2, 0, 'CG'), 'c16x12x20_f32': ('poisson', (16, 12, 20), 'float32', 2, 1, 'CG'),
+                 'c12x10_f64_small': ('poisson', (12, 10), 'float64', 1, 2, 'CG'), 'c20x14x10_adv_f64': ('advdiff', (20, 14, 10), 'float64', 2, 3, 'biCG-stab(2)')}
+
+
+@pytest.mark.parametrize('name', sorted(CLUSTER_CASES))
+def test_cluster_preconditioner_matches_reference(name):
+    """Device ExplicitClusterSolve (phb200_precond_cluster) against parts, one application and a preconditioned solve recorded from the
+    reference's NumPy backend: cluster map bit-exact, inverse / application to rounding, solve within +-1 iteration, same method string."""
+    op, grid, dt, nb, seed, method = CLUSTER_CASES[name]
+    g = golden('cluster')
+    key = f"cluster/{name}"
+    csr = oracle_matrix(op, grid, dt)
+    m = pb.as_matrix(dev_csr(csr))
+    pre = pb.ClusterPreconditioner.from_matrix(m, grid=grid)
+    assert pre.cluster_count == int(g[key + '/cluster_count']) and repr(pre) == f"cluster ({pre.cluster_count})"
+    np.testing.assert_array_equal(pre.clusters.cpu().numpy(), g[key + '/clusters'][0])
+    np.testing.assert_array_equal(pre.cluster_size.cpu().numpy(), g[key + '/cluster_size'])
+    f64 = dt == 'float64'
+    ref_inv = g[key + '/inv_coarse']
+    inv = pre.inv_coarse_matrix.cpu().numpy()
+    mine = inv if ref_inv.shape[0] == pre.cluster_count else inv[::7, ::5]
+    np.testing.assert_allclose(mine, ref_inv, rtol=0, atol=(1e-10 if f64 else 2e-4) * np.abs(ref_inv).max())
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((nb, csr.shape[0])).astype(dt)
+    got = pre.apply(torch.as_tensor(v, device=DEV)).cpu().numpy()
+    np.testing.assert_allclose(got, g[key + '/apply'], rtol=0, atol=(1e-10 if f64 else 2e-4) * np.abs(g[key + '/apply']).max())
+    assert torch.equal(pre.apply_inv_l(torch.as_tensor(v, device=DEV)).cpu(), torch.as_tensor(v))
+    # deterministic: the segmented sums do not depend on scheduling
+    assert np.array_equal(got, pre.apply(torch.as_tensor(v, device=DEV)).cpu().numpy())
+    y = rng.standard_normal((nb, csr.shape[0])).astype(dt)
+    rtol = np.asarray([1e-10 if f64 else 1e-5] * nb, dt)
+    yd = torch.as_tensor(y, device=DEV)
+    if method == 'CG':
+        res = pb.generic_conjugate_gradient(m, yd, torch.zeros_like(yd), rtol, np.zeros(nb, dt), np.array([[1000] * nb]), pre)
+    else:
+        res = pb.linear_solve(method, m, yd, torch.zeros_like(yd), rtol, np.zeros(nb, dt), np.array([[1000] * nb]), pre, None)
+    its = res.iterations.cpu().numpy().astype(int)
+    assert np.max(np.abs(its - g[key + '/iterations'].astype(int))) <= 1, (its, g[key + '/iterations'])
+    assert bool(res.converged.all())
+    assert res.method == str(g[key + '/method']).replace('(numpy)', '(torch)')
+    tol = 1e-8 if f64 else 1e-4
+    assert np.max(np.abs(res.x.cpu().numpy() - g[key + '/x'])) <= tol * np.abs(g[key + '/x']).max()
+    assert int(g[key + '/iterations'].max()) <= int(g[key + '/iterations_without'].max())
+
+
+def test_cluster_preconditioner_at_scale_cuts_iterations_128_cubed():
+    """Size-independent property at a size the reference's host path cannot reach comfortably: cluster-CG on 128^3 converges to the
+    requested residual in clearly fewer iterations than plain CG (297), with every part built and applied on the device."""
+    n = 128
+    shifts = shifts_for('poisson', 3, np.float32)
+    st = pb.Matrix.stencil_matrix((n, n, n), [s for s, _ in shifts], [float(c) for _, c in shifts], torch.float32, DEV)
+    csr = st.to_csr()
+    m = pb.as_matrix(torch.sparse_csr_tensor(csr.rowptr, csr.col, csr.values, csr.shape))
+    pre = pb.ClusterPreconditioner.from_matrix(m, grid=(n, n, n))
+    assert pre.cluster_count == 729
+    y = torch.as_tensor(np.random.default_rng(0).standard_normal((1, n ** 3)).astype(np.float32), device=DEV)
+    res = pb.generic_conjugate_gradient(m, y, torch.zeros_like(y), [1e-5], [0.0], np.array([[2000]]), pre)
+    assert bool(res.converged[0]) and int(res.iterations[0]) < 297
+    true_r = y - st.matvec(res.x)
+    assert float(true_r.norm() / y.norm()) < 5e-5

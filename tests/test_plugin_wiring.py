@@ -252,3 +252,99 @@ def test_front_end_solves_on_the_bridged_matrix(phiml_env):
     g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'frontend.npz'))
     np.testing.assert_allclose(x.numpy('b,x,y'), g['front/torch/cg16/x'], rtol=0, atol=2e-5)
     np.testing.assert_array_equal(info.iterations.numpy('b'), g['front/torch/cg16/iterations'])
+
+
+def test_jit_compiled_solve_is_one_registered_operator_node(phiml_env, monkeypatch):
+    """under ``math.jit_compile`` PhiML traces with torch.jit.trace; the plug-in must put the solve into the graph as ONE
+    registered operator (phb200::linear_solve) that runs the device loop on every execution — not an unrolled Python loop and not a
+    constant baked in at trace time.  Engine replaced by the oracle here; the operator, its schema and the routing are the real ones."""
+    import torch
+    import scipy.sparse as sp
+    from phiml import math
+    from phiml.math import spatial, Solve, extrapolation
+    from oracle import krylov
+    from phiml_b200 import solve as host, torch_op
+    plugin, TORCH = phiml_env
+    seen = []
+
+    def fake_linear_solve(method, lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None):
+        seen.append((method, lin.layout, tuple(y.shape), np.asarray(max_iter).shape, pre))
+        a = sp.csr_matrix((lin.values().numpy(), lin.col_indices().numpy(), lin.crow_indices().numpy()), shape=tuple(lin.shape))
+        r = krylov.torch_fastpath_cg(a, y.numpy(), x0.numpy(), rtol.numpy(), atol.numpy(), np.asarray(max_iter))
+        t = torch.as_tensor
+        return host.SolveResult(r.method, t(r.x), t(r.residual), t(r.iterations), t(r.function_evaluations), t(r.converged), t(r.diverged), r.message)
+
+    monkeypatch.setattr(plugin, '_traceable', lambda lin, y: torch._C._get_tracing_state() is not None and isinstance(lin, torch.Tensor) and lin.layout != torch.strided)
+    monkeypatch.setattr(host, 'linear_solve', fake_linear_solve)
+    lap = math.jit_compile_linear(lambda x: -math.laplace(x, padding=extrapolation.ZERO))
+
+    @math.jit_compile
+    def solve_for(y):
+        return math.solve_linear(lap, y, Solve('CG', 1e-5, 0, x0=math.zeros(spatial(x=12, y=10)), max_iterations=500))
+
+    from oracle.assemble import poisson_csr
+    a = poisson_csr((12, 10), np.float32)
+    rng = np.random.default_rng(3)
+    calls0 = torch_op._STATE['calls']
+    with TORCH, math.precision(32):
+        for k in range(3):                      # first call traces, the next ones execute the traced graph
+            y_np = rng.standard_normal((12, 10)).astype(np.float32)
+            x = solve_for(math.tensor(y_np, spatial('x,y')))
+            ref = krylov.torch_fastpath_cg(a, y_np.reshape(1, -1), np.zeros((1, 120), np.float32), np.float32([1e-5]), np.float32([0]), np.array([[500]]))
+            np.testing.assert_allclose(x.numpy('x,y').reshape(-1), ref.x[0], rtol=0, atol=1e-6)
+    assert torch_op._STATE['calls'] - calls0 >= 3, "every execution of the traced graph must run the operator (no baked-in constants)"
+    assert all(s[0] == 'CG' and s[1] == torch.sparse_csr and s[2] == (1, 120) and s[3] == (1, 1) and s[4] is None for s in seen)
+    # the traced graph of the compiled function holds the operator as a node
+    parts, layout = torch_op.parts_of_native(torch.sparse_csr_tensor(torch.as_tensor(a.indptr), torch.as_tensor(a.indices), torch.as_tensor(a.data), a.shape))
+
+    def direct(y):
+        return torch_op.register()(parts, layout, 120, 120, y, torch.zeros_like(y), torch.full((1,), 1e-5), torch.zeros(1), [500], 1, 'CG', '')[0]
+    graph = torch.jit.trace(direct, (torch.ones(1, 120),), check_trace=False).graph
+    assert 'phb200::linear_solve' in str(graph)
+
+
+def test_matrix_gradient_inside_phimls_backward_pass_comes_from_the_boundary(phiml_env, monkeypatch):
+    """grad_for_f=True: implicit_gradient_solve forms dm = -(dy[row] * x[col]) summed over the batch (_optimize.py:803-807).  With the
+    plug-in PhiML's own backward pass hands (row, col, dy, x) to phb200's matrix-gradient entry; here that entry is the oracle's
+    restatement, and dL/dk must equal what the unmodified reference gives."""
+    import torch
+    from phiml import math
+    from phiml.math import spatial, batch, channel, Solve
+    from oracle import adjoint as oracle_adjoint
+    from phiml_b200 import adjoint as host_adjoint
+    from _util import ADVDIFF
+    plugin, TORCH = phiml_env
+    seen = []
+
+    def fake_matrix_gradient(native, dy, x):
+        idx = native._indices().numpy()
+        seen.append((tuple(dy.shape), tuple(x.shape), idx.shape))
+        return torch.as_tensor(oracle_adjoint.matrix_gradient(idx[0], idx[1], dy.numpy(), x.numpy()))
+
+    def advdiff_k(x, k):
+        u = math.wrap(list(ADVDIFF['velocity'][:2]), channel(gradient='x,y'))
+        g = math.spatial_gradient(x, padding=math.extrapolation.ZERO, difference='central', stack_dim=channel(gradient='x,y'))
+        return x + ADVDIFF['c'] * math.sum(g * u, 'gradient') - k * ADVDIFF['nu'] * math.laplace(x, padding=math.extrapolation.ZERO)
+
+    def run():
+        with TORCH, math.precision(64):
+            f = math.jit_compile_linear(advdiff_k)
+            y = math.tensor(np.random.default_rng(4).standard_normal((2, 10, 8)), batch('b'), spatial('x,y'))
+            x0 = math.zeros(spatial(x=10, y=8))
+
+            def loss(y, k):
+                x = math.solve_linear(f, y, Solve('biCG-stab(2)', 1e-10, 0, x0=x0, max_iterations=1000), k=k, grad_for_f=True)
+                return math.l2_loss(x), x
+            (l, x), (dy, dk) = math.gradient(loss, 'y,k', get_output=True)(y, math.tensor(1.))
+            return dy.numpy('b,x,y'), float(dk.numpy())
+
+    dy_ref, dk_ref = run()                       # operands on the CPU: the reference's own rule
+    assert plugin.DM_STATS['device'] == 0
+    monkeypatch.setattr(plugin, '_device_tensor', lambda t: isinstance(t, torch.Tensor))
+    monkeypatch.setattr(host_adjoint, 'matrix_gradient', fake_matrix_gradient)
+    dy_dev, dk_dev = run()
+    assert plugin.DM_STATS['device'] == 1 and len(seen) == 1
+    assert seen[0][0] == (2, 80) and seen[0][1] == (2, 80) and seen[0][2][0] == 2
+    np.testing.assert_allclose(dy_dev, dy_ref, rtol=0, atol=1e-12 * np.abs(dy_ref).max())
+    assert abs(dk_dev - dk_ref) <= 1e-10 * max(1.0, abs(dk_ref))
+    plugin.DM_STATS.update(device=0, reference=0)
