@@ -2,6 +2,7 @@
 #include "phase.cuh"
 #include "precond.cuh"
 #include "star_trsv.cuh"
+#include "star_trsv_pipe.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <vector>
 #include <stdlib.h>
@@ -704,6 +705,75 @@ static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     return PHB200_OK;
 }
 
+// x-marching row pipelines (star_trsv_pipe.cuh): R rows per CTA, one CTA per (row tile, z chunk)
+constexpr int kPpRows = 8;
+
+template <typename T, bool LOWER>
+static int pipe_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, int64_t ld, cudaStream_t stream) {
+    const StarDesc& st = p->star;
+    constexpr int R = kPpRows;
+    PipeTrsvArgs a;
+    a.nx = (int)st.nx; a.ny = (int)st.ny; a.nz = (int)st.nz;
+    a.nj = (a.ny + R - 1) / R;
+    constexpr int ZC = 32 * pipe_vec<T>();
+    a.nch = (a.nz + ZC - 1) / ZC;
+    a.batch = (int)batch;
+    a.ld = ld;
+    a.rd = LOWER ? p->rd_l : p->rd;
+    a.B = B;
+    a.X = X;
+    const int64_t n_ctas = batch * a.nj * a.nch;
+    constexpr int64_t W = sizeof(T) / 4;
+    const int64_t y_words = batch * a.nj * (int64_t)a.nx * a.nch * ZC * W, z_words = batch * a.nch * (int64_t)a.nx * a.ny * W;
+    const bool grow = y_words + z_words > p->pp_words;
+    if (grow || (unsigned long long)p->pp_epoch + (unsigned long long)a.nx + 2ull >= (1ull << 32)) {
+        // (re)start with empty hand-over words: first use, a larger batch, or the 32-bit tag space is used up
+        if (grow) {
+            PHB_CUDA(cudaStreamSynchronize(stream));
+            if (p->pp_buf) cudaFree(p->pp_buf);
+            p->pp_buf = nullptr;
+            PHB_CUDA(cudaMalloc(&p->pp_buf, sizeof(unsigned long long) * (size_t)(y_words + z_words)));
+            p->pp_words = y_words + z_words;
+        }
+        PHB_CUDA(cudaMemsetAsync(p->pp_buf, 0, sizeof(unsigned long long) * (size_t)p->pp_words, stream));
+        p->pp_epoch = 0;
+    }
+    a.ybuf = (unsigned long long*)p->pp_buf;
+    a.zbuf = a.ybuf + y_words;
+    a.tag_base = p->pp_epoch;
+    a.dbg = nullptr;
+    if (const char* e = getenv("PHB200_TRSV_DBG")) a.dbg = (unsigned long long*)strtoull(e, nullptr, 0);
+    p->pp_epoch += (unsigned)a.nx + 1u;
+    a.ticket = p->tr_ticket;
+    a.n_ctas = (unsigned)n_ctas;
+    a.order = p->pp_order;
+    a.cx = LOWER ? st.cxm : st.cxp;
+    a.cy = LOWER ? st.cym : st.cyp;
+    a.cz = LOWER ? st.czm : st.czp;
+    auto kernel = k_star_trsv_pipe<T, LOWER, R>;
+    constexpr size_t smem = pipe_smem_bytes<T, R>();
+    static bool attr = false;
+    if (!attr) {
+        PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    PHB_LAUNCH(kernel, a.n_ctas, R * 32, smem, stream, a);
+    return PHB200_OK;
+}
+
+static int pipe_order_setup(phb200_precond* p, const StarDesc& st, cudaStream_t stream) {
+    const int zc = 32 * (p->dtype == PHB200_F32 ? 4 : 2);
+    const int nj = (int)((st.ny + kPpRows - 1) / kPpRows), nch = (int)((st.nz + zc - 1) / zc);
+    std::vector<int32_t> order;
+    order.reserve((size_t)nj * nch);
+    for (int dg = 0; dg < nj + nch - 1; ++dg)
+        for (int j = dg < nch ? 0 : dg - nch + 1; j <= dg && j < nj; ++j) order.push_back(j * nch + (dg - j));
+    PHB_CUDA(cudaMalloc(&p->pp_order, sizeof(int32_t) * order.size()));
+    PHB_CUDA(cudaMemcpyAsync(p->pp_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    return PHB200_OK;
+}
+
 static int scan_order_setup(phb200_precond* p, const StarDesc& st, cudaStream_t stream) {
     const int ni = (int)((st.nx + kScT - 1) / kScT), nj = (int)((st.ny + kScT - 1) / kScT);
     std::vector<int32_t> order;
@@ -743,8 +813,12 @@ static int star_setup(phb200_precond* p, const phb200_matrix* twin, const T* lu_
     PHB_CUDA(cudaFreeAsync(d_ok, stream));
     if (ok) {
         p->star = st;
-        p->star_mode = (e && strcmp(e, "skew") == 0) ? 1 : ((e && strcmp(e, "flow") == 0) ? 3 : 2);
-        if (p->star_mode >= 2) PHB_TRY(scan_order_setup(p, st, stream));
+        // default: x-marching row pipelines when there are planes to march over (3-D), row scans otherwise; PHB200_TRSV=scan|flow|skew|pipe
+        const bool pipe_default = st.nx >= 16 && st.nx * st.ny * st.nz < (1ll << 31);
+        p->star_mode = (e && strcmp(e, "skew") == 0) ? 1 : (e && strcmp(e, "flow") == 0) ? 3 : (e && strcmp(e, "scan") == 0) ? 2 : (e && strcmp(e, "pipe") == 0) ? 4
+                       : (pipe_default ? 4 : 2);
+        if (p->star_mode == 2 || p->star_mode == 3) PHB_TRY(scan_order_setup(p, st, stream));
+        if (p->star_mode == 4) PHB_TRY(pipe_order_setup(p, st, stream));
     } else {
         if (p->rd_l != p->rd) cudaFree(p->rd_l);
         cudaFree(p->rd);
@@ -840,6 +914,10 @@ int precond_apply_inv_l(const phb200_precond* p, const void* in, void* out, int6
     if (p->kind == PHB200_PRE_ILU) {
         if (p->star_mode) {
             phb200_precond* q = const_cast<phb200_precond*>(p);   // counters / epoch are bookkeeping
+            if (p->star_mode == 4) {
+                if (p->dtype == PHB200_F32) return pipe_trsv_launch<float, true>(q, (const float*)in, (float*)out, batch, ld, stream);
+                return pipe_trsv_launch<double, true>(q, (const double*)in, (double*)out, batch, ld, stream);
+            }
             if (p->star_mode >= 2) {
                 if (p->dtype == PHB200_F32) return scan_trsv_launch<float, true>(q, (const float*)in, (float*)out, batch, ld, stream);
                 return scan_trsv_launch<double, true>(q, (const double*)in, (double*)out, batch, ld, stream);
@@ -867,6 +945,10 @@ int precond_apply(const phb200_precond* p, const void* in, void* out, void* tmp,
         PHB_TRY(precond_apply_inv_l(p, in, out, batch, ld, stream));
         if (p->star_mode) {
             phb200_precond* q = const_cast<phb200_precond*>(p);
+            if (p->star_mode == 4) {
+                if (p->dtype == PHB200_F32) return pipe_trsv_launch<float, false>(q, (const float*)out, (float*)out, batch, ld, stream);
+                return pipe_trsv_launch<double, false>(q, (const double*)out, (double*)out, batch, ld, stream);
+            }
             if (p->star_mode >= 2) {
                 if (p->dtype == PHB200_F32) return scan_trsv_launch<float, false>(q, (const float*)out, (float*)out, batch, ld, stream);
                 return scan_trsv_launch<double, false>(q, (const double*)out, (double*)out, batch, ld, stream);
@@ -1126,6 +1208,8 @@ int phb200_precond_destroy(phb200_precond* p) {
     if (p->tr_flags) cudaFree(p->tr_flags);
     if (p->tr_ticket) cudaFree(p->tr_ticket);
     if (p->sc_order) cudaFree(p->sc_order);
+    if (p->pp_order) cudaFree(p->pp_order);
+    if (p->pp_buf) cudaFree(p->pp_buf);
     if (p->cl_scratch) cudaFree(p->cl_scratch);
     phb200_sptrsv_plan_destroy(p->plan_l);
     phb200_sptrsv_plan_destroy(p->plan_u);

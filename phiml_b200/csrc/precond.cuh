@@ -32,9 +32,13 @@ struct phb200_precond {
     phb200_trsv_plan* plan_l;
     phb200_trsv_plan* plan_u;
     // star-stencil wavefront solves (star_trsv.cuh): reciprocal pivots + block counters; star_mode 0 = CSR level solves,
-    // 1 = skewed warps, 2 = row scans with CTA barriers (default), 3 = row scans as a warp dataflow
+    // 1 = skewed warps, 2 = row scans with CTA barriers, 3 = row scans as a warp dataflow, 4 = x-marching row pipelines (default in 3-D)
     int star_mode;
     int32_t* sc_order;                 // device, owned: tiles of the row-scan kernel in dependency (anti-diagonal) order
+    int32_t* pp_order;                 // device, owned: (row tile, z chunk) CTAs of the x-marching pipelines in dependency order
+    void* pp_buf;                      // device, owned: hand-over words of the pipelines (row above a tile, carry into a chunk)
+    int64_t pp_words;
+    unsigned pp_epoch;                 // tags handed out so far
     phb::StarDesc star;
     void* rd;                          // device, owned: 1 / U_ii
     void* rd_l;                        // device: reciprocal pivots that define L (L_ik = A_ik rd_l[k]); == rd for the exact factors,
