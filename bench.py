@@ -537,6 +537,10 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = e2e_single(ctx, native, n) if world == 1 else e2e_slab(ctx, n)
 
+    # ---- the same solve through PhiML's OWN front end (math.solve_linear with the plug-in installed; baseline/_ref), cold and warm
+    if e2e is not None and world == 1 and rank == 0:
+        e2e["front_end"] = front_end_block(n)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, its, dt, kind, sample = cpu_baseline(n, 3, 20)
@@ -686,6 +690,27 @@ def e2e_single(ctx, native, n):
     e2e["cold"] = {"value": its / dt, "unit": UNIT, "seconds_per_solve": dt, "h2d_bytes": int(sum(t.numel() * t.element_size() for t in host_csr)) + 2 * N * w,
                    "seconds_breakdown": dict(zip(parts, pt)), "note": "first call: CSR native uploaded from pinned host memory inside the timed region"}
     return e2e
+
+
+def front_end_block(n):
+    """math.solve_linear(jit_compile_linear(-laplace), y, Solve('CG', 1e-5, preconditioner='jacobi')) on the unmodified reference's front end
+    with the phb200 plug-in (scripts/phiml_front_end.py in a child process: trace -> device assembly -> residency -> device loop; host y in,
+    host x out).  cold = first call (trace + assembly + preconditioner), warm = repeated calls."""
+    script = os.path.join(ROOT, 'scripts', 'phiml_front_end.py')
+    if not os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'phiml')):
+        return {"unavailable": "no copy of the reference (baseline/_ref)"}
+    try:
+        r = subprocess.run([sys.executable, script, '--n', str(n), '--pre', 'jacobi', '--reps', '4'], capture_output=True, text=True, timeout=240)
+        line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
+        d = json.loads(line)
+        cold, warm = d["calls"][0], d["calls"][1:]
+        ws = float(np.median([c["seconds"] for c in warm]))
+        return {"call": "phiml.math.solve_linear through the plug-in (host y in, host x out)", "iterations": cold["iterations"], "method": cold["method"],
+                "cold_seconds": cold["seconds"], "warm_seconds": ws, "warm_value": cold["iterations"] / ws, "unit": UNIT,
+                "warm_backend_call_seconds": float(np.median([c["backend_call_seconds"] for c in warm])), "true_residual": d.get("true_residual"),
+                "device_assemblies": d.get("assembly", {}).get("device_assemblies"), "native_cache": d.get("native_cache")}
+    except Exception as exc:
+        return {"error": repr(exc)[:300]}
 
 
 def e2e_slab(ctx, n):

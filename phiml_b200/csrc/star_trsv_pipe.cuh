@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(R * 32) k_star_trsv_pipe(const PipeTrsvArgs a)
 #pragma unroll
         for (int p = 0; p < G; ++p)
 #pragma unroll
-            for (int e = 0; e < V; ++e) by[p][e] = Tagged<T>::unpack(yw[p][e]);
+            for (int e = 0; e < V; ++e) by[p][e] = needs_y ? Tagged<T>::unpack(yw[p][e]) : T(0);
         load_boundary(g0 + G);       // words of the next group travel while this one is computed
 #pragma unroll
         for (int p = 0; p < G; ++p) {
