@@ -256,6 +256,29 @@ typedef int (*phb200_allreduce_fn)(void* totals, int64_t count, void* stream, vo
 typedef int (*phb200_halo_fn)(void* vec, void* stream, void* user);
 int phb200_solver_set_dist_callbacks(phb200_solver* s, void* totals, phb200_allreduce_fn allreduce, phb200_halo_fn halo, void* user);
 
+/* Native distributed mode: the callback-driven mode above with NOTHING on the host inside the loop (BASELINE config 5 across GPUs).
+ * Reductions all-reduce inside the kernels that produce them (mailboxes as for phb200_solver_set_peer_reduce); before every product the
+ * library launches a small kernel that stores the first / last owned plane of the product's input vector into the slab neighbours' halo
+ * planes of THEIR copy of that vector (peer memory over NVLink) and exchanges one sequence word with each neighbour.  For that every rank
+ * maps its neighbours' X, R and workspace allocations (phb200_ipc_export / _open) and passes them here, before start():
+ *   X, R, ws   the neighbour's arrays as given to ITS phb200_solver_start (same method, same batch on every rank);
+ *   ld         its leading dimension (elements per system; ranks may own different numbers of planes);
+ *   halo_off   element offset, inside one of its vectors, of the halo plane this rank feeds (its upper halo plane for the lower neighbour,
+ *              its lower halo plane for the upper neighbour);
+ *   flag       address, in the neighbour's memory, of the sequence word this rank writes: its my_flags[1] for the lower neighbour
+ *              (this rank is ITS upper neighbour), its my_flags[0] for the upper one.
+ * my_flags: two zero-filled 8-byte words in this rank's memory.  A missing neighbour is passed as NULL (or X == NULL). */
+typedef struct {
+    void* X;
+    void* R;
+    void* ws;
+    int64_t ld;
+    int64_t halo_off;
+    void* flag;
+} phb200_peer_slab;
+int phb200_solver_set_peer_native(phb200_solver* s, void* totals, void* const* mailboxes, int world, int rank,
+                                  const phb200_peer_slab* lower, const phb200_peer_slab* upper, void* my_flags, void* stream);
+
 /* Enqueue up to n_iter further iterations (asynchronous; iterations after all systems finished are skipped on
  * the device). */
 int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream);

@@ -45,6 +45,7 @@ SIGNATURES = {
     'phb200_precond_cluster': (c_int, [_PP, _P, _P, _P, c_int64, c_int, _P, _P, c_int]),
     'phb200_solver_set_dist_callbacks': (c_int, [_P, _P, _P, _P, _P]),
     'phb200_solver_set_peer_halos': (c_int, [_P, _P, c_int64, _P, c_int64]),
+    'phb200_solver_set_peer_native': (c_int, [_P, _P, POINTER(c_void_p), c_int, c_int, _P, _P, _P, _P]),
     'phb200_solver_set_peer_reduce': (c_int, [_P, POINTER(c_void_p), c_int, c_int, _P]),
     'phb200_peer_mailbox_bytes': (c_size_t, [c_int, c_int64]),
     'phb200_solver_dist_advance': (c_int, [_P, c_int, _P]),

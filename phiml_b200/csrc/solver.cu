@@ -841,6 +841,13 @@ struct phb200_solver {
     void* peer_lo;             // slab mode: the neighbours' halo planes of R (CUDA IPC mappings), see phb200_solver_set_peer_halos
     void* peer_hi;
     int64_t peer_ld_lo, peer_ld_hi;
+    // native distributed mode (phb200_solver_set_peer_native): any method on x-slabs with NO host in the loop — reductions all-reduce
+    // inside the kernels (peer_reduce), boundary planes of every product's input are pushed into the neighbours' arrays by k_halo_push
+    int native_peer;
+    phb200_peer_slab nb_lo, nb_hi;          // the slab neighbours' X / R / workspace (CUDA IPC mappings), leading dimension, halo-plane offset, flag word
+    unsigned long long* halo_flags;         // device, caller-owned, zero-filled: [0] written by the lower neighbour, [1] by the upper one
+    unsigned long long halo_seq;            // exchanges made so far (host counter; identical on all ranks)
+    unsigned* halo_ticket;                  // device, owned
     int resident;              // PHB200_OPT_RESIDENT: -1 cost model decides, 0 never, 1 whenever the system fits on chip
     int resident_used;         // 1 if the last run() went through the resident kernel
     int64_t off, n_act;        // element range [off, off + n_act) of every vector that this rank owns (whole vector if not a slab)
@@ -898,6 +905,49 @@ static int vectors_needed(int method, int L, int pre) {
     return 0;
 }
 
+// Native halo exchange of the distributed mode: every rank stores the first / last owned plane of `v` into the slab neighbours' halo planes
+// of THEIR copy of the same vector (peer memory, plain coalesced stores over NVLink), fences at system scope, and the last CTA tells the
+// neighbours "exchange number seq has landed" with one 8-byte word each, then waits for theirs.  The product that follows on the stream
+// therefore reads current halo planes without any host involvement.  Skipped (like every other kernel of a pass) once all systems finished.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_halo_push(const T* __restrict__ v, int64_t ld, int64_t first_off, int64_t last_off, int64_t plane, int batch,
+                                                      T* lo_dst, int64_t lo_ld, T* hi_dst, int64_t hi_ld,
+                                                      unsigned long long* lo_flag, unsigned long long* hi_flag, const unsigned long long* my_flags,
+                                                      unsigned long long seq, unsigned* ticket, const Glob* glob, int always) {
+    if (!always && glob->any_go == 0) return;
+    const int64_t total = plane * batch;
+    bool wrote = false;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < total; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t b = i / plane, o = i - b * plane;
+        if (lo_dst) { lo_dst[b * lo_ld + o] = v[b * ld + first_off + o]; wrote = true; }
+        if (hi_dst) { hi_dst[b * hi_ld + o] = v[b * ld + last_off + o]; wrote = true; }
+    }
+    if (wrote) __threadfence_system();
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    *ticket = 0u;
+    __threadfence_system();
+    if (lo_flag) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(lo_flag), "l"(seq) : "memory");
+    if (hi_flag) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(hi_flag), "l"(seq) : "memory");
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+        if (!(side == 0 ? lo_flag : hi_flag)) continue;          // no neighbour on that side
+        unsigned long long got = 0;
+        while (true) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(my_flags + side) : "memory");
+            if (got >= seq) break;
+            if (clock64() - t0 > 8000000000ll) __trap();
+        }
+    }
+    __threadfence_system();
+}
+
 template <typename T>
 struct Run {
     phb200_solver* s;
@@ -923,7 +973,8 @@ struct Run {
     void prof_end() {
         if (s->prof) cudaEventRecord(s->prof_events->back(), st);
     }
-    bool cb_mode() const { return s->ar_cb != nullptr; }
+    bool cb_mode() const { return s->ar_cb != nullptr || s->native_peer; }
+    bool native() const { return s->native_peer != 0; }
     // all-reduce of the deferred local sums over the ranks, then the scalar step on every rank identically
     template <class F> int reduce_and_finalize(const F& f) {
         const int rc = s->ar_cb(s->totals, (int64_t)batch * kMaxDots, (void*)st, s->cb_user);
@@ -932,7 +983,7 @@ struct Run {
     }
     template <class P> int phase(const P& p) {
         if constexpr (P::ND > 0) {
-            if (cb_mode()) {
+            if (cb_mode() && !native()) {        // (native mode: the kernel all-reduces and finalises by itself, red.peer is set)
                 P q = p;
                 q.defer = s->totals;
                 prof_begin();
@@ -952,7 +1003,9 @@ struct Run {
         return PHB200_OK;
     }
     template <class E> int spmv(const T* x, T* y, const E& e) {
-        if (cb_mode()) {
+        if (native()) {
+            PHB_TRY(native_halo(x, e.always != 0));
+        } else if (cb_mode()) {
             const int rc = s->halo_cb((void*)x, (void*)st, s->cb_user);   // the neighbours' boundary planes of the input vector
             if (rc != 0) { set_error("halo callback failed (%d)", rc); return PHB200_ERR_CUDA; }
             if constexpr (E::ND > 0) {
@@ -969,6 +1022,30 @@ struct Run {
         int r = launch_spmv<T, E>(s->A, x, ld, y, ld, (const T*)nullptr, batch, e, st);
         prof_end();
         return r;
+    }
+
+    // the same vector in a neighbour's memory: X, R or work vector k of ITS workspace (ranks may own different numbers of planes)
+    T* peer_vector(const phb200_peer_slab& nb, const T* x) const {
+        if (!nb.X) return nullptr;
+        if ((const void*)x == s->X) return (T*)nb.X;
+        if ((const void*)x == s->R) return (T*)nb.R;
+        const int64_t k = (x - (const T*)s->ws) / ((int64_t)batch * ld);
+        return (T*)nb.ws + k * batch * nb.ld;
+    }
+    int native_halo(const T* x, bool always) {
+        const StarDesc& sd = s->A->star;
+        const int64_t plane = sd.ny * sd.nz;
+        T* lo = peer_vector(s->nb_lo, x);
+        T* hi = peer_vector(s->nb_hi, x);
+        if (lo) lo += s->nb_lo.halo_off;
+        if (hi) hi += s->nb_hi.halo_off;
+        s->halo_seq += 1;
+        const int64_t total = plane * batch;
+        const unsigned grid = (unsigned)std::min<int64_t>((total + kBlock - 1) / kBlock, kSMs * 2);
+        PHB_LAUNCH(k_halo_push<T>, grid, kBlock, 0, st, x, ld, sd.xb * plane, (sd.xe - 1) * plane, plane, batch, lo, s->nb_lo.ld, hi, s->nb_hi.ld,
+                   (unsigned long long*)s->nb_lo.flag, (unsigned long long*)s->nb_hi.flag, (const unsigned long long*)s->halo_flags, s->halo_seq, s->halo_ticket,
+                   (const Glob*)s->glob, always ? 1 : 0);
+        return PHB200_OK;
     }
 
     int lin2(T* out, const T* a, const T* b, int slot, int sign) {
@@ -1898,6 +1975,29 @@ int phb200_solver_set_dist_callbacks(phb200_solver* s, void* totals, phb200_allr
     return PHB200_OK;
 }
 
+int phb200_solver_set_peer_native(phb200_solver* s, void* totals, void* const* mailboxes, int world, int rank,
+                                  const phb200_peer_slab* lower, const phb200_peer_slab* upper, void* my_flags, void* stream_) {
+    PHB_ARG(s && !s->started && !s->totals, "set_peer_native must be called before start, instead of the other distributed modes");
+    PHB_ARG(totals && my_flags, "null argument");
+    PHB_ARG(s->A->kind == PHB200_MAT_STENCIL && s->A->is_star, "distributed solves need a star stencil in slab mode (phb200_matrix_set_slab)");
+    PHB_ARG(!pre_applied(s->pre), "ILU across slabs is a pipeline along x (and 'cluster' a global coarse solve): not supported in distributed mode");
+    s->totals = (double*)totals;          // marks the solver as distributed; the native mode defers nothing into it
+    int r = phb200_solver_set_peer_reduce(s, mailboxes, world, rank, stream_);
+    if (r != PHB200_OK) { s->totals = nullptr; return r; }
+    memset(&s->nb_lo, 0, sizeof(s->nb_lo));
+    memset(&s->nb_hi, 0, sizeof(s->nb_hi));
+    if (lower && lower->X) s->nb_lo = *lower;
+    if (upper && upper->X) s->nb_hi = *upper;
+    s->halo_flags = (unsigned long long*)my_flags;
+    s->halo_seq = 0;
+    if (!s->halo_ticket) {
+        PHB_CUDA(cudaMalloc(&s->halo_ticket, sizeof(unsigned)));
+        PHB_CUDA(cudaMemsetAsync(s->halo_ticket, 0, sizeof(unsigned), (cudaStream_t)stream_));
+    }
+    s->native_peer = 1;
+    return PHB200_OK;
+}
+
 int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, int64_t ld_lower, void* upper_neighbour_halo, int64_t ld_upper) {
     PHB_ARG(s && s->totals && !s->ar_cb, "peer halos belong to the step-driven distributed mode (phb200_solver_set_dist)");
     s->peer_lo = lower_neighbour_halo;
@@ -1908,7 +2008,7 @@ int phb200_solver_set_peer_halos(phb200_solver* s, void* lower_neighbour_halo, i
 }
 
 int phb200_solver_set_peer_reduce(phb200_solver* s, void* const* mailboxes, int world, int rank, void* stream_) {
-    PHB_ARG(s && s->totals && !s->ar_cb && !s->started, "peer reduce belongs to the step-driven distributed mode and is set before start");
+    PHB_ARG(s && s->totals && !s->ar_cb && !s->started, "peer reduce belongs to the step-driven / native distributed modes and is set before start");
     PHB_ARG(mailboxes && world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad world / rank (at most 8 ranks)");
     cudaStream_t st = (cudaStream_t)stream_;
     PeerReduce h;
@@ -1954,7 +2054,7 @@ int phb200_solver_dist_advance(phb200_solver* s, int n_iter, void* stream_) {
 
 int phb200_solver_advance(phb200_solver* s, int n_iter, void* stream_) {
     PHB_ARG(s && s->started, "solver not started");
-    PHB_ARG(!s->totals || s->ar_cb, "a step-driven distributed solver is advanced with phb200_solver_dist_step");
+    PHB_ARG(!s->totals || s->ar_cb || s->native_peer, "a step-driven distributed solver is advanced with phb200_solver_dist_step");
     PHB_ARG(n_iter >= 0, "n_iter must be >= 0");
     return advance(s, n_iter, (cudaStream_t)stream_);
 }
@@ -1986,7 +2086,7 @@ int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream_) {
 int phb200_solver_run(phb200_solver* s, int64_t iteration_cap, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started, "solver not started");
-    PHB_ARG(!s->totals || s->ar_cb, "a step-driven distributed solver is advanced with phb200_solver_dist_step");
+    PHB_ARG(!s->totals || s->ar_cb || s->native_peer, "a step-driven distributed solver is advanced with phb200_solver_dist_step");
     if (s->passes == 0) {   // small systems: the whole loop on chip (resident.cuh)
         int cs = 0, lpc = 0;
         size_t smem = 0;
@@ -2069,6 +2169,7 @@ int phb200_solver_destroy(phb200_solver* s) {
         delete s->prof_slots;
     }
     if (s->peer_reduce) cudaFree(s->peer_reduce);
+    if (s->halo_ticket) cudaFree(s->halo_ticket);
     if (s->peer_seq) cudaFree(s->peer_seq);
     if (s->scratch) {
         ScratchBlock blk{s->scratch, s->scratch_bytes, s->h_flag, {s->ev[0], s->ev[1]}, s->device};

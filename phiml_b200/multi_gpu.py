@@ -369,7 +369,7 @@ class SlabSolver:
     """
 
     def __init__(self, grid: Sequence[int], offsets, coeffs, dtype: torch.dtype, method: str = 'biCG-stab(2)', jacobi: bool = False,
-                 device=None, group=None, engine_factory=None):
+                 device=None, group=None, engine_factory=None, native: Optional[bool] = None):
         assert len(grid) == 3, "slab partition is for 3-D grids (x is the partitioned axis)"
         self.grid = tuple(int(g) for g in grid)
         self.group = group
@@ -382,7 +382,16 @@ class SlabSolver:
         self.method = method
         self.counts = {'allreduce': 0, 'halo': 0}
         ext_grid = (self.nxl + 2, self.grid[1], self.grid[2])
-        factory = engine_factory or (lambda g, xb, xe: CudaCallbackEngine(g, xb, xe, offsets, coeffs, dtype, method, jacobi, device))
+        # native: nothing on the host inside the loop (peer-memory halo pushes + in-kernel all-reduces, CudaPeerEngine); needs one process per GPU
+        # with peer access.  Default: native on CUDA with more than one rank (PHB200_SLAB_NATIVE=0 restores the callbacks).
+        if native is None:
+            import os
+            native = engine_factory is None and self.world > 1 and os.environ.get('PHB200_SLAB_NATIVE', '1') != '0'
+        self.native = bool(native)
+        if self.native:
+            factory = lambda g, xb, xe: CudaPeerEngine(g, xb, xe, offsets, coeffs, dtype, method, jacobi, device, self.rank, self.world, self.nxl, self.plane, self.group)
+        else:
+            factory = engine_factory or (lambda g, xb, xe: CudaCallbackEngine(g, xb, xe, offsets, coeffs, dtype, method, jacobi, device))
         self.engine = factory(ext_grid, 1, self.nxl + 1)
 
     extend = SlabCG.extend
@@ -483,5 +492,107 @@ class CudaCallbackEngine:
                 raise errors[0]
             raise
         its, fev, conv, div = solver.result()
+        self.last_solver = solver
+        return solver.x, solver.r, its, fev, conv, div
+
+
+class CudaPeerEngine:
+    """libphb200's NATIVE distributed mode (phb200_solver_set_peer_native) behind the SlabSolver engine interface: every rank maps its slab
+    neighbours' X / R / workspace arrays and all ranks' mailboxes through CUDA IPC once per solve; after that a pass of ANY method is only
+    kernels — halo planes are pushed into the neighbours' arrays by k_halo_push, dot products are all-reduced inside the kernels that form
+    them.  The callbacks of the engine interface are ignored (counts of collectives stay at what the algorithm needs: see `counts`)."""
+
+    def __init__(self, ext_grid, xb, xe, offsets, coeffs, dtype, method, jacobi, device, rank, world, nxl, plane, group):
+        from . import _engine as E
+        from .sparse import Matrix
+        from .precond import JacobiPreconditioner
+        self.E = E
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.matrix = Matrix.stencil_matrix(ext_grid, offsets, coeffs, dtype, self.device)
+        E.check(E.lib().phb200_matrix_set_slab(self.matrix.handle, xb, xe))
+        self.pre = JacobiPreconditioner(self.matrix) if jacobi else None
+        self.method = method
+        self.rank, self.world, self.nxl, self.plane, self.group = rank, world, nxl, plane, group
+
+    def _export(self, t: torch.Tensor):
+        import ctypes
+        handle = (ctypes.c_ubyte * 64)()
+        offset = ctypes.c_int64()
+        self.E.check(self.E.lib().phb200_ipc_export(self.E.ptr(t), handle, ctypes.byref(offset)))
+        return bytes(handle), int(offset.value)
+
+    def _open(self, exported):
+        import ctypes
+        h, off = exported
+        base = ctypes.c_void_p()
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+        self.E.check(self.E.lib().phb200_ipc_open(buf, ctypes.byref(base)))
+        self._bases.append(base)
+        return base.value + off
+
+    def solve(self, y_ext, x_ext, rtol, atol, max_iter, allreduce, halo, fixed_iterations=None):
+        import ctypes
+        from .solve import DeviceSolver
+        E = self.E
+        nb, n_ext = y_ext.shape
+        dev = y_ext.device
+        w = y_ext.element_size()
+        code, order, _ = _method_code(self.method, self.pre, np.array([[max_iter]]))
+        if code == E.CG_TORCH:
+            code = E.CG
+        if code == E.CG_ADAPTIVE_TORCH:
+            code = E.CG_ADAPTIVE
+        solver = DeviceSolver(self.matrix, self.pre, code, order, nb)
+        rt = torch.as_tensor(rtol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
+        at = torch.as_tensor(atol, device=dev).to(y_ext.dtype).reshape(-1).expand(nb).contiguous()
+        mi = torch.full((nb,), int(max_iter), dtype=torch.int32, device=dev)
+        # every array a neighbour may store into is its own allocation (IPC handles name whole allocations), zero-filled: halo planes start as zeros
+        x = torch.zeros_like(y_ext)
+        r = torch.zeros_like(y_ext)
+        ws = torch.zeros(solver.workspace_bytes(), dtype=torch.uint8, device=dev)
+        mail_bytes = int(E.lib().phb200_peer_mailbox_bytes(self.world, nb))
+        mail = torch.zeros(mail_bytes + 64, dtype=torch.uint8, device=dev)          # + two sequence words of the halo exchange
+        totals = torch.zeros(nb * 4, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        self._bases = []
+        mine = {'x': self._export(x), 'r': self._export(r), 'ws': self._export(ws), 'mail': self._export(mail), 'nxl': int(self.nxl)}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        boxes = (ctypes.c_void_p * self.world)()
+        for p in range(self.world):
+            boxes[p] = mail.data_ptr() if p == self.rank else self._open(everyone[p]['mail'])
+
+        class PeerSlab(ctypes.Structure):
+            _fields_ = [('X', ctypes.c_void_p), ('R', ctypes.c_void_p), ('ws', ctypes.c_void_p), ('ld', ctypes.c_int64), ('halo_off', ctypes.c_int64), ('flag', ctypes.c_void_p)]
+
+        def neighbour(nbr, lower):
+            if nbr < 0 or nbr >= self.world:
+                return None
+            info = everyone[nbr]
+            nxl_nb = info['nxl']
+            halo_plane = nxl_nb + 1 if lower else 0            # its upper halo plane (I am its upper neighbour) / its lower one
+            flag_index = 1 if lower else 0                      # its my_flags[1] is written by ITS upper neighbour, [0] by its lower one
+            return PeerSlab(self._open(info['x']), self._open(info['r']), self._open(info['ws']), (nxl_nb + 2) * self.plane, halo_plane * self.plane,
+                            boxes[nbr] + mail_bytes + 8 * flag_index)
+        lo, hi = neighbour(self.rank - 1, True), neighbour(self.rank + 1, False)
+        E.check(E.lib().phb200_solver_set_peer_native(solver._h, E.ptr(totals), boxes, self.world, self.rank, ctypes.byref(lo) if lo else None,
+                                                      ctypes.byref(hi) if hi else None, ctypes.c_void_p(mail.data_ptr() + mail_bytes), E.stream_ptr(dev)))
+        self._keep = (x, r, ws, mail, totals, lo, hi)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)        # every rank has mapped and zero-filled before anybody stores
+        try:
+            solver.start(y_ext, x_ext, rt, at, mi, zero_init=True, buffers=(x, r, ws))
+            if fixed_iterations is not None:
+                solver.advance(int(fixed_iterations))
+            else:
+                solver.run(int(max_iter))
+            its, fev, conv, div = solver.result()
+            torch.cuda.synchronize(dev)
+        finally:
+            if dist.is_initialized():
+                dist.barrier(group=self.group)    # nobody unmaps while a neighbour's kernel may still store
+            for base in self._bases:
+                E.check(E.lib().phb200_ipc_close(base))
+            self._bases = []
         self.last_solver = solver
         return solver.x, solver.r, its, fev, conv, div

@@ -86,13 +86,21 @@ class DeviceSolver:
     def resident_used(self) -> bool:
         return bool(self.option(OPT_RESIDENT_USED))
 
-    def start(self, y, x0, rtol, atol, max_iter, zero_init=False):
+    def workspace_bytes(self) -> int:
+        return int(E.lib().phb200_solver_workspace_bytes(self._h))
+
+    def start(self, y, x0, rtol, atol, max_iter, zero_init=False, buffers=None):
+        """``buffers``: (x, r, workspace) allocated by the caller (native distributed mode: the slab neighbours map them beforehand)."""
         dev = y.device
         alloc = torch.zeros_like if zero_init else torch.empty_like     # slab mode: halo planes must start as zeros
-        self.x = alloc(y)
-        self.r = alloc(y)
-        nbytes = int(E.lib().phb200_solver_workspace_bytes(self._h))
-        self.workspace = (torch.zeros if zero_init else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
+        nbytes = self.workspace_bytes()
+        if buffers is not None:
+            self.x, self.r, self.workspace = buffers
+            assert self.x.shape == y.shape and self.r.shape == y.shape and self.workspace.numel() >= nbytes
+        else:
+            self.x = alloc(y)
+            self.r = alloc(y)
+            self.workspace = (torch.zeros if zero_init else torch.empty)(nbytes, dtype=torch.uint8, device=dev)
         self._keep = (y, x0, rtol, atol, max_iter)
         E.check(E.lib().phb200_solver_start(self._h, E.ptr(y), E.ptr(x0), E.ptr(self.x), E.ptr(self.r), E.ptr(rtol), E.ptr(atol), E.ptr(max_iter),
                                             E.ptr(self.workspace), nbytes, E.stream_ptr(dev)))
