@@ -251,8 +251,13 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 for (int k = 0; k < kStages && k < P; ++k) issue((int)x0 - 1 + k);
             Quad<T> x_cur{{T(0), T(0), T(0), T(0)}};
             Quad<T> r_prev{{T(0), T(0), T(0), T(0)}};          // r of the plane whose product is formed next (ALG 1: d.r)
+            // the thread's own quad of d_new of the last two planes and the row's halo-column value (first / last lane) stay in registers:
+            // only the y neighbours (other warps' rows) are read back from the plane ring; z neighbours inside a row travel by warp shuffle
+            Quad<T> dn_m{{T(0), T(0), T(0), T(0)}}, dn_c{{T(0), T(0), T(0), T(0)}};
+            T hz_c = T(0);
+            const int hcol = lane == 0 ? 3 : 4 + SZ;
             int64_t off = ((x0 - 1) * ny + jy) * nz + jz;      // element offset of (plane x0-1, jy, jz); advanced per plane
-            uint32_t pl_off = 0, pc_off = 3 * TB, pm_off = 2 * TB;   // byte offsets of planes k, k-1, k-2 in the ring
+            uint32_t pl_off = 0, pc_off = 3 * TB;              // byte offsets of planes k, k-1 in the ring
             for (int k = 0; k < P; ++k) {
                 const bool owned = mine && k >= 1 && k <= P - 2;
                 // the x values of the next owned plane travel while this plane is processed
@@ -264,93 +269,91 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 T(*dt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg + 1) * TB);
                 T(*pl)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pl_off);
                 stg = stg + 1 == kStages ? 0 : stg + 1;
-                Quad<T> rv_keep{{T(0), T(0), T(0), T(0)}};
-                {
-                    const Quad<T> rv = ld4<T>(&rt[sr][c]), dv = ld4<T>(&dt[sr][c]);
-                    rv_keep = rv;
-                    Quad<T> dn;
+                const Quad<T> rv = ld4<T>(&rt[sr][c]), dv = ld4<T>(&dt[sr][c]);
+                Quad<T> dn;
+                T hz_n = T(0);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
-                    st4(&pl[sr][c], dn);
-                    if (owned) {
-                        if (has(6)) st4_hint(d_new + off, dn, pol_of(6));
-                        else st4(d_new + off, dn);
-                        if (apply_x) {
+                for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
+                st4(&pl[sr][c], dn);
+                if (owned) {
+                    if (has(6)) st4_hint(d_new + off, dn, pol_of(6));
+                    else st4(d_new + off, dn);
+                    if (apply_x) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
-                            if (has(4)) st4_hint(xb + off, x_cur, pol_of(4));
-                            else st4(xb + off, x_cur);
-                        }
-                    } else if ((k == 0 && halo_lo) || (k == P - 1 && halo_hi)) {
-                        st4(d_new + off, dn);
+                        for (int e = 0; e < 4; ++e) x_cur.v[e] = add_rn(x_cur.v[e], mul_rn(alpha, dv.v[e]));
+                        if (has(4)) st4_hint(xb + off, x_cur, pol_of(4));
+                        else st4(xb + off, x_cur);
                     }
-                    if (warp < 2) {   // halo rows
-                        const int hr = warp == 0 ? 0 : SY + 1;
-                        const Quad<T> rh = ld4<T>(&rt[hr][c]), dh = ld4<T>(&dt[hr][c]);
-                        Quad<T> hn;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e]);
-                        st4(&pl[hr][c], hn);
-                    }
-                    if (t >= 64 && t < 64 + 2 * SROWS) {   // halo columns
-                        const int row = (t - 64) >> 1, col = ((t - 64) & 1) ? 4 + SZ : 3;
-                        pl[row][col] = dir(rt[row][col], dt[row][col]);
-                    }
+                } else if ((k == 0 && halo_lo) || (k == P - 1 && halo_hi)) {
+                    st4(d_new + off, dn);
                 }
+                if (warp < 2) {   // halo rows
+                    const int hr = warp == 0 ? 0 : SY + 1;
+                    const Quad<T> rh = ld4<T>(&rt[hr][c]), dh = ld4<T>(&dt[hr][c]);
+                    Quad<T> hn;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e]);
+                    st4(&pl[hr][c], hn);
+                }
+                if (lane == 0 || lane == 31) hz_n = dir(rt[sr][hcol], dt[sr][hcol]);   // halo columns of this row
                 x_cur = x_next;
                 __syncthreads();   // plane k complete; its stage fully read
                 if (t == 0 && k + kStages < P) issue((int)x0 - 1 + k + kStages);
-                if (k >= 2 && mine) {
-                    T(*pm)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pm_off);
+                if (k >= 2) {
                     T(*pc)[SROW] = reinterpret_cast<T(*)[SROW]>(planes0 + pc_off);
-                    const Quad<T> ce = ld4<T>(&pc[sr][c]);
                     const Quad<T> ym = ld4<T>(&pc[sr - 1][c]), yp = ld4<T>(&pc[sr + 1][c]);
-                    const Quad<T> xm = ld4<T>(&pm[sr][c]), xp = ld4<T>(&pl[sr][c]);
-                    const T left = pc[sr][c - 1], right = pc[sr][c + 4];
-                    Quad<T> out;
-                    T part = T(0), part_r = T(0);
+                    T left = __shfl_up_sync(0xffffffffu, dn_c.v[3], 1), right = __shfl_down_sync(0xffffffffu, dn_c.v[0], 1);
+                    if (lane == 0) left = hz_c;
+                    if (lane == 31) right = hz_c;
+                    if (mine) {
+                        const Quad<T>& ce = dn_c;
+                        const Quad<T>& xm = dn_m;
+                        const Quad<T>& xp = dn;
+                        Quad<T> out;
+                        T part = T(0), part_r = T(0);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const T zm = e == 0 ? left : ce.v[e - 1];
-                        const T zp = e == 3 ? right : ce.v[e + 1];
-                        T sum;
-                        if constexpr (UNIT) {      // all six neighbour coefficients are -1: c*v == -v exactly, no multiply needed
-                            sum = -xm.v[e];
-                            sum = add_rn(sum, -ym.v[e]);
-                            sum = add_rn(sum, -zm);
-                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
-                            sum = add_rn(sum, -zp);
-                            sum = add_rn(sum, -yp.v[e]);
-                            sum = add_rn(sum, -xp.v[e]);
-                        } else {
-                            sum = mul_rn(cxm, xm.v[e]);
-                            sum = add_rn(sum, mul_rn(cym, ym.v[e]));
-                            sum = add_rn(sum, mul_rn(czm, zm));
-                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
-                            sum = add_rn(sum, mul_rn(czp, zp));
-                            sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
-                            sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                        for (int e = 0; e < 4; ++e) {
+                            const T zm = e == 0 ? left : ce.v[e - 1];
+                            const T zp = e == 3 ? right : ce.v[e + 1];
+                            T sum;
+                            if constexpr (UNIT) {      // all six neighbour coefficients are -1: c*v == -v exactly, no multiply needed
+                                sum = -xm.v[e];
+                                sum = add_rn(sum, -ym.v[e]);
+                                sum = add_rn(sum, -zm);
+                                sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                                sum = add_rn(sum, -zp);
+                                sum = add_rn(sum, -yp.v[e]);
+                                sum = add_rn(sum, -xp.v[e]);
+                            } else {
+                                sum = mul_rn(cxm, xm.v[e]);
+                                sum = add_rn(sum, mul_rn(cym, ym.v[e]));
+                                sum = add_rn(sum, mul_rn(czm, zm));
+                                sum = add_rn(sum, mul_rn(c0, ce.v[e]));
+                                sum = add_rn(sum, mul_rn(czp, zp));
+                                sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
+                                sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                            }
+                            out.v[e] = sum;
+                            const T pr = mul_rn(ce.v[e], sum);
+                            part = e == 0 ? pr : add_rn(part, pr);
+                            if constexpr (ALG == 1) {
+                                const T prr = mul_rn(ce.v[e], r_prev.v[e]);
+                                part_r = e == 0 ? prr : add_rn(part_r, prr);
+                            }
                         }
-                        out.v[e] = sum;
-                        const T pr = mul_rn(ce.v[e], sum);
-                        part = e == 0 ? pr : add_rn(part, pr);
-                        if constexpr (ALG == 1) {
-                            const T prr = mul_rn(ce.v[e], r_prev.v[e]);
-                            part_r = e == 0 ? prr : add_rn(part_r, prr);
-                        }
+                        acc[0] += (double)part;        // the four products of a quad are added in T before they join the double sum
+                        if constexpr (ALG == 1) acc[1] += (double)part_r;
+                        if (has(8)) st4_hint(qb + off - pstride, out, pol_of(8));
+                        else st4(qb + off - pstride, out);
                     }
-                    acc[0] += (double)part;        // the four products of a quad are added in T before they join the double sum
-                    if constexpr (ALG == 1) acc[1] += (double)part_r;
-                    if (has(8)) st4_hint(qb + off - pstride, out, pol_of(8));
-                    else st4(qb + off - pstride, out);
                 }
                 off += pstride;
-                r_prev = rv_keep;
-                const uint32_t tmp_off = pm_off;   // rotate the ring: k-1 -> k-2, k -> k-1, next plane reuses the slot after k-2's
-                pm_off = pc_off;
-                pc_off = pl_off;
+                r_prev = rv;
+                dn_m = dn_c;
+                dn_c = dn;
+                hz_c = hz_n;
+                pc_off = pl_off;   // rotate the ring: k -> k-1; the next plane takes the slot after k's (the slot of k-1 may still be read by slower warps)
                 pl_off = pl_off + TB == 4 * TB ? 0 : pl_off + TB;
-                (void)tmp_off;
             }
         }
     }
@@ -413,22 +416,34 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
             };
             __syncthreads();   // every stage of the previous item has been consumed
             if (t == 0)
-                for (int k = 0; k < S - 1 && k < P; ++k) issue((int)x0 - 1 + k);
+                for (int k = 0; k < S && k < P; ++k) issue((int)x0 - 1 + k);
             int64_t off = (x0 * ny + jy) * nz + jz;              // element offset of the first OUTPUT plane
-            uint32_t s_m = 0, s_c = 0;                           // stages of planes k-2, k-1
+            uint32_t s_c = 0;                                    // stage of plane k-1
+            // every thread keeps its own quad of the last three planes in registers (a plane's quad is read from shared memory once, when
+            // the plane arrives); only the y neighbours (other warps' rows) and the two halo columns of a row come from the staged tiles.
+            // z neighbours inside the row travel by warp shuffle (the scalar loads at c-1 / c+4 were 4-way bank conflicts).
+            Quad<T> q_m{{T(0), T(0), T(0), T(0)}}, q_c{{T(0), T(0), T(0), T(0)}};
+            const int hcol = lane == 0 ? 3 : 4 + SZ;             // halo column read by the first / last lane of a row
             for (int k = 0; k < P; ++k) {
                 mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
                 phase_bits ^= 1u << stg;
                 const uint32_t s_p = stg;
                 stg = stg + 1 == S ? 0 : stg + 1;
-                if (k >= 2 && mine) {
-                    T(*pm)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_m * TB);
+                T(*pp)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_p * TB);
+                const Quad<T> q_p = ld4<T>(&pp[sr][c]);
+                if (k >= 2) {
                     T(*pc)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_c * TB);
-                    T(*pp)[SROW] = reinterpret_cast<T(*)[SROW]>(base + (size_t)s_p * TB);
-                    const Quad<T> ce = ld4<T>(&pc[sr][c]);
                     const Quad<T> ym = ld4<T>(&pc[sr - 1][c]), yp = ld4<T>(&pc[sr + 1][c]);
-                    const Quad<T> xm = ld4<T>(&pm[sr][c]), xp = ld4<T>(&pp[sr][c]);
-                    const T left = pc[sr][c - 1], right = pc[sr][c + 4];
+                    T left = __shfl_up_sync(0xffffffffu, q_c.v[3], 1), right = __shfl_down_sync(0xffffffffu, q_c.v[0], 1);
+                    if (lane == 0 || lane == 31) {
+                        const T h = pc[sr][hcol];
+                        if (lane == 0) left = h;
+                        else right = h;
+                    }
+                    if (mine) {
+                    const Quad<T>& ce = q_c;
+                    const Quad<T>& xm = q_m;
+                    const Quad<T>& xp = q_p;
                     Quad<T> out;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -458,11 +473,13 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
 #pragma unroll
                     for (int e = 0; e < 4; ++e) epi.row(b, off + e, out.v[e], acc);
                     off += pstride;
+                    }
                 }
-                __syncthreads();   // the stage of plane k-2 is free; plane k-1, k stay
-                // planes in flight: k+1 .. k+S-2 have been issued; the freed stage takes plane k+S-1
-                if (t == 0 && k >= 1 && k + S - 2 < P) issue((int)x0 - 1 + k + S - 2);
-                s_m = s_c;
+                q_m = q_c;
+                q_c = q_p;
+                __syncthreads();   // the stage of plane k-1 is free (its rows were read as y neighbours above); plane k stays for the next step
+                // planes k+1 .. k+S-2 are in flight; the freed stage takes plane k+S-1
+                if (t == 0 && k >= 1 && k + S - 1 < P) issue((int)x0 - 1 + k + S - 1);
                 s_c = s_p;
             }
         }
