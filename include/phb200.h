@@ -66,6 +66,7 @@ extern "C" {
 /* matrix kinds */
 #define PHB200_MAT_CSR 0
 #define PHB200_MAT_STENCIL 1
+#define PHB200_MAT_CODED 2
 
 typedef struct phb200_matrix phb200_matrix;
 typedef struct phb200_precond phb200_precond;
@@ -98,6 +99,17 @@ int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int r
  * phb200_stencil_nnz gives the array sizes. */
 int phb200_stencil_nnz(const phb200_matrix* stencil, int64_t* nnz);
 int phb200_stencil_to_csr(const phb200_matrix* stencil, int32_t* rowptr, int32_t* col, void* val, void* stream);
+
+/* Pattern-coded form of a CSR matrix whose rows fall into few distinct (offset, value) patterns — what matrix_from_function emits for
+ * stencils with ZERO_GRADIENT / PERIODIC boundaries, masks or piecewise-constant coefficients (phiml/math/_lin_trace.py:750-807: one
+ * value array per shift, wrapped columns).  The device recognises <= 16 distinct flat offsets (col - row) and <= 256 distinct rows, verifies
+ * every row bit for bit and stores ONE BYTE per row plus a table of the distinct rows; products (phb200_spmv, every Krylov loop) then move
+ * N + 2 N w bytes instead of 8 nnz + 4 (N+1) + 2 N w and are bit-identical to the CSR product (ascending-column order, separately rounded
+ * products).  *out views the CSR arrays as well (they must stay alive) and owns its code / table arrays.  PHB200_ERR_NOT_STENCIL when the
+ * matrix does not qualify (unsorted columns, too many offsets or patterns, non-square).  Synchronises stream. */
+int phb200_coded_from_csr(phb200_matrix** out, const phb200_matrix* csr, void* stream);
+/* number of offsets / patterns of a coded matrix; offsets (may be NULL) receives up to 16 flat offsets in ascending order */
+int phb200_coded_info(const phb200_matrix* coded, int* n_offsets, int* n_patterns, int64_t* offsets);
 
 /* Slab (row-partition) mode for multi-GPU solves of ONE system: the arrays span `grid[0]` planes (owned planes plus one
  * halo plane per neighbour), but only planes [x_begin, x_end) are produced / updated / reduced over.  Halo planes are

@@ -2,6 +2,7 @@
 #pragma once
 #include "star_tma.cuh"
 #include "csr_bulk.cuh"
+#include "coded.cuh"
 
 namespace phb {
 
@@ -24,6 +25,7 @@ int launch_spmv(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t l
         else PHB_LAUNCH((k_spmv_stencil<T, false, Epi>), grid, kBlock, 0, stream, A->st, n, X, ldx, Y, ldy, scale, batch, epi);
         return PHB200_OK;
     }
+    if (A->kind == PHB200_MAT_CODED && !scale) return launch_coded_spmv<T, Epi>(A->coded, A->n_rows, X, ldx, Y, ldy, batch, epi, stream);
     if (A->transposed) {
         set_error("fused product with a transposed (CSC-native) matrix is not supported; use phb200_spmv");
         return PHB200_ERR_UNSUPPORTED;

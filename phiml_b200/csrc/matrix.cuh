@@ -20,6 +20,17 @@ struct StarDesc {       // centre + nearest neighbours per axis; see stencil_fas
     double c0, cxm, cxp, cym, cyp, czm, czp;
 };
 
+// Pattern-coded stencil (coded.cuh): distinct flat offsets, distinct rows, one code byte per row
+constexpr int kCodedMaxPat = 256;
+struct CodedView {
+    int K, npat;
+    int k_m1, k_p1;                    // index of the offsets -1 / +1 in off[] or -1
+    int fast_na;                       // >= 0: the interior pattern is [na aligned offsets, -1, 0, +1, na aligned offsets] (star stencil with 16-byte aligned rows)
+    int64_t off[kMaxStencil];
+    const uint8_t* code;               // [n_rows rounded up to a multiple of 4]
+    const void* table;                 // [npat][kMaxStencil] of T
+};
+
 struct StencilDesc {
     int rank, npts;
     int64_t dims[3];        // padded with leading 1s: always (nx, ny, nz)
@@ -38,6 +49,8 @@ struct phb200_matrix {
     phb::StencilDesc st;
     int is_star;            // stencil qualifies for the plane-marching kernels (star shape, nz % 4 == 0)
     phb::StarDesc star;
+    phb::CodedView coded;   // PHB200_MAT_CODED: the csr view stays valid next to it
+    void* owned[2];         // device arrays freed with the handle (code bytes, pattern table)
     // lazily computed CSR analysis
     mutable int analysed;
     mutable int64_t max_block_nnz;   // max entries of any 256-row block

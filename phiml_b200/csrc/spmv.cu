@@ -422,6 +422,138 @@ int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int r
     return PHB200_OK;
 }
 
+int phb200_coded_from_csr(phb200_matrix** out, const phb200_matrix* csr, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(out && csr, "null argument");
+    PHB_ARG(csr->kind == PHB200_MAT_CSR && !csr->transposed, "coded-stencil recognition needs a plain CSR matrix");
+    const int64_t n = csr->csr.n_rows;
+    if (n != csr->csr.n_cols || n < 1) { set_error("coded stencils need a square, non-empty matrix"); return PHB200_ERR_NOT_STENCIL; }
+    // pass 1: distinct offsets, distinct row hashes with their first rows
+    CodedScan* h_scan = new CodedScan();
+    for (int k = 0; k < kCodedOffSlots; ++k) h_scan->offs[k] = (unsigned long long)kCodedEmptyOff;
+    for (int k = 0; k < kCodedHashSlots; ++k) { h_scan->hash[k] = 0ull; h_scan->rep[k] = 0x7fffffff; h_scan->cnt[k] = 0; }
+    h_scan->fail = 0;
+    CodedScan* d_scan = nullptr;
+    cudaError_t ce = phb_malloc_async(&d_scan, sizeof(CodedScan), stream);
+    if (ce != cudaSuccess) { delete h_scan; set_error("allocation failed: %s", cudaGetErrorString(ce)); return PHB200_ERR_CUDA; }
+    struct Guard {
+        CodedScan* h; void* d[4]; cudaStream_t st;
+        ~Guard() { delete h; for (void* p : d) if (p) cudaFreeAsync(p, st); }
+    } guard{h_scan, {d_scan, nullptr, nullptr, nullptr}, stream};
+    PHB_CUDA(cudaMemcpyAsync(d_scan, h_scan, sizeof(CodedScan), cudaMemcpyHostToDevice, stream));
+    const unsigned gridx = (unsigned)grid_x((n + kBlock - 1) / kBlock, 1, 4);
+    if (csr->dtype == PHB200_F32) PHB_LAUNCH(k_coded_scan<float>, gridx, kBlock, 0, stream, csr->csr, d_scan);
+    else PHB_LAUNCH(k_coded_scan<double>, gridx, kBlock, 0, stream, csr->csr, d_scan);
+    PHB_CUDA(cudaMemcpyAsync(h_scan, d_scan, sizeof(CodedScan), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    if (h_scan->fail) { set_error("rows with unsorted columns, more than %d entries, or too many distinct offsets / rows", kMaxStencil); return PHB200_ERR_NOT_STENCIL; }
+    std::vector<long long> offs;
+    for (int k = 0; k < kCodedOffSlots; ++k)
+        if (h_scan->offs[k] != (unsigned long long)kCodedEmptyOff) offs.push_back((long long)h_scan->offs[k]);
+    std::sort(offs.begin(), offs.end());
+    std::vector<std::pair<int, unsigned long long>> pats;      // (first row, hash)
+    int best_cnt = -1, best_rep = 0;
+    for (int k = 0; k < kCodedHashSlots; ++k)
+        if (h_scan->hash[k] != 0ull) {
+            pats.emplace_back(h_scan->rep[k], h_scan->hash[k]);
+            if (h_scan->cnt[k] > best_cnt || (h_scan->cnt[k] == best_cnt && h_scan->rep[k] < best_rep)) { best_cnt = h_scan->cnt[k]; best_rep = h_scan->rep[k]; }
+        }
+    if (offs.empty() || (int)offs.size() > kMaxStencil || pats.empty() || (int)pats.size() > kCodedMaxPat) {
+        set_error("%d distinct offsets / %d distinct rows: not a coded stencil (limits %d / %d)", (int)offs.size(), (int)pats.size(), kMaxStencil, kCodedMaxPat);
+        return PHB200_ERR_NOT_STENCIL;
+    }
+    std::sort(pats.begin(), pats.end());
+    for (size_t k = 0; k < pats.size(); ++k)                   // pattern 0 = the most frequent one (the interior stencil)
+        if (pats[k].first == best_rep) { std::rotate(pats.begin(), pats.begin() + k, pats.begin() + k + 1); break; }
+    CodedDict h_dict;
+    memset(&h_dict, 0, sizeof(h_dict));
+    h_dict.K = (int)offs.size();
+    h_dict.npat = (int)pats.size();
+    for (int k = 0; k < h_dict.K; ++k) h_dict.off[k] = offs[k];
+    for (int k = 0; k < h_dict.npat; ++k) { h_dict.rep[k] = pats[k].first; h_dict.hash[k] = pats[k].second; }
+    // pass 2 + 3: table of the distinct rows, code byte per row with bit-for-bit verification
+    const size_t w = csr->dtype == PHB200_F32 ? 4 : 8;
+    CodedDict* d_dict = nullptr;
+    int* d_fail = nullptr;
+    PHB_CUDA(phb_malloc_async(&d_dict, sizeof(CodedDict), stream));
+    guard.d[1] = d_dict;
+    PHB_CUDA(phb_malloc_async(&d_fail, sizeof(int), stream));
+    guard.d[2] = d_fail;
+    void* d_table = nullptr;
+    uint8_t* d_code = nullptr;
+    const size_t code_bytes = (size_t)((n + 3) / 4 * 4 + 16);
+    PHB_CUDA(cudaMalloc(&d_table, (size_t)h_dict.npat * kMaxStencil * w));
+    if (cudaMalloc((void**)&d_code, code_bytes) != cudaSuccess) { cudaFree(d_table); set_error("allocation of %zu code bytes failed", code_bytes); return PHB200_ERR_CUDA; }
+    auto fail_free = [&](int rc) { cudaFree(d_table); cudaFree(d_code); return rc; };
+    if (cudaMemcpyAsync(d_dict, &h_dict, sizeof(CodedDict), cudaMemcpyHostToDevice, stream) != cudaSuccess || cudaMemsetAsync(d_fail, 0, sizeof(int), stream) != cudaSuccess ||
+        cudaMemsetAsync(d_code, 0, code_bytes, stream) != cudaSuccess) { set_error("set-up copies failed"); return fail_free(PHB200_ERR_CUDA); }
+    if (csr->dtype == PHB200_F32) {
+        k_coded_table<float><<<(h_dict.npat + 63) / 64, 64, 0, stream>>>(csr->csr, d_dict, (float*)d_table);
+        k_coded_assign<float><<<gridx, kBlock, 0, stream>>>(csr->csr, d_dict, (const float*)d_table, d_code, d_fail);
+    } else {
+        k_coded_table<double><<<(h_dict.npat + 63) / 64, 64, 0, stream>>>(csr->csr, d_dict, (double*)d_table);
+        k_coded_assign<double><<<gridx, kBlock, 0, stream>>>(csr->csr, d_dict, (const double*)d_table, d_code, d_fail);
+    }
+    g_launches.fetch_add(2);
+    int h_fail = 0;
+    if (cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {
+        set_error("coded-stencil kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail_free(PHB200_ERR_CUDA);
+    }
+    if (h_fail) { set_error("row verification failed (hash collision or inconsistent rows): the matrix stays CSR"); return fail_free(PHB200_ERR_NOT_STENCIL); }
+    phb200_matrix* m = new phb200_matrix();
+    memset(m, 0, sizeof(*m));
+    m->kind = PHB200_MAT_CODED;
+    m->dtype = csr->dtype;
+    m->csr = csr->csr;
+    m->n_rows = m->n_cols = n;
+    m->nnz = csr->nnz;
+    m->coded.K = h_dict.K;
+    m->coded.npat = h_dict.npat;
+    m->coded.k_m1 = m->coded.k_p1 = -1;
+    for (int k = 0; k < h_dict.K; ++k) {
+        m->coded.off[k] = offs[k];
+        if (offs[k] == -1) m->coded.k_m1 = k;
+        if (offs[k] == 1) m->coded.k_p1 = k;
+    }
+    // shape of the interior pattern (row 0 of the table): [na aligned offsets, -1, 0, +1, na aligned offsets] selects the specialised product
+    {
+        double c0[kMaxStencil];
+        if (csr->dtype == PHB200_F32) {
+            float t32[kMaxStencil];
+            if (cudaMemcpy(t32, d_table, sizeof(t32), cudaMemcpyDeviceToHost) != cudaSuccess) { delete m; set_error("table copy failed"); return fail_free(PHB200_ERR_CUDA); }
+            for (int k = 0; k < kMaxStencil; ++k) c0[k] = t32[k];
+        } else if (cudaMemcpy(c0, d_table, sizeof(c0), cudaMemcpyDeviceToHost) != cudaSuccess) { delete m; set_error("table copy failed"); return fail_free(PHB200_ERR_CUDA); }
+        const long long va = 16 / (long long)w;
+        std::vector<long long> nzo;
+        for (int k = 0; k < h_dict.K; ++k)
+            if (c0[k] != 0.0) nzo.push_back(offs[k]);
+        m->coded.fast_na = -1;
+        const int cnt = (int)nzo.size();
+        if (cnt >= 3 && (cnt - 3) % 2 == 0) {
+            const int na = (cnt - 3) / 2;
+            bool ok = nzo[na] == -1 && nzo[na + 1] == 0 && nzo[na + 2] == 1;
+            for (int u = 0; u < na && ok; ++u) ok = nzo[u] % va == 0 && nzo[na + 3 + u] % va == 0;
+            if (ok) m->coded.fast_na = na;
+        }
+    }
+    m->coded.code = d_code;
+    m->coded.table = d_table;
+    m->owned[0] = d_code;
+    m->owned[1] = d_table;
+    *out = m;
+    return PHB200_OK;
+}
+
+int phb200_coded_info(const phb200_matrix* m, int* n_offsets, int* n_patterns, int64_t* offsets) {
+    PHB_ARG(m && m->kind == PHB200_MAT_CODED, "need a coded matrix");
+    if (n_offsets) *n_offsets = m->coded.K;
+    if (n_patterns) *n_patterns = m->coded.npat;
+    if (offsets)
+        for (int k = 0; k < m->coded.K; ++k) offsets[k] = m->coded.off[k];
+    return PHB200_OK;
+}
+
 int phb200_stencil_nnz(const phb200_matrix* m, int64_t* nnz) {
     PHB_ARG(m && nnz && m->kind == PHB200_MAT_STENCIL, "need a stencil matrix");
     const StencilDesc& st = m->st;
@@ -485,6 +617,9 @@ int phb200_matrix_info(const phb200_matrix* m, int* kind, int64_t* n_rows, int64
 }
 
 int phb200_matrix_destroy(phb200_matrix* m) {
+    if (m)
+        for (void* p : m->owned)
+            if (p) cudaFree(p);
     delete m;
     return PHB200_OK;
 }

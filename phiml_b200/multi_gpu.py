@@ -86,7 +86,7 @@ def solve_sharded(method: str, lin, y_local: torch.Tensor, x0_local: torch.Tenso
         code, name = E.CG_ADAPTIVE, f"Φ-ML CG-adaptive ({host.BACKEND_NAME}) "
     matrix, y, x0, rtol_t, atol_t, max_iter = host._prepare(lin, y_local, x0_local, rtol, atol, max_iter)
     pre = host._device_pre(pre, matrix)
-    sm = matrix.stencil if matrix.stencil is not None else matrix
+    sm = matrix.product_twin
     nb = y.shape[0]
     mi = torch.as_tensor(np.broadcast_to(np.asarray(max_iter)[-1, :], (nb,)).astype(np.int32).copy(), device=y.device)
     solver = host.DeviceSolver(sm, pre, code, order, nb)

@@ -207,7 +207,7 @@ def _device_pre(pre, matrix):
 def _run(code: int, poly_order: int, name: str, matrix, y, x0, rtol, atol, max_iter: np.ndarray, pre) -> SolveResult:
     nb = y.shape[0]
     # products go through the stencil twin when the matrix was recognised as one (the ILU factors keep the CSR pattern)
-    solver_matrix = matrix.stencil if matrix.stencil is not None else matrix
+    solver_matrix = matrix.product_twin
     if nb <= 65535:
         x, r, its, fev, conv, div = _run_slab(code, poly_order, solver_matrix, y, x0, rtol, atol, max_iter, pre)
         return SolveResult(name, x, r, its, fev, conv, div, [""] * nb)

@@ -26,10 +26,12 @@ class Matrix:
         self.dtype = dtype
         self.shape = tuple(int(s) for s in shape)
         self._keep = keep
-        self.kind = kind          # 'csr' | 'csc' | 'stencil'
+        self.kind = kind          # 'csr' | 'csc' | 'stencil' | 'coded'
         self.device = device
         self.stencil: Optional['Matrix'] = None   # detected stencil twin of a CSR matrix
+        self.coded: Optional['Matrix'] = None     # pattern-coded twin (variable coefficients / non-ZERO boundaries), products only
         self._stencil_checked = False
+        self._coded_checked = False
         self.grid = None
 
     @property
@@ -101,6 +103,34 @@ class Matrix:
         self.stencil = st
         return st
 
+    def detect_coded(self) -> Optional['Matrix']:
+        """Pattern-coded twin (csrc/coded.cuh) of a CSR matrix that is NOT a constant-coefficient ZERO-boundary stencil but still has few
+        distinct rows — ZERO_GRADIENT / PERIODIC boundaries, masks, piecewise-constant coefficients: one code byte per row instead of the
+        matrix stream, products bit-identical to the CSR product.  None if the matrix does not qualify (``PHB200_CODED=0`` switches it off)."""
+        import os
+        if self.kind != 'csr' or self.shape[0] != self.shape[1] or self.shape[0] == 0 or os.environ.get('PHB200_CODED', '1') == '0':
+            return None
+        if self._coded_checked:
+            return self.coded
+        self._coded_checked = True
+        h = ctypes.c_void_p()
+        try:
+            E.check(E.lib().phb200_coded_from_csr(ctypes.byref(h), self._h, E.stream_ptr(self.device)))
+        except E.NotAStencil:
+            return None
+        tw = Matrix(h, self.dtype, self.shape, (self.rowptr, self.col, self.values), 'coded', self.device)     # views this matrix' CSR arrays
+        k, p = ctypes.c_int(), ctypes.c_int()
+        offs = (ctypes.c_int64 * 16)()
+        E.check(E.lib().phb200_coded_info(h, ctypes.byref(k), ctypes.byref(p), offs))
+        tw.offsets, tw.patterns = [int(offs[i]) for i in range(k.value)], int(p.value)
+        self.coded = tw
+        return tw
+
+    @property
+    def product_twin(self) -> 'Matrix':
+        """The handle products and Krylov loops run on: stencil twin, else coded twin, else the matrix itself."""
+        return self.stencil if self.stencil is not None else (self.coded if self.coded is not None else self)
+
     def nnz(self) -> int:
         n = ctypes.c_int64()
         E.check(E.lib().phb200_matrix_info(self._h, None, None, None, ctypes.byref(n), None))
@@ -123,7 +153,7 @@ class Matrix:
         E.require_cuda(x)
         assert x.dim() == 2 and x.shape[1] == self.shape[1], f"expected (batch, {self.shape[1]}), got {tuple(x.shape)}"
         x = x.to(self.dtype).contiguous()
-        m = self.stencil if (use_stencil and self.stencil is not None) else self
+        m = self.product_twin if use_stencil else self
         y = torch.empty((x.shape[0], self.shape[0]), dtype=self.dtype, device=x.device)
         for b0 in range(0, x.shape[0], 65535):
             xb, yb = x[b0:b0 + 65535], y[b0:b0 + 65535]
@@ -201,7 +231,8 @@ def as_matrix(native, detect_stencil=True, grid=None) -> Matrix:
     if hit is not None:
         _CACHE.move_to_end(key)
         if detect_stencil and hit.kind == 'csr' and (grid is not None or not hit._stencil_checked):
-            hit.detect_stencil(grid)          # cached without recognition (detect_stencil=False) earlier
+            if hit.detect_stencil(grid) is None:          # cached without recognition (detect_stencil=False) earlier
+                hit.detect_coded()
         return hit
     kind, a, b, v = comps
     if kind == 'coo':
@@ -213,8 +244,11 @@ def as_matrix(native, detect_stencil=True, grid=None) -> Matrix:
         keep = (native,)
     m._keep = m._keep + keep
     if detect_stencil and m.kind == 'csr':
-        if m.detect_stencil(grid) is None and kind == 'coo':
-            _detect_ignoring_stored_zeros(m, grid)
+        st = m.detect_stencil(grid)
+        if st is None and kind == 'coo':
+            st = _detect_ignoring_stored_zeros(m, grid)
+        if st is None:
+            m.detect_coded()
     _CACHE[key] = m
     while len(_CACHE) > _CACHE_SIZE:
         _CACHE.popitem(last=False)
@@ -253,6 +287,7 @@ def plain_csr(m: Matrix) -> Matrix:
         E.check(E.lib().phb200_csr_transpose(E.ptr(m.rowptr), E.ptr(m.col), E.ptr(m.values), rows_stored, m.shape[0], nnz, E.dtype_code(m.dtype),
                                              E.ptr(rowptr), E.ptr(col), E.ptr(val), E.stream_ptr(m.device)))
         t = Matrix.csr(rowptr, col, val, m.shape)
-        t.detect_stencil()
+        if t.detect_stencil() is None:
+            t.detect_coded()
         m._plain = t
     return t

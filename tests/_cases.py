@@ -70,3 +70,23 @@ SOLVE_CASES = {
     'a24_bicg2_f64': _c('advdiff', (24, 20, 28), 'float64', 'biCG-stab(2)', 1e-10),
     'a24_bicg1_f32': _c('advdiff', (24, 20, 28), 'float32', 'biCG-stab(1)', 1e-5),
 }
+
+
+# operators with ZERO_GRADIENT / PERIODIC / mixed boundaries and piecewise-constant coefficients (tests/golden/boundaries.npz;
+# the operator functions live in make_golden.py: BOUNDARY_OPERATORS)
+BOUNDARY_CASES = [   # (operator, grid, dtype, method, preconditioner, rtol, batch)
+    ('neumann', (12, 10, 8), 'float64', 'CG', 'jacobi', 1e-10, 2),
+    ('neumann', (12, 10, 8), 'float32', 'CG', None, 1e-5, 2),
+    ('neumann', (20, 16), 'float32', 'CG', 'jacobi', 1e-5, 1),
+    ('periodic', (8, 12, 16), 'float64', 'CG', None, 1e-10, 2),
+    ('periodic', (8, 12, 16), 'float32', 'CG', 'jacobi', 1e-5, 1),
+    ('mixed', (10, 9, 12), 'float64', 'CG', 'jacobi', 1e-10, 2),
+    ('mixed', (10, 9, 12), 'float32', 'CG-adaptive', None, 1e-5, 1),
+    ('varcoef', (9, 8, 12), 'float64', 'biCG-stab(2)', None, 1e-10, 2),
+    ('periodic_advdiff', (8, 6, 12), 'float64', 'biCG-stab(2)', None, 1e-10, 2),
+    ('periodic_advdiff', (8, 6, 12), 'float32', 'biCG-stab(2)', 'jacobi', 1e-5, 1),
+    ('varcoef', (9, 8, 12), 'float32', 'biCG-stab(1)', 'jacobi', 1e-5, 2),
+    ('neumann', (31,), 'float64', 'CG', None, 1e-10, 1),
+]
+
+

@@ -25,7 +25,7 @@ from phiml.math._optimize import factor_ilu                                    #
 from phiml.backend._backend import get_backend, Preconditioner                 # noqa: E402
 from phiml.backend import NUMPY                                                # noqa: E402
 
-from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF                   # noqa: E402
+from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES                   # noqa: E402
 
 warnings.filterwarnings('ignore')
 DIMS = 'xyz'
@@ -403,8 +403,45 @@ def golden_cluster(out):
             print(key, repr(pre), r.method, r.iterations, 'without:', r0.iterations, out[key + '/inv_coarse'].dtype, out[key + '/cluster_size'].dtype, out[key + '/clusters'].shape)
 
 
+# ----------------------------------------------------------------------------------------------------------------------------------
+# Operators whose rows are not all alike (second half): ZERO_GRADIENT / PERIODIC / mixed boundaries, piecewise-constant
+# coefficients.  The reference assembles them as general sparse matrices; phb200 recognises the CSR native as a pattern-coded stencil.
+# ----------------------------------------------------------------------------------------------------------------------------------
+from _boundary_ops import BOUNDARY_OPERATORS                                   # noqa: E402
+
+
+def golden_boundaries(out):
+    for op, grid, dt, method, pre_name, rtol, nb in BOUNDARY_CASES:
+        dtype = np.dtype(dt).type
+        with math.precision(64 if dtype == np.float64 else 32):
+            x0 = math.zeros(spatial(**{DIMS[i]: g for i, g in enumerate(grid)}))
+            m, _ = matrix_from_function(BOUNDARY_OPERATORS[op], x0, auto_compress=True)
+            csr = native_matrix(m, NUMPY)
+            assert csr.indices.dtype == np.int32 and csr.indptr.dtype == np.int32, (csr.indices.dtype, csr.indptr.dtype)
+            key = f"bnd/{op}/{'x'.join(map(str, grid))}/{dt}/{method}/{pre_name}"
+            out[key + '/indptr'] = csr.indptr
+            out[key + '/indices'] = csr.indices
+            out[key + '/data'] = csr.data
+            out[key + '/sorted'] = np.bool_(csr.has_sorted_indices)
+            rng = np.random.default_rng(11)
+            v = rng.standard_normal((3, csr.shape[0])).astype(dtype)
+            out[key + '/spmv'] = NUMPY.mul_matrix_batched_vector(csr, v)
+            y = rng.standard_normal((nb, csr.shape[0])).astype(dtype)
+            pre = RefJacobi(csr) if pre_name == 'jacobi' else None
+            rt, at = np.full(nb, rtol, dtype), np.zeros(nb, dtype)
+            with NUMPY:
+                r = NUMPY.linear_solve(method, csr, y, np.zeros_like(y), rt, at, np.full((1, nb), 2000), pre, None)
+            out[key + '/x'] = np.asarray(r.x)
+            out[key + '/iterations'] = np.asarray(r.iterations)
+            out[key + '/function_evaluations'] = np.asarray(r.function_evaluations)
+            out[key + '/converged'] = np.asarray(r.converged)
+            out[key + '/method'] = np.asarray(r.method)
+            rows = np.diff(csr.indptr)
+            print(key, csr.shape, csr.nnz, 'row lengths', np.unique(rows), 'sorted', csr.has_sorted_indices, 'zeros stored', int((csr.data == 0).sum()), r.method, r.iterations, r.converged)
+
+
 def main():
-    groups = {'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}
