@@ -476,6 +476,74 @@ def time_cfg4(ctx, n, iters):
     return out
 
 
+def time_coded(ctx, n, kind):
+    """SURVEY 8f N2 (second half): the n^3 7-point operator with ZERO_GRADIENT ('neumann') or PERIODIC boundaries (+ 0.01 I), as the CSR native
+    matrix_from_function would hand over, recognised on the device as a pattern-coded stencil (csrc/coded.cuh).  Product and Jacobi-CG on the
+    coded kernel and on the CSR kernel of the SAME native (operands rotated over > 4 x L2)."""
+    import phiml_b200 as pb
+    from phiml_b200 import _engine as E
+    torch = ctx.torch
+    dev, N = ctx.dev, n ** 3
+    idx = torch.arange(N, device=dev, dtype=torch.int64)
+    comps = (idx // (n * n), (idx // n) % n, idx % n)
+    cols, vals = [], []
+    deg = torch.zeros(N, device=dev, dtype=torch.float32)
+    for comp, stride in zip(comps, (n * n, n, 1)):
+        for sgn in (-1, 1):
+            j = comp + sgn
+            inside = torch.ones_like(j, dtype=torch.bool) if kind == 'periodic' else (j >= 0) & (j < n)
+            jj = idx + ((j % n) - comp) * stride
+            cols.append(torch.where(inside, jj, torch.full_like(jj, 2 ** 40)))
+            vals.append(torch.where(inside, -torch.ones(N, device=dev), torch.zeros(N, device=dev)))
+            deg += inside.float()
+    cols.append(idx)
+    vals.append(deg + 0.01)
+    C, V = torch.stack(cols, 1), torch.stack(vals, 1)
+    del cols, vals
+    order = torch.argsort(C, dim=1)
+    C, V = torch.gather(C, 1, order), torch.gather(V, 1, order)
+    keep = C < 2 ** 40
+    rowptr = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+    rowptr[1:] = torch.cumsum(keep.sum(1), 0).to(torch.int32)
+    col, val = C[keep].to(torch.int32), V[keep]
+    del C, V, keep, order
+    t0 = time.perf_counter()
+    m = pb.as_matrix(torch.sparse_csr_tensor(rowptr, col, val, (N, N)))
+    torch.cuda.synchronize(dev)
+    rec_s = time.perf_counter() - t0
+    assert m.stencil is None and m.coded is not None, "the operator must be recognised as a pattern-coded stencil"
+    nnz = int(val.numel())
+    pairs = max(2, int(np.ceil(4 * 126e6 / (2 * N * 4))))
+    xs = [torch.randn((1, N), dtype=torch.float32, device=dev, generator=ctx.gen) for _ in range(pairs)]
+    ys = [torch.empty_like(xs[0]) for _ in range(pairs)]
+    out = {"workload": f"3D 7-point operator {n}^3 with {'PERIODIC' if kind == 'periodic' else 'ZERO_GRADIENT'} boundaries (+0.01 I), fp32, CSR native recognised as a coded stencil",
+           "n": n, "nnz": nnz, "patterns": m.coded.patterns, "offsets": len(m.coded.offsets), "recognition_s": rec_s}
+    lib, sp = E.lib(), E.stream_ptr(dev)
+    for name, mat, nbytes in (("coded", m.coded, N + 2 * N * 4), ("csr", m, 8 * nnz + 4 * (N + 1) + 2 * N * 4)):
+        def call(i):
+            E.check(lib.phb200_spmv(mat.handle, E.ptr(xs[i % pairs]), E.ptr(ys[i % pairs]), 1, N, N, sp))
+        for i in range(pairs + 1):
+            call(i)
+        ms = min(ctx.timed(lambda: [call(i) for i in range(40)], 2)) / 40
+        y = xs[0]
+        zero = torch.zeros(1, dtype=torch.float32, device=dev)
+        mi = torch.full((1,), 2 ** 30, dtype=torch.int32, device=dev)
+        solver = pb.DeviceSolver(mat, pb.JacobiPreconditioner(m), E.CG, 0, 1)
+        solver.start(y, torch.zeros_like(y), zero, zero, mi)
+        solver.advance(10)
+        it_ms = min(ctx.timed(lambda: solver.advance(60), 2)) / 60
+        out[name] = {"spmv_ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6, "frac_of_peak": nbytes / ms / 1e6 / ctx.peak, "jacobi_cg_iterations_per_s": 1e3 / it_ms}
+        del solver
+    ya, yb = torch.empty_like(xs[0]), torch.empty_like(xs[0])
+    E.check(lib.phb200_spmv(m.coded.handle, E.ptr(xs[0]), E.ptr(ya), 1, N, N, sp))
+    E.check(lib.phb200_spmv(m.handle, E.ptr(xs[0]), E.ptr(yb), 1, N, N, sp))
+    out["products_bit_identical"] = bool(torch.equal(ya, yb))
+    del m, xs, ys, ya, yb, rowptr, col, val
+    pb.clear_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
 def guarded(name, fn, sink, ctx):
     """Extra blocks must never take the headline down: an error is recorded in the block instead (all ranks stay in step)."""
     try:
@@ -585,6 +653,8 @@ def run_ours(args):
             if world == 1:
                 guarded("cfg4_ilu_256", lambda: time_cfg4(ctx, 256, 30), configs, ctx)
                 guarded("cfg4_ilu_512", lambda: time_cfg4(ctx, 512, 20), configs, ctx)
+                guarded("coded_neumann_256", lambda: time_coded(ctx, 256, 'neumann'), configs, ctx)
+                guarded("coded_periodic_256", lambda: time_coded(ctx, 256, 'periodic'), configs, ctx)
         except Exception as exc:              # multi-rank: a failed block may leave the ranks out of step — stop here, keep the headline
             configs["aborted"] = repr(exc)[:300]
             emit()

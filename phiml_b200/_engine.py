@@ -142,8 +142,45 @@ def ptr(t) -> c_void_p:
 
 
 def stream_ptr(device=None) -> c_void_p:
+    """Current stream of ``device``.  The library allocates its scratch and launches on the CURRENT device, so the operands' device must be
+    the current one — the public entry points enter it (``on_operand_device``); anything else fails loudly here instead of running across GPUs."""
     import torch
+    if device is not None:
+        idx = torch.device(device).index
+        if idx is not None and idx != torch.cuda.current_device():
+            raise EngineError(f"operands live on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}; call inside torch.cuda.device({idx})")
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _device_of(obj):
+    import torch
+    if isinstance(obj, torch.Tensor):
+        return obj.device if obj.is_cuda else None
+    dev = getattr(obj, 'device', None)           # Matrix, preconditioners (through .matrix)
+    if isinstance(dev, torch.device) and dev.type == 'cuda':
+        return dev
+    m = getattr(obj, 'matrix', None)
+    return _device_of(m) if m is not None and m is not obj else None
+
+
+def on_operand_device(fn):
+    """Runs ``fn`` with the device of its first CUDA operand (tensor, Matrix or preconditioner) as the current device (ADVICE round 1:
+    scratch, set-up temporaries and launches must not land on another GPU when the caller's current device differs from the operands')."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            dev = _device_of(a)
+            if dev is not None:
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def require_cuda(*tensors):

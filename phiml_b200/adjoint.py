@@ -23,6 +23,7 @@ from . import solve as _solve
 from .sparse import Matrix, as_matrix
 
 
+@E.on_operand_device
 def transpose(native):
     """A^T the way the reference's backward pass presents it to ``Backend.linear_solve``: zero-copy re-labelling of the stored
     arrays (CSR <-> CSC), swapped coordinates for COO, mirrored offsets for a constant-coefficient stencil handle."""
@@ -61,6 +62,7 @@ def _entries(native) -> Tuple[str, torch.Tensor, torch.Tensor, Tuple[int, int]]:
     raise NotImplementedError("matrix gradients need a CSR or COO native (the reference decompresses CSR to COO, _optimize.py:800-801)")
 
 
+@E.on_operand_device
 def matrix_gradient(native, dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     """``dm[k] = -sum_b dy[b,row[k]] * x[b,col[k]]`` for every stored entry k of ``native`` (entry order of the native)."""
     kind, a, b, (rows, cols) = _entries(native)
@@ -81,6 +83,7 @@ def matrix_gradient(native, dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@E.on_operand_device
 def implicit_gradient_solve(method: str, native, x: torch.Tensor, dx: torch.Tensor, rtol, atol, max_iter, pre=None, matrix_adjoint: bool = False,
                             x0: Optional[torch.Tensor] = None):
     """Backward pass of ``x = solve(A, y)``.  Returns ``(SolveResult of A^T dy = dx, dm or None)``; ``.x`` of the result is dL/dy.

@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(kBlock) k_coded_spmv(CodedView cv, int64_t n, 
 template <typename T, int NA, class Epi>
 int launch_coded_vec(const CodedView& cv, int64_t n, const T* X, int64_t ldx, T* Y, int64_t ldy, int batch, const Epi& epi, cudaStream_t stream) {
     auto kernel = k_coded_spmv<T, true, NA, Epi>;
-    static int occ = 0;
+    static int occ_dev[kMaxDevices] = {};
+    int& occ = occ_dev[device_slot()];
     if (occ == 0) {
         int v = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, coded_smem<T>(32)) != cudaSuccess || v < 1) { cudaGetLastError(); v = 4; }

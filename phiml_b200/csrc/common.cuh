@@ -124,6 +124,15 @@ int l2_persist_mode();   // 0 off, 1 window on q, 2 window on r
         }                                                                                       \
     } while (0)
 
+// cudaFuncSetAttribute and occupancy queries are PER DEVICE: "done once" flags of the launchers are kept per device (a process may hold
+// operands on several GPUs; one process per GPU is the common case).
+constexpr int kMaxDevices = 32;
+inline int device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+    return d;
+}
+
 constexpr int kSMs = 148;          // B200
 constexpr int kBlock = 256;        // threads per CTA for all streaming kernels
 constexpr int kMaxDots = 4;        // fused dot products per kernel

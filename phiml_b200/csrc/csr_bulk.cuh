@@ -199,7 +199,8 @@ template <typename T, bool PRESCALE, int BT, class Epi>
 int launch_csr_bulk_t(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t ldy, const T* scale, int batch, const Epi& epi, cudaStream_t stream) {
     auto kernel = k_spmv_csr_bulk<T, PRESCALE, BT, Epi>;
     constexpr int smem = bulk_smem_bytes<T>();
-    static int occ = 0;
+    static int occ_dev[kMaxDevices] = {};
+    int& occ = occ_dev[device_slot()];
     if (occ == 0) {
         PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int v = 0;

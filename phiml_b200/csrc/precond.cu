@@ -639,7 +639,8 @@ static int star_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     a.cz = LOWER ? st.czm : st.czp;
     auto kernel = k_star_trsv<T, LOWER>;
     constexpr size_t smem = trsv_warp_smem<T>() * W;
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {};
+    bool& attr = attr_dev[device_slot()];
     if (!attr) {
         PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
@@ -686,7 +687,8 @@ static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     if (p->star_mode == 3) {
         auto kernel = k_star_trsv_flow<T, LOWER>;
         constexpr size_t smem = flow_smem_bytes<T>();
-        static bool attr = false;
+        static bool attr_dev[kMaxDevices] = {};
+        bool& attr = attr_dev[device_slot()];
         if (!attr) {
             PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = true;
@@ -696,7 +698,8 @@ static int scan_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     }
     auto kernel = k_star_trsv_scan<T, LOWER>;
     constexpr size_t smem = scan_smem_bytes<T>();
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {};
+    bool& attr = attr_dev[device_slot()];
     if (!attr) {
         PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
@@ -752,7 +755,8 @@ static int pipe_trsv_launch(phb200_precond* p, const T* B, T* X, int64_t batch, 
     a.cz = LOWER ? st.czm : st.czp;
     auto kernel = k_star_trsv_pipe<T, LOWER, R>;
     constexpr size_t smem = pipe_smem_bytes<T, R>();
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {};
+    bool& attr = attr_dev[device_slot()];
     if (!attr) {
         PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;

@@ -1302,7 +1302,8 @@ struct Run {
     int launch_tma_t(T* X, T* q, T cinv, const CgDq<T>& e) {
         auto kernel = k_star_cg_tma<T, PRE, CgDq<T>, UNIT>;
         constexpr int smem = star_tma_smem<T>();
-        static int occ = 0;
+        static int occ_dev[kMaxDevices] = {};
+        int& occ = occ_dev[device_slot()];
         if (occ == 0) {
             PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             int v = 0;
@@ -1414,7 +1415,8 @@ struct Run {
     int launch_tma_adaptive(T* X, T* q, int apply_x, const AdDots<T>& e) {
         auto kernel = k_star_cg_tma<T, 0, AdDots<T>, UNIT, 1>;
         constexpr int smem = star_tma_smem<T>();
-        static int occ = 0;
+        static int occ_dev[kMaxDevices] = {};
+        int& occ = occ_dev[device_slot()];
         if (occ == 0) {
             PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             int v = 0;
@@ -1656,7 +1658,8 @@ static bool resident_plan(const phb200_solver* s, int& cs, int& lpc, size_t& sme
 template <typename T, int PRE, bool RANK3, bool CLUSTER, int ALG = 0>
 static int launch_resident_t(const ResArgs& a, const ResCoef<T>& cf, size_t smem, cudaStream_t st) {
     auto kernel = k_cg_resident<T, PRE, RANK3, CLUSTER, ALG>;
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {};
+    bool& attr = attr_dev[device_slot()];
     if (!attr) {
         PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         attr = true;

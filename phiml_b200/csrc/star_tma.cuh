@@ -501,7 +501,8 @@ int launch_star_spmv_tma(const StarDesc& st, const T* X, int64_t ldx, T* Y, int6
     int xchunk;
     if (unit) {
         auto kernel = k_star_spmv_tma<T, Epi, true>;
-        static int occ = 0;
+        static int occ_dev[kMaxDevices] = {};
+        int& occ = occ_dev[device_slot()];
         if (occ == 0) {
             PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             int v = 0;
@@ -512,7 +513,8 @@ int launch_star_spmv_tma(const StarDesc& st, const T* X, int64_t ldx, T* Y, int6
         PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
     } else {
         auto kernel = k_star_spmv_tma<T, Epi, false>;
-        static int occ = 0;
+        static int occ_dev[kMaxDevices] = {};
+        int& occ = occ_dev[device_slot()];
         if (occ == 0) {
             PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             int v = 0;

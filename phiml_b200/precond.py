@@ -55,6 +55,7 @@ class _Handle:
 class JacobiPreconditioner(Preconditioner, _Handle):
     """M^-1 = diag(A)^-1; the split used by biCG-stab(1) is (L^-1, U^-1) = (D^-1, I)."""
 
+    @E.on_operand_device
     def __init__(self, matrix):
         _Handle.__init__(self)
         m = as_matrix(matrix)
@@ -68,12 +69,14 @@ class JacobiPreconditioner(Preconditioner, _Handle):
         E.check(E.lib().phb200_precond_jacobi(ctypes.byref(h), E.ptr(self.inv_diag), m.shape[0], E.dtype_code(m.dtype), 1 if src.kind == 'stencil' else 0))
         self._h = h
 
+    @E.on_operand_device
     def apply(self, vec):
         return vec * self.inv_diag
 
     apply_transposed = apply
     apply_inv_l = apply
 
+    @E.on_operand_device
     def apply_inv_u(self, vec):
         return vec
 
@@ -99,6 +102,7 @@ class IncompleteLU(Preconditioner, _Handle):
     ``'exact'`` — the fixed point itself (sequential-equivalent ILU(0), level-scheduled), reported as ``'ilu (exact)'``.
     ``safe``: ``divide_no_nan`` for the lower entries (rank-deficient matrices, _linalg.py:576)."""
 
+    @E.on_operand_device
     def __init__(self, matrix, sweeps=None, safe: bool = False, rank_deficiency=0):
         _Handle.__init__(self)
         m = plain_csr(as_matrix(matrix))
@@ -160,12 +164,14 @@ class IncompleteLU(Preconditioner, _Handle):
     def upper(self):
         return self.factors()[1]
 
+    @E.on_operand_device
     def apply(self, vec):
         vec = vec.to(self.matrix.dtype).contiguous()
         out = torch.empty_like(vec)
         E.check(E.lib().phb200_precond_apply(self._h, E.ptr(vec), E.ptr(out), vec.shape[0], vec.shape[1], E.stream_ptr(vec.device)))
         return out
 
+    @E.on_operand_device
     def apply_transposed(self, vec):
         """(LU)^-T vec = L^-T (U^-T vec), phiml/backend/_linalg.py:481-485: a lower solve with U^T followed by an upper solve with
         L^T; the transposed factors are built once on the device (phb200_csr_transpose)."""
@@ -178,10 +184,12 @@ class IncompleteLU(Preconditioner, _Handle):
         intermediate = solve_triangular_sparse(Ut, vec, lower=True, unit_diagonal=self.upper_unit_diagonal)
         return solve_triangular_sparse(Lt, intermediate, lower=False, unit_diagonal=self.lower_unit_diagonal)
 
+    @E.on_operand_device
     def apply_inv_l(self, vec):
         from .solve import solve_triangular_sparse
         return solve_triangular_sparse(self.factors()[0], vec, lower=True, unit_diagonal=True)
 
+    @E.on_operand_device
     def apply_inv_u(self, vec):
         from .solve import solve_triangular_sparse
         return solve_triangular_sparse(self.factors()[1], vec, lower=False, unit_diagonal=False)
@@ -217,6 +225,7 @@ class ClusterPreconditioner(Preconditioner, _Handle):
     ``cluster_count``, ``cluster_size (C,)``; ``from_matrix`` builds them like ``explicit_coarse`` / ``coarse_explicit_preconditioner_coo``
     (:769-799; the dense inverse is taken with NumPy on the host, as the reference does on every backend)."""
 
+    @E.on_operand_device
     def __init__(self, inv_coarse_matrix: torch.Tensor, clusters: torch.Tensor, cluster_count: int, cluster_size: torch.Tensor):
         _Handle.__init__(self)
         E.require_cuda(inv_coarse_matrix, clusters, cluster_size)
@@ -239,6 +248,7 @@ class ClusterPreconditioner(Preconditioner, _Handle):
         self._h = h
 
     @classmethod
+    @E.on_operand_device
     def from_matrix(cls, matrix, grid=None, cluster_count: int = 3 ** 6):
         import numpy as np
         m = plain_csr(as_matrix(matrix))
@@ -256,18 +266,22 @@ class ClusterPreconditioner(Preconditioner, _Handle):
         size = torch.bincount(cl, minlength=count).to(m.dtype)
         return cls(inv, clusters, count, size)
 
+    @E.on_operand_device
     def apply(self, vec):
         vec = vec.to(self.inv_coarse_matrix.dtype).contiguous()
         out = torch.empty_like(vec)
         E.check(E.lib().phb200_precond_apply(self._h, E.ptr(vec), E.ptr(out), vec.shape[0], vec.shape[1], E.stream_ptr(vec.device)))
         return out
 
+    @E.on_operand_device
     def apply_transposed(self, vec):
         raise NotImplementedError      # as the reference (_linalg.py:755-756)
 
+    @E.on_operand_device
     def apply_inv_l(self, vec):
         return vec
 
+    @E.on_operand_device
     def apply_inv_u(self, vec):
         return self.apply(vec)
 
@@ -275,6 +289,7 @@ class ClusterPreconditioner(Preconditioner, _Handle):
         return f"cluster ({self.cluster_count})"
 
 
+@E.on_operand_device
 def compute_preconditioner(method: Optional[str], matrix, rank_deficiency=0, **_ignored) -> Optional[Preconditioner]:
     """'jacobi' | 'ilu' | 'ilu-exact' | 'cluster' | 'auto' | None on a native matrix (torch sparse tensor or Matrix).  'auto' resolves to 'ilu'
     as in the reference for backends with sparse triangular solves (phiml/math/_optimize.py:838-846); 'ilu' builds the

@@ -283,6 +283,7 @@ def _run_slab(code, poly_order, matrix, y, x0, rtol, atol, max_iter, pre):
 # Backend.linear_solve and friends
 # ----------------------------------------------------------------------------------------------------------------------
 
+@E.on_operand_device
 def conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None) -> SolveResult:
     assert matrix_offset is None, "matrix_offset is not supported"
     matrix, y, x0, rtol, atol, max_iter = _prepare(lin, y, x0, rtol, atol, max_iter)
@@ -292,6 +293,7 @@ def conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset
     return _run(E.CG_TORCH, 0, method_string('CG', None, False), matrix, y, x0, rtol, atol, max_iter, None)
 
 
+@E.on_operand_device
 def conjugate_gradient_adaptive(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None) -> SolveResult:
     assert matrix_offset is None, "matrix_offset is not supported"
     if pre:
@@ -303,6 +305,7 @@ def conjugate_gradient_adaptive(lin, y, x0, rtol, atol, max_iter, pre=None, matr
     return _run(E.CG_ADAPTIVE_TORCH, 0, method_string('CG-adaptive', None, False), matrix, y, x0, rtol, atol, max_iter, None)
 
 
+@E.on_operand_device
 def bi_conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None, poly_order=2) -> SolveResult:
     assert matrix_offset is None, "matrix_offset is not supported"
     if poly_order == 0:
@@ -315,6 +318,7 @@ def bi_conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None, matrix_off
     return _run(E.BICGSTAB, poly_order, name, matrix, y, x0, rtol, atol, max_iter, pre)
 
 
+@E.on_operand_device
 def generic_conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None) -> SolveResult:
     """The generic loop ``_linalg.cg`` regardless of the torch fast-path rules (what the NumPy backend runs)."""
     matrix, y, x0, rtol, atol, max_iter = _prepare(lin, y, x0, rtol, atol, max_iter)
@@ -322,11 +326,13 @@ def generic_conjugate_gradient(lin, y, x0, rtol, atol, max_iter, pre=None) -> So
     return _run(E.CG, 0, f"Φ-ML CG ({BACKEND_NAME}) {_pre_str(pre)}", matrix, y, x0, rtol, atol, max_iter, pre)
 
 
+@E.on_operand_device
 def generic_conjugate_gradient_adaptive(lin, y, x0, rtol, atol, max_iter) -> SolveResult:
     matrix, y, x0, rtol, atol, max_iter = _prepare(lin, y, x0, rtol, atol, max_iter)
     return _run(E.CG_ADAPTIVE, 0, f"Φ-ML CG-adaptive ({BACKEND_NAME}) ", matrix, y, x0, rtol, atol, max_iter, None)
 
 
+@E.on_operand_device
 def linear_solve(method: str, lin, y, x0, rtol, atol, max_iter, pre=None, matrix_offset=None) -> SolveResult:
     """Method-string dispatch of Backend.linear_solve."""
     if method == 'auto':
@@ -352,6 +358,7 @@ def linear_solve(method: str, lin, y, x0, rtol, atol, max_iter, pre=None, matrix
 # products
 # ----------------------------------------------------------------------------------------------------------------------
 
+@E.on_operand_device
 def mul_matrix_batched_vector(A, b: torch.Tensor) -> torch.Tensor:
     """(A b^T)^T for b of shape (batch, N)."""
     return as_matrix(A).matvec(b)
@@ -360,6 +367,7 @@ def mul_matrix_batched_vector(A, b: torch.Tensor) -> torch.Tensor:
 linear = mul_matrix_batched_vector
 
 
+@E.on_operand_device
 def mul_csr_dense(column_indices, row_pointers, values, shape, dense) -> torch.Tensor:
     """
     column_indices (batch, nnz), row_pointers (batch, rows+1), values (batch, nnz, channels),
@@ -382,6 +390,7 @@ def mul_csr_dense(column_indices, row_pointers, values, shape, dense) -> torch.T
     return out
 
 
+@E.on_operand_device
 def mul_coo_dense(indices, values, shape, dense) -> torch.Tensor:
     """indices (batch, nnz, 2), values (batch, nnz, channels), dense (batch, cols, channels, dense_cols)."""
     values, dense = torch.as_tensor(values), torch.as_tensor(dense)
@@ -424,6 +433,7 @@ class _Plan:
         self._h = None
 
 
+@E.on_operand_device
 def solve_triangular_sparse(matrix, rhs: torch.Tensor, lower: bool, unit_diagonal: bool) -> torch.Tensor:
     """X = T^-1 B for a sparse triangular native T and B of shape (batch, N); the level schedule is cached on the matrix."""
     m = plain_csr(as_matrix(matrix, detect_stencil=False))
@@ -442,6 +452,7 @@ def solve_triangular_sparse(matrix, rhs: torch.Tensor, lower: bool, unit_diagona
     return x
 
 
+@E.on_operand_device
 def solve_triangular(matrix, rhs, lower: bool, unit_diagonal: bool):
     if isinstance(matrix, Matrix) or (isinstance(matrix, torch.Tensor) and matrix.layout != torch.strided):
         return solve_triangular_sparse(matrix, rhs, lower, unit_diagonal)

@@ -80,6 +80,7 @@ class Matrix:
         return m
 
     # --- stencil recognition ---
+    @E.on_operand_device
     def detect_stencil(self, grid: Optional[Sequence[int]] = None) -> Optional['Matrix']:
         """Returns the stencil twin if every row matches bit for bit, else None.  ``grid`` defaults to an inference
         from the neighbour offsets of a few probe rows (nearest-neighbour stencils on C-ordered grids)."""
@@ -103,6 +104,7 @@ class Matrix:
         self.stencil = st
         return st
 
+    @E.on_operand_device
     def detect_coded(self) -> Optional['Matrix']:
         """Pattern-coded twin (csrc/coded.cuh) of a CSR matrix that is NOT a constant-coefficient ZERO-boundary stencil but still has few
         distinct rows — ZERO_GRADIENT / PERIODIC boundaries, masks, piecewise-constant coefficients: one code byte per row instead of the
@@ -136,6 +138,7 @@ class Matrix:
         E.check(E.lib().phb200_matrix_info(self._h, None, None, None, ctypes.byref(n), None))
         return int(n.value)
 
+    @E.on_operand_device
     def to_csr(self) -> 'Matrix':
         """Stencil -> canonical CSR assembled on the device (byte-identical to the reference's compress())."""
         assert self.kind == 'stencil'
@@ -148,6 +151,7 @@ class Matrix:
         return Matrix.csr(rowptr, col, val, self.shape)
 
     # --- product ---
+    @E.on_operand_device
     def matvec(self, x: torch.Tensor, use_stencil=True) -> torch.Tensor:
         """(batch, cols) -> (batch, rows)"""
         E.require_cuda(x)
@@ -210,6 +214,7 @@ def clear_cache():
     _CACHE.clear()
 
 
+@E.on_operand_device
 def as_matrix(native, detect_stencil=True, grid=None) -> Matrix:
     """torch sparse CSR / CSC / COO tensor (or Matrix) -> Matrix.  COO is converted to CSR once (sorted, duplicates summed)."""
     if isinstance(native, Matrix):
@@ -274,6 +279,7 @@ def _detect_ignoring_stored_zeros(m: Matrix, grid=None):
     return st
 
 
+@E.on_operand_device
 def plain_csr(m: Matrix) -> Matrix:
     """CSC-native (arrays of A^T) -> CSR of A, via one transposition on the device (set-up cost, cached on the matrix)."""
     if m.kind != 'csc':

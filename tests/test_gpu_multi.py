@@ -80,3 +80,30 @@ def test_bench_multi_gpu_times_a_loop_with_a_collective():
     assert line['n_gpus'] == 2 and line['scaling'] == 'strong' and line['value'] > 0
     assert line['headline_detail']['collectives_per_iteration']['all_reduce_in_kernel'] == 2
     assert line['e2e']['iterations_per_solve'] in range(551, 556)      # the reference's 553 +- 2
+
+
+def test_operands_on_a_non_current_device():
+    """scratch, set-up temporaries and launches follow the operands' device, not the caller's current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip(f"needs 2 GPUs, the box has {torch.cuda.device_count()}")
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import phiml_b200 as pb
+    from _util import oracle_matrix
+    csr = oracle_matrix('poisson', (24, 20, 28), 'float32')
+    y = np.random.default_rng(0).standard_normal((2, csr.shape[0])).astype(np.float32)
+    rt, at, mi = np.float32([1e-5, 1e-5]), np.float32([0, 0]), np.array([[1000, 1000]])
+    results = []
+    assert torch.cuda.current_device() == 0
+    for dev in ('cuda:0', 'cuda:1'):
+        nat = torch.sparse_csr_tensor(torch.as_tensor(csr.indptr, device=dev), torch.as_tensor(csr.indices, device=dev), torch.as_tensor(csr.data, device=dev), csr.shape)
+        m = pb.as_matrix(nat)
+        assert m.stencil is not None
+        for pre in (pb.JacobiPreconditioner(m), pb.IncompleteLU(m)):
+            yd = torch.as_tensor(y, device=dev)
+            res = pb.generic_conjugate_gradient(m, yd, torch.zeros_like(yd), rt, at, mi, pre)
+            assert res.x.device == torch.device(dev) and bool(res.converged.all())
+            results.append((res.iterations.cpu(), res.x.cpu()))
+        assert torch.cuda.current_device() == 0, "the caller's current device must be restored"
+    for a, b in zip(results[:2], results[2:]):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
