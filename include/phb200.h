@@ -100,6 +100,15 @@ int phb200_stencil_from_csr(phb200_matrix** out, const phb200_matrix* csr, int r
 int phb200_stencil_nnz(const phb200_matrix* stencil, int64_t* nnz);
 int phb200_stencil_to_csr(const phb200_matrix* stencil, int32_t* rowptr, int32_t* col, void* val, void* stream);
 
+/* General device assembly of a traced operator (phiml/math/_lin_trace.py:750-807 + SparseCoordinateTensor.compress, _sparse.py:347-390): a
+ * ShiftLinTracer is `nshifts` (<= 16) shifts (rank ints each, source = output + shift, wrapped periodically) with ONE value per grid cell and
+ * shift — values: device array [nshifts][N] in C order, N = prod(grid).  Entries with value 0 are dropped (np.nonzero, :774), rows are ordered by
+ * column: the result is byte-identical to the reference's compress_rows() for variable coefficients, PERIODIC wrap and ZERO boundaries alike.
+ * phb200_shift_count fills rowptr (N + 1) and *nnz (synchronises stream; PHB200_ERR_ARG if nnz does not fit int32), phb200_shift_fill writes col / val
+ * (nnz each; PHB200_ERR_UNSUPPORTED if two shifts wrap onto one column — the reference asserts there, _sparse.py:378). */
+int phb200_shift_count(int rank, const int64_t* grid, int nshifts, const int32_t* shifts, const void* values, int dtype, int32_t* rowptr, int64_t* nnz, void* stream);
+int phb200_shift_fill(int rank, const int64_t* grid, int nshifts, const int32_t* shifts, const void* values, int dtype, const int32_t* rowptr, int32_t* col, void* val, void* stream);
+
 /* Pattern-coded form of a CSR matrix whose rows fall into few distinct (offset, value) patterns — what matrix_from_function emits for
  * stencils with ZERO_GRADIENT / PERIODIC boundaries, masks or piecewise-constant coefficients (phiml/math/_lin_trace.py:750-807: one
  * value array per shift, wrapped columns).  The device recognises <= 16 distinct flat offsets (col - row) and <= 256 distinct rows, verifies

@@ -77,6 +77,29 @@ def stencil_coo(grid: Sequence[int], shifts, dtype=np.float64, periodic: bool = 
     return np.concatenate(idx_blocks).astype(np.int64), np.concatenate(val_blocks)
 
 
+def shift_values_coo(grid: Sequence[int], offsets, values):
+    """
+    General form of phiml/math/_lin_trace.py:750-807 (tracer_to_coo) for NumPy-backed shift values: ``values[k]`` is the full-grid value array of
+    shift ``offsets[k]``; per shift the cells with a non-zero value (``np.nonzero(np.sum(abs(v), 0))``, :773-774) are kept in C order and the source
+    index wraps periodically (``(component + shift) % size``, :775).  Covers variable coefficients and PERIODIC boundaries.
+    """
+    grid = tuple(int(g) for g in grid)
+    rank = len(grid)
+    idx_blocks, val_blocks = [], []
+    for shift, v in zip(offsets, values):
+        v = np.asarray(v).reshape(grid)
+        out_idx = np.nonzero(np.abs(v))
+        src_idx = [(component + int(shift[d])) % grid[d] for d, component in enumerate(out_idx)]
+        idx_blocks.append(np.stack(list(src_idx) + list(out_idx), axis=1))
+        val_blocks.append(v[out_idx])
+    return np.concatenate(idx_blocks).astype(np.int64).reshape(-1, 2 * rank), np.concatenate(val_blocks)
+
+
+def shift_values_csr(grid, offsets, values) -> sp.csr_matrix:
+    idx, val = shift_values_coo(grid, offsets, values)
+    return coo_to_csr(grid, idx, val)
+
+
 def coo_to_csr(grid: Sequence[int], indices: np.ndarray, values: np.ndarray) -> sp.csr_matrix:
     """Canonical CSR (sorted columns, int32) through the same SciPy permutation trick the reference uses."""
     grid = tuple(int(g) for g in grid)

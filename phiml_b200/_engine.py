@@ -28,6 +28,8 @@ SIGNATURES = {
     'phb200_matrix_csr': (c_int, [_PP, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int]),
     'phb200_matrix_stencil': (c_int, [_PP, c_int, POINTER(c_int64), c_int, POINTER(c_int32), POINTER(c_double), c_int]),
     'phb200_stencil_from_csr': (c_int, [_PP, _P, c_int, POINTER(c_int64), _P]),
+    'phb200_shift_count': (c_int, [c_int, POINTER(c_int64), c_int, POINTER(c_int32), _P, c_int, _P, POINTER(c_int64), _P]),
+    'phb200_shift_fill': (c_int, [c_int, POINTER(c_int64), c_int, POINTER(c_int32), _P, c_int, _P, _P, _P, _P]),
     'phb200_coded_from_csr': (c_int, [_PP, _P, _P]),
     'phb200_coded_info': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
     'phb200_stencil_nnz': (c_int, [_P, POINTER(c_int64)]),

@@ -26,7 +26,9 @@ MAX_POINTS = 16
 
 
 def analyse_tracer(tracer, sparsify, separate_independent) -> Optional[dict]:
-    """Returns the stencil description of a constant-coefficient ZERO-boundary ``ShiftLinTracer`` or None."""
+    """Returns the description of a ``ShiftLinTracer`` the device can assemble, or None.  Constant coefficients with ZERO boundaries give a
+    stencil description (``offsets`` / ``coeffs``); anything else with one value per cell and shift — variable coefficients, PERIODIC wrap,
+    non-zero edge values — gives the general description (``general=True``, ``values``: one full-grid array per shift)."""
     from phiml.backend import NUMPY
     from phiml.math._lin_trace import ShiftLinTracer, Shift, matrix_dims_for_tracer, pattern_dim_names
     from phiml.math._shape import batch, merge_shapes, non_batch
@@ -47,10 +49,12 @@ def analyse_tracer(tracer, sparsify, separate_independent) -> Optional[dict]:
         return None
     if not merge_shapes(*tracer.val.values()).without(out_shape).is_empty:
         return None          # batched values
-    if len(tracer.val) > MAX_POINTS or any(v.default_backend is not NUMPY for v in tracer.val.values()):
+    if any(v.default_backend is not NUMPY for v in tracer.val.values()):
         return None
     grid = tuple(int(s) for s in out_shape.sizes)
     offsets, coeffs = [], []
+    all_offsets, all_values = [], []
+    constant = True          # constant coefficients, ZERO boundaries (the stencil form)
     dtype = None
     for shift_, shift_val in tracer.val.items():
         assert isinstance(shift_, Shift)
@@ -60,31 +64,39 @@ def analyse_tracer(tracer, sparsify, separate_independent) -> Optional[dict]:
         v = np.asarray(shift_val.native([*out_shape]))
         if v.shape != grid or v.dtype.kind != 'f':
             return None
-        dtype = v.dtype if dtype is None else np.promote_types(dtype, v.dtype)
+        if dtype is not None and v.dtype != dtype:
+            return None
+        dtype = v.dtype
+        if not np.any(v):
+            continue          # all-zero shifts leave no entries (np.nonzero, _lin_trace.py:774-776); ZERO_GRADIENT traces carry many of them
+        all_offsets.append(off)
+        all_values.append(v)
+        if len(all_offsets) > MAX_POINTS:
+            return None
+        if not constant:
+            continue
         box = tuple(slice(max(0, -o), n - max(0, o)) for o, n in zip(off, grid))
         inner = v[box]
         if inner.size == 0:
-            if np.any(v):
-                return None
+            constant = False
             continue
         c = inner.flat[0]
-        if not np.all(inner == c):
-            return None      # variable coefficients
         nz = int(np.count_nonzero(v))
-        if c == 0:
-            if nz:
-                return None
-            continue          # the reference drops all-zero shifts as well (np.nonzero, _lin_trace.py:774-776)
-        if nz != inner.size:
-            return None      # non-zero values at wrapped positions: periodic / other boundaries
+        if not np.all(inner == c) or (c == 0 and nz) or (c != 0 and nz != inner.size):
+            constant = False  # variable coefficients / non-zero values at wrapped positions (periodic and other boundaries)
+            continue
         offsets.append(off)
         coeffs.append(float(c))
-    if not offsets or dtype not in (np.float32, np.float64):
+    if dtype not in (np.float32, np.float64):
         return None
-    if any(v.dtype != dtype for v in (np.asarray(t.native([*out_shape])) for t in tracer.val.values())):
+    common = dict(grid=grid, dtype=np.dtype(dtype), out_shape=out_shape, src_shape=src_shape, m_rank=out_shape.volume - tracer.min_rank_deficiency())
+    if not all_offsets:
         return None
-    return dict(grid=grid, offsets=offsets, coeffs=coeffs, dtype=np.dtype(dtype), out_shape=out_shape, src_shape=src_shape,
-                m_rank=out_shape.volume - tracer.min_rank_deficiency())
+    if constant:
+        return dict(common, general=False, offsets=offsets, coeffs=coeffs)
+    if any(abs(o) >= n for off in all_offsets for o, n in zip(off, grid)):
+        return None           # a shift as long as the grid wraps onto its own column
+    return dict(common, general=True, offsets=all_offsets, values=all_values)
 
 
 def cuda_assemble(grid, offsets, coeffs, dtype: np.dtype, device=None):
@@ -97,6 +109,39 @@ def cuda_assemble(grid, offsets, coeffs, dtype: np.dtype, device=None):
         return None          # int32 CSR (the reference's native) cannot hold it
     csr = st.to_csr()
     return csr.rowptr, csr.col, csr.values
+
+
+def cuda_assemble_general(grid, offsets, values, dtype: np.dtype, device=None):
+    """(rowptr int32, col int32, values) on the device for a ``ShiftLinTracer`` with one value per cell and shift (variable coefficients, PERIODIC wrap):
+    the per-shift arrays are uploaded once ((shifts, N) values) and ``phb200_shift_count`` / ``phb200_shift_fill`` do what ``tracer_to_coo`` +
+    ``compress_rows()`` do on the host — drop the zeros, wrap the columns, order every row by column — byte-identical, without any array of size nnz
+    on the host.  None if no int32 CSR exists (the caller then falls back to the reference)."""
+    import ctypes
+    import torch
+    from . import _engine as E
+    dev = torch.device(device if device is not None else 'cuda')
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    n = int(np.prod(grid))
+    rank = len(grid)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    with torch.cuda.device(dev):
+        vals = torch.empty((len(offsets), n), dtype=tdt, device=dev)
+        for k, v in enumerate(values):                      # shift by shift: no second full copy on the host
+            vals[k].copy_(torch.as_tensor(np.ascontiguousarray(v).reshape(-1)))
+        g = (ctypes.c_int64 * rank)(*[int(s) for s in grid])
+        flat = [int(o) for off in offsets for o in off]
+        sh = (ctypes.c_int32 * len(flat))(*flat)
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        nnz = ctypes.c_int64()
+        try:
+            E.check(E.lib().phb200_shift_count(rank, g, len(offsets), sh, E.ptr(vals), E.dtype_code(tdt), E.ptr(rowptr), ctypes.byref(nnz), E.stream_ptr(dev)))
+            col = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+            out = torch.empty(nnz.value, dtype=tdt, device=dev)
+            E.check(E.lib().phb200_shift_fill(rank, g, len(offsets), sh, E.ptr(vals), E.dtype_code(tdt), E.ptr(rowptr), E.ptr(col), E.ptr(out), E.stream_ptr(dev)))
+        except (ValueError, NotImplementedError):
+            return None
+    return rowptr, col, out
 
 
 def build_compressed(info: dict, natives):
@@ -141,10 +186,10 @@ def owner_of(values):
     return m if (own.data_ptr() == values.data_ptr() and own._version == values._version and own.numel() == values.numel() and own.dtype == values.dtype) else None
 
 
-STATS = {'device_assemblies': 0, 'fallbacks': 0}
+STATS = {'device_assemblies': 0, 'general_assemblies': 0, 'fallbacks': 0}
 
 
-def make_tracer_to_coo(original: Callable, eligible: Callable[[], bool], assemble: Callable = cuda_assemble):
+def make_tracer_to_coo(original: Callable, eligible: Callable[[], bool], assemble: Callable = cuda_assemble, assemble_general: Callable = cuda_assemble_general):
     """Wrapper for ``phiml.math._lin_trace.tracer_to_coo``.  ``eligible()`` says whether the matrix is wanted on the CUDA torch backend
     right now (the wrapped function is not told the target backend); ``assemble`` is injectable so that the CPU tests can check the
     PhiML-side structure against the reference's own matrix with arrays from the oracle."""
@@ -153,9 +198,12 @@ def make_tracer_to_coo(original: Callable, eligible: Callable[[], bool], assembl
         if eligible():
             info = analyse_tracer(tracer, sparsify, separate_independent)
         if info is not None:
-            natives = assemble(info['grid'], info['offsets'], info['coeffs'], info['dtype'])
+            if info['general']:
+                natives = assemble_general(info['grid'], info['offsets'], info['values'], info['dtype'])
+            else:
+                natives = assemble(info['grid'], info['offsets'], info['coeffs'], info['dtype'])
             if natives is not None:
-                STATS['device_assemblies'] += 1
+                STATS['general_assemblies' if info['general'] else 'device_assemblies'] += 1
                 return build_compressed(info, natives), tracer._bias
         STATS['fallbacks'] += 1
         return original(tracer, sparsify, separate_independent)

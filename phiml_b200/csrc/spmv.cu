@@ -257,6 +257,64 @@ __global__ void __launch_bounds__(kBlock) k_stencil_fill(StencilDesc st, int64_t
     }
 }
 
+// ---------------------------------------------------------------------------------------------- shift tracer -> CSR
+// General form of the device assembly: a ShiftLinTracer holds one full-grid value array per shift (phiml/math/_lin_trace.py:57-99);
+// tracer_to_coo (:750-807) keeps the entries whose value is non-zero and wraps the shifted index periodically ((idx + shift) % size, :775),
+// SparseCoordinateTensor.compress (phiml/math/_sparse.py:347-390) orders every row by column through SciPy.  Here: one thread per row counts its
+// non-zero shifts, an exclusive scan gives the row pointers, the fill pass gathers (wrapped column, value) per non-zero shift and sorts the <= 16
+// pairs of the row by column.  Two shifts that wrap onto the same column (grids smaller than the stencil) set the failure flag — the reference
+// asserts in that case.
+struct ShiftSet {
+    int rank, nshifts;
+    int64_t dims[3];
+    int off[kMaxStencil][3];
+};
+
+__global__ void __launch_bounds__(kBlock) k_narrow_i64(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) out[i] = (int32_t)in[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_shift_count(ShiftSet sh, int64_t n, const T* __restrict__ vals, int32_t* __restrict__ counts) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i <= n; i += (int64_t)gridDim.x * kBlock) {
+        int c = 0;
+        if (i < n)
+            for (int s = 0; s < sh.nshifts; ++s) c += vals[(int64_t)s * n + i] != T(0);
+        counts[i] = c;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_shift_fill(ShiftSet sh, int64_t n, const T* __restrict__ vals, const int32_t* __restrict__ rowptr,
+                                                       int32_t* __restrict__ col, T* __restrict__ val, int* fail) {
+    const int64_t ny = sh.dims[1], nz = sh.dims[2], nx = sh.dims[0];
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+        int32_t c[kMaxStencil];
+        T v[kMaxStencil];
+        int m = 0;
+        for (int s = 0; s < sh.nshifts; ++s) {
+            const T a = vals[(int64_t)s * n + i];
+            if (a == T(0)) continue;
+            int64_t jx = (ix + sh.off[s][0]) % nx, jy = (iy + sh.off[s][1]) % ny, jz = (iz + sh.off[s][2]) % nz;
+            if (jx < 0) jx += nx;
+            if (jy < 0) jy += ny;
+            if (jz < 0) jz += nz;
+            const int32_t cc = (int32_t)((jx * ny + jy) * nz + jz);
+            int p = m++;
+            while (p > 0 && c[p - 1] > cc) { c[p] = c[p - 1]; v[p] = v[p - 1]; --p; }     // insertion sort by column
+            c[p] = cc;
+            v[p] = a;
+        }
+        const int k0 = rowptr[i];
+        for (int p = 0; p < m; ++p) {
+            if (p > 0 && c[p] == c[p - 1]) *fail = 1;
+            col[k0 + p] = c[p];
+            val[k0 + p] = v[p];
+        }
+    }
+}
+
 static int make_stencil(phb200_matrix** out, int rank, const int64_t* grid, int npts, const int32_t* offsets, const double* coeffs, int dtype) {
     PHB_ARG(out && grid && offsets && coeffs, "null argument");
     PHB_ARG(rank >= 1 && rank <= 3, "stencil rank must be 1..3, got %d", rank);
@@ -591,6 +649,81 @@ int phb200_stencil_to_csr(const phb200_matrix* m, int32_t* rowptr, int32_t* col,
     else PHB_LAUNCH(k_stencil_fill<double>, gridx, kBlock, 0, stream, m->st, n, rowptr, col, (double*)val);
     PHB_CUDA(cudaFreeAsync(tmp, stream));
     PHB_CUDA(cudaFreeAsync(counts, stream));
+    return PHB200_OK;
+}
+
+static int shift_set(ShiftSet& sh, int rank, const int64_t* grid, int nshifts, const int32_t* shifts, int64_t* n_out) {
+    PHB_ARG(grid && shifts, "null argument");
+    PHB_ARG(rank >= 1 && rank <= 3, "rank must be 1..3, got %d", rank);
+    PHB_ARG(nshifts >= 1 && nshifts <= kMaxStencil, "1..%d shifts, got %d", kMaxStencil, nshifts);
+    memset(&sh, 0, sizeof(sh));
+    sh.rank = rank;
+    sh.nshifts = nshifts;
+    int64_t n = 1;
+    for (int d = 0; d < 3; ++d) sh.dims[d] = 1;
+    for (int d = 0; d < rank; ++d) {
+        PHB_ARG(grid[d] >= 1, "grid size must be positive");
+        sh.dims[3 - rank + d] = grid[d];
+        n *= grid[d];
+    }
+    for (int s = 0; s < nshifts; ++s)
+        for (int d = 0; d < rank; ++d) sh.off[s][3 - rank + d] = shifts[s * rank + d];
+    PHB_ARG(n < (1ll << 31) - 1, "CSR natives hold at most 2^31-1 rows (int32)");
+    *n_out = n;
+    return PHB200_OK;
+}
+
+int phb200_shift_count(int rank, const int64_t* grid, int nshifts, const int32_t* shifts, const void* values, int dtype, int32_t* rowptr, int64_t* nnz, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(values && rowptr && nnz, "null argument");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    ShiftSet sh;
+    int64_t n = 0;
+    PHB_TRY(shift_set(sh, rank, grid, nshifts, shifts, &n));
+    const unsigned gridx = (unsigned)grid_x((n + kBlock) / kBlock, 1);
+    int32_t* counts = nullptr;
+    PHB_CUDA(phb_malloc_async(&counts, (n + 1) * sizeof(int32_t), stream));
+    if (dtype == PHB200_F32) PHB_LAUNCH(k_shift_count<float>, gridx, kBlock, 0, stream, sh, n, (const float*)values, counts);
+    else PHB_LAUNCH(k_shift_count<double>, gridx, kBlock, 0, stream, sh, n, (const double*)values, counts);
+    // the total may exceed int32 (then no CSR native exists): scan in 64 bits, narrow afterwards
+    int64_t* wide = nullptr;
+    PHB_CUDA(phb_malloc_async(&wide, (n + 1) * sizeof(int64_t), stream));
+    size_t tmp_bytes = 0;
+    PHB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, wide, (int)(n + 1), stream));
+    void* tmp = nullptr;
+    PHB_CUDA(phb_malloc_async(&tmp, tmp_bytes, stream));
+    PHB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, wide, (int)(n + 1), stream));
+    g_launches.fetch_add(2);
+    int64_t total = 0;
+    PHB_CUDA(cudaMemcpyAsync(&total, wide + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    *nnz = total;
+    if (total < (1ll << 31)) PHB_LAUNCH(k_narrow_i64, gridx, kBlock, 0, stream, wide, rowptr, n + 1);
+    PHB_CUDA(cudaFreeAsync(tmp, stream));
+    PHB_CUDA(cudaFreeAsync(wide, stream));
+    PHB_CUDA(cudaFreeAsync(counts, stream));
+    PHB_ARG(total < (1ll << 31), "CSR with %lld entries does not fit int32 indices", (long long)total);
+    return PHB200_OK;
+}
+
+int phb200_shift_fill(int rank, const int64_t* grid, int nshifts, const int32_t* shifts, const void* values, int dtype, const int32_t* rowptr, int32_t* col, void* val, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(values && rowptr && col && val, "null argument");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    ShiftSet sh;
+    int64_t n = 0;
+    PHB_TRY(shift_set(sh, rank, grid, nshifts, shifts, &n));
+    const unsigned gridx = (unsigned)grid_x((n + kBlock - 1) / kBlock, 1);
+    int* d_fail = nullptr;
+    PHB_CUDA(phb_malloc_async(&d_fail, sizeof(int), stream));
+    PHB_CUDA(cudaMemsetAsync(d_fail, 0, sizeof(int), stream));
+    if (dtype == PHB200_F32) PHB_LAUNCH(k_shift_fill<float>, gridx, kBlock, 0, stream, sh, n, (const float*)values, rowptr, col, (float*)val, d_fail);
+    else PHB_LAUNCH(k_shift_fill<double>, gridx, kBlock, 0, stream, sh, n, (const double*)values, rowptr, col, (double*)val, d_fail);
+    int h = 0;
+    PHB_CUDA(cudaMemcpyAsync(&h, d_fail, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PHB_CUDA(cudaStreamSynchronize(stream));
+    PHB_CUDA(cudaFreeAsync(d_fail, stream));
+    if (h) { set_error("two shifts wrap onto the same column (grid smaller than the stencil)"); return PHB200_ERR_UNSUPPORTED; }
     return PHB200_OK;
 }
 

@@ -169,17 +169,19 @@ def test_backward_pass_reaches_the_boundary_with_the_transposed_native(phiml_env
 
 def test_tracer_bridge_builds_the_reference_matrix(phiml_env):
     """the bridge from ShiftLinTracer.val to the assembler returns the SAME CompressedSparseMatrix as the reference's
-    tracer_to_coo + compress_rows (dims, int32 indices / pointers, values, rank) for constant-coefficient ZERO-boundary operators and
-    leaves everything else (periodic, zero-gradient = variable diagonal) to the reference.  Arrays come from the oracle HERE (no GPU);
-    on the device they come from phb200_stencil_to_csr, pinned byte for byte by test_device_assembly_bit_exact."""
+    tracer_to_coo + compress_rows (dims, int32 indices / pointers, values, rank) for constant-coefficient ZERO-boundary operators (stencil
+    form) AND for shift tracers with one value per cell — PERIODIC wrap, ZERO_GRADIENT, variable coefficients (general form).  Arrays come from the oracle HERE (no GPU); on the device they come from
+    phb200_stencil_to_csr / phb200_shift_count + phb200_shift_fill, pinned byte for byte by test_device_assembly_bit_exact and
+    tests/test_gpu_coded.py::test_general_device_assembly_is_byte_identical."""
     import torch
     from phiml import math
     from phiml.math import spatial, channel, extrapolation
     from phiml.math._lin_trace import matrix_from_function
     import phiml.math._lin_trace as lt
     from phiml_b200 import assembly
-    from oracle.assemble import stencil_csr
+    from oracle.assemble import stencil_csr, shift_values_csr
     from _util import ADVDIFF
+    from _boundary_ops import varcoef, periodic_advdiff
 
     def neg_laplace(x): return -math.laplace(x, padding=extrapolation.ZERO)
     def periodic(x): return -math.laplace(x, padding=extrapolation.PERIODIC)
@@ -195,20 +197,27 @@ def test_tracer_bridge_builds_the_reference_matrix(phiml_env):
         csr = stencil_csr(grid, list(zip(offsets, coeffs)), dtype.type)
         return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
 
+    def oracle_assemble_general(grid, offsets, values, dtype):
+        csr = shift_values_csr(grid, offsets, values)
+        assert csr.data.dtype == dtype
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
     bridged = lt.tracer_to_coo            # the plug-in's wrapper (not eligible here: no GPU)
     original = phiml_env[0]._INSTALLED['original_t2c']
     try:
         for prec in (32, 64):
-            for f, shape, expect in ((neg_laplace, dict(x=6, y=5), True), (neg_laplace, dict(x=5, y=4, z=8), True), (advdiff, dict(x=6, y=5, z=4), True),
-                                     (neg_laplace, dict(x=9), True), (periodic, dict(x=6, y=5), False), (zero_gradient, dict(x=6, y=5), False)):
+            for f, shape, expect in ((neg_laplace, dict(x=6, y=5), 'stencil'), (neg_laplace, dict(x=5, y=4, z=8), 'stencil'), (advdiff, dict(x=6, y=5, z=4), 'stencil'),
+                                     (neg_laplace, dict(x=9), 'stencil'), (periodic, dict(x=6, y=5), 'general'), (periodic, dict(x=4, y=5, z=6), 'general'),
+                                     (varcoef, dict(x=9, y=8, z=12), 'general'), (periodic_advdiff, dict(x=8, y=6, z=12), 'general'), (zero_gradient, dict(x=6, y=5), 'general'), (zero_gradient, dict(x=5, y=6, z=4), 'general')):
                 with math.precision(prec):
                     x0 = math.zeros(spatial(**shape))
                     lt.tracer_to_coo = original
                     ref, _ = matrix_from_function(f, x0, auto_compress=True)
-                    assembly.STATS.update(device_assemblies=0, fallbacks=0)
-                    lt.tracer_to_coo = assembly.make_tracer_to_coo(original, lambda: True, oracle_assemble)
+                    assembly.STATS.update(device_assemblies=0, general_assemblies=0, fallbacks=0)
+                    lt.tracer_to_coo = assembly.make_tracer_to_coo(original, lambda: True, oracle_assemble, oracle_assemble_general)
                     mine, _ = matrix_from_function(f, x0, auto_compress=True)
-                assert (assembly.STATS['device_assemblies'] == 1) == expect, (f.__name__, assembly.STATS)
+                assert (assembly.STATS['device_assemblies'] == 1) == (expect == 'stencil'), (f.__name__, assembly.STATS)
+                assert (assembly.STATS['general_assemblies'] == 1) == (expect == 'general'), (f.__name__, assembly.STATS)
                 assert type(mine) is type(ref) and mine.shape == ref.shape
                 assert mine._compressed_dims == ref._compressed_dims and mine._uncompressed_dims == ref._uncompressed_dims
                 for name, dim in (('_indices', 'sp_entries'), ('_pointers', 'pointers'), ('_values', 'sp_entries')):
