@@ -404,16 +404,41 @@ def mul_coo_dense(indices, values, shape, dense) -> torch.Tensor:
     assert dense.shape[0] == batch_size and dense.shape[1] == cols and dense.shape[2] == channels
     out = torch.empty((batch_size, rows, channels, dense_cols), dtype=dt, device=values.device)
     for b in range(batch_size):
-        row = indices[b, :, 0].contiguous()
-        col = indices[b, :, 1].contiguous()
+        # The reference scatters with atomics (Backend.mul_coo_dense, _backend.py:1324-1326: order unspecified).  Here the entries are ordered by
+        # row ONCE per index array (stable sort: entry order kept inside a row, cached) and the product runs on the CSR kernels: every row is
+        # summed sequentially in entry order — deterministic, duplicates included.
+        rowptr, perm, col = _coo_row_order(indices[b], rows)
         for c in range(channels):
-            val = values[b, :, c].contiguous()
-            x = dense[b, :, c, :].t().contiguous()                       # (dense_cols, cols)
-            y = torch.zeros((dense_cols, rows), dtype=dt, device=values.device)
-            E.check(E.lib().phb200_spmv_coo(E.ptr(row), E.ptr(col), E.ptr(val), nnz, rows, cols, E.ptr(x), E.ptr(y), dense_cols, cols, rows,
-                                            E.dtype_code(dt), E.stream_ptr(values.device)))
-            out[b, :, c, :] = y.t()
+            val = values[b, :, c][perm].contiguous()
+            m = Matrix.csr(rowptr, col, val, (rows, cols))
+            out[b, :, c, :] = m.matvec(dense[b, :, c, :].t().contiguous()).t()
     return out
+
+
+_COO_ORDER: 'dict' = {}
+
+
+def _coo_row_order(idx: torch.Tensor, rows: int):
+    """(rowptr int32, permutation, sorted columns int32) of a (nnz, 2) coordinate array; cached on the array's storage + version."""
+    key = (idx.data_ptr(), idx._version, tuple(idx.shape), rows, str(idx.device))
+    hit = _COO_ORDER.get(key)
+    if hit is not None and hit[0]() is not None:
+        return hit[1]
+    import weakref
+    row = idx[:, 0].contiguous()
+    _, perm = torch.sort(row, stable=True)
+    counts = torch.bincount(row, minlength=rows)
+    rowptr = torch.zeros(rows + 1, dtype=torch.int32, device=idx.device)
+    rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    col = idx[:, 1][perm].to(torch.int32).contiguous()
+    value = (rowptr, perm, col)
+    if len(_COO_ORDER) >= 8:
+        _COO_ORDER.pop(next(iter(_COO_ORDER)))
+    try:
+        _COO_ORDER[key] = (weakref.ref(idx), value)
+    except TypeError:
+        pass
+    return value
 
 
 # ----------------------------------------------------------------------------------------------------------------------

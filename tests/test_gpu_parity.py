@@ -105,11 +105,24 @@ def test_mul_csr_dense_and_mul_coo_dense_shapes():
     bk = pb.B200Backend(DEV)
     out = bk.mul_csr_dense(np.tile(csr.indices, (b, 1)), np.tile(csr.indptr, (b, 1)), vals, csr.shape, dense)
     assert tuple(out.shape) == (b, csr.shape[0], ch, rhs)
-    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)          # rows summed sequentially in entry order, like SciPy's csr_matvecs
     coo = csr.tocoo()
     idx = np.tile(np.stack([coo.row, coo.col], -1)[None], (b, 1, 1))
     out = bk.mul_coo_dense(idx, vals, csr.shape, dense)
-    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)          # entries already in row-major order: same sums as the CSR form
+    # entries in arbitrary order with duplicates: deterministic (rows ordered once, stable; no atomics), equal to the dense product
+    perm = rng.permutation(csr.nnz)
+    idx2 = np.concatenate([idx[:, perm], idx[:, :7]], axis=1)
+    vals2 = np.concatenate([vals[:, perm], vals[:, :7]], axis=1)
+    a = bk.mul_coo_dense(idx2, vals2, csr.shape, dense)
+    a2 = bk.mul_coo_dense(idx2.copy(), vals2, csr.shape, dense)
+    assert torch.equal(a, a2)
+    ref2 = ref.copy()
+    for i in range(b):
+        for c in range(ch):
+            extra = sp.coo_matrix((vals[i, :7, c], (coo.row[:7], coo.col[:7])), shape=csr.shape).tocsr()
+            ref2[i, :, c, :] += extra @ dense[i, :, c, :]
+    np.testing.assert_allclose(a.cpu().numpy(), ref2, rtol=1e-5, atol=1e-5)
 
 
 # --------------------------------------------------------------------------------------------------- stencil <-> CSR
