@@ -31,7 +31,7 @@ SIGNATURES = {
     'phb200_shift_count': (c_int, [c_int, POINTER(c_int64), c_int, POINTER(c_int32), _P, c_int, _P, POINTER(c_int64), _P]),
     'phb200_shift_fill': (c_int, [c_int, POINTER(c_int64), c_int, POINTER(c_int32), _P, c_int, _P, _P, _P, _P]),
     'phb200_coded_from_csr': (c_int, [_PP, _P, _P]),
-    'phb200_coded_info': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
+    'phb200_coded_info': (c_int, [_P, POINTER(c_int), POINTER(c_int), POINTER(c_int64), POINTER(c_int)]),
     'phb200_stencil_nnz': (c_int, [_P, POINTER(c_int64)]),
     'phb200_stencil_to_csr': (c_int, [_P, _P, _P, _P, _P]),
     'phb200_matrix_set_slab': (c_int, [_P, c_int64, c_int64]),

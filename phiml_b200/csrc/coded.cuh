@@ -196,6 +196,39 @@ __global__ void __launch_bounds__(kBlock) k_coded_assign(CsrView A, const CodedD
     }
 }
 
+// Is the coded matrix a star whose rows only lose the neighbours that lie outside the grid (and differ in the diagonal)?  Every row is checked:
+// for each of the 2 * rank directions the table entry of the row's pattern must be the interior coefficient when the neighbour is inside the grid and
+// absent (0) when it is outside.  Writes the diagonal of every pattern and its inverse (1 / d in T, as Jacobi computes it).
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_coded_star_check(CodedView cv, int64_t n, int64_t nx, int64_t ny, int64_t nz, int k_diag, int k_xm, int k_xp, int k_ym, int k_yp,
+                                                            int k_zm, int k_zp, int* fail) {
+    const T* __restrict__ tab = (const T*)cv.table;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+        const T* row = tab + (int)cv.code[i] * kMaxStencil;
+        bool ok = true;
+        auto dir = [&](int k, bool inside) {
+            if (k < 0) return;
+            const T want = inside ? tab[k] : T(0);
+            if (coded_bits<T>(row[k]) != coded_bits<T>(want) && !(want == T(0) && row[k] == T(0))) ok = false;
+        };
+        dir(k_xm, ix > 0); dir(k_xp, ix + 1 < nx);
+        dir(k_ym, iy > 0); dir(k_yp, iy + 1 < ny);
+        dir(k_zm, iz > 0); dir(k_zp, iz + 1 < nz);
+        if (k_diag < 0 || row[k_diag] == T(0)) ok = false;
+        if (!ok) *fail = 1;
+    }
+}
+
+template <typename T>
+__global__ void k_coded_diag_tables(CodedView cv, int k_diag, T* __restrict__ diag, T* __restrict__ inv) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= cv.npat) return;
+    const T d = ((const T*)cv.table)[p * kMaxStencil + k_diag];
+    diag[p] = d;
+    inv[p] = T(1) / d;
+}
+
 // ---------------------------------------------------------------------------------------------- product
 template <typename T> constexpr size_t coded_smem(int npat) { return (size_t)npat * kMaxStencil * sizeof(T); }
 

@@ -29,6 +29,12 @@ struct CodedView {
     int64_t off[kMaxStencil];
     const uint8_t* code;               // [n_rows rounded up to a multiple of 4]
     const void* table;                 // [npat][kMaxStencil] of T
+    // "star with a per-row diagonal": every row is the interior star with the neighbours outside the grid cut off (ZERO_GRADIENT-type boundaries);
+    // only the diagonal differs between the patterns.  Such a matrix runs the fused TMA CG kernels (phb200_matrix.star holds the star, the TMA zero
+    // fill makes the cut-off neighbours harmless) with the diagonal / its inverse looked up per row.
+    int star_diag;
+    const void* diag_tab;              // [npat] of T: diagonal of every pattern
+    const void* inv_tab;               // [npat] of T: 1 / diagonal (Jacobi)
 };
 
 struct StencilDesc {
@@ -50,7 +56,7 @@ struct phb200_matrix {
     int is_star;            // stencil qualifies for the plane-marching kernels (star shape, nz % 4 == 0)
     phb::StarDesc star;
     phb::CodedView coded;   // PHB200_MAT_CODED: the csr view stays valid next to it
-    void* owned[2];         // device arrays freed with the handle (code bytes, pattern table)
+    void* owned[4];         // device arrays freed with the handle (code bytes, pattern table, diagonal tables)
     // lazily computed CSR analysis
     mutable int analysed;
     mutable int64_t max_block_nnz;   // max entries of any 256-row block

@@ -826,6 +826,7 @@ struct phb200_solver {
     // TMA descriptors of r and the two direction buffers (fused stencil CG); valid for the vectors bound by start()
     CUtensorMap tm_r, tm_a, tm_b;
     int tma_ok;
+    int coded_star_off;     // coded star matrix, but no tensor maps could be built: generic phases + coded product
     int tma_occ;               // resident CTAs per SM of the TMA stencil kernel (decides its x-chunking)
     // slab / multi-GPU mode: kernels store local sums in `totals`, the host all-reduces, dist_step() finalises
     double* totals;            // device, caller-owned (batch x kMaxDots doubles); non-null = distributed mode
@@ -1103,11 +1104,13 @@ struct Run {
         const int method = s->method;
         s->rtol = rtol; s->atol = atol; s->max_iter = max_iter;
         s->tma_ok = 0;
+        s->coded_star_off = 0;
         if ((fused() || fused_adaptive()) && !getenv("PHB200_NO_TMA")) {
             const StarDesc& sd = s->A->star;
             s->tma_ok = make_star_tmap(&s->tm_r, R, s->dtype, sd, batch, ld) && make_star_tmap(&s->tm_a, vec(0), s->dtype, sd, batch, ld) &&
                         make_star_tmap(&s->tm_b, vec(2), s->dtype, sd, batch, ld);
         }
+        if (s->A->kind == PHB200_MAT_CODED && !s->tma_ok) s->coded_star_off = 1;      // no tensor maps (alignment): the generic phases + coded product
         if (X != X0) PHB_CUDA(cudaMemcpyAsync(X, X0, sizeof(T) * (size_t)batch * ld, cudaMemcpyDeviceToDevice, st));
         PHB_CUDA(cudaMemsetAsync(s->tickets, 0, sizeof(unsigned) * (size_t)batch, st));
         PHB_CUDA(cudaMemsetAsync(s->glob, 0, sizeof(Glob), st));
@@ -1155,13 +1158,17 @@ struct Run {
         static int torch_on = -1;
         if (torch_on < 0) { const char* e = getenv("PHB200_CG_TORCH_FUSED"); torch_on = (e && e[0] == '0') ? 0 : 1; }
         const bool cg = s->method == PHB200_CG || (torch_on && s->method == PHB200_CG_TORCH && s->pre == PHB200_PRE_NONE && !s->totals);
-        return cg && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star && !pre_applied(s->pre) && !cb_mode();
+        return cg && (star_stencil() || coded_star()) && !pre_applied(s->pre) && !cb_mode();
     }
+    bool star_stencil() const { return s->A->kind == PHB200_MAT_STENCIL && s->A->is_star; }
+    // pattern-coded star with a per-row diagonal (ZERO_GRADIENT-type boundaries): the fused kernels in their DIAG form, TMA path only
+    bool coded_star() const { return s->A->kind == PHB200_MAT_CODED && s->A->coded.star_diag && s->A->is_star && !s->coded_star_off && !s->totals; }
+    StarDiag star_diag() const { return StarDiag{s->A->coded.code, s->A->coded.diag_tab, s->A->coded.inv_tab, s->A->coded.npat}; }
     // 'CG-adaptive' / 'auto' on a star stencil: residual kernel + TMA stencil kernel (direction, x update, product, d.q, d.r)
     bool fused_adaptive() const {
         static int on = -1;
         if (on < 0) { const char* e = getenv("PHB200_ADAPTIVE_FUSED"); on = (e && e[0] == '0') ? 0 : 1; }
-        return on && (s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH) && s->A->kind == PHB200_MAT_STENCIL && s->A->is_star &&
+        return on && (s->method == PHB200_CG_ADAPTIVE || s->method == PHB200_CG_ADAPTIVE_TORCH) && (star_stencil() || coded_star()) &&
                s->pre == PHB200_PRE_NONE && !cb_mode() && !s->totals;
     }
     CgDq<T> make_dq() {
@@ -1194,7 +1201,11 @@ struct Run {
         CgDq<T> e = make_dq();
         prof_begin();
         int r;
-        if constexpr (PRE != 1) {
+        if (coded_star()) {
+            // per-row diagonal: Jacobi (PRE == 1 here: the inverse diagonal is a vector for the residual kernel) takes the inverse from the pattern table
+            if constexpr (PRE == 0) r = launch_tma_coded<0>(X, q, e);
+            else r = launch_tma_coded<3>(X, q, e);
+        } else if constexpr (PRE != 1) {
             if (s->tma_ok) r = launch_tma<PRE>(X, q, loader.cinv, e);
             else r = launch_star<T, CgDirLoad<T, PRE>, CgDq<T>, true>(s->A->star, loader, q, ld, batch, e, st);
         } else {
@@ -1314,7 +1325,32 @@ struct Run {
         dim3 grid;
         int xchunk;
         star_grid_balanced(s->A->star, batch, occ, grid, xchunk);
-        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e, l2_hints(0));
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, cinv, ld, xchunk, 1, e, l2_hints(0), StarDiag{});
+        return PHB200_OK;
+    }
+    template <int PRE>
+    int launch_tma_coded(T* X, T* q, const CgDq<T>& e) {
+        const StarDesc& sd = s->A->star;
+        const bool unit = sd.cxm == -1.0 && sd.cxp == -1.0 && sd.cym == -1.0 && sd.cyp == -1.0 && sd.czm == -1.0 && sd.czp == -1.0;
+        return unit ? launch_tma_coded_t<PRE, true>(X, q, e) : launch_tma_coded_t<PRE, false>(X, q, e);
+    }
+    template <int PRE, bool UNIT>
+    int launch_tma_coded_t(T* X, T* q, const CgDq<T>& e) {
+        auto kernel = k_star_cg_tma<T, PRE, CgDq<T>, UNIT, 0, true>;
+        constexpr int smem = star_tma_smem<T>();
+        static int occ_dev[kMaxDevices] = {};
+        int& occ = occ_dev[device_slot()];
+        if (occ == 0) {
+            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
+            occ = v;
+        }
+        s->tma_occ = occ;
+        dim3 grid;
+        int xchunk;
+        star_grid_balanced(s->A->star, batch, occ, grid, xchunk);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, 1, e, l2_hints(0), star_diag());
         return PHB200_OK;
     }
     int pass_cg_fused(T* X, T* R, const T* Y, bool refresh) {
@@ -1411,9 +1447,9 @@ struct Run {
         return phase(c);
     }
 
-    template <bool UNIT>
+    template <bool UNIT, bool DIAG = false>
     int launch_tma_adaptive(T* X, T* q, int apply_x, const AdDots<T>& e) {
-        auto kernel = k_star_cg_tma<T, 0, AdDots<T>, UNIT, 1>;
+        auto kernel = k_star_cg_tma<T, 0, AdDots<T>, UNIT, 1, DIAG>;
         constexpr int smem = star_tma_smem<T>();
         static int occ_dev[kMaxDevices] = {};
         int& occ = occ_dev[device_slot()];
@@ -1427,7 +1463,8 @@ struct Run {
         dim3 grid;
         int xchunk;
         star_grid_balanced(s->A->star, batch, occ, grid, xchunk);
-        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, apply_x, e, 0u);
+        PHB_LAUNCH_PDL(kernel, grid, dim3(kBlock), (size_t)smem, st, s->tm_r, s->tm_a, s->tm_b, s->A->star, X, vec(0), vec(2), q, T(1), ld, xchunk, apply_x, e, 0u,
+                       DIAG ? star_diag() : StarDiag{});
         return PHB200_OK;
     }
     int pass_cg_adaptive_fused(T* X, T* R, const T* Y, bool refresh) {
@@ -1461,7 +1498,9 @@ struct Run {
         const StarDesc& sd = s->A->star;
         const bool unit = sd.cxm == -1.0 && sd.cxp == -1.0 && sd.cym == -1.0 && sd.cyp == -1.0 && sd.czm == -1.0 && sd.czp == -1.0;
         prof_begin();
-        const int r = unit ? launch_tma_adaptive<true>(X, q, apply_x, e) : launch_tma_adaptive<false>(X, q, apply_x, e);
+        int r;
+        if (coded_star()) r = unit ? launch_tma_adaptive<true, true>(X, q, apply_x, e) : launch_tma_adaptive<false, true>(X, q, apply_x, e);
+        else r = unit ? launch_tma_adaptive<true>(X, q, apply_x, e) : launch_tma_adaptive<false>(X, q, apply_x, e);
         prof_end();
         return r;
     }

@@ -599,12 +599,65 @@ int phb200_coded_from_csr(phb200_matrix** out, const phb200_matrix* csr, void* s
     m->coded.table = d_table;
     m->owned[0] = d_code;
     m->owned[1] = d_table;
+    // star with a per-row diagonal (ZERO_GRADIENT-type boundaries)?  Then the fused TMA CG kernels can run it (csrc/star_tma.cuh, DIAG form).
+    m->coded.star_diag = 0;
+    const int na = m->coded.fast_na;
+    if ((na == 1 || na == 2) && h_dict.K == 2 * na + 3 && !getenv("PHB200_CODED_STAR_OFF")) {
+        const long long s1 = offs[na + 3], s2 = na == 2 ? offs[na + 4] : 0;     // row stride (nz), plane stride (ny nz)
+        const long long nz = s1, ny = na == 2 ? (s1 > 0 ? s2 / s1 : 0) : n / (s1 > 0 ? s1 : 1), nx = na == 2 ? (s2 > 0 ? n / s2 : 0) : 1;
+        const bool mirrored = offs[na - 1] == -s1 && (na == 1 || offs[0] == -s2);
+        if (mirrored && nz >= 4 && ny >= 1 && nx >= 1 && nx * ny * nz == n && (na == 1 || s2 == ny * nz) && nz % 4 == 0) {
+            int* d_sf = nullptr;
+            void* d_diag = nullptr;
+            void* d_inv = nullptr;
+            bool ok = phb_malloc_async(&d_sf, sizeof(int), stream) == cudaSuccess && cudaMemsetAsync(d_sf, 0, sizeof(int), stream) == cudaSuccess &&
+                      cudaMalloc(&d_diag, (size_t)h_dict.npat * w) == cudaSuccess && cudaMalloc(&d_inv, (size_t)h_dict.npat * w) == cudaSuccess;
+            const int kd = na + 1, kzm = na, kzp = na + 2, kym = na - 1, kyp = na + 3, kxm = na == 2 ? 0 : -1, kxp = na == 2 ? na + 4 : -1;
+            if (ok) {
+                if (csr->dtype == PHB200_F32) {
+                    k_coded_star_check<float><<<gridx, kBlock, 0, stream>>>(m->coded, n, nx, ny, nz, kd, kxm, kxp, kym, kyp, kzm, kzp, d_sf);
+                    k_coded_diag_tables<float><<<(h_dict.npat + 63) / 64, 64, 0, stream>>>(m->coded, kd, (float*)d_diag, (float*)d_inv);
+                } else {
+                    k_coded_star_check<double><<<gridx, kBlock, 0, stream>>>(m->coded, n, nx, ny, nz, kd, kxm, kxp, kym, kyp, kzm, kzp, d_sf);
+                    k_coded_diag_tables<double><<<(h_dict.npat + 63) / 64, 64, 0, stream>>>(m->coded, kd, (double*)d_diag, (double*)d_inv);
+                }
+                g_launches.fetch_add(2);
+                int h_sf = 1;
+                ok = cudaMemcpyAsync(&h_sf, d_sf, sizeof(int), cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess && h_sf == 0;
+            }
+            if (d_sf) cudaFreeAsync(d_sf, stream);
+            if (ok) {
+                double c0[kMaxStencil];
+                bool got = true;
+                if (csr->dtype == PHB200_F32) {
+                    float t32[kMaxStencil];
+                    got = cudaMemcpy(t32, d_table, sizeof(t32), cudaMemcpyDeviceToHost) == cudaSuccess;
+                    for (int k = 0; k < kMaxStencil; ++k) c0[k] = t32[k];
+                } else got = cudaMemcpy(c0, d_table, sizeof(c0), cudaMemcpyDeviceToHost) == cudaSuccess;
+                ok = got;
+                if (ok) {
+                    StarDesc& sd = m->star;
+                    sd.nx = nx; sd.ny = ny; sd.nz = nz; sd.xb = 0; sd.xe = nx; sd.store_halo = 0;
+                    sd.c0 = c0[kd]; sd.czm = c0[kzm]; sd.czp = c0[kzp]; sd.cym = c0[kym]; sd.cyp = c0[kyp];
+                    sd.cxm = kxm >= 0 ? c0[kxm] : 0.0; sd.cxp = kxp >= 0 ? c0[kxp] : 0.0;
+                    m->is_star = 1;
+                    m->coded.star_diag = 1;
+                    m->coded.diag_tab = d_diag;
+                    m->coded.inv_tab = d_inv;
+                    m->owned[2] = d_diag;
+                    m->owned[3] = d_inv;
+                }
+            }
+            if (!ok) { if (d_diag) cudaFree(d_diag); if (d_inv) cudaFree(d_inv); cudaGetLastError(); }
+        }
+    }
     *out = m;
     return PHB200_OK;
 }
 
-int phb200_coded_info(const phb200_matrix* m, int* n_offsets, int* n_patterns, int64_t* offsets) {
+int phb200_coded_info(const phb200_matrix* m, int* n_offsets, int* n_patterns, int64_t* offsets, int* star_diag) {
     PHB_ARG(m && m->kind == PHB200_MAT_CODED, "need a coded matrix");
+    if (star_diag) *star_diag = m->coded.star_diag;
     if (n_offsets) *n_offsets = m->coded.K;
     if (n_patterns) *n_patterns = m->coded.npat;
     if (offsets)

@@ -159,12 +159,22 @@ template <typename T> __device__ __forceinline__ void st4_hint(T* p, const Quad<
 
 // L2 hint bits of k_star_cg_tma (two bits per stream: 0 plain, 1 keep = evict_last, 2 stream = evict_first):
 //   bits 0-1 r (TMA loads), 2-3 d_old (TMA loads), 4-5 x (loads and stores), 6-7 d_new (stores), 8-9 q (stores)
-// PRE: 0 none, 3 Jacobi with constant inverse diagonal
+// Per-row diagonal of a pattern-coded star (coded.cuh, CodedView::star_diag): code byte per row, diagonal / inverse diagonal per pattern
+struct StarDiag {
+    const uint8_t* code;
+    const void* diag_tab;
+    const void* inv_tab;
+    int npat;
+};
+
+// PRE: 0 none, 3 Jacobi with constant inverse diagonal (DIAG: inverse diagonal of the row's pattern)
 // ALG 0: CG direction d = M^-1 r + beta d ; ALG 1: CG-adaptive direction d = r - (r.q / d.q) d with the second dot d.r
-template <typename T, int PRE, class Epi, bool UNIT, int ALG = 0>
+// DIAG: the diagonal coefficient (and its inverse) is looked up per row through the pattern code — stars whose boundary rows only lose the neighbours
+//       outside the grid (ZERO_GRADIENT-type): the TMA zero fill makes the cut-off neighbours contribute a signed zero, exactly like ZERO boundaries
+template <typename T, int PRE, class Epi, bool UNIT, int ALG = 0, bool DIAG = false>
 __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_a,
                                                         const __grid_constant__ CUtensorMap tm_b, StarDesc st, T* __restrict__ X, T* buf_a, T* buf_b,
-                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, int apply_x, Epi epi, unsigned l2h = 0) {
+                                                        T* __restrict__ Q, T cinv, int64_t ld, int xchunk, int apply_x, Epi epi, unsigned l2h = 0, StarDiag dg = StarDiag{}) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TB = tile_bytes<T>();
     constexpr uint32_t kTxBytes = 2u * SROWS * SROW * sizeof(T);
@@ -179,6 +189,13 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
     double acc[NDA];
 #pragma unroll
     for (int dd = 0; dd < NDA; ++dd) acc[dd] = 0.0;
+    __shared__ T s_c0[DIAG ? 256 : 1], s_inv[DIAG ? 256 : 1];
+    if constexpr (DIAG) {
+        if (t < dg.npat) {
+            s_c0[t] = ((const T*)dg.diag_tab)[t];
+            s_inv[t] = ((const T*)dg.inv_tab)[t];
+        }
+    }
     if (t == 0) {
 #pragma unroll
         for (int k = 0; k < kStages; ++k) mbar_init(smem_u32(&bars[k]), 1);
@@ -203,16 +220,20 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
         auto pol_of = [&](unsigned sh) { return ((l2h >> sh) & 3u) == 1u ? pol_keep : pol_stream; };
         auto has = [&](unsigned sh) { return ((l2h >> sh) & 3u) != 0u; };
         const T ad_rq = (T)epi.sys[b].s[5 /*S_RQ*/], ad_dq = (T)epi.sys[b].s[3 /*S_DQ*/];
-        auto dir = [&](T rv, T dv) {
+        auto dir = [&](T rv, T dv, T ci) {
             if constexpr (ALG == 1) {      // AdDirection: d = r - safe_div(rq * d, dq)
                 const T tt = mul_rn(ad_rq, dv);
                 const T u = ad_dq == T(0) ? T(0) : tt / ad_dq;
                 return add_rn(rv, -u);
             } else {
-                const T s = PRE == 3 ? mul_rn(rv, cinv) : rv;
+                const T s = PRE == 3 ? mul_rn(rv, ci) : rv;
                 return add_rn(s, mul_rn(beta, dv));
             }
         };
+        constexpr bool DINV = DIAG && PRE == 3 && ALG == 0;      // the direction needs the inverse diagonal of every cell it is formed on (tile + halo)
+        const T cinv0 = DIAG ? s_inv[0] : cinv;
+        const T c00 = DIAG ? s_c0[0] : c0;
+        auto inv_of = [&](unsigned cw, int e) { return DINV ? (cw == 0u ? cinv0 : s_inv[(cw >> (8 * e)) & 0xffu]) : cinv; };
 
         // running state instead of per-plane index arithmetic: TMA stage + its mbarrier phase bits, byte offsets of the
         // tile pair and of the three live planes of the d_new ring, element offset of the current plane in global memory
@@ -257,12 +278,36 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
             T hz_c = T(0);
             const int hcol = lane == 0 ? 3 : 4 + SZ;
             int64_t off = ((x0 - 1) * ny + jy) * nz + jz;      // element offset of (plane x0-1, jy, jz); advanced per plane
+            // DIAG: pattern codes of the cells this thread forms directions / products on, fetched one plane ahead: its own quad (one 32-bit
+            // word), the halo row of warps 0 / 1 and the halo column of the edge lanes (inverse diagonal of the halo cells, Jacobi only)
+            const int jy_h = warp == 0 ? y0 - 1 : y0 + SY;                  // halo row formed by warp 0 / 1
+            const bool hrow_in = DINV && warp < 2 && jy_h >= 0 && jy_h < ny && jz < nz;
+            const int64_t hrow_d = (int64_t)(jy_h - jy) * nz;
+            const int jz_h = lane == 0 ? z0 - 1 : z0 + SZ;                  // halo column formed by lane 0 / 31
+            const bool hcol_in = DINV && (lane == 0 || lane == 31) && jz_h >= 0 && jz_h < nz && jy < ny;
+            const int64_t hcol_d = (int64_t)(jz_h - jz);
+            unsigned cw_c = 0, cw_p = 0, cwh_c = 0, cb_c = 0;               // own quad (this plane, previous plane), halo row, halo column
+            if constexpr (DIAG) {
+                if (x0 - 1 >= 0) {
+                    if (mine) cw_c = *reinterpret_cast<const unsigned*>(dg.code + off);
+                    if (hrow_in) cwh_c = *reinterpret_cast<const unsigned*>(dg.code + off + hrow_d);
+                    if (hcol_in) cb_c = dg.code[off + hcol_d];
+                }
+            }
             uint32_t pl_off = 0, pc_off = 3 * TB;              // byte offsets of planes k, k-1 in the ring
             for (int k = 0; k < P; ++k) {
                 const bool owned = mine && k >= 1 && k <= P - 2;
                 // the x values of the next owned plane travel while this plane is processed
                 Quad<T> x_next{{T(0), T(0), T(0), T(0)}};
                 if (apply_x && mine && k <= P - 3) x_next = has(4) ? ld4_hint<T>(xb + off + pstride, pol_of(4)) : ld4<T>(xb + off + pstride);
+                unsigned cw_n = 0, cwh_n = 0, cb_n = 0;
+                if constexpr (DIAG) {
+                    if (k + 1 < P && x0 + k < nx) {       // plane x0 + k (the next one) lies inside the grid
+                        if (mine) cw_n = *reinterpret_cast<const unsigned*>(dg.code + off + pstride);
+                        if (hrow_in) cwh_n = *reinterpret_cast<const unsigned*>(dg.code + off + pstride + hrow_d);
+                        if (hcol_in) cb_n = dg.code[off + pstride + hcol_d];
+                    }
+                }
                 mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
                 phase_bits ^= 1u << stg;
                 T(*rt)[SROW] = reinterpret_cast<T(*)[SROW]>(tiles0 + (size_t)(2 * stg) * TB);
@@ -273,7 +318,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 Quad<T> dn;
                 T hz_n = T(0);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e]);
+                for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e], inv_of(cw_c, e));
                 st4(&pl[sr][c], dn);
                 if (owned) {
                     if (has(6)) st4_hint(d_new + off, dn, pol_of(6));
@@ -292,10 +337,10 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                     const Quad<T> rh = ld4<T>(&rt[hr][c]), dh = ld4<T>(&dt[hr][c]);
                     Quad<T> hn;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e]);
+                    for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e], inv_of(cwh_c, e));
                     st4(&pl[hr][c], hn);
                 }
-                if (lane == 0 || lane == 31) hz_n = dir(rt[sr][hcol], dt[sr][hcol]);   // halo columns of this row
+                if (lane == 0 || lane == 31) hz_n = dir(rt[sr][hcol], dt[sr][hcol], inv_of(cb_c, 0));   // halo columns of this row
                 x_cur = x_next;
                 __syncthreads();   // plane k complete; its stage fully read
                 if (t == 0 && k + kStages < P) issue((int)x0 - 1 + k + kStages);
@@ -315,6 +360,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                         for (int e = 0; e < 4; ++e) {
                             const T zm = e == 0 ? left : ce.v[e - 1];
                             const T zp = e == 3 ? right : ce.v[e + 1];
+                            const T c0 = DIAG ? (cw_p == 0u ? c00 : s_c0[(cw_p >> (8 * e)) & 0xffu]) : c00;      // diagonal of this row (plane k-1)
                             T sum;
                             if constexpr (UNIT) {      // all six neighbour coefficients are -1: c*v == -v exactly, no multiply needed
                                 sum = -xm.v[e];
@@ -352,6 +398,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 dn_m = dn_c;
                 dn_c = dn;
                 hz_c = hz_n;
+                cw_p = cw_c; cw_c = cw_n; cwh_c = cwh_n; cb_c = cb_n;
                 pc_off = pl_off;   // rotate the ring: k -> k-1; the next plane takes the slot after k's (the slot of k-1 may still be read by slower warps)
                 pl_off = pl_off + TB == 4 * TB ? 0 : pl_off + TB;
             }

@@ -121,10 +121,11 @@ class Matrix:
         except E.NotAStencil:
             return None
         tw = Matrix(h, self.dtype, self.shape, (self.rowptr, self.col, self.values), 'coded', self.device)     # views this matrix' CSR arrays
-        k, p = ctypes.c_int(), ctypes.c_int()
+        k, p, sd = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         offs = (ctypes.c_int64 * 16)()
-        E.check(E.lib().phb200_coded_info(h, ctypes.byref(k), ctypes.byref(p), offs))
+        E.check(E.lib().phb200_coded_info(h, ctypes.byref(k), ctypes.byref(p), offs, ctypes.byref(sd)))
         tw.offsets, tw.patterns = [int(offs[i]) for i in range(k.value)], int(p.value)
+        tw.star_diag = bool(sd.value)      # star with a per-row diagonal: CG / CG-adaptive run on the fused TMA kernels
         self.coded = tw
         return tw
 

@@ -39,6 +39,7 @@ SOLVE_CASES = {
     'p128_auto_f32_torch': _c('poisson', (128, 128), 'float32', 'auto', 1e-5, backend='torch'),
     'p128_cgadaptive_f32': _c('poisson', (128, 128), 'float32', 'CG-adaptive', 1e-5),
     'p128_bicg2_f64': _c('poisson', (128, 128), 'float64', 'biCG-stab(2)', 1e-10),
+    'p128_bicg2_f64_torch': _c('poisson', (128, 128), 'float64', 'biCG-stab(2)', 1e-10, backend='torch'),   # the reference's own spread on this chaotic case
     'p128_jacobi_f64': _c('poisson', (128, 128), 'float64', 'CG', 1e-10, pre='jacobi'),
     'p128_ilu_f64': _c('poisson', (128, 128), 'float64', 'CG', 1e-10, pre='ilu'),
     'p128_ilu_f32': _c('poisson', (128, 128), 'float32', 'CG', 1e-5, pre='ilu'),

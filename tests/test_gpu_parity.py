@@ -191,9 +191,16 @@ def test_solve_matches_reference(name, use_stencil):
     its, fev = res.iterations.cpu().numpy(), res.function_evaluations.cpu().numpy()
     ref_it, ref_fe = g[key + '/iterations'], g[key + '/function_evaluations']
     assert its.dtype == np.int32 and res.converged.dtype == torch.bool
-    # +-2 everywhere; BiCGstab(2) on the ill-conditioned Poisson system is chaotic: the reference's own NumPy and torch
-    # backends disagree by 4 iterations there, so that one case gets +-10 (6 %)
-    it_tol = 10 if name == 'p128_bicg2_f64' else 2
+    # +-2 everywhere.  BiCGstab(2) on the ill-conditioned 2-D Poisson system is chaotic: the reference's OWN backends disagree there — 164 iterations
+    # on NumPy, 159 on torch (both recorded in solves.npz: p128_bicg2_f64 / p128_bicg2_f64_torch); any change of the summation order of a dot product
+    # moves the stopping iteration.  For that system the count must lie within the reference's own spread of one of its two results.
+    it_tol = 2
+    if name.startswith('p128_bicg2_f64'):
+        pair = [int(g[f"solve/{k}/iterations"][0]) for k in ('p128_bicg2_f64', 'p128_bicg2_f64_torch')]
+        it_tol = abs(pair[0] - pair[1])
+        nearest = min(pair, key=lambda v: abs(int(its[0]) - v))
+        ref_it = np.asarray([nearest], ref_it.dtype)
+        ref_fe = g[f"solve/{'p128_bicg2_f64' if nearest == pair[0] else 'p128_bicg2_f64_torch'}/function_evaluations"]
     assert np.max(np.abs(its.astype(int) - ref_it.astype(int))) <= it_tol, f"iterations {its} vs reference {ref_it}"
     per_it = 2 * int(case['method'][-2]) if case['method'].startswith('biCG-stab(') else 1
     assert np.max(np.abs(fev.astype(int) - ref_fe.astype(int))) <= it_tol * per_it + 1, f"function_evaluations {fev} vs reference {ref_fe}"
