@@ -597,7 +597,7 @@ def run_ours(args):
         dom = max(range(len(kernels)), key=lambda k: kernels[k]['avg_ms'])
         kd = kernels[dom]
         roofline = {"bound": "hbm", "kernel": kd['kernel'], "achieved": kd['gbs'], "peak": peak, "unit": "GB/s", "frac": kd['gbs'] / peak, "traffic": kd['traffic'],
-                    "traffic_source": "ncu --set full capture (cold L2), profiles/ncu_traffic.json" if kd['traffic'] else None, "peak_source": peak_src,
+                    "traffic_source": "ncu --set full capture (cold L2), profiles/ncu_traffic.json <- profiles/r02_ncu_full_cg.txt" if kd['traffic'] else None, "peak_source": peak_src,
                     "per_gpu": world > 1, "share_of_step": kd['avg_ms'] / sum(k_['avg_ms'] for k_ in kernels), "kernels": kernels}
     iteration = {"bytes_moved_by_design": 9 * N * w, "achieved_gbs_per_gpu": head["hbm_gbs_per_gpu"], "frac_of_peak_per_gpu": head["hbm_frac_of_peak_per_gpu"],
                  "survey_model_bytes": 13 * N * w, "survey_model_frac_of_peak_per_gpu": head["survey_model_frac_of_peak_per_gpu"]}

@@ -22,11 +22,15 @@ p.add_argument('--n', type=int, default=256)
 p.add_argument('--pre', default='jacobi')
 p.add_argument('--method', default='CG')
 p.add_argument('--reps', type=int, default=3)
+p.add_argument('--op', default='zero', choices=['zero', 'neumann', 'periodic'], help="boundary of the Laplacian: ZERO (stencil kernels), ZERO_GRADIENT (+0.05 I; coded star, fused CG), PERIODIC (+0.05 I; coded stencil)")
 a = p.parse_args()
 TORCH = phiml_plugin.install()
 n = a.n
-f = math.jit_compile_linear(lambda x: -math.laplace(x, padding=extrapolation.ZERO))
-out = {"n": n, "method": a.method, "preconditioner": a.pre, "calls": []}
+OPS = {'zero': lambda x: -math.laplace(x, padding=extrapolation.ZERO),
+       'neumann': lambda x: 0.05 * x - math.laplace(x, padding=extrapolation.ZERO_GRADIENT),
+       'periodic': lambda x: 0.05 * x - math.laplace(x, padding=extrapolation.PERIODIC)}
+f = math.jit_compile_linear(OPS[a.op])
+out = {"n": n, "operator": a.op, "method": a.method, "preconditioner": a.pre, "calls": []}
 with TORCH, math.precision(32):
     y_host = np.random.default_rng(0).standard_normal((n, n, n)).astype(np.float32)
     x0 = math.zeros(spatial(x=n, y=n, z=n))
@@ -47,6 +51,8 @@ with TORCH, math.precision(32):
     r = y - f(x)
     out["true_residual"] = float(math.l2_loss(r).numpy()) ** 0.5 / float(math.l2_loss(y).numpy()) ** 0.5
 out["assembly"] = dict(assembly.STATS)
+from phiml_b200 import sparse as _sp
+out["natives"] = [{"kind": m.kind, "stencil": m.stencil is not None, "coded": m.coded is not None, "star_diag": bool(getattr(m.coded, 'star_diag', False)) if m.coded is not None else False} for m in _sp._CACHE.values()]
 out["native_cache"] = {"hits": phiml_plugin.NATIVE_CACHE.hits, "misses": phiml_plugin.NATIVE_CACHE.misses}
 out["host_peak_rss_gb"] = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6
 out["device_peak_gb"] = torch.cuda.max_memory_allocated() / 1e9
