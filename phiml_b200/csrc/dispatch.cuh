@@ -6,6 +6,12 @@
 
 namespace phb {
 
+inline bool coded_star_tma() {        // PHB200_CODED_STAR_TMA=0: coded stars through the flat coded product (A/B)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PHB200_CODED_STAR_TMA"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 // Host-side dispatch used by phb200_spmv and by the solver.  `scale` != nullptr selects y = A (scale .* x).
 template <typename T, class Epi>
 int launch_spmv(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t ldy, const T* scale, int batch,
@@ -25,7 +31,16 @@ int launch_spmv(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t l
         else PHB_LAUNCH((k_spmv_stencil<T, false, Epi>), grid, kBlock, 0, stream, A->st, n, X, ldx, Y, ldy, scale, batch, epi);
         return PHB200_OK;
     }
-    if (A->kind == PHB200_MAT_CODED && !scale) return launch_coded_spmv<T, Epi>(A->coded, A->n_rows, X, ldx, Y, ldy, batch, epi, stream);
+    if (A->kind == PHB200_MAT_CODED && !scale) {
+        if (A->coded.star_diag && A->is_star && coded_star_tma()) {
+            // star with a per-row diagonal (ZERO_GRADIENT-type boundaries): the TMA-staged stencil product with the diagonal looked up per row
+            bool used = false;
+            const StarDiag dg{A->coded.code, A->coded.diag_tab, A->coded.inv_tab, A->coded.npat};
+            PHB_TRY((launch_star_spmv_tma_diag<T, Epi>(A->star, dg, X, ldx, Y, ldy, batch, A->dtype, epi, stream, &used)));
+            if (used) return PHB200_OK;
+        }
+        return launch_coded_spmv<T, Epi>(A->coded, A->n_rows, X, ldx, Y, ldy, batch, epi, stream);
+    }
     if (A->transposed) {
         set_error("fused product with a transposed (CSC-native) matrix is not supported; use phb200_spmv");
         return PHB200_ERR_UNSUPPORTED;

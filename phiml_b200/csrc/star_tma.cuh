@@ -415,8 +415,10 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
 constexpr int kSpStages = 5;
 template <typename T> constexpr int star_spmv_smem() { return kSpStages * tile_bytes<T>() + 8 * kSpStages + 128; }
 
-template <typename T, class Epi, bool UNIT>
-__global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant__ CUtensorMap tm_x, StarDesc st, T* __restrict__ Y, int64_t ldy, int xchunk, Epi epi) {
+// DIAG: the diagonal coefficient is looked up per row through the pattern code of a coded star (coded.cuh, CodedView::star_diag)
+template <typename T, class Epi, bool UNIT, bool DIAG = false>
+__global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant__ CUtensorMap tm_x, StarDesc st, T* __restrict__ Y, int64_t ldy, int xchunk, Epi epi,
+                                                          StarDiag dg = StarDiag{}) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TB = tile_bytes<T>();
     constexpr int S = kSpStages;
@@ -431,6 +433,10 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
     double acc[NDA];
 #pragma unroll
     for (int d = 0; d < NDA; ++d) acc[d] = 0.0;
+    __shared__ T s_c0[DIAG ? 256 : 1];
+    if constexpr (DIAG) {
+        if (t < dg.npat) s_c0[t] = ((const T*)dg.diag_tab)[t];
+    }
     if (t == 0) {
 #pragma unroll
         for (int k = 0; k < S; ++k) mbar_init(smem_u32(&bars[k]), 1);
@@ -471,7 +477,13 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
             // z neighbours inside the row travel by warp shuffle (the scalar loads at c-1 / c+4 were 4-way bank conflicts).
             Quad<T> q_m{{T(0), T(0), T(0), T(0)}}, q_c{{T(0), T(0), T(0), T(0)}};
             const int hcol = lane == 0 ? 3 : 4 + SZ;             // halo column read by the first / last lane of a row
+            unsigned cw_c = 0;                                   // DIAG: pattern codes of this step's output quad, fetched one step ahead
+            const T c00 = DIAG ? s_c0[0] : c0;
             for (int k = 0; k < P; ++k) {
+                unsigned cw_n = 0;
+                if constexpr (DIAG) {
+                    if (mine && k >= 1 && k + 1 < P) cw_n = *reinterpret_cast<const unsigned*>(dg.code + off + (k >= 2 ? pstride : 0));
+                }
                 mbar_wait(smem_u32(&bars[stg]), (phase_bits >> stg) & 1u);
                 phase_bits ^= 1u << stg;
                 const uint32_t s_p = stg;
@@ -496,6 +508,7 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
                     for (int e = 0; e < 4; ++e) {
                         const T zm = e == 0 ? left : ce.v[e - 1];
                         const T zp = e == 3 ? right : ce.v[e + 1];
+                        const T c0 = DIAG ? (cw_c == 0u ? c00 : s_c0[(cw_c >> (8 * e)) & 0xffu]) : c00;      // diagonal of this row
                         T sum;
                         if constexpr (UNIT) {
                             sum = -xm.v[e];
@@ -524,6 +537,7 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
                 }
                 q_m = q_c;
                 q_c = q_p;
+                cw_c = cw_n;
                 __syncthreads();   // the stage of plane k-1 is free (its rows were read as y neighbours above); plane k stays for the next step
                 // planes k+1 .. k+S-2 are in flight; the freed stage takes plane k+S-1
                 if (t == 0 && k >= 1 && k + S - 1 < P) issue((int)x0 - 1 + k + S - 1);
@@ -532,6 +546,36 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
         }
     }
     epilogue_tail(epi, acc, b, blockIdx.x, gridDim.x);
+}
+
+template <typename T, class Epi, bool UNIT, bool DIAG>
+int launch_star_spmv_tma_t(const CUtensorMap& tm, const StarDesc& st, T* Y, int64_t ldy, int batch, const Epi& epi, cudaStream_t stream, const StarDiag& dg) {
+    auto kernel = k_star_spmv_tma<T, Epi, UNIT, DIAG>;
+    constexpr int smem = star_spmv_smem<T>();
+    static int occ_dev[kMaxDevices] = {};
+    int& occ = occ_dev[device_slot()];
+    if (occ == 0) {
+        PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
+        occ = v;
+    }
+    dim3 grid;
+    int xchunk;
+    star_grid_balanced(st, batch, occ, grid, xchunk);
+    PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi, dg);
+    return PHB200_OK;
+}
+
+// coded star with a per-row diagonal (dg != nullptr): the same kernel in its DIAG form
+template <typename T, class Epi>
+int launch_star_spmv_tma_diag(const StarDesc& st, const StarDiag& dg, const T* X, int64_t ldx, T* Y, int64_t ldy, int batch, int dtype, const Epi& epi, cudaStream_t stream, bool* used) {
+    *used = false;
+    CUtensorMap tm;
+    if (!make_star_tmap(&tm, X, dtype, st, batch, ldx)) return PHB200_OK;
+    const bool unit = st.cxm == -1.0 && st.cxp == -1.0 && st.cym == -1.0 && st.cyp == -1.0 && st.czm == -1.0 && st.czp == -1.0;
+    *used = true;
+    return unit ? launch_star_spmv_tma_t<T, Epi, true, true>(tm, st, Y, ldy, batch, epi, stream, dg) : launch_star_spmv_tma_t<T, Epi, false, true>(tm, st, Y, ldy, batch, epi, stream, dg);
 }
 
 template <typename T, class Epi>
@@ -543,36 +587,8 @@ int launch_star_spmv_tma(const StarDesc& st, const T* X, int64_t ldx, T* Y, int6
     CUtensorMap tm;
     if (!make_star_tmap(&tm, X, dtype, st, batch, ldx)) return PHB200_OK;
     const bool unit = st.cxm == -1.0 && st.cxp == -1.0 && st.cym == -1.0 && st.cyp == -1.0 && st.czm == -1.0 && st.czp == -1.0;
-    constexpr int smem = star_spmv_smem<T>();
-    dim3 grid;
-    int xchunk;
-    if (unit) {
-        auto kernel = k_star_spmv_tma<T, Epi, true>;
-        static int occ_dev[kMaxDevices] = {};
-        int& occ = occ_dev[device_slot()];
-        if (occ == 0) {
-            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            int v = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
-            occ = v;
-        }
-        star_grid_balanced(st, batch, occ, grid, xchunk);
-        PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
-    } else {
-        auto kernel = k_star_spmv_tma<T, Epi, false>;
-        static int occ_dev[kMaxDevices] = {};
-        int& occ = occ_dev[device_slot()];
-        if (occ == 0) {
-            PHB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            int v = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kBlock, smem) != cudaSuccess || v < 1) { cudaGetLastError(); v = 1; }
-            occ = v;
-        }
-        star_grid_balanced(st, batch, occ, grid, xchunk);
-        PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi);
-    }
     *used = true;
-    return PHB200_OK;
+    return unit ? launch_star_spmv_tma_t<T, Epi, true, false>(tm, st, Y, ldy, batch, epi, stream, StarDiag{}) : launch_star_spmv_tma_t<T, Epi, false, false>(tm, st, Y, ldy, batch, epi, stream, StarDiag{});
 }
 
 }  // namespace phb
