@@ -199,23 +199,36 @@ __global__ void __launch_bounds__(kBlock) k_coded_assign(CsrView A, const CodedD
 // Is the coded matrix a star whose rows only lose the neighbours that lie outside the grid (and differ in the diagonal)?  Every row is checked:
 // for each of the 2 * rank directions the table entry of the row's pattern must be the interior coefficient when the neighbour is inside the grid and
 // absent (0) when it is outside.  Writes the diagonal of every pattern and its inverse (1 / d in T, as Jacobi computes it).
+struct StarCheck {
+    int64_t nx, ny, nz;
+    int k_diag;
+    int k_dir[6];      // table index of the direct offset per direction (x-, x+, y-, y+, z-, z+) or -1 (axis absent)
+    int k_wrap[6];     // table index of the wrapped offset per direction (PERIODIC axis) or -1
+};
+
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_coded_star_check(CodedView cv, int64_t n, int64_t nx, int64_t ny, int64_t nz, int k_diag, int k_xm, int k_xp, int k_ym, int k_yp,
-                                                            int k_zm, int k_zp, int* fail) {
+__global__ void __launch_bounds__(kBlock) k_coded_star_check(CodedView cv, int64_t n, StarCheck sc, int* fail) {
     const T* __restrict__ tab = (const T*)cv.table;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
-        const int64_t iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+        const int64_t iz = i % sc.nz, iy = (i / sc.nz) % sc.ny, ix = i / (sc.nz * sc.ny);
         const T* row = tab + (int)cv.code[i] * kMaxStencil;
         bool ok = true;
-        auto dir = [&](int k, bool inside) {
-            if (k < 0) return;
-            const T want = inside ? tab[k] : T(0);
-            if (coded_bits<T>(row[k]) != coded_bits<T>(want) && !(want == T(0) && row[k] == T(0))) ok = false;
+        // direction d: inside -> the direct entry carries the interior coefficient, the wrapped one is absent; outside -> the other way round on a
+        // PERIODIC axis, both absent otherwise
+        auto dir = [&](int d, bool inside) {
+            const int kd = sc.k_dir[d], kw = sc.k_wrap[d];
+            if (kd < 0) return;
+            const T want = tab[kd];                          // interior coefficient of this direction (pattern 0)
+            const T direct = row[kd], wrapped = kw >= 0 ? row[kw] : T(0);
+            // NOTE: a wrapped offset of one direction may coincide with nothing else (axes with >= 3 cells), so the two entries are independent
+            if (inside) { if (coded_bits<T>(direct) != coded_bits<T>(want) || wrapped != T(0)) ok = false; }
+            else if (kw >= 0) { if (coded_bits<T>(wrapped) != coded_bits<T>(want) || direct != T(0)) ok = false; }
+            else if (direct != T(0)) ok = false;
         };
-        dir(k_xm, ix > 0); dir(k_xp, ix + 1 < nx);
-        dir(k_ym, iy > 0); dir(k_yp, iy + 1 < ny);
-        dir(k_zm, iz > 0); dir(k_zp, iz + 1 < nz);
-        if (k_diag < 0 || row[k_diag] == T(0)) ok = false;
+        dir(0, ix > 0); dir(1, ix + 1 < sc.nx);
+        dir(2, iy > 0); dir(3, iy + 1 < sc.ny);
+        dir(4, iz > 0); dir(5, iz + 1 < sc.nz);
+        if (sc.k_diag < 0 || row[sc.k_diag] == T(0)) ok = false;
         if (!ok) *fail = 1;
     }
 }

@@ -35,7 +35,7 @@ int launch_spmv(const phb200_matrix* A, const T* X, int64_t ldx, T* Y, int64_t l
         if (A->coded.star_diag && A->is_star && coded_star_tma()) {
             // star with a per-row diagonal (ZERO_GRADIENT-type boundaries): the TMA-staged stencil product with the diagonal looked up per row
             bool used = false;
-            const StarDiag dg{A->coded.code, A->coded.diag_tab, A->coded.inv_tab, A->coded.npat};
+            const StarDiag dg{A->coded.code, A->coded.diag_tab, A->coded.inv_tab, A->coded.npat, nullptr, 0};
             PHB_TRY((launch_star_spmv_tma_diag<T, Epi>(A->star, dg, X, ldx, Y, ldy, batch, A->dtype, epi, stream, &used)));
             if (used) return PHB200_OK;
         }

@@ -18,6 +18,7 @@ struct StarDesc {       // centre + nearest neighbours per axis; see stencil_fas
     int64_t xb, xe;         // planes [xb, xe) are produced; reads reach planes xb-1 and xe when they lie inside the array
     int store_halo;         // slab mode: the fused CG kernel also stores d_new on the halo planes xb-1 and xe
     double c0, cxm, cxp, cym, cyp, czm, czp;
+    int wrap;               // coded stars: PERIODIC axes (bit 0: x, 1: y, 2: z) — the neighbour across the boundary is the cell at the other end
 };
 
 // Pattern-coded stencil (coded.cuh): distinct flat offsets, distinct rows, one code byte per row

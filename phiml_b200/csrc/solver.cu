@@ -1162,8 +1162,8 @@ struct Run {
     }
     bool star_stencil() const { return s->A->kind == PHB200_MAT_STENCIL && s->A->is_star; }
     // pattern-coded star with a per-row diagonal (ZERO_GRADIENT-type boundaries): the fused kernels in their DIAG form, TMA path only
-    bool coded_star() const { return s->A->kind == PHB200_MAT_CODED && s->A->coded.star_diag && s->A->is_star && !s->coded_star_off && !s->totals; }
-    StarDiag star_diag() const { return StarDiag{s->A->coded.code, s->A->coded.diag_tab, s->A->coded.inv_tab, s->A->coded.npat}; }
+    bool coded_star() const { return s->A->kind == PHB200_MAT_CODED && s->A->coded.star_diag && s->A->is_star && s->A->star.wrap == 0 && !s->coded_star_off && !s->totals; }
+    StarDiag star_diag() const { return StarDiag{s->A->coded.code, s->A->coded.diag_tab, s->A->coded.inv_tab, s->A->coded.npat, nullptr, 0}; }
     // 'CG-adaptive' / 'auto' on a star stencil: residual kernel + TMA stencil kernel (direction, x update, product, d.q, d.r)
     bool fused_adaptive() const {
         static int on = -1;

@@ -602,23 +602,57 @@ int phb200_coded_from_csr(phb200_matrix** out, const phb200_matrix* csr, void* s
     // star with a per-row diagonal (ZERO_GRADIENT-type boundaries)?  Then the fused TMA CG kernels can run it (csrc/star_tma.cuh, DIAG form).
     m->coded.star_diag = 0;
     const int na = m->coded.fast_na;
-    if ((na == 1 || na == 2) && h_dict.K == 2 * na + 3 && !getenv("PHB200_CODED_STAR_OFF")) {
-        const long long s1 = offs[na + 3], s2 = na == 2 ? offs[na + 4] : 0;     // row stride (nz), plane stride (ny nz)
+    if ((na == 1 || na == 2) && !getenv("PHB200_CODED_STAR_OFF")) {
+        // interior pattern [(-S2,) -S1, -1, 0, 1, S1 (, S2)]: S1 = row stride (nz), S2 = plane stride (ny nz)
+        std::vector<long long> nzo;
+        {
+            double c0t[kMaxStencil];
+            bool got = true;
+            if (csr->dtype == PHB200_F32) {
+                float t32[kMaxStencil];
+                got = cudaMemcpy(t32, d_table, sizeof(t32), cudaMemcpyDeviceToHost) == cudaSuccess;
+                for (int k = 0; k < kMaxStencil; ++k) c0t[k] = t32[k];
+            } else got = cudaMemcpy(c0t, d_table, sizeof(c0t), cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (got)
+                for (int k = 0; k < h_dict.K; ++k)
+                    if (c0t[k] != 0.0) nzo.push_back(offs[k]);
+        }
+        auto index_of = [&](long long d) { for (int k = 0; k < h_dict.K; ++k) if (offs[k] == d) return k; return -1; };
+        const bool shape_ok = (int)nzo.size() == 2 * na + 3;
+        const long long s1 = shape_ok ? nzo[na + 3] : 0, s2 = (shape_ok && na == 2) ? nzo[na + 4] : 0;
         const long long nz = s1, ny = na == 2 ? (s1 > 0 ? s2 / s1 : 0) : n / (s1 > 0 ? s1 : 1), nx = na == 2 ? (s2 > 0 ? n / s2 : 0) : 1;
-        const bool mirrored = offs[na - 1] == -s1 && (na == 1 || offs[0] == -s2);
+        const bool mirrored = shape_ok && nzo[na - 1] == -s1 && (na == 1 || nzo[0] == -s2);
+        StarCheck sc;
+        memset(&sc, 0, sizeof(sc));
+        int wrap = 0, accounted = 2 * na + 3;
         if (mirrored && nz >= 4 && ny >= 1 && nx >= 1 && nx * ny * nz == n && (na == 1 || s2 == ny * nz) && nz % 4 == 0) {
+            sc.nx = nx; sc.ny = ny; sc.nz = nz;
+            sc.k_diag = index_of(0);
+            const long long stride[3] = {s2, s1, 1}, ext[3] = {nx, ny, nz};
+            for (int ax = 0; ax < 3; ++ax) {
+                const bool present = ax > 0 || na == 2;
+                sc.k_dir[2 * ax] = present ? index_of(-stride[ax]) : -1;
+                sc.k_dir[2 * ax + 1] = present ? index_of(stride[ax]) : -1;
+                sc.k_wrap[2 * ax] = sc.k_wrap[2 * ax + 1] = -1;
+                if (present && ext[ax] >= 3) {
+                    const int kw_m = index_of((ext[ax] - 1) * stride[ax]), kw_p = index_of(-(ext[ax] - 1) * stride[ax]);   // x- wraps to +(n-1) stride, x+ to -(n-1) stride
+                    if (kw_m >= 0 && kw_p >= 0) { sc.k_wrap[2 * ax] = kw_m; sc.k_wrap[2 * ax + 1] = kw_p; wrap |= 1 << ax; accounted += 2; }
+                }
+            }
+        }
+        if (sc.nz > 0 && accounted == h_dict.K && sc.k_diag >= 0) {
             int* d_sf = nullptr;
             void* d_diag = nullptr;
             void* d_inv = nullptr;
             bool ok = phb_malloc_async(&d_sf, sizeof(int), stream) == cudaSuccess && cudaMemsetAsync(d_sf, 0, sizeof(int), stream) == cudaSuccess &&
                       cudaMalloc(&d_diag, (size_t)h_dict.npat * w) == cudaSuccess && cudaMalloc(&d_inv, (size_t)h_dict.npat * w) == cudaSuccess;
-            const int kd = na + 1, kzm = na, kzp = na + 2, kym = na - 1, kyp = na + 3, kxm = na == 2 ? 0 : -1, kxp = na == 2 ? na + 4 : -1;
+            const int kd = sc.k_diag, kzm = sc.k_dir[4], kzp = sc.k_dir[5], kym = sc.k_dir[2], kyp = sc.k_dir[3], kxm = sc.k_dir[0], kxp = sc.k_dir[1];
             if (ok) {
                 if (csr->dtype == PHB200_F32) {
-                    k_coded_star_check<float><<<gridx, kBlock, 0, stream>>>(m->coded, n, nx, ny, nz, kd, kxm, kxp, kym, kyp, kzm, kzp, d_sf);
+                    k_coded_star_check<float><<<gridx, kBlock, 0, stream>>>(m->coded, n, sc, d_sf);
                     k_coded_diag_tables<float><<<(h_dict.npat + 63) / 64, 64, 0, stream>>>(m->coded, kd, (float*)d_diag, (float*)d_inv);
                 } else {
-                    k_coded_star_check<double><<<gridx, kBlock, 0, stream>>>(m->coded, n, nx, ny, nz, kd, kxm, kxp, kym, kyp, kzm, kzp, d_sf);
+                    k_coded_star_check<double><<<gridx, kBlock, 0, stream>>>(m->coded, n, sc, d_sf);
                     k_coded_diag_tables<double><<<(h_dict.npat + 63) / 64, 64, 0, stream>>>(m->coded, kd, (double*)d_diag, (double*)d_inv);
                 }
                 g_launches.fetch_add(2);
@@ -640,6 +674,7 @@ int phb200_coded_from_csr(phb200_matrix** out, const phb200_matrix* csr, void* s
                     sd.nx = nx; sd.ny = ny; sd.nz = nz; sd.xb = 0; sd.xe = nx; sd.store_halo = 0;
                     sd.c0 = c0[kd]; sd.czm = c0[kzm]; sd.czp = c0[kzp]; sd.cym = c0[kym]; sd.cyp = c0[kyp];
                     sd.cxm = kxm >= 0 ? c0[kxm] : 0.0; sd.cxp = kxp >= 0 ? c0[kxp] : 0.0;
+                    sd.wrap = wrap;
                     m->is_star = 1;
                     m->coded.star_diag = 1;
                     m->coded.diag_tab = d_diag;

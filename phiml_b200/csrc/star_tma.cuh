@@ -37,13 +37,13 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // (batch, nx, ny, nz) row-major vector set with leading dimension ld -> 4-D map with box (SROW, SROWS, 1, 1)
-inline bool make_star_tmap(CUtensorMap* out, const void* base, int dtype, const StarDesc& st, int64_t batch, int64_t ld) {
+inline bool make_star_tmap(CUtensorMap* out, const void* base, int dtype, const StarDesc& st, int64_t batch, int64_t ld, int box_z = SROW, int box_y = SROWS) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     const cuuint64_t w = dtype == PHB200_F32 ? 4 : 8;
     cuuint64_t dims[4] = {(cuuint64_t)st.nz, (cuuint64_t)st.ny, (cuuint64_t)st.nx, (cuuint64_t)batch};
     cuuint64_t strides[3] = {(cuuint64_t)st.nz * w, (cuuint64_t)st.ny * st.nz * w, (cuuint64_t)ld * w};
-    cuuint32_t box[4] = {(cuuint32_t)SROW, (cuuint32_t)SROWS, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_z, (cuuint32_t)box_y, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int k = 0; k < 3; ++k)
         if (strides[k] % 16 != 0 || strides[k] >= (1ull << 40)) return false;
@@ -165,6 +165,8 @@ struct StarDiag {
     const void* diag_tab;
     const void* inv_tab;
     int npat;
+    const void* x;          // product kernel: the input vector itself (PERIODIC axes: neighbours across the boundary are loaded from it directly)
+    int64_t ldx;
 };
 
 // PRE: 0 none, 3 Jacobi with constant inverse diagonal (DIAG: inverse diagonal of the row's pattern)
@@ -408,19 +410,52 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
 }
 
 
+// Row sum of a star whose neighbours across a PERIODIC boundary sit at the other end of their axis: the CSR row is ordered by column, so a
+// wrapped neighbour is added at its WRAPPED position.  Ascending offsets of everything a row can hold:
+//   x+ wrapped, x-, y+ wrapped, y-, z+ wrapped, z-, centre, z+, z- wrapped, y+, y- wrapped, x+, x- wrapped
+// wf bits: 0 x- wrapped, 1 x+ wrapped, 2 y- wrapped, 3 y+ wrapped, 4 z- wrapped, 5 z+ wrapped.  With wf == 0 this is the ordinary order.
+template <typename T>
+__device__ __forceinline__ T star_sum_wrapped(unsigned wf, T txm, T txp, T tym, T typ, T tzm, T tzp, T tc) {
+    T sum = T(0);
+    bool first = true;
+    auto add = [&](T v) { sum = first ? v : add_rn(sum, v); first = false; };
+    if (wf & 2u) add(txp);
+    if (!(wf & 1u)) add(txm);
+    if (wf & 8u) add(typ);
+    if (!(wf & 4u)) add(tym);
+    if (wf & 32u) add(tzp);
+    if (!(wf & 16u)) add(tzm);
+    add(tc);
+    if (!(wf & 32u)) add(tzp);
+    if (wf & 16u) add(tzm);
+    if (!(wf & 8u)) add(typ);
+    if (wf & 4u) add(tym);
+    if (!(wf & 2u)) add(txp);
+    if (wf & 1u) add(txm);
+    return sum;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Plain product y = A x on a star stencil with TMA staging: the x tiles (with halo, zero-filled outside the domain) ARE the
 // plane ring — kSpStages planes per CTA in flight, one barrier per plane, any epilogue (dots of BiCGstab, none for phb200_spmv).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kSpStages = 5;
-template <typename T> constexpr int star_spmv_smem() { return kSpStages * tile_bytes<T>() + 8 * kSpStages + 128; }
+// WRAP: every stage also holds the rows / columns from the other end of a PERIODIC axis (filled by extra TMA boxes of the boundary tiles):
+// [tile][y-low row][y-high row][z-low 4-column box][z-high 4-column box]
+template <typename T> constexpr int wrap_row_bytes() { return ((SROW * (int)sizeof(T) + 127) / 128) * 128; }
+template <typename T> constexpr int wrap_col_bytes() { return ((SROWS * 4 * (int)sizeof(T) + 127) / 128) * 128; }
+template <typename T, bool WRAP> constexpr int spmv_stage_bytes() { return tile_bytes<T>() + (WRAP ? 2 * wrap_row_bytes<T>() + 2 * wrap_col_bytes<T>() : 0); }
+template <typename T, bool WRAP = false> constexpr int star_spmv_smem() { return kSpStages * spmv_stage_bytes<T, WRAP>() + 8 * kSpStages + 128; }
 
 // DIAG: the diagonal coefficient is looked up per row through the pattern code of a coded star (coded.cuh, CodedView::star_diag)
-template <typename T, class Epi, bool UNIT, bool DIAG = false>
+// WRAP (with DIAG): some axes are PERIODIC (st.wrap): the neighbour across the boundary is the cell at the other end of the axis
+template <typename T, class Epi, bool UNIT, bool DIAG = false, bool WRAP = false>
 __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant__ CUtensorMap tm_x, StarDesc st, T* __restrict__ Y, int64_t ldy, int xchunk, Epi epi,
-                                                          StarDiag dg = StarDiag{}) {
+                                                          StarDiag dg, const __grid_constant__ CUtensorMap tm_row, const __grid_constant__ CUtensorMap tm_col) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int TB = tile_bytes<T>();
+    constexpr int TB = spmv_stage_bytes<T, WRAP>();          // bytes per stage (tile + wrap buffers)
+    constexpr int TILE = tile_bytes<T>(), WROW = wrap_row_bytes<T>(), WCOL = wrap_col_bytes<T>();
+    (void)TILE; (void)WROW; (void)WCOL;
     constexpr int S = kSpStages;
     constexpr uint32_t kTx = (uint32_t)(SROWS * SROW * sizeof(T));
     // 128-byte aligned start inside the dynamic window, by pointer arithmetic on the shared array (an integer round trip makes
@@ -461,12 +496,29 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
             const int jy = y0 + warp, jz = z0 + 4 * lane;
             const bool mine = jy < ny && jz < nz;
             const int P = (int)(x1 - x0) + 2;   // planes x0-1 .. x1
+            const int nxi = (int)st.nx;
+            const bool wrap_x = WRAP && (st.wrap & 1), wrap_y = WRAP && (st.wrap & 2), wrap_z = WRAP && (st.wrap & 4);
+            // PERIODIC y / z: tiles at the boundary of such an axis also fetch the row / the 4-column box from the other end of the axis into
+            // the stage's wrap buffers (the main tile holds zeros there), with the same TMA transaction barrier
+            const bool t_ylo = wrap_y && y0 == 0, t_yhi = wrap_y && y0 + SY >= ny, t_zlo = wrap_z && z0 == 0, t_zhi = wrap_z && z0 + SZ >= nz;
+            const uint32_t tx_bytes = kTx + (WRAP ? ((t_ylo ? 1u : 0u) + (t_yhi ? 1u : 0u)) * (uint32_t)(SROW * sizeof(T)) +
+                                                        ((t_zlo ? 1u : 0u) + (t_zhi ? 1u : 0u)) * (uint32_t)(SROWS * 4 * sizeof(T)) : 0u);
             auto issue = [&](int px) {
                 const uint32_t bar = smem_u32(&bars[issue_stg]);
-                mbar_expect_tx(bar, kTx);
-                tma_load_4d(smem_u32(base + (size_t)issue_stg * TB), &tm_x, bar, z0 - 4, y0 - 1, px, b);
+                mbar_expect_tx(bar, tx_bytes);
+                if (wrap_x) px = px < 0 ? px + nxi : (px >= nxi ? px - nxi : px);      // PERIODIC x: the plane before the first is the last one
+                unsigned char* stage = base + (size_t)issue_stg * TB;
+                tma_load_4d(smem_u32(stage), &tm_x, bar, z0 - 4, y0 - 1, px, b);
+                if constexpr (WRAP) {
+                    if (t_ylo) tma_load_4d(smem_u32(stage + TILE), &tm_row, bar, z0 - 4, (int)ny - 1, px, b);
+                    if (t_yhi) tma_load_4d(smem_u32(stage + TILE + WROW), &tm_row, bar, z0 - 4, 0, px, b);
+                    if (t_zlo) tma_load_4d(smem_u32(stage + TILE + 2 * WROW), &tm_col, bar, (int)nz - 4, y0 - 1, px, b);
+                    if (t_zhi) tma_load_4d(smem_u32(stage + TILE + 2 * WROW + WCOL), &tm_col, bar, 0, y0 - 1, px, b);
+                }
                 issue_stg = issue_stg + 1 == S ? 0 : issue_stg + 1;
             };
+            const bool wy_lo = wrap_y && mine && jy == 0, wy_hi = wrap_y && mine && jy == ny - 1;
+            const bool wz_lo = wrap_z && mine && jz == 0, wz_hi = wrap_z && mine && jz + 4 == nz;
             __syncthreads();   // every stage of the previous item has been consumed
             if (t == 0)
                 for (int k = 0; k < S && k < P; ++k) issue((int)x0 - 1 + k);
@@ -504,28 +556,47 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
                     const Quad<T>& xm = q_m;
                     const Quad<T>& xp = q_p;
                     Quad<T> out;
+                    unsigned wf_row = 0;                   // WRAP: wrapped neighbours of this step's output rows (see star_sum_wrapped)
+                    Quad<T> ymw = ym, ypw = yp;
+                    if constexpr (WRAP) {
+                        const int xo = (int)x0 + k - 2;    // output plane
+                        if (wrap_x && xo == 0) wf_row |= 1u;
+                        if (wrap_x && xo == nxi - 1) wf_row |= 2u;
+                        const unsigned char* stage_c = base + (size_t)s_c * TB;      // wrap buffers of the product plane
+                        if (wy_lo) { wf_row |= 4u; ymw = ld4<T>(reinterpret_cast<const T*>(stage_c + TILE) + c); }
+                        if (wy_hi) { wf_row |= 8u; ypw = ld4<T>(reinterpret_cast<const T*>(stage_c + TILE + WROW) + c); }
+                        if (wz_lo) left = reinterpret_cast<const T*>(stage_c + TILE + 2 * WROW)[sr * 4 + 3];
+                        if (wz_hi) right = reinterpret_cast<const T*>(stage_c + TILE + 2 * WROW + WCOL)[sr * 4];
+                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const T zm = e == 0 ? left : ce.v[e - 1];
                         const T zp = e == 3 ? right : ce.v[e + 1];
                         const T c0 = DIAG ? (cw_c == 0u ? c00 : s_c0[(cw_c >> (8 * e)) & 0xffu]) : c00;      // diagonal of this row
                         T sum;
-                        if constexpr (UNIT) {
-                            sum = -xm.v[e];
-                            sum = add_rn(sum, -ym.v[e]);
-                            sum = add_rn(sum, -zm);
-                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
-                            sum = add_rn(sum, -zp);
-                            sum = add_rn(sum, -yp.v[e]);
-                            sum = add_rn(sum, -xp.v[e]);
+                        // the seven terms (UNIT: the six neighbour coefficients are -1, c*v == -v exactly), then their sum in ascending column order
+                        const T txm = UNIT ? -xm.v[e] : mul_rn(cxm, xm.v[e]), txp = UNIT ? -xp.v[e] : mul_rn(cxp, xp.v[e]);
+                        const T tym = UNIT ? -ymw.v[e] : mul_rn(cym, ymw.v[e]), typ = UNIT ? -ypw.v[e] : mul_rn(cyp, ypw.v[e]);
+                        const T tzm = UNIT ? -zm : mul_rn(czm, zm), tzp = UNIT ? -zp : mul_rn(czp, zp), tc = mul_rn(c0, ce.v[e]);
+                        if (WRAP && wf_row != 0u) {           // rows on a PERIODIC x / y boundary (uniform over the warp, rare): general order
+                            const unsigned wf = wf_row | ((wz_lo && e == 0) ? 16u : 0u) | ((wz_hi && e == 3) ? 32u : 0u);
+                            sum = star_sum_wrapped<T>(wf, txm, txp, tym, typ, tzm, tzp, tc);
                         } else {
-                            sum = mul_rn(cxm, xm.v[e]);
-                            sum = add_rn(sum, mul_rn(cym, ym.v[e]));
-                            sum = add_rn(sum, mul_rn(czm, zm));
-                            sum = add_rn(sum, mul_rn(c0, ce.v[e]));
-                            sum = add_rn(sum, mul_rn(czp, zp));
-                            sum = add_rn(sum, mul_rn(cyp, yp.v[e]));
-                            sum = add_rn(sum, mul_rn(cxp, xp.v[e]));
+                            // a z neighbour across a PERIODIC boundary changes the order of the three middle terms only (selects, no divergence):
+                            // z- wrapped (first cell of a row): centre, z+, z- ; z+ wrapped (last cell): z+, z-, centre
+                            T a1 = tzm, a2 = tc, a3 = tzp;
+                            if constexpr (WRAP) {
+                                const bool wl = wz_lo && e == 0, wh = wz_hi && e == 3;
+                                a1 = wl ? tc : (wh ? tzp : tzm);
+                                a2 = wl ? tzp : (wh ? tzm : tc);
+                                a3 = wl ? tzm : (wh ? tc : tzp);
+                            }
+                            sum = add_rn(txm, tym);
+                            sum = add_rn(sum, a1);
+                            sum = add_rn(sum, a2);
+                            sum = add_rn(sum, a3);
+                            sum = add_rn(sum, typ);
+                            sum = add_rn(sum, txp);
                         }
                         out.v[e] = sum;
                     }
@@ -548,10 +619,11 @@ __global__ void __launch_bounds__(kBlock) k_star_spmv_tma(const __grid_constant_
     epilogue_tail(epi, acc, b, blockIdx.x, gridDim.x);
 }
 
-template <typename T, class Epi, bool UNIT, bool DIAG>
-int launch_star_spmv_tma_t(const CUtensorMap& tm, const StarDesc& st, T* Y, int64_t ldy, int batch, const Epi& epi, cudaStream_t stream, const StarDiag& dg) {
-    auto kernel = k_star_spmv_tma<T, Epi, UNIT, DIAG>;
-    constexpr int smem = star_spmv_smem<T>();
+template <typename T, class Epi, bool UNIT, bool DIAG, bool WRAP = false>
+int launch_star_spmv_tma_t(const CUtensorMap& tm, const StarDesc& st, T* Y, int64_t ldy, int batch, const Epi& epi, cudaStream_t stream, const StarDiag& dg,
+                           const CUtensorMap* tm_row = nullptr, const CUtensorMap* tm_col = nullptr) {
+    auto kernel = k_star_spmv_tma<T, Epi, UNIT, DIAG, WRAP>;
+    constexpr int smem = star_spmv_smem<T, WRAP>();
     static int occ_dev[kMaxDevices] = {};
     int& occ = occ_dev[device_slot()];
     if (occ == 0) {
@@ -563,18 +635,26 @@ int launch_star_spmv_tma_t(const CUtensorMap& tm, const StarDesc& st, T* Y, int6
     dim3 grid;
     int xchunk;
     star_grid_balanced(st, batch, occ, grid, xchunk);
-    PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi, dg);
+    PHB_LAUNCH(kernel, grid, kBlock, smem, stream, tm, st, Y, ldy, xchunk, epi, dg, tm_row ? *tm_row : tm, tm_col ? *tm_col : tm);
     return PHB200_OK;
 }
 
 // coded star with a per-row diagonal (dg != nullptr): the same kernel in its DIAG form
 template <typename T, class Epi>
-int launch_star_spmv_tma_diag(const StarDesc& st, const StarDiag& dg, const T* X, int64_t ldx, T* Y, int64_t ldy, int batch, int dtype, const Epi& epi, cudaStream_t stream, bool* used) {
+int launch_star_spmv_tma_diag(const StarDesc& st, StarDiag dg, const T* X, int64_t ldx, T* Y, int64_t ldy, int batch, int dtype, const Epi& epi, cudaStream_t stream, bool* used) {
     *used = false;
+    dg.x = X;
+    dg.ldx = ldx;
     CUtensorMap tm;
     if (!make_star_tmap(&tm, X, dtype, st, batch, ldx)) return PHB200_OK;
     const bool unit = st.cxm == -1.0 && st.cxp == -1.0 && st.cym == -1.0 && st.cyp == -1.0 && st.czm == -1.0 && st.czp == -1.0;
     *used = true;
+    if (st.wrap) {
+        CUtensorMap tm_row, tm_col;      // boxes of one row / of a 4-column strip: the neighbours across a PERIODIC boundary
+        if (!make_star_tmap(&tm_row, X, dtype, st, batch, ldx, SROW, 1) || !make_star_tmap(&tm_col, X, dtype, st, batch, ldx, 4, SROWS)) { *used = false; return PHB200_OK; }
+        return unit ? launch_star_spmv_tma_t<T, Epi, true, true, true>(tm, st, Y, ldy, batch, epi, stream, dg, &tm_row, &tm_col)
+                    : launch_star_spmv_tma_t<T, Epi, false, true, true>(tm, st, Y, ldy, batch, epi, stream, dg, &tm_row, &tm_col);
+    }
     return unit ? launch_star_spmv_tma_t<T, Epi, true, true>(tm, st, Y, ldy, batch, epi, stream, dg) : launch_star_spmv_tma_t<T, Epi, false, true>(tm, st, Y, ldy, batch, epi, stream, dg);
 }
 
