@@ -117,9 +117,11 @@ int phb200_shift_fill(int rank, const int64_t* grid, int nshifts, const int32_t*
  * products).  *out views the CSR arrays as well (they must stay alive) and owns its code / table arrays.  PHB200_ERR_NOT_STENCIL when the
  * matrix does not qualify (unsorted columns, too many offsets or patterns, non-square).  Synchronises stream. */
 int phb200_coded_from_csr(phb200_matrix** out, const phb200_matrix* csr, void* stream);
-/* number of offsets / patterns of a coded matrix; offsets (may be NULL) receives up to 16 flat offsets in ascending order; *star_diag = 1 if every
- * row is the interior star with the neighbours outside the grid cut off and only the diagonal differs (ZERO_GRADIENT-type boundaries): such matrices
- * run the fused TMA CG kernels with a per-row diagonal. */
+/* number of offsets / patterns of a coded matrix; offsets (may be NULL) receives up to 16 flat offsets in ascending order; *star_diag = 1 if the
+ * matrix is a STAR on a grid (centre + nearest neighbours per axis, rows of 16-byte aligned length) whose rows differ only at the boundary: a
+ * neighbour outside the grid is cut off (ZERO / ZERO_GRADIENT-type boundaries; the diagonal may differ per row) or, on a PERIODIC axis, sits at the
+ * other end of the axis — verified for every row.  Such matrices run the TMA-staged stencil product (diagonal looked up per row, wrap boxes for
+ * periodic axes) and, without periodic axes, the fused CG / CG-adaptive kernels. */
 int phb200_coded_info(const phb200_matrix* coded, int* n_offsets, int* n_patterns, int64_t* offsets, int* star_diag);
 
 /* Slab (row-partition) mode for multi-GPU solves of ONE system: the arrays span `grid[0]` planes (owned planes plus one

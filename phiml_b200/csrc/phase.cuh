@@ -38,6 +38,10 @@ struct PeerHalo {
     int64_t plane;     // elements per plane
     int64_t ld_lo, ld_hi;   // leading dimensions (elements per system) of the neighbours' arrays
 };
+// a phase functor that defines `per_index` gets the element's index: elem(e, acc, sc, i) (per-row table look-ups, e.g. the inverse diagonal
+// of a pattern-coded star through the row's code byte)
+template <class P, class = void> struct HasIndex : std::false_type {};
+template <class P> struct HasIndex<P, std::void_t<decltype(P::per_index)>> : std::true_type {};
 template <class P, class = void> struct HasPeer : std::false_type {};
 template <class P> struct HasPeer<P, std::void_t<decltype(std::declval<P>().peer)>> : std::true_type {};
 
@@ -122,7 +126,8 @@ __global__ void __launch_bounds__(kBlock) k_phase(P p, int64_t n, int64_t ld, in
                     T el[NA];
 #pragma unroll
                     for (int a = 0; a < NA; ++a) el[a] = e[u][a][l];
-                    p.elem(el, acc, sc);
+                    if constexpr (HasIndex<P>::value) p.elem(el, acc, sc, off + idx[u] + l);
+                    else p.elem(el, acc, sc);
 #pragma unroll
                     for (int a = 0; a < NA; ++a) e[u][a][l] = el[a];
                 }

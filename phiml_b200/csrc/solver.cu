@@ -292,6 +292,41 @@ struct CgResid : FBase {
     }
 };
 
+// The same second half for a pattern-coded star (coded.cuh, star_diag): Jacobi's inverse diagonal comes from the pattern table through the row's
+// code byte (N bytes of traffic instead of the N w of an inverse-diagonal vector).  The table values are the 1 / d the vector would hold.
+template <typename T>
+struct CgResidCoded : FBase {
+    static constexpr int NA = 2;   // r, q
+    static constexpr unsigned RMASK = 0b11u, WMASK = 0b01u, SHARED = 0u;
+    static constexpr int ND = 1;
+    static constexpr bool GLOBAL = true;
+    static constexpr bool per_index = true;
+    const void* v[NA];
+    const uint8_t* code;
+    const T* inv_tab;
+    int rules;
+    struct Scal { T alpha; T inv0; };
+    __device__ Scal load(int b) const { return Scal{(T)sys[b].s[S_ALPHA], inv_tab[0]}; }
+    __device__ void elem(T (&e)[NA], double (&acc)[1], const Scal& sc, int64_t i) const {
+        e[0] = add_rn(e[0], -mul_rn(sc.alpha, e[1]));
+        const unsigned c = code[i];
+        const T s = mul_rn(e[0], c == 0u ? sc.inv0 : __ldg(inv_tab + c));
+        acc[0] += (double)mul_rn(e[0], s);
+    }
+    __device__ void finalize(int b, const double (&tot)[1]) const {
+        Sys& s = sys[b];
+        if (freeze && !s.go) return;
+        const T dold = (T)s.s[S_DELTA], dnew = (T)tot[0];
+        s.s[S_DELTA] = (double)dnew;
+        s.s[S_BETA] = (double)safe_div(dnew, dold);
+        s.rsq = (double)dnew;
+    }
+    __device__ void finalize_all() const {
+        check_all<T>(*this, rules);
+        if (threadIdx.x == 0) glob->pass = glob->pass + 1;
+    }
+};
+
 // x += alpha d_cur for every system (pending update of the fused iteration), then alpha = 0
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_flush_x(T* __restrict__ X, const T* __restrict__ buf_a, const T* __restrict__ buf_b,
@@ -1160,6 +1195,11 @@ struct Run {
         const bool cg = s->method == PHB200_CG || (torch_on && s->method == PHB200_CG_TORCH && s->pre == PHB200_PRE_NONE && !s->totals);
         return cg && (star_stencil() || coded_star()) && !pre_applied(s->pre) && !cb_mode();
     }
+    static bool coded_resid() {      // PHB200_CODED_RESID=0: residual half of the coded fused CG with the inverse-diagonal vector (A/B)
+        static int v = -1;
+        if (v < 0) { const char* e = getenv("PHB200_CODED_RESID"); v = (e && e[0] == '0') ? 0 : 1; }
+        return v == 1;
+    }
     bool star_stencil() const { return s->A->kind == PHB200_MAT_STENCIL && s->A->is_star; }
     // pattern-coded star with a per-row diagonal (ZERO_GRADIENT-type boundaries): the fused kernels in their DIAG form, TMA path only
     bool coded_star() const { return s->A->kind == PHB200_MAT_CODED && s->A->coded.star_diag && s->A->is_star && s->A->star.wrap == 0 && !s->coded_star_off && !s->totals; }
@@ -1263,7 +1303,19 @@ struct Run {
         if (which & 1) l2_window() = win;
         int r = fused_first<PRE>(X, R);
         l2_window() = (which & 2) ? win : L2Window{nullptr, 0, 0.f};
-        if (r == PHB200_OK) r = phase_ordered(make_resid<PRE>(R), resid_order());
+        if (r == PHB200_OK) {
+            if (PRE == 1 && coded_star() && coded_resid()) {      // inverse diagonal from the pattern table (code byte per row) instead of the vector
+                CgResidCoded<T> u;
+                fill_base(u, s, false, frozen());
+                u.v[0] = R; u.v[1] = vec(1); u.code = s->A->coded.code; u.inv_tab = (const T*)s->A->coded.inv_tab; u.rules = rules();
+                u.defer = defer();
+                PhaseOrder o = resid_order();
+                o.keep_mask &= 0b11u; o.stream_mask &= 0b11u;
+                r = phase_ordered(u, o);
+            } else {
+                r = phase_ordered(make_resid<PRE>(R), resid_order());
+            }
+        }
         l2_window() = L2Window{nullptr, 0, 0.f};
         return r;
     }

@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
             const int jz_h = lane == 0 ? z0 - 1 : z0 + SZ;                  // halo column formed by lane 0 / 31
             const bool hcol_in = DINV && (lane == 0 || lane == 31) && jz_h >= 0 && jz_h < nz && jy < ny;
             const int64_t hcol_d = (int64_t)(jz_h - jz);
-            unsigned cw_c = 0, cw_p = 0, cwh_c = 0, cb_c = 0;               // own quad (this plane, previous plane), halo row, halo column
+            unsigned cw_c = 0, cwh_c = 0, cb_c = 0;                        // own quad, halo row, halo column (codes of the plane being formed)
+            T c0_p[4] = {c00, c00, c00, c00};                              // diagonals of the own quad of the previous plane (the product's rows)
             if constexpr (DIAG) {
                 if (x0 - 1 >= 0) {
                     if (mine) cw_c = *reinterpret_cast<const unsigned*>(dg.code + off);
@@ -319,8 +320,21 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 const Quad<T> rv = ld4<T>(&rt[sr][c]), dv = ld4<T>(&dt[sr][c]);
                 Quad<T> dn;
                 T hz_n = T(0);
+                // diagonal and inverse diagonal of the own quad: interior rows (code 0) take the constants, the others ONE look-up each under a branch
+                // that only boundary lanes enter; the diagonals travel to the next step's product in registers
+                T ci_q[4] = {cinv0, cinv0, cinv0, cinv0}, c0_q[4] = {c00, c00, c00, c00};
+                if constexpr (DIAG) {
+                    if (cw_c != 0u) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e], inv_of(cw_c, e));
+                        for (int e = 0; e < 4; ++e) {
+                            const unsigned cd = (cw_c >> (8 * e)) & 0xffu;
+                            c0_q[e] = s_c0[cd];
+                            if constexpr (DINV) ci_q[e] = s_inv[cd];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dn.v[e] = dir(rv.v[e], dv.v[e], DINV ? ci_q[e] : cinv);
                 st4(&pl[sr][c], dn);
                 if (owned) {
                     if (has(6)) st4_hint(d_new + off, dn, pol_of(6));
@@ -338,8 +352,15 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                     const int hr = warp == 0 ? 0 : SY + 1;
                     const Quad<T> rh = ld4<T>(&rt[hr][c]), dh = ld4<T>(&dt[hr][c]);
                     Quad<T> hn;
+                    T ci_h[4] = {cinv0, cinv0, cinv0, cinv0};
+                    if constexpr (DINV) {
+                        if (cwh_c != 0u) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e], inv_of(cwh_c, e));
+                            for (int e = 0; e < 4; ++e) ci_h[e] = s_inv[(cwh_c >> (8 * e)) & 0xffu];
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hn.v[e] = dir(rh.v[e], dh.v[e], DINV ? ci_h[e] : cinv);
                     st4(&pl[hr][c], hn);
                 }
                 if (lane == 0 || lane == 31) hz_n = dir(rt[sr][hcol], dt[sr][hcol], inv_of(cb_c, 0));   // halo columns of this row
@@ -362,7 +383,7 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                         for (int e = 0; e < 4; ++e) {
                             const T zm = e == 0 ? left : ce.v[e - 1];
                             const T zp = e == 3 ? right : ce.v[e + 1];
-                            const T c0 = DIAG ? (cw_p == 0u ? c00 : s_c0[(cw_p >> (8 * e)) & 0xffu]) : c00;      // diagonal of this row (plane k-1)
+                            const T c0 = DIAG ? c0_p[e] : c00;      // diagonal of this row (plane k-1)
                             T sum;
                             if constexpr (UNIT) {      // all six neighbour coefficients are -1: c*v == -v exactly, no multiply needed
                                 sum = -xm.v[e];
@@ -400,7 +421,9 @@ __global__ void __launch_bounds__(kBlock) k_star_cg_tma(const __grid_constant__ 
                 dn_m = dn_c;
                 dn_c = dn;
                 hz_c = hz_n;
-                cw_p = cw_c; cw_c = cw_n; cwh_c = cwh_n; cb_c = cb_n;
+                cw_c = cw_n; cwh_c = cwh_n; cb_c = cb_n;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c0_p[e] = c0_q[e];
                 pc_off = pl_off;   // rotate the ring: k -> k-1; the next plane takes the slot after k's (the slot of k-1 may still be read by slower warps)
                 pl_off = pl_off + TB == 4 * TB ? 0 : pl_off + TB;
             }

@@ -69,11 +69,13 @@ out['bit_identical'] = bool(torch.equal(ya, yb))
 y = torch.randn((1, N), device=dev)
 zero = torch.zeros(1, device=dev); mi = torch.full((1,), 2 ** 30, dtype=torch.int32, device=dev)
 for name, mat in (('coded', m.coded), ('csr', m)):
-    pre = pb.JacobiPreconditioner(m)
-    s = pb.DeviceSolver(mat, pre, E.CG, 0, 1)
-    s.start(y, torch.zeros_like(y), zero, zero, mi)
-    s.advance(20); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); s.advance(100); e1.record(); torch.cuda.synchronize()
-    out[name]['jacobi_cg_it_per_s'] = 100 / (e0.elapsed_time(e1) * 1e-3)
+    for tag, pre in (('jacobi_cg', pb.JacobiPreconditioner(m)), ('cg', None)):
+        s = pb.DeviceSolver(mat, pre, E.CG, 0, 1)
+        s.start(y, torch.zeros_like(y), zero, zero, mi)
+        s.advance(20); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); s.advance(100); e1.record(); torch.cuda.synchronize()
+        out[name][tag + '_it_per_s'] = 100 / (e0.elapsed_time(e1) * 1e-3)
+        s.profile(True); s.advance(40); prof = s.profile_read(); s.profile(False)
+        out[name][tag + '_kernels_us'] = [round(p[0] / max(p[1], 1) * 1e3, 1) for p in prof[:4]]
 print(json.dumps(out))
