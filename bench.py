@@ -657,7 +657,7 @@ def run_ours(args):
             big = args.big
             guarded("slab_1024", lambda: time_jacobi_cg(ctx, big, 5, 30)[0], configs, ctx)
             guarded("sharded_cfg3", lambda: time_cfg3(ctx), configs, ctx)
-            guarded("slab_cfg5", lambda: time_cfg5(ctx, big, 6), configs, ctx)
+            guarded("slab_cfg5", lambda: time_cfg5(ctx, big, 6 if world == 1 else 8), configs, ctx)
             if world == 1:
                 guarded("cfg4_ilu_256", lambda: time_cfg4(ctx, 256, 30), configs, ctx)
                 guarded("cfg4_ilu_512", lambda: time_cfg4(ctx, 512, 20), configs, ctx)
