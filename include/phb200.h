@@ -142,6 +142,14 @@ int phb200_spmv(const phb200_matrix* A, const void* X, void* Y, int64_t batch, i
 int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int64_t nnz, int64_t n_rows, int64_t n_cols,
                     const void* X, void* Y, int64_t batch, int64_t ldx, int64_t ldy, int dtype, void* stream);
 
+/* Batched CSR x dense product outside the solver — replaces Backend.mul_csr_dense (phiml/backend/_backend.py:1366-1387; torch
+ * _torch_backend.py:912-922 / numpy _numpy_backend.py:510-519: a Python loop over (batch, channel) pairs with one native matrix each;
+ * called from dot_compressed_dense, phiml/math/_sparse.py:1590) with ONE launch.  col (batch, nnz) int32, rowptr (batch, n_rows+1) int32,
+ * val (batch, nnz, channels), dense (batch, n_cols, channels, dense_cols) -> out (batch, n_rows, channels, dense_cols), all C-contiguous.
+ * Every output is summed over its row's entries in entry order with separately rounded products (SciPy's csr_matvecs, bit for bit). */
+int phb200_csr_dense_batched(const int32_t* col, const int32_t* rowptr, const void* val, const void* dense, void* out, int64_t batch, int64_t n_rows,
+                             int64_t n_cols, int64_t nnz, int64_t channels, int64_t dense_cols, int dtype, void* stream);
+
 /* CSR of A^T from the CSR of A (= reading the arrays of a CSC native, TorchBackend.csc_matrix _torch_backend.py:885-896, the layout the
  * backward solve receives, phiml/math/_optimize.py:823-833, as the plain CSR the solver kernels take).  Rows of the result are
  * sorted by column; values are moved, not changed.  t_rowptr: n_cols+1, t_col / t_val: nnz.  Temporaries (12 bytes per entry +

@@ -14,6 +14,8 @@ Each function names the reference lines it follows (paths relative to /root/refe
 * ``run_loop``            -> phiml/backend/_backend.py:697-735 (eager while_loop, non-trajectory branch)
 * ``matvec``              -> phiml/backend/_numpy_backend.py:282-283 (per-batch ``A.dot(b[i])``)
 * ``linear_solve``        -> phiml/backend/_backend.py:1460-1516 (method-string dispatch)
+* ``mul_csr_dense``       -> phiml/backend/_numpy_backend.py:510-519 (one SciPy product per (batch, channel) pair = csr_matvecs order)
+* ``mul_coo_dense``       -> phiml/backend/_backend.py:1303-1328 (gather, multiply, scatter-add; NumPy scatter = np.add.at, entry order)
 
 The arithmetic dtype is the dtype of ``y`` (float32 or float64); tolerances are cast to it like the
 reference does through ``backend.as_tensor`` of a float tensor.
@@ -61,6 +63,31 @@ def matvec(lin, v: np.ndarray) -> np.ndarray:
     if callable(lin):
         return lin(v)
     return np.stack([lin.dot(v[i]) for i in range(v.shape[0])])
+
+
+def mul_csr_dense(column_indices, row_pointers, values, shape, dense) -> np.ndarray:
+    """(batch, nnz), (batch, rows+1), (batch, nnz, channels), (batch, cols, channels, dense_cols) -> (batch, rows, channels, dense_cols).
+    Written out entry by entry: every output starts at 0 and receives `value * dense` of its row's entries in entry order (products and sums
+    rounded separately in the arithmetic dtype) — what SciPy's csr_matvecs does for `mat * dense[b, :, c, :]` (_numpy_backend.py:510-519)."""
+    batch, nnz, channels = values.shape
+    rows, cols = shape
+    out = np.zeros((batch, rows, channels, dense.shape[-1]), values.dtype)
+    for b in range(batch):
+        for r in range(rows):
+            for k in range(row_pointers[b, r], row_pointers[b, r + 1]):
+                out[b, r] += values[b, k][:, None] * dense[b, column_indices[b, k]]
+    return out
+
+
+def mul_coo_dense(indices, values, shape, dense) -> np.ndarray:
+    """(batch, nnz, 2), (batch, nnz, channels), (batch, cols, channels, dense_cols) -> (batch, rows, channels, dense_cols); entries added in entry
+    order, duplicates included (Backend.mul_coo_dense _backend.py:1303-1328 with NumPy's scatter, np.add.at, _numpy_backend.py:420)."""
+    batch, nnz, channels = values.shape
+    out = np.zeros((batch, shape[0], channels, dense.shape[-1]), values.dtype)
+    for b in range(batch):
+        for k in range(nnz):
+            out[b, indices[b, k, 0]] += values[b, k][:, None] * dense[b, indices[b, k, 1]]
+    return out
 
 
 def rowdot(a, b):

@@ -39,6 +39,7 @@ SIGNATURES = {
     'phb200_matrix_destroy': (c_int, [_P]),
     'phb200_spmv': (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P]),
     'phb200_spmv_coo': (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int, _P]),
+    'phb200_csr_dense_batched': (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, _P]),
     'phb200_csr_transpose': (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int, _P, _P, _P, _P]),
     'phb200_matrix_gradient_coo': (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_int, _P]),
     'phb200_matrix_gradient_csr': (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_int, _P]),

@@ -145,6 +145,31 @@ __global__ void __launch_bounds__(kBlock) k_spmv_coo(const int64_t* __restrict__
         atomicAdd(&Y[(int64_t)b * ldy + row[k]], val[k] * X[(int64_t)b * ldx + col[k]]);
 }
 
+// ---------------------------------------------------------------------------------------------- batched CSR x dense
+// `matrix @ x` outside the solver: Backend.mul_csr_dense (_backend.py:1366-1387; torch _torch_backend.py:912-922 builds one CSR tensor
+// per (batch, channel) pair in a Python double loop, numpy _numpy_backend.py:510-519 one SciPy matrix per pair).  ONE launch for the
+// whole (batch, rows, channels, dense_cols) result: a thread owns one output element, consecutive threads own consecutive (channel,
+// dense column) slots of a row and then consecutive rows, so the gathers of `dense` are contiguous over the inner width and the
+// index loads of a row are shared by its threads.  Every output is summed over its row's entries in entry order with separately
+// rounded products, starting from 0 — SciPy's csr_matvecs (y += a * x per entry), bit for bit, per (batch, channel, column).
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_csr_dense_batched(const int32_t* __restrict__ col, const int32_t* __restrict__ rowptr, const T* __restrict__ val,
+                                                              const T* __restrict__ dense, T* __restrict__ out, int64_t batch, int64_t rows, int64_t cols,
+                                                              int64_t nnz, int channels, int dcols) {
+    const int64_t width = (int64_t)channels * dcols, total = batch * rows * width;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < total; i += (int64_t)gridDim.x * kBlock) {
+        const int64_t t = i / width, v = i - t * width, b = t / rows, r = t - b * rows;
+        const int c = (int)(v / dcols);
+        const int32_t* __restrict__ rp = rowptr + b * (rows + 1);
+        const int32_t* __restrict__ cb = col + b * nnz;
+        const T* __restrict__ vb = val + b * nnz * channels + c;
+        const T* __restrict__ db = dense + b * cols * width + v;
+        T acc = T(0);
+        for (int k = rp[r], k1 = rp[r + 1]; k < k1; ++k) acc = add_rn(acc, mul_rn(vb[(int64_t)k * channels], db[(int64_t)cb[k] * width]));
+        out[i] = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- matrix gradient
 // Sampled outer product of the implicit-gradient step (phiml/math/_optimize.py:803-807):
 //   dm[k] = -sum_b dy[b,row[k]] * x[b,col[k]]     on the stored entries, batch summed in order, products rounded separately.
@@ -878,6 +903,21 @@ int phb200_spmv_coo(const int64_t* row, const int64_t* col, const void* val, int
     dim3 grid((unsigned)grid_x((nnz + kBlock - 1) / kBlock, batch), (unsigned)batch);
     if (dtype == PHB200_F32) PHB_LAUNCH(k_spmv_coo<float>, grid, kBlock, 0, stream, row, col, (const float*)val, nnz, (const float*)X, ldx, (float*)Y, ldy);
     else PHB_LAUNCH(k_spmv_coo<double>, grid, kBlock, 0, stream, row, col, (const double*)val, nnz, (const double*)X, ldx, (double*)Y, ldy);
+    return PHB200_OK;
+}
+
+int phb200_csr_dense_batched(const int32_t* col, const int32_t* rowptr, const void* val, const void* dense, void* out, int64_t batch, int64_t n_rows,
+                             int64_t n_cols, int64_t nnz, int64_t channels, int64_t dense_cols, int dtype, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PHB_ARG(batch >= 0 && n_rows >= 0 && n_cols >= 0 && nnz >= 0 && channels >= 0 && dense_cols >= 0, "negative size");
+    PHB_ARG(nnz <= 2147483647LL && channels <= 2147483647LL && dense_cols <= 2147483647LL, "CSR natives hold at most 2^31-1 entries (int32 pointers)");
+    PHB_ARG(dtype == PHB200_F32 || dtype == PHB200_F64, "bad dtype %d", dtype);
+    const int64_t total = batch * n_rows * channels * dense_cols;
+    if (total == 0) return PHB200_OK;
+    PHB_ARG(rowptr && out && (nnz == 0 || (col && val && dense)), "null argument");
+    dim3 grid((unsigned)grid_x((total + kBlock - 1) / kBlock, 1));
+    if (dtype == PHB200_F32) PHB_LAUNCH(k_csr_dense_batched<float>, grid, kBlock, 0, stream, col, rowptr, (const float*)val, (const float*)dense, (float*)out, batch, n_rows, n_cols, nnz, (int)channels, (int)dense_cols);
+    else PHB_LAUNCH(k_csr_dense_batched<double>, grid, kBlock, 0, stream, col, rowptr, (const double*)val, (const double*)dense, (double*)out, batch, n_rows, n_cols, nnz, (int)channels, (int)dense_cols);
     return PHB200_OK;
 }
 

@@ -372,6 +372,10 @@ def mul_csr_dense(column_indices, row_pointers, values, shape, dense) -> torch.T
     """
     column_indices (batch, nnz), row_pointers (batch, rows+1), values (batch, nnz, channels),
     dense (batch, cols, channels, dense_cols)  ->  (batch, rows, channels, dense_cols)
+
+    Mirrors `TorchBackend.mul_csr_dense` (phiml/backend/torch/_torch_backend.py:912-922).  The reference loops over (batch, channel) pairs in
+    Python and builds a native per pair; here ONE matrix with one channel runs on the solver's CSR product kernels and everything else is
+    one launch of `phb200_csr_dense_batched`.  Both sum a row's entries in entry order with separately rounded products (SciPy's order).
     """
     values, dense = torch.as_tensor(values), torch.as_tensor(dense)
     E.require_cuda(values, dense)
@@ -381,61 +385,77 @@ def mul_csr_dense(column_indices, row_pointers, values, shape, dense) -> torch.T
     row_pointers = torch.as_tensor(row_pointers, device=values.device)
     batch_size, nnz, channels = values.shape
     rows, cols = int(shape[0]), int(shape[1])
+    assert dense.shape[0] == batch_size and dense.shape[1] == cols and dense.shape[2] == channels, f"dense {tuple(dense.shape)} does not match values {tuple(values.shape)} and shape {shape}"
+    if batch_size == 1 and channels == 1:
+        m = Matrix.csr(row_pointers[0], column_indices[0], values[0, :, 0], (rows, cols))
+        return m.matvec(dense[0, :, 0, :].t().contiguous()).t()[None, :, None, :].contiguous()
+    return _csr_dense_batched(column_indices, row_pointers, values, dense, rows, cols)
+
+
+def _csr_dense_batched(column_indices: torch.Tensor, row_pointers: torch.Tensor, values: torch.Tensor, dense: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """All (batch, channel, dense column) products of `mul_csr_dense` / `mul_coo_dense` in one launch (include/phb200.h: phb200_csr_dense_batched)."""
+    batch_size, nnz, channels = values.shape
     dense_cols = dense.shape[-1]
-    out = torch.empty((batch_size, rows, channels, dense_cols), dtype=dt, device=values.device)
-    for b in range(batch_size):
-        for c in range(channels):
-            m = Matrix.csr(row_pointers[b], column_indices[b], values[b, :, c], (rows, cols))
-            out[b, :, c, :] = m.matvec(dense[b, :, c, :].t().contiguous()).t()
+    assert column_indices.shape[-1] == nnz and row_pointers.shape[-1] == rows + 1
+    col = column_indices.to(torch.int32).expand(batch_size, nnz).contiguous()
+    ptr = row_pointers.to(torch.int32).expand(batch_size, rows + 1).contiguous()
+    values, dense = values.contiguous(), dense.contiguous()
+    out = torch.empty((batch_size, rows, channels, dense_cols), dtype=values.dtype, device=values.device)
+    E.check(E.lib().phb200_csr_dense_batched(E.ptr(col), E.ptr(ptr), E.ptr(values), E.ptr(dense), E.ptr(out), batch_size, rows, cols, nnz, channels,
+                                              dense_cols, E.dtype_code(values.dtype), E.stream_ptr(values.device)))
     return out
 
 
 @E.on_operand_device
 def mul_coo_dense(indices, values, shape, dense) -> torch.Tensor:
-    """indices (batch, nnz, 2), values (batch, nnz, channels), dense (batch, cols, channels, dense_cols)."""
+    """
+    indices (batch, nnz, 2), values (batch, nnz, channels), dense (batch, cols, channels, dense_cols)  ->  (batch, rows, channels, dense_cols)
+
+    The reference scatters with atomics (`Backend.mul_coo_dense`, phiml/backend/_backend.py:1303-1328: gather, multiply, `scatter_add` — order
+    unspecified).  Here the entries are ordered by row ONCE per index array (stable sort: entry order kept inside a row, cached) and the product
+    runs on the CSR kernels — one launch for the whole batch: every row is summed sequentially in entry order, deterministic, duplicates included.
+    """
     values, dense = torch.as_tensor(values), torch.as_tensor(dense)
     E.require_cuda(values, dense)
     dt = _float_type(values, dense)
     values, dense = values.to(dt), dense.to(dt)
-    indices = torch.as_tensor(indices, device=values.device).to(torch.int64)
+    indices = torch.as_tensor(indices, device=values.device)
     batch_size, nnz, channels = values.shape
     rows, cols = int(shape[0]), int(shape[1])
-    dense_cols = dense.shape[-1]
     assert dense.shape[0] == batch_size and dense.shape[1] == cols and dense.shape[2] == channels
-    out = torch.empty((batch_size, rows, channels, dense_cols), dtype=dt, device=values.device)
-    for b in range(batch_size):
-        # The reference scatters with atomics (Backend.mul_coo_dense, _backend.py:1324-1326: order unspecified).  Here the entries are ordered by
-        # row ONCE per index array (stable sort: entry order kept inside a row, cached) and the product runs on the CSR kernels: every row is
-        # summed sequentially in entry order — deterministic, duplicates included.
-        rowptr, perm, col = _coo_row_order(indices[b], rows)
-        for c in range(channels):
-            val = values[b, :, c][perm].contiguous()
-            m = Matrix.csr(rowptr, col, val, (rows, cols))
-            out[b, :, c, :] = m.matvec(dense[b, :, c, :].t().contiguous()).t()
-    return out
+    rowptr, perm, col = _coo_row_order(indices, rows)
+    if perm.shape[0] != batch_size:
+        rowptr, perm, col = rowptr.expand(batch_size, -1), perm.expand(batch_size, -1), col.expand(batch_size, -1)
+    if batch_size == 1 and channels == 1:
+        m = Matrix.csr(rowptr[0], col[0], values[0, :, 0][perm[0]].contiguous(), (rows, cols))
+        return m.matvec(dense[0, :, 0, :].t().contiguous()).t()[None, :, None, :].contiguous()
+    ordered = torch.gather(values, 1, perm[:, :, None].expand(batch_size, nnz, channels))
+    return _csr_dense_batched(col, rowptr, ordered, dense, rows, cols)
 
 
 _COO_ORDER: 'dict' = {}
 
 
-def _coo_row_order(idx: torch.Tensor, rows: int):
-    """(rowptr int32, permutation, sorted columns int32) of a (nnz, 2) coordinate array; cached on the array's storage + version."""
-    key = (idx.data_ptr(), idx._version, tuple(idx.shape), rows, str(idx.device))
+def _coo_row_order(indices: torch.Tensor, rows: int):
+    """
+    (rowptr int32 (batch, rows+1), permutation int64 (batch, nnz), ordered columns int32 (batch, nnz)) of a (batch, nnz, 2) coordinate array:
+    entries ordered by row, entry order kept inside a row.  Cached on the caller's array (storage + version; the entry dies with the array).
+    """
+    key = (indices.data_ptr(), indices._version, tuple(indices.shape), str(indices.dtype), rows, str(indices.device))
     hit = _COO_ORDER.get(key)
-    if hit is not None and hit[0]() is not None:
+    if hit is not None and hit[0]() is indices:
         return hit[1]
     import weakref
-    row = idx[:, 0].contiguous()
-    _, perm = torch.sort(row, stable=True)
-    counts = torch.bincount(row, minlength=rows)
-    rowptr = torch.zeros(rows + 1, dtype=torch.int32, device=idx.device)
-    rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
-    col = idx[:, 1][perm].to(torch.int32).contiguous()
+    row = indices[:, :, 0].to(torch.int64)
+    row_sorted, perm = torch.sort(row, dim=1, stable=True)
+    bounds = torch.arange(rows + 1, device=indices.device, dtype=torch.int64)[None, :].expand(indices.shape[0], rows + 1).contiguous()
+    rowptr = torch.searchsorted(row_sorted.contiguous(), bounds).to(torch.int32)      # entries with a row index below r
+    col = torch.gather(indices[:, :, 1], 1, perm).to(torch.int32).contiguous()
     value = (rowptr, perm, col)
     if len(_COO_ORDER) >= 8:
         _COO_ORDER.pop(next(iter(_COO_ORDER)))
     try:
-        _COO_ORDER[key] = (weakref.ref(idx), value)
+        _COO_ORDER[key] = (weakref.ref(indices), value)
     except TypeError:
         pass
     return value

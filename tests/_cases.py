@@ -91,3 +91,39 @@ BOUNDARY_CASES = [   # (operator, grid, dtype, method, preconditioner, rtol, bat
 ]
 
 
+
+
+# `matrix @ x` outside the solver (tests/golden/dense.npz): Backend.mul_csr_dense / mul_coo_dense with a different matrix per batch entry.
+# rows with no entries, duplicated coordinates and entries in arbitrary order included.  The reference's mul_coo_dense multiplies
+# values (batch, nnz, channels) with gathered rows of width channels * dense_cols, so its COO cases need channels == 1 or dense_cols == 1.
+DENSE_CASES = {
+    'b3_c2_k4_f32': dict(batch=3, rows=37, cols=29, nnz=211, channels=2, dense_cols=4, dtype='float32', seed=11),
+    'b1_c1_k1_f64': dict(batch=1, rows=64, cols=64, nnz=300, channels=1, dense_cols=1, dtype='float64', seed=12),
+    'b2_c1_k3_f64': dict(batch=2, rows=50, cols=41, nnz=60, channels=1, dense_cols=3, dtype='float64', seed=13),
+    'b4_c3_k1_f32': dict(batch=4, rows=33, cols=47, nnz=400, channels=3, dense_cols=1, dtype='float32', seed=14),
+    'b1_c3_k2_f32': dict(batch=1, rows=19, cols=23, nnz=90, channels=3, dense_cols=2, dtype='float32', seed=15),
+    'b5_c1_k1_f32': dict(batch=5, rows=300, cols=300, nnz=2100, channels=1, dense_cols=1, dtype='float32', seed=16),
+}
+
+
+def dense_case_inputs(name: str):
+    """col (batch, nnz) int32, rowptr (batch, rows+1) int32 [CSR: ordered by row, columns ascending], coordinates (batch, nnz', 2) int64 [COO: the CSR
+    entries in a random order followed by 9 repeated coordinates], values for both forms, dense (batch, cols, channels, dense_cols)."""
+    c = DENSE_CASES[name]
+    rng = np.random.default_rng(c['seed'])
+    b, rows, cols, nnz, ch, k = c['batch'], c['rows'], c['cols'], c['nnz'], c['channels'], c['dense_cols']
+    col = np.empty((b, nnz), np.int32)
+    ptr = np.empty((b, rows + 1), np.int32)
+    coo = np.empty((b, nnz + 9, 2), np.int64)
+    for i in range(b):
+        flat = np.sort(rng.choice(rows * cols, nnz, replace=False))
+        r, cc = flat // cols, flat % cols
+        col[i] = cc
+        ptr[i] = np.searchsorted(r, np.arange(rows + 1))
+        order = rng.permutation(nnz)
+        coo[i, :nnz, 0], coo[i, :nnz, 1] = r[order], cc[order]
+        coo[i, nnz:] = coo[i, :9]
+    vals = rng.standard_normal((b, nnz, ch)).astype(c['dtype'])
+    coo_vals = rng.standard_normal((b, nnz + 9, ch)).astype(c['dtype'])
+    dense = rng.standard_normal((b, cols, ch, k)).astype(c['dtype'])
+    return col, ptr, vals, coo, coo_vals, dense

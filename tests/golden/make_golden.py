@@ -25,7 +25,7 @@ from phiml.math._optimize import factor_ilu                                    #
 from phiml.backend._backend import get_backend, Preconditioner                 # noqa: E402
 from phiml.backend import NUMPY                                                # noqa: E402
 
-from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES                   # noqa: E402
+from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs                   # noqa: E402
 
 warnings.filterwarnings('ignore')
 DIMS = 'xyz'
@@ -440,8 +440,21 @@ def golden_boundaries(out):
             print(key, csr.shape, csr.nnz, 'row lengths', np.unique(rows), 'sorted', csr.has_sorted_indices, 'zeros stored', int((csr.data == 0).sum()), r.method, r.iterations, r.converged)
 
 
+def golden_dense(out):
+    """`matrix @ x` outside the solver: NUMPY.mul_csr_dense (_numpy_backend.py:510-519) and Backend.mul_coo_dense (_backend.py:1303-1328; NumPy scatter =
+    np.add.at, i.e. entry order) on a different matrix per batch entry."""
+    for name, c in DENSE_CASES.items():
+        col, ptr, vals, coo, coo_vals, dense = dense_case_inputs(name)
+        shape = (c['rows'], c['cols'])
+        with math.precision(64 if c['dtype'] == 'float64' else 32):      # auto_cast follows the global precision, not the operands
+            out[f"dense/{name}/csr"] = NUMPY.mul_csr_dense(col, ptr, vals, shape, dense)
+            if c['channels'] == 1 or c['dense_cols'] == 1:
+                out[f"dense/{name}/coo"] = NUMPY.mul_coo_dense(coo, coo_vals, shape, dense)
+            assert out[f"dense/{name}/csr"].dtype == np.dtype(c['dtype'])
+
+
 def main():
-    groups = {'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}

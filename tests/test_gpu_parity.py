@@ -125,6 +125,56 @@ def test_mul_csr_dense_and_mul_coo_dense_shapes():
     np.testing.assert_allclose(a.cpu().numpy(), ref2, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('key', sorted(golden('dense').files))
+def test_products_outside_the_solver_match_reference(key):
+    """mul_csr_dense / mul_coo_dense with a different matrix per batch entry: ONE launch of phb200_csr_dense_batched (or the solver's CSR product for
+    one matrix with one channel), bit-identical to the reference's NumPy backend (tests/golden/dense.npz) — empty rows, shuffled and repeated coordinates."""
+    from _cases import DENSE_CASES, dense_case_inputs
+    _, name, form = key.split('/')
+    c = DENSE_CASES[name]
+    col, ptr, vals, coo, coo_vals, dense = dense_case_inputs(name)
+    shape = (c['rows'], c['cols'])
+    bk = pb.B200Backend(DEV)
+    ref = golden('dense')[key]
+    before = E.launch_count()
+    out = bk.mul_csr_dense(col, ptr, vals, shape, dense) if form == 'csr' else bk.mul_coo_dense(coo, coo_vals, shape, dense)
+    launches = E.launch_count() - before
+    assert out.dtype == (torch.float64 if c['dtype'] == 'float64' else torch.float32) and tuple(out.shape) == ref.shape
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    if c['batch'] * c['channels'] > 1:
+        assert launches == 1, f"{launches} launches for {c['batch']} x {c['channels']} (batch, channel) pairs"
+    if form == 'coo':      # the row order is computed once per coordinate array
+        from phiml_b200 import solve as S
+        idx = torch.as_tensor(coo, device=DEV)
+        first = S._coo_row_order(idx, c['rows'])
+        assert S._coo_row_order(idx, c['rows']) is first
+        idx[0, 0, 0] = idx[0, 1, 0]           # in-place change -> new version -> recomputed
+        assert S._coo_row_order(idx, c['rows']) is not first
+
+
+def test_batched_products_against_the_oracle_on_larger_inputs():
+    """Many (batch, channel, column) slots, indices shared across the batch (broadcast), int64 index arrays as PhiML hands them over."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(21)
+    csr = oracle_matrix('advdiff', (12, 10, 9), 'float32')
+    b, ch, k = 6, 2, 5
+    vals = rng.standard_normal((b, csr.nnz, ch)).astype(np.float32)
+    dense = rng.standard_normal((b, csr.shape[1], ch, k)).astype(np.float32)
+    ref = np.zeros((b, csr.shape[0], ch, k), np.float32)
+    for i in range(b):
+        for c in range(ch):
+            ref[i, :, c, :] = sp.csr_matrix((vals[i, :, c], csr.indices, csr.indptr), shape=csr.shape) @ dense[i, :, c, :]
+    bk = pb.B200Backend(DEV)
+    out = bk.mul_csr_dense(csr.indices[None].astype(np.int64), csr.indptr[None].astype(np.int64), vals, csr.shape, dense)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    coo = csr.tocoo()
+    out = bk.mul_coo_dense(np.stack([coo.row, coo.col], -1)[None].astype(np.int64), vals, csr.shape, dense)
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+    # empty operands
+    e = bk.mul_csr_dense(np.zeros((2, 0), np.int32), np.zeros((2, 5), np.int32), np.zeros((2, 0, 3), np.float32), (4, 7), dense[:2, :7, :1].repeat(3, 2))
+    assert tuple(e.shape) == (2, 4, 3, k) and not e.any()
+
+
 # --------------------------------------------------------------------------------------------------- stencil <-> CSR
 
 @pytest.mark.parametrize('key', sorted({k.rsplit('/', 1)[0] for k in golden('assembly').files}))
