@@ -331,7 +331,10 @@ int phb200_solver_option(phb200_solver* s, int option, int value, int* previous 
 /* *any_continue = 1 while at least one system is still iterating.  Synchronises the stream. */
 int phb200_solver_poll(phb200_solver* s, int* any_continue, void* stream);
 
-/* Device outputs, (batch,) each: iterations, function_evaluations int32; converged, diverged uint8. */
+/* Device outputs, (batch,) each: iterations, function_evaluations int32; converged, diverged uint8.
+ * PHB200_CG / PHB200_CG_ADAPTIVE (generic loops, phiml/backend/_linalg.py:52-128): systems that stopped on a non-finite residual norm while other
+ * systems of the batch went on iterating get X and R filled with NaN here — the reference's masked updates (step_size * continue_ = NaN * 0) do
+ * that on the next pass; the device loop skips stopped systems instead. */
 int phb200_solver_result(phb200_solver* s, int32_t* iterations, int32_t* function_evaluations,
                          uint8_t* converged, uint8_t* diverged, void* stream);
 /* loop passes executed so far (host counter), kernels launched by this solver */

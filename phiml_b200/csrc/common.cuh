@@ -151,6 +151,8 @@ struct Sys {
     int its, fev, go, conv, div, max_iter, pad0, pad1;
 };
 
+constexpr int kSlotYY = 11;   // Sys::s slot holding |y_b|^2 (S_YY in solver.cu)
+
 struct Glob {
     double tol_min;    // minimum squared tolerance over the batch (the (batch,batch) broadcast of stop_on_l2)
     double yy_sum;     // sum over the batch of |y_b|^2 (generic cg_adaptive / bicg: the reference's tolerance is relative to it)
@@ -350,7 +352,9 @@ __device__ __forceinline__ void progress_check(Sys* sys, Glob* g, int batch, boo
         bool div;
         if (first) {
             s->rsq0 = (double)rsq;
-            div = nonfin;
+            // generic loops: non-finite monitored value (stop_on_l2).  torch_sparse_cg(_adaptive) test x0 instead — any(~isfinite(x0)), _torch_backend.py:1362 —
+            // so a non-finite right-hand side does NOT stop the system (it iterates on NaNs up to max_iter); |r0|^2 non-finite while |y|^2 is finite = x0's doing
+            div = torch_rules ? (nonfin && isfinite(s->s[kSlotYY])) : nonfin;
         } else {
             T ratio = rsq / (T)s->rsq0;
             if (torch_rules) div = (ratio > T(100)) && s->its >= 8;

@@ -18,6 +18,7 @@ enum Slot {
     S_ALPHA = 0, S_BETA, S_DELTA, S_DQ, S_DR, S_RQ, S_RHO0, S_RHO1, S_OMEGA, S_RHOP, S_GAMMA, S_YY,
     S_TAU = 12, S_SIGMA = 17, S_GAM = 22, S_GAMP = 27, S_GAMPP = 32   // 5 entries each: poly_order <= 4
 };
+static_assert(S_YY == kSlotYY, "progress_check reads |y|^2 from this slot");
 
 enum Rules { RULES_GENERIC = 0, RULES_TORCH = 1 };
 
@@ -816,6 +817,30 @@ __global__ void k_collect(const Sys* __restrict__ sys, int batch, int32_t* its, 
     if (fev) fev[b] = sys[b].fev;
     if (conv) conv[b] = (uint8_t)sys[b].conv;
     if (div) div[b] = (uint8_t)sys[b].div;
+}
+
+// Generic cg / cg_adaptive (phiml/backend/_linalg.py:52-128): a system that stopped on a NON-FINITE monitored value (NaN / Inf in y or x0, overflow)
+// is not left alone by the reference while other systems of the batch keep the loop alive — its step size is divide_no_nan(delta, dx.dy) * continue_
+// = (non-finite) * 0 = NaN (:74-77, :112-114), so x += step_size * dx and residual -= step_size * dy turn the whole system NaN on the very next pass.
+// The device loop skips stopped systems; this kernel writes the NaNs the reference would have produced (rows [off, off + n) of system blockIdx.y).
+template <typename T>
+__global__ void __launch_bounds__(256) k_poison_nonfinite(const Sys* __restrict__ sys, int batch, T* __restrict__ X, T* __restrict__ R, int64_t ld, int64_t off, int64_t n) {
+    const int b = blockIdx.y;
+    const Sys& me = sys[b];
+    if (!me.div || isfinite(me.rsq)) return;
+    __shared__ int s_more;
+    if (threadIdx.x == 0) s_more = 0;
+    __syncthreads();
+    int more = 0;
+    for (int k = threadIdx.x; k < batch; k += blockDim.x) more |= sys[k].its > me.its ? 1 : 0;      // did the loop make another pass after this system stopped?
+    if (more) atomicOr(&s_more, 1);
+    __syncthreads();
+    if (!s_more) return;
+    const T nan = (T)NAN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        X[(int64_t)b * ld + off + i] = nan;
+        R[(int64_t)b * ld + off + i] = nan;
+    }
 }
 
 template <typename T>
@@ -2215,6 +2240,13 @@ int phb200_solver_result(phb200_solver* s, int32_t* iterations, int32_t* functio
     cudaStream_t st = (cudaStream_t)stream_;
     PHB_ARG(s && s->started, "solver not started");
     PHB_LAUNCH(k_collect, (unsigned)((s->batch + 255) / 256), 256, 0, st, s->sys, (int)s->batch, iterations, function_evaluations, converged, diverged);
+    if ((s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE) && s->batch > 1 && s->X && s->R && s->n_act > 0) {
+        // stopped systems with a non-finite residual norm: the NaNs the reference's masked updates produce while the rest of the batch iterates
+        const unsigned gx = (unsigned)std::min<int64_t>((s->n_act + 255) / 256, 64);
+        dim3 grid(gx, (unsigned)s->batch);
+        if (s->dtype == PHB200_F32) PHB_LAUNCH(k_poison_nonfinite<float>, grid, 256, 0, st, s->sys, (int)s->batch, (float*)s->X, (float*)s->R, s->n, s->off, s->n_act);
+        else PHB_LAUNCH(k_poison_nonfinite<double>, grid, 256, 0, st, s->sys, (int)s->batch, (double*)s->X, (double*)s->R, s->n, s->off, s->n_act);
+    }
     return PHB200_OK;
 }
 

@@ -267,7 +267,9 @@ def _run_slab(code, poly_order, matrix, y, x0, rtol, atol, max_iter, pre):
     # --- trajectory recording (Backend.while_loop with a list of checkpoints, _backend.py:722-735) ---
     assert np.all(max_iter == max_iter[:, :1]), "When recording a trajectory, max_iter must be equal for all batch entries"
     checkpoints = max_iter[:, 0].tolist()
-    snap = lambda: (solver.x.clone(), solver.r.clone(), *solver.result())
+    def snap():
+        flags = solver.result()       # first: result() also writes the NaNs of systems that stopped on a non-finite residual (include/phb200.h)
+        return (solver.x.clone(), solver.r.clone(), *flags)
     trj = [snap()] if 0 in checkpoints else []
     for i in range(1, max(checkpoints) + 1):
         solver.advance(1)

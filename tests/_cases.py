@@ -127,3 +127,51 @@ def dense_case_inputs(name: str):
     coo_vals = rng.standard_normal((b, nnz + 9, ch)).astype(c['dtype'])
     dense = rng.standard_normal((b, cols, ch, k)).astype(c['dtype'])
     return col, ptr, vals, coo, coo_vals, dense
+
+
+# Edge inputs of Backend.linear_solve (tests/golden/edges.npz, recorded from the reference): zero / non-finite right-hand sides, iteration limits of
+# 0 and 1, per-system limits and tolerances, zero tolerances, warm starts, loose absolute tolerances, 1- and 2-cell systems.
+def _e(method, backend='numpy', op='poisson', grid=(7, 6), dtype='float32', batch=2, seed=31, y='random', x0='zero', rtol=1e-5, atol=0.0, max_iter=1000, pre=None):
+    return dict(method=method, backend=backend, op=op, grid=grid, dtype=dtype, batch=batch, seed=seed, y=y, x0=x0, rtol=rtol, atol=atol, max_iter=max_iter, pre=pre)
+
+
+EDGE_CASES = {}
+for _m, _b in [('CG', 'numpy'), ('CG-adaptive', 'numpy'), ('biCG-stab(1)', 'numpy'), ('biCG-stab(2)', 'numpy'), ('CG', 'torch'), ('auto', 'torch')]:
+    _t = f"{_m}_{_b}".replace('(', '').replace(')', '').replace('-', '')
+    _op = 'advdiff' if _m.startswith('biCG') else 'poisson'
+    _g = (5, 4, 6) if _m.startswith('biCG') else (7, 6)
+    EDGE_CASES[f"zero_rhs/{_t}"] = _e(_m, _b, _op, _g, y='zero')
+    EDGE_CASES[f"nan_rhs/{_t}"] = _e(_m, _b, _op, _g, batch=3, y='nan_row1')
+    EDGE_CASES[f"inf_rhs/{_t}"] = _e(_m, _b, _op, _g, batch=2, y='inf_row0')
+    EDGE_CASES[f"max_iter_0/{_t}"] = _e(_m, _b, _op, _g, max_iter=0)
+    EDGE_CASES[f"max_iter_1/{_t}"] = _e(_m, _b, _op, _g, max_iter=1)
+    EDGE_CASES[f"per_system/{_t}"] = _e(_m, _b, _op, _g, rtol=(1e-2, 1e-6), max_iter=(3, 1000))
+    EDGE_CASES[f"zero_tol/{_t}"] = _e(_m, _b, _op, _g, rtol=0.0, atol=0.0, max_iter=7)
+    EDGE_CASES[f"warm_start/{_t}"] = _e(_m, _b, _op, _g, x0='random', dtype='float64', rtol=1e-10)
+    EDGE_CASES[f"loose_atol/{_t}"] = _e(_m, _b, _op, _g, atol=1e3)
+    EDGE_CASES[f"one_cell/{_t}"] = _e(_m, _b, 'poisson', (1,), batch=2)
+    EDGE_CASES[f"two_cells/{_t}"] = _e(_m, _b, 'poisson', (2,), batch=1, dtype='float64', rtol=1e-10)
+    if _b == 'numpy' and not _m.startswith('CG-adaptive'):
+        EDGE_CASES[f"jacobi_zero_rhs/{_t}"] = _e(_m, _b, _op, _g, y='zero_row0', batch=2, pre='jacobi')
+
+
+def edge_case_inputs(name: str, n: int):
+    """y, x0 (batch, n), rtol, atol (batch,), max_iter (1, batch) of an edge case for a matrix with n rows."""
+    c = EDGE_CASES[name]
+    rng = np.random.default_rng(c['seed'])
+    nb = c['batch']
+    y = rng.standard_normal((nb, n))
+    x0 = rng.standard_normal((nb, n)) if c['x0'] == 'random' else np.zeros((nb, n))
+    if c['y'] == 'zero':
+        y[:] = 0
+    elif c['y'] == 'zero_row0':
+        y[0] = 0
+    elif c['y'] == 'nan_row1':
+        y[1, n // 2] = np.nan
+    elif c['y'] == 'inf_row0':
+        y[0, 0] = np.inf
+    dt = np.dtype(c['dtype']).type
+    rtol = np.broadcast_to(np.asarray(c['rtol'], dt), (nb,)).copy()
+    atol = np.broadcast_to(np.asarray(c['atol'], dt), (nb,)).copy()
+    max_iter = np.broadcast_to(np.asarray(c['max_iter']), (1, nb)).copy()
+    return y.astype(dt), x0.astype(dt), rtol, atol, max_iter

@@ -25,7 +25,7 @@ from phiml.math._optimize import factor_ilu                                    #
 from phiml.backend._backend import get_backend, Preconditioner                 # noqa: E402
 from phiml.backend import NUMPY                                                # noqa: E402
 
-from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs                   # noqa: E402
+from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs, EDGE_CASES, edge_case_inputs                   # noqa: E402
 
 warnings.filterwarnings('ignore')
 DIMS = 'xyz'
@@ -453,8 +453,32 @@ def golden_dense(out):
             assert out[f"dense/{name}/csr"].dtype == np.dtype(c['dtype'])
 
 
+def golden_edges(out):
+    """Edge inputs through the reference's Backend.linear_solve (NumPy backend = generic loops; torch backend on the CPU = torch_sparse_cg rules)."""
+    for name, c in EDGE_CASES.items():
+        dtype = np.dtype(c['dtype']).type
+        _, csr, _, _ = build(c['op'], c['grid'], dtype)
+        y, x0, rtol, atol, max_iter = edge_case_inputs(name, csr.shape[0])
+        backend = get_backend(c['backend'])
+        pre = RefJacobi(csr) if c['pre'] == 'jacobi' else None
+        with math.precision(64 if dtype == np.float64 else 32), np.errstate(all='ignore'):
+            if backend.name == 'torch':
+                import torch
+                lin = torch.sparse_csr_tensor(torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data), csr.shape)
+                args = [torch.as_tensor(a) for a in (y, x0, rtol, atol)]
+            else:
+                lin, args = csr, [y, x0, rtol, atol]
+            with backend:
+                ret = backend.linear_solve(c['method'], lin, *args, max_iter, pre, None)
+        key = f"edge/{name}"
+        out[key + '/method'] = ret.method
+        for f in ('x', 'residual', 'iterations', 'function_evaluations', 'converged', 'diverged'):
+            out[f"{key}/{f}"] = backend.numpy(getattr(ret, f))
+        print(key, ret.method, out[key + '/iterations'], out[key + '/function_evaluations'], out[key + '/converged'], out[key + '/diverged'])
+
+
 def main():
-    groups = {'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}

@@ -433,6 +433,58 @@ def test_reference_known_answers():
         pb.linear_solve('no-such-method', nat, one, torch.zeros_like(one), [1e-5], [0], np.array([[10]]), None, None)
 
 
+EDGE_NAMES = sorted({k.split('/', 1)[1].rsplit('/', 1)[0] for k in golden('edges').files})
+
+
+@pytest.mark.parametrize('use_stencil', [True, False], ids=['stencil', 'csr'])
+@pytest.mark.parametrize('name', EDGE_NAMES)
+def test_edge_inputs_match_reference(name, use_stencil):
+    """Zero / NaN / Inf right-hand sides, iteration limits 0 and 1, per-system limits and tolerances, zero tolerances, warm starts, loose absolute
+    tolerances, 1- and 2-cell systems (tests/golden/edges.npz, recorded from the reference's NumPy and torch backends): flags and counters as the
+    reference reports them — exactly where the limit or the input decides them, +-2 iterations where rounding does."""
+    from _cases import EDGE_CASES, edge_case_inputs
+    g = golden('edges')
+    c = EDGE_CASES[name]
+    csr = oracle_matrix(c['op'], c['grid'], c['dtype'])
+    y, x0, rtol, atol, max_iter = edge_case_inputs(name, csr.shape[0])
+    m = pb.as_matrix(dev_csr(csr))
+    if use_stencil and m.stencil is None:
+        pytest.skip("no stencil form (fewer cells than the stencil has points)")
+    if not use_stencil:
+        m.stencil = None
+    yd, x0d = torch.as_tensor(y, device=DEV), torch.as_tensor(x0, device=DEV)
+    keep = x0d.clone()
+    pre = pb.JacobiPreconditioner(m) if c['pre'] == 'jacobi' else None
+    if c['backend'] == 'numpy' and c['method'] == 'CG':      # generic rules
+        res = pb.generic_conjugate_gradient(m, yd, x0d, rtol, atol, max_iter, pre)
+    elif c['backend'] == 'numpy' and c['method'] == 'CG-adaptive':
+        res = pb.generic_conjugate_gradient_adaptive(m, yd, x0d, rtol, atol, max_iter)
+    else:
+        res = pb.linear_solve(c['method'], m, yd, x0d, rtol, atol, max_iter, pre, None)
+    assert torch.equal(x0d, keep)
+    key = f"edge/{name}"
+    ref_it, ref_fe = g[key + '/iterations'].astype(int), g[key + '/function_evaluations'].astype(int)
+    its, fev = res.iterations.cpu().numpy().astype(int), res.function_evaluations.cpu().numpy().astype(int)
+    np.testing.assert_array_equal(res.converged.cpu().numpy(), g[key + '/converged'])
+    np.testing.assert_array_equal(res.diverged.cpu().numpy(), g[key + '/diverged'])
+    decided = name.split('/')[0] in ('zero_rhs', 'max_iter_0', 'max_iter_1', 'zero_tol', 'loose_atol', 'one_cell', 'two_cells', 'jacobi_zero_rhs', 'nan_rhs', 'inf_rhs')
+    if name == 'jacobi_zero_rhs/CG_numpy':
+        decided = False      # the zero system makes the batch-wide tolerance 0: the other system stops when its delta underflows to exactly 0 (60 iterations in NumPy's rounding)
+    per_it = 2 * int(c['method'][-2]) if c['method'].startswith('biCG-stab(') else 1
+    it_tol = 0 if decided else 2
+    assert np.max(np.abs(its - ref_it)) <= it_tol, f"iterations {its} vs reference {ref_it}"
+    assert np.max(np.abs(fev - ref_fe)) <= it_tol * per_it + (0 if decided else 1), f"function evaluations {fev} vs reference {ref_fe}"
+    x, ref_x = res.x.cpu().numpy(), g[key + '/x']
+    np.testing.assert_array_equal(np.isfinite(x), np.isfinite(ref_x))
+    ok = np.isfinite(ref_x)
+    tol = 1e-10 if c['dtype'] == 'float64' else 1e-5
+    if not np.array_equal(its, ref_it):
+        tol = max(tol, 30 * float(np.max(rtol)))
+    scale = np.maximum(np.max(np.abs(np.where(ok, ref_x, 0)), axis=-1, keepdims=True), 1e-30)
+    conv = g[key + '/converged'][:, None] | (ref_it[:, None] == its[:, None])
+    assert np.all(np.abs(np.where(ok & conv, x - ref_x, 0)) <= 50 * tol * scale)
+
+
 def test_singular_system_is_reported_not_raised():
     """tests/commit/math/test__optimize.py:128-143: CG on a singular 2-cell Laplace must not converge; numerical failure
     is reported through the flags (SolveInfo turns it into Diverged/NotConverged)."""
