@@ -11,7 +11,7 @@ Each function names the reference lines it follows (paths relative to /root/refe
 * ``bicgstab_1``          -> phiml/backend/_linalg.py:227-274 (classic BiCGstab with shadow residual = ones)
 * ``torch_fastpath_cg``   -> phiml/backend/torch/_torch_backend.py:932-946,1353-1382
 * ``torch_fastpath_cg_adaptive`` -> phiml/backend/torch/_torch_backend.py:948-963,1385-1413
-* ``run_loop``            -> phiml/backend/_backend.py:697-735 (eager while_loop, non-trajectory branch)
+* ``run_loop``            -> phiml/backend/_backend.py:697-735 (eager while_loop, both branches)
 * ``matvec``              -> phiml/backend/_numpy_backend.py:282-283 (per-batch ``A.dot(b[i])``)
 * ``linear_solve``        -> phiml/backend/_backend.py:1460-1516 (method-string dispatch)
 * ``mul_csr_dense``       -> phiml/backend/_numpy_backend.py:510-519 (one SciPy product per (batch, channel) pair = csr_matvecs order)
@@ -123,14 +123,28 @@ class StopOnL2:
         return go_on, converged, diverged
 
 
-def loop_limit(max_iter: np.ndarray) -> int:
-    """_linalg.py:43-49 for the single-checkpoint case."""
-    assert max_iter.shape[0] == 1, "the oracle restates the non-trajectory branch only"
-    return int(np.max(max_iter))
+def loop_limit(max_iter: np.ndarray):
+    """_linalg.py:43-49: the largest limit for one row of limits, the list of checkpoints (equal for all systems) for several."""
+    if max_iter.shape[0] == 1:
+        return int(np.max(max_iter))
+    assert np.all(max_iter == max_iter[:, :1]), "When recording a trajectory, max_iter must be equal for all batch entries"
+    return max_iter[:, 0].tolist()
 
 
-def run_loop(body: Callable, state: tuple, limit: int) -> tuple:
-    """Eager loop of Backend.while_loop: test ``any(continue)`` *before* each body evaluation."""
+def run_loop(body: Callable, state: tuple, limit) -> tuple:
+    """Backend.while_loop (_backend.py:697-735).  One limit: eager loop that tests ``any(continue)`` *before* each body evaluation.  A list of
+    checkpoints: the body runs BEFORE the first test, copies are recorded at the checkpoints reached (a repeated checkpoint is recorded once), the
+    loop breaks after the pass that left nothing to continue, and the missing records are filled with the LAST RECORDED one (:726-732)."""
+    if isinstance(limit, list):
+        trj = [state] if 0 in limit else []
+        for i in range(1, max(limit) + 1):
+            state = body(*state)
+            if i in limit:
+                trj.append(state)
+            if not np.any(state[0]):
+                break
+        trj.extend([trj[-1]] * (len(limit) - len(trj)))
+        return tuple(np.stack([np.asarray(t[k]) for t in trj]) for k in range(len(state)))
     for _ in range(limit):
         if not np.any(state[0]):
             break

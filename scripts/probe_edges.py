@@ -22,7 +22,7 @@ for name, c in EDGE_CASES.items():
         if not use_stencil:
             m.stencil = None
         yd, x0d = torch.as_tensor(y, device=DEV), torch.as_tensor(x0, device=DEV)
-        pre = pb.JacobiPreconditioner(m) if c['pre'] == 'jacobi' else None
+        pre = pb.compute_preconditioner(c['pre'], m)
         if c['backend'] == 'numpy' and c['method'] == 'CG':
             res = pb.generic_conjugate_gradient(m, yd, x0d, rtol, atol, max_iter, pre)
         elif c['backend'] == 'numpy' and c['method'] == 'CG-adaptive':

@@ -155,6 +155,27 @@ for _m, _b in [('CG', 'numpy'), ('CG-adaptive', 'numpy'), ('biCG-stab(1)', 'nump
         EDGE_CASES[f"jacobi_zero_rhs/{_t}"] = _e(_m, _b, _op, _g, y='zero_row0', batch=2, pre='jacobi')
 
 
+# second group: checkpoint lists (Backend.while_loop's trajectory branch), ILU-preconditioned loops and BiCGstab(3 / 4) on edge inputs
+for _m, _b in [('CG', 'numpy'), ('CG', 'torch'), ('CG-adaptive', 'numpy'), ('biCG-stab(1)', 'numpy'), ('biCG-stab(2)', 'numpy')]:
+    _t = f"{_m}_{_b}".replace('(', '').replace(')', '').replace('-', '')
+    _op = 'advdiff' if _m.startswith('biCG') else 'poisson'
+    _g = (5, 4, 6) if _m.startswith('biCG') else (7, 6)
+    EDGE_CASES[f"traj_repeated_checkpoints/{_t}"] = _e(_m, _b, _op, _g, rtol=(1e-1, 1e-6), max_iter=[[0, 0], [3, 3], [3, 3], [7, 7], [200, 200]])
+    EDGE_CASES[f"traj_late_start/{_t}"] = _e(_m, _b, _op, _g, dtype='float64', rtol=1e-10, max_iter=[[4, 4], [9, 9], [1000, 1000]])
+    EDGE_CASES[f"traj_zero_rhs_row/{_t}"] = _e(_m, _b, _op, _g, y='zero_row0', atol=1e-6, max_iter=[[0, 0], [1, 1], [2, 2], [100, 100]])
+for _m in ('CG', 'biCG-stab(1)', 'biCG-stab(2)'):
+    _t = f"{_m}_numpy".replace('(', '').replace(')', '').replace('-', '')
+    _op = 'advdiff' if _m.startswith('biCG') else 'poisson'
+    EDGE_CASES[f"ilu_zero_rhs_row/{_t}"] = _e(_m, 'numpy', _op, (5, 4, 6), y='zero_row0', atol=1e-7, pre='ilu')
+    EDGE_CASES[f"ilu_max_iter_1/{_t}"] = _e(_m, 'numpy', _op, (5, 4, 6), max_iter=1, pre='ilu')
+    EDGE_CASES[f"ilu_nan_rhs/{_t}"] = _e(_m, 'numpy', _op, (5, 4, 6), batch=3, y='nan_row1', pre='ilu', max_iter=30)
+for _m in ('biCG-stab(3)', 'biCG-stab(4)'):
+    _t = f"{_m}_numpy".replace('(', '').replace(')', '').replace('-', '')
+    EDGE_CASES[f"zero_tol/{_t}"] = _e(_m, 'numpy', 'advdiff', (5, 4, 6), rtol=0.0, atol=0.0, max_iter=3)
+    EDGE_CASES[f"zero_rhs/{_t}"] = _e(_m, 'numpy', 'advdiff', (5, 4, 6), y='zero')
+    EDGE_CASES[f"max_iter_0/{_t}"] = _e(_m, 'numpy', 'advdiff', (5, 4, 6), max_iter=0)
+
+
 def edge_case_inputs(name: str, n: int):
     """y, x0 (batch, n), rtol, atol (batch,), max_iter (1, batch) of an edge case for a matrix with n rows."""
     c = EDGE_CASES[name]
@@ -173,5 +194,6 @@ def edge_case_inputs(name: str, n: int):
     dt = np.dtype(c['dtype']).type
     rtol = np.broadcast_to(np.asarray(c['rtol'], dt), (nb,)).copy()
     atol = np.broadcast_to(np.asarray(c['atol'], dt), (nb,)).copy()
-    max_iter = np.broadcast_to(np.asarray(c['max_iter']), (1, nb)).copy()
+    mi = np.asarray(c['max_iter'])
+    max_iter = mi.copy() if mi.ndim == 2 else np.broadcast_to(mi, (1, nb)).copy()
     return y.astype(dt), x0.astype(dt), rtol, atol, max_iter

@@ -457,11 +457,14 @@ def golden_edges(out):
     """Edge inputs through the reference's Backend.linear_solve (NumPy backend = generic loops; torch backend on the CPU = torch_sparse_cg rules)."""
     for name, c in EDGE_CASES.items():
         dtype = np.dtype(c['dtype']).type
-        _, csr, _, _ = build(c['op'], c['grid'], dtype)
+        m, csr, _, _ = build(c['op'], c['grid'], dtype)
         y, x0, rtol, atol, max_iter = edge_case_inputs(name, csr.shape[0])
         backend = get_backend(c['backend'])
         pre = RefJacobi(csr) if c['pre'] == 'jacobi' else None
         with math.precision(64 if dtype == np.float64 else 32), np.errstate(all='ignore'):
+            if c['pre'] == 'ilu':
+                from phiml.math._optimize import compute_preconditioner
+                pre = compute_preconditioner('ilu', m, 0, NUMPY, c['method'])
             if backend.name == 'torch':
                 import torch
                 lin = torch.sparse_csr_tensor(torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data), csr.shape)
