@@ -11,7 +11,7 @@
 // so a product moves N + 2 N w bytes (9 N for fp32) — the matrix has become one byte per row.
 //
 // Recognition happens on the device from the CSR native (three passes over the arrays, set-up only):
-//   k_coded_scan    every row: offsets must ascend (sorted columns), <= 16 entries; the distinct offsets go into a 64-slot set,
+//   k_coded_scan    every row: offsets must ascend (sorted columns), <= 16 entries, no stored zeros; the distinct offsets go into a 64-slot set,
 //                   a 64-bit hash of the row's (offset, value bits) sequence into a 1024-slot set together with the smallest row
 //                   index that shows it (CTA-local sets in shared memory first, merged once per CTA);
 //   k_coded_table   one thread per pattern copies its representative row into the table;
@@ -55,6 +55,7 @@ __device__ __forceinline__ unsigned long long coded_row_hash(const CsrView& A, i
     for (int k = k0; k < k1 && k < k0 + kMaxStencil; ++k) {
         const long long d = (long long)A.col[k] - (long long)i;
         if (d <= prev) ok = false;                  // unsorted or duplicate columns: the CSR product order is not the offset order
+        if (val[k] == T(0)) ok = false;             // a STORED zero still multiplies its x (0 * Inf = NaN in the CSR product); the table's 0 means "no entry"
         prev = d;
         h = coded_mix(h, (unsigned long long)d);
         h = coded_mix(h, coded_bits<T>(val[k]));

@@ -197,3 +197,69 @@ def edge_case_inputs(name: str, n: int):
     mi = np.asarray(c['max_iter'])
     max_iter = mi.copy() if mi.ndim == 2 else np.broadcast_to(mi, (1, nb)).copy()
     return y.astype(dt), x0.astype(dt), rtol, atol, max_iter
+
+
+# Products on natives whose arrays are legal but not canonical (tests/golden/spmv_edges.npz): entries of a row in arbitrary order, repeated
+# coordinates, stored zeros, empty rows, rectangular shapes, non-finite operands.  SciPy (the reference's NumPy backend) walks a row's entries
+# in STORED order, so does every product kernel here; matrices with stencil structure must not be re-ordered by the stencil recognition.
+SPMV_EDGE_CASES = ['shuffled_rows_f32', 'shuffled_rows_f64', 'stored_zeros_f32', 'split_diagonal_f32', 'rectangular_f64', 'inf_times_stored_zero_f32',
+                   'nan_in_x_f32', 'neumann_shuffled_rows_f32', 'all_rows_empty_f32']
+
+
+def spmv_edge_case(name: str):
+    """(indptr int32, indices int32, data, shape, x (batch, cols)) of a non-canonical CSR native."""
+    import scipy.sparse as sp
+    from oracle.assemble import stencil_csr, laplace_shifts
+    dt = np.float64 if name.endswith('f64') else np.float32
+    rng = np.random.default_rng(sum(map(ord, name)))
+    grid = (6, 5, 4)
+    base = stencil_csr(grid, laplace_shifts(3), dt)
+    n = base.shape[0]
+    if name.startswith('neumann'):      # ZERO_GRADIENT-type rows: the diagonal counts the neighbours inside the grid
+        off = base - sp.diags(base.diagonal())
+        base = (off + sp.diags(-np.asarray(off.sum(axis=1)).ravel() + 0.25)).tocsr().astype(dt)
+        base.sort_indices()
+    indptr, indices, data, shape = base.indptr.copy(), base.indices.copy(), base.data.copy(), base.shape
+    x = rng.standard_normal((3, shape[1])).astype(dt)
+    if 'shuffled_rows' in name:
+        for r in range(n):
+            p = rng.permutation(indptr[r + 1] - indptr[r]) + indptr[r]
+            indices[indptr[r]:indptr[r + 1]], data[indptr[r]:indptr[r + 1]] = indices[p], data[p]
+    elif name.startswith('stored_zeros') or name.startswith('inf_times'):
+        rows, cols, vals = [], [], []
+        for r in range(n):
+            c = list(indices[indptr[r]:indptr[r + 1]]); v = list(data[indptr[r]:indptr[r + 1]])
+            extra = (r + 11) % n
+            if extra not in c:
+                c.append(extra); v.append(0.0)
+            order = np.argsort(c, kind='stable')
+            rows += [r] * len(c); cols += [c[k] for k in order]; vals += [v[k] for k in order]
+        indices, data = np.asarray(cols, np.int32), np.asarray(vals, dt)
+        indptr = np.searchsorted(np.asarray(rows), np.arange(n + 1)).astype(np.int32)
+        if name.startswith('inf_times'):
+            x[0, 17] = np.inf
+            x[1, 40] = -np.inf
+    elif name.startswith('split_diagonal'):
+        rows, cols, vals = [], [], []
+        for r in range(n):
+            for k in range(indptr[r], indptr[r + 1]):
+                if indices[k] == r:
+                    rows += [r, r]; cols += [r, r]; vals += [data[k] * 0.75, data[k] * 0.25]
+                else:
+                    rows.append(r); cols.append(indices[k]); vals.append(data[k])
+        indices, data = np.asarray(cols, np.int32), np.asarray(vals, dt)
+        indptr = np.searchsorted(np.asarray(rows), np.arange(n + 1)).astype(np.int32)
+    elif name.startswith('rectangular'):
+        shape = (37, 29)
+        flat = np.sort(rng.choice(37 * 29, 150, replace=False))
+        r, c = flat // 29, flat % 29
+        keep = (r % 5) != 2           # rows 2, 7, 12, ... stay empty
+        r, c = r[keep], c[keep]
+        indices, data = c.astype(np.int32), rng.standard_normal(len(c)).astype(dt)
+        indptr = np.searchsorted(r, np.arange(38)).astype(np.int32)
+        x = rng.standard_normal((3, 29)).astype(dt)
+    elif name.startswith('nan_in_x'):
+        x[1, 33] = np.nan
+    elif name.startswith('all_rows_empty'):
+        indptr, indices, data = np.zeros(n + 1, np.int32), np.zeros(0, np.int32), np.zeros(0, dt)
+    return indptr.astype(np.int32), indices.astype(np.int32), data, shape, x

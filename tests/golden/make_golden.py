@@ -15,6 +15,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))          # tests/
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))          # repo root (oracle.assemble builds the case matrices)
 sys.path.insert(0, '/root/reference')
 
 from phiml import math                                                         # noqa: E402
@@ -25,7 +26,7 @@ from phiml.math._optimize import factor_ilu                                    #
 from phiml.backend._backend import get_backend, Preconditioner                 # noqa: E402
 from phiml.backend import NUMPY                                                # noqa: E402
 
-from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs, EDGE_CASES, edge_case_inputs                   # noqa: E402
+from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs, EDGE_CASES, edge_case_inputs, SPMV_EDGE_CASES, spmv_edge_case                   # noqa: E402
 
 warnings.filterwarnings('ignore')
 DIMS = 'xyz'
@@ -480,8 +481,23 @@ def golden_edges(out):
         print(key, ret.method, out[key + '/iterations'], out[key + '/function_evaluations'], out[key + '/converged'], out[key + '/diverged'])
 
 
+def golden_spmv_edges(out):
+    """Products on non-canonical natives through the reference: NUMPY.mul_matrix_batched_vector on the CSR native as given (_numpy_backend.py:282-283)
+    and on the same entries as a COO native."""
+    import scipy.sparse as sp
+    for name in SPMV_EDGE_CASES:
+        indptr, indices, data, shape, x = spmv_edge_case(name)
+        with np.errstate(all='ignore'):
+            csr = sp.csr_matrix((data, indices, indptr), shape=shape)
+            assert csr.indices is indices or np.array_equal(csr.indices, indices)      # SciPy keeps the arrays as they are
+            out[f"spmv_edge/{name}/csr"] = NUMPY.mul_matrix_batched_vector(csr, x)
+            rows = np.repeat(np.arange(shape[0]), np.diff(indptr))
+            coo = sp.coo_matrix((data, (rows, indices)), shape=shape)
+            out[f"spmv_edge/{name}/coo"] = NUMPY.mul_matrix_batched_vector(coo, x)
+
+
 def main():
-    groups = {'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'spmv_edges': golden_spmv_edges, 'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}
