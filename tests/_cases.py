@@ -263,3 +263,53 @@ def spmv_edge_case(name: str):
     elif name.startswith('all_rows_empty'):
         indptr, indices, data = np.zeros(n + 1, np.int32), np.zeros(0, np.int32), np.zeros(0, dt)
     return indptr.astype(np.int32), indices.astype(np.int32), data, shape, x
+
+
+# ILU sweeps on matrices that are not stencils (tests/golden/ilu_edges.npz, recorded from incomplete_lu_coo): structurally unsymmetric random patterns,
+# a 1-D chain, a diagonal matrix, a dense block, an upper-triangular matrix (the reference returns identity / the matrix itself; a LOWER-triangular one makes
+# its pattern helper raise IndexError, _linalg.py:618, so there is nothing to pin), and a rank-deficient matrix with `safe` sweeps.
+ILU_EDGE_CASES = {   # name: (builder, dtype, sweeps, safe)
+    'random_unsymmetric_f64': ('random', 'float64', 7, False),
+    'random_unsymmetric_f32': ('random', 'float32', 5, False),
+    'chain_f32': ('chain', 'float32', 9, False),
+    'diagonal_f64': ('diagonal', 'float64', 3, False),
+    'dense_block_f64': ('dense', 'float64', 6, False),
+    'upper_triangular_f64': ('upper', 'float64', 4, False),
+    'singular_safe_f64': ('singular', 'float64', 6, True),
+    'one_by_one_f32': ('one', 'float32', 2, False),
+}
+
+
+def ilu_edge_matrix(name: str):
+    import scipy.sparse as sp
+    kind, dt, sweeps, safe = ILU_EDGE_CASES[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    if kind == 'random':
+        n = 40
+        a = sp.random(n, n, density=0.12, random_state=np.random.RandomState(5), format='lil')
+        a.setdiag(0)
+        a = a.tocsr()
+        a = a + sp.diags(np.asarray(abs(a).sum(axis=1)).ravel() + 1.0)
+    elif kind == 'chain':
+        n = 17
+        a = sp.diags([-np.ones(n - 1), np.full(n, 2.5), -0.5 * np.ones(n - 1)], [-1, 0, 1])
+    elif kind == 'diagonal':
+        a = sp.diags(rng.uniform(1, 2, 12))
+    elif kind == 'dense':
+        a = sp.csr_matrix(rng.standard_normal((5, 5)) + 6 * np.eye(5))
+    elif kind in ('upper', 'lower'):
+        n = 15
+        a = sp.random(n, n, density=0.3, random_state=np.random.RandomState(7), format='csr')
+        a = (sp.triu(a, 1) if kind == 'upper' else sp.tril(a, -1)) + sp.diags(rng.uniform(1, 2, n))
+    elif kind == 'singular':       # periodic 2-D Laplacian: constant null space; two decoupled copies -> rank deficiency 2
+        n = 6
+        p = sp.diags([-np.ones(n - 1), np.full(n, 2.0), -np.ones(n - 1)], [-1, 0, 1], format='lil')
+        p[0, n - 1] = p[n - 1, 0] = -1
+        lap = sp.kron(p, sp.identity(n)) + sp.kron(sp.identity(n), p)
+        a = sp.block_diag([lap, lap])
+    else:
+        a = sp.csr_matrix(np.array([[3.0]]))
+    a = sp.csr_matrix(a).astype(dt)
+    a.sort_indices()
+    a.eliminate_zeros()
+    return a, sweeps, safe

@@ -26,7 +26,7 @@ from phiml.math._optimize import factor_ilu                                    #
 from phiml.backend._backend import get_backend, Preconditioner                 # noqa: E402
 from phiml.backend import NUMPY                                                # noqa: E402
 
-from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs, EDGE_CASES, edge_case_inputs, SPMV_EDGE_CASES, spmv_edge_case                   # noqa: E402
+from _cases import SOLVE_CASES, rhs_for, sample_index, ADVDIFF, BOUNDARY_CASES, DENSE_CASES, dense_case_inputs, EDGE_CASES, edge_case_inputs, SPMV_EDGE_CASES, spmv_edge_case, ILU_EDGE_CASES, ilu_edge_matrix                   # noqa: E402
 
 warnings.filterwarnings('ignore')
 DIMS = 'xyz'
@@ -496,8 +496,24 @@ def golden_spmv_edges(out):
             out[f"spmv_edge/{name}/coo"] = NUMPY.mul_matrix_batched_vector(coo, x)
 
 
+def golden_ilu_edges(out):
+    """incomplete_lu_coo (phiml/backend/_linalg.py:524-594) on matrices that are not stencils; factors stored as the (indices, values) pairs it returns,
+    in the entry order it returns them."""
+    from phiml.backend._linalg import incomplete_lu_coo
+    for name in ILU_EDGE_CASES:
+        a, sweeps, safe = ilu_edge_matrix(name)
+        coo = a.tocoo()      # CSR order: rows ascending, columns ascending
+        idx = np.stack([coo.row, coo.col], -1)[None].astype(np.int64)
+        with math.precision(64 if a.dtype == np.float64 else 32), np.errstate(all='ignore'):
+            (li, lv), (ui, uv) = incomplete_lu_coo(idx, coo.data[None, :, None], a.shape, sweeps, safe)
+        key = f"ilu_edge/{name}"
+        out[key + '/L_idx'], out[key + '/L_val'] = np.asarray(li)[0], np.asarray(lv)[0, :, 0]
+        out[key + '/U_idx'], out[key + '/U_val'] = np.asarray(ui)[0], np.asarray(uv)[0, :, 0]
+        print(key, a.shape, a.nnz, out[key + '/L_val'].shape, out[key + '/U_val'].shape, out[key + '/L_val'].dtype, np.isfinite(out[key + '/U_val']).all())
+
+
 def main():
-    groups = {'spmv_edges': golden_spmv_edges, 'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'ilu_edges': golden_ilu_edges, 'spmv_edges': golden_spmv_edges, 'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}

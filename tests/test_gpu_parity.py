@@ -606,6 +606,39 @@ def test_ilu_sweeps_reproduce_the_reference_factors_bit_for_bit(key):
     np.testing.assert_allclose(ilu.apply_transposed(v).cpu().numpy(), ref_t, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize('name', sorted({k.split('/')[1] for k in golden('ilu_edges').files}))
+def test_ilu_sweeps_on_matrices_that_are_not_stencils(name):
+    """phb200_precond_ilu_sweeps against incomplete_lu_coo (tests/golden/ilu_edges.npz) on structurally unsymmetric random patterns, a chain, a diagonal
+    matrix, a dense block, an upper-triangular matrix (the reference returns identity and the matrix itself) and a rank-deficient matrix with `safe`
+    sweeps: the factor values per stored entry, in entry order, to the last bit; the triangular solves against SciPy on the reference's factors."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import spsolve_triangular
+    from _cases import ilu_edge_matrix
+    g = golden('ilu_edges')
+    a, sweeps, safe = ilu_edge_matrix(name)
+    key = f"ilu_edge/{name}"
+    ilu = pb.IncompleteLU(dev_csr(a), sweeps=sweeps, safe=safe)
+    assert repr(ilu) == f"ilu (iter={sweeps})"
+    lu = ilu.lu.cpu().numpy()
+    coo = a.tocoo()
+    lower = coo.row > coo.col
+    ref_l, ref_u = g[key + '/L_val'], g[key + '/U_val']
+    l_idx = g[key + '/L_idx']
+    np.testing.assert_array_equal(g[key + '/U_idx'], np.stack([coo.row, coo.col], -1)[~lower])
+    np.testing.assert_array_equal(lu[~lower], ref_u)
+    np.testing.assert_array_equal(lu[lower], ref_l[l_idx[:, 0] > l_idx[:, 1]])
+    n = a.shape[0]
+    Lr = sp.csr_matrix((ref_l, (l_idx[:, 0], l_idx[:, 1])), shape=(n, n))
+    Ur = sp.csr_matrix((ref_u, (g[key + '/U_idx'][:, 0], g[key + '/U_idx'][:, 1])), shape=(n, n))
+    if name.startswith('singular'):
+        return      # U has a zero pivot (the rank deficiency): SciPy refuses the solve, the reference's CG never applies these factors to convergence
+    rhs = np.random.default_rng(3).standard_normal((2, n)).astype(a.dtype)
+    ref = spsolve_triangular(Ur, spsolve_triangular(Lr, rhs.T.astype(np.float64), lower=True, unit_diagonal=True), lower=False).T
+    tol = 1e-11 if a.dtype == np.float64 else 2e-5
+    got = ilu.apply(torch.as_tensor(rhs, device=DEV)).cpu().numpy()
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
+
+
 @pytest.mark.parametrize('dt', ['float32', 'float64'])
 @pytest.mark.parametrize('op,grid', [('poisson', (12, 8, 8)), ('advdiff', (7, 9, 8)), ('poisson', (24, 20))])
 def test_ilu_sweeps_match_the_oracle_sweeps(op, grid, dt):
