@@ -189,13 +189,28 @@ def owner_of(values):
 STATS = {'device_assemblies': 0, 'general_assemblies': 0, 'fallbacks': 0}
 
 
+def _caller_wants_compressed() -> bool:
+    """``matrix_from_function(..., auto_compress=False)`` — the default of the public function — returns the coordinate form (SparseCoordinateTensor,
+    phiml/math/_lin_trace.py:680,743); only ``auto_compress=True`` (``jit_compile_linear`` / ``solve_linear``, phiml/math/_functional.py:436) asks for the
+    compressed rows the device assembler produces.  ``tracer_to_coo`` is not told, so the flag is read from the calling frame (two frames up from here);
+    any other caller gets the compressed form."""
+    import sys
+    try:
+        frame = sys._getframe(2)
+        if frame.f_code.co_name == 'matrix_from_function':
+            return bool(frame.f_locals.get('auto_compress', True))
+    except ValueError:
+        pass
+    return True
+
+
 def make_tracer_to_coo(original: Callable, eligible: Callable[[], bool], assemble: Callable = cuda_assemble, assemble_general: Callable = cuda_assemble_general):
     """Wrapper for ``phiml.math._lin_trace.tracer_to_coo``.  ``eligible()`` says whether the matrix is wanted on the CUDA torch backend
     right now (the wrapped function is not told the target backend); ``assemble`` is injectable so that the CPU tests can check the
     PhiML-side structure against the reference's own matrix with arrays from the oracle."""
     def tracer_to_coo(tracer, sparsify, separate_independent):
         info = None
-        if eligible():
+        if eligible() and _caller_wants_compressed():
             info = analyse_tracer(tracer, sparsify, separate_independent)
         if info is not None:
             if info['general']:

@@ -512,8 +512,31 @@ def golden_ilu_edges(out):
         print(key, a.shape, a.nnz, out[key + '/L_val'].shape, out[key + '/U_val'].shape, out[key + '/L_val'].dtype, np.isfinite(out[key + '/U_val']).all())
 
 
+def golden_frontend_products(out):
+    """`matrix @ x` through the front end (dot_coordinate_dense -> Backend.mul_coo_dense, phiml/math/_sparse.py:1613; dot_compressed_dense ->
+    Backend.mul_csr_dense, :1590) with batch and channel dimensions on x, on the reference's NumPy backend."""
+    with NUMPY:
+        for prec, dt in ((32, np.float32), (64, np.float64)):
+            with math.precision(prec):
+                f = math.jit_compile_linear(neg_laplace)          # per precision: the trace cache of a linear function does not key on it
+                f_adv = math.jit_compile_linear(advdiff)
+                rng = np.random.default_rng(9)
+                x0 = math.zeros(spatial(x=16, y=12))
+                v = math.tensor(rng.standard_normal((3, 16, 12, 2)).astype(dt), batch('b'), spatial('x,y'), channel('c'))
+                coo, _ = matrix_from_function(neg_laplace, x0)
+                csr, _ = f.sparse_matrix_and_bias(x0)
+                assert type(coo).__name__ == 'SparseCoordinateTensor' and type(csr).__name__ == 'CompressedSparseMatrix'
+                out[f"prod/coo_laplace_f{prec}"] = (coo @ v).numpy('b,x,y,c')
+                out[f"prod/csr_laplace_f{prec}"] = (csr @ v).numpy('b,x,y,c')
+                x03 = math.zeros(spatial(x=6, y=5, z=7))
+                v3 = math.tensor(rng.standard_normal((6, 5, 7)).astype(dt), spatial('x,y,z'))
+                csr3, _ = f_adv.sparse_matrix_and_bias(x03)
+                out[f"prod/csr_advdiff_f{prec}"] = (csr3 @ v3).numpy('x,y,z')
+                print(prec, [out[k].shape for k in out])
+
+
 def main():
-    groups = {'ilu_edges': golden_ilu_edges, 'spmv_edges': golden_spmv_edges, 'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
+    groups = {'frontend_products': golden_frontend_products, 'ilu_edges': golden_ilu_edges, 'spmv_edges': golden_spmv_edges, 'edges': golden_edges, 'dense': golden_dense, 'boundaries': golden_boundaries, 'cluster': golden_cluster, 'assembly': golden_assembly, 'spmv': golden_spmv, 'solves': golden_solves, 'ilu': golden_ilu, 'frontend': golden_frontend, 'adjoint': golden_adjoint}
     only = sys.argv[1:] or list(groups)
     for g in only:
         out = {}

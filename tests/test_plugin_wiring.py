@@ -224,6 +224,18 @@ def test_tracer_bridge_builds_the_reference_matrix(phiml_env):
                     a, b = np.asarray(getattr(mine, name).native(dim)), getattr(ref, name).numpy(dim)
                     assert a.dtype == b.dtype and np.array_equal(a, b), (f.__name__, name)
                 assert float(mine._matrix_rank) == float(ref._matrix_rank)
+        # auto_compress=False (the default of the public function) asks for the coordinate form: the bridge leaves it to the reference
+        with math.precision(32):
+            x0 = math.zeros(spatial(x=6, y=5))
+            lt.tracer_to_coo = original
+            ref, _ = matrix_from_function(neg_laplace, x0)
+            assembly.STATS.update(device_assemblies=0, general_assemblies=0, fallbacks=0)
+            lt.tracer_to_coo = assembly.make_tracer_to_coo(original, lambda: True, oracle_assemble, oracle_assemble_general)
+            mine, _ = matrix_from_function(neg_laplace, x0)
+        assert type(ref).__name__ == 'SparseCoordinateTensor' and type(mine) is type(ref)
+        assert assembly.STATS['device_assemblies'] == 0 and assembly.STATS['fallbacks'] == 1
+        assert np.array_equal(mine._indices.numpy(mine._indices.shape.names), ref._indices.numpy(ref._indices.shape.names))
+        assert np.array_equal(mine._values.numpy(mine._values.shape.names), ref._values.numpy(ref._values.shape.names))
     finally:
         lt.tracer_to_coo = bridged
 
