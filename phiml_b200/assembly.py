@@ -161,6 +161,27 @@ def build_compressed(info: dict, natives):
     return m
 
 
+def coordinates_of_compressed(m):
+    """The coordinates ``SparseCoordinateTensor.compress_rows()`` would have kept for the compressed matrix ``m`` (phiml/math/_sparse.py:383-390), rebuilt from its
+    CSR arrays: one row of per-dimension indices per stored entry, in CSR order, labels = uncompressed (dual) names followed by compressed (primal) names."""
+    import torch
+    from phiml.math._shape import instance, channel
+    from phiml.math._ops import reshaped_tensor
+    col = torch.as_tensor(m._indices.native('sp_entries')).to(torch.int64)
+    ptr = torch.as_tensor(m._pointers.native('pointers')).to(torch.int64).to(col.device)
+    rows = torch.repeat_interleave(torch.arange(ptr.numel() - 1, device=col.device, dtype=torch.int64), ptr[1:] - ptr[:-1])
+    parts = []
+    for flat, dims in ((col, m._uncompressed_dims), (rows, m._compressed_dims)):
+        comps, rem = [], flat
+        for size in reversed(dims.sizes):
+            comps.append(rem % size)
+            rem = rem // size
+        parts += comps[::-1]
+    native = torch.stack(parts, -1)
+    labels = m._uncompressed_dims.names + m._compressed_dims.names
+    return reshaped_tensor(native, [instance('sp_entries'), channel(sparse_idx=labels)], convert=False)
+
+
 # PhiML hands constants around as detached copies (stop_gradient in key_from_args, phiml/math/_functional.py:147): new tensor objects over
 # the SAME storage on every call.  The residency caches of the plug-in need one stable object per matrix to tie their entries to:
 # the bridged matrix itself (kept alive by the LinearFunction that traced it), found again through the address of its value array.

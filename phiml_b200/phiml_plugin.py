@@ -381,12 +381,46 @@ def install():
         solve_with_grad = opt.custom_gradient(forward_solve, backward, auxiliary_args=auxiliary_args)
         return solve_with_grad
 
+    # ---- the coordinate form of a bridged matrix.  compress_rows() keeps the coordinates it started from (_uncompressed_indices, phiml/math/_sparse.py:383-390)
+    #      and decompress() hands them back (:895-908); the bridge never had them (they are the 2 * rank * 8 bytes per entry it avoids), so decompress() —
+    #      called by math.factor_ilu (_optimize.py:922), explicit_coarse (:966), the reference's matrix gradient (:801) or a user — would raise
+    #      NotImplementedError.  They are rebuilt from the CSR arrays on demand, in the reference's layout: (sp_entries, sparse_idx = dual names + primal names), int64.
+    from phiml.math._sparse import CompressedSparseMatrix
+    original_decompress = CompressedSparseMatrix.decompress
+
+    def decompress(self):
+        # (1-D grids: the reference has a branch of its own for matrices without kept coordinates, with the labels the other way round; only matrices the
+        #  bridge made are given the compress_rows() layout there, everything else keeps the reference's branch)
+        rebuild = not (self._compressed_dims.rank == self._uncompressed_dims.rank == 1) or getattr(self, '_phb200_device_assembled', False)
+        if self._uncompressed_indices is None and rebuild and self._uncompressed_offset is None \
+                and self._indices.shape.names == ('sp_entries',) and self._pointers.shape.names == ('pointers',):
+            self._uncompressed_indices = assembly.coordinates_of_compressed(self)
+            self._uncompressed_indices_perm = None
+        return original_decompress(self)
+
+    CompressedSparseMatrix.decompress = decompress
+
+    # ---- math.factor_ilu (_optimize.py:883-939) calls incomplete_lu_coo (looked up as a module global at :925): one matrix with one channel whose values are a
+    #      CUDA tensor is factored by the device sweeps (bit-identical factors, tests/golden/ilu_edges.npz) and handed back in the reference's layout; index
+    #      arrays living on the device (bridged matrices) are brought to the host first, where the reference insists on NumPy (:545)
+    original_ilu_coo = opt.incomplete_lu_coo
+
+    def incomplete_lu_coo(indices, values, shape, iterations, safe):
+        out = _precond.incomplete_lu_coo_device(indices, values, shape, iterations, safe)
+        if out is not None:
+            return out
+        if isinstance(indices, torch.Tensor):
+            indices = indices.detach().cpu().numpy()
+        return original_ilu_coo(indices, values, shape, iterations, safe)
+
+    opt.incomplete_lu_coo = incomplete_lu_coo
+
     TORCH.__class__ = B200TorchBackend
     opt.compute_preconditioner = compute_preconditioner
     opt.native_matrix = native_matrix
     opt.attach_gradient_solve = attach_gradient_solve
     _INSTALLED.update(torch=TORCH, original_class=TorchBackend, original_compute=original_compute, original_native=original_native, opt=opt, original_attach=original_attach,
-                      lin_trace=lin_trace, original_t2c=original_t2c)
+                      lin_trace=lin_trace, original_t2c=original_t2c, csm=CompressedSparseMatrix, original_decompress=original_decompress, original_ilu_coo=original_ilu_coo)
     return TORCH
 
 
@@ -398,6 +432,8 @@ def uninstall():
     _INSTALLED['opt'].native_matrix = _INSTALLED['original_native']
     _INSTALLED['opt'].attach_gradient_solve = _INSTALLED['original_attach']
     _INSTALLED['lin_trace'].tracer_to_coo = _INSTALLED['original_t2c']
+    _INSTALLED['csm'].decompress = _INSTALLED['original_decompress']
+    _INSTALLED['opt'].incomplete_lu_coo = _INSTALLED['original_ilu_coo']
     NATIVE_CACHE.clear()
     PRECOND_CACHE.clear()
     _INSTALLED.clear()

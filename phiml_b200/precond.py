@@ -290,6 +290,44 @@ class ClusterPreconditioner(Preconditioner, _Handle):
 
 
 @E.on_operand_device
+def incomplete_lu_coo_device(indices, values, shape, iterations: int, safe: bool):
+    """``incomplete_lu_coo`` (phiml/backend/_linalg.py:524-594) for ONE matrix with ONE channel whose values are a CUDA tensor, on the device sweeps:
+    returns ``((l_indices, l_values), (u_indices, u_values))`` in the reference's layout — NumPy index arrays (1, nnz_L|U, 2) holding the lower + diagonal /
+    the upper + diagonal coordinates in the order they were given, value tensors (1, nnz_L|U, 1) with L's unit diagonal stored — or ``None`` when the
+    call is not of that kind (several matrices or channels, CPU values, repeated coordinates), which the caller hands to the reference."""
+    import numpy as np
+    if not (isinstance(values, torch.Tensor) and values.is_cuda and values.dim() == 3 and values.shape[0] == 1 and values.shape[2] == 1 and values.dtype in (torch.float32, torch.float64)):
+        return None
+    if int(shape[0]) != int(shape[1]) or tuple(indices.shape) != (1, values.shape[1], 2):
+        return None
+    with torch.cuda.device(values.device):
+        n, dev = int(shape[0]), values.device
+        idx = torch.as_tensor(indices, device=dev)[0].to(torch.int64)
+        row, col = idx[:, 0].contiguous(), idx[:, 1].contiguous()
+        key = row * n + col
+        order = None
+        if key.numel() > 1 and not bool((key[1:] > key[:-1]).all()):
+            key, order = torch.sort(key, stable=True)
+            if bool((key[1:] == key[:-1]).any()):
+                return None                                   # repeated coordinates: not a CSR pattern
+            row, col = row[order], col[order]
+        vals = values[0, :, 0].detach()
+        vals = (vals[order] if order is not None else vals).contiguous()
+        rowptr = torch.searchsorted(row, torch.arange(n + 1, device=dev, dtype=torch.int64)).to(torch.int32)
+        ilu = IncompleteLU(Matrix.csr(rowptr, col.to(torch.int32), vals, (n, n)), sweeps=int(iterations), safe=bool(safe))
+        lu = ilu.lu
+        if order is not None:
+            lu = torch.empty_like(lu).index_copy_(0, order, lu)
+        row, col = idx[:, 0], idx[:, 1]
+        lower, diag = row > col, row == col
+        keep_l = lower | diag
+        l_val = torch.where(lower, lu, torch.ones_like(lu))[keep_l]
+        u_val = lu[~lower]
+        idx_host = np.asarray(indices.detach().cpu().numpy() if isinstance(indices, torch.Tensor) else indices)
+        keep_l_h, upper_h = keep_l.cpu().numpy(), (~lower).cpu().numpy()
+        return (idx_host[:, keep_l_h], l_val[None, :, None]), (idx_host[:, upper_h], u_val[None, :, None])
+
+
 def compute_preconditioner(method: Optional[str], matrix, rank_deficiency=0, **_ignored) -> Optional[Preconditioner]:
     """'jacobi' | 'ilu' | 'ilu-exact' | 'cluster' | 'auto' | None on a native matrix (torch sparse tensor or Matrix).  'auto' resolves to 'ilu'
     as in the reference for backends with sparse triangular solves (phiml/math/_optimize.py:838-846); 'ilu' builds the

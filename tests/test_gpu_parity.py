@@ -639,6 +639,49 @@ def test_ilu_sweeps_on_matrices_that_are_not_stencils(name):
     assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
 
 
+@pytest.mark.parametrize('shuffle', [False, True], ids=['csr_order', 'shuffled'])
+@pytest.mark.parametrize('name', sorted({k.split('/')[1] for k in golden('ilu_edges').files}))
+def test_incomplete_lu_coo_drop_in(name, shuffle):
+    """The function math.factor_ilu calls (phiml/math/_optimize.py:925), in the reference's own signature and return layout: NumPy coordinate arrays of the
+    lower + diagonal / upper + diagonal entries in the order they were given, value tensors with L's unit diagonal stored — identical to the recorded
+    reference output (tests/golden/ilu_edges.npz), also when the coordinates arrive in arbitrary order or as device tensors."""
+    from phiml_b200.precond import incomplete_lu_coo_device
+    from _cases import ilu_edge_matrix
+    g = golden('ilu_edges')
+    a, sweeps, safe = ilu_edge_matrix(name)
+    key = f"ilu_edge/{name}"
+    coo = a.tocoo()
+    idx = np.stack([coo.row, coo.col], -1).astype(np.int64)
+    vals = coo.data
+    perm = np.random.default_rng(3).permutation(len(vals)) if shuffle else np.arange(len(vals))
+    idx_in, vals_in = idx[perm][None], torch.as_tensor(vals[perm], device=DEV)[None, :, None]
+    for indices in (idx_in, torch.as_tensor(idx_in, device=DEV)):
+        out = incomplete_lu_coo_device(indices, vals_in, a.shape, sweeps, safe)
+        assert out is not None
+        (li, lv), (ui, uv) = out
+        assert isinstance(li, np.ndarray) and isinstance(ui, np.ndarray) and lv.shape == (1, li.shape[1], 1) and uv.shape == (1, ui.shape[1], 1)
+        # the reference lists the entries in the order given: undo the shuffle by sorting both sides by coordinate
+        def canon(i, v):
+            o = np.lexsort((i[:, 1], i[:, 0]))
+            return i[o], np.asarray(v)[o]
+        for nm, mi, mv in (('L', li[0], lv[0, :, 0].cpu().numpy()), ('U', ui[0], uv[0, :, 0].cpu().numpy())):
+            ri, rv = g[f"{key}/{nm}_idx"], g[f"{key}/{nm}_val"]
+            if not shuffle:
+                np.testing.assert_array_equal(mi, ri)
+                np.testing.assert_array_equal(mv, rv)
+            else:
+                given = idx_in[0]
+                keep = (given[:, 0] >= given[:, 1]) if nm == 'L' else (given[:, 0] <= given[:, 1])
+                np.testing.assert_array_equal(mi, given[keep])          # order of arrival kept
+                a_i, a_v = canon(mi, mv)
+                b_i, b_v = canon(ri, rv)
+                np.testing.assert_array_equal(a_i, b_i)
+                np.testing.assert_array_equal(a_v, b_v)
+    # not this function's business: several channels, CPU values
+    assert incomplete_lu_coo_device(idx_in, torch.as_tensor(vals[perm])[None, :, None], a.shape, sweeps, safe) is None
+    assert incomplete_lu_coo_device(idx_in, vals_in.repeat(1, 1, 2), a.shape, sweeps, safe) is None
+
+
 @pytest.mark.parametrize('dt', ['float32', 'float64'])
 @pytest.mark.parametrize('op,grid', [('poisson', (12, 8, 8)), ('advdiff', (7, 9, 8)), ('poisson', (24, 20))])
 def test_ilu_sweeps_match_the_oracle_sweeps(op, grid, dt):

@@ -224,6 +224,15 @@ def test_tracer_bridge_builds_the_reference_matrix(phiml_env):
                     a, b = np.asarray(getattr(mine, name).native(dim)), getattr(ref, name).numpy(dim)
                     assert a.dtype == b.dtype and np.array_equal(a, b), (f.__name__, name)
                 assert float(mine._matrix_rank) == float(ref._matrix_rank)
+                # the coordinate form: compress_rows() keeps the coordinates it came from, the bridge rebuilds them on demand (phiml_plugin: decompress)
+                assert mine._uncompressed_indices is None
+                c_mine, c_ref = mine.decompress(), ref.decompress()
+                assert type(c_mine) is type(c_ref) and c_mine.shape == c_ref.shape
+                assert c_mine._indices.shape == c_ref._indices.shape and c_mine._indices.dtype == c_ref._indices.dtype
+                order = c_ref._indices.shape.names
+                assert np.array_equal(np.asarray(c_mine._indices.native(order)), c_ref._indices.numpy(order)), f.__name__
+                assert np.array_equal(np.asarray(c_mine._values.native('sp_entries')), c_ref._values.numpy('sp_entries'))
+                assert (c_mine._can_contain_double_entries, c_mine._indices_sorted, c_mine._indices_constant) == (c_ref._can_contain_double_entries, c_ref._indices_sorted, c_ref._indices_constant)
         # auto_compress=False (the default of the public function) asks for the coordinate form: the bridge leaves it to the reference
         with math.precision(32):
             x0 = math.zeros(spatial(x=6, y=5))
