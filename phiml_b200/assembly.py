@@ -177,7 +177,7 @@ def coordinates_of_compressed(m):
             comps.append(rem % size)
             rem = rem // size
         parts += comps[::-1]
-    native = torch.stack(parts, -1)
+    native = torch.stack(parts, -1).cpu().numpy()      # NumPy-backed like every coordinate array of the reference (its packing / slicing utilities insist: _sparse.py:394)
     labels = m._uncompressed_dims.names + m._compressed_dims.names
     return reshaped_tensor(native, [instance('sp_entries'), channel(sparse_idx=labels)], convert=False)
 

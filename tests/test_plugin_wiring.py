@@ -233,6 +233,10 @@ def test_tracer_bridge_builds_the_reference_matrix(phiml_env):
                 assert np.array_equal(np.asarray(c_mine._indices.native(order)), c_ref._indices.numpy(order)), f.__name__
                 assert np.array_equal(np.asarray(c_mine._values.native('sp_entries')), c_ref._values.numpy('sp_entries'))
                 assert (c_mine._can_contain_double_entries, c_mine._indices_sorted, c_mine._indices_constant) == (c_ref._can_contain_double_entries, c_ref._indices_sorted, c_ref._indices_constant)
+                assert c_mine._indices.default_backend.name == 'numpy'        # what the reference's packing utilities insist on (_sparse.py:394)
+                probe = math.tensor(np.random.default_rng(2).standard_normal(tuple(shape.values())), spatial(','.join(shape)))
+                order_x = ','.join(shape)
+                assert np.allclose((c_mine @ probe).numpy(order_x), (c_ref @ probe).numpy(order_x), rtol=1e-6 if prec == 32 else 1e-13, atol=1e-6 if prec == 32 else 1e-13)
         # auto_compress=False (the default of the public function) asks for the coordinate form: the bridge leaves it to the reference
         with math.precision(32):
             x0 = math.zeros(spatial(x=6, y=5))
