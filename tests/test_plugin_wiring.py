@@ -382,3 +382,94 @@ def test_matrix_gradient_inside_phimls_backward_pass_comes_from_the_boundary(phi
     np.testing.assert_allclose(dy_dev, dy_ref, rtol=0, atol=1e-12 * np.abs(dy_ref).max())
     assert abs(dk_dev - dk_ref) <= 1e-10 * max(1.0, abs(dk_ref))
     plugin.DM_STATS.update(device=0, reference=0)
+
+
+def test_bridged_matrix_behaves_like_the_reference_matrix_under_phimls_operations(phiml_env):
+    """A device-assembled (bridged) CompressedSparseMatrix is a PhiML tensor like any other: 40 operations a user can apply to the matrix — products with
+    batch / channel dimensions, arithmetic, reductions, format changes, the coordinate form and its products, math.factor_ilu, casts, conversion to the
+    NumPy backend, natives for SciPy and torch — give the reference matrix' result, and raise where the reference itself raises."""
+    import torch
+    from phiml import math
+    from phiml.math import spatial, batch, channel, dual, extrapolation
+    from phiml.backend import NUMPY
+    from phiml.math._sparse import native_matrix
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly
+    from oracle.assemble import stencil_csr
+    TORCH = phiml_env[1]
+
+    def neg_laplace(x): return -math.laplace(x, padding=extrapolation.ZERO)
+
+    def oracle_assemble(grid, offsets, coeffs, dtype):
+        csr = stencil_csr(grid, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    ops = {
+        'matmul': lambda M, v: (M @ v).numpy('x,y'),
+        'matmul_batched': lambda M, v: (M @ math.stack([v, 2 * v], batch('b'))).numpy('b,x,y'),
+        'matmul_channels': lambda M, v: (M @ math.stack([v, 2 * v], channel('c'))).numpy('x,y,c'),
+        'dense': lambda M, v: math.dense(M).numpy('x,y,~x,~y'),
+        'scale': lambda M, v: ((M * 2.5) @ v).numpy('x,y'),
+        'neg': lambda M, v: ((-M) @ v).numpy('x,y'),
+        'add': lambda M, v: ((M + M) @ v).numpy('x,y'),
+        'sub': lambda M, v: ((M - 0.5 * M) @ v).numpy('x,y'),
+        'abs': lambda M, v: (abs(M) @ v).numpy('x,y'),
+        'pow': lambda M, v: ((M ** 2) @ v).numpy('x,y'),
+        'where': lambda M, v: (math.where(M > 0, M, 0) @ v).numpy('x,y'),
+        'mul_tensor': lambda M, v: ((M * v) @ v).numpy('x,y'),
+        'stored_values': lambda M, v: math.stored_values(M).numpy('entries'),
+        'stored_indices': lambda M, v: math.stored_indices(M).numpy('entries,index'),
+        'sum_dual': lambda M, v: math.sum(M, dual).numpy('x,y'),
+        'sum_primal': lambda M, v: math.sum(M, 'x,y').numpy('~x,~y'),
+        'sum_all': lambda M, v: np.asarray(float(math.sum(M, M.shape))),
+        'max_all': lambda M, v: np.asarray(float(math.max(M, M.shape))),
+        'sparsity': lambda M, v: np.asarray(float(math.get_sparsity(M))),
+        'is_sparse': lambda M, v: np.asarray(math.is_sparse(M)),
+        'matrix_rank': lambda M, v: np.asarray(float(M._matrix_rank)),
+        'repr': lambda M, v: np.asarray(len(repr(M)) > 0),
+        'close': lambda M, v: np.asarray(bool(math.close(M, M))),
+        'copy': lambda M, v: (math.copy(M) @ v).numpy('x,y'),
+        'rename': lambda M, v: math.dense(math.rename_dims(M, 'x', 'a')).numpy('a,y,~x,~y'),
+        'slice_row': lambda M, v: math.dense(M[{'x': 1}]).numpy('y,~x,~y'),
+        'to_dense': lambda M, v: (math.to_format(M, 'dense') @ v).numpy('x,y'),
+        'to_csc': lambda M, v: (math.to_format(M, 'csc') @ v).numpy('x,y'),
+        'to_coo': lambda M, v: (math.to_format(M, 'coo') @ v).numpy('x,y'),
+        'coo_dense': lambda M, v: math.dense(math.to_format(M, 'coo')).numpy('x,y,~x,~y'),
+        'coo_scaled': lambda M, v: ((math.to_format(M, 'coo') * 3) @ v).numpy('x,y'),
+        'coo_to_csr': lambda M, v: (math.to_format(math.to_format(M, 'coo'), 'csr') @ v).numpy('x,y'),
+        'decompress': lambda M, v: (M.decompress() @ v).numpy('x,y'),
+        'factor_ilu': lambda M, v: np.concatenate([math.dense(t).numpy('x,y,~x,~y').ravel() for t in math.factor_ilu(M, 4)]),
+        'to_float': lambda M, v: (math.to_float(M) @ v).numpy('x,y'),
+        'cast32': lambda M, v: (math.cast(M, math.DType(float, 32)) @ math.cast(v, math.DType(float, 32))).numpy('x,y'),
+        'convert_numpy': lambda M, v: (math.convert(M, NUMPY) @ math.convert(v, NUMPY)).numpy('x,y'),
+        'scipy_native': lambda M, v: native_matrix(M, NUMPY).toarray(),
+        'torch_native': lambda M, v: native_matrix(M, TORCH).to_dense().numpy(),
+        'trace_through': lambda M, v: (math.matrix_from_function(lambda x: M @ x, v)[0] @ v).numpy('x,y'),
+    }
+    bridged = lt.tracer_to_coo
+    original = phiml_env[0]._INSTALLED['original_t2c']
+    try:
+        with TORCH, math.precision(64):
+            x0 = math.zeros(spatial(x=6, y=5))
+            v = math.tensor(np.random.default_rng(1).standard_normal((6, 5)), spatial('x,y'))
+            lt.tracer_to_coo = original
+            ref, _ = math.jit_compile_linear(lambda x: neg_laplace(x)).sparse_matrix_and_bias(x0)
+            lt.tracer_to_coo = assembly.make_tracer_to_coo(original, lambda: True, oracle_assemble, None)
+            mine, _ = math.jit_compile_linear(lambda x: neg_laplace(x)).sparse_matrix_and_bias(x0)
+            assert getattr(mine, '_phb200_device_assembled', False) and mine._uncompressed_indices is None
+            ok = 0
+            for name, op in ops.items():
+                res = []
+                for M in (ref, mine):
+                    try:
+                        res.append(('ok', op(M, v)))
+                    except Exception as exc:
+                        res.append(('raised', type(exc).__name__))
+                (s0, a), (s1, b) = res
+                assert s0 == s1, f"{name}: the reference matrix {s0} ({a if s0 == 'raised' else ''}), the bridged matrix {s1} ({b if s1 == 'raised' else ''})"
+                if s0 == 'ok':
+                    ok += 1
+                    assert np.shape(a) == np.shape(b) and np.allclose(a, b, rtol=1e-13, atol=1e-13), name
+            assert ok >= 33, ok
+    finally:
+        lt.tracer_to_coo = bridged
