@@ -2242,7 +2242,8 @@ int phb200_solver_result(phb200_solver* s, int32_t* iterations, int32_t* functio
     PHB_LAUNCH(k_collect, (unsigned)((s->batch + 255) / 256), 256, 0, st, s->sys, (int)s->batch, iterations, function_evaluations, converged, diverged);
     if ((s->method == PHB200_CG || s->method == PHB200_CG_ADAPTIVE) && s->batch > 1 && s->X && s->R && s->n_act > 0) {
         // stopped systems with a non-finite residual norm: the NaNs the reference's masked updates produce while the rest of the batch iterates
-        const unsigned gx = (unsigned)std::min<int64_t>((s->n_act + 255) / 256, 64);
+        // (almost always nothing to do: one CTA per system and 16 K rows keeps the check itself cheap for batches of thousands of small systems)
+        const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((s->n_act + 16383) / 16384, 64));
         dim3 grid(gx, (unsigned)s->batch);
         if (s->dtype == PHB200_F32) PHB_LAUNCH(k_poison_nonfinite<float>, grid, 256, 0, st, s->sys, (int)s->batch, (float*)s->X, (float*)s->R, s->n, s->off, s->n_act);
         else PHB_LAUNCH(k_poison_nonfinite<double>, grid, 256, 0, st, s->sys, (int)s->batch, (double*)s->X, (double*)s->R, s->n, s->off, s->n_act);
