@@ -68,11 +68,11 @@ sys.exit(rc)
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'tests', 'commit', 'math')), reason="the reference's test files are not on this machine")
 def test_the_references_own_tests_pass_on_bridged_matrices(tmp_path):
-    """The same files (+ test__nd.py, test_extrapolation.py) with the tracer bridge switched ON whenever PhiML's default backend is torch — what a CUDA
+    """The reference's whole tests/commit/math directory (+ backend/test__backend.py) with the tracer bridge switched ON whenever PhiML's default backend is torch — what a CUDA
     machine does — and the CSR arrays coming from the oracle instead of the device assembler (no GPU here): every matrix_from_function /
     jit_compile_linear matrix the reference's tests build under torch is then a bridged CompressedSparseMatrix, and their expectations must still hold."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    files = [os.path.join(REF, 'tests', 'commit', f) for f in FILES[:4] + ['math/test__nd.py', 'math/test_extrapolation.py']]
+    files = [os.path.join(REF, 'tests', 'commit', 'math'), os.path.join(REF, 'tests', 'commit', 'backend', 'test__backend.py')]      # 400 tests
     code = BRIDGED_RUNNER % dict(ref=REF, root=root, tmp=str(tmp_path), files=files)
     r = subprocess.run([sys.executable, '-c', code], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
     tail = '\n'.join((r.stdout + r.stderr).splitlines()[-15:])
