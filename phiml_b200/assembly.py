@@ -210,6 +210,20 @@ def owner_of(values):
 STATS = {'device_assemblies': 0, 'general_assemblies': 0, 'fallbacks': 0}
 
 
+def _caller_target_backend():
+    """``matrix_from_function`` determines the backend its matrix is FOR from the tensor it traces (``target_backend = backend_for(*tensors)``,
+    phiml/math/_lin_trace.py:714) — NumPy-backed inputs are solved on the NumPy backend even while torch is the default one.  ``tracer_to_coo`` is not
+    told; read from the calling frame like ``auto_compress`` below (``None`` for any other caller)."""
+    import sys
+    try:
+        frame = sys._getframe(2)
+        if frame.f_code.co_name == 'matrix_from_function':
+            return frame.f_locals.get('target_backend')
+    except ValueError:
+        pass
+    return None
+
+
 def _caller_wants_compressed() -> bool:
     """``matrix_from_function(..., auto_compress=False)`` — the default of the public function — returns the coordinate form (SparseCoordinateTensor,
     phiml/math/_lin_trace.py:680,743); only ``auto_compress=True`` (``jit_compile_linear`` / ``solve_linear``, phiml/math/_functional.py:436) asks for the
@@ -226,12 +240,16 @@ def _caller_wants_compressed() -> bool:
 
 
 def make_tracer_to_coo(original: Callable, eligible: Callable[[], bool], assemble: Callable = cuda_assemble, assemble_general: Callable = cuda_assemble_general):
-    """Wrapper for ``phiml.math._lin_trace.tracer_to_coo``.  ``eligible()`` says whether the matrix is wanted on the CUDA torch backend
-    right now (the wrapped function is not told the target backend); ``assemble`` is injectable so that the CPU tests can check the
+    """Wrapper for ``phiml.math._lin_trace.tracer_to_coo``.  ``eligible([target_backend])`` says whether the matrix is wanted on the CUDA torch backend
+    right now (the wrapped function is not told the target backend: it is read from ``matrix_from_function``'s frame and handed over when ``eligible`` takes an argument); ``assemble`` is injectable so that the CPU tests can check the
     PhiML-side structure against the reference's own matrix with arrays from the oracle."""
+    import inspect
+    takes_backend = len(inspect.signature(eligible).parameters) >= 1
+
     def tracer_to_coo(tracer, sparsify, separate_independent):
         info = None
-        if eligible() and _caller_wants_compressed():
+        wanted = eligible(_caller_target_backend()) if takes_backend else eligible()
+        if wanted and _caller_wants_compressed():
             info = analyse_tracer(tracer, sparsify, separate_independent)
         if info is not None:
             if info['general']:

@@ -280,10 +280,13 @@ def install():
     from . import assembly
     original_t2c = lin_trace.tracer_to_coo
 
-    def wants_device_matrix() -> bool:
+    def wants_device_matrix(target_backend=None) -> bool:
+        # the backend the matrix is FOR is the one of the traced tensor (matrix_from_function: target_backend = backend_for(*tensors), _lin_trace.py:714):
+        # NumPy-backed x0 / y are solved on the NumPy backend even while torch is the default backend, and need the reference's NumPy-backed matrix
         from phiml.backend import default_backend
-        return (default_backend() is TORCH and torch.cuda.is_available() and str(TORCH.get_default_device().device_type).upper() == 'GPU'
-                and torch._C._get_tracing_state() is None)
+        if not (torch.cuda.is_available() and str(TORCH.get_default_device().device_type).upper() == 'GPU' and torch._C._get_tracing_state() is None):
+            return False
+        return (target_backend is TORCH) if target_backend is not None else (default_backend() is TORCH)
 
     def assemble(grid, offsets, coeffs, dtype):
         return assembly.cuda_assemble(grid, offsets, coeffs, dtype, TORCH.get_default_device().ref)

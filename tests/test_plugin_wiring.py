@@ -473,3 +473,52 @@ def test_bridged_matrix_behaves_like_the_reference_matrix_under_phimls_operation
             assert ok >= 33, ok
     finally:
         lt.tracer_to_coo = bridged
+
+
+def test_numpy_backed_inputs_keep_the_references_numpy_matrix(phiml_env):
+    """The backend a matrix is FOR is the one of the traced tensor (matrix_from_function: target_backend = backend_for(*tensors), _lin_trace.py:714): with
+    torch as the default backend but NumPy-backed y / x0 (math.wrap(ndarray)), the reference solves on its NumPy backend with a NumPy-backed matrix — a
+    bridged (torch-backed) matrix would reach NUMPY.linear_solve as a torch sparse tensor.  The bridge follows the traced tensor: NumPy-backed inputs are
+    left to the reference, torch-backed ones are bridged; both give the reference's results for Φ-ML and SciPy methods."""
+    import torch
+    from phiml import math
+    from phiml.math import spatial, batch, extrapolation, Solve, SolveTape
+    from phiml.backend import default_backend
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly
+    from oracle.assemble import stencil_csr
+    TORCH = phiml_env[1]
+
+    def neg_laplace(x): return -math.laplace(x, padding=extrapolation.ZERO)
+
+    def oracle_assemble(grid, offsets, coeffs, dtype):
+        csr = stencil_csr(grid, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    bridged = lt.tracer_to_coo
+    original = phiml_env[0]._INSTALLED['original_t2c']
+    # the plug-in's own rule (phiml_plugin.wants_device_matrix) with "a CUDA device is present" taken for granted
+    rule = lambda tb=None: (tb is TORCH) if tb is not None else (default_backend() is TORCH)
+    try:
+        for kind, make in (('numpy-backed', math.wrap), ('torch-backed', math.tensor)):
+            res = {}
+            for name, t2c in (('reference', original), ('bridge', assembly.make_tracer_to_coo(original, rule, oracle_assemble, None))):
+                lt.tracer_to_coo = t2c
+                assembly.STATS.update(device_assemblies=0, general_assemblies=0, fallbacks=0)
+                f = math.jit_compile_linear(lambda x: neg_laplace(x))
+                with TORCH, math.precision(64):
+                    y = make(np.random.default_rng(0).standard_normal((2, 8, 6)), batch('b'), spatial('x,y'))
+                    x0 = make(np.zeros((8, 6)), spatial('x,y'))
+                    for method in ('CG', 'auto', 'biCG-stab(2)', 'scipy-direct'):
+                        solve = Solve(method, 1e-9, 0, x0=x0, max_iterations=500)
+                        with SolveTape() as tape:
+                            x = math.solve_linear(f, y, solve)
+                        res[(name, method)] = (x.numpy('b,x,y'), tape[solve].method)
+                if name == 'bridge':
+                    assert assembly.STATS['device_assemblies'] == (1 if kind == 'torch-backed' else 0), (kind, assembly.STATS)
+            for method in ('CG', 'auto', 'biCG-stab(2)', 'scipy-direct'):
+                (a, ma), (b, mb) = res[('reference', method)], res[('bridge', method)]
+                assert ma == mb and np.allclose(a, b, rtol=1e-7, atol=1e-9), (kind, method, ma, mb)
+                assert ('numpy' in ma) == (kind == 'numpy-backed') or method == 'scipy-direct' or 'PyTorch' in ma, (kind, method, ma)
+    finally:
+        lt.tracer_to_coo = bridged
