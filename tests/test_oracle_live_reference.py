@@ -88,3 +88,131 @@ def test_random_solves_agree_with_the_imported_reference(seed):
     scale = max(float(np.abs(np.where(ok, rx, 0)).max()), 1e-30)
     assert float(np.abs(np.where(ok, mine.x - rx, 0)).max()) <= (1e-12 if dt == np.float64 else 1e-5) * scale
     assert mine.method == ref.method
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_random_operators_through_the_tracer_bridge_equal_the_references_matrix(seed):
+    """Random linear functions — sums of shifted copies of x (offsets up to +-2 along random axes, ZERO / PERIODIC / ZERO_GRADIENT padding) with scalar or
+    per-cell coefficients — traced by the imported reference: the matrix the bridge builds from the tracer (phiml_b200.assembly.analyse_tracer + the
+    oracle's assembly here, the device assembler on a GPU, pinned to the oracle byte for byte by the GPU suite) must equal tracer_to_coo + compress_rows:
+    same type, dims, int32 pointers / indices, values, rank.  Operators the bridge does not take (it falls back) are counted, not failed."""
+    import torch
+    NUMPY, math = reference_backend()
+    from phiml.math import spatial, extrapolation
+    from phiml.math._lin_trace import matrix_from_function
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly
+    from oracle.assemble import stencil_csr, shift_values_csr
+    rng = np.random.default_rng(500 + seed)
+    rank = int(rng.integers(1, 4))
+    names = 'xyz'[:rank]
+    grid = {d: int(rng.integers(4, 8)) for d in names}
+    pad = [extrapolation.ZERO, extrapolation.PERIODIC, extrapolation.ZERO_GRADIENT][seed % 3]
+    n_terms = int(rng.integers(2, 6))
+    terms = []
+    for _ in range(n_terms):
+        d = names[int(rng.integers(0, rank))]
+        off = int(rng.choice([-2, -1, 1, 2]))
+        coef = float(rng.uniform(-1, 1))
+        field = rng.uniform(0.5, 1.5, tuple(grid.values())) if rng.random() < 0.35 else None
+        terms.append((d, off, coef, field))
+    diag = float(rng.uniform(2, 4))
+
+    def f(x):
+        out = diag * x
+        for d, off, coef, field in terms:
+            shifted = math.shift(x, (off,), dims=d, padding=pad, stack_dim=None)[0]
+            c = coef if field is None else math.wrap(field * coef, spatial(','.join(names)))
+            out = out + c * shifted
+        return out
+
+    def oracle_assemble(g, offsets, coeffs, dtype):
+        csr = stencil_csr(g, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    def oracle_assemble_general(g, offsets, values, dtype):
+        csr = shift_values_csr(g, offsets, values)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    original = lt.tracer_to_coo if not hasattr(lt.tracer_to_coo, '__wrapped_by_phb200__') else lt.tracer_to_coo
+    from phiml_b200 import phiml_plugin
+    if phiml_plugin._INSTALLED:
+        original = phiml_plugin._INSTALLED['original_t2c']
+    saved = lt.tracer_to_coo
+    try:
+        with math.precision(64 if seed % 2 else 32):
+            x0 = math.zeros(spatial(**grid))
+            lt.tracer_to_coo = original
+            try:
+                ref, ref_bias = matrix_from_function(f, x0, auto_compress=True)
+            except AssertionError as exc:       # e.g. an offset of 2 wrapping onto itself on a 4-cell periodic axis: the reference cannot compress repeated entries
+                pytest.skip(f"the reference does not build this operator: {str(exc)[:80]}")
+            assembly.STATS.update(device_assemblies=0, general_assemblies=0, fallbacks=0)
+            lt.tracer_to_coo = assembly.make_tracer_to_coo(original, lambda: True, oracle_assemble, oracle_assemble_general)
+            mine, mine_bias = matrix_from_function(f, x0, auto_compress=True)
+    finally:
+        lt.tracer_to_coo = saved
+    taken = assembly.STATS['device_assemblies'] + assembly.STATS['general_assemblies']
+    assert taken + assembly.STATS['fallbacks'] == 1
+    assert type(mine) is type(ref) and mine.shape == ref.shape
+    if type(ref).__name__ == 'CompressedSparseMatrix':
+        for name, dim in (('_indices', 'sp_entries'), ('_pointers', 'pointers'), ('_values', 'sp_entries')):
+            a, b = np.asarray(getattr(mine, name).native(dim)), getattr(ref, name).numpy(dim)
+            assert a.dtype == b.dtype and np.array_equal(a, b), (name, pad, terms)
+        rank_of = lambda m: np.asarray(m._matrix_rank.numpy(m._matrix_rank.shape.names)) if hasattr(m._matrix_rank, 'numpy') else np.asarray(m._matrix_rank)
+        assert np.array_equal(rank_of(mine), rank_of(ref))
+    # what the matrix does, whichever way it was built
+    probe = math.wrap(rng.standard_normal(tuple(grid.values())), spatial(','.join(names)))
+    order = ','.join(names)
+    assert np.allclose((mine @ probe).numpy(order), (ref @ probe).numpy(order), rtol=1e-5, atol=1e-5)
+    assert np.allclose((mine @ probe).numpy(order), f(probe).numpy(order), rtol=1e-4, atol=1e-4)
+    _TAKEN.append(taken)
+
+
+_TAKEN = []
+
+
+def test_the_bridge_took_most_random_operators():
+    if not _TAKEN:
+        pytest.skip("runs after the random-operator cases")
+    print(f"the bridge took {sum(_TAKEN)} of {len(_TAKEN)} random operators")
+    assert sum(_TAKEN) >= len(_TAKEN) * 0.6, f"the bridge took {sum(_TAKEN)} of {len(_TAKEN)} random operators"
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_random_ilu_sweeps_agree_with_the_imported_reference(seed):
+    """incomplete_lu_coo (phiml/backend/_linalg.py:524-594) on random sparse patterns with a full diagonal — structurally unsymmetric, random sweep counts,
+    `safe` on and off — against the oracle's sweeps: same entries in the same order, values to rounding; and the triangular solves of the factors against
+    the reference's NumPy backend (SciPy spsolve_triangular)."""
+    from oracle import precond
+    NUMPY, math = reference_backend()
+    from phiml.backend._linalg import incomplete_lu_coo
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(5, 40))
+    dt = np.float64 if seed % 2 else np.float32
+    a = sp.random(n, n, density=float(rng.uniform(0.05, 0.3)), random_state=np.random.RandomState(seed), format='lil')
+    a.setdiag(0)
+    a = a.tocsr()
+    a = (a + sp.diags(np.asarray(abs(a).sum(axis=1)).ravel() + rng.uniform(0.5, 2.0, n))).tocsr().astype(dt)
+    a.sort_indices()
+    if sp.tril(a, -1).nnz == 0 or sp.triu(a, 1).nnz == 0:
+        pytest.skip("triangular input: the reference has a branch of its own (upper) or raises (lower); pinned in tests/golden/ilu_edges.npz")
+    sweeps, safe = int(rng.integers(1, 9)), bool(seed % 3 == 0)
+    coo = a.tocoo()
+    idx = np.stack([coo.row, coo.col], -1)[None].astype(np.int64)
+    with math.precision(64 if dt == np.float64 else 32), np.errstate(all='ignore'):
+        (li, lv), (ui, uv) = incomplete_lu_coo(idx, coo.data[None, :, None], a.shape, sweeps, safe)
+    L, U = precond.ilu_fixed_point(a, sweeps, safe)
+    tol = 1e-12 if dt == np.float64 else 2e-5
+    for mine, i, v in ((L, np.asarray(li)[0], np.asarray(lv)[0, :, 0]), (U, np.asarray(ui)[0], np.asarray(uv)[0, :, 0])):
+        ref = sp.csr_matrix((v, (i[:, 0], i[:, 1])), shape=a.shape)
+        assert (abs(mine - ref) > tol * max(1.0, abs(ref).max())).nnz == 0
+        pat_m = sp.csr_matrix((np.ones(mine.nnz), mine.indices, mine.indptr), shape=a.shape)
+        pat_r = sp.csr_matrix((np.ones(len(v)), (i[:, 0], i[:, 1])), shape=a.shape)
+        assert (pat_m != pat_r).nnz == 0
+    rhs = rng.standard_normal((2, n)).astype(dt)
+    with np.errstate(all='ignore'):
+        ref_l = NUMPY.solve_triangular_sparse(L.astype(np.float64), rhs.astype(np.float64), True, True)
+        ref_u = NUMPY.solve_triangular_sparse(U.astype(np.float64), rhs.astype(np.float64), False, False)
+    assert np.allclose(precond.sptrsv(L.astype(np.float64), rhs.astype(np.float64), True, True), ref_l, rtol=1e-10, atol=1e-10)
+    assert np.allclose(precond.sptrsv(U.astype(np.float64), rhs.astype(np.float64), False, False), ref_u, rtol=1e-9, atol=1e-9)
