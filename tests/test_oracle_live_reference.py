@@ -216,3 +216,72 @@ def test_random_ilu_sweeps_agree_with_the_imported_reference(seed):
         ref_u = NUMPY.solve_triangular_sparse(U.astype(np.float64), rhs.astype(np.float64), False, False)
     assert np.allclose(precond.sptrsv(L.astype(np.float64), rhs.astype(np.float64), True, True), ref_l, rtol=1e-10, atol=1e-10)
     assert np.allclose(precond.sptrsv(U.astype(np.float64), rhs.astype(np.float64), False, False), ref_u, rtol=1e-9, atol=1e-9)
+
+
+def test_exotic_linear_functions_through_the_bridge_behave_like_the_reference():
+    """Operators outside the plain stencils: biharmonic, grad-div, different paddings per axis and per side, non-zero constant extrapolation and affine
+    functions (bias), upwind shifts, slicing + padding, per-cell factors, 1-D and 4-D grids, down-sampling, identity / zero functions, and functions the
+    reference's tracer itself rejects.  With the bridge switched on every one gives the reference's matrix type, the same `M @ x + bias`, and raises
+    where the reference raises; what the bridge cannot express falls back to the reference's own assembly."""
+    import torch
+    NUMPY, math = reference_backend()
+    from phiml.math import spatial, channel, extrapolation as E_
+    from phiml.math._lin_trace import matrix_from_function
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly, phiml_plugin
+    from oracle.assemble import stencil_csr, shift_values_csr
+
+    def oa(g, offsets, coeffs, dtype):
+        csr = stencil_csr(g, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    def oag(g, offsets, values, dtype):
+        csr = shift_values_csr(g, offsets, values)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    ops = {
+        'biharmonic': (lambda x: math.laplace(math.laplace(x, padding=E_.ZERO), padding=E_.ZERO), dict(x=7, y=6)),
+        'grad_div': (lambda x: math.sum(math.spatial_gradient(math.sum(math.spatial_gradient(x, padding=E_.ZERO, stack_dim=channel('g')), 'g'), padding=E_.ZERO, stack_dim=channel('h')), 'h'), dict(x=6, y=5)),
+        'mixed_axes': (lambda x: -math.laplace(x, padding=E_.combine_sides(x=E_.PERIODIC, y=E_.ZERO_GRADIENT)) + x, dict(x=6, y=5)),
+        'sides_differ': (lambda x: -math.laplace(x, padding=E_.combine_sides(x=(E_.ZERO, E_.ZERO_GRADIENT), y=E_.PERIODIC)) + x, dict(x=6, y=5)),
+        'one_extrapolation': (lambda x: -math.laplace(x, padding=E_.ONE) + x, dict(x=6, y=5)),
+        'constant_3': (lambda x: -math.laplace(x, padding=E_.ConstantExtrapolation(3.0)) + x, dict(x=6, y=5)),
+        'symmetric': (lambda x: -math.laplace(x, padding=E_.SYMMETRIC) + x, dict(x=6, y=5)),
+        'upwind': (lambda x: x - 0.3 * (x - math.shift(x, (-1,), dims='x', padding=E_.ZERO, stack_dim=None)[0]), dict(x=6, y=5)),
+        'affine': (lambda x: -math.laplace(x, padding=E_.ZERO) + 1.5, dict(x=6, y=5)),
+        'slice_pad': (lambda x: math.pad(x[{'x': slice(1, None)}], {'x': (0, 1)}, E_.ZERO) - x, dict(x=6, y=5)),
+        'mean_removed': (lambda x: x - math.mean(x, 'x,y'), dict(x=5, y=4)),
+        'per_cell_factor': (lambda x: x * math.wrap(np.arange(20.).reshape(5, 4), spatial('x,y')), dict(x=5, y=4)),
+        'one_d': (lambda x: -math.laplace(x, padding=E_.ZERO), dict(x=9)),
+        'four_d': (lambda x: -math.laplace(x, padding=E_.ZERO), dict(x=3, y=4, z=3, w=3)),
+        'downsample': (lambda x: x[{'x': slice(0, None, 2)}], dict(x=6, y=5)),
+        'identity': (lambda x: x, dict(x=6, y=5)),
+        'zero_fn': (lambda x: 0 * x, dict(x=6, y=5)),
+    }
+    original = phiml_plugin._INSTALLED['original_t2c'] if phiml_plugin._INSTALLED else lt.tracer_to_coo
+    saved = lt.tracer_to_coo
+    bridge = assembly.make_tracer_to_coo(original, lambda: True, oa, oag)
+    took = 0
+    try:
+        for name, (f, shape) in ops.items():
+            out = []
+            for t2c in (original, bridge):
+                lt.tracer_to_coo = t2c
+                assembly.STATS.update(device_assemblies=0, general_assemblies=0, fallbacks=0)
+                try:
+                    with math.precision(64):
+                        x0 = math.zeros(spatial(**shape))
+                        m, bias = matrix_from_function(f, x0, auto_compress=True)
+                        probe = math.wrap(np.random.default_rng(1).standard_normal(tuple(shape.values())), spatial(','.join(shape)))
+                        y = m @ probe + bias
+                        out.append(('ok', type(m).__name__, np.asarray(y.numpy(y.shape.names))))
+                except Exception as exc:
+                    out.append(('raised', type(exc).__name__, None))
+            (s0, t0, a), (s1, t1, b) = out
+            assert (s0, t0) == (s1, t1), f"{name}: the reference {s0} {t0}, with the bridge {s1} {t1}"
+            if s0 == 'ok':
+                assert a.shape == b.shape and np.allclose(a, b, rtol=1e-12, atol=1e-12), name
+            took += assembly.STATS['device_assemblies'] + assembly.STATS['general_assemblies']
+    finally:
+        lt.tracer_to_coo = saved
+    assert took >= 9, took
