@@ -522,3 +522,63 @@ def test_numpy_backed_inputs_keep_the_references_numpy_matrix(phiml_env):
                 assert ('numpy' in ma) == (kind == 'numpy-backed') or method == 'scipy-direct' or 'PyTorch' in ma, (kind, method, ma)
     finally:
         lt.tracer_to_coo = bridged
+
+
+def test_batch_and_channel_dimensions_on_x0_through_the_bridge(phiml_env):
+    """solve_linear with batch / channel dimensions on x0 or y, and functions whose trace the reference rejects (batched coefficients, channel mixing):
+    with the bridge on, the same x and iteration counts as with the reference's own assembly, and the same exceptions."""
+    import torch
+    from phiml import math
+    from phiml.math import spatial, batch, channel, extrapolation as E_, Solve, SolveTape
+    from phiml.backend import default_backend
+    import phiml.math._lin_trace as lt
+    from phiml_b200 import assembly
+    from oracle.assemble import stencil_csr, shift_values_csr
+    TORCH = phiml_env[1]
+
+    def oa(g, offsets, coeffs, dtype):
+        csr = stencil_csr(g, list(zip(offsets, coeffs)), dtype.type)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    def oag(g, offsets, values, dtype):
+        csr = shift_values_csr(g, offsets, values)
+        return torch.as_tensor(csr.indptr), torch.as_tensor(csr.indices), torch.as_tensor(csr.data)
+
+    k = math.tensor(np.array([1.0, 2.0]), batch('k'))
+    lap = lambda: (lambda x: -math.laplace(x, padding=E_.ZERO) + 0.1 * x)
+    cases = {
+        'batched_x0': (lap, lambda: math.zeros(batch(b=2), spatial(x=6, y=5)), lambda r: math.tensor(r.standard_normal((2, 6, 5)), batch('b'), spatial('x,y')), 'ok'),
+        'channel_x0': (lap, lambda: math.zeros(spatial(x=6, y=5), channel(c=2)), lambda r: math.tensor(r.standard_normal((6, 5, 2)), spatial('x,y'), channel('c')), 'ok'),
+        'y_batch_only': (lap, lambda: math.zeros(spatial(x=6, y=5)), lambda r: math.tensor(r.standard_normal((3, 6, 5)), batch('b'), spatial('x,y')), 'ok'),
+        'batched_coefficient': (lambda: (lambda x: -math.laplace(x, padding=E_.ZERO) + k * x), lambda: math.zeros(spatial(x=6, y=5)), lambda r: math.tensor(r.standard_normal((6, 5)), spatial('x,y')), 'raised'),
+        'channel_mixing': (lambda: (lambda x: -math.laplace(x, padding=E_.ZERO) + math.sum(x, 'c')), lambda: math.zeros(spatial(x=6, y=5), channel(c=2)), lambda r: math.tensor(r.standard_normal((6, 5, 2)), spatial('x,y'), channel('c')), 'raised'),
+    }
+    bridged = lt.tracer_to_coo
+    original = phiml_env[0]._INSTALLED['original_t2c']
+    bridge = assembly.make_tracer_to_coo(original, lambda: default_backend() is TORCH, oa, oag)
+    try:
+        for name, (mkf, mkx0, mky, expect) in cases.items():
+            out = []
+            for t2c in (original, bridge):
+                lt.tracer_to_coo = t2c
+                assembly.STATS.update(device_assemblies=0, general_assemblies=0, fallbacks=0)
+                f = math.jit_compile_linear(mkf())
+                try:
+                    with TORCH, math.precision(64):
+                        x0, y = mkx0(), mky(np.random.default_rng(0))
+                        solve = Solve('CG', 1e-9, 0, x0=x0, max_iterations=500)
+                        with SolveTape() as tape:
+                            x = math.solve_linear(f, y, solve)
+                        its = tape[solve].iterations
+                        out.append(('ok', np.asarray(x.numpy(x.shape.names)), its.numpy(its.shape.names).tolist()))
+                except Exception as exc:
+                    out.append(('raised', type(exc).__name__, None))
+            (s0, a, i0), (s1, b, i1) = out
+            assert s0 == s1 == expect, (name, out)
+            if s0 == 'ok':
+                assert a.shape == b.shape and np.allclose(a, b, rtol=1e-8, atol=1e-9) and i0 == i1, name
+                assert assembly.STATS['device_assemblies'] == 1, (name, assembly.STATS)
+            else:
+                assert a == b, (name, a, b)
+    finally:
+        lt.tracer_to_coo = bridged
